@@ -1,0 +1,494 @@
+"""CPU oracle: a numpy/scipy restatement of the reference's uncertainty path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``contouring_uncertainty_b200`` imports this module; it is
+imported by ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` -- as the checker or the timed CPU arm, never as the product path.
+
+Parity status: the reference (ThierryJudge/contouring-uncertainty) ships no test that pins this
+path, so the oracle is pinned against outputs of the reference itself,
+executed in the build container by ``tests/golden/make_golden.py`` and committed as
+``tests/golden/*.npz`` (checked by ``tests/test_oracle_golden.py``).  Third-party arithmetic the
+reference calls and that is present in this image is called the same way here
+(``scipy.interpolate.splprep/splev``, ``scipy.ndimage.binary_fill_holes``, ``scipy.stats.entropy``);
+``skimage.draw.line`` is absent from the image and restated (``bresenham_line``) -- "parity
+unpinned" for that one function (it draws the <= ~80 px base line between landmarks 20 and 0).
+
+Every function cites the reference file:line it follows (paths relative to the reference root;
+``cu/`` = ``contour_uncertainty/``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+from scipy import interpolate
+from scipy.ndimage import binary_fill_holes
+import scipy.stats
+
+K_POINTS = 21
+
+# cu/data/config.py:110-130  (a real 21-point LV contour in a 256x256 frame)
+LV_EXAMPLE_SHAPE = np.array(
+    [[114., 205.], [105., 185.], [102., 167.], [102., 151.], [101., 134.], [98., 116.], [98., 100.],
+     [99., 83.], [100., 67.], [106., 51.], [123., 35.], [139., 40.], [153., 55.], [168., 74.],
+     [174., 92.], [179., 111.], [182., 128.], [184., 145.], [182., 163.], [179., 180.], [173., 200.]])
+
+
+# --------------------------------------------------------------------------------------------------
+# DSNT heads                                                  cu/task/regression/dsnt/utils.py
+# --------------------------------------------------------------------------------------------------
+def normalized_linspace(length: int, dtype=np.float64) -> np.ndarray:
+    """cu/task/regression/dsnt/utils.py:50-68 -- cell centres of a [-1, 1] grid."""
+    first = -(length - 1.0) / length
+    return (np.arange(length, dtype=dtype) * dtype(2.0 / length) + dtype(first)).astype(dtype)
+
+
+def flat_softmax(inp: np.ndarray) -> np.ndarray:
+    """cu/task/regression/dsnt/utils.py:71-77 -- softmax over the flattened H*W of each (n, k)."""
+    flat = inp.reshape(inp.shape[0], inp.shape[1], -1)
+    flat = flat - flat.max(-1, keepdims=True)
+    e = np.exp(flat)
+    return (e / e.sum(-1, keepdims=True)).reshape(inp.shape)
+
+
+def dsnt(heatmaps: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """cu/task/regression/dsnt/utils.py:7-47 -- expectation and central second moments.
+
+    X varies along columns (utils.py:9-10).  Two-pass like the reference: the variances are taken
+    about the computed mean.  Returns coords (N,K,2) [x, y], var (N,K,2), covar (N,K).
+    """
+    dt = heatmaps.dtype.type
+    w = heatmaps.shape[-1]
+    lin = normalized_linspace(w, dtype=dt)
+    X = np.broadcast_to(lin[None, :], (w, w))
+    Y = X.T
+    h = heatmaps
+    x = (h * X).sum((-2, -1))
+    y = (h * Y).sum((-2, -1))
+    coords = np.stack([x, y], -1)
+    xt = X[None, None] - x[..., None, None]
+    yt = Y[None, None] - y[..., None, None]
+    var_x = (h * xt * xt).sum((-2, -1))
+    var_y = (h * yt * yt).sum((-2, -1))
+    covar = (h * xt * yt).sum((-2, -1))
+    return coords, np.stack([var_x, var_y], -1), covar
+
+
+def normalized_to_pixel_coordinates(coords: np.ndarray, size: int) -> np.ndarray:
+    """cu/task/regression/dsnt/utils.py:95-105."""
+    return 0.5 * ((coords + 1) * size - 1)
+
+
+def dsnt_predict_on_batch(logits: np.ndarray, covar: bool = True, dtype=np.float64):
+    """cu/task/regression/dsnt/dsnt_al.py:118-131 + cu/task/regression/aleatoric.py:138-144.
+
+    logits (N,K,H,W) -> pixel mu (N,K,2), pixel Sigma (N,K,2,2).  ``dtype=np.float64`` is the tight
+    oracle (the reference runs the same formulas in fp32 torch).
+    """
+    logits = np.asarray(logits).astype(dtype)
+    size = logits.shape[2]
+    coords, var, cv = dsnt(flat_softmax(logits))
+    if not covar:
+        cv = np.zeros_like(cv)
+    mu = normalized_to_pixel_coordinates(coords, size)
+    pv = var * (size / 2) ** 2
+    pc = cv * (size / 2) ** 2
+    sigma = np.zeros(mu.shape[:2] + (2, 2), dtype=dtype)
+    sigma[..., 0, 0] = pv[..., 0]
+    sigma[..., 0, 1] = pc
+    sigma[..., 1, 0] = pc
+    sigma[..., 1, 1] = pv[..., 1]
+    return mu, sigma
+
+
+# --------------------------------------------------------------------------------------------------
+# Contour -> mask                        cu/utils/contour.py, cu/data/camus/utils.py
+# --------------------------------------------------------------------------------------------------
+def bresenham_line(r0, c0, r1, c1):
+    """``skimage.draw.line`` = skimage/draw/_draw.pyx::_line, restated (scikit-image is absent).
+
+    Call sites: cu/utils/contour.py:37,48.  Returns (rr, cc) integer arrays, end point included.
+    """
+    r0, c0, r1, c1 = int(r0), int(c0), int(r1), int(c1)
+    steep = False
+    r, c = r0, c0
+    dr, dc = abs(r1 - r0), abs(c1 - c0)
+    sc = 1 if (c1 - c) > 0 else -1
+    sr = 1 if (r1 - r) > 0 else -1
+    if dr > dc:
+        steep = True
+        c, r = r, c
+        dc, dr = dr, dc
+        sc, sr = sr, sc
+    d = 2 * dr - dc
+    n = max(dc, dr) + 1
+    rr = np.zeros(n, dtype=np.intp)
+    cc = np.zeros(n, dtype=np.intp)
+    for i in range(dc):
+        if steep:
+            rr[i], cc[i] = c, r
+        else:
+            rr[i], cc[i] = r, c
+        while d >= 0:
+            r += sr
+            d -= 2 * dc
+        c += sc
+        d += 2 * dr
+    rr[dc], cc[dc] = r1, c1
+    return rr, cc
+
+
+def contour_spline(mu: np.ndarray, n: int = 1001, close: bool = False) -> np.ndarray:
+    """cu/utils/contour.py:9-25 -- FITPACK interpolating cubic B-spline, bare-except fallback."""
+    try:
+        tck, _u = interpolate.splprep([mu[:, 0], mu[:, 1]], k=3, s=0)
+        unew = np.linspace(0, 1.0, n)
+        spline = np.array(interpolate.splev(unew, tck)).transpose()
+    except Exception:  # the reference uses a bare except (ValueError on a zero chord)
+        spline = mu
+    if close:
+        spline = np.concatenate((spline, spline[0][None]))
+    return spline
+
+
+def reconstruction(points: np.ndarray, height: int, width: int) -> np.ndarray:
+    """cu/utils/contour.py:28-40 -- spline raster + closing line + hole fill.
+
+    The reference's ``except`` around the pixel assignment only plots; the effect on the result is
+    that NOTHING of the spline is drawn when any index is < -height / -width (IndexError), while
+    indices in [-size, -1] wrap (numpy negative indexing) and indices > size-1 are clipped.
+    """
+    seg_map = np.zeros((height, width))
+    spline = contour_spline(points, n=1000).round().astype(int)
+    try:
+        seg_map[spline[:, 1].clip(max=height - 1), spline[:, 0].clip(max=width - 1)] = 1
+    except IndexError:
+        pass
+    points = points.round().astype(int)
+    rr, cc = bresenham_line(points[-1, 1], points[-1, 0], points[0, 1], points[0, 0])
+    seg_map[rr.clip(max=height - 1, min=0), cc.clip(max=width - 1, min=0)] = 1
+    return binary_fill_holes(seg_map).astype(int)
+
+
+def us_contour_to_mask(landmarks: np.ndarray, shape=(256, 256), apply_argmax: bool = True) -> np.ndarray:
+    """cu/data/camus/utils.py:31-98, LV-only branch (:43, :85-90): round landmarks first."""
+    landmarks = np.asarray(landmarks).round().astype(int).squeeze()
+    assert landmarks.ndim == 2 and landmarks.shape[1] == 2
+    seg_map = reconstruction(landmarks, shape[0], shape[1])
+    if not apply_argmax:
+        seg_map = seg_map[None]
+    return seg_map
+
+
+def convert_to_mask(contour_samples: np.ndarray, shape=(256, 256)) -> np.ndarray:
+    """cu/task/regression/contour_uncertainty.py:35-53 -- masks of every sample.
+
+    contour_samples (..., K, 2) -> uint8 masks (..., H, W).  (The reference stacks int64.)
+    """
+    lead = contour_samples.shape[:-2]
+    flat = contour_samples.reshape((-1,) + contour_samples.shape[-2:])
+    out = np.empty((flat.shape[0],) + tuple(shape), dtype=np.uint8)
+    for i in range(flat.shape[0]):
+        out[i] = us_contour_to_mask(flat[i], shape)
+    return out.reshape(lead + tuple(shape))
+
+
+def sample_entropy(samples: np.ndarray) -> np.ndarray:
+    """cu/task/uncertainty.py:107-133 for C == 1: binary entropy (base 2) of the sample mean.
+
+    samples (T, 1, H, W) or (T_e, T_a, 1, H, W) float.  Non-finite -> 0.
+    """
+    samples = np.asarray(samples, dtype=np.float64)
+    if samples.ndim == 5:
+        samples = samples.reshape((-1,) + samples.shape[2:])
+    y_hat = samples.mean(0)
+    assert samples.shape[1] == 1
+    y_hat = np.concatenate([y_hat, 1 - y_hat], axis=0)
+    umap = scipy.stats.entropy(y_hat, axis=0, base=2)
+    umap[~np.isfinite(umap)] = 0
+    return umap
+
+
+def maps_from_counts(count: np.ndarray, T: int):
+    """mean / entropy / pred from an exact integer count map.
+
+    mean = count/T (what ``samples.mean(0)`` gives for 0/1 doubles), entropy as ``sample_entropy``,
+    pred = ``mean.round()`` half-to-even (cu/task/regression/aleatoric.py:111).
+    """
+    p = count.astype(np.float64) / T
+    yh = np.stack([p, 1 - p], 0)
+    ent = scipy.stats.entropy(yh, axis=0, base=2)
+    ent[~np.isfinite(ent)] = 0
+    return p, ent, p.round().astype(np.int64)
+
+
+def lv_area(mask: np.ndarray, voxelarea: Optional[float] = None):
+    """cu/utils/clinical.py:92-93 -> vital/vital/utils/image/measure.py:21-40."""
+    v = 1 if voxelarea is None else voxelarea
+    return mask.astype(bool).sum((-2, -1)) * v
+
+
+def lv_fac(ed_mask: np.ndarray, es_mask: np.ndarray):
+    """cu/utils/clinical.py:11-29."""
+    ed, es = lv_area(ed_mask), lv_area(es_mask)
+    return (ed - es) / ed
+
+
+def aleatoric_epistemic_uncertainty(metric_mc: np.ndarray):
+    """cu/results/clinical/utils.py:3-18 (std with ddof=0 despite the 'var' names)."""
+    assert metric_mc.ndim == 2
+    means = np.nanmean(metric_mc, axis=-1)
+    stds = np.nanstd(metric_mc, axis=-1)
+    mean = np.nanmean(means)
+    epi = np.nanstd(means)
+    alea = np.nanmean(stds)
+    return mean, alea, epi, epi + alea
+
+
+# ---- own spline (documents the algorithm the CUDA rasteriser uses; validated against FITPACK) ----
+def chord_parameters(pts: np.ndarray) -> np.ndarray:
+    """FITPACK parcur.f: u_i = cumulative chord length / total, fp64, sequential sums."""
+    m = pts.shape[0]
+    u = np.zeros(m)
+    for i in range(1, m):
+        dist = 0.0
+        for j in range(pts.shape[1]):
+            d = float(pts[i, j]) - float(pts[i - 1, j])
+            dist += d * d
+        u[i] = u[i - 1] + math.sqrt(dist)
+    if u[m - 1] <= 0:
+        raise ValueError("zero total chord")
+    for i in range(1, m):
+        u[i] = u[i] / u[m - 1]
+        if u[i] <= u[i - 1]:
+            raise ValueError("Error on input data")  # FITPACK ier=10: u must be strictly increasing
+    u[m - 1] = 1.0
+    return u
+
+
+def _bspl_basis(t: np.ndarray, x: float, l: int) -> np.ndarray:
+    """FITPACK fpbspl.f for k=3: the 4 non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)."""
+    h = np.zeros(4)
+    hh = np.zeros(3)
+    h[0] = 1.0
+    for j in range(1, 4):
+        hh[:j] = h[:j]
+        h[0] = 0.0
+        for i in range(1, j + 1):
+            li = l + i
+            lj = li - j
+            f = hh[i - 1] / (t[li] - t[lj])
+            h[i - 1] = h[i - 1] + f * (t[li] - x)
+            h[i] = f * (x - t[lj])
+    return h
+
+
+def own_spline(points: np.ndarray, n: int = 1000) -> np.ndarray:
+    """Interpolating cubic B-spline by collocation (SURVEY.md section 9 'Spline recipe').
+
+    knots t = [0,0,0,0, u_2..u_{m-3}, 1,1,1,1]; 21x21 banded collocation solve; de Boor evaluation at
+    j/(n-1).  Agrees with splprep/splev to ~1e-13 (tests/test_oracle_golden.py); raises ValueError
+    when FITPACK would (zero chord), so callers take the reference's fallback.
+    """
+    pts = np.asarray(points, dtype=np.float64)
+    m = pts.shape[0]
+    u = chord_parameters(pts)
+    t = np.concatenate([np.zeros(4), u[2:m - 2], np.ones(4)])
+    nk = len(t)  # m + 4
+    A = np.zeros((m, m))
+    l = 3
+    for i in range(m):
+        while l < nk - 5 and u[i] >= t[l + 1]:
+            l += 1
+        A[i, l - 3:l + 1] = _bspl_basis(t, u[i], l)
+    c = np.linalg.solve(A, pts)
+    out = np.zeros((n, pts.shape[1]))
+    l = 3
+    for j in range(n):
+        x = j / (n - 1) if n > 1 else 0.0
+        while l < nk - 5 and x >= t[l + 1]:
+            l += 1
+        out[j] = _bspl_basis(t, x, l) @ c[l - 3:l + 1]
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Samplers                                                               cu/sampler/**
+# --------------------------------------------------------------------------------------------------
+def naive_colouring(cov: np.ndarray) -> np.ndarray:
+    """numpy ``RandomState.multivariate_normal`` colouring (cu/sampler/sampler.py:37).
+
+    x = z @ (sqrt(s)[:, None] * v) + mean with (u, s, v) = svd(cov).  Returns M (K,2,2) with
+    x = z @ M[k] (row-vector convention).
+    """
+    cov = np.asarray(cov, dtype=np.float64)
+    out = np.zeros_like(cov)
+    for k in range(cov.shape[0]):
+        _u, s, v = np.linalg.svd(cov[k])
+        out[k] = np.sqrt(s)[:, None] * v
+    return out
+
+
+def naive_sample(mu: np.ndarray, cov: np.ndarray, z: np.ndarray) -> np.ndarray:
+    """cu/sampler/naive.py:13-25 + cu/sampler/sampler.py:22-41 with the normal draws ``z`` fed in.
+
+    z (n, K, 2): z[:, k] are the n draws consumed for landmark k (the reference consumes them
+    landmark-major).  Returns (n, K, 2) float64.
+    """
+    M = naive_colouring(cov)
+    mu = np.asarray(mu, dtype=np.float64)
+    return np.einsum("nke,ked->nkd", np.asarray(z, dtype=np.float64), M) + mu[None]
+
+
+def get_points_order(nb_points: int = 21, nb_initial_points: int = 3, levels: Optional[int] = None):
+    """cu/sampler/posterior_shape_model/psm.py:43-71."""
+    initial_points = np.round(np.linspace(0, nb_points - 1, nb_initial_points)).astype(int).tolist()
+    levels = levels or int(math.log(nb_points, 2))
+    all_points, point_order = list(initial_points), []
+    for _ in range(levels):
+        level_points = []
+        for j in range(len(all_points) - 1):
+            if all_points[j] + 1 != all_points[j + 1]:
+                point = (all_points[j] + all_points[j + 1]) / 2
+                point = math.ceil(point) if point > nb_points / 2 else math.floor(point)
+                level_points.append(int(point))
+        if not level_points:
+            break
+        all_points.extend(level_points)
+        all_points.sort()
+        point_order.append(level_points)
+    return initial_points, point_order
+
+
+def index_to_flat(indices: Sequence[int]) -> List[int]:
+    """cu/sampler/posterior_shape_model/utils.py:4-24."""
+    out = []
+    for i in indices:
+        out.extend([2 * i, 2 * i + 1])
+    return out
+
+
+@dataclass
+class ShapeModel:
+    """The pickled dict of ``camus-cont_psm_11_no_std.npy`` (cu/sampler/.../psm.py:30-41)."""
+    mean: np.ndarray      # scaler_mean (P,)
+    scale: np.ndarray     # scaler_scale (P,)
+    X_train: np.ndarray   # (N, P)
+    initial_points: List[int]
+    points_order: List[List[int]]
+
+    @staticmethod
+    def load(path: str, levels: int = 3) -> "ShapeModel":
+        d = np.load(str(path), allow_pickle=True).item()
+        # the reference casts everything to torch.float (fp32) on load (psm.py:33-38)
+        f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+        p = np.asarray(d["mu"]).shape[0]
+        ini, order = get_points_order(p // 2, levels=levels)
+        return ShapeModel(f32(d["scaler_mean"]), f32(d["scaler_scale"]), f32(d["X_train"]), ini, order)
+
+
+def pca_cov(X_train: np.ndarray, mu_t: np.ndarray) -> np.ndarray:
+    """cu/sampler/posterior_shape_model/posteriorshapemodel.py:9-27: C = (X^T - mu)(X^T - mu)^T / N.
+
+    The reference then takes Q = U sqrt(|lambda|) (:29-41); every later use is through Q Q^T = C
+    and Q_g^T Q_g, so the oracle keeps C and uses the algebraically identical eig-free form
+    (probed against the verbatim code to its own fp32 noise).
+    """
+    diff = X_train.T - mu_t.reshape(-1, 1)
+    return diff @ diff.T / X_train.shape[0]
+
+
+def posterior_shape_model(s_t: np.ndarray, g: List[int], mu_t: np.ndarray, S: np.ndarray, sigma2: float):
+    """cu/sampler/posterior_shape_model/posteriorshapemodel.py:49-81 in eig-free form.
+
+    mu_c = mu + Q (Q_g^T Q_g + s2 I)^-1 Q_g^T (s_g - mu_g) = mu + S[:,g] (S[g,g] + s2 I)^-1 (s_g - mu_g)
+    cov_c = s2 Q (Q_g^T Q_g + s2 I)^-1 Q^T             = S - S[:,g] (S[g,g] + s2 I)^-1 S[g,:]
+    """
+    Sgg = S[np.ix_(g, g)] + sigma2 * np.eye(len(g))
+    M = np.linalg.solve(Sgg, S[g, :]).T  # (P, |g|)
+    mu_c = mu_t + M @ (s_t[g] - mu_t[g])
+    cov_c = S - M @ S[g, :]
+    return mu_c, cov_c
+
+
+def merge_priors(mu1, cov1, mu2, cov2):
+    """cu/sampler/posterior_shape_model/psm.py:424-440 -- product of Gaussians, batched over points."""
+    inv = np.linalg.inv(cov1 + cov2)
+    sigma_f = cov1 @ inv @ cov2
+    mu_f = (cov1 @ inv @ mu2[..., None] + cov2 @ inv @ mu1[..., None])[..., 0]
+    return mu_f, sigma_f
+
+
+def _chol2(c: np.ndarray) -> np.ndarray:
+    """Lower Cholesky factor of a 2x2 matrix reading only its lower triangle (torch.linalg.cholesky)."""
+    l00 = math.sqrt(c[0, 0])
+    l10 = c[1, 0] / l00
+    l11 = math.sqrt(c[1, 1] - l10 * l10)
+    return np.array([[l00, 0.0], [l10, l11]])
+
+
+def psm_sample(model: ShapeModel, mu: np.ndarray, cov: np.ndarray, z: np.ndarray) -> np.ndarray:
+    """cu/sampler/posterior_shape_model/psm.py:73-93 (``__call__``) + :199-384
+    (``sample_endo_contour``), alpha=None, in fp64, with the standard-normal draws fed in.
+
+    mu (K,2), cov (K,2,2), z (n, 17, 2): per sample the draws are consumed in the order
+    initial points [0,10,20], then each level's points (psm.py:239, :285); each draw d gives
+    ``mu_f + chol(cov_f) d`` (MultivariateNormal.rsample).  Returns (n, K, 2).
+    """
+    mu = np.asarray(mu, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64)
+    z = np.asarray(z, dtype=np.float64)
+    K = mu.shape[0]
+    mu_t = ((mu.reshape(-1) - model.mean) / model.scale)            # transform (psm.py:442-445)
+    S = pca_cov(model.X_train, mu_t)                                 # psm.py:91
+    sigmas = [1, 1, 1, 1]                                            # psm.py:225
+    out = np.zeros((z.shape[0], K, 2))
+    for n in range(z.shape[0]):
+        zi = 0
+        s = np.zeros((K, 2))
+        sampled = list(model.initial_points)
+        for j in model.initial_points:                               # psm.py:239 -> :413
+            s[j] = mu[j] + _chol2(cov[j]) @ z[n, zi]
+            zi += 1
+        for lvl, points in enumerate(model.points_order):
+            sampled.sort()
+            if len(sampled) == K:
+                break
+            s_t = (s.reshape(-1) - model.mean) / model.scale         # psm.py:265
+            mu_c, cov_c = posterior_shape_model(s_t, index_to_flat(sampled), mu_t, S, sigmas[lvl])
+            mu_c = (mu_c * model.scale + model.mean).reshape(K, 2)   # psm.py:269
+            cov_c = cov_c * model.scale[None, :]                     # psm.py:270 (scales columns)
+            cov_c = np.stack([cov_c[2 * i:2 * i + 2, 2 * i:2 * i + 2] for i in range(K)])
+            mu_f, cov_f = merge_priors(mu, cov, mu_c, cov_c)         # psm.py:275
+            for j in points:                                         # psm.py:278 -> :413
+                s[j] = mu_f[j] + _chol2(cov_f[j]) @ z[n, zi]
+                zi += 1
+            sampled.extend(points)
+        sampled.sort()
+        if len(sampled) != K:                                        # psm.py:355-368
+            s_t = (s.reshape(-1) - model.mean) / model.scale
+            mu_c, _ = posterior_shape_model(s_t, index_to_flat(sampled), mu_t, S, 0.001)
+            mu_c = (mu_c * model.scale + model.mean).reshape(K, 2)
+            rest = [i for i in range(K) if i not in sampled]
+            s[rest] = mu_c[rest]
+        out[n] = s
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# End-to-end hot path for one image (what bench.py's CPU arm times)
+# --------------------------------------------------------------------------------------------------
+def uncertainty_from_samples(contour_samples: np.ndarray, shape=(256, 256)):
+    """cu/task/regression/aleatoric.py:110-111 + cu/task/regression/contour_uncertainty.py:76-77.
+
+    contour_samples (T, K, 2) of ONE image -> dict(count, mean, entropy, pred, area).
+    """
+    masks = convert_to_mask(contour_samples, shape)                  # (T, H, W) uint8
+    T = masks.shape[0]
+    ent = sample_entropy(masks[:, None].astype(float))
+    mean = masks.astype(np.float64).mean(0)
+    pred = mean.round().astype(np.int64)
+    return dict(count=masks.sum(0, dtype=np.int64), mean=mean, entropy=ent, pred=pred,
+                area=lv_area(masks), T=T)

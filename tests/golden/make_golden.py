@@ -1,0 +1,162 @@
+"""Generate the golden vectors under tests/golden/ by EXECUTING THE REFERENCE.
+
+Run by hand in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference through ``_refstub`` (import stubs for absent plotting /
+training packages, a restated ``skimage.draw.line``), feeds it seeded inputs and recorded random
+draws and stores inputs + outputs as small ``.npz`` files.  The GPU box has no /root/reference:
+tests there compare the oracle (``oracle/port.py``) and the CUDA path against these files.
+
+Inputs that are large (heatmap logits) are NOT stored; ``synth.py`` regenerates them from the seed.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import _refstub  # noqa: E402
+
+_refstub.install()
+
+import torch  # noqa: E402
+
+import synth  # noqa: E402  (tests/synth.py: seeded synthetic inputs shared by tests / bench)
+
+PSM_PATH = os.path.join(_refstub.REFERENCE_ROOT, "camus-cont_psm_11_no_std.npy")
+
+
+def golden_dsnt():
+    """flat_softmax + dsnt + DSNTAleatoric.predict_on_batch on synthetic Gaussian-bump logits."""
+    from contour_uncertainty.task.regression.dsnt.utils import flat_softmax, dsnt
+    from contour_uncertainty.task.regression.dsnt.dsnt_al import DSNTAleatoric
+    from contour_uncertainty.task.regression.aleatoric import AleatoricUncertaintyTask
+
+    out = {}
+    for name, (n, seed, kind) in {"bumps": (3, 11, "bumps"), "noise": (2, 12, "noise"),
+                                  "bimodal": (2, 13, "bimodal")}.items():
+        logits = synth.heatmap_logits(n, seed=seed, kind=kind)
+        t = torch.from_numpy(logits)
+        coords, var, covar = dsnt(flat_softmax(t))
+        fake = SimpleNamespace(hparams=SimpleNamespace(covar=True), device="cpu")
+        fake.get_cov_matrix = lambda vx, vy, c=0, _f=fake: AleatoricUncertaintyTask.get_cov_matrix(_f, vx, vy, c)
+        px, sig = DSNTAleatoric.predict_on_batch(fake, t, lambda x: x)
+        out[f"{name}_n"] = n
+        out[f"{name}_seed"] = seed
+        out[f"{name}_coords"] = coords.numpy()
+        out[f"{name}_var"] = var.numpy()
+        out[f"{name}_covar"] = covar.numpy()
+        out[f"{name}_pixel_mu"] = px.numpy()
+        out[f"{name}_pixel_sigma"] = sig.numpy()
+    np.savez_compressed(os.path.join(HERE, "dsnt.npz"), **out)
+    print("dsnt.npz", {k: np.asarray(v).shape for k, v in out.items() if k.endswith("coords")})
+
+
+def golden_raster():
+    """USContourToMask / reconstruction on random + adversarial contours; bit-packed masks."""
+    from contour_uncertainty.data.camus.utils import USContourToMask
+    from contour_uncertainty.utils.contour import reconstruction
+
+    contours, tags = synth.raster_cases(seed=21, n_random=160)
+    masks = np.zeros((len(contours), 256, 256), dtype=np.uint8)
+    for i, c in enumerate(contours):
+        masks[i] = USContourToMask.__call__(c.astype(np.float32), (256, 256), labels=[], apply_argmax=True)
+    # the demo scripts call reconstruction() on UNROUNDED float contours (sampling_example3.py:127)
+    unr = np.zeros((32, 256, 256), dtype=np.uint8)
+    for i in range(32):
+        unr[i] = reconstruction(contours[i].astype(np.float64), 256, 256)
+    np.savez_compressed(os.path.join(HERE, "raster.npz"), contours=np.stack(contours).astype(np.float32),
+                        tags=np.array(tags), masks=np.packbits(masks, axis=-1, bitorder="little"),
+                        masks_unrounded=np.packbits(unr, axis=-1, bitorder="little"))
+    print("raster.npz", masks.shape, "areas", masks.sum((1, 2))[:8], "tags", sorted(set(tags)))
+
+
+def golden_psm():
+    """PosteriorShapeModelSampler.__call__ with replayed standard-normal draws (fp32 reference)."""
+    from contour_uncertainty.sampler.posterior_shape_model.psm import PosteriorShapeModelSampler
+
+    sampler = PosteriorShapeModelSampler(PSM_PATH)
+    rng = np.random.default_rng(31)
+    n_img, n_s = 4, 12
+    mus, covs = synth.point_distributions(n_img, seed=32)
+    z = rng.standard_normal((n_img, n_s, 17, 2)).astype(np.float32)
+    out = np.zeros((n_img, n_s, 21, 2), dtype=np.float32)
+    for i in range(n_img):
+        draws = [z[i, s, d][None] for s in range(n_s) for d in range(17)]
+        with _refstub.replay_standard_normal(draws) as log:
+            res = sampler(torch.from_numpy(mus[i]), torch.from_numpy(covs[i]), n=n_s)
+        assert len(log) == n_s * 17 and all(sh == (1, 2) for sh in log), log[:3]
+        out[i] = res.detach().numpy()
+    # The same UNMODIFIED reference code executed in fp64 (default dtype + members cast to double):
+    # removes the noise of its fp32 42x42 inverses (sigma2=1e-3 fill: up to ~3e-2 px) and is the
+    # tight anchor for the oracle (agreement ~1e-10 px).
+    torch.set_default_dtype(torch.float64)
+    try:
+        s64 = PosteriorShapeModelSampler(PSM_PATH)
+        for a in ("mean", "scale", "X_train", "X_val", "mu", "Q"):
+            setattr(s64, a, getattr(s64, a).double())
+        out64 = np.zeros((n_img, n_s, 21, 2), dtype=np.float64)
+        for i in range(n_img):
+            draws = [z[i, s, d][None].astype(np.float64) for s in range(n_s) for d in range(17)]
+            with _refstub.replay_standard_normal(draws):
+                res = s64(torch.from_numpy(mus[i]).double(), torch.from_numpy(covs[i]).double(), n=n_s)
+            assert res.dtype == torch.float64
+            out64[i] = res.detach().numpy()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    print("psm fp32-vs-fp64 reference max diff (px)", np.abs(out64 - out).max())
+    np.savez_compressed(os.path.join(HERE, "psm.npz"), mu=mus, cov=covs, z=z, samples=out, samples_f64=out64,
+                        initial_points=np.array(sampler.initial_points),
+                        order=np.array(sum(sampler.points_order, [])))
+    print("psm.npz", out.shape, "max |s-mu|", np.abs(out - mus[:, None]).max())
+
+
+def golden_naive():
+    """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
+    from contour_uncertainty.sampler.naive import NaiveSampler
+
+    mus, covs = synth.point_distributions(2, seed=41)
+    n_s = 16
+    outs, zs = [], []
+    for i in range(2):
+        np.random.seed(410 + i)
+        outs.append(NaiveSampler()(mus[i], covs[i], n_s))
+        rs = np.random.RandomState(410 + i)
+        zs.append(np.stack([rs.standard_normal((n_s, 2)) for _ in range(21)], 1))  # (n, K, 2)
+    np.savez_compressed(os.path.join(HERE, "naive.npz"), mu=mus, cov=covs, z=np.stack(zs),
+                        samples=np.stack(outs))
+    print("naive.npz", np.stack(outs).shape, np.stack(outs).dtype)
+
+
+def golden_maps():
+    """samples -> masks -> mean / pred / sample_entropy / lv_area, as _predict_step + predict_step do."""
+    from contour_uncertainty.data.camus.utils import USContourToMask
+    from contour_uncertainty.task.uncertainty import UncertaintyTask
+    from contour_uncertainty.utils.clinical import lv_area
+
+    g = np.load(os.path.join(HERE, "psm.npz"))
+    samples = g["samples"]  # (4, 12, 21, 2)
+    n, T = samples.shape[:2]
+    pred_samples = np.array([USContourToMask.__call__(samples[i, k], (256, 256), labels=[], apply_argmax=False)
+                             for i in range(n) for k in range(T)]).reshape(n, 1, T, 1, 256, 256)
+    pred = pred_samples.mean(axis=(1, 2)).squeeze().round().astype(int)  # aleatoric.py:111
+    ent = np.array([UncertaintyTask.sample_entropy(pred_samples[i].astype(float)) for i in range(n)])
+    area = np.array([[lv_area(pred_samples[i, 0, k, 0]) for k in range(T)] for i in range(n)])
+    np.savez_compressed(os.path.join(HERE, "maps.npz"), count=pred_samples.sum((1, 2, 3)).astype(np.int32),
+                        pred=pred.astype(np.uint8), entropy=ent, area=area.astype(np.int64),
+                        mean=pred_samples.astype(float).mean(axis=(1, 2)).squeeze())
+    print("maps.npz", ent.shape, ent.dtype, "entropy max", ent.max(), "areas", area[0, :4])
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps"]
+    for w in which:
+        globals()["golden_" + w]()

@@ -1,0 +1,105 @@
+"""Seeded synthetic inputs shared by the golden generator and the tests (numpy, CPU, deterministic).
+
+Shapes follow SURVEY.md section 8(d): K = 21 landmarks, 256x256 frames, landmark means around the
+reference's ``LV_example_shape`` (contour_uncertainty/data/config.py:110-130).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+K = 21
+H = W = 256
+
+LV_EXAMPLE_SHAPE = np.array(
+    [[114., 205.], [105., 185.], [102., 167.], [102., 151.], [101., 134.], [98., 116.], [98., 100.],
+     [99., 83.], [100., 67.], [106., 51.], [123., 35.], [139., 40.], [153., 55.], [168., 74.],
+     [174., 92.], [179., 111.], [182., 128.], [184., 145.], [182., 163.], [179., 180.], [173., 200.]])
+
+
+def random_spd(rng, n, lo=4.0, hi=36.0):
+    """n random 2x2 SPD matrices R(theta) diag(l1, l2) R(theta)^T, l ~ U[lo, hi] px^2."""
+    th = rng.uniform(0, np.pi, n)
+    l1, l2 = rng.uniform(lo, hi, n), rng.uniform(lo, hi, n)
+    c, s = np.cos(th), np.sin(th)
+    out = np.zeros((n, 2, 2))
+    out[:, 0, 0] = c * c * l1 + s * s * l2
+    out[:, 0, 1] = out[:, 1, 0] = c * s * (l1 - l2)
+    out[:, 1, 1] = s * s * l1 + c * c * l2
+    return out
+
+
+def point_distributions(n_img, seed):
+    """(mu (n,K,2) fp32, cov (n,K,2,2) fp32): LV example shape + shift/jitter, random SPD covariances."""
+    rng = np.random.default_rng(seed)
+    mu = LV_EXAMPLE_SHAPE[None] + rng.normal(0, 4.0, (n_img, 1, 2)) + rng.normal(0, 1.5, (n_img, K, 2))
+    cov = random_spd(rng, n_img * K).reshape(n_img, K, 2, 2)
+    return mu.astype(np.float32), cov.astype(np.float32)
+
+
+def heatmap_logits(n_img, seed, kind="bumps"):
+    """(n_img, K, 256, 256) fp32 logits whose softmax is ~N(mu_ik, Sigma_ik) per landmark.
+
+    kind: 'bumps'   logit = -1/2 d^T Sigma^-1 d + 0.05 N(0,1)           
+          'noise'   a weak bump (x0.05) under N(0,1) logit noise          (broad, noisy heatmap)
+          'bimodal' two equal bumps 30-60 px apart                        (re-centring stress)
+    """
+    rng = np.random.default_rng(seed)
+    mu, cov = point_distributions(n_img, seed + 1000)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = np.empty((n_img, K, H, W), dtype=np.float32)
+    for i in range(n_img):
+        for k in range(K):
+            P = np.linalg.inv(cov[i, k].astype(np.float64))
+
+            def bump(m):
+                dx, dy = xx - m[0], yy - m[1]
+                return -0.5 * (P[0, 0] * dx * dx + 2 * P[0, 1] * dx * dy + P[1, 1] * dy * dy)
+
+            if kind == "bumps":
+                l = bump(mu[i, k]) + 0.05 * rng.standard_normal((H, W))
+            elif kind == "noise":
+                l = 0.05 * bump(mu[i, k]) + rng.standard_normal((H, W))
+            elif kind == "bimodal":
+                off = rng.uniform(30, 60) * np.array([np.cos(k), np.sin(k)])
+                l = np.logaddexp(bump(mu[i, k]), bump(mu[i, k] + off)) + 0.05 * rng.standard_normal((H, W))
+            else:
+                raise ValueError(kind)
+            out[i, k] = l.astype(np.float32)
+    return out
+
+
+def raster_cases(seed, n_random=160):
+    """Contours (K,2) float64 exercising the reference's rasterisation rules.
+
+    tags: 'example', 'random' (sigma 3 px), 'wild' (sigma 12 px: self-intersections), 'dup'
+    (duplicate consecutive rounded landmarks -> splprep ValueError -> 21 isolated pixels, no
+    spline), 'right'/'bottom' (clipped at 255), 'left'/'top' (negative indices wrap), 'far'
+    (index < -256: IndexError -> spline not drawn), 'half' (x.5 ties, round-half-even), 'tiny'.
+    """
+    rng = np.random.default_rng(seed)
+    base = LV_EXAMPLE_SHAPE
+    cases, tags = [base.copy()], ["example"]
+    for _ in range(n_random):
+        cases.append(base + rng.normal(0, 3.0, (K, 2)) + rng.normal(0, 5.0, (1, 2)))
+        tags.append("random")
+    for _ in range(24):
+        cases.append(base + rng.normal(0, 12.0, (K, 2)))
+        tags.append("wild")
+    for j in (0, 7, 19):
+        c = base + rng.normal(0, 2.0, (K, 2))
+        c[j + 1] = c[j] + 0.2
+        cases.append(c)
+        tags.append("dup")
+    for dx, dy, t in ((90, 0, "right"), (0, 70, "bottom"), (-110, 0, "left"), (0, -60, "top"),
+                      (-300, 0, "far"), (0, -340, "far"), (-200, -30, "left"), (75, 52, "right")):
+        cases.append(base + np.array([dx, dy]) + rng.normal(0, 2.0, (K, 2)))
+        tags.append(t)
+    for _ in range(6):
+        c = np.round(base + rng.normal(0, 3.0, (K, 2))) + 0.5
+        cases.append(c)
+        tags.append("half")
+    ctr = base.mean(0)
+    for s in (0.02, 0.1, 0.3):
+        cases.append(ctr + (base - ctr) * s)
+        tags.append("tiny")
+    return cases, tags

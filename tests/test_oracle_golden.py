@@ -1,0 +1,106 @@
+"""Pin the oracle (oracle/port.py) against outputs of the reference itself (tests/golden/*.npz,
+made by tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import port
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _unpack(a):
+    return np.unpackbits(a, axis=-1, bitorder="little")
+
+
+@pytest.mark.parametrize("name", ["bumps", "noise", "bimodal"])
+def test_dsnt_matches_reference(name):
+    g = np.load(os.path.join(G, "dsnt.npz"))
+    logits = synth.heatmap_logits(int(g[f"{name}_n"]), seed=int(g[f"{name}_seed"]), kind=name)
+    coords, var, covar = port.dsnt(port.flat_softmax(logits.astype(np.float64)))
+    # the reference runs in fp32 torch: its own error vs fp64 truth is ~1.5e-6 rel
+    np.testing.assert_allclose(coords, g[f"{name}_coords"], rtol=0, atol=6e-6)  # fp32 sum of 65536 terms
+    np.testing.assert_allclose(var, g[f"{name}_var"], rtol=2e-5, atol=1e-9)
+    scale = np.sqrt(var[..., 0] * var[..., 1])
+    assert np.max(np.abs(covar - g[f"{name}_covar"]) / scale) < 2e-5
+    mu, sig = port.dsnt_predict_on_batch(logits)
+    np.testing.assert_allclose(mu, g[f"{name}_pixel_mu"], rtol=0, atol=8e-4)  # 128 x the coords bound
+    np.testing.assert_allclose(sig, g[f"{name}_pixel_sigma"], rtol=2e-5, atol=2e-4)
+
+
+def test_raster_bit_exact():
+    g = np.load(os.path.join(G, "raster.npz"))
+    contours, masks = g["contours"], _unpack(g["masks"])
+    bad = []
+    for i, c in enumerate(contours):
+        m = port.us_contour_to_mask(c)
+        if not np.array_equal(m, masks[i]):
+            bad.append((i, str(g["tags"][i])))
+    assert not bad, bad
+    unr = _unpack(g["masks_unrounded"])
+    for i in range(unr.shape[0]):
+        assert np.array_equal(port.reconstruction(contours[i].astype(np.float64), 256, 256), unr[i])
+
+
+def test_own_spline_matches_fitpack():
+    """The collocation spline the CUDA kernel implements == splprep/splev to ~1e-12, same pixels."""
+    g = np.load(os.path.join(G, "raster.npz"))
+    worst = 0.0
+    for i, c in enumerate(g["contours"][:120]):
+        pts = c.round().astype(int).astype(np.float64)
+        try:
+            own = port.own_spline(pts, 1000)
+        except ValueError:
+            assert str(g["tags"][i]) in ("dup", "tiny"), g["tags"][i]
+            continue
+        ref = port.contour_spline(pts, n=1000)
+        worst = max(worst, np.abs(own - ref).max())
+        assert np.array_equal(own.round().astype(int), ref.round().astype(int)), i
+    assert worst < 1e-10, worst
+
+
+def test_psm_sampler_matches_reference():
+    g = np.load(os.path.join(G, "psm.npz"))
+    model = port.ShapeModel.load(os.path.join(os.path.dirname(G), "..", "contouring_uncertainty_b200", "data",
+                                              "camus-cont_psm_11_no_std.npy"))
+    assert model.initial_points == list(g["initial_points"])
+    assert sum(model.points_order, []) == list(g["order"])
+    for i in range(g["mu"].shape[0]):
+        s = port.psm_sample(model, g["mu"][i], g["cov"][i], g["z"][i])
+        # tight anchor: the reference's own code executed in fp64 (make_golden.py)
+        assert np.abs(s - g["samples_f64"][i]).max() < 1e-8
+        # loose anchor: the verbatim fp32 reference, whose ill-conditioned fp32 42x42 inverses
+        # (sigma2 = 1e-3 fill of points 4, 9, 11, 16) carry up to ~3.4e-2 px of its own noise
+        assert np.abs(s - g["samples"][i]).max() < 6e-2
+        sampled = [k for k in range(21) if k not in (4, 9, 11, 16)]
+        assert np.abs(s[:, sampled] - g["samples"][i][:, sampled]).max() < 6e-3
+
+
+def test_naive_sampler_matches_reference():
+    g = np.load(os.path.join(G, "naive.npz"))
+    for i in range(g["mu"].shape[0]):
+        s = port.naive_sample(g["mu"][i], g["cov"][i], g["z"][i])
+        np.testing.assert_allclose(s, g["samples"][i], rtol=0, atol=1e-9)
+
+
+def test_maps_match_reference():
+    g = np.load(os.path.join(G, "maps.npz"))
+    p = np.load(os.path.join(G, "psm.npz"))
+    for i in range(p["samples"].shape[0]):
+        r = port.uncertainty_from_samples(p["samples"][i])
+        assert np.array_equal(r["count"], g["count"][i])
+        assert np.array_equal(r["pred"], g["pred"][i])
+        assert np.array_equal(r["area"], g["area"][i])
+        np.testing.assert_allclose(r["entropy"], g["entropy"][i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r["mean"], g["mean"][i], rtol=0, atol=1e-15)
+        m, e, pr = port.maps_from_counts(r["count"], r["T"])
+        np.testing.assert_allclose(e, g["entropy"][i], rtol=0, atol=1e-12)
+        assert np.array_equal(pr, g["pred"][i])
+
+
+def test_points_order():
+    ini, order = port.get_points_order(21, levels=3)
+    assert ini == [0, 10, 20]
+    assert order == [[5, 15], [2, 7, 13, 18], [1, 3, 6, 8, 12, 14, 17, 19]]
