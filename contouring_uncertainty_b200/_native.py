@@ -1,0 +1,85 @@
+"""ctypes binding of libcub200.so (the C ABI declared in include/cub200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.  The
+library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcub200.so")
+
+EINVAL, ECUDA = -1, -2
+
+_lib: Optional[C.CDLL] = None
+
+_vp, _i32, _i64, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+
+# name -> argtypes; every function returns int except the three queries
+SIGNATURES = {
+    "cub200_dsnt_moments": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "cub200_psm_factor": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "cub200_naive_factor": [_vp, _i64, _vp, _vp],
+    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
+    "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],
+}
+QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm")
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU / PyTorch fallback for this path.")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        l.cub200_last_error.restype = C.c_char_p
+        l.cub200_last_error.argtypes = []
+        l.cub200_abi_version.restype = C.c_int
+        l.cub200_built_for_sm.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc == EINVAL:
+        raise ValueError(f"{what}: invalid argument (shape / null pointer / unsupported size)")
+    msg = lib().cub200_last_error().decode()
+    raise NativeError(f"{what}: CUDA error: {msg}")
+
+
+def require_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device: this path has no CPU implementation")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()

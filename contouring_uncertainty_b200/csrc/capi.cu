@@ -1,0 +1,24 @@
+// Error plumbing + version queries of the C ABI (include/cub200.h).
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace cub200 {
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* what, cudaError_t e) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error(what, e);
+        return CUB200_ECUDA;
+    }
+    return 0;
+}
+}  // namespace cub200
+
+extern "C" const char* cub200_last_error(void) { return cub200::g_err; }
+extern "C" int cub200_abi_version(void) { return 1; }
+extern "C" int cub200_built_for_sm(void) { return 100; }

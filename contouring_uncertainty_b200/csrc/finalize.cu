@@ -1,0 +1,117 @@
+// K4  finalize_maps: difference map -> count -> mean / binary entropy / pred, plus FAC from areas.
+//
+// Replaces  pred = pred_samples.mean((1,2)).round()   contour_uncertainty/task/regression/aleatoric.py:111
+//           UncertaintyTask.sample_entropy            contour_uncertainty/task/uncertainty.py:107-133
+//           lv_FAC / FAC.compute per-sample part      contour_uncertainty/utils/clinical.py:11-29,
+//                                                     contour_uncertainty/results/clinical/view.py:35-78
+// The maps are functions of exact integer counts, so the entropy is a (T+1)-entry fp64 table.
+// HBM-bound streaming kernel: one warp per row, 8 columns per lane, warp prefix sum.
+#include "common.cuh"
+
+namespace cub200 {
+
+// scipy.stats.entropy([p, 1-p], base=2): pk /= sum(pk); S = sum(entr(pk)) / log(2); non-finite -> 0
+__global__ void entropy_lut_kernel(double* __restrict__ lut, int64_t T) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > T) return;
+    const double p = (double)c / (double)T;
+    const double q = 1.0 - p;
+    const double s = p + q;
+    const double pn = p / s, qn = q / s;
+    const double ep = pn > 0.0 ? -pn * log(pn) : 0.0;
+    const double eq = qn > 0.0 ? -qn * log(qn) : 0.0;
+    double e = (ep + eq) / log(2.0);
+    if (!isfinite(e)) e = 0.0;
+    lut[c] = e;
+}
+
+__global__ void __launch_bounds__(256)
+finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T, int32_t* __restrict__ count_out,
+                     double* __restrict__ mean_out, double* __restrict__ entropy_out, uint8_t* __restrict__ pred_out,
+                     const double* __restrict__ lut) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int4* d4 = reinterpret_cast<const int4*>(diff + row * 256) + 2 * lane;
+    const int4 a = d4[0], b = d4[1];
+    int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 1; j < 8; ++j) c[j] += c[j - 1];
+    int incl = c[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int excl = incl - c[7];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] += excl;
+    const int64_t base = row * 256 + 8 * lane;
+    if (count_out) {
+        int4* o = reinterpret_cast<int4*>(count_out + base);
+        o[0] = make_int4(c[0], c[1], c[2], c[3]);
+        o[1] = make_int4(c[4], c[5], c[6], c[7]);
+    }
+    const double dT = (double)T;
+    if (mean_out) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2)
+            reinterpret_cast<double2*>(mean_out + base)[j >> 1] = make_double2((double)c[j] / dT, (double)c[j + 1] / dT);
+    }
+    if (entropy_out) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const int c0 = min(max(c[j], 0), (int)T), c1 = min(max(c[j + 1], 0), (int)T);
+            reinterpret_cast<double2*>(entropy_out + base)[j >> 1] = make_double2(lut[c0], lut[c1]);
+        }
+    }
+    if (pred_out) {
+        // round-half-even(count / T): 1 iff count/T > 0.5 (exactly 0.5 rounds to 0)
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            lo |= (uint32_t)(2 * (int64_t)c[j] > T) << (8 * j);
+            hi |= (uint32_t)(2 * (int64_t)c[j + 4] > T) << (8 * j);
+        }
+        reinterpret_cast<uint2*>(pred_out + base)[0] = make_uint2(lo, hi);
+    }
+}
+
+__global__ void fac_kernel(const int32_t* __restrict__ ed, const int32_t* __restrict__ es, int64_t n, double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = (double)ed[i], b = (double)es[i];
+    double f = (a - b) / a;                              // clinical.py:29
+    if (!(f >= 0.0 && f <= 1.0)) f = nan("");            // view.py: samples outside [0, 1] are rejected
+    out[i] = f;
+}
+
+}  // namespace cub200
+
+extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
+                                    double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,
+                                    void* stream) {
+    using namespace cub200;
+    if (!diff || n_img < 0 || n_samples < 1 || n_samples > 0x3fffffff) return CUB200_EINVAL;
+    if (entropy_out && !lut_ws) return CUB200_EINVAL;
+    if (n_img == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (entropy_out) {
+        entropy_lut_kernel<<<(unsigned)((n_samples + 1 + 255) / 256), 256, 0, st>>>(lut_ws, n_samples);
+        int rc = check_launch("entropy_lut_kernel");
+        if (rc) return rc;
+    }
+    const int64_t rows = n_img * 256;
+    finalize_maps_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(diff, rows, n_samples, count_out, mean_out,
+                                                                    entropy_out, pred_out, lut_ws);
+    return check_launch("finalize_maps_kernel");
+}
+
+extern "C" int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_t n, double* fac_out,
+                                     void* stream) {
+    using namespace cub200;
+    if (!area_ed || !area_es || !fac_out || n < 0) return CUB200_EINVAL;
+    if (n == 0) return 0;
+    fac_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(area_ed, area_es, n, fac_out);
+    return check_launch("fac_kernel");
+}

@@ -1,0 +1,507 @@
+// K3  sample_raster_aggregate: Monte-Carlo contour sampler -> spline rasteriser -> background
+// flood -> streaming aggregation, ONE WARP PER SAMPLE, masks never leave shared memory.
+//
+// Replaces (reference paths, cu/ = contour_uncertainty/):
+//   AleatoricUncertaintyTask.sample            cu/task/regression/aleatoric.py:54-78
+//   ContourUncertaintyTask.convert_to_mask     cu/task/regression/contour_uncertainty.py:26-57
+//   USContourToMask.__call__ (LV branch)       cu/data/camus/utils.py:31-98
+//   reconstruction / contour_spline            cu/utils/contour.py:9-40
+//   lv_area                                    cu/utils/clinical.py:92-93
+//
+// The mask rule is NOT point-in-polygon.  Per sample:
+//   1. contour = mu + A z (z replayed from memory or Philox4x32-10 + Box-Muller), lane k = landmark k
+//   2. landmarks -> round half-even -> int                         (camus/utils.py:43)
+//   3. interpolating cubic B-spline of FITPACK splprep(k=3, s=0): chord-length parameter, knots at
+//      u_2..u_{m-3} == the not-a-knot cubic spline through (u_i, p_i); solved in fp64 as a
+//      tridiagonal system for the second derivatives and evaluated piecewise (Horner) at
+//      u = j/999, j = 0..999; zero chord -> FITPACK raises -> the reference's bare except draws
+//      the 21 raw points instead                                   (contour.py:9-25)
+//   4. np.round half-even -> int; index clip(max=255) only: [-256,-1] wraps, < -256 raises and
+//      NOTHING of the spline is drawn                              (contour.py:30-35)
+//   5. Bresenham closing line landmark 20 -> 0 (skimage.draw.line), clipped to the frame (:36-38)
+//   6. scipy.ndimage.binary_fill_holes == complement of the 4-connected background reachable from
+//      outside the frame                                           (:39)
+//   7. area = popcount; every run boundary of every mask row becomes a +1 / -1 red.global into the
+//      image's difference map (the row prefix sum of which is the per-pixel count).
+//
+// Shared memory per warp: the 256x256 boundary bitmap (8 rows per lane, padded band stride 68
+// words so the 128-bit band loads are bank-conflict free) + ~2 KB of spline scratch.
+#include "common.cuh"
+
+namespace cub200 {
+
+constexpr int FW_WARPS = 8;
+constexpr int FW_THREADS = FW_WARPS * 32;
+constexpr int BAND_STRIDE = 68;                 // 8 rows x 8 words + 4 pad words
+constexpr int BMP_WORDS = 32 * BAND_STRIDE;     // 2176
+constexpr int NPTS = 1000;                      // contour_spline(points, n=1000)   contour.py:30
+constexpr int KP = CUB200_K;                    // 21
+constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px behave as +-8192
+
+struct __align__(16) WarpScratch {
+    uint32_t bmp[BMP_WORDS];
+    double u[24];          // chord parameters u_0..u_20
+    double coef[20][8];    // piece i on [u_i, u_{i+1}]: x c0..c3, y c0..c3 (powers of u - u_i)
+    double sub[24], dia[24], sup[24], rx[24], ry[24];
+    double mx[24], my[24];
+    float z[CUB200_ZMAX + 2];
+};
+
+// ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// ---------------------------------------------------------------- bitmap helpers
+__device__ __forceinline__ int bmp_addr(int row, int word) { return row * 8 + word + (row >> 3) * 4; }
+
+__device__ __forceinline__ void set_pixel(uint32_t* bmp, int row, int col) {
+    atomicOr(&bmp[bmp_addr(row, col >> 5)], 1u << (col & 31));
+}
+
+// Fill complete runs of F that contain a seed (seeds subset of F).  256-bit rows as 8 words,
+// bit b of word w = column 32w + b.  Add-with-carry trick, once upward and once on the
+// bit-reversed row (rare path: only rows where the flood actually advances vertically).
+__device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8]) {
+    uint32_t X[8];
+    // upward: X = F + r
+    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(F[0]), "r"(r[0]));
+#pragma unroll
+    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(F[w]), "r"(r[w]));
+    uint32_t up[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) up[w] = (F[w] & ~X[w]) | r[w];
+    // downward: same on reversed bits (word w <-> 7-w, brev)
+    uint32_t Fr[8], rr[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { Fr[w] = __brev(F[7 - w]); rr[w] = __brev(r[7 - w]); }
+    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(Fr[0]), "r"(rr[0]));
+#pragma unroll
+    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(Fr[w]), "r"(rr[w]));
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t dn = Fr[7 - w] & ~X[7 - w];
+        r[w] = up[w] | __brev(dn);
+    }
+}
+
+// ---------------------------------------------------------------- one sample, one warp
+// Lane k < 21 holds landmark k as (fx, fy).  Returns the mask area; accumulates run boundaries
+// into diff_img (may be null) and stores the packed mask (may be null).
+__device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_landmarks,
+                             int32_t* __restrict__ diff_img, uint32_t* __restrict__ mask_out) {
+    const int lane = lane_id();
+    uint32_t* bmp = ws.bmp;
+
+    // zero the boundary bitmap (uint4 stores)
+    {
+        uint4* b4 = reinterpret_cast<uint4*>(bmp);
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < BMP_WORDS / 4 / 32; ++i) b4[lane + 32 * i] = zero;
+    }
+
+    // 2. rounded landmarks (closing line always uses them; the spline too when round_landmarks)
+    fx = fminf(fmaxf(fx, -(float)COORD_CLAMP), (float)COORD_CLAMP);
+    fy = fminf(fmaxf(fy, -(float)COORD_CLAMP), (float)COORD_CLAMP);
+    const int rix = (int)rintf(fx), riy = (int)rintf(fy);
+    const double X = round_landmarks ? (double)rix : (double)fx;
+    const double Y = round_landmarks ? (double)riy : (double)fy;
+
+    // 3a. chord-length parameter (FITPACK parcur)
+    const double Xp = __shfl_up_sync(FULL, X, 1), Yp = __shfl_up_sync(FULL, Y, 1);
+    double dch = 0.0;
+    if (lane >= 1 && lane < KP) dch = sqrt((X - Xp) * (X - Xp) + (Y - Yp) * (Y - Yp));
+    double cum = dch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(FULL, cum, o);
+        if (lane >= o) cum += t;
+    }
+    const double total = __shfl_sync(FULL, cum, KP - 1);
+    double u = (lane == KP - 1) ? 1.0 : cum / total;
+    if (lane == 0) u = 0.0;
+    const double uprev = __shfl_up_sync(FULL, u, 1);
+    // FITPACK rejects non-increasing parameters (zero chord) -> ValueError -> raw points drawn
+    const bool bad = __any_sync(FULL, lane >= 1 && lane < KP && !(u > uprev)) || !(total > 0.0);
+    __syncwarp();
+
+    bool oob = false;
+    if (!bad) {
+        // 3b. not-a-knot cubic spline: tridiagonal system for the second derivatives M_1..M_19
+        const double unext = __shfl_down_sync(FULL, u, 1);
+        const double Xn = __shfl_down_sync(FULL, X, 1), Yn = __shfl_down_sync(FULL, Y, 1);
+        const double h = unext - u;                         // h_k, k < 20
+        const double ih = 1.0 / h;
+        const double dxk = (Xn - X) * ih, dyk = (Yn - Y) * ih;  // divided differences delta_k
+        const double hm = __shfl_up_sync(FULL, h, 1);
+        const double dxm = __shfl_up_sync(FULL, dxk, 1), dym = __shfl_up_sync(FULL, dyk, 1);
+        if (lane < KP) ws.u[lane] = u;
+        if (lane >= 1 && lane <= KP - 2) {
+            double a = hm, b = 2.0 * (hm + h), c = h;
+            double r1 = 6.0 * (dxk - dxm), r2 = 6.0 * (dyk - dym);
+            if (lane == 1) {                                 // M_0 eliminated (not-a-knot at u_1)
+                const double f = h / (hm + h);
+                a = 0.0; b = hm + 2.0 * h; c = h - hm; r1 *= f; r2 *= f;
+            } else if (lane == KP - 2) {                     // M_20 eliminated (not-a-knot at u_19)
+                const double f = hm / (hm + h);
+                a = hm - h; b = h + 2.0 * hm; c = 0.0; r1 *= f; r2 *= f;
+            }
+            ws.sub[lane] = a; ws.dia[lane] = b; ws.sup[lane] = c; ws.rx[lane] = r1; ws.ry[lane] = r2;
+        }
+        __syncwarp();
+        if (lane < 2) {                                      // Thomas: lane 0 -> x, lane 1 -> y
+            double* r = lane ? ws.ry : ws.rx;
+            double* m = lane ? ws.my : ws.mx;
+            double bp = ws.dia[1];
+            double ivp = 1.0 / bp;
+            double rp = r[1];
+            double* inv = m;                                 // pivots' reciprocals live in m[] until overwritten
+            inv[1] = ivp;
+            for (int i = 2; i <= KP - 2; ++i) {
+                const double w = ws.sub[i] * ivp;
+                bp = ws.dia[i] - w * ws.sup[i - 1];
+                rp = r[i] - w * rp;
+                r[i] = rp;
+                ivp = 1.0 / bp;
+                inv[i] = ivp;
+            }
+            double mi = rp * ivp;
+            m[KP - 2] = mi;
+            for (int i = KP - 3; i >= 1; --i) {
+                mi = (r[i] - ws.sup[i] * mi) * inv[i];
+                m[i] = mi;
+            }
+            const double h0 = ws.u[1] - ws.u[0], h1 = ws.u[2] - ws.u[1];
+            m[0] = m[1] - (h0 / h1) * (m[2] - m[1]);
+            const double hl = ws.u[KP - 1] - ws.u[KP - 2], hl1 = ws.u[KP - 2] - ws.u[KP - 3];
+            m[KP - 1] = m[KP - 2] + (hl / hl1) * (m[KP - 2] - m[KP - 3]);
+        }
+        __syncwarp();
+        if (lane < KP - 1) {                                 // piece coefficients
+            const double m0x = ws.mx[lane], m1x = ws.mx[lane + 1];
+            const double m0y = ws.my[lane], m1y = ws.my[lane + 1];
+            double* c = ws.coef[lane];
+            c[0] = X; c[1] = dxk - h * (2.0 * m0x + m1x) * (1.0 / 6.0); c[2] = 0.5 * m0x; c[3] = (m1x - m0x) * ih * (1.0 / 6.0);
+            c[4] = Y; c[5] = dyk - h * (2.0 * m0y + m1y) * (1.0 / 6.0); c[6] = 0.5 * m0y; c[7] = (m1y - m0y) * ih * (1.0 / 6.0);
+        }
+        __syncwarp();
+
+        // 3c/4. evaluate 1000 points (32 consecutive per lane), round, apply the index rules
+        uint32_t pix[32];
+        const int j0 = lane * 32;
+        const double step = 1.0 / (double)(NPTS - 1);       // np.linspace(0, 1, 1000)
+        int piece = 0;
+        {
+            const double us = (double)j0 * step;
+#pragma unroll
+            for (int k = 1; k <= KP - 2; ++k) piece = (us >= ws.u[k]) ? k : piece;
+        }
+        double ub = ws.u[piece], un = ws.u[piece + 1];
+        double c0 = ws.coef[piece][0], c1 = ws.coef[piece][1], c2 = ws.coef[piece][2], c3 = ws.coef[piece][3];
+        double e0 = ws.coef[piece][4], e1 = ws.coef[piece][5], e2 = ws.coef[piece][6], e3 = ws.coef[piece][7];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + jj;
+            const double uj = (j == NPTS - 1) ? 1.0 : (double)j * step;
+            while (piece < KP - 2 && uj >= un) {
+                ++piece;
+                ub = un; un = ws.u[piece + 1];
+                c0 = ws.coef[piece][0]; c1 = ws.coef[piece][1]; c2 = ws.coef[piece][2]; c3 = ws.coef[piece][3];
+                e0 = ws.coef[piece][4]; e1 = ws.coef[piece][5]; e2 = ws.coef[piece][6]; e3 = ws.coef[piece][7];
+            }
+            const double s = uj - ub;
+            const double xv = fma(fma(fma(c3, s, c2), s, c1), s, c0);
+            const double yv = fma(fma(fma(e3, s, e2), s, e1), s, e0);
+            int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
+            if (j < NPTS) {
+                oob |= (ix < -256) | (iy < -256);
+                ix += (ix < 0) ? 256 : 0;                    // numpy negative index wrap
+                iy += (iy < 0) ? 256 : 0;
+                pix[jj] = ((uint32_t)(iy & 255) << 8) | (uint32_t)(ix & 255);
+            } else {
+                pix[jj] = 0xffffffffu;
+            }
+        }
+        oob = __any_sync(FULL, oob);
+        __syncwarp();                                        // bitmap zeroing visible
+        if (!oob) {
+            uint32_t cur = 0xffffffffu, bits = 0;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+                const uint32_t p = pix[jj];
+                if (p != 0xffffffffu) {
+                    const uint32_t cell = p >> 5;            // row * 8 + word
+                    const uint32_t bit = 1u << (p & 31);
+                    if (cell != cur) {
+                        if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+                        cur = cell; bits = 0;
+                    }
+                    bits |= bit;
+                }
+            }
+            if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+        }
+    } else {
+        // fallback of contour_spline(): spline = the 21 raw points (already ints when rounded)
+        int ix = 0, iy = 0;
+        if (lane < KP) {
+            ix = min(__double2int_rn(X), 255); iy = min(__double2int_rn(Y), 255);
+            oob = (ix < -256) | (iy < -256);
+            ix += (ix < 0) ? 256 : 0;
+            iy += (iy < 0) ? 256 : 0;
+        }
+        oob = __any_sync(FULL, oob);
+        __syncwarp();
+        if (!oob && lane < KP) set_pixel(bmp, iy & 255, ix & 255);
+    }
+
+    // 5. closing line (r0,c0) = landmark 20 -> (r1,c1) = landmark 0, skimage.draw.line closed form:
+    //    pixel i < dmaj: major = m0 + i*smaj, minor = n0 + smin * floor((2*dmin*i + dmaj) / (2*dmaj));
+    //    pixel dmaj = (r1, c1).
+    {
+        const int r0 = __shfl_sync(FULL, riy, KP - 1), c0 = __shfl_sync(FULL, rix, KP - 1);
+        const int r1 = __shfl_sync(FULL, riy, 0), c1 = __shfl_sync(FULL, rix, 0);
+        const int dr = abs(r1 - r0), dc = abs(c1 - c0);
+        const int sc = (c1 - c0) > 0 ? 1 : -1, sr = (r1 - r0) > 0 ? 1 : -1;
+        const bool steep = dr > dc;
+        const int dmaj = steep ? dr : dc, dmin = steep ? dc : dr;
+        for (int i = lane; i <= dmaj; i += 32) {
+            int rr, cc;
+            if (i == dmaj) { rr = r1; cc = c1; }
+            else {
+                const int nmin = (2 * dmin * i + dmaj) / (2 * dmaj);
+                if (steep) { rr = r0 + i * sr; cc = c0 + nmin * sc; }
+                else { cc = c0 + i * sc; rr = r0 + nmin * sr; }
+            }
+            rr = min(max(rr, 0), 255); cc = min(max(cc, 0), 255);
+            set_pixel(bmp, rr, cc);
+        }
+    }
+    __syncwarp();
+
+    // 6. background flood.  Lane owns rows 8*lane .. 8*lane+7; R = reached-from-outside.
+    uint32_t R[8][8];
+    const uint4* band4 = reinterpret_cast<const uint4*>(bmp + lane * BAND_STRIDE);
+    // 6a. rows are seeded from the left and right frame borders: everything left of the first and
+    //     right of the last boundary pixel of the row; rows 0 and 255 are seeded everywhere.
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
+        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const bool border_row = (lane == 0 && i == 0) || (lane == 31 && i == 7);
+        bool seen = false;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t low = (B[w] & (0u - B[w])) - 1u;      // bits below the lowest set bit (all if 0)
+            R[i][w] = seen ? 0u : low;
+            seen |= (B[w] != 0u);
+        }
+        seen = false;
+#pragma unroll
+        for (int w = 7; w >= 0; --w) {
+            const uint32_t high = B[w] ? ~(0xffffffffu >> __clz(B[w])) : 0xffffffffu;  // above the highest set bit
+            R[i][w] |= seen ? 0u : high;
+            seen |= (B[w] != 0u);
+        }
+        if (border_row) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) R[i][w] = ~B[w];
+        }
+    }
+    // 6b. vertical propagation to a fixed point (Gauss-Seidel sweeps inside the band, neighbours'
+    //     edge rows by shuffle).  Typical convex-ish contours exit after one quiescent pass.
+    for (;;) {
+        bool changed = false;
+        uint32_t upn[8], dnn[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            upn[w] = __shfl_up_sync(FULL, R[7][w], 1);
+            dnn[w] = __shfl_down_sync(FULL, R[0][w], 1);
+            if (lane == 0) upn[w] = 0u;
+            if (lane == 31) dnn[w] = 0u;
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+                const int i = pass ? 7 - ii : ii;
+                const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
+                const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t cand[8], any = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const uint32_t above = (i == 0) ? upn[w] : R[i - 1][w];
+                    const uint32_t below = (i == 7) ? dnn[w] : R[i + 1][w];
+                    cand[w] = ~(B[w] | R[i][w]) & (above | below);
+                    any |= cand[w];
+                }
+                if (any) {
+                    uint32_t F[8], r[8];
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) { F[w] = ~B[w]; r[w] = R[i][w] | cand[w]; }
+                    run_fill(F, r);
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) R[i][w] = r[w];
+                    changed = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, changed)) break;
+    }
+
+    // 7. mask = not reached; area, optional packed store, run boundaries -> difference map
+    int area = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = lane * 8 + i;
+        uint32_t M[8], rowany = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { M[w] = ~R[i][w]; rowany |= M[w]; area += __popc(M[w]); }
+        if (mask_out) {
+            uint4* o = reinterpret_cast<uint4*>(mask_out + row * 8);
+            o[0] = make_uint4(M[0], M[1], M[2], M[3]);
+            o[1] = make_uint4(M[4], M[5], M[6], M[7]);
+        }
+        if (diff_img && rowany) {
+            int32_t* drow = diff_img + row * 256;
+            uint32_t carry = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                uint32_t t = M[w] ^ ((M[w] << 1) | carry);
+                carry = M[w] >> 31;
+                while (t) {
+                    const int b = __ffs(t) - 1;
+                    t &= t - 1;
+                    atomicAdd(drow + 32 * w + b, ((M[w] >> b) & 1u) ? 1 : -1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(FULL, area, o);
+    __syncwarp();
+    return area;
+}
+
+// ---------------------------------------------------------------- kernels
+template <bool FROM_CONTOURS>
+__global__ void __launch_bounds__(FW_THREADS, 2)
+sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim,
+                     const float* __restrict__ z, uint64_t seed, int64_t n_img, int64_t n_samples,
+                     int round_landmarks, const float* __restrict__ contours_in,
+                     float* __restrict__ contours_out, int32_t* __restrict__ area_out,
+                     int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = lane_id();
+    const int64_t total = FROM_CONTOURS ? n_samples : n_img * n_samples;
+    const int64_t nwarps = (int64_t)gridDim.x * FW_WARPS;
+    for (int64_t g = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5); g < total; g += nwarps) {
+        float fx = 0.f, fy = 0.f;
+        int64_t img;
+        if (FROM_CONTOURS) {
+            img = per_image > 0 ? g / per_image : 0;
+            if (lane < KP) {
+                const float2 p = reinterpret_cast<const float2*>(contours_in)[g * KP + lane];
+                fx = p.x; fy = p.y;
+            }
+        } else {
+            img = g / n_samples;
+            // 1. draws
+            if (z) {
+                for (int e = lane; e < zdim; e += 32) ws.z[e] = z[g * zdim + e];
+            } else if (lane * 4 < zdim) {
+                uint32_t r[4];
+                philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)lane, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                float n0, n1, n2, n3;
+                box_muller(r[0], r[1], n0, n1);
+                box_muller(r[2], r[3], n2, n3);
+                ws.z[4 * lane] = n0; ws.z[4 * lane + 1] = n1; ws.z[4 * lane + 2] = n2; ws.z[4 * lane + 3] = n3;
+            }
+            __syncwarp();
+            if (lane < KP) {
+                const float2 m = reinterpret_cast<const float2*>(mu)[img * KP + lane];
+                fx = m.x; fy = m.y;
+                const float2* a = reinterpret_cast<const float2*>(a_t + img * (int64_t)zdim * CUB200_P) + lane;
+#pragma unroll 2
+                for (int e = 0; e < zdim; ++e) {
+                    const float2 av = __ldg(a + e * KP);
+                    const float ze = ws.z[e];
+                    fx = fmaf(av.x, ze, fx);
+                    fy = fmaf(av.y, ze, fy);
+                }
+                if (contours_out) reinterpret_cast<float2*>(contours_out)[g * KP + lane] = make_float2(fx, fy);
+            }
+            __syncwarp();
+        }
+        const int area = raster_sample(ws, fx, fy, round_landmarks != 0,
+                                       diff ? diff + img * 65536 : nullptr,
+                                       masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
+        if (area_out && lane == 0) area_out[g] = area;
+    }
+}
+
+static int launch_cfg(int64_t total, const void* kernel, int* grid_out) {
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        CUB200_CUDA_OK(cudaGetDevice(&dev));
+        CUB200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
+    const int64_t need = (total + FW_WARPS - 1) / FW_WARPS;
+    const int64_t cap = (int64_t)num_sms * 2;   // 2 resident CTAs per SM, grid-stride beyond
+    *grid_out = (int)(need < cap ? need : cap);
+    return 0;
+}
+
+}  // namespace cub200
+
+extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
+                                              uint64_t seed, int64_t n_img, int64_t n_samples,
+                                              int round_landmarks, float* contours_out, int32_t* area_out,
+                                              int32_t* diff, uint32_t* masks_out, void* stream) {
+    using namespace cub200;
+    if (!mu || !a_t || zdim < 1 || zdim > CUB200_ZMAX || n_img < 0 || n_samples < 0) return CUB200_EINVAL;
+    const int64_t total = n_img * n_samples;
+    if (total == 0) return 0;
+    int grid = 0;
+    int rc = launch_cfg(total, (const void*)sample_raster_kernel<false>, &grid);
+    if (rc) return rc;
+    sample_raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
+        mu, a_t, zdim, z, seed, n_img, n_samples, round_landmarks, nullptr, contours_out, area_out, diff, masks_out, 0);
+    return check_launch("sample_raster_kernel");
+}
+
+extern "C" int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
+                                         int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
+    using namespace cub200;
+    if (!contours || n < 0 || (diff && per_image <= 0)) return CUB200_EINVAL;
+    if (n == 0) return 0;
+    int grid = 0;
+    int rc = launch_cfg(n, (const void*)sample_raster_kernel<true>, &grid);
+    if (rc) return rc;
+    sample_raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
+        nullptr, nullptr, 0, nullptr, 0, 0, n, round_landmarks, contours, nullptr, area_out, diff, masks_out, per_image);
+    return check_launch("sample_raster_kernel<contours>");
+}

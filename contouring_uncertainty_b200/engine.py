@@ -1,0 +1,261 @@
+"""Thin host layer over the C ABI: tensor checks, output allocation, and the end-to-end engine.
+
+PyTorch is used for device memory and streams only; every computation on the path is a kernel of
+``libcub200.so`` (``contouring_uncertainty_b200/csrc``).  Reference call sites are cited per op.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+K = 21
+P = 42
+HW = 256
+Z_PSM = 34
+Z_NAIVE = 42
+MASK_WORDS = 2048
+
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+DEFAULT_PSM = os.path.join(DATA_DIR, "camus-cont_psm_11_no_std.npy")
+DEFAULT_SEQ_PSM = os.path.join(DATA_DIR, "camus-cont_sequence_psm_11_no_std.npy")
+
+
+# --------------------------------------------------------------------------------------------------
+# K1
+# --------------------------------------------------------------------------------------------------
+def dsnt_moments(heat: torch.Tensor, is_logit: bool = True, covar: bool = True):
+    """Fused flat_softmax + dsnt + pixel rescale (dsnt/utils.py:7-47,71-77,95-105; dsnt_al.py:118-131).
+
+    heat (N, K, 256, 256) fp32 CUDA.  Returns (norm (N,K,5) [x, y, var_x, var_y, covar on the
+    [-1,1] grid], pix_mu (N,K,2), pix_sigma (N,K,2,2)).
+    """
+    heat = nat.require_cuda(heat, torch.float32, "heat")
+    if heat.dim() != 4 or heat.shape[-1] != HW or heat.shape[-2] != HW:
+        raise ValueError(f"heat must be (N, K, {HW}, {HW}), got {tuple(heat.shape)}")
+    n, k = heat.shape[:2]
+    norm = torch.empty((n, k, 5), dtype=torch.float32, device=heat.device)
+    mu = torch.empty((n, k, 2), dtype=torch.float32, device=heat.device)
+    sig = torch.empty((n, k, 2, 2), dtype=torch.float32, device=heat.device)
+    with torch.cuda.device(heat.device):
+        rc = nat.lib().cub200_dsnt_moments(nat.ptr(heat), n * k, HW, HW, int(is_logit), int(covar), nat.ptr(norm),
+                                           nat.ptr(mu), nat.ptr(sig), nat.stream_ptr(heat.device))
+    nat.check(rc, "cub200_dsnt_moments")
+    return norm, mu, sig
+
+
+# --------------------------------------------------------------------------------------------------
+# K2
+# --------------------------------------------------------------------------------------------------
+class ShapeModelConstants:
+    """Per-model constants of the posterior shape model, uploaded once.
+
+    Mirrors what ``PosteriorShapeModelSampler.__init__`` loads (psm.py:30-41): scaler_mean,
+    scaler_scale, X_train, cast to fp32 like the reference; ``pca`` (posteriorshapemodel.py:9-46)
+    of X_train about an arbitrary centre mu is C0 + (xbar - mu)(xbar - mu)^T, so only C0 (42x42)
+    and xbar are needed on the device.
+    """
+
+    def __init__(self, path: str = DEFAULT_PSM, device="cuda"):
+        d = np.load(str(path), allow_pickle=True).item()
+        f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+        x = f32(d["X_train"])
+        if x.shape[1] != P:
+            raise ValueError(f"shape model must be {P}-dimensional, got {x.shape}")
+        xbar = x.mean(0)
+        c0 = (x - xbar).T @ (x - xbar) / x.shape[0]
+        self.path = str(path)
+        self.device = torch.device(device)
+        self.c0 = torch.tensor(c0, dtype=torch.float64, device=self.device).contiguous()
+        self.xbar = torch.tensor(xbar, dtype=torch.float64, device=self.device)
+        self.mean = torch.tensor(f32(d["scaler_mean"]), dtype=torch.float64, device=self.device)
+        self.scale = torch.tensor(f32(d["scaler_scale"]), dtype=torch.float64, device=self.device)
+
+
+def psm_factor(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor) -> torch.Tensor:
+    """Affine map of the PSM sampler per image: (N,21,2),(N,21,2,2) -> A^T (N,34,42) fp32."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    if mu.shape[-2:] != (K, 2) or cov.shape[-3:] != (K, 2, 2) or mu.shape[:-2] != cov.shape[:-3]:
+        raise ValueError(f"mu (..,{K},2) / cov (..,{K},2,2) expected, got {tuple(mu.shape)} / {tuple(cov.shape)}")
+    n = int(np.prod(mu.shape[:-2])) if mu.dim() > 2 else 1
+    a = torch.empty(tuple(mu.shape[:-2]) + (Z_PSM, P), dtype=torch.float32, device=mu.device)
+    with torch.cuda.device(mu.device):
+        rc = nat.lib().cub200_psm_factor(nat.ptr(model.c0), nat.ptr(model.xbar), nat.ptr(model.mean),
+                                         nat.ptr(model.scale), nat.ptr(mu), nat.ptr(cov), n, nat.ptr(a),
+                                         nat.stream_ptr(mu.device))
+    nat.check(rc, "cub200_psm_factor")
+    return a
+
+
+def naive_factor(cov: torch.Tensor) -> torch.Tensor:
+    """Block-diagonal Cholesky colouring of the independent sampler: (N,21,2,2) -> A^T (N,42,42)."""
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    if cov.shape[-3:] != (K, 2, 2):
+        raise ValueError(f"cov (..,{K},2,2) expected, got {tuple(cov.shape)}")
+    n = int(np.prod(cov.shape[:-3])) if cov.dim() > 3 else 1
+    a = torch.empty(tuple(cov.shape[:-3]) + (Z_NAIVE, P), dtype=torch.float32, device=cov.device)
+    with torch.cuda.device(cov.device):
+        rc = nat.lib().cub200_naive_factor(nat.ptr(cov), n, nat.ptr(a), nat.stream_ptr(cov.device))
+    nat.check(rc, "cub200_naive_factor")
+    return a
+
+
+# --------------------------------------------------------------------------------------------------
+# K3
+# --------------------------------------------------------------------------------------------------
+def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Optional[torch.Tensor] = None,
+                            seed: int = 0, round_landmarks: bool = True, return_contours: bool = True,
+                            return_masks: bool = False, diff: Optional[torch.Tensor] = None):
+    """Fused sampler -> rasteriser -> aggregation.  mu (N,21,2); a_t (N,Z,42); z (N,T,Z) or None.
+
+    Returns dict(contours (N,T,21,2) | None, area (N,T) int32, diff (N,256,256) int32,
+    masks (N,T,2048) uint32-as-int32 | None).  ``diff`` may be passed to keep accumulating.
+    """
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    a_t = nat.require_cuda(a_t, torch.float32, "a_t")
+    if mu.dim() != 3 or mu.shape[1:] != (K, 2):
+        raise ValueError(f"mu must be (N,{K},2), got {tuple(mu.shape)}")
+    n = mu.shape[0]
+    if a_t.dim() != 3 or a_t.shape[0] != n or a_t.shape[2] != P or not (1 <= a_t.shape[1] <= 42):
+        raise ValueError(f"a_t must be (N,Z<=42,{P}), got {tuple(a_t.shape)}")
+    zdim = a_t.shape[1]
+    T = int(n_samples)
+    dev = mu.device
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (n, T, zdim):
+            raise ValueError(f"z must be ({n},{T},{zdim}), got {tuple(z.shape)}")
+    contours = torch.empty((n, T, K, 2), dtype=torch.float32, device=dev) if return_contours else None
+    area = torch.empty((n, T), dtype=torch.int32, device=dev)
+    if diff is None:
+        diff = torch.zeros((n, HW, HW), dtype=torch.int32, device=dev)
+    else:
+        diff = nat.require_cuda(diff, torch.int32, "diff")
+        if tuple(diff.shape) != (n, HW, HW):
+            raise ValueError("diff must be (N,256,256) int32")
+    masks = torch.empty((n, T, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
+                                                      n, T, int(round_landmarks), nat.ptr(contours), nat.ptr(area),
+                                                      nat.ptr(diff), nat.ptr(masks), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_sample_raster_aggregate")
+    return dict(contours=contours, area=area, diff=diff, masks=masks)
+
+
+def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, return_masks: bool = True,
+                       diff: Optional[torch.Tensor] = None, per_image: int = 0):
+    """Rasteriser alone: contours (M,21,2) fp32 -> (masks (M,2048) int32 bit-packed | None, area (M) int32)."""
+    contours = nat.require_cuda(contours, torch.float32, "contours")
+    if contours.dim() != 3 or contours.shape[1:] != (K, 2):
+        raise ValueError(f"contours must be (M,{K},2), got {tuple(contours.shape)}")
+    m = contours.shape[0]
+    dev = contours.device
+    masks = torch.empty((m, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
+    area = torch.empty((m,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_rasterize_contours(nat.ptr(contours), m, int(round_landmarks), nat.ptr(masks), nat.ptr(area),
+                                                 nat.ptr(diff), int(per_image), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_rasterize_contours")
+    return masks, area
+
+
+def unpack_masks(masks: torch.Tensor) -> torch.Tensor:
+    """(..., 2048) int32 bit-packed -> (..., 256, 256) uint8 (host or device; plain torch bit ops)."""
+    w = masks.reshape(masks.shape[:-1] + (HW, 8, 1))
+    bits = (w >> torch.arange(32, device=masks.device, dtype=torch.int32)) & 1
+    return bits.reshape(masks.shape[:-1] + (HW, HW)).to(torch.uint8)
+
+
+# --------------------------------------------------------------------------------------------------
+# K4
+# --------------------------------------------------------------------------------------------------
+def finalize_maps(diff: torch.Tensor, n_samples: int, want_count: bool = True):
+    """difference map -> (count int32 | None, mean fp64, entropy fp64 [bits], pred uint8), all (N,256,256).
+
+    aleatoric.py:111 (pred) and uncertainty.py:107-133 (sample_entropy).
+    """
+    diff = nat.require_cuda(diff, torch.int32, "diff")
+    if diff.dim() != 3 or diff.shape[1:] != (HW, HW):
+        raise ValueError("diff must be (N,256,256) int32")
+    n = diff.shape[0]
+    dev = diff.device
+    count = torch.empty_like(diff) if want_count else None
+    mean = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
+    ent = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
+    pred = torch.empty((n, HW, HW), dtype=torch.uint8, device=dev)
+    lut = torch.empty((int(n_samples) + 1,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_finalize_maps(nat.ptr(diff), n, int(n_samples), nat.ptr(count), nat.ptr(mean), nat.ptr(ent),
+                                            nat.ptr(pred), nat.ptr(lut), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_finalize_maps")
+    return count, mean, ent, pred
+
+
+def fac_from_areas(area_ed: torch.Tensor, area_es: torch.Tensor) -> torch.Tensor:
+    """Per-sample FAC = (A_ED - A_ES)/A_ED, NaN outside [0,1] (clinical.py:11-29, view.py:35-78)."""
+    area_ed = nat.require_cuda(area_ed, torch.int32, "area_ed")
+    area_es = nat.require_cuda(area_es, torch.int32, "area_es")
+    if area_ed.shape != area_es.shape:
+        raise ValueError("area_ed / area_es shapes differ")
+    out = torch.empty(area_ed.shape, dtype=torch.float64, device=area_ed.device)
+    with torch.cuda.device(area_ed.device):
+        rc = nat.lib().cub200_fac_from_areas(nat.ptr(area_ed), nat.ptr(area_es), area_ed.numel(), nat.ptr(out),
+                                             nat.stream_ptr(area_ed.device))
+    nat.check(rc, "cub200_fac_from_areas")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# End-to-end engine
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class UncertaintyResult:
+    mu: torch.Tensor              # (N,21,2) pixel coordinates
+    cov: torch.Tensor             # (N,21,2,2)
+    contour_samples: Optional[torch.Tensor]  # (N,T,21,2)
+    area: torch.Tensor            # (N,T) int32 LV pixel counts
+    count: Optional[torch.Tensor]  # (N,256,256) int32
+    mean: torch.Tensor            # (N,256,256) fp64
+    entropy: torch.Tensor         # (N,256,256) fp64, bits
+    pred: torch.Tensor            # (N,256,256) uint8
+    masks: Optional[torch.Tensor] = None  # (N,T,2048) int32 bit-packed
+
+
+class UncertaintyEngine:
+    """heatmap logits -> DSNT -> sampler factor -> fused sample/raster/aggregate -> maps.
+
+    The data-parallel hot path of ``AleatoricUncertaintyTask._predict_step`` + ``predict_step``
+    (aleatoric.py:80-135, contour_uncertainty.py:71-82) for T_e = 1.
+    """
+
+    def __init__(self, psm_path: str = DEFAULT_PSM, device="cuda", sampler: str = "psm", covar: bool = True):
+        if sampler not in ("psm", "naive"):
+            raise ValueError("sampler must be 'psm' or 'naive'")
+        self.device = torch.device(device)
+        self.sampler = sampler
+        self.covar = covar
+        self.model = ShapeModelConstants(psm_path, self.device) if sampler == "psm" else None
+        nat.lib()  # fail now if the extension is missing
+
+    def factor(self, mu, cov):
+        return psm_factor(self.model, mu, cov) if self.sampler == "psm" else naive_factor(cov)
+
+    def from_moments(self, mu, cov, t_a: int, z=None, seed: int = 0, return_contours=True, return_masks=False,
+                     want_count=True) -> UncertaintyResult:
+        a_t = self.factor(mu, cov)
+        r = sample_raster_aggregate(mu, a_t, t_a, z=z, seed=seed, return_contours=return_contours,
+                                    return_masks=return_masks)
+        count, mean, ent, pred = finalize_maps(r["diff"], t_a, want_count=want_count)
+        return UncertaintyResult(mu, cov, r["contours"], r["area"], count, mean, ent, pred, r["masks"])
+
+    def __call__(self, logits: torch.Tensor, t_a: int, z=None, seed: int = 0, return_contours=True,
+                 return_masks=False, want_count=True) -> UncertaintyResult:
+        _, mu, cov = dsnt_moments(logits, is_logit=True, covar=self.covar)
+        return self.from_moments(mu, cov, t_a, z=z, seed=seed, return_contours=return_contours,
+                                 return_masks=return_masks, want_count=want_count)

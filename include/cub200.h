@@ -1,0 +1,148 @@
+/*
+ * cub200.h -- C ABI of the B200-native uncertainty path of contouring-uncertainty.
+ *
+ * One shared library (libcub200.so, sm_100a).  Plain pointers and sizes only: no torch / C++ types
+ * cross this boundary.  All data pointers are DEVICE pointers unless the name ends in `_host`.
+ * Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ * stream), allocates nothing, and returns 0 or a negative error code:
+ *     CUB200_EINVAL (-1)  bad shape / null pointer / unsupported size
+ *     CUB200_ECUDA  (-2)  a CUDA runtime error (text: cub200_last_error())
+ * Buffers are owned by the caller.  Calls on distinct streams are thread-safe.
+ *
+ * The reference (ThierryJudge/contouring-uncertainty) has no FFI layer -- it is pure Python -- so
+ * each entry point cites the Python function(s) it replaces (paths relative to the reference root,
+ * cu/ = contour_uncertainty/).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Fixed geometry of this path: K = 21 landmarks (config/data/camus-cont.yaml:15), frames of
+ * 256 x 256 (config/task/model/unet2.yaml:8).
+ */
+#ifndef CUB200_H
+#define CUB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUB200_K 21          /* landmarks per contour                        */
+#define CUB200_P 42          /* 2K: flattened contour dimension              */
+#define CUB200_HW 256        /* frame height = width                         */
+#define CUB200_ZMAX 42       /* max number of standard-normal draws / sample */
+#define CUB200_MASK_WORDS 2048 /* 256 rows x 8 uint32 (bit x&31 of word x>>5) */
+
+#define CUB200_EINVAL (-1)
+#define CUB200_ECUDA (-2)
+
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char* cub200_last_error(void);
+/* ABI version (bumped on any signature change) and the SM the kernels were built for (100). */
+int cub200_abi_version(void);
+int cub200_built_for_sm(void);
+
+/*
+ * K1  DSNT heads: fused flat-softmax + coordinate expectation + 2x2 central second moments, one
+ * pass over each heatmap.
+ *   replaces  flat_softmax            cu/task/regression/dsnt/utils.py:71-77
+ *             dsnt                    cu/task/regression/dsnt/utils.py:7-47
+ *             normalized_to_pixel_coordinates  cu/task/regression/dsnt/utils.py:95-105
+ *             DSNTAleatoric.predict_on_batch   cu/task/regression/dsnt/dsnt_al.py:118-131
+ *             get_cov_matrix          cu/task/regression/aleatoric.py:138-144
+ *   heat      (n_maps, h, w) fp32 contiguous, h = w = 256.  Logits when is_logit != 0 (softmax is
+ *             fused), already-normalised heatmaps otherwise (what dsnt() receives).
+ *   norm_out  optional (n_maps, 5) fp32: x, y, var_x, var_y, covar on the [-1,1] grid (= dsnt()).
+ *   pix_mu    optional (n_maps, 2) fp32 pixel coordinates (x, y).
+ *   pix_sigma optional (n_maps, 2, 2) fp32 pixel covariance; off-diagonals 0 when use_covar == 0
+ *             (hparams.covar, dsnt_al.py:124).
+ */
+int cub200_dsnt_moments(const float* heat, int64_t n_maps, int h, int w, int is_logit, int use_covar,
+                        float* norm_out, float* pix_mu, float* pix_sigma, void* stream);
+
+/*
+ * K2  Posterior-shape-model factor: per image, the affine map of the hierarchical PSM sampler,
+ *     contour = mu + A z,  z in R^34 (17 draws of shape (1,2): points 0,10,20 | 5,15 | 2,7,13,18 |
+ *     1,3,6,8,12,14,17,19),  A in R^(42 x 34).
+ *   replaces  pca                     cu/sampler/posterior_shape_model/posteriorshapemodel.py:9-46
+ *             posterior_shape_model   .../posteriorshapemodel.py:49-81
+ *             PosteriorShapeModelSampler.__call__ / sample_endo_contour / merge_priors / transform
+ *                                     cu/sampler/posterior_shape_model/psm.py:73-93,199-384,424-450
+ *   model_c0   (42,42) fp64: covariance of X_train about its own mean (biased, /N)
+ *   model_xbar (42)    fp64: mean of X_train
+ *   scaler_mean, scaler_scale (42) fp64
+ *   mu (n_img, 21, 2) fp32, cov (n_img, 21, 2, 2) fp32
+ *   a_out (n_img, 34, 42) fp32, stored TRANSPOSED (draw-major) so that a sample is
+ *         contour[d] = mu[d] + sum_e a_out[e][d] * z[e].
+ */
+int cub200_psm_factor(const double* model_c0, const double* model_xbar, const double* scaler_mean,
+                      const double* scaler_scale, const float* mu, const float* cov, int64_t n_img,
+                      float* a_out, void* stream);
+
+/*
+ * Independent-Gaussian (naive) sampler factor: block-diagonal A (42 draws), 2x2 Cholesky colouring.
+ *   replaces  Sampler.sample_points / NaiveSampler.__call__   cu/sampler/sampler.py:22-41, naive.py:13-25
+ *   a_out (n_img, 42, 42) fp32 transposed as above; draw slot of landmark k = (2k, 2k+1).
+ *   (numpy colours with an SVD factor; for draw-replay parity the host passes its own A.)
+ */
+int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* stream);
+
+/*
+ * K3  Fused Monte-Carlo sampler -> rasteriser -> streaming aggregation.  One warp per sample:
+ *     contour = mu + A z  ->  round  ->  cubic spline (fp64, 1000 points)  ->  pixel set + closing
+ *     line  ->  4-connected background flood from the frame border  ->  per-sample area and
+ *     run-boundary increments into the image's difference map.  Masks never leave shared memory.
+ *   replaces  AleatoricUncertaintyTask.sample          cu/task/regression/aleatoric.py:54-78
+ *             ContourUncertaintyTask.convert_to_mask   cu/task/regression/contour_uncertainty.py:26-57
+ *             USContourToMask.__call__ (LV branch)     cu/data/camus/utils.py:31-98
+ *             reconstruction / contour_spline          cu/utils/contour.py:9-40
+ *             lv_area                                  cu/utils/clinical.py:92-93
+ *   mu (n_img, 42) fp32; a_t (n_img, zdim, 42) fp32 (transposed factor), zdim <= 42
+ *   z  optional (n_img, n_samples, zdim) fp32 standard-normal draws to replay; NULL -> Philox4x32-10
+ *      + Box-Muller keyed by (seed, image, sample)
+ *   contours_out optional (n_img, n_samples, 21, 2) fp32 (the API's contour_samples)
+ *   area_out     optional (n_img, n_samples) int32  mask pixel counts
+ *   diff         (n_img, 256, 256) int32, ACCUMULATED into (caller zeroes): +1 where a mask run
+ *                starts, -1 one past where it ends; the row prefix sum is the count map
+ *   masks_out    optional (n_img, n_samples, 2048) uint32 bit-packed masks (debug / return_masks)
+ *   round_landmarks: 1 = USContourToMask semantics (round landmarks first), 0 = reconstruction()
+ *                on the raw float contour (cu/sampler/sampling_example3.py:127)
+ */
+int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
+                                   uint64_t seed, int64_t n_img, int64_t n_samples,
+                                   int round_landmarks, float* contours_out, int32_t* area_out,
+                                   int32_t* diff, uint32_t* masks_out, void* stream);
+
+/*
+ * Rasteriser alone (the same device code as K3, contours given): bit-packed masks out.
+ *   contours (n, 21, 2) fp32; masks_out (n, 2048) uint32 optional; area_out (n) int32 optional;
+ *   diff optional (n_img, 256, 256) int32 accumulated, image of contour i = i / per_image.
+ */
+int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
+                              int32_t* area_out, int32_t* diff, int64_t per_image, void* stream);
+
+/*
+ * K4  Finalise the per-image maps from the difference map.
+ *   replaces  pred = pred_samples.mean((1,2)).round()   cu/task/regression/aleatoric.py:111
+ *             UncertaintyTask.sample_entropy            cu/task/uncertainty.py:107-133
+ *   diff (n_img,256,256) int32; n_samples = T (samples aggregated per image)
+ *   count_out optional (n_img,256,256) int32; mean_out optional fp64 = count/T;
+ *   entropy_out optional fp64 binary entropy in bits (scipy.stats.entropy([p,1-p], base=2));
+ *   pred_out optional uint8 = round-half-even(count/T)
+ *   lut_ws: device workspace of (n_samples + 1) doubles (entropy of c/T), written by the call.
+ */
+int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
+                         double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,
+                         void* stream);
+
+/*
+ * Per-view clinical reductions from per-sample areas.
+ *   replaces  lv_FAC / FAC.compute (per-sample part)    cu/utils/clinical.py:11-29,
+ *                                                      cu/results/clinical/view.py:35-78
+ *   area_ed, area_es (n) int32 -> fac_out (n) fp64 = (ed - es)/ed, NaN when outside [0,1].
+ */
+int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_t n, double* fac_out,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUB200_H */
