@@ -142,7 +142,7 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
     if (lane == 0) u = 0.0;
     const double uprev = __shfl_up_sync(FULL, u, 1);
     // FITPACK rejects non-increasing parameters (zero chord) -> ValueError -> raw points drawn
-    const bool bad = __any_sync(FULL, lane >= 1 && lane < KP && !(u > uprev)) || !(total > 0.0);
+    const bool bad = __any_sync(FULL, lane >= 1 && lane < KP && (dch == 0.0 || !(u > uprev))) || !(total > 0.0);
     __syncwarp();
 
     bool oob = false;
@@ -496,8 +496,8 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
 extern "C" int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
                                          int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
     using namespace cub200;
-    if (!contours || n < 0 || (diff && per_image <= 0)) return CUB200_EINVAL;
     if (n == 0) return 0;
+    if (!contours || n < 0 || (diff && per_image <= 0)) return CUB200_EINVAL;
     int grid = 0;
     int rc = launch_cfg(n, (const void*)sample_raster_kernel<true>, &grid);
     if (rc) return rc;
