@@ -241,7 +241,7 @@ def run_ours(args):
     # nvidia-smi is started BEFORE the warm-up and given time to reach its polling loop: its start-up
     # takes driver locks that stall launches for milliseconds, which must not land in the timed region
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         clocks.start()
         t_wait = time.time()
         while len(clocks.lines) < 3 and time.time() - t_wait < 5.0 and clocks.proc is not None:
@@ -262,7 +262,7 @@ def run_ours(args):
     for e in evs:
         for name, a, b in (("dsnt", 0, 1), ("psm_factor", 1, 2), ("fused", 2, 3), ("finalize", 3, 4)):
             kernel_ms[name].append(e[a].elapsed_time(e[b]))
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (rank == 0 and not args.no_clocks) else None
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

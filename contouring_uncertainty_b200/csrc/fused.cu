@@ -42,8 +42,6 @@ struct __align__(16) WarpScratch {
     uint32_t bmp[BMP_WORDS];
     double u[24];          // chord parameters u_0..u_20
     double coef[20][8];    // piece i on [u_i, u_{i+1}]: x c0..c3, y c0..c3 (powers of u - u_i)
-    double sub[24], dia[24], sup[24], rx[24], ry[24];
-    double mx[24], my[24];
     float z[CUB200_ZMAX + 2];
 };
 
@@ -104,6 +102,48 @@ __device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8]) {
     }
 }
 
+// One Gauss-Seidel sweep of the vertical flood over the lane's 8-row band (UP = 0: rows 0->7,
+// UP = 1: rows 7->0).  A row advances where a free, unreached pixel has a reached vertical
+// neighbour; the whole run containing it is then filled.  Returns whether this lane advanced.
+template <int UP>
+__device__ __forceinline__ bool flood_sweep(uint32_t (&R)[8][8], const uint4* band4, int lane) {
+    bool changed = false;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+        constexpr int dummy = 0; (void)dummy;
+        const int i = UP ? 7 - ii : ii;
+        uint32_t nb[8];                                      // the row across the band edge
+        if (i == 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { nb[w] = __shfl_up_sync(FULL, R[7][w], 1); if (lane == 0) nb[w] = 0u; }
+        }
+        if (i == 7) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { nb[w] = __shfl_down_sync(FULL, R[0][w], 1); if (lane == 31) nb[w] = 0u; }
+        }
+        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
+        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t cand[8], any = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t above = (i == 0) ? nb[w] : R[i > 0 ? i - 1 : 0][w];
+            const uint32_t below = (i == 7) ? nb[w] : R[i < 7 ? i + 1 : 7][w];
+            cand[w] = ~(B[w] | R[i][w]) & (above | below);
+            any |= cand[w];
+        }
+        if (any) {
+            uint32_t F[8], r[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { F[w] = ~B[w]; r[w] = R[i][w] | cand[w]; }
+            run_fill(F, r);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) R[i][w] = r[w];
+            changed = true;
+        }
+    }
+    return changed;
+}
+
 // ---------------------------------------------------------------- one sample, one warp
 // Lane k < 21 holds landmark k as (fx, fy).  Returns the mask area; accumulates run boundaries
 // into diff_img (may be null) and stores the packed mask (may be null).
@@ -156,6 +196,8 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
         const double hm = __shfl_up_sync(FULL, h, 1);
         const double dxm = __shfl_up_sync(FULL, dxk, 1), dym = __shfl_up_sync(FULL, dyk, 1);
         if (lane < KP) ws.u[lane] = u;
+        // rows 1..19 (lane = row), normalised to unit diagonal; other lanes hold identity rows
+        double ta = 0.0, tc = 0.0, tx = 0.0, ty = 0.0;
         if (lane >= 1 && lane <= KP - 2) {
             double a = hm, b = 2.0 * (hm + h), c = h;
             double r1 = 6.0 * (dxk - dxm), r2 = 6.0 * (dyk - dym);
@@ -166,43 +208,43 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
                 const double f = hm / (hm + h);
                 a = hm - h; b = h + 2.0 * hm; c = 0.0; r1 *= f; r2 *= f;
             }
-            ws.sub[lane] = a; ws.dia[lane] = b; ws.sup[lane] = c; ws.rx[lane] = r1; ws.ry[lane] = r2;
+            const double ib = 1.0 / b;
+            ta = a * ib; tc = c * ib; tx = r1 * ib; ty = r2 * ib;
         }
-        __syncwarp();
-        if (lane < 2) {                                      // Thomas: lane 0 -> x, lane 1 -> y
-            double* r = lane ? ws.ry : ws.rx;
-            double* m = lane ? ws.my : ws.mx;
-            double bp = ws.dia[1];
-            double ivp = 1.0 / bp;
-            double rp = r[1];
-            double* inv = m;                                 // pivots' reciprocals live in m[] until overwritten
-            inv[1] = ivp;
-            for (int i = 2; i <= KP - 2; ++i) {
-                const double w = ws.sub[i] * ivp;
-                bp = ws.dia[i] - w * ws.sup[i - 1];
-                rp = r[i] - w * rp;
-                r[i] = rp;
-                ivp = 1.0 / bp;
-                inv[i] = ivp;
-            }
-            double mi = rp * ivp;
-            m[KP - 2] = mi;
-            for (int i = KP - 3; i >= 1; --i) {
-                mi = (r[i] - ws.sup[i] * mi) * inv[i];
-                m[i] = mi;
-            }
-            const double h0 = ws.u[1] - ws.u[0], h1 = ws.u[2] - ws.u[1];
-            m[0] = m[1] - (h0 / h1) * (m[2] - m[1]);
-            const double hl = ws.u[KP - 1] - ws.u[KP - 2], hl1 = ws.u[KP - 2] - ws.u[KP - 3];
-            m[KP - 1] = m[KP - 2] + (hl / hl1) * (m[KP - 2] - m[KP - 3]);
+        // parallel cyclic reduction: 5 steps decouple the 19 equations (x and y share the matrix)
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            double am = __shfl_up_sync(FULL, ta, sft), cm = __shfl_up_sync(FULL, tc, sft);
+            double xm = __shfl_up_sync(FULL, tx, sft), ym = __shfl_up_sync(FULL, ty, sft);
+            double ap = __shfl_down_sync(FULL, ta, sft), cp = __shfl_down_sync(FULL, tc, sft);
+            double xp = __shfl_down_sync(FULL, tx, sft), yp = __shfl_down_sync(FULL, ty, sft);
+            if (lane < sft) { am = cm = xm = ym = 0.0; }
+            if (lane + sft > 31) { ap = cp = xp = yp = 0.0; }
+            const double r = 1.0 / (1.0 - ta * cm - tc * ap);
+            tx = (tx - ta * xm - tc * xp) * r;
+            ty = (ty - ta * ym - tc * yp) * r;
+            ta = -ta * am * r;
+            tc = -tc * cp * r;
         }
-        __syncwarp();
-        if (lane < KP - 1) {                                 // piece coefficients
-            const double m0x = ws.mx[lane], m1x = ws.mx[lane + 1];
-            const double m0y = ws.my[lane], m1y = ws.my[lane + 1];
-            double* c = ws.coef[lane];
-            c[0] = X; c[1] = dxk - h * (2.0 * m0x + m1x) * (1.0 / 6.0); c[2] = 0.5 * m0x; c[3] = (m1x - m0x) * ih * (1.0 / 6.0);
-            c[4] = Y; c[5] = dyk - h * (2.0 * m0y + m1y) * (1.0 / 6.0); c[6] = 0.5 * m0y; c[7] = (m1y - m0y) * ih * (1.0 / 6.0);
+        // second derivatives: lane i holds M_i (i = 1..19); M_0, M_20 from the not-a-knot relations
+        double Mx = tx, My = ty;
+        {
+            const double m1x = __shfl_down_sync(FULL, Mx, 1), m2x = __shfl_down_sync(FULL, Mx, 2);
+            const double m1y = __shfl_down_sync(FULL, My, 1), m2y = __shfl_down_sync(FULL, My, 2);
+            const double h1 = __shfl_down_sync(FULL, h, 1);
+            const double p1x = __shfl_up_sync(FULL, Mx, 1), p2x = __shfl_up_sync(FULL, Mx, 2);
+            const double p1y = __shfl_up_sync(FULL, My, 1), p2y = __shfl_up_sync(FULL, My, 2);
+            const double hm2 = __shfl_up_sync(FULL, h, 2);
+            if (lane == 0) { const double q = h / h1; Mx = m1x - q * (m2x - m1x); My = m1y - q * (m2y - m1y); }
+            if (lane == KP - 1) { const double q = hm / hm2; Mx = p1x + q * (p1x - p2x); My = p1y + q * (p1y - p2y); }
+        }
+        {
+            const double m1x = __shfl_down_sync(FULL, Mx, 1), m1y = __shfl_down_sync(FULL, My, 1);
+            if (lane < KP - 1) {                             // piece coefficients
+                double* c = ws.coef[lane];
+                c[0] = X; c[1] = dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0); c[2] = 0.5 * Mx; c[3] = (m1x - Mx) * ih * (1.0 / 6.0);
+                c[4] = Y; c[5] = dyk - h * (2.0 * My + m1y) * (1.0 / 6.0); c[6] = 0.5 * My; c[7] = (m1y - My) * ih * (1.0 / 6.0);
+            }
         }
         __syncwarp();
 
@@ -221,7 +263,7 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
         double e0 = ws.coef[piece][4], e1 = ws.coef[piece][5], e2 = ws.coef[piece][6], e3 = ws.coef[piece][7];
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-            const int j = j0 + jj;
+            const int j = min(j0 + jj, NPTS - 1);            // lane 31 repeats the last point
             const double uj = (j == NPTS - 1) ? 1.0 : (double)j * step;
             while (piece < KP - 2 && uj >= un) {
                 ++piece;
@@ -233,14 +275,10 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
             const double xv = fma(fma(fma(c3, s, c2), s, c1), s, c0);
             const double yv = fma(fma(fma(e3, s, e2), s, e1), s, e0);
             int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
-            if (j < NPTS) {
-                oob |= (ix < -256) | (iy < -256);
-                ix += (ix < 0) ? 256 : 0;                    // numpy negative index wrap
-                iy += (iy < 0) ? 256 : 0;
-                pix[jj] = ((uint32_t)(iy & 255) << 8) | (uint32_t)(ix & 255);
-            } else {
-                pix[jj] = 0xffffffffu;
-            }
+            oob |= (ix < -256) | (iy < -256);
+            ix += (ix < 0) ? 256 : 0;                        // numpy negative index wrap
+            iy += (iy < 0) ? 256 : 0;
+            pix[jj] = ((uint32_t)(iy & 255) << 8) | (uint32_t)(ix & 255);
         }
         oob = __any_sync(FULL, oob);
         __syncwarp();                                        // bitmap zeroing visible
@@ -249,15 +287,12 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
                 const uint32_t p = pix[jj];
-                if (p != 0xffffffffu) {
-                    const uint32_t cell = p >> 5;            // row * 8 + word
-                    const uint32_t bit = 1u << (p & 31);
-                    if (cell != cur) {
-                        if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
-                        cur = cell; bits = 0;
-                    }
-                    bits |= bit;
+                const uint32_t cell = p >> 5;                // row * 8 + word
+                if (cell != cur) {
+                    if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+                    cur = cell; bits = 0;
                 }
+                bits |= 1u << (p & 31);
             }
             if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
         }
@@ -308,91 +343,68 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
     for (int i = 0; i < 8; ++i) {
         const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
         const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t rowor = (B[0] | B[1] | B[2]) | (B[3] | B[4] | B[5]) | (B[6] | B[7]);
         const bool border_row = (lane == 0 && i == 0) || (lane == 31 && i == 7);
-        bool seen = false;
+        if (rowor == 0u) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t low = (B[w] & (0u - B[w])) - 1u;      // bits below the lowest set bit (all if 0)
-            R[i][w] = seen ? 0u : low;
-            seen |= (B[w] != 0u);
-        }
-        seen = false;
-#pragma unroll
-        for (int w = 7; w >= 0; --w) {
-            const uint32_t high = B[w] ? ~(0xffffffffu >> __clz(B[w])) : 0xffffffffu;  // above the highest set bit
-            R[i][w] |= seen ? 0u : high;
-            seen |= (B[w] != 0u);
-        }
-        if (border_row) {
+            for (int w = 0; w < 8; ++w) R[i][w] = 0xffffffffu;
+        } else if (border_row) {
 #pragma unroll
             for (int w = 0; w < 8; ++w) R[i][w] = ~B[w];
-        }
-    }
-    // 6b. vertical propagation to a fixed point (Gauss-Seidel sweeps inside the band, neighbours'
-    //     edge rows by shuffle).  Typical convex-ish contours exit after one quiescent pass.
-    for (;;) {
-        bool changed = false;
-        uint32_t upn[8], dnn[8];
+        } else {
+            // left part: bits below the lowest set bit of the 256-bit row = (B - 1) & ~B
+            uint32_t X[8];
+            asm("sub.cc.u32 %0, %1, 1;" : "=r"(X[0]) : "r"(B[0]));
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            upn[w] = __shfl_up_sync(FULL, R[7][w], 1);
-            dnn[w] = __shfl_down_sync(FULL, R[0][w], 1);
-            if (lane == 0) upn[w] = 0u;
-            if (lane == 31) dnn[w] = 0u;
-        }
+            for (int w = 1; w < 8; ++w) asm("subc.cc.u32 %0, %1, 0;" : "=r"(X[w]) : "r"(B[w]));
+            // right part: bits above the highest set bit
+            bool seen = false;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) {
-                const int i = pass ? 7 - ii : ii;
-                const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
-                const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                uint32_t cand[8], any = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                    const uint32_t above = (i == 0) ? upn[w] : R[i - 1][w];
-                    const uint32_t below = (i == 7) ? dnn[w] : R[i + 1][w];
-                    cand[w] = ~(B[w] | R[i][w]) & (above | below);
-                    any |= cand[w];
-                }
-                if (any) {
-                    uint32_t F[8], r[8];
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) { F[w] = ~B[w]; r[w] = R[i][w] | cand[w]; }
-                    run_fill(F, r);
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) R[i][w] = r[w];
-                    changed = true;
-                }
+            for (int w = 7; w >= 0; --w) {
+                const uint32_t smear = __funnelshift_rc(0xffffffffu, 0u, __clz(B[w]));  // 0 when B[w] == 0
+                R[i][w] = (X[w] & ~B[w]) | (seen ? 0u : ~smear);
+                seen |= (B[w] != 0u);
             }
         }
-        if (!__any_sync(FULL, changed)) break;
+    }
+    // 6b. vertical propagation to a fixed point: alternating Gauss-Seidel sweeps inside the band
+    //     (neighbour lanes' edge rows by shuffle), stopping after the first sweep in which no lane
+    //     advanced.  Convex-ish contours exit after one quiescent sweep.
+    for (;;) {
+        if (!__any_sync(FULL, flood_sweep<0>(R, band4, lane))) break;
+        if (!__any_sync(FULL, flood_sweep<1>(R, band4, lane))) break;
     }
 
-    // 7. mask = not reached; area, optional packed store, run boundaries -> difference map
+    // 7. mask = not reached.  The run boundaries of the mask are the transitions of R along the row
+    //    (virtual R = 1 left of column 0): +1 where the mask starts, -1 one past where it ends.
+    //    area = sum of run lengths = sum(end) - sum(start).
     int area = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = lane * 8 + i;
-        uint32_t M[8], rowany = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { M[w] = ~R[i][w]; rowany |= M[w]; area += __popc(M[w]); }
         if (mask_out) {
             uint4* o = reinterpret_cast<uint4*>(mask_out + row * 8);
-            o[0] = make_uint4(M[0], M[1], M[2], M[3]);
-            o[1] = make_uint4(M[4], M[5], M[6], M[7]);
+            o[0] = make_uint4(~R[i][0], ~R[i][1], ~R[i][2], ~R[i][3]);
+            o[1] = make_uint4(~R[i][4], ~R[i][5], ~R[i][6], ~R[i][7]);
         }
-        if (diff_img && rowany) {
-            int32_t* drow = diff_img + row * 256;
-            uint32_t carry = 0;
+        uint32_t t[8];
+        t[0] = R[i][0] ^ __funnelshift_l(0xffffffffu, R[i][0], 1);
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t[w] = R[i][w] ^ __funnelshift_l(R[i][w - 1], R[i][w], 1);
+        const uint32_t tany = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]) | (t[6] | t[7]);
+        if (tany) {
+            int32_t* drow = diff_img ? diff_img + row * 256 : nullptr;
+            if (!(R[i][7] >> 31)) area += 256;                   // run reaching column 255 ends at 256
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                uint32_t t = M[w] ^ ((M[w] << 1) | carry);
-                carry = M[w] >> 31;
-                while (t) {
-                    const int b = __ffs(t) - 1;
-                    t &= t - 1;
-                    atomicAdd(drow + 32 * w + b, ((M[w] >> b) & 1u) ? 1 : -1);
+                uint32_t tw = t[w];
+                while (tw) {
+                    const int b = __ffs(tw) - 1;
+                    tw &= tw - 1;
+                    const int x = 32 * w + b;
+                    const bool start = !((R[i][w] >> b) & 1u);   // mask starts where R drops to 0
+                    area += start ? -x : x;
+                    if (drow) atomicAdd(drow + x, start ? 1 : -1);
                 }
             }
         }
@@ -443,12 +455,16 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
                 const float2 m = reinterpret_cast<const float2*>(mu)[img * KP + lane];
                 fx = m.x; fy = m.y;
                 const float2* a = reinterpret_cast<const float2*>(a_t + img * (int64_t)zdim * CUB200_P) + lane;
-#pragma unroll 2
-                for (int e = 0; e < zdim; ++e) {
-                    const float2 av = __ldg(a + e * KP);
-                    const float ze = ws.z[e];
-                    fx = fmaf(av.x, ze, fx);
-                    fy = fmaf(av.y, ze, fy);
+                for (int e0 = 0; e0 < zdim; e0 += 8) {            // 8 factor rows in flight
+                    float2 av[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) av[q] = (e0 + q < zdim) ? __ldg(a + (e0 + q) * KP) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float ze = (e0 + q < zdim) ? ws.z[e0 + q] : 0.f;
+                        fx = fmaf(av[q].x, ze, fx);
+                        fy = fmaf(av[q].y, ze, fy);
+                    }
                 }
                 if (contours_out) reinterpret_cast<float2*>(contours_out)[g * KP + lane] = make_float2(fx, fy);
             }
