@@ -41,7 +41,7 @@ constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px be
 struct __align__(16) WarpScratch {
     uint32_t bmp[BMP_WORDS];
     double u[24];          // chord parameters u_0..u_20
-    double coef[20][8];    // piece i on [u_i, u_{i+1}]: x c0..c3, y c0..c3 (powers of u - u_i)
+    double piece[20][10];  // piece i on [u_i, u_{i+1}]: {u_{i+1}, u_i, x c0..c3, y c0..c3} (powers of u - u_i)
     float z[CUB200_ZMAX + 2];
 };
 
@@ -102,12 +102,54 @@ __device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8]) {
     }
 }
 
+// Generic run extraction of one mask row (mask = ~R): every transition of R along the row (virtual
+// R = 1 left of column 0) is +1 where the mask starts, -1 one past where it ends.  Returns the row's
+// mask area.  Rare path (frame-border rows, rows of concave / self-intersecting samples).
+__device__ __noinline__ int emit_row_generic(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                             uint32_t r5, uint32_t r6, uint32_t r7, int32_t* drow) {
+    const uint32_t Rw[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    int area = (r7 >> 31) ? 0 : 256;                         // a run reaching column 255 ends at 256
+    uint32_t prev = 0xffffffffu;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t tw = Rw[w] ^ __funnelshift_l(prev, Rw[w], 1);
+        prev = Rw[w];
+        while (tw) {
+            const int b = __ffs(tw) - 1;
+            tw &= tw - 1;
+            const int x = 32 * w + b;
+            const bool start = !((Rw[w] >> b) & 1u);
+            area += start ? -x : x;
+            if (drow) atomicAdd(drow + x, start ? 1 : -1);
+        }
+    }
+    return area;
+}
+
+// Take back the single run [first, last boundary pixel] that step 6a emitted for this row (rare).
+__device__ __noinline__ int undo_row_span(const uint32_t* brow, int32_t* drow) {
+    int xs = -1, xe = 0;
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t b = brow[w];
+        if (b) {
+            if (xs < 0) xs = 32 * w + __ffs(b) - 1;
+            xe = 32 * w + 32 - __clz(b);
+        }
+    }
+    if (xs < 0) return 0;
+    if (drow) {
+        atomicAdd(drow + xs, -1);
+        if (xe < 256) atomicAdd(drow + xe, 1);
+    }
+    return xe - xs;
+}
+
 // One Gauss-Seidel sweep of the vertical flood over the lane's 8-row band (UP = 0: rows 0->7,
 // UP = 1: rows 7->0).  A row advances where a free, unreached pixel has a reached vertical
-// neighbour; the whole run containing it is then filled.  Returns whether this lane advanced.
+// neighbour; the whole run containing it is then filled.  Returns the bitmask of rows advanced.
 template <int UP>
-__device__ __forceinline__ bool flood_sweep(uint32_t (&R)[8][8], const uint4* band4, int lane) {
-    bool changed = false;
+__device__ __forceinline__ uint32_t flood_sweep(uint32_t (&R)[8][8], const uint4* band4, int lane) {
+    uint32_t changed = 0u;
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
         constexpr int dummy = 0; (void)dummy;
@@ -138,7 +180,7 @@ __device__ __forceinline__ bool flood_sweep(uint32_t (&R)[8][8], const uint4* ba
             run_fill(F, r);
 #pragma unroll
             for (int w = 0; w < 8; ++w) R[i][w] = r[w];
-            changed = true;
+            changed |= 1u << i;
         }
     }
     return changed;
@@ -159,6 +201,7 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
 #pragma unroll
         for (int i = 0; i < BMP_WORDS / 4 / 32; ++i) b4[lane + 32 * i] = zero;
     }
+    __syncwarp();
 
     // 2. rounded landmarks (closing line always uses them; the spline too when round_landmarks)
     fx = fminf(fmaxf(fx, -(float)COORD_CLAMP), (float)COORD_CLAMP);
@@ -241,60 +284,67 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
         {
             const double m1x = __shfl_down_sync(FULL, Mx, 1), m1y = __shfl_down_sync(FULL, My, 1);
             if (lane < KP - 1) {                             // piece coefficients
-                double* c = ws.coef[lane];
-                c[0] = X; c[1] = dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0); c[2] = 0.5 * Mx; c[3] = (m1x - Mx) * ih * (1.0 / 6.0);
-                c[4] = Y; c[5] = dyk - h * (2.0 * My + m1y) * (1.0 / 6.0); c[6] = 0.5 * My; c[7] = (m1y - My) * ih * (1.0 / 6.0);
+                double2* c = reinterpret_cast<double2*>(ws.piece[lane]);
+                c[0] = make_double2(unext, u);
+                c[1] = make_double2(X, dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0));
+                c[2] = make_double2(0.5 * Mx, (m1x - Mx) * ih * (1.0 / 6.0));
+                c[3] = make_double2(Y, dyk - h * (2.0 * My + m1y) * (1.0 / 6.0));
+                c[4] = make_double2(0.5 * My, (m1y - My) * ih * (1.0 / 6.0));
             }
         }
         __syncwarp();
 
-        // 3c/4. evaluate 1000 points (32 consecutive per lane), round, apply the index rules
-        uint32_t pix[32];
-        const int j0 = lane * 32;
-        const double step = 1.0 / (double)(NPTS - 1);       // np.linspace(0, 1, 1000)
+        // 3c/4. evaluate 1000 points (32 consecutive per lane), round half-even, apply the index
+        //       rules and set the pixels on the fly (consecutive points falling into the same
+        //       32-pixel word are merged into one shared-memory atomic).  An index < -256 makes the
+        //       reference's whole assignment raise: then the bitmap is simply cleared again (the
+        //       closing line is drawn afterwards).
+        const int j0 = min(lane * 32, NPTS - 32);           // lane 31 re-draws 24 points of lane 30
+        const double step = 1.0 / (double)(NPTS - 1);       // j * step == np.linspace(0, 1, 1000)[j] exactly
         int piece = 0;
         {
             const double us = (double)j0 * step;
 #pragma unroll
             for (int k = 1; k <= KP - 2; ++k) piece = (us >= ws.u[k]) ? k : piece;
         }
-        double ub = ws.u[piece], un = ws.u[piece + 1];
-        double c0 = ws.coef[piece][0], c1 = ws.coef[piece][1], c2 = ws.coef[piece][2], c3 = ws.coef[piece][3];
-        double e0 = ws.coef[piece][4], e1 = ws.coef[piece][5], e2 = ws.coef[piece][6], e3 = ws.coef[piece][7];
-#pragma unroll
+        double un, ub, c0, c1, c2, c3, e0, e1, e2, e3;
+#define CUB200_LOAD_PIECE()                                                              \
+        {                                                                                \
+            const double2* pc = reinterpret_cast<const double2*>(ws.piece[piece]);       \
+            const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];    \
+            un = q0.x; ub = q0.y; c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;            \
+            e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                  \
+        }
+        CUB200_LOAD_PIECE();
+        uint32_t cur = 0xffffffffu, bits = 0;
+        int lowest = 0;
+#pragma unroll 4
         for (int jj = 0; jj < 32; ++jj) {
-            const int j = min(j0 + jj, NPTS - 1);            // lane 31 repeats the last point
-            const double uj = (j == NPTS - 1) ? 1.0 : (double)j * step;
+            const double uj = (double)(j0 + jj) * step;
             while (piece < KP - 2 && uj >= un) {
                 ++piece;
-                ub = un; un = ws.u[piece + 1];
-                c0 = ws.coef[piece][0]; c1 = ws.coef[piece][1]; c2 = ws.coef[piece][2]; c3 = ws.coef[piece][3];
-                e0 = ws.coef[piece][4]; e1 = ws.coef[piece][5]; e2 = ws.coef[piece][6]; e3 = ws.coef[piece][7];
+                CUB200_LOAD_PIECE();
             }
-            const double s = uj - ub;
-            const double xv = fma(fma(fma(c3, s, c2), s, c1), s, c0);
-            const double yv = fma(fma(fma(e3, s, e2), s, e1), s, e0);
-            int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
-            oob |= (ix < -256) | (iy < -256);
-            ix += (ix < 0) ? 256 : 0;                        // numpy negative index wrap
-            iy += (iy < 0) ? 256 : 0;
-            pix[jj] = ((uint32_t)(iy & 255) << 8) | (uint32_t)(ix & 255);
+            const double sv = uj - ub;
+            const double xv = fma(fma(fma(c3, sv, c2), sv, c1), sv, c0);
+            const double yv = fma(fma(fma(e3, sv, e2), sv, e1), sv, e0);
+            const int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
+            lowest = min(lowest, min(ix, iy));
+            // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
+            const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
+            if (cell != cur) {
+                if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+                cur = cell; bits = 0;
+            }
+            bits |= 1u << (ix & 31);
         }
-        oob = __any_sync(FULL, oob);
-        __syncwarp();                                        // bitmap zeroing visible
-        if (!oob) {
-            uint32_t cur = 0xffffffffu, bits = 0;
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const uint32_t p = pix[jj];
-                const uint32_t cell = p >> 5;                // row * 8 + word
-                if (cell != cur) {
-                    if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
-                    cur = cell; bits = 0;
-                }
-                bits |= 1u << (p & 31);
-            }
-            if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+#undef CUB200_LOAD_PIECE
+        if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+        oob = __any_sync(FULL, lowest < -256);
+        if (oob) {                                           // IndexError in the reference: nothing drawn
+            __syncwarp();
+            uint4* b4 = reinterpret_cast<uint4*>(bmp);
+            for (int i = 0; i < BMP_WORDS / 4 / 32; ++i) b4[lane + 32 * i] = make_uint4(0, 0, 0, 0);
         }
     } else {
         // fallback of contour_spline(): spline = the 21 raw points (already ints when rounded)
@@ -302,11 +352,8 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
         if (lane < KP) {
             ix = min(__double2int_rn(X), 255); iy = min(__double2int_rn(Y), 255);
             oob = (ix < -256) | (iy < -256);
-            ix += (ix < 0) ? 256 : 0;
-            iy += (iy < 0) ? 256 : 0;
         }
         oob = __any_sync(FULL, oob);
-        __syncwarp();
         if (!oob && lane < KP) set_pixel(bmp, iy & 255, ix & 255);
     }
 
@@ -336,6 +383,9 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
 
     // 6. background flood.  Lane owns rows 8*lane .. 8*lane+7; R = reached-from-outside.
     uint32_t R[8][8];
+    uint32_t generic = 0;        // bit i: row i needs the generic run extraction (border rows, rows the
+                                 // vertical flood advanced in)
+    int area = 0;
     const uint4* band4 = reinterpret_cast<const uint4*>(bmp + lane * BAND_STRIDE);
     // 6a. rows are seeded from the left and right frame borders: everything left of the first and
     //     right of the last boundary pixel of the row; rows 0 and 255 are seeded everywhere.
@@ -351,6 +401,7 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
         } else if (border_row) {
 #pragma unroll
             for (int w = 0; w < 8; ++w) R[i][w] = ~B[w];
+            generic |= 1u << i;
         } else {
             // left part: bits below the lowest set bit of the 256-bit row = (B - 1) & ~B
             uint32_t X[8];
@@ -359,11 +410,24 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
             for (int w = 1; w < 8; ++w) asm("subc.cc.u32 %0, %1, 0;" : "=r"(X[w]) : "r"(B[w]));
             // right part: bits above the highest set bit
             bool seen = false;
+            int nlow = 0, nhigh = 0;
 #pragma unroll
             for (int w = 7; w >= 0; --w) {
                 const uint32_t smear = __funnelshift_rc(0xffffffffu, 0u, __clz(B[w]));  // 0 when B[w] == 0
-                R[i][w] = (X[w] & ~B[w]) | (seen ? 0u : ~smear);
+                const uint32_t lo = X[w] & ~B[w], hi = seen ? 0u : ~smear;
+                R[i][w] = lo | hi;
+                nlow += __popc(lo);
+                nhigh += __popc(hi);
                 seen |= (B[w] != 0u);
+            }
+            // An ordinary row holds the single run [first, last boundary pixel] unless the vertical
+            // flood later advances in it: emit it now (+1 at its start, -1 one past its end).
+            const int xs = nlow, xe = 256 - nhigh;
+            area += xe - xs;
+            if (diff_img) {
+                int32_t* drow = diff_img + (lane * 8 + i) * 256;
+                atomicAdd(drow + xs, 1);
+                if (xe < 256) atomicAdd(drow + xe, -1);
             }
         }
     }
@@ -371,14 +435,18 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
     //     (neighbour lanes' edge rows by shuffle), stopping after the first sweep in which no lane
     //     advanced.  Convex-ish contours exit after one quiescent sweep.
     for (;;) {
-        if (!__any_sync(FULL, flood_sweep<0>(R, band4, lane))) break;
-        if (!__any_sync(FULL, flood_sweep<1>(R, band4, lane))) break;
+        uint32_t touched = flood_sweep<0>(R, band4, lane);
+        generic |= touched;
+        if (!__any_sync(FULL, touched != 0u)) break;
+        touched = flood_sweep<1>(R, band4, lane);
+        generic |= touched;
+        if (!__any_sync(FULL, touched != 0u)) break;
     }
 
-    // 7. mask = not reached.  The run boundaries of the mask are the transitions of R along the row
-    //    (virtual R = 1 left of column 0): +1 where the mask starts, -1 one past where it ends.
-    //    area = sum of run lengths = sum(end) - sum(start).
-    int area = 0;
+    // 7. mask = not reached.  Ordinary rows were emitted in 6a.  Rows the vertical flood advanced in
+    //    (concave / self-intersecting samples) take their 6a run back and go, like the frame-border
+    //    rows, through the generic run extraction.
+    const bool top = (lane == 0), bottom = (lane == 31);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = lane * 8 + i;
@@ -387,26 +455,11 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
             o[0] = make_uint4(~R[i][0], ~R[i][1], ~R[i][2], ~R[i][3]);
             o[1] = make_uint4(~R[i][4], ~R[i][5], ~R[i][6], ~R[i][7]);
         }
-        uint32_t t[8];
-        t[0] = R[i][0] ^ __funnelshift_l(0xffffffffu, R[i][0], 1);
-#pragma unroll
-        for (int w = 1; w < 8; ++w) t[w] = R[i][w] ^ __funnelshift_l(R[i][w - 1], R[i][w], 1);
-        const uint32_t tany = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]) | (t[6] | t[7]);
-        if (tany) {
+        if ((generic >> i) & 1u) {
             int32_t* drow = diff_img ? diff_img + row * 256 : nullptr;
-            if (!(R[i][7] >> 31)) area += 256;                   // run reaching column 255 ends at 256
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                uint32_t tw = t[w];
-                while (tw) {
-                    const int b = __ffs(tw) - 1;
-                    tw &= tw - 1;
-                    const int x = 32 * w + b;
-                    const bool start = !((R[i][w] >> b) & 1u);   // mask starts where R drops to 0
-                    area += start ? -x : x;
-                    if (drow) atomicAdd(drow + x, start ? 1 : -1);
-                }
-            }
+            const bool border_row = (top && i == 0) || (bottom && i == 7);
+            if (!border_row) area -= undo_row_span(bmp + lane * BAND_STRIDE + i * 8, drow);
+            area += emit_row_generic(R[i][0], R[i][1], R[i][2], R[i][3], R[i][4], R[i][5], R[i][6], R[i][7], drow);
         }
     }
 #pragma unroll
@@ -427,8 +480,10 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
     const int64_t total = FROM_CONTOURS ? n_samples : n_img * n_samples;
-    const int64_t nwarps = (int64_t)gridDim.x * FW_WARPS;
-    for (int64_t g = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5); g < total; g += nwarps) {
+    // each CTA walks a contiguous chunk of samples, so its 8 warps share the image's factor in L1
+    const int64_t chunk = (total + gridDim.x - 1) / gridDim.x;
+    const int64_t g_end = min(total, (int64_t)(blockIdx.x + 1) * chunk);
+    for (int64_t g = (int64_t)blockIdx.x * chunk + (threadIdx.x >> 5); g < g_end; g += FW_WARPS) {
         float fx = 0.f, fy = 0.f;
         int64_t img;
         if (FROM_CONTOURS) {
