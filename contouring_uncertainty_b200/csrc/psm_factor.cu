@@ -16,121 +16,96 @@
 
 namespace cub200 {
 
-constexpr int PF_THREADS = 128;
+constexpr int PF_THREADS = 256;
 constexpr int P = CUB200_P;   // 42
 constexpr int Z = 34;         // draws of the PSM sampler
 
-__constant__ int c_initial[3] = {0, 10, 20};
-__constant__ int c_level_pts[3][8] = {{5, 15, 0, 0, 0, 0, 0, 0}, {2, 7, 13, 18, 0, 0, 0, 0}, {1, 3, 6, 8, 12, 14, 17, 19}};
-__constant__ int c_level_n[3] = {2, 4, 8};
-__constant__ int c_rest[4] = {4, 9, 11, 16};
-// draw slot of each landmark (order 0,10,20,5,15,2,7,13,18,1,3,6,8,12,14,17,19); -1 = filled
-__constant__ int c_slot[21] = {0, 9, 5, 10, -1, 3, 11, 6, 12, -1, 1, -1, 13, 7, 14, 4, -1, 15, 8, 16, 2};
+// Landmarks in sampling order: initial [0,10,20], levels [5,15], [2,7,13,18], [1,3,6,8,12,14,17,19]
+// (get_points_order, psm.py:43-71), then the four posterior-mean-filled points.  The draw slot of
+// the landmark at position pi < 17 is pi.
+__constant__ int c_order[21] = {0, 10, 20, 5, 15, 2, 7, 13, 18, 1, 3, 6, 8, 12, 14, 17, 19, 4, 9, 11, 16};
 
+// Everything is done in the permuted variable order v = 2*pi + c, so every conditioning set is a
+// prefix [0, n) with n = 6, 10, 18, 34, and ONE right-looking Cholesky sweep serves all levels:
+// after eliminating the first n variables of T = S + s2 I_[0,n) the trailing block holds the
+// posterior covariance Sig_c = S22 - S21 G^-1 S12, and Acc = L21 (L11^-1 At_g) holds the posterior
+// mean map M At_g (At = A / scale, the sampled contour in the scaler's space).
 struct PFShared {
-    double S[P][P];
-    double A[P][Z];
-    double G[Z][Z];
-    double Mt[Z][16];   // solution columns: Mt[q][c], c = 2*(point index in level) + component
+    double T[P][P + 1];     // working matrix (lower part: L; trailing block: Schur complement)
+    double A[P][Z];         // pixel-space map of every variable (row v = permuted variable)
+    double Acc[P][Z];       // sum_k L[v][k] y_k
+    double y[Z];
+    double col[P];
     double scale[P];
     double d[P];
-    int g[Z];
+    int perm[P];
 };
 
-// In-place lower Cholesky of s.G[0..n)[0..n)
-__device__ void cholesky(PFShared& s, int n) {
-    for (int k = 0; k < n; ++k) {
-        if (threadIdx.x == 0) {
-            double v = s.G[k][k];
-            for (int p = 0; p < k; ++p) v -= s.G[k][p] * s.G[k][p];
-            s.G[k][k] = sqrt(v);
-        }
-        __syncthreads();
-        for (int i = k + 1 + threadIdx.x; i < n; i += PF_THREADS) {
-            double v = s.G[i][k];
-            for (int p = 0; p < k; ++p) v -= s.G[i][p] * s.G[k][p];
-            s.G[i][k] = v / s.G[k][k];
-        }
-        __syncthreads();
+__device__ __forceinline__ void pf_init_T(PFShared& s, const double* __restrict__ c0, double sigma2, int n_noise) {
+    for (int i = threadIdx.x; i < P * P; i += PF_THREADS) {
+        const int a = i / P, b = i % P;
+        // pca() covariance about transform(mu): C0 + d d^T          posteriorshapemodel.py:25-27
+        s.T[a][b] = c0[s.perm[a] * P + s.perm[b]] + s.d[a] * s.d[b] + ((a == b && a < n_noise) ? sigma2 : 0.0);
     }
 }
 
-// One level: condition on the ng observed flat indices s.g, produce the rows of A for `npts` points.
-__device__ void psm_level(PFShared& s, int ng, const int* pts, int npts, double sigma2, bool merge,
-                          const float* __restrict__ cov_img) {
+// Eliminate variable k (right-looking): column of L, y_k, rank-1 updates of the trailing block of T
+// and of Acc.  `upto`: rows >= this bound are the only ones whose Acc is still needed (all rows > k
+// are updated in T).
+__device__ __forceinline__ void pf_eliminate(PFShared& s, int k) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < ng * ng; i += PF_THREADS) {
-        const int a = i / ng, b = i % ng;
-        s.G[a][b] = s.S[s.g[a]][s.g[b]] + (a == b ? sigma2 : 0.0);
+    const double lkk = sqrt(s.T[k][k]);
+    const double ilkk = 1.0 / lkk;
+    if (tid < P) s.col[tid] = (tid > k) ? s.T[tid][k] * ilkk : 0.0;
+    else if (tid >= 64 && tid < 64 + Z) {
+        const int e = tid - 64;
+        s.y[e] = (s.A[k][e] / s.scale[k] - s.Acc[k][e]) * ilkk;
     }
     __syncthreads();
-    cholesky(s, ng);
-    const int ncol = 2 * npts;
-    if (tid < ncol) {  // G x = S[g, row]  ->  x = M[row, :]
-        const int row = 2 * pts[tid >> 1] + (tid & 1);
-        for (int i = 0; i < ng; ++i) {
-            double v = s.S[s.g[i]][row];
-            for (int p = 0; p < i; ++p) v -= s.G[i][p] * s.Mt[p][tid];
-            s.Mt[i][tid] = v / s.G[i][i];
-        }
-        for (int i = ng - 1; i >= 0; --i) {
-            double v = s.Mt[i][tid];
-            for (int p = i + 1; p < ng; ++p) v -= s.G[p][i] * s.Mt[p][tid];
-            s.Mt[i][tid] = v / s.G[i][i];
-        }
+    // 2-D thread map (no integer division): lane -> column(s), warp -> rows k+1+w, k+1+w+8, ...
+    const int tx = tid & 31, ty = tid >> 5;
+    for (int a = k + 1 + ty; a < P; a += PF_THREADS / 32) {
+        const double ca = s.col[a];
+        const int b0 = k + 1 + tx, b1 = b0 + 32;
+        if (b0 < P) s.T[a][b0] -= ca * s.col[b0];
+        if (b1 < P) s.T[a][b1] -= ca * s.col[b1];
+        s.Acc[a][tx] += ca * s.y[tx];
+        if (tx + 32 < Z) s.Acc[a][tx + 32] += ca * s.y[tx + 32];
     }
     __syncthreads();
-    // B[c][e] = scale[row_c] * sum_q Mt[q][c] / scale[g[q]] * A[g[q]][e]   -> staged in G (free now)
-    double (*B)[Z] = reinterpret_cast<double (*)[Z]>(&s.G[0][0]);  // needs ncol <= 34 rows: ok (<=16)
-    for (int i = tid; i < ncol * Z; i += PF_THREADS) {
-        const int c = i / Z, e = i % Z;
-        const int row = 2 * pts[c >> 1] + (c & 1);
-        double v = 0.0;
-        for (int q = 0; q < ng; ++q) v += s.Mt[q][c] / s.scale[s.g[q]] * s.A[s.g[q]][e];
-        B[c][e] = v * s.scale[row];
-    }
-    __syncthreads();
-    // per point: merge with the predicted distribution and add the coloured draw
-    for (int i = tid; i < npts * Z; i += PF_THREADS) {
-        const int pi = i / Z, e = i % Z;
-        const int j = pts[pi];
-        if (!merge) {
-            s.A[2 * j][e] = B[2 * pi][e];
-            s.A[2 * j + 1][e] = B[2 * pi + 1][e];
-            continue;
-        }
-        // Sig_c diagonal block, then cov_c = Sig_c * scale (columns)        psm.py:269-272
-        double cc[2][2];
-        for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2; ++b) {
-                double v = s.S[2 * j + a][2 * j + b];
-                for (int q = 0; q < ng; ++q) v -= s.Mt[q][2 * pi + a] * s.S[s.g[q]][2 * j + b];
-                cc[a][b] = v * s.scale[2 * j + b];
-            }
+}
+
+// Level: the points at positions [p0, p1) get  mu_f = mu + G (mu_c - mu) + chol(cov_f) z_slot  with
+// mu_c - mu = scale * Acc, cov_c = Sig_c * scale (columns), G = cov_p (cov_p + cov_c)^-1,
+// cov_f = G cov_c                                                   psm.py:265-285, 424-440
+__device__ __forceinline__ void pf_level(PFShared& s, int p0, int p1, const float* __restrict__ cov_img) {
+    const int n = (p1 - p0) * Z;
+    for (int i = threadIdx.x; i < n; i += PF_THREADS) {
+        const int pi = p0 + i / Z, e = i % Z;
+        const int v0 = 2 * pi, v1 = v0 + 1;
+        const int j = c_order[pi];
+        const double c00 = s.T[v0][v0] * s.scale[v0], c01 = s.T[v0][v1] * s.scale[v1];
+        const double c10 = s.T[v1][v0] * s.scale[v0], c11 = s.T[v1][v1] * s.scale[v1];
         const double p00 = cov_img[4 * j + 0], p01 = cov_img[4 * j + 1], p10 = cov_img[4 * j + 2], p11 = cov_img[4 * j + 3];
-        const double t00 = p00 + cc[0][0], t01 = p01 + cc[0][1], t10 = p10 + cc[1][0], t11 = p11 + cc[1][1];
+        const double t00 = p00 + c00, t01 = p01 + c01, t10 = p10 + c10, t11 = p11 + c11;
         const double idet = 1.0 / (t00 * t11 - t01 * t10);
         const double i00 = t11 * idet, i01 = -t01 * idet, i10 = -t10 * idet, i11 = t00 * idet;
-        // Gm = cov_p inv(T)                                                psm.py:436-437
         const double g00 = p00 * i00 + p01 * i10, g01 = p00 * i01 + p01 * i11;
         const double g10 = p10 * i00 + p11 * i10, g11 = p10 * i01 + p11 * i11;
-        double a0 = g00 * B[2 * pi][e] + g01 * B[2 * pi + 1][e];
-        double a1 = g10 * B[2 * pi][e] + g11 * B[2 * pi + 1][e];
-        const int sl = c_slot[j];
-        if (e == 2 * sl || e == 2 * sl + 1) {
-            // cov_f = Gm cov_c ; lower Cholesky reading the lower triangle (torch.linalg.cholesky)
-            const double f00 = g00 * cc[0][0] + g01 * cc[1][0];
-            const double f10 = g10 * cc[0][0] + g11 * cc[1][0];
-            const double f11 = g10 * cc[0][1] + g11 * cc[1][1];
+        const double b0 = s.scale[v0] * s.Acc[v0][e], b1 = s.scale[v1] * s.Acc[v1][e];
+        double a0 = g00 * b0 + g01 * b1, a1 = g10 * b0 + g11 * b1;
+        if (e == v0 || e == v1) {          // draw slot of position pi is columns (2 pi, 2 pi + 1)
+            // cov_f = G cov_c ; lower Cholesky reading the lower triangle (torch.linalg.cholesky)
+            const double f00 = g00 * c00 + g01 * c10;
+            const double f10 = g10 * c00 + g11 * c10;
+            const double f11 = g10 * c01 + g11 * c11;
             const double l00 = sqrt(f00), l10 = f10 / l00, l11 = sqrt(f11 - l10 * l10);
-            if (e == 2 * sl) { a0 += l00; a1 += l10; }
+            if (e == v0) { a0 += l00; a1 += l10; }
             else { a1 += l11; }
         }
-        s.A[2 * j][e] = a0;
-        s.A[2 * j + 1][e] = a1;
+        s.A[v0][e] = a0;
+        s.A[v1][e] = a1;
     }
-    __syncthreads();
-    if (tid < npts) { s.g[ng + 2 * tid] = 2 * pts[tid]; s.g[ng + 2 * tid + 1] = 2 * pts[tid] + 1; }
     __syncthreads();
 }
 
@@ -146,35 +121,50 @@ psm_factor_kernel(const double* __restrict__ c0, const double* __restrict__ xbar
     const float* cov_i = cov + img * (CUB200_K * 4);
 
     if (tid < P) {
-        s.scale[tid] = sscale[tid];
-        s.d[tid] = xbar[tid] - ((double)mu_i[tid] - smean[tid]) / sscale[tid];  // xbar - transform(mu)
+        const int o = 2 * c_order[tid >> 1] + (tid & 1);      // original flat index of permuted variable
+        s.perm[tid] = o;
+        s.scale[tid] = sscale[o];
+        s.d[tid] = xbar[o] - ((double)mu_i[o] - smean[o]) / sscale[o];  // xbar - transform(mu)
     }
-    for (int i = tid; i < P * Z; i += PF_THREADS) s.A[i / Z][i % Z] = 0.0;
+    for (int i = tid; i < P * Z; i += PF_THREADS) { s.A[i / Z][i % Z] = 0.0; s.Acc[i / Z][i % Z] = 0.0; }
     __syncthreads();
-    for (int i = tid; i < P * P; i += PF_THREADS) {
-        const int a = i / P, b = i % P;
-        s.S[a][b] = c0[i] + s.d[a] * s.d[b];  // pca() covariance about transform(mu)   posteriorshapemodel.py:25-27
-    }
+    pf_init_T(s, c0, 1.0, 6);                                 // sigmas = [1, 1, 1, 1]   psm.py:225
     // initial points: independent draws mu_j + chol(cov_j) z                       psm.py:239
     if (tid < 3) {
-        const int j = c_initial[tid], sl = c_slot[j];
+        const int j = c_order[tid];
         const double p00 = cov_i[4 * j], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
         const double l00 = sqrt(p00), l10 = p10 / l00, l11 = sqrt(p11 - l10 * l10);
-        s.A[2 * j][2 * sl] = l00;
-        s.A[2 * j + 1][2 * sl] = l10;
-        s.A[2 * j + 1][2 * sl + 1] = l11;
-        s.g[2 * tid] = 2 * j;
-        s.g[2 * tid + 1] = 2 * j + 1;
+        s.A[2 * tid][2 * tid] = l00;
+        s.A[2 * tid + 1][2 * tid] = l10;
+        s.A[2 * tid + 1][2 * tid + 1] = l11;
     }
     __syncthreads();
-    int ng = 6;
-    for (int lvl = 0; lvl < 3; ++lvl) {  // sigmas = [1, 1, 1, 1]                     psm.py:225
-        psm_level(s, ng, c_level_pts[lvl], c_level_n[lvl], 1.0, true, cov_i);
-        ng += 2 * c_level_n[lvl];
+    // sweep 1: sigma2 = 1; levels at n = 6, 10, 18
+    for (int k = 0; k < 18; ++k) {
+        if (k == 6 || k == 10) {
+            const int p0 = k >> 1, p1 = (k == 6) ? 5 : 9;
+            pf_level(s, p0, p1, cov_i);
+            if (tid >= 2 * p0 && tid < 2 * p1) s.T[tid][tid] += 1.0;   // the new points join the conditioning set
+            __syncthreads();
+        }
+        pf_eliminate(s, k);
     }
-    psm_level(s, ng, c_rest, 4, 0.001, false, cov_i);  // posterior mean fill         psm.py:355-368
+    pf_level(s, 9, 17, cov_i);
+    // sweep 2: posterior mean of the remaining points given all 17 sampled ones, sigma2 = 0.001   psm.py:355-368
+    pf_init_T(s, c0, 0.001, Z);
+    for (int i = tid; i < P * Z; i += PF_THREADS) s.Acc[i / Z][i % Z] = 0.0;
+    __syncthreads();
+    for (int k = 0; k < Z; ++k) pf_eliminate(s, k);
+    for (int i = tid; i < 8 * Z; i += PF_THREADS) {
+        const int v = Z + i / Z, e = i % Z;
+        s.A[v][e] = s.scale[v] * s.Acc[v][e];
+    }
+    __syncthreads();
     float* out = a_out + img * (Z * P);
-    for (int i = tid; i < Z * P; i += PF_THREADS) out[i] = (float)s.A[i % P][i / P];  // out[e][d]
+    for (int i = tid; i < Z * P; i += PF_THREADS) {
+        const int e = i / P, v = i % P;
+        out[e * P + s.perm[v]] = (float)s.A[v][e];            // out[e][d], d = original flat index
+    }
 }
 
 __global__ void naive_factor_kernel(const float* __restrict__ cov, int64_t n_img, float* __restrict__ a_out) {

@@ -1,0 +1,34 @@
+"""Mirror of contour_uncertainty/data/camus/utils.py::USContourToMask (LV-only branch :43, :85-90)."""
+from typing import Literal
+
+import numpy as np
+import torch
+
+from ... import engine as E
+from ..utils import ContourToMask
+
+
+class USContourToMask(ContourToMask):
+    @staticmethod
+    def __call__(landmarks, shape=(256, 256), labels=None, apply_argmax: bool = True,
+                 reconstruction_type: Literal['spline', 'linear'] = 'spline'):
+        """landmarks (K,2) [or (M,K,2)] -> int64 mask (H,W) [(M,H,W)]; channel axis added when not apply_argmax.
+
+        Rounds the landmarks first, then spline raster + closing line + hole fill (cu/utils/contour.py:28-40).
+        """
+        if reconstruction_type != 'spline':
+            raise NotImplementedError("only reconstruction_type='spline' (the reference default) is on the GPU path")
+        if tuple(shape) != (E.HW, E.HW):
+            raise ValueError("only 256x256 frames are supported")
+        if labels is not None and any(str(l).lower().endswith("myo") for l in labels):
+            raise NotImplementedError("the MYO (two-structure) branch is out of scope (SURVEY.md section 2, #5)")
+        lm = np.asarray(landmarks, dtype=np.float32).squeeze()
+        single = lm.ndim == 2
+        lm = lm.reshape(-1, E.K, 2)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        masks, _ = E.rasterize_contours(torch.from_numpy(lm).to(dev), round_landmarks=True)
+        out = E.unpack_masks(masks).cpu().numpy().astype(np.int64)
+        if single:
+            out = out[0]
+            return out if apply_argmax else out[None]
+        return out if apply_argmax else out[:, None]

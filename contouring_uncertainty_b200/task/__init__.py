@@ -1,0 +1,81 @@
+"""Reference-shaped orchestration of the predict path (no Lightning dependency).
+
+``ContourUncertaintyPipeline`` does what ``AleatoricUncertaintyTask._predict_step`` +
+``ContourUncertaintyTask.predict_step`` do after the network forward
+(cu/task/regression/aleatoric.py:80-135, contour_uncertainty.py:71-82) for T_e epistemic passes
+given as a list of logit tensors, and returns a ``BatchResult``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import engine as E
+from ..data.config import BatchResult
+
+
+def sample_entropy(samples) -> np.ndarray:
+    """UncertaintyTask.sample_entropy (cu/task/uncertainty.py:107-133) for C == 1.
+
+    samples (T,1,H,W) or (T_e,T_a,1,H,W) of 0/1 values -> binary entropy (bits) of the sample mean.
+    The count map is formed by an exact integer sum; the entropy table runs on the GPU (K4).
+    """
+    s = np.asarray(samples)
+    if s.ndim == 5:
+        s = s.reshape((-1,) + s.shape[2:])
+    if s.shape[1] != 1:
+        raise NotImplementedError("multi-class entropy is out of scope (labels = [lv])")
+    T = s.shape[0]
+    count = torch.from_numpy(s[:, 0].astype(np.int32).sum(0, dtype=np.int32))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    count = count.to(dev)
+    diff = torch.zeros((1,) + tuple(count.shape), dtype=torch.int32, device=dev)
+    diff[0, :, 0] = count[:, 0]
+    diff[0, :, 1:] = count[:, 1:] - count[:, :-1]
+    _, _, ent, _ = E.finalize_maps(diff, T, want_count=False)
+    return ent[0].cpu().numpy()
+
+
+def batch_result_from(res: E.UncertaintyResult, img, uncertainty_map=None, gt=None, id="", labels=("lv",),
+                      return_pred_samples: bool = False, **kw) -> BatchResult:
+    n = res.mu.shape[0]
+    T = res.area.shape[1]
+    ent = res.entropy.cpu().numpy()
+    pred_samples = None
+    if return_pred_samples:
+        if res.masks is None:
+            raise ValueError("run the engine with return_masks=True to materialise pred_samples")
+        pred_samples = E.unpack_masks(res.masks).cpu().numpy().astype(np.int64).reshape(n, 1, T, 1, E.HW, E.HW)
+    return BatchResult(
+        id=id, labels=labels, img=np.asarray(img), gt=gt, pred=res.pred.cpu().numpy().astype(np.int64),
+        uncertainty_map=ent if uncertainty_map is None else uncertainty_map, mu=res.mu.cpu().numpy(),
+        mode=res.mu.cpu().numpy(), cov=res.cov.cpu().numpy(),
+        contour_samples=None if res.contour_samples is None else res.contour_samples.cpu().numpy().reshape(n, 1, T, E.K, 2),
+        pred_samples=pred_samples, entropy_map=ent, sample_area=res.area.cpu().numpy().reshape(n, 1, T), **kw)
+
+
+class ContourUncertaintyPipeline:
+    """dsnt-al / dsnt-al2 predict path on logits.  ``covar`` = hparams.covar (config/task/dsnt-al.yaml)."""
+
+    def __init__(self, psm_path: Optional[str] = None, t_a: int = 25, covar: bool = True, sampler: str = "psm",
+                 device="cuda"):
+        self.t_a = t_a
+        self.engine = E.UncertaintyEngine(psm_path or E.DEFAULT_PSM, device=device, sampler=sampler, covar=covar)
+
+    def predict(self, logits_per_model: Sequence[torch.Tensor]):
+        """DSNTAleatoric.predict (dsnt_al.py:133-151): stack T_e passes -> (N,T_e,K,2), (N,T_e,K,2,2)."""
+        S, cov = [], []
+        for lg in logits_per_model:
+            _, mu, sig = E.dsnt_moments(lg, is_logit=True, covar=self.engine.covar)
+            S.append(mu)
+            cov.append(sig)
+        return torch.stack(S, 1), torch.stack(cov, 1)
+
+    def predict_step(self, logits, img=None, seed: int = 0, z=None, return_pred_samples: bool = False, **kw) -> BatchResult:
+        """T_e = 1 path: logits (N,21,256,256) CUDA -> BatchResult."""
+        res = self.engine(logits, self.t_a, z=z, seed=seed, return_masks=return_pred_samples)
+        if img is None:
+            img = np.zeros((logits.shape[0], E.HW, E.HW), dtype=np.float32)
+        return batch_result_from(res, img, return_pred_samples=return_pred_samples, **kw)

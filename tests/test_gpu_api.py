@@ -1,0 +1,106 @@
+"""GPU tests of the reference-shaped Python API (same names / argument meaning as the reference)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_us_contour_to_mask_functor():
+    from contouring_uncertainty_b200.data.camus.utils import USContourToMask
+
+    g = np.load(os.path.join(G, "raster.npz"))
+    want = np.unpackbits(g["masks"], axis=-1, bitorder="little")
+    m = USContourToMask.__call__(g["contours"][3], (256, 256), labels=[], apply_argmax=True)
+    assert m.shape == (256, 256) and m.dtype == np.int64 and np.array_equal(m, want[3])
+    m = USContourToMask.__call__(g["contours"][5][None], (256, 256), labels=[], apply_argmax=False)
+    assert m.shape == (1, 256, 256) and np.array_equal(m[0], want[5])
+    mm = USContourToMask.__call__(g["contours"][:16], (256, 256))
+    assert mm.shape == (16, 256, 256) and np.array_equal(mm, want[:16])
+    with pytest.raises(NotImplementedError):
+        USContourToMask.__call__(g["contours"][0], reconstruction_type="linear")
+
+
+def test_psm_sampler_call_signature_and_replay():
+    from contouring_uncertainty_b200.sampler import PosteriorShapeModelSampler
+
+    g = np.load(os.path.join(G, "psm.npz"))
+    s = PosteriorShapeModelSampler()
+    assert s.initial_points == [0, 10, 20] and s.points_order[0] == [5, 15]
+    mu, cov = torch.from_numpy(g["mu"][1]), torch.from_numpy(g["cov"][1])       # CPU tensors in, like the reference
+    out = s(mu, cov, n=g["z"].shape[1], z=g["z"][1])
+    assert out.shape == (12, 21, 2) and out.dtype == torch.float32 and out.device.type == "cpu"
+    assert np.abs(out.numpy() - g["samples_f64"][1]).max() < 2.6e-4
+    out2 = s(torch.from_numpy(g["mu"]).cuda(), torch.from_numpy(g["cov"]).cuda(), n=5, seed=3)
+    assert out2.shape == (4, 5, 21, 2) and out2.is_cuda
+    # Philox samples follow the affine law: empirical mean ~ mu on the three free points
+    big = s(mu, cov, n=20000, seed=1).double()
+    assert (big.mean(0) - mu.double()).abs().max() < 0.15
+
+
+def test_naive_sampler_matches_reference_with_numpy_colouring():
+    from contouring_uncertainty_b200.sampler import NaiveSampler
+
+    g = np.load(os.path.join(G, "naive.npz"))
+    s = NaiveSampler()
+    out = s(g["mu"][0], g["cov"][0], g["z"].shape[1], z=g["z"][0], colouring=port.naive_colouring(g["cov"][0]))
+    assert out.shape == (16, 21, 2) and out.dtype == np.float64
+    assert np.abs(out - g["samples"][0]).max() < 1e-4
+    big = s(g["mu"][0], g["cov"][0], 20000, seed=2)
+    emp = np.stack([np.cov(big[:, k].T) for k in range(21)])
+    assert np.abs(emp - g["cov"][0]).max() / np.abs(g["cov"][0]).max() < 0.06
+
+
+def test_sample_entropy_and_pipeline_batch_result():
+    from contouring_uncertainty_b200.task import ContourUncertaintyPipeline, sample_entropy
+
+    g = np.load(os.path.join(G, "maps.npz"))
+    p = np.load(os.path.join(G, "psm.npz"))
+    masks = port.convert_to_mask(p["samples"][0])                                # (T,H,W)
+    e = sample_entropy(masks[:, None].astype(float))
+    assert np.abs(e - g["entropy"][0]).max() <= 1e-12
+    e5 = sample_entropy(masks.reshape(3, 4, 1, 256, 256).astype(float))
+    assert np.abs(e5 - g["entropy"][0]).max() <= 1e-12
+
+    pipe = ContourUncertaintyPipeline(t_a=20)
+    logits = torch.from_numpy(synth.heatmap_logits(2, seed=8)).cuda()
+    br = pipe.predict_step(logits, seed=4, return_pred_samples=True, id="patient0001/2CH")
+    assert br.pred.shape == (2, 256, 256) and br.entropy_map.shape == (2, 256, 256)
+    assert br.contour_samples.shape == (2, 1, 20, 21, 2) and br.pred_samples.shape == (2, 1, 20, 1, 256, 256)
+    assert br.mu.shape == (2, 21, 2) and br.cov.shape == (2, 21, 2, 2) and br.sample_area.shape == (2, 1, 20)
+    # the record is self-consistent with the reference's own definitions
+    assert np.array_equal(br.pred, br.pred_samples.mean(axis=(1, 2)).squeeze().round().astype(int))
+    assert np.array_equal(br.sample_area[:, 0], br.pred_samples[:, 0, :, 0].sum((-2, -1)))
+    for i in range(2):
+        o = port.uncertainty_from_samples(br.contour_samples[i, 0])
+        assert np.array_equal(o["pred"], br.pred[i]) and np.abs(o["entropy"] - br.entropy_map[i]).max() <= 1e-12
+    S, cov = pipe.predict([logits, logits])
+    assert S.shape == (2, 2, 21, 2) and cov.shape == (2, 2, 21, 2, 2)
+
+
+def test_dsnt_mirror_functions():
+    from contouring_uncertainty_b200.task.regression.dsnt import utils as U
+
+    logits = torch.from_numpy(synth.heatmap_logits(1, seed=9)).cuda()
+    heat = U.flat_softmax(logits)
+    coords, var, covar = U.dsnt(heat)
+    (c2, v2, cv2), (px, sig) = U.dsnt_from_logits(logits)
+    assert coords.shape == (1, 21, 2) and var.shape == (1, 21, 2) and covar.shape == (1, 21)
+    assert (coords - c2).abs().max() < 2e-6 and ((var - v2).abs() / v2).max() < 2e-5
+    assert (U.normalized_to_pixel_coordinates(c2, 256) - px).abs().max() < 3e-4
+    assert (U.pixel_to_normalized_coordinates(px, 256) - c2).abs().max() < 3e-6
+    o_mu, o_sig = port.dsnt_predict_on_batch(logits.cpu().numpy())
+    assert np.abs(px.cpu().numpy() - o_mu).max() < 2.6e-4
