@@ -192,6 +192,7 @@ def run_ours(args):
 
     import __graft_entry__ as ge
     from contouring_uncertainty_b200 import engine as E
+    from contouring_uncertainty_b200 import parallel as PAR
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,27 +212,33 @@ def run_ours(args):
     eng = E.UncertaintyEngine(device=dev)
     logits = make_logits_on_device(torch, dev, N_IMG, seed=1002 + rank)
     stream = torch.cuda.current_stream(dev)
-    gathered = [torch.empty((N_IMG, T_A), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+    sizes = PAR.shard_sizes(N_IMG * world, world)          # weak scaling: 64 images per rank
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kernel_ms = {"dsnt": [], "psm_factor": [], "fused": [], "finalize": []}
+    ws = eng.workspace(N_IMG, T_A)
 
-    def step(i, timed):
-        e = [ev() for _ in range(5)] if timed else None
-        if timed: e[0].record(stream)
-        _, mu, cov = E.dsnt_moments(logits, is_logit=True, covar=True)
-        if timed: e[1].record(stream)
-        a_t = E.psm_factor(eng.model, mu, cov)
-        if timed: e[2].record(stream)
-        r = E.sample_raster_aggregate(mu, a_t, T_A, seed=1000 + i, return_contours=True)
-        if timed: e[3].record(stream)
-        out = E.finalize_maps(r["diff"], T_A)
-        if timed: e[4].record(stream)
+    def step(i):
+        """One pass of the hot path over the batch: 6 launches of libcub200 into preallocated buffers."""
+        eng.run_into(ws, logits, seed=1000 + i)
         if world > 1:
-            dist.all_gather(gathered, r["area"])
-            stats = torch.stack([r["area"].sum().double(), out[1].sum()])
-            dist.all_reduce(stats)
-        return e, r, out, mu, cov
+            # the path's only exchange: per-image area distributions + dataset-level sums (NCCL)
+            PAR.gather_metric_distributions(ws.area, sizes)
+            PAR.reduce_dataset_stats(torch.stack([ws.area.sum().double(), ws.mean.sum()]))
+
+    def step_evented(i):
+        """Same kernels through the allocating per-op API with an event between them (per-kernel times)."""
+        e = [ev() for _ in range(5)]
+        e[0].record(stream)
+        _, mu, cov = E.dsnt_moments(logits, is_logit=True, covar=True)
+        e[1].record(stream)
+        a_t = E.psm_factor(eng.model, mu, cov)
+        e[2].record(stream)
+        r = E.sample_raster_aggregate(mu, a_t, T_A, seed=1000 + i, return_contours=True, diff=ws.diff.zero_())
+        e[3].record(stream)
+        E.finalize_maps(r["diff"], T_A)
+        e[4].record(stream)
+        return e
 
     def sync_all():
         if world > 1:
@@ -245,64 +252,54 @@ def run_ours(args):
         clocks.start()
         t_wait = time.time()
         while len(clocks.lines) < 3 and time.time() - t_wait < 5.0 and clocks.proc is not None:
-            step(0, False)
+            step(0)
             torch.cuda.synchronize(dev)
     for i in range(args.warmup):
-        step(i, False)
+        step(i)
     sync_all()
     t0, t1 = ev(), ev()
     t0.record(stream)
-    evs = []
     for i in range(args.steps):
-        e, r, out, mu, cov = step(args.warmup + i, True)
-        evs.append(e)
+        step(args.warmup + i)
     t1.record(stream)
     sync_all()
     ms_total = t0.elapsed_time(t1)
+    clk = clocks.stop() if (rank == 0 and not args.no_clocks) else None
+    evs = [step_evented(i) for i in range(min(args.steps, 20))]
+    sync_all()
     for e in evs:
         for name, a, b in (("dsnt", 0, 1), ("psm_factor", 1, 2), ("fused", 2, 3), ("finalize", 3, 4)):
             kernel_ms[name].append(e[a].elapsed_time(e[b]))
-    clk = clocks.stop() if (rank == 0 and not args.no_clocks) else None
     tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_step = float(tt.item()) / args.steps
     value = world * N_IMG * T_A / (ms_step * 1e-3)
+    r = {"contours": ws.contours, "area": ws.area}
 
-    # ---- e2e: public API with HOST (pinned) buffers, H2D + D2H inside the timed region
+    # ---- e2e: public host-buffer API (HostPipeline): pinned host logits in, pinned host results out;
+    #      H2D + kernels + D2H all inside the timed region, every step
+    pipe = E.HostPipeline(eng, N_IMG, T_A, chunk=8, n_streams=2)
     h_logits = torch.empty(logits.shape, dtype=torch.float32, pin_memory=True)
     h_logits.copy_(logits)
-    d_in = torch.empty_like(logits)
-    h_out = {k: torch.empty(s, dtype=d, pin_memory=True) for k, (s, d) in {
-        "mean": ((N_IMG, HW, HW), torch.float64), "entropy": ((N_IMG, HW, HW), torch.float64),
-        "pred": ((N_IMG, HW, HW), torch.uint8), "area": ((N_IMG, T_A), torch.int32),
-        "contours": ((N_IMG, T_A, K, 2), torch.float32), "mu": ((N_IMG, K, 2), torch.float32),
-        "cov": ((N_IMG, K, 2, 2), torch.float32)}.items()}
+    h_out = pipe.host_outputs()
     h2d = h_logits.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in h_out.values())
-
-    def e2e_step(i):
-        d_in.copy_(h_logits, non_blocking=True)
-        res = eng(d_in, T_A, seed=5000 + i, want_count=False)
-        h_out["mean"].copy_(res.mean, non_blocking=True); h_out["entropy"].copy_(res.entropy, non_blocking=True)
-        h_out["pred"].copy_(res.pred, non_blocking=True); h_out["area"].copy_(res.area, non_blocking=True)
-        h_out["contours"].copy_(res.contour_samples, non_blocking=True)
-        h_out["mu"].copy_(res.mu, non_blocking=True); h_out["cov"].copy_(res.cov, non_blocking=True)
-
-    for i in range(max(1, args.warmup // 2)):
-        e2e_step(i)
+    for i in range(3):
+        pipe.run(h_logits, h_out, seed=5000 + i)
     sync_all()
     t0, t1 = ev(), ev()
     t0.record(stream)
-    n_e2e = max(2, min(args.steps, 10))
+    n_e2e = max(3, min(args.steps, 20))
     for i in range(n_e2e):
-        e2e_step(i)
+        pipe.run(h_logits, h_out, seed=6000 + i)
     t1.record(stream)
     sync_all()
     te = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N_IMG * T_A / (float(te.item()) / n_e2e * 1e-3)
+    e2e_check = bool(torch.equal(h_out["area"][-8:], pipe.ws[(N_IMG // 8 - 1) % 2].area.cpu()))
 
     if rank != 0:
         if world > 1:
@@ -347,9 +344,9 @@ def run_ours(args):
         "roofline_dsnt": roof("dsnt"),
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 5 * args.steps,   # dsnt, psm_factor, fused, entropy_lut, finalize per step
         "clocks": clk,
-        "parity_spot_check": parity_ok,
+        "parity_spot_check": parity_ok and e2e_check,
     }
     print(json.dumps(line))
     if world > 1:

@@ -227,6 +227,29 @@ class UncertaintyResult:
     masks: Optional[torch.Tensor] = None  # (N,T,2048) int32 bit-packed
 
 
+class Workspace:
+    """Preallocated device buffers for ``UncertaintyEngine.run_into`` (no allocation per step)."""
+
+    def __init__(self, n_img: int, t_a: int, zdim: int, device, want_count: bool = True, want_contours: bool = True):
+        dev = torch.device(device)
+        f32, i32, f64 = torch.float32, torch.int32, torch.float64
+        self.n_img, self.t_a, self.zdim, self.device = n_img, t_a, zdim, dev
+        self.mu = torch.empty((n_img, K, 2), dtype=f32, device=dev)
+        self.cov = torch.empty((n_img, K, 2, 2), dtype=f32, device=dev)
+        self.a_t = torch.empty((n_img, zdim, P), dtype=f32, device=dev)
+        self.contours = torch.empty((n_img, t_a, K, 2), dtype=f32, device=dev) if want_contours else None
+        self.area = torch.empty((n_img, t_a), dtype=i32, device=dev)
+        self.diff = torch.empty((n_img, HW, HW), dtype=i32, device=dev)
+        self.count = torch.empty((n_img, HW, HW), dtype=i32, device=dev) if want_count else None
+        self.mean = torch.empty((n_img, HW, HW), dtype=f64, device=dev)
+        self.entropy = torch.empty((n_img, HW, HW), dtype=f64, device=dev)
+        self.pred = torch.empty((n_img, HW, HW), dtype=torch.uint8, device=dev)
+        self.lut = torch.empty((t_a + 1,), dtype=f64, device=dev)
+
+    def result(self) -> "UncertaintyResult":
+        return UncertaintyResult(self.mu, self.cov, self.contours, self.area, self.count, self.mean, self.entropy, self.pred)
+
+
 class UncertaintyEngine:
     """heatmap logits -> DSNT -> sampler factor -> fused sample/raster/aggregate -> maps.
 
@@ -254,8 +277,93 @@ class UncertaintyEngine:
         count, mean, ent, pred = finalize_maps(r["diff"], t_a, want_count=want_count)
         return UncertaintyResult(mu, cov, r["contours"], r["area"], count, mean, ent, pred, r["masks"])
 
+    def workspace(self, n_img: int, t_a: int, **kw) -> Workspace:
+        return Workspace(n_img, t_a, Z_PSM if self.sampler == "psm" else Z_NAIVE, self.device, **kw)
+
+    def run_into(self, ws: Workspace, logits: torch.Tensor, seed: int = 0, stream: Optional[torch.cuda.Stream] = None):
+        """The whole path into preallocated buffers: 6 launches (+1 memset), no allocation, no sync.
+
+        ``logits`` must be (ws.n_img,21,256,256) fp32 CUDA contiguous.  Returns ``ws``.
+        """
+        if logits.dtype != torch.float32 or not logits.is_cuda or not logits.is_contiguous() or \
+                tuple(logits.shape) != (ws.n_img, K, HW, HW):
+            raise ValueError(f"logits must be ({ws.n_img},{K},{HW},{HW}) fp32 CUDA contiguous")
+        L = nat.lib()
+        st = (stream or torch.cuda.current_stream(ws.device)).cuda_stream
+        n, T = ws.n_img, ws.t_a
+        with torch.cuda.device(ws.device):
+            nat.check(L.cub200_dsnt_moments(logits.data_ptr(), n * K, HW, HW, 1, int(self.covar), None, ws.mu.data_ptr(),
+                                            ws.cov.data_ptr(), st), "cub200_dsnt_moments")
+            if self.sampler == "psm":
+                m = self.model
+                nat.check(L.cub200_psm_factor(m.c0.data_ptr(), m.xbar.data_ptr(), m.mean.data_ptr(), m.scale.data_ptr(),
+                                              ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "cub200_psm_factor")
+            else:
+                nat.check(L.cub200_naive_factor(ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "cub200_naive_factor")
+            if stream is None:
+                ws.diff.zero_()
+            else:
+                with torch.cuda.stream(stream):
+                    ws.diff.zero_()
+            nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
+                                                       int(seed) & (2**64 - 1), n, T, 1, nat.ptr(ws.contours),
+                                                       ws.area.data_ptr(), ws.diff.data_ptr(), None, st),
+                      "cub200_sample_raster_aggregate")
+            nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), ws.mean.data_ptr(),
+                                             ws.entropy.data_ptr(), ws.pred.data_ptr(), ws.lut.data_ptr(), st),
+                      "cub200_finalize_maps")
+        return ws
+
     def __call__(self, logits: torch.Tensor, t_a: int, z=None, seed: int = 0, return_contours=True,
                  return_masks=False, want_count=True) -> UncertaintyResult:
         _, mu, cov = dsnt_moments(logits, is_logit=True, covar=self.covar)
         return self.from_moments(mu, cov, t_a, z=z, seed=seed, return_contours=return_contours,
                                  return_masks=return_masks, want_count=want_count)
+
+
+class HostPipeline:
+    """Host-buffer entry of the path: pinned host logits in, pinned host results out.
+
+    The batch is cut into chunks that flow through ``n_streams`` CUDA streams, so the host->device
+    copy of chunk i+1 and the device->host copy of chunk i-1 overlap the kernels of chunk i (PCIe is
+    the bottleneck of this entry: 5.5 MB of logits per image).  What the reference does at this
+    boundary is the opposite copy (``S.cpu()``, dsnt_al.py:147-148) followed by seconds of Python.
+    """
+
+    OUT_KEYS = ("mu", "cov", "contours", "area", "mean", "entropy", "pred")
+
+    def __init__(self, engine: UncertaintyEngine, n_img: int, t_a: int, chunk: int = 8, n_streams: int = 2):
+        if n_img % chunk:
+            raise ValueError("n_img must be a multiple of chunk")
+        self.engine, self.n_img, self.t_a, self.chunk = engine, n_img, t_a, chunk
+        dev = engine.device
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+        self.d_in = [torch.empty((chunk, K, HW, HW), dtype=torch.float32, device=dev) for _ in range(n_streams)]
+        self.ws = [engine.workspace(chunk, t_a, want_count=False) for _ in range(n_streams)]
+
+    def host_outputs(self):
+        n, T = self.n_img, self.t_a
+        spec = {"mu": ((n, K, 2), torch.float32), "cov": ((n, K, 2, 2), torch.float32),
+                "contours": ((n, T, K, 2), torch.float32), "area": ((n, T), torch.int32),
+                "mean": ((n, HW, HW), torch.float64), "entropy": ((n, HW, HW), torch.float64),
+                "pred": ((n, HW, HW), torch.uint8)}
+        return {k: torch.empty(s, dtype=d, pin_memory=True) for k, (s, d) in spec.items()}
+
+    def run(self, h_logits: torch.Tensor, h_out: dict, seed: int = 0):
+        """Asynchronous: returns after enqueueing; the caller's current stream waits for the result."""
+        if h_logits.is_cuda or tuple(h_logits.shape) != (self.n_img, K, HW, HW) or h_logits.dtype != torch.float32:
+            raise ValueError(f"h_logits must be a host ({self.n_img},{K},{HW},{HW}) fp32 tensor (pinned for overlap)")
+        cur = torch.cuda.current_stream(self.engine.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for ci, c0 in enumerate(range(0, self.n_img, self.chunk)):
+            si = ci % len(self.streams)
+            st, ws = self.streams[si], self.ws[si]
+            with torch.cuda.stream(st):
+                self.d_in[si].copy_(h_logits[c0:c0 + self.chunk], non_blocking=True)
+                self.engine.run_into(ws, self.d_in[si], seed=seed + ci, stream=st)
+                for k in self.OUT_KEYS:
+                    h_out[k][c0:c0 + self.chunk].copy_(getattr(ws, k), non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return h_out

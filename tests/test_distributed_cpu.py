@@ -1,0 +1,49 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: sharding, ragged gather, dataset reduction."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from contouring_uncertainty_b200 import parallel as P
+
+
+def test_shard_images_keeps_patients_together_and_covers_everything():
+    for n_pat, world, ipp in ((10, 4, 4), (7, 2, 2), (64, 8, 1), (3, 4, 4)):
+        n = n_pat * ipp
+        blocks = [P.shard_images(n, r, world, ipp) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        for (a, b), (c, d) in zip(blocks, blocks[1:]):
+            assert b == c
+        for a, b in blocks:
+            assert a % ipp == 0 and b % ipp == 0
+        sizes = P.shard_sizes(n, world, ipp)
+        assert sum(sizes) == n and max(sizes) - min(sizes) <= ipp
+
+
+def _worker(rank, world, port, n_images, T):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(n_images * T, dtype=torch.int32).reshape(n_images, T)     # "areas" of every image
+        a, b = P.shard_images(n_images, rank, world, images_per_patient=2)
+        sizes = P.shard_sizes(n_images, world, images_per_patient=2)
+        got = P.gather_metric_distributions(full[a:b].clone(), sizes)
+        assert torch.equal(got, full), (rank, got.shape)
+        stats = torch.tensor([float(full[a:b].sum()), float(b - a)], dtype=torch.float64)
+        P.reduce_dataset_stats(stats)
+        assert stats[0].item() == float(full.sum()) and stats[1].item() == n_images
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_and_reduce_world_size_2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    # 5 patients x 2 images over 2 ranks -> ragged shards (6 and 4 images)
+    mp.spawn(_worker, args=(2, port, 10, 7), nprocs=2, join=True)

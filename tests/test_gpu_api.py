@@ -104,3 +104,31 @@ def test_dsnt_mirror_functions():
     assert (U.pixel_to_normalized_coordinates(px, 256) - c2).abs().max() < 3e-6
     o_mu, o_sig = port.dsnt_predict_on_batch(logits.cpu().numpy())
     assert np.abs(px.cpu().numpy() - o_mu).max() < 2.6e-4
+
+
+def test_run_into_and_host_pipeline_match_allocating_path():
+    from contouring_uncertainty_b200 import UncertaintyEngine
+    from contouring_uncertainty_b200.engine import HostPipeline
+
+    dev = torch.device("cuda:0")
+    eng = UncertaintyEngine(device=dev)
+    logits = torch.from_numpy(synth.heatmap_logits(4, seed=15)).to(dev)
+    ref = eng(logits, 30, seed=77)
+    ws = eng.run_into(eng.workspace(4, 30), logits, seed=77)
+    torch.cuda.synchronize()
+    for k in ("mu", "cov", "area", "count", "mean", "entropy", "pred"):
+        assert torch.equal(getattr(ws, k), getattr(ref, k)), k
+    assert torch.equal(ws.contours, ref.contour_samples)
+    # host pipeline: chunks of 2 images on 2 streams; chunk c uses seed + c and restarts the sample index
+    pipe = HostPipeline(eng, 4, 30, chunk=2, n_streams=2)
+    h_in = logits.cpu().pin_memory()
+    h_out = pipe.run(h_in, pipe.host_outputs(), seed=5)
+    torch.cuda.synchronize()
+    for c in range(2):
+        r = eng(logits[2 * c:2 * c + 2].contiguous(), 30, seed=5 + c)
+        assert torch.equal(h_out["area"][2 * c:2 * c + 2], r.area.cpu())
+        assert torch.equal(h_out["pred"][2 * c:2 * c + 2], r.pred.cpu())
+        assert torch.equal(h_out["entropy"][2 * c:2 * c + 2], r.entropy.cpu())
+        assert torch.equal(h_out["contours"][2 * c:2 * c + 2], r.contour_samples.cpu())
+    with pytest.raises(ValueError):
+        pipe.run(logits, h_out)                               # device tensor where host logits are expected
