@@ -202,7 +202,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     if not os.path.exists(E.nat.LIB_PATH):
         if rank == 0:
             ge.build()
@@ -252,7 +253,7 @@ def run_ours(args):
         clocks.start()
         t_wait = time.time()
         while len(clocks.lines) < 3 and time.time() - t_wait < 5.0 and clocks.proc is not None:
-            step(0)
+            eng.run_into(ws, logits, seed=0)          # local work only: no collective outside lock-step
             torch.cuda.synchronize(dev)
     for i in range(args.warmup):
         step(i)
