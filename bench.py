@@ -40,6 +40,16 @@ BYTES_FUSED_PER_IMG = lambda T: T * (168 + 4) + 34 * 42 * 4 + 168
 BYTES_FINAL_PER_IMG = HW * HW * (4 + 4 + 8 + 8 + 1)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01a_ncu_full_summary.csv for dsnt / finalize, profiles/r01d_ncu_full_summary_fused.csv)
+NCU_TRAFFIC = {"dsnt": 352339968 + 4504832, "fused": 5135104 + 450560, "finalize": 19132160 + 35917056, "psm_factor": 113664}
+ROOF_NOTES = {
+    "fused": "NOT HBM-bound by construction (masks never leave shared memory): binding resources are issue slots / ALU "
+             "pipe -- ncu: IPC 2.2 of 4, ALU pipe 39 %, 4875 warp-instructions per sample (DESIGN.md section 3, profiles/r01d_*)",
+    "dsnt": "HBM-bound: every logit read once; DRAM traffic == algorithmic bytes",
+}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -322,7 +332,8 @@ def run_ours(args):
     def roof(k):
         ach = alg_bytes[k] / (km[k] * 1e-3) / 1e9
         return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "ms_per_launch": km[k], "algorithmic_bytes": alg_bytes[k], "peak_source": peak_src}
+                "traffic": NCU_TRAFFIC.get(k), "ms_per_launch": km[k], "algorithmic_bytes": alg_bytes[k],
+                "peak_source": peak_src, "note": ROOF_NOTES.get(k)}
 
     cpu = None
     if world == 1 and not args.no_cpu:

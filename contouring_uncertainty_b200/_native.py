@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcub200.so")
+LIB_PATH = os.environ.get("CUB200_LIB") or os.path.join(_HERE, "lib", "libcub200.so")
 
 EINVAL, ECUDA = -1, -2
 

@@ -30,7 +30,14 @@
 
 namespace cub200 {
 
-constexpr int FW_WARPS = 8;
+#ifndef CUB200_FW_WARPS
+#define CUB200_FW_WARPS 8
+#endif
+#ifndef CUB200_FW_MINBLOCKS
+#define CUB200_FW_MINBLOCKS 2
+#endif
+constexpr int FW_WARPS = CUB200_FW_WARPS;
+constexpr int FW_MINBLOCKS = CUB200_FW_MINBLOCKS;
 constexpr int FW_THREADS = FW_WARPS * 32;
 constexpr int BAND_STRIDE = 68;                 // 8 rows x 8 words + 4 pad words
 constexpr int BMP_WORDS = 32 * BAND_STRIDE;     // 2176
@@ -470,7 +477,7 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
 
 // ---------------------------------------------------------------- kernels
 template <bool FROM_CONTOURS>
-__global__ void __launch_bounds__(FW_THREADS, 2)
+__global__ void __launch_bounds__(FW_THREADS, FW_MINBLOCKS)
 sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim,
                      const float* __restrict__ z, uint64_t seed, int64_t n_img, int64_t n_samples,
                      int round_landmarks, const float* __restrict__ contours_in,
@@ -541,7 +548,7 @@ static int launch_cfg(int64_t total, const void* kernel, int* grid_out) {
     }
     CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
     const int64_t need = (total + FW_WARPS - 1) / FW_WARPS;
-    const int64_t cap = (int64_t)num_sms * 2;   // 2 resident CTAs per SM, grid-stride beyond
+    const int64_t cap = (int64_t)num_sms * FW_MINBLOCKS;   // resident CTAs per SM; each walks a contiguous chunk
     *grid_out = (int)(need < cap ? need : cap);
     return 0;
 }
