@@ -25,10 +25,11 @@ SIGNATURES = {
     "cub200_dsnt_moments": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "cub200_psm_factor": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
-    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
     "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],
+    "cub200_sample_moments": [_vp, _i64, _i64, _vp, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm")
 

@@ -86,7 +86,47 @@ __global__ void fac_kernel(const int32_t* __restrict__ ed, const int32_t* __rest
     out[i] = f;
 }
 
+// post_mu / post_cov of aleatoric.py:96-102: thread (k, sg) streams the float2 of landmark k over the
+// samples sg, sg+12, ...; moments about the first sample (no cancellation), fp64, block reduction.
+constexpr int SM_GROUPS = 12;
+__global__ void __launch_bounds__(CUB200_K * SM_GROUPS)
+sample_moments_kernel(const float* __restrict__ contours, int64_t T, double* __restrict__ mean_out, double* __restrict__ cov_out) {
+    __shared__ double red[SM_GROUPS][CUB200_K][5];
+    const int k = threadIdx.x % CUB200_K, sg = threadIdx.x / CUB200_K;
+    const float2* base = reinterpret_cast<const float2*>(contours) + (int64_t)blockIdx.x * T * CUB200_K + k;
+    const float2 c = base[0];
+    double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+    for (int64_t t = sg; t < T; t += SM_GROUPS) {
+        const float2 p = base[t * CUB200_K];
+        const double dx = (double)p.x - (double)c.x, dy = (double)p.y - (double)c.y;
+        sx += dx; sy += dy; sxx += dx * dx; syy += dy * dy; sxy += dx * dy;
+    }
+    red[sg][k][0] = sx; red[sg][k][1] = sy; red[sg][k][2] = sxx; red[sg][k][3] = syy; red[sg][k][4] = sxy;
+    __syncthreads();
+    if (sg == 0) {
+        double a[5] = {0, 0, 0, 0, 0};
+        for (int g = 0; g < SM_GROUPS; ++g)
+            for (int q = 0; q < 5; ++q) a[q] += red[g][k][q];
+        const double n = (double)T, mx = a[0] / n, my = a[1] / n;
+        const int64_t o = (int64_t)blockIdx.x * CUB200_K + k;
+        mean_out[o * 2 + 0] = (double)c.x + mx;
+        mean_out[o * 2 + 1] = (double)c.y + my;
+        const double den = n - 1.0;                       // np.cov default ddof = 1
+        const double cxx = (a[2] - n * mx * mx) / den, cyy = (a[3] - n * my * my) / den, cxy = (a[4] - n * mx * my) / den;
+        cov_out[o * 4 + 0] = cxx; cov_out[o * 4 + 1] = cxy; cov_out[o * 4 + 2] = cxy; cov_out[o * 4 + 3] = cyy;
+    }
+}
+
 }  // namespace cub200
+
+extern "C" int cub200_sample_moments(const float* contours, int64_t n_img, int64_t n_samples, double* mean_out,
+                                     double* cov_out, void* stream) {
+    using namespace cub200;
+    if (n_img == 0) return 0;
+    if (!contours || !mean_out || !cov_out || n_img < 0 || n_samples < 1 || n_img > 0x7fffffff) return CUB200_EINVAL;
+    sample_moments_kernel<<<(unsigned)n_img, CUB200_K * SM_GROUPS, 0, (cudaStream_t)stream>>>(contours, n_samples, mean_out, cov_out);
+    return check_launch("sample_moments_kernel");
+}
 
 extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
                                     double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,

@@ -492,15 +492,17 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
     const int64_t g_end = min(total, (int64_t)(blockIdx.x + 1) * chunk);
     for (int64_t g = (int64_t)blockIdx.x * chunk + (threadIdx.x >> 5); g < g_end; g += FW_WARPS) {
         float fx = 0.f, fy = 0.f;
-        int64_t img;
+        int64_t img, map;
         if (FROM_CONTOURS) {
             img = per_image > 0 ? g / per_image : 0;
+            map = img;
             if (lane < KP) {
                 const float2 p = reinterpret_cast<const float2*>(contours_in)[g * KP + lane];
                 fx = p.x; fy = p.y;
             }
         } else {
             img = g / n_samples;
+            map = img / per_image;                          // per_image = images_per_map here
             // 1. draws
             if (z) {
                 for (int e = lane; e < zdim; e += 32) ws.z[e] = z[g * zdim + e];
@@ -533,7 +535,7 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
             __syncwarp();
         }
         const int area = raster_sample(ws, fx, fy, round_landmarks != 0,
-                                       diff ? diff + img * 65536 : nullptr,
+                                       diff ? diff + map * 65536 : nullptr,
                                        masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
         if (area_out && lane == 0) area_out[g] = area;
     }
@@ -558,16 +560,17 @@ static int launch_cfg(int64_t total, const void* kernel, int* grid_out) {
 extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
                                               uint64_t seed, int64_t n_img, int64_t n_samples,
                                               int round_landmarks, float* contours_out, int32_t* area_out,
-                                              int32_t* diff, uint32_t* masks_out, void* stream) {
+                                              int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* stream) {
     using namespace cub200;
     if (!mu || !a_t || zdim < 1 || zdim > CUB200_ZMAX || n_img < 0 || n_samples < 0) return CUB200_EINVAL;
+    if (images_per_map < 1 || n_img % images_per_map) return CUB200_EINVAL;
     const int64_t total = n_img * n_samples;
     if (total == 0) return 0;
     int grid = 0;
     int rc = launch_cfg(total, (const void*)sample_raster_kernel<false>, &grid);
     if (rc) return rc;
     sample_raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
-        mu, a_t, zdim, z, seed, n_img, n_samples, round_landmarks, nullptr, contours_out, area_out, diff, masks_out, 0);
+        mu, a_t, zdim, z, seed, n_img, n_samples, round_landmarks, nullptr, contours_out, area_out, diff, masks_out, images_per_map);
     return check_launch("sample_raster_kernel");
 }
 

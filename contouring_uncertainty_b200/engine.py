@@ -111,7 +111,7 @@ def naive_factor(cov: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Optional[torch.Tensor] = None,
                             seed: int = 0, round_landmarks: bool = True, return_contours: bool = True,
-                            return_masks: bool = False, diff: Optional[torch.Tensor] = None):
+                            return_masks: bool = False, diff: Optional[torch.Tensor] = None, images_per_map: int = 1):
     """Fused sampler -> rasteriser -> aggregation.  mu (N,21,2); a_t (N,Z,42); z (N,T,Z) or None.
 
     Returns dict(contours (N,T,21,2) | None, area (N,T) int32, diff (N,256,256) int32,
@@ -133,17 +133,20 @@ def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int,
             raise ValueError(f"z must be ({n},{T},{zdim}), got {tuple(z.shape)}")
     contours = torch.empty((n, T, K, 2), dtype=torch.float32, device=dev) if return_contours else None
     area = torch.empty((n, T), dtype=torch.int32, device=dev)
+    if images_per_map < 1 or n % images_per_map:
+        raise ValueError("N must be a multiple of images_per_map")
+    n_maps = n // images_per_map
     if diff is None:
-        diff = torch.zeros((n, HW, HW), dtype=torch.int32, device=dev)
+        diff = torch.zeros((n_maps, HW, HW), dtype=torch.int32, device=dev)
     else:
         diff = nat.require_cuda(diff, torch.int32, "diff")
-        if tuple(diff.shape) != (n, HW, HW):
-            raise ValueError("diff must be (N,256,256) int32")
+        if tuple(diff.shape) != (n_maps, HW, HW):
+            raise ValueError("diff must be (N / images_per_map,256,256) int32")
     masks = torch.empty((n, T, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
     with torch.cuda.device(dev):
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
                                                       n, T, int(round_landmarks), nat.ptr(contours), nat.ptr(area),
-                                                      nat.ptr(diff), nat.ptr(masks), nat.stream_ptr(dev))
+                                                      nat.ptr(diff), int(images_per_map), nat.ptr(masks), nat.stream_ptr(dev))
     nat.check(rc, "cub200_sample_raster_aggregate")
     return dict(contours=contours, area=area, diff=diff, masks=masks)
 
@@ -209,6 +212,21 @@ def fac_from_areas(area_ed: torch.Tensor, area_es: torch.Tensor) -> torch.Tensor
                                              nat.stream_ptr(area_ed.device))
     nat.check(rc, "cub200_fac_from_areas")
     return out
+
+
+def sample_moments(contours: torch.Tensor):
+    """post_mu / post_cov (aleatoric.py:96-102): contours (..., T, 21, 2) -> mean (...,21,2), cov (...,21,2,2) fp64, ddof=1."""
+    contours = nat.require_cuda(contours, torch.float32, "contours")
+    if contours.dim() < 3 or contours.shape[-2:] != (K, 2):
+        raise ValueError(f"contours must be (..., T, {K}, 2)")
+    lead, T = tuple(contours.shape[:-3]), contours.shape[-3]
+    n = int(np.prod(lead)) if lead else 1
+    mean = torch.empty(lead + (K, 2), dtype=torch.float64, device=contours.device)
+    cov = torch.empty(lead + (K, 2, 2), dtype=torch.float64, device=contours.device)
+    with torch.cuda.device(contours.device):
+        rc = nat.lib().cub200_sample_moments(nat.ptr(contours), n, T, nat.ptr(mean), nat.ptr(cov), nat.stream_ptr(contours.device))
+    nat.check(rc, "cub200_sample_moments")
+    return mean, cov
 
 
 # --------------------------------------------------------------------------------------------------
@@ -307,7 +325,7 @@ class UncertaintyEngine:
                     ws.diff.zero_()
             nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
                                                        int(seed) & (2**64 - 1), n, T, 1, nat.ptr(ws.contours),
-                                                       ws.area.data_ptr(), ws.diff.data_ptr(), None, st),
+                                                       ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, st),
                       "cub200_sample_raster_aggregate")
             nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), ws.mean.data_ptr(),
                                              ws.entropy.data_ptr(), ws.pred.data_ptr(), ws.lut.data_ptr(), st),

@@ -74,8 +74,39 @@ class ContourUncertaintyPipeline:
         return torch.stack(S, 1), torch.stack(cov, 1)
 
     def predict_step(self, logits, img=None, seed: int = 0, z=None, return_pred_samples: bool = False, **kw) -> BatchResult:
-        """T_e = 1 path: logits (N,21,256,256) CUDA -> BatchResult."""
-        res = self.engine(logits, self.t_a, z=z, seed=seed, return_masks=return_pred_samples)
+        """logits (N,21,256,256) CUDA, or a list of T_e such tensors (ensemble / MC-dropout passes) -> BatchResult.
+
+        Follows AleatoricUncertaintyTask._predict_step (aleatoric.py:80-135) + predict_step
+        (contour_uncertainty.py:71-82): T_a samples per (image, pass), masks of all T_e*T_a samples
+        aggregated per image, epistemic + aleatoric covariance, posterior moments of the samples.
+        """
+        passes = list(logits) if isinstance(logits, (list, tuple)) else [logits]
+        te, n, T = len(passes), passes[0].shape[0], self.t_a
+        mu, cov = self.predict(passes)                                  # (N,T_e,K,2), (N,T_e,K,2,2)
+        m2, c2 = mu.reshape(n * te, E.K, 2).contiguous(), cov.reshape(n * te, E.K, 2, 2).contiguous()
+        a_t = self.engine.factor(m2, c2)
+        zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=mu.device).reshape(n * te, T, a_t.shape[1])
+        r = E.sample_raster_aggregate(m2, a_t, T, z=zt, seed=seed, return_masks=return_pred_samples, images_per_map=te)
+        count, mean, ent, pred = E.finalize_maps(r["diff"], te * T)
+        samples = r["contours"].reshape(n, te, T, E.K, 2)
+        # aleatoric.py:90-94 (tiny (N,T_e,K) tensors: plain tensor algebra)
+        mu_mean = mu.mean(1, keepdim=True)
+        d = (mu - mu_mean)[..., None]
+        cov_out = cov.mean(1) + (d * d.transpose(-1, -2)).mean(1)
+        # aleatoric.py:96-108: per-pass sample mean / unbiased covariance (kernel), then the same split
+        pm, pc = E.sample_moments(samples)                              # (N,T_e,K,2), (N,T_e,K,2,2) fp64
+        d = (pm - pm.mean(1, keepdim=True))[..., None]
+        post_cov = pc.mean(1) + (d * d.transpose(-1, -2)).mean(1)
         if img is None:
-            img = np.zeros((logits.shape[0], E.HW, E.HW), dtype=np.float32)
-        return batch_result_from(res, img, return_pred_samples=return_pred_samples, **kw)
+            img = np.zeros((n, E.HW, E.HW), dtype=np.float32)
+        ent_np = ent.cpu().numpy()
+        pred_samples = None
+        if return_pred_samples:
+            pred_samples = E.unpack_masks(r["masks"]).cpu().numpy().astype(np.int64).reshape(n, te, T, 1, E.HW, E.HW)
+        mu_np = mu.mean(1).cpu().numpy()
+        return BatchResult(
+            id=kw.pop("id", ""), labels=kw.pop("labels", ("lv",)), img=np.asarray(img), gt=kw.pop("gt", None),
+            pred=pred.cpu().numpy().astype(np.int64), uncertainty_map=kw.pop("uncertainty_map", ent_np),
+            mu=mu_np, mode=mu_np, cov=cov_out.cpu().numpy(), post_mu=pm.mean(1).cpu().numpy(), post_cov=post_cov.cpu().numpy(),
+            contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent_np,
+            sample_area=r["area"].reshape(n, te, T).cpu().numpy(), **kw)

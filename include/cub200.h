@@ -105,11 +105,13 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *   masks_out    optional (n_img, n_samples, 2048) uint32 bit-packed masks (debug / return_masks)
  *   round_landmarks: 1 = USContourToMask semantics (round landmarks first), 0 = reconstruction()
  *                on the raw float contour (cu/sampler/sampling_example3.py:127)
+ *   images_per_map: consecutive (mu, a_t) entries that aggregate into ONE difference map (the T_e
+ *                epistemic passes of an image, aleatoric.py:71-73); diff is (n_img / images_per_map, 256, 256)
  */
 int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
                                    uint64_t seed, int64_t n_img, int64_t n_samples,
                                    int round_landmarks, float* contours_out, int32_t* area_out,
-                                   int32_t* diff, uint32_t* masks_out, void* stream);
+                                   int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* stream);
 
 /*
  * Rasteriser alone (the same device code as K3, contours given): bit-packed masks out.
@@ -141,6 +143,15 @@ int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, 
  */
 int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_t n, double* fac_out,
                           void* stream);
+
+/*
+ * Posterior moments of the sampled contours: per (image, landmark) the sample mean and the unbiased
+ * 2x2 sample covariance over the T samples.
+ *   replaces  post_mu = contour_samples.mean(axis=2); post_cov = np.cov(...)   cu/task/regression/aleatoric.py:96-102
+ *   contours (n_img, n_samples, 21, 2) fp32 -> mean_out (n_img, 21, 2) fp64, cov_out (n_img, 21, 2, 2) fp64 (ddof = 1)
+ */
+int cub200_sample_moments(const float* contours, int64_t n_img, int64_t n_samples, double* mean_out,
+                          double* cov_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -492,3 +492,31 @@ def uncertainty_from_samples(contour_samples: np.ndarray, shape=(256, 256)):
     pred = mean.round().astype(np.int64)
     return dict(count=masks.sum(0, dtype=np.int64), mean=mean, entropy=ent, pred=pred,
                 area=lv_area(masks), T=T)
+
+
+# --------------------------------------------------------------------------------------------------
+# Epistemic / aleatoric bookkeeping of _predict_step            cu/task/regression/aleatoric.py:90-108
+# --------------------------------------------------------------------------------------------------
+def aleatoric_epistemic_moments(mu: np.ndarray, cov: np.ndarray):
+    """aleatoric.py:90-94: mu (N,T_e,K,2), cov (N,T_e,K,2,2) -> (mu (N,K,2), cov_al + cov_ep (N,K,2,2))."""
+    mu_mean = mu.mean(axis=1, keepdims=True)
+    cov_al = cov.mean(1)
+    d = (mu - mu_mean)[..., None]
+    cov_ep = np.mean(d * np.swapaxes(d, -1, -2), axis=1)
+    return mu.mean(axis=1), cov_al + cov_ep
+
+
+def posterior_moments(contour_samples: np.ndarray):
+    """aleatoric.py:96-108: contour_samples (N,T_e,T_a,K,2) -> post_mu (N,K,2), post_cov (N,K,2,2)."""
+    n, te, _ta, k, _ = contour_samples.shape
+    post_mu = contour_samples.mean(axis=2)
+    post_cov = np.zeros((n, te, k, 2, 2))
+    for idx in range(n):
+        for i in range(te):
+            for kk in range(k):
+                post_cov[idx, i, kk] = np.cov(contour_samples[idx, i, :, kk].reshape(-1, 2).T)
+    post_mu_mean = post_mu.mean(axis=1, keepdims=True)
+    post_cov_al = post_cov.mean(1)
+    d = (post_mu - post_mu_mean)[..., None]
+    post_cov_ep = np.mean(d * np.swapaxes(d, -1, -2), axis=1)
+    return post_mu.mean(axis=1), post_cov_ep + post_cov_al

@@ -132,3 +132,27 @@ def test_run_into_and_host_pipeline_match_allocating_path():
         assert torch.equal(h_out["contours"][2 * c:2 * c + 2], r.contour_samples.cpu())
     with pytest.raises(ValueError):
         pipe.run(logits, h_out)                               # device tensor where host logits are expected
+
+
+def test_predict_step_with_epistemic_passes_matches_oracle():
+    """T_e = 3 passes: aggregation over T_e*T_a samples, epistemic+aleatoric covariance, posterior moments."""
+    from contouring_uncertainty_b200.task import ContourUncertaintyPipeline
+
+    pipe = ContourUncertaintyPipeline(t_a=15)
+    passes = [torch.from_numpy(synth.heatmap_logits(2, seed=30 + e)).cuda() for e in range(3)]
+    br = pipe.predict_step(passes, seed=9, return_pred_samples=True)
+    assert br.contour_samples.shape == (2, 3, 15, 21, 2) and br.pred_samples.shape == (2, 3, 15, 1, 256, 256)
+    mus, covs = zip(*[port.dsnt_predict_on_batch(p.cpu().numpy()) for p in passes])
+    mu_o, cov_o = port.aleatoric_epistemic_moments(np.stack(mus, 1), np.stack(covs, 1))
+    assert np.abs(br.mu - mu_o).max() < 3e-4 and np.abs(br.cov - cov_o).max() < 2e-3
+    pm_o, pc_o = port.posterior_moments(br.contour_samples)
+    assert np.abs(br.post_mu - pm_o).max() < 1e-4                     # reference means in fp32, ours in fp64
+    # the reference's per-pass means are fp32 (numpy mean of a float32 array), which leaks ~1e-5 px^2 into
+    # the epistemic term; ours are fp64
+    assert np.abs(br.post_cov - pc_o).max() < 5e-5 * np.abs(pc_o).max()
+    for i in range(2):
+        masks = port.convert_to_mask(br.contour_samples[i].reshape(-1, 21, 2))
+        assert np.array_equal(masks.reshape(3, 15, 256, 256), br.pred_samples[i, :, :, 0])
+        o = port.maps_from_counts(masks.sum(0, dtype=np.int64), 45)
+        assert np.array_equal(o[2], br.pred[i]) and np.abs(o[1] - br.entropy_map[i]).max() <= 1e-12
+        assert np.array_equal(br.sample_area[i].reshape(-1), masks.reshape(45, -1).sum(1))
