@@ -533,6 +533,7 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
                 if (contours_out) reinterpret_cast<float2*>(contours_out)[g * KP + lane] = make_float2(fx, fy);
             }
             __syncwarp();
+            if (!diff && !area_out && !masks_out) continue;     // sample-only call
         }
         const int area = raster_sample(ws, fx, fy, round_landmarks != 0,
                                        diff ? diff + map * 65536 : nullptr,
@@ -564,6 +565,7 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
     using namespace cub200;
     if (!mu || !a_t || zdim < 1 || zdim > CUB200_ZMAX || n_img < 0 || n_samples < 0) return CUB200_EINVAL;
     if (images_per_map < 1 || n_img % images_per_map) return CUB200_EINVAL;
+    if (!diff && !area_out && !masks_out && !contours_out) return CUB200_EINVAL;
     const int64_t total = n_img * n_samples;
     if (total == 0) return 0;
     int grid = 0;

@@ -151,6 +151,26 @@ def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int,
     return dict(contours=contours, area=area, diff=diff, masks=masks)
 
 
+def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Optional[torch.Tensor] = None,
+                    seed: int = 0) -> torch.Tensor:
+    """Sampling only (K3 without rasterisation): contour = mu + A z -> (N,T,21,2) fp32."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    a_t = nat.require_cuda(a_t, torch.float32, "a_t")
+    n, zdim, T = mu.shape[0], a_t.shape[1], int(n_samples)
+    if mu.shape[1:] != (K, 2) or a_t.shape[0] != n or a_t.shape[2] != P:
+        raise ValueError("mu (N,21,2) / a_t (N,Z,42) expected")
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (n, T, zdim):
+            raise ValueError(f"z must be ({n},{T},{zdim}), got {tuple(z.shape)}")
+    out = torch.empty((n, T, K, 2), dtype=torch.float32, device=mu.device)
+    with torch.cuda.device(mu.device):
+        rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
+                                                      n, T, 1, nat.ptr(out), None, None, 1, None, nat.stream_ptr(mu.device))
+    nat.check(rc, "cub200_sample_raster_aggregate(sample-only)")
+    return out
+
+
 def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, return_masks: bool = True,
                        diff: Optional[torch.Tensor] = None, per_image: int = 0):
     """Rasteriser alone: contours (M,21,2) fp32 -> (masks (M,2048) int32 bit-packed | None, area (M) int32)."""
@@ -211,6 +231,87 @@ def fac_from_areas(area_ed: torch.Tensor, area_es: torch.Tensor) -> torch.Tensor
         rc = nat.lib().cub200_fac_from_areas(nat.ptr(area_ed), nat.ptr(area_es), area_ed.numel(), nat.ptr(out),
                                              nat.stream_ptr(area_ed.device))
     nat.check(rc, "cub200_fac_from_areas")
+    return out
+
+
+class SequenceModelConstants:
+    """Per-model constants of the 84-dim (ED, ES) sequence shape model (sequence_sampler.py:15-24).
+
+    seq_mu / seq_Q are used as stored (the reference does not re-centre them), so for each choice b
+    of the first-sampled instant the conditional-mean map M_b = S[o,g] (S[g,g] + I)^-1 and the 2x2
+    conditional covariances are constants; they are computed here once, in fp64, on the host.
+    """
+
+    def __init__(self, path: str = DEFAULT_SEQ_PSM, device="cuda"):
+        d = np.load(str(path), allow_pickle=True).item()
+        f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+        q = f32(d["Q"])
+        if q.shape != (2 * P, 2 * P):
+            raise ValueError(f"sequence shape model must be {2 * P}-dimensional, got {q.shape}")
+        S = q @ q.T
+        scale = f32(d["scaler_scale"]).reshape(-1)
+        m2t = np.zeros((2, P, P))
+        covc = np.zeros((2, K, 2, 2))
+        for b in (0, 1):
+            g = np.arange(P) + P * b
+            o = np.arange(P) + P * (1 - b)
+            M = np.linalg.solve(S[np.ix_(g, g)] + np.eye(P), S[np.ix_(g, o)]).T          # (o, g)
+            m2t[b] = M.T                                                                  # [e][row]
+            C = (S[np.ix_(o, o)] - M @ S[np.ix_(g, o)]) * scale[o][None, :]               # cov_c *= seq_scale (columns)
+            covc[b] = np.stack([C[2 * i:2 * i + 2, 2 * i:2 * i + 2] for i in range(K)])
+        self.path = str(path)
+        self.device = torch.device(device)
+        t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=self.device)
+        self.m2t, self.covc = t(m2t), t(covc)
+        self.mu, self.mean, self.scale = t(f32(d["mu"]).reshape(-1)), t(f32(d["scaler_mean"]).reshape(-1)), t(scale)
+
+
+def sequence_sample(model: ShapeModelConstants, seq: SequenceModelConstants, mu: torch.Tensor, cov: torch.Tensor,
+                    n_samples: int, z: Optional[torch.Tensor] = None, first_instant: Optional[torch.Tensor] = None,
+                    seed: int = 0) -> torch.Tensor:
+    """SequencePSMSampler (sequence_sampler.py:26-144) for a batch of (ED, ES) pairs.
+
+    mu (Np,2,21,2), cov (Np,2,21,2,2) fp32 CUDA; z (Np,T,2,34) optional draws (z[:,:,0] for the
+    first-sampled instant, z[:,:,1] for the other); first_instant (Np,T) uint8 optional (else
+    Bernoulli(1/2) from torch's generator).  Returns contours (Np, T, 2, 21, 2).
+
+    Pipeline: K2 on both instants -> one PSM sample of every image (sample-only K3) -> seq_condition
+    (84-dim conditioning + merge) -> K2 per (pair, sample) on the merged distribution of the other
+    instant (its PCA is re-centred per sample, psm.py:91) -> sample-only K3.
+    """
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    if mu.dim() != 4 or mu.shape[1:] != (2, K, 2) or cov.shape != mu.shape[:3] + (2, 2):
+        raise ValueError("mu (Np,2,21,2) / cov (Np,2,21,2,2) expected")
+    npair, T, dev = mu.shape[0], int(n_samples), mu.device
+    if first_instant is None:
+        first_instant = (torch.rand((npair, T), device=dev) < 0.5).to(torch.uint8)
+    first_instant = nat.require_cuda(first_instant, torch.uint8, "first_instant")
+    z1 = z2 = None
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (npair, T, 2, Z_PSM):
+            raise ValueError(f"z must be ({npair},{T},2,{Z_PSM})")
+        z1 = z[:, :, 0].repeat_interleave(2, dim=0).contiguous()          # same draws whichever instant goes first
+        z2 = z[:, :, 1].reshape(npair * T, 1, Z_PSM).contiguous()
+    m2, c2 = mu.reshape(2 * npair, K, 2), cov.reshape(2 * npair, K, 2, 2)
+    a_t = psm_factor(model, m2, c2)
+    first_all = sample_contours(m2, a_t, T, z=z1, seed=seed)                 # (2Np,T,21,2)
+    first = torch.empty((npair, T, K, 2), dtype=torch.float32, device=dev)
+    mu_f = torch.empty((npair * T, K, 2), dtype=torch.float32, device=dev)
+    cov_f = torch.empty((npair * T, K, 2, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_seq_condition(nat.ptr(mu), nat.ptr(cov), nat.ptr(first_all), nat.ptr(first_instant), npair, T,
+                                            nat.ptr(seq.m2t), nat.ptr(seq.covc), nat.ptr(seq.mu), nat.ptr(seq.mean),
+                                            nat.ptr(seq.scale), nat.ptr(first), nat.ptr(mu_f), nat.ptr(cov_f),
+                                            nat.stream_ptr(dev))
+    nat.check(rc, "cub200_seq_condition")
+    a2 = psm_factor(model, mu_f, cov_f)                                      # per (pair, sample)
+    second = sample_contours(mu_f, a2, 1, z=z2, seed=seed + 0x9E3779B9).reshape(npair, T, K, 2)
+    fi = first_instant.bool()[..., None, None]
+    out = torch.empty((npair, T, 2, K, 2), dtype=torch.float32, device=dev)
+    out[:, :, 0] = torch.where(fi, second, first)                            # instant 0 is "first" when bit == 0
+    out[:, :, 1] = torch.where(fi, first, second)
     return out
 
 

@@ -98,7 +98,8 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *   mu (n_img, 42) fp32; a_t (n_img, zdim, 42) fp32 (transposed factor), zdim <= 42
  *   z  optional (n_img, n_samples, zdim) fp32 standard-normal draws to replay; NULL -> Philox4x32-10
  *      + Box-Muller keyed by (seed, image, sample)
- *   contours_out optional (n_img, n_samples, 21, 2) fp32 (the API's contour_samples)
+ *   contours_out optional (n_img, n_samples, 21, 2) fp32 (the API's contour_samples).  When area_out,
+ *                diff and masks_out are all NULL the call only samples (no rasterisation).
  *   area_out     optional (n_img, n_samples) int32  mask pixel counts
  *   diff         (n_img, 256, 256) int32, ACCUMULATED into (caller zeroes): +1 where a mask run
  *                starts, -1 one past where it ends; the row prefix sum is the count map
@@ -152,6 +153,25 @@ int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_
  */
 int cub200_sample_moments(const float* contours, int64_t n_img, int64_t n_samples, double* mean_out,
                           double* cov_out, void* stream);
+
+/*
+ * Sequence (ED/ES-coupled) sampler: condition the second instant of every pair on the sampled first one.
+ *   replaces  SequencePSMSampler.sample_two_contours, lines 68-91
+ *             cu/sampler/posterior_shape_model/sequence_sampler.py  (+ merge_priors psm.py:424-440)
+ *   mu (n_pairs, 2, 21, 2), cov (n_pairs, 2, 21, 2, 2) fp32: predicted distributions of (instant 0, instant 1)
+ *   first_samples (n_pairs * 2, n_samples, 21, 2) fp32: a PSM sample of EVERY image (K2 + K3 sample-only)
+ *   first_instant (n_pairs, n_samples) uint8: which instant is sampled first (random.randint(0,1), :47)
+ *   m2t (2, 42, 42) fp64: [b][e][row] = (S[o,g] (S[g,g] + I)^-1)[row][e] of the 84-dim model, g = dims of
+ *        instant b, o = the other instant;  covc (2, 21, 2, 2) fp64: 2x2 blocks of S[o,o] - M S[g,o], columns
+ *        scaled by seq_scale;  seq_mu, seq_mean, seq_scale (84) fp64
+ *   first_out (n_pairs, n_samples, 21, 2): the first-sampled contour;  mu_f_out (n_pairs, n_samples, 21, 2),
+ *   cov_f_out (n_pairs, n_samples, 21, 2, 2): merged distribution of the OTHER instant, to be sampled by a
+ *   second pass of K2 + K3 (sequence_sampler.py:94).
+ */
+int cub200_seq_condition(const float* mu, const float* cov, const float* first_samples, const uint8_t* first_instant,
+                         int64_t n_pairs, int64_t n_samples, const double* m2t, const double* covc,
+                         const double* seq_mu, const double* seq_mean, const double* seq_scale,
+                         float* first_out, float* mu_f_out, float* cov_f_out, void* stream);
 
 #ifdef __cplusplus
 }

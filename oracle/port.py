@@ -520,3 +520,56 @@ def posterior_moments(contour_samples: np.ndarray):
     d = (post_mu - post_mu_mean)[..., None]
     post_cov_ep = np.mean(d * np.swapaxes(d, -1, -2), axis=1)
     return post_mu.mean(axis=1), post_cov_ep + post_cov_al
+
+
+# --------------------------------------------------------------------------------------------------
+# Sequence (ED/ES-coupled) sampler        cu/sampler/posterior_shape_model/sequence_sampler.py
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class SequenceShapeModel:
+    """The pickled dict of ``camus-cont_sequence_psm_11_no_std.npy`` (sequence_sampler.py:15-24):
+    an 84-dim PCA of (ED, ES) contour pairs.  seq_mu / seq_Q are used AS STORED (the per-call
+    re-centring is commented out in the reference, :73-76)."""
+    mu: np.ndarray      # (84,)
+    Q: np.ndarray       # (84, 84)
+    mean: np.ndarray    # scaler_mean (84,)
+    scale: np.ndarray   # scaler_scale (84,)
+
+    @staticmethod
+    def load(path: str) -> "SequenceShapeModel":
+        d = np.load(str(path), allow_pickle=True).item()
+        f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+        return SequenceShapeModel(f32(d["mu"]).reshape(-1), f32(d["Q"]), f32(d["scaler_mean"]), f32(d["scaler_scale"]))
+
+
+def seq_psm_sample(model: ShapeModel, seq: SequenceShapeModel, mu: np.ndarray, cov: np.ndarray,
+                   first_instant: np.ndarray, z: np.ndarray) -> np.ndarray:
+    """sequence_sampler.py:26-50 (``__call__``) + :52-144 (``sample_two_contours``), fp64, draws fed in.
+
+    mu (2,K,2), cov (2,K,2,2); first_instant (n,) in {0,1} (the reference draws random.randint(0,1));
+    z (n, 2, 17, 2): z[:,0] drives the first-sampled instant, z[:,1] the other one.  Returns (n,2,K,2).
+    """
+    mu = np.asarray(mu, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64)
+    K = mu.shape[1]
+    S = seq.Q @ seq.Q.T
+    out = np.zeros((len(first_instant), 2, K, 2))
+    for n, b in enumerate(first_instant):
+        b = int(b)
+        o = 1 - b
+        s = np.zeros((2, K, 2))
+        s[b] = psm_sample(model, mu[b], cov[b], z[n, 0][None])[0]               # :66
+        s_g = np.zeros((2, K, 2))
+        s_g[b] = s[b]
+        s_t = (s_g.reshape(-1) - seq.mean) / seq.scale                          # :70-71
+        g = index_to_flat(range(K) if b == 0 else range(K, 2 * K))              # :73
+        mu_c, cov_c = posterior_shape_model(s_t, g, seq.mu, S, 1.0)             # :80
+        mu_c = (mu_c * seq.scale + seq.mean).reshape(2 * K, 2)                  # :81
+        cov_c = cov_c * seq.scale[None, :]                                      # :82
+        cov_c = np.stack([cov_c[2 * i:2 * i + 2, 2 * i:2 * i + 2] for i in range(2 * K)])
+        mu_f, cov_f = merge_priors(mu.reshape(2 * K, 2), cov.reshape(2 * K, 2, 2), mu_c, cov_c)   # :85
+        mu_f = mu_f.reshape(2, K, 2)
+        cov_f = cov_f.reshape(2, K, 2, 2)
+        s[o] = psm_sample(model, mu_f[o], cov_f[o], z[n, 1][None])[0]           # :94
+        out[n] = s
+    return out

@@ -119,6 +119,60 @@ def golden_psm():
     print("psm.npz", out.shape, "max |s-mu|", np.abs(out - mus[:, None]).max())
 
 
+def golden_seq():
+    """SequencePSMSampler.__call__ with replayed draws and first-instant bits (fp32 and fp64 runs)."""
+    import random
+
+    from contour_uncertainty.sampler.posterior_shape_model.sequence_sampler import SequencePSMSampler
+
+    SEQ_PATH = os.path.join(_refstub.REFERENCE_ROOT, "camus-cont_sequence_psm_11_no_std.npy")
+    rng = np.random.default_rng(51)
+    n_pair, n_s = 3, 8
+    mus, covs = synth.point_distributions(2 * n_pair, seed=52)
+    mus = mus.reshape(n_pair, 2, 21, 2).copy()
+    ctr = mus[:, 1].mean(1, keepdims=True)
+    mus[:, 1] = ctr + (mus[:, 1] - ctr) * 0.8                 # ES = ED shrunk about its centroid
+    covs = covs.reshape(n_pair, 2, 21, 2, 2)
+    z = rng.standard_normal((n_pair, n_s, 2, 17, 2)).astype(np.float32)
+    bits = rng.integers(0, 2, (n_pair, n_s))
+    outs = {}
+    for mode in ("f32", "f64"):
+        orig_float = torch.Tensor.float
+        if mode == "f64":
+            torch.set_default_dtype(torch.float64)
+            torch.Tensor.float = lambda self, *a, **k: self.double()   # sequence_sampler.py:85 casts mu_c/cov_c to fp32
+        try:
+            smp = SequencePSMSampler(PSM_PATH, SEQ_PATH)
+            if mode == "f64":
+                for a in ("mean", "scale", "X_train", "X_val", "mu", "Q", "seq_mu", "seq_Q", "seq_mean", "seq_scale"):
+                    setattr(smp, a, getattr(smp, a).double())
+            res = np.zeros((n_pair, n_s, 2, 21, 2))
+            for i in range(n_pair):
+                draws = [z[i, s, c, d][None].astype(np.float64 if mode == "f64" else np.float32)
+                         for s in range(n_s) for c in range(2) for d in range(17)]
+                it = iter(bits[i].tolist())
+                orig = random.randint
+                random.randint = lambda a, b, _it=it: int(next(_it))
+                try:
+                    with _refstub.replay_standard_normal(draws) as log:
+                        m = torch.from_numpy(mus[i]); c = torch.from_numpy(covs[i])
+                        if mode == "f64":
+                            m, c = m.double(), c.double()
+                        r = smp(m, c, n=n_s)
+                finally:
+                    random.randint = orig
+                assert len(log) == n_s * 34, len(log)
+                res[i] = r.detach().numpy()
+            outs[mode] = res
+        finally:
+            torch.set_default_dtype(torch.float32)
+            torch.Tensor.float = orig_float
+    print("seq fp32-vs-fp64 reference max diff (px)", np.abs(outs["f32"] - outs["f64"]).max())
+    np.savez_compressed(os.path.join(HERE, "seq.npz"), mu=mus, cov=covs, z=z, bits=bits,
+                        samples=outs["f32"].astype(np.float32), samples_f64=outs["f64"])
+    print("seq.npz", outs["f64"].shape)
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -157,6 +211,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq"]
     for w in which:
         globals()["golden_" + w]()

@@ -156,3 +156,31 @@ def test_predict_step_with_epistemic_passes_matches_oracle():
         o = port.maps_from_counts(masks.sum(0, dtype=np.int64), 45)
         assert np.array_equal(o[2], br.pred[i]) and np.abs(o[1] - br.entropy_map[i]).max() <= 1e-12
         assert np.array_equal(br.sample_area[i].reshape(-1), masks.reshape(45, -1).sum(1))
+
+
+def test_sequence_sampler_vs_golden_and_pair_rasterisation():
+    from contouring_uncertainty_b200 import engine as E
+    from contouring_uncertainty_b200.sampler import SequencePSMSampler
+
+    g = np.load(os.path.join(G, "seq.npz"))
+    s = SequencePSMSampler()
+    npair, T = g["z"].shape[:2]
+    # single pair, CPU tensors in -> (n,2,K,2) CPU out, like the reference
+    out = s(torch.from_numpy(g["mu"][0]), torch.from_numpy(g["cov"][0]), n=T, z=g["z"][0], first_instant=g["bits"][0])
+    assert out.shape == (T, 2, 21, 2) and out.device.type == "cpu"
+    # vs the reference's code executed in fp64: the second instant goes through two fp32 hand-overs
+    # (mu_f, cov_f) -> 1e-5 of the 256-px scale
+    assert np.abs(out.numpy() - g["samples_f64"][0]).max() < 2.6e-3
+    assert np.abs(out.numpy() - g["samples"][0]).max() < 0.2                    # verbatim fp32 reference
+    # batched
+    outb = s(torch.from_numpy(g["mu"]).cuda(), torch.from_numpy(g["cov"]).cuda(), n=T, z=g["z"], first_instant=g["bits"])
+    assert outb.shape == (npair, T, 2, 21, 2)
+    assert np.abs(outb.cpu().numpy() - g["samples_f64"]).max() < 2.6e-3
+    # ED/ES coupling: with random bits / Philox the areas of the two instants are positively correlated
+    big = s(torch.from_numpy(g["mu"][:1]).cuda(), torch.from_numpy(g["cov"][:1]).cuda(), n=2000, seed=4)[0]   # (T,2,K,2)
+    cont = big.permute(1, 0, 2, 3).reshape(-1, 21, 2).contiguous()
+    _, area = E.rasterize_contours(cont, return_masks=False)
+    a = area.reshape(2, 2000).double()
+    assert torch.corrcoef(a)[0, 1].item() > 0.3
+    fac = E.fac_from_areas(area[:2000].contiguous(), area[2000:].contiguous())
+    assert torch.isfinite(fac).float().mean().item() > 0.95

@@ -104,3 +104,14 @@ def test_points_order():
     ini, order = port.get_points_order(21, levels=3)
     assert ini == [0, 10, 20]
     assert order == [[5, 15], [2, 7, 13, 18], [1, 3, 6, 8, 12, 14, 17, 19]]
+
+
+def test_sequence_sampler_matches_reference():
+    g = np.load(os.path.join(G, "seq.npz"))
+    data = os.path.join(os.path.dirname(G), "..", "contouring_uncertainty_b200", "data")
+    model = port.ShapeModel.load(os.path.join(data, "camus-cont_psm_11_no_std.npy"))
+    seq = port.SequenceShapeModel.load(os.path.join(data, "camus-cont_sequence_psm_11_no_std.npy"))
+    for i in range(g["mu"].shape[0]):
+        s = port.seq_psm_sample(model, seq, g["mu"][i], g["cov"][i], g["bits"][i], g["z"][i])
+        assert np.abs(s - g["samples_f64"][i]).max() < 1e-7          # the reference's own code run in fp64
+        assert np.abs(s - g["samples"][i]).max() < 0.2               # verbatim fp32 run (its own noise)
