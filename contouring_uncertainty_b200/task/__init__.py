@@ -60,9 +60,12 @@ class ContourUncertaintyPipeline:
     """dsnt-al / dsnt-al2 predict path on logits.  ``covar`` = hparams.covar (config/task/dsnt-al.yaml)."""
 
     def __init__(self, psm_path: Optional[str] = None, t_a: int = 25, covar: bool = True, sampler: str = "psm",
-                 device="cuda"):
+                 device="cuda", sequence_sampler: bool = False, seq_psm_path: Optional[str] = None):
+        """``sequence_sampler`` = hparams.sequence_sampler (aleatoric.py:43-49): consecutive images are
+        (ED, ES) pairs of one view and are sampled jointly through the 84-dim sequence PSM."""
         self.t_a = t_a
         self.engine = E.UncertaintyEngine(psm_path or E.DEFAULT_PSM, device=device, sampler=sampler, covar=covar)
+        self.seq = E.SequenceModelConstants(seq_psm_path or E.DEFAULT_SEQ_PSM, device=self.engine.device) if sequence_sampler else None
 
     def predict(self, logits_per_model: Sequence[torch.Tensor]):
         """DSNTAleatoric.predict (dsnt_al.py:133-151): stack T_e passes -> (N,T_e,K,2), (N,T_e,K,2,2)."""
@@ -84,11 +87,27 @@ class ContourUncertaintyPipeline:
         te, n, T = len(passes), passes[0].shape[0], self.t_a
         mu, cov = self.predict(passes)                                  # (N,T_e,K,2), (N,T_e,K,2,2)
         m2, c2 = mu.reshape(n * te, E.K, 2).contiguous(), cov.reshape(n * te, E.K, 2, 2).contiguous()
-        a_t = self.engine.factor(m2, c2)
-        zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=mu.device).reshape(n * te, T, a_t.shape[1])
-        r = E.sample_raster_aggregate(m2, a_t, T, z=zt, seed=seed, return_masks=return_pred_samples, images_per_map=te)
+        if self.seq is not None:
+            # aleatoric.py:66-69: per pass, the (ED, ES) pairs are sampled jointly; (n,2,K,2) per pair -> (N,T_e,T_a,K,2)
+            if n % 2:
+                raise ValueError("sequence_sampler needs (ED, ES) pairs: an even number of images")
+            per_pass = []
+            for e in range(te):
+                zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=mu.device).reshape(te, n // 2, T, 2, E.Z_PSM)[e].contiguous()
+                sp = E.sequence_sample(self.engine.model, self.seq, mu[:, e].reshape(n // 2, 2, E.K, 2).contiguous(),
+                                       cov[:, e].reshape(n // 2, 2, E.K, 2, 2).contiguous(), T, z=zt, seed=seed + 7919 * e)
+                per_pass.append(sp.permute(0, 2, 1, 3, 4).reshape(n, T, E.K, 2))         # (Np,T,2,..) -> (N,T,..)
+            samples = torch.stack(per_pass, 1).contiguous()                                # (N,T_e,T_a,K,2)
+            diff = torch.zeros((n, E.HW, E.HW), dtype=torch.int32, device=mu.device)
+            masks, area = E.rasterize_contours(samples.reshape(-1, E.K, 2), return_masks=return_pred_samples, diff=diff,
+                                               per_image=te * T)
+            r = dict(diff=diff, area=area, masks=masks)
+        else:
+            a_t = self.engine.factor(m2, c2)
+            zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=mu.device).reshape(n * te, T, a_t.shape[1])
+            r = E.sample_raster_aggregate(m2, a_t, T, z=zt, seed=seed, return_masks=return_pred_samples, images_per_map=te)
+            samples = r["contours"].reshape(n, te, T, E.K, 2)
         count, mean, ent, pred = E.finalize_maps(r["diff"], te * T)
-        samples = r["contours"].reshape(n, te, T, E.K, 2)
         # aleatoric.py:90-94 (tiny (N,T_e,K) tensors: plain tensor algebra)
         mu_mean = mu.mean(1, keepdim=True)
         d = (mu - mu_mean)[..., None]

@@ -21,3 +21,14 @@ def aleatoric_epistemic_uncertainty(metric_mc):
     stds = np.nanstd(metric_mc, axis=-1)
     mean, epi, alea = np.nanmean(means), np.nanstd(means), np.nanmean(stds)
     return mean, alea, epi, epi + alea
+
+
+def fac_mc(sample_area_ed, sample_area_es):
+    """FAC.compute, Monte-Carlo part (results/clinical/view.py:35-78): per sample index
+    (A_ED - A_ES) / A_ED from exact pixel counts, values outside [0, 1] -> NaN."""
+    ed = np.asarray(sample_area_ed, dtype=np.float64)
+    es = np.asarray(sample_area_es, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = (ed - es) / ed
+    f[~((f >= 0) & (f <= 1))] = np.nan
+    return f

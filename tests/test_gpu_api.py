@@ -184,3 +184,25 @@ def test_sequence_sampler_vs_golden_and_pair_rasterisation():
     assert torch.corrcoef(a)[0, 1].item() > 0.3
     fac = E.fac_from_areas(area[:2000].contiguous(), area[2000:].contiguous())
     assert torch.isfinite(fac).float().mean().item() > 0.95
+
+
+def test_pipeline_sequence_sampler_view():
+    """dsnt-al with task.sequence_sampler=True (tmi_scripts/test.sh): one view = (ED, ES)."""
+    from contouring_uncertainty_b200.task import ContourUncertaintyPipeline
+    from contouring_uncertainty_b200.utils.clinical import fac_mc, aleatoric_epistemic_uncertainty
+
+    pipe = ContourUncertaintyPipeline(t_a=40, sequence_sampler=True)
+    logits = torch.from_numpy(synth.heatmap_logits(2, seed=41)).cuda()
+    br = pipe.predict_step(logits, seed=3, return_pred_samples=True)
+    assert br.contour_samples.shape == (2, 1, 40, 21, 2) and br.sample_area.shape == (2, 1, 40)
+    for i in range(2):
+        masks = port.convert_to_mask(br.contour_samples[i, 0])
+        assert np.array_equal(masks, br.pred_samples[i, 0, :, 0])
+        assert np.array_equal(br.sample_area[i, 0], masks.reshape(40, -1).sum(1))
+        o = port.maps_from_counts(masks.sum(0, dtype=np.int64), 40)
+        assert np.array_equal(o[2], br.pred[i]) and np.abs(o[1] - br.entropy_map[i]).max() <= 1e-12
+    f = fac_mc(br.sample_area[0], br.sample_area[1])
+    want = np.array([[port.lv_fac(br.pred_samples[0, 0, k, 0], br.pred_samples[1, 0, k, 0]) for k in range(40)]])
+    want[~((want >= 0) & (want <= 1))] = np.nan
+    assert np.allclose(f, want, equal_nan=True)
+    assert len(aleatoric_epistemic_uncertainty(f)) == 4
