@@ -573,3 +573,134 @@ def seq_psm_sample(model: ShapeModel, seq: SequenceShapeModel, mu: np.ndarray, c
         s[o] = psm_sample(model, mu_f[o], cov_f[o], z[n, 1][None])[0]           # :94
         out[n] = s
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Bivariate skew-normal law                       cu/distributions/bivariateskewnormal.py, bivariatenormal.py
+# --------------------------------------------------------------------------------------------------
+def sym_matrix_pow_2x2(cov: np.ndarray, p: float) -> np.ndarray:
+    """``batch_matrix_pow`` (cu/distributions/utils.py:100-129) for one symmetric positive-definite 2x2:
+    V diag(lambda^p) V^-1.  (The reference goes through ``torch.linalg.eig`` and keeps real parts.)"""
+    w, v = np.linalg.eigh(np.asarray(cov, dtype=np.float64))
+    return (v * w ** p) @ v.T
+
+
+def normal_logpdf(x: np.ndarray, loc: np.ndarray, cov: np.ndarray) -> np.ndarray:
+    """``BivariateNormal.logpdf`` (cu/distributions/bivariatenormal.py:15-32): x (..., 2)."""
+    d = np.asarray(x, dtype=np.float64) - np.asarray(loc, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64)
+    inv = np.linalg.inv(cov)
+    maha = np.einsum("...i,ij,...j->...", d, inv, d)
+    return -math.log(2 * math.pi) - 0.5 * math.log(np.linalg.det(cov)) - 0.5 * maha
+
+
+def skew_logpdf(x: np.ndarray, loc: np.ndarray, cov: np.ndarray, alpha: np.ndarray) -> np.ndarray:
+    """``BivariateSkewNormal.logpdf`` (bivariateskewnormal.py:20-49):
+    log 2 + log N(x; loc, cov) + log(Phi(alpha^T cov^-1/2 (x - loc)) + 1e-7)."""
+    d = np.asarray(x, dtype=np.float64) - np.asarray(loc, dtype=np.float64)
+    w = d @ (np.asarray(alpha, dtype=np.float64) @ sym_matrix_pow_2x2(cov, -0.5))
+    from scipy.special import erf
+
+    cdf = 0.5 * (1 + erf(w / math.sqrt(2)))
+    return math.log(2) + normal_logpdf(x, loc, cov) + np.log(cdf + 1e-7)
+
+
+def skew_grid() -> np.ndarray:
+    """The sampling grid of psm_skew.py:181-185: grid[i, j] = (x = i, y = j) (``indexing='ij'``)."""
+    g = np.arange(256, dtype=np.float64)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    return np.stack([X, Y], -1)
+
+
+def skew_pdf_grid(mu: np.ndarray, cov: np.ndarray, alpha: np.ndarray) -> np.ndarray:
+    """``pdfs`` of ``sample_one_instant`` (psm_skew.py:234-238): (K,256,256) table, [k, x, y].
+    ``alpha`` is used as given (the sampler's sign flip, :232, is applied by the caller)."""
+    g = skew_grid()
+    return np.stack([np.exp(skew_logpdf(g, mu[k], cov[k], alpha[k])) for k in range(mu.shape[0])])
+
+
+def skew_rvs_fast(mu: np.ndarray, cov: np.ndarray, alpha: np.ndarray, z3: np.ndarray) -> np.ndarray:
+    """``BivariateSkewNormal.rvs_fast`` (bivariateskewnormal.py:160-191) for one draw, normals fed in.
+
+    delta = cov alpha / sqrt(1 + alpha^T cov alpha); x = chol([[1, delta^T], [delta, cov]]) z3
+    (MultivariateNormal.sample); x[1:] negated when x[0] <= 0; + mu."""
+    mu, cov, alpha = (np.asarray(a, dtype=np.float64) for a in (mu, cov, alpha))
+    delta = cov @ alpha / math.sqrt(1 + alpha @ cov @ alpha)
+    cs = np.zeros((3, 3))
+    cs[0, 0] = 1
+    cs[1:, 0] = delta
+    cs[0, 1:] = delta
+    cs[1:, 1:] = cov
+    x = np.linalg.cholesky(cs) @ np.asarray(z3, dtype=np.float64)
+    x1 = -x[1:] if x[0] <= 0 else x[1:]
+    return x1 + mu
+
+
+def skew_numerical_sampling(p1: np.ndarray, mu2: np.ndarray, cov2: np.ndarray, q: np.ndarray, store=np.float32):
+    """``numerical_sampling`` (psm_skew.py:45-158) with p1 given and alpha2 = None.
+
+    p = p1 * N(grid; mu2, cov2), normalised; ``torch.multinomial(p, 1)`` == argmax(p / q) with q ~ Exp(1)
+    (ATen's single-draw path; checked against torch in tests/golden/make_golden.py).  When the product
+    vanishes everywhere p / sum(p) is NaN, torch raises and the reference's bare ``except`` returns mu2.
+    ``store`` is the dtype the factors and the product are rounded to (fp32 = the reference's tensors, so
+    the underflow pattern is the reference's).  Returns ((x, y), flat index or -1)."""
+    p2 = np.exp(normal_logpdf(skew_grid(), mu2, cov2)).astype(store)
+    with np.errstate(under="ignore"):
+        p = (np.asarray(p1).astype(store) * p2).astype(store)
+    s = p.sum(dtype=store)
+    if not np.isfinite(s) or s <= 0 or not np.all(np.isfinite(p)):
+        return np.asarray(mu2, dtype=np.float64).copy(), -1
+    p = (p / s).astype(store)
+    with np.errstate(under="ignore", over="ignore"):
+        idx = int(np.argmax(p.reshape(-1) / np.asarray(q).astype(store)))
+    return np.array([idx // 256, idx % 256], dtype=np.float64), idx
+
+
+def skew_psm_sample(model: ShapeModel, mu: np.ndarray, cov: np.ndarray, alpha: np.ndarray, z: np.ndarray,
+                    q_fn, store=np.float32, return_indices: bool = False):
+    """``SkewPosteriorShapeModelSampler.sample_one_instant`` + ``sample_contour`` (psm_skew.py:210-411)
+    for one image, skew_indices = all points, random draws fed in.
+
+    mu (K,2), cov (K,2,2), alpha (K,2) as predicted (the sampler's own alpha * [1,-1], :232, happens
+    here); z (n, 3, 3): the (1,3) normals of ``rvs_fast`` for the initial points 0, 10, 20;
+    ``q_fn(sample, draw)`` -> (65536,) Exp(1) field of the draw-th multinomial of the sample (14 per
+    sample, in level order).  Returns (n, K, 2) [, flat grid indices (n, 14), -1 = fallback to mu_c]."""
+    mu = np.asarray(mu, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64)
+    alpha = np.asarray(alpha, dtype=np.float64) * np.array([1.0, -1.0])     # psm_skew.py:232
+    K = mu.shape[0]
+    mu_t = (mu.reshape(-1) - model.mean) / model.scale
+    S = pca_cov(model.X_train, mu_t)                                        # psm_skew.py:228
+    pdfs = skew_pdf_grid(mu, cov, alpha).astype(store)                      # psm_skew.py:234-238
+    sigmas = [1, 1, 1, 1]
+    out = np.zeros((z.shape[0], K, 2))
+    indices = np.full((z.shape[0], 14), -1, dtype=np.int64)
+    for n in range(z.shape[0]):
+        s = np.zeros((K, 2))
+        sampled = list(model.initial_points)
+        for zi, j in enumerate(model.initial_points):                       # :281 -> :414-448
+            s[j] = skew_rvs_fast(mu[j], cov[j], alpha[j], z[n, zi])
+        di = 0
+        for lvl, points in enumerate(model.points_order):
+            sampled.sort()
+            if len(sampled) == K:
+                break
+            s_t = (s.reshape(-1) - model.mean) / model.scale                # compute_psm :469-491
+            mu_c, cov_c = posterior_shape_model(s_t, index_to_flat(sampled), mu_t, S, sigmas[lvl])
+            mu_c = (mu_c * model.scale + model.mean).reshape(K, 2)
+            cov_c = cov_c * model.scale[None, :]
+            for j in points:                                                # :317-326
+                c2 = cov_c[2 * j:2 * j + 2, 2 * j:2 * j + 2]
+                c2 = np.array([[c2[0, 0], c2[1, 0]], [c2[1, 0], c2[1, 1]]])   # MultivariateNormal reads the lower triangle
+                s[j], indices[n, di] = skew_numerical_sampling(pdfs[j], mu_c[j], c2, q_fn(n, di), store)
+                di += 1
+            sampled.extend(points)
+        sampled.sort()
+        if len(sampled) != K:                                               # :384-395
+            s_t = (s.reshape(-1) - model.mean) / model.scale
+            mu_c, _ = posterior_shape_model(s_t, index_to_flat(sampled), mu_t, S, 0.001)
+            mu_c = (mu_c * model.scale + model.mean).reshape(K, 2)
+            rest = [i for i in range(K) if i not in sampled]
+            s[rest] = mu_c[rest]
+        out[n] = s
+    return (out, indices) if return_indices else out

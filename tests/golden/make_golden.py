@@ -173,6 +173,100 @@ def golden_seq():
     print("seq.npz", outs["f64"].shape)
 
 
+def _skew_inputs(n_s):
+    """3 images x n_s samples.  Image 2 has tight covariances and its last sample replays huge normals
+    for the initial points, so that the shape model's conditional means land far from the predicted
+    landmarks: the product pdf then underflows to 0 everywhere in fp32, torch.multinomial raises and
+    the reference falls back to mu_c (psm_skew.py:135-154)."""
+    mus, covs = synth.point_distributions(3, seed=61)
+    alphas = synth.skew_alphas(3, seed=62)
+    covs[2] *= 0.15
+    z = np.random.default_rng(64).standard_normal((3, n_s, 3, 3)).astype(np.float32)
+    z[2, n_s - 1] = np.array([[1.0, 25.0, -30.0], [0.5, -28.0, 22.0], [2.0, 30.0, 30.0]], dtype=np.float32)
+    return mus, covs, alphas, z
+
+
+def golden_skew():
+    """SkewPosteriorShapeModelSampler.__call__ (psm_skew.py) with the (1,3) normals of rvs_fast replayed
+    and torch.multinomial's exponential race fed from synth.exponential_field; fp32 and fp64 runs."""
+    from contour_uncertainty.sampler.posterior_shape_model.psm_skew import SkewPosteriorShapeModelSampler
+    from contour_uncertainty.distributions.bivariateskewnormal import BivariateSkewNormal
+
+    # torch.multinomial(p, 1) IS argmax(p / Exp(1)) on this torch build (ATen single-draw path)
+    gen = torch.Generator().manual_seed(123)
+    for trial in range(20):
+        p = torch.rand(65536, generator=gen) ** 8
+        torch.manual_seed(1000 + trial)
+        want = torch.multinomial(p, 1)
+        torch.manual_seed(1000 + trial)
+        q = torch.empty_like(p).exponential_(1)
+        assert int(torch.argmax(p / q)) == int(want), "multinomial != exponential race"
+
+    Q_SEED = 63
+    n_img, n_s = 3, 4
+    mus, covs, alphas, z = _skew_inputs(n_s)
+    real_multinomial = torch.multinomial
+    outs, idxs, nfallback = {}, {}, {}
+    for mode in ("f32", "f64"):
+        if mode == "f64":
+            torch.set_default_dtype(torch.float64)
+        try:
+            smp = SkewPosteriorShapeModelSampler(PSM_PATH)
+            if mode == "f64":
+                for a in ("mean", "scale", "X_train", "mu", "Q"):
+                    setattr(smp, a, getattr(smp, a).double())
+            res = np.zeros((n_img, n_s, 21, 2))
+            index_log = []
+            for i in range(n_img):
+                state = {"draw": 0}
+
+                def fake_multinomial(p, n, *a, _i=i, _st=state, **k):
+                    d = _st["draw"]
+                    _st["draw"] += 1
+                    stream = (_i * n_s + d // 14) * 14 + d % 14
+                    try:
+                        real_multinomial(p, n)          # raises exactly when the reference's would
+                    except Exception:
+                        index_log.append(-1)
+                        raise
+                    q = torch.from_numpy(synth.exponential_field(Q_SEED, stream)).to(p.dtype)
+                    idx = torch.argmax(p / q).reshape(1)
+                    index_log.append(int(idx))
+                    return idx
+
+                draws = [z[i, s, d][None].astype(np.float64 if mode == "f64" else np.float32)
+                         for s in range(n_s) for d in range(3)]
+                torch.multinomial = fake_multinomial
+                try:
+                    with _refstub.replay_standard_normal(draws) as log:
+                        m, c, al = (torch.from_numpy(a[i:i + 1]) for a in (mus, covs, alphas))
+                        if mode == "f64":
+                            m, c, al = m.double(), c.double(), al.double()
+                        r = smp(m, c, al, n=n_s)
+                finally:
+                    torch.multinomial = real_multinomial
+                assert len(log) == 3 * n_s and all(sh == (1, 3) for sh in log), log
+                assert state["draw"] == 14 * n_s
+                res[i] = r[0].detach().numpy()
+            outs[mode] = res
+            idxs[mode] = np.array(index_log).reshape(n_img, n_s, 14)
+            nfallback[mode] = int((idxs[mode] < 0).sum())
+            if mode == "f32":
+                al_flip = torch.from_numpy(alphas) * torch.tensor([1., -1.])
+                pdf_sub = np.stack([np.stack([BivariateSkewNormal.pdf(smp.grid_points, torch.from_numpy(mus[i, k]),
+                                                                      torch.from_numpy(covs[i, k]), al_flip[i, k]).numpy()[3::16, 5::16]
+                                              for k in range(21)]) for i in range(n_img)])
+        finally:
+            torch.set_default_dtype(torch.float32)
+    same = (idxs["f32"] == idxs["f64"]).mean()
+    print("skew: fallbacks", nfallback, "fp32-vs-fp64 identical draws", same,
+          "max diff (px)", np.abs(outs["f32"] - outs["f64"]).max())
+    np.savez_compressed(os.path.join(HERE, "skew.npz"), mu=mus, cov=covs, alpha=alphas, z=z, q_seed=Q_SEED,
+                        samples=outs["f32"].astype(np.float32), samples_f64=outs["f64"],
+                        indices=idxs["f32"], indices_f64=idxs["f64"], pdf_sub=pdf_sub.astype(np.float32))
+    print("skew.npz", outs["f32"].shape)
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -211,6 +305,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew"]
     for w in which:
         globals()["golden_" + w]()

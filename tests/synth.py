@@ -103,3 +103,27 @@ def raster_cases(seed, n_random=160):
         cases.append(ctr + (base - ctr) * s)
         tags.append("tiny")
     return cases, tags
+
+
+def _splitmix64(x):
+    """SplitMix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def exponential_field(seed, stream, n=H * W):
+    """(n,) fp32 Exp(1) variates of replay stream ``stream`` -- the ``q`` of torch.multinomial's
+    exponential race (argmax(p / q)).  Counter-based and numpy-version independent, so the 256 KB
+    fields of the skew-sampler fixtures are regenerated from (seed, stream) instead of stored."""
+    with np.errstate(over="ignore"):
+        ctr = np.arange(n, dtype=np.uint64) + np.uint64(stream) * np.uint64(1 << 20)
+        bits = _splitmix64(ctr ^ _splitmix64(np.full(n, seed, dtype=np.uint64)))
+    u = ((bits >> np.uint64(40)).astype(np.float64) + 0.5) / float(1 << 24)
+    return (-np.log(u)).astype(np.float32)
+
+
+def skew_alphas(n_img, seed, scale=2.0):
+    """(n_img, K, 2) fp32 skewness vectors ~ N(0, scale^2)."""
+    return np.random.default_rng(seed).normal(0, scale, (n_img, K, 2)).astype(np.float32)

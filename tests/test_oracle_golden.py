@@ -115,3 +115,39 @@ def test_sequence_sampler_matches_reference():
         s = port.seq_psm_sample(model, seq, g["mu"][i], g["cov"][i], g["bits"][i], g["z"][i])
         assert np.abs(s - g["samples_f64"][i]).max() < 1e-7          # the reference's own code run in fp64
         assert np.abs(s - g["samples"][i]).max() < 0.2               # verbatim fp32 run (its own noise)
+
+
+def _skew_q(g, i, n_s):
+    return lambda n, d: synth.exponential_field(int(g["q_seed"]), (i * n_s + n) * 14 + d)
+
+
+@pytest.mark.parametrize("img", [0, 2])
+def test_skew_sampler_matches_reference(img):
+    """psm_skew.py with the rvs_fast normals and the multinomial's exponential race replayed.  Grid indices
+    are exact against both the verbatim fp32 run (incl. its 3 underflow fallbacks on image 2) and the fp64
+    run of the same code; the fp64 run pins the float parts to 1e-9 px."""
+    g = np.load(os.path.join(G, "skew.npz"))
+    model = port.ShapeModel.load(os.path.join(os.path.dirname(G), "..", "contouring_uncertainty_b200", "data",
+                                              "camus-cont_psm_11_no_std.npy"))
+    n_s = g["z"].shape[1]
+    s32, i32 = port.skew_psm_sample(model, g["mu"][img], g["cov"][img], g["alpha"][img], g["z"][img],
+                                    _skew_q(g, img, n_s), store=np.float32, return_indices=True)
+    assert np.array_equal(i32, g["indices"][img])
+    assert (g["indices"][2] < 0).sum() == 3
+    assert np.abs(s32 - g["samples"][img]).max() < 5e-2          # the reference's own fp32 PSM noise on the 4 filled points
+    if img == 0:
+        s64, i64 = port.skew_psm_sample(model, g["mu"][img], g["cov"][img], g["alpha"][img], g["z"][img],
+                                        _skew_q(g, img, n_s), store=np.float64, return_indices=True)
+        assert np.array_equal(i64, g["indices_f64"][img])
+        assert np.abs(s64 - g["samples_f64"][img]).max() < 1e-9
+
+
+def test_skew_pdf_table_matches_reference():
+    g = np.load(os.path.join(G, "skew.npz"))
+    al = g["alpha"] * np.array([1.0, -1.0])
+    for i in range(3):
+        tab = port.skew_pdf_grid(g["mu"][i], g["cov"][i], al[i])[:, 3::16, 5::16]
+        ref = g["pdf_sub"][i]
+        assert np.abs(tab - ref).max() < 2e-8
+        big = ref > 1e-6
+        assert (np.abs(tab - ref) / ref)[big].max() < 5e-5       # fp32 exp of a fp32 exponent of magnitude ~15
