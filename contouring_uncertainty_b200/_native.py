@@ -31,6 +31,9 @@ SIGNATURES = {
     "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],
     "cub200_sample_moments": [_vp, _i64, _i64, _vp, _vp, _vp],
     "cub200_seq_condition": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cub200_skew_pdf_grid": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    "cub200_psm_conditionals": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cub200_skew_sample": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm")
 

@@ -167,6 +167,72 @@ psm_factor_kernel(const double* __restrict__ c0, const double* __restrict__ xbar
     }
 }
 
+// ---------------------------------------------------------------- conditional maps (skew path)
+// The skew-normal sampler (psm_skew.py:247-411) draws every level point from a GRID pdf, so its contour
+// is not affine in Gaussian draws; what stays constant per image is the shape model's conditional law
+// of each level given the already-sampled points (compute_psm, psm_skew.py:469-491):
+//     mu_c[v] = mu[v] + sum_{e < n} Mc[v][e] (s[e] - mu[e]),      cov_c = 2x2 blocks of Sig_c * scale
+// The same right-looking sweep as above with A = identity (the sampled values themselves are the
+// free variables) yields Mc; rows/columns are in the permuted (sampling) order.
+//   mc_t (n_img, 34, 36) fp64: [e][v - 6], v = 6..41 (level points at positions 3..16, then the four
+//        posterior-mean-filled points with sigma2 = 1e-3); zero for e >= the level's prefix
+//   covc (n_img, 14, 3) fp64: (c00, c10, c11) of positions 3..16 (MultivariateNormal reads the lower
+//        triangle, psm_skew.py:78)
+__device__ __forceinline__ void pc_emit(PFShared& s, int p0, int p1, int n, double* __restrict__ mc, double* __restrict__ cc) {
+    const int rows = 2 * (p1 - p0);
+    for (int i = threadIdx.x; i < rows * Z; i += PF_THREADS) {
+        const int v = 2 * p0 + i / Z, e = i % Z;
+        mc[e * 36 + (v - 6)] = (e < n) ? s.scale[v] * s.Acc[v][e] : 0.0;
+    }
+    if (cc) {
+        for (int pi = p0 + threadIdx.x; pi < p1; pi += PF_THREADS) {
+            const int v0 = 2 * pi, v1 = v0 + 1;
+            cc[(pi - 3) * 3 + 0] = s.T[v0][v0] * s.scale[v0];
+            cc[(pi - 3) * 3 + 1] = s.T[v1][v0] * s.scale[v0];
+            cc[(pi - 3) * 3 + 2] = s.T[v1][v1] * s.scale[v1];
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PF_THREADS)
+psm_cond_kernel(const double* __restrict__ c0, const double* __restrict__ xbar, const double* __restrict__ smean,
+                const double* __restrict__ sscale, const float* __restrict__ mu, double* __restrict__ mc_t,
+                double* __restrict__ covc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PFShared& s = *reinterpret_cast<PFShared*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t img = blockIdx.x;
+    const float* mu_i = mu + img * P;
+    double* mc = mc_t + img * (Z * 36);
+    double* cc = covc + img * (14 * 3);
+    if (tid < P) {
+        const int o = 2 * c_order[tid >> 1] + (tid & 1);
+        s.perm[tid] = o;
+        s.scale[tid] = sscale[o];
+        s.d[tid] = xbar[o] - ((double)mu_i[o] - smean[o]) / sscale[o];
+    }
+    for (int i = tid; i < P * Z; i += PF_THREADS) { s.A[i / Z][i % Z] = (i / Z == i % Z) ? 1.0 : 0.0; s.Acc[i / Z][i % Z] = 0.0; }
+    __syncthreads();
+    pf_init_T(s, c0, 1.0, 6);                                 // sigmas = [1, 1, 1, 1]   psm_skew.py:270
+    __syncthreads();
+    for (int k = 0; k < 18; ++k) {
+        if (k == 6 || k == 10) {
+            const int p0 = k >> 1, p1 = (k == 6) ? 5 : 9;
+            pc_emit(s, p0, p1, k, mc, cc);
+            if (tid >= 2 * p0 && tid < 2 * p1) s.T[tid][tid] += 1.0;
+            __syncthreads();
+        }
+        pf_eliminate(s, k);
+    }
+    pc_emit(s, 9, 17, 18, mc, cc);
+    pf_init_T(s, c0, 0.001, Z);                               // psm_skew.py:388
+    for (int i = tid; i < P * Z; i += PF_THREADS) s.Acc[i / Z][i % Z] = 0.0;
+    __syncthreads();
+    for (int k = 0; k < Z; ++k) pf_eliminate(s, k);
+    pc_emit(s, 17, 21, Z, mc, nullptr);
+}
+
 __global__ void naive_factor_kernel(const float* __restrict__ cov, int64_t n_img, float* __restrict__ a_out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one (image, landmark)
     if (i >= n_img * CUB200_K) return;
@@ -208,4 +274,21 @@ extern "C" int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out
     const int64_t n = n_img * CUB200_K;
     naive_factor_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cov, n_img, a_out);
     return check_launch("naive_factor_kernel");
+}
+
+extern "C" int cub200_psm_conditionals(const double* model_c0, const double* model_xbar, const double* scaler_mean,
+                                       const double* scaler_scale, const float* mu, int64_t n_img, double* mc_t,
+                                       double* covc, void* stream) {
+    using namespace cub200;
+    if (!model_c0 || !model_xbar || !scaler_mean || !scaler_scale || !mu || !mc_t || !covc || n_img < 0) return CUB200_EINVAL;
+    if (n_img == 0) return 0;
+    if (n_img > 0x7fffffff) return CUB200_EINVAL;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUB200_CUDA_OK(cudaFuncSetAttribute(psm_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PFShared)));
+        attr_set = true;
+    }
+    psm_cond_kernel<<<(unsigned)n_img, PF_THREADS, sizeof(PFShared), (cudaStream_t)stream>>>(
+        model_c0, model_xbar, scaler_mean, scaler_scale, mu, mc_t, covc);
+    return check_launch("psm_cond_kernel");
 }

@@ -331,6 +331,84 @@ def sample_moments(contours: torch.Tensor):
 
 
 # --------------------------------------------------------------------------------------------------
+# Skew-normal path (dsnt-skew)
+# --------------------------------------------------------------------------------------------------
+N_DRAW_SKEW = 14      # multinomial draws per sample (level points)
+
+
+def skew_pdf_grid(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, flip_alpha_y: bool = False) -> torch.Tensor:
+    """BivariateSkewNormal.pdf on the 256x256 integer grid (bivariateskewnormal.py:20-49; the ``pdfs``
+    loop of psm_skew.py:234-238).  mu (...,2), cov (...,2,2), alpha (...,2) -> (...,256,256) fp32,
+    table[x, y] (``indexing='ij'``)."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    alpha = nat.require_cuda(alpha, torch.float32, "alpha")
+    lead = tuple(mu.shape[:-1])
+    if mu.shape[-1] != 2 or tuple(cov.shape) != lead + (2, 2) or tuple(alpha.shape) != lead + (2,):
+        raise ValueError("mu (...,2) / cov (...,2,2) / alpha (...,2) expected")
+    n = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead + (HW, HW), dtype=torch.float32, device=mu.device)
+    with torch.cuda.device(mu.device):
+        rc = nat.lib().cub200_skew_pdf_grid(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, int(flip_alpha_y), nat.ptr(out),
+                                            nat.stream_ptr(mu.device))
+    nat.check(rc, "cub200_skew_pdf_grid")
+    return out
+
+
+def psm_conditionals(model: ShapeModelConstants, mu: torch.Tensor):
+    """Per-image conditional maps of the shape model (compute_psm, psm_skew.py:469-491):
+    mu (N,21,2) -> (mc_t (N,34,36) fp64, covc (N,14,3) fp64), see include/cub200.h."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    if mu.dim() != 3 or mu.shape[1:] != (K, 2):
+        raise ValueError(f"mu must be (N,{K},2)")
+    n = mu.shape[0]
+    mc = torch.empty((n, Z_PSM, 36), dtype=torch.float64, device=mu.device)
+    cc = torch.empty((n, N_DRAW_SKEW, 3), dtype=torch.float64, device=mu.device)
+    with torch.cuda.device(mu.device):
+        rc = nat.lib().cub200_psm_conditionals(nat.ptr(model.c0), nat.ptr(model.xbar), nat.ptr(model.mean), nat.ptr(model.scale),
+                                               nat.ptr(mu), n, nat.ptr(mc), nat.ptr(cc), nat.stream_ptr(mu.device))
+    nat.check(rc, "cub200_psm_conditionals")
+    return mc, cc
+
+
+def skew_sample(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, n_samples: int,
+                z: Optional[torch.Tensor] = None, expo: Optional[torch.Tensor] = None, seed: int = 0,
+                return_indices: bool = False, pdfs: Optional[torch.Tensor] = None):
+    """SkewPosteriorShapeModelSampler.__call__ (psm_skew.py:187-411) for a batch of images.
+
+    mu (N,21,2), cov (N,21,2,2), alpha (N,21,2) fp32 CUDA as predicted.  z (N,T,3,3): normals of
+    rvs_fast; expo (N,T,14,65536): Exp(1) fields of the multinomial races (both optional: Philox).
+    Returns contours (N,T,21,2) [, indices (N,T,14) int32, -1 = fell back to mu_c]."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    alpha = nat.require_cuda(alpha, torch.float32, "alpha")
+    if mu.dim() != 3 or mu.shape[1:] != (K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,) or alpha.shape != mu.shape:
+        raise ValueError("mu (N,21,2) / cov (N,21,2,2) / alpha (N,21,2) expected")
+    n, T, dev = mu.shape[0], int(n_samples), mu.device
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (n, T, 3, 3):
+            raise ValueError(f"z must be ({n},{T},3,3)")
+    if expo is not None:
+        expo = nat.require_cuda(expo, torch.float32, "expo")
+        if tuple(expo.shape) != (n, T, N_DRAW_SKEW, HW * HW):
+            raise ValueError(f"expo must be ({n},{T},{N_DRAW_SKEW},{HW * HW})")
+    if pdfs is None:
+        pdfs = skew_pdf_grid(mu, cov, alpha, flip_alpha_y=True)
+    elif tuple(pdfs.shape) != (n, K, HW, HW):
+        raise ValueError("pdfs must be (N,21,256,256)")
+    mc, cc = psm_conditionals(model, mu)
+    out = torch.empty((n, T, K, 2), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, T, N_DRAW_SKEW), dtype=torch.int32, device=dev) if return_indices else None
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_skew_sample(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), nat.ptr(pdfs), nat.ptr(mc), nat.ptr(cc),
+                                          nat.ptr(z), nat.ptr(expo), int(seed) & (2**64 - 1), n, T, nat.ptr(out), nat.ptr(idx),
+                                          nat.stream_ptr(dev))
+    nat.check(rc, "cub200_skew_sample")
+    return (out, idx) if return_indices else out
+
+
+# --------------------------------------------------------------------------------------------------
 # End-to-end engine
 # --------------------------------------------------------------------------------------------------
 @dataclass

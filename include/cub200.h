@@ -173,6 +173,49 @@ int cub200_seq_condition(const float* mu, const float* cov, const float* first_s
                          const double* seq_mu, const double* seq_mean, const double* seq_scale,
                          float* first_out, float* mu_f_out, float* cov_f_out, void* stream);
 
+/*
+ * Skew-normal grid pdf tables: table[d][x][y] = 2 N((x,y); mu_d, cov_d) (Phi(alpha_d^T cov_d^-1/2 ((x,y) - mu_d)) + 1e-7)
+ * on the integer grid x, y = 0..255 (torch.meshgrid(indexing='ij'), psm_skew.py:181-185).
+ *   replaces  BivariateSkewNormal.pdf / logpdf / affine / unit_normal_logcdf  cu/distributions/bivariateskewnormal.py:20-49
+ *             BivariateNormal.logpdf                                          cu/distributions/bivariatenormal.py:15-32
+ *             batch_matrix_pow(cov, -0.5)                                     cu/distributions/utils.py:100-129
+ *             the `pdfs` loop of sample_one_instant                           cu/sampler/posterior_shape_model/psm_skew.py:234-238
+ *   mu (n_dist,2), cov (n_dist,2,2), alpha (n_dist,2) fp32; flip_alpha_y != 0 applies the sampler's
+ *   alpha * [1,-1] (psm_skew.py:232); pdf_out (n_dist,256,256) fp32.
+ */
+int cub200_skew_pdf_grid(const float* mu, const float* cov, const float* alpha, int64_t n_dist, int flip_alpha_y,
+                         float* pdf_out, void* stream);
+
+/*
+ * Conditional maps of the posterior shape model per image (the part of compute_psm that does not depend
+ * on the sampled values): mu_c = mu + Mc (s - mu) over the already-sampled coordinates, and the 2x2
+ * conditional covariances of the 14 level points.
+ *   replaces  pca + posterior_shape_model + compute_psm   cu/sampler/posterior_shape_model/posteriorshapemodel.py:9-81,
+ *                                                         psm_skew.py:228,469-491 (and the sigma2 = 1e-3 fill, :384-395)
+ *   mu (n_img,21,2) fp32;  mc_t (n_img,34,36) fp64 = [e][v-6] in sampling order (points 0,10,20 | 5,15 | 2,7,13,18 |
+ *   1,3,6,8,12,14,17,19 | 4,9,11,16; variable v = 2*position + coordinate);  covc (n_img,14,3) fp64 = (c00,c10,c11).
+ */
+int cub200_psm_conditionals(const double* model_c0, const double* model_xbar, const double* scaler_mean,
+                            const double* scaler_scale, const float* mu, int64_t n_img, double* mc_t, double* covc,
+                            void* stream);
+
+/*
+ * Skew-normal posterior-shape-model sampler, one warp per sample.
+ *   replaces  SkewPosteriorShapeModelSampler.__call__ / sample_one_instant / sample_contour   psm_skew.py:187-411
+ *             numerical_sampling (torch.multinomial == exponential race argmax(p / q))       psm_skew.py:45-158
+ *             BivariateSkewNormal.rvs_fast                                                   bivariateskewnormal.py:160-191
+ *   mu, cov, alpha (n_img,21,..) fp32 as predicted (the kernel applies alpha * [1,-1]); pdfs (n_img,21,256,256)
+ *   from cub200_skew_pdf_grid(flip_alpha_y = 1); mc_t, covc from cub200_psm_conditionals.
+ *   z    optional (n_img, n_samples, 3, 3) fp32: the (1,3) normals of rvs_fast for points 0, 10, 20
+ *   expo optional (n_img, n_samples, 14, 65536) fp32 Exp(1) fields of the 14 multinomial draws (level order);
+ *        NULL -> Philox4x32-10 keyed by (seed, sample, draw, cell)
+ *   contours_out (n_img, n_samples, 21, 2) fp32; indices_out optional (n_img, n_samples, 14) int32 flat grid
+ *   index x*256 + y of every draw, -1 where the product pdf vanished and mu_c was taken (psm_skew.py:135-154).
+ */
+int cub200_skew_sample(const float* mu, const float* cov, const float* alpha, const float* pdfs, const double* mc_t,
+                       const double* covc, const float* z, const float* expo, uint64_t seed, int64_t n_img,
+                       int64_t n_samples, float* contours_out, int32_t* indices_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
