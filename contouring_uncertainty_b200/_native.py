@@ -34,8 +34,10 @@ SIGNATURES = {
     "cub200_skew_pdf_grid": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],
     "cub200_psm_conditionals": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_skew_sample": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _vp, _vp],
+    "cub200_simpson_diameters": [_vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp],
+    "cub200_simpson_volumes": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
 }
-QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm")
+QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes")
 
 
 class NativeError(RuntimeError):
@@ -57,6 +59,8 @@ def lib() -> C.CDLL:
             fn.restype = C.c_int
         l.cub200_last_error.restype = C.c_char_p
         l.cub200_last_error.argtypes = []
+        l.cub200_simpson_workspace_bytes.restype = C.c_int64
+        l.cub200_simpson_workspace_bytes.argtypes = [_i64]
         l.cub200_abi_version.restype = C.c_int
         l.cub200_built_for_sm.restype = C.c_int
         _lib = l

@@ -1,0 +1,330 @@
+// Simpson's biplane volumes from sampled masks: marching-squares contour -> base chord -> apex ->
+// 20 disc diameters per mask, then EDV / ESV / EF per Monte-Carlo sample.
+//
+// Replaces (reference paths):
+//   skimage.measure.find_contours(mask, 0.5)[0]       (third party; restated, see oracle/port.py::find_contours)
+//   _compute_diameters / _find_distance_to_edge / _distance_line_to_points / _get_angle_of_lines_to_point
+//                                                     vital/vital/metrics/evaluate/clinical/heart_us.py:74-167
+//   compute_left_ventricle_volumes / _compute_left_ventricle_volume_by_instant        heart_us.py:13-71
+//   the Monte-Carlo loop of Volume.compute            contour_uncertainty/results/clinical/patient.py:166-190
+//
+// find_contours()[0] of a binary mask is the boundary component that owns the raster-first
+// marching-squares segment; its point list follows the segment direction and starts at the to-point of
+// the component's raster-LAST segment (that segment closes the loop in _assemble_contours) or, for a
+// component cut by the frame (no padding), at the chain's open start.  All points lie on half-pixel
+// positions, so they are stored exactly as (2 row, 2 col) uint16 pairs and every comparison of the
+// chord search (angle <= 45 deg, distance-to-line <= 8 px, longest chord, farthest apex) is done in
+// exact integer arithmetic; the ray marching that measures the discs repeats the reference's fp64
+// operations one by one (no FMA contraction).
+#include "common.cuh"
+
+namespace cub200 {
+
+constexpr int SP_NMAX = CUB200_SIMPSON_MAX_POINTS;   // contour points kept per mask
+constexpr int SP_WARPS = 4;
+
+// to-edge of the segment that STARTS at edge f (to_of_from) / from-edge of the segment that ENDS at
+// edge t (from_of_to), per square case (bit 0 ul, 1 ur, 2 ll, 3 lr; 'low' vertex connectivity).
+// Edges: 0 top, 1 bottom, 2 left, 3 right; 9 = no such segment.
+__constant__ unsigned char c_to_of_from[16][4] = {
+    {9, 9, 9, 9}, {2, 9, 9, 9}, {9, 9, 9, 0}, {9, 9, 9, 2}, {9, 9, 1, 9}, {1, 9, 9, 9}, {9, 9, 1, 0}, {9, 9, 9, 1},
+    {9, 3, 9, 9}, {2, 3, 9, 9}, {9, 0, 9, 9}, {9, 2, 9, 9}, {9, 9, 3, 9}, {3, 9, 9, 9}, {9, 9, 0, 9}, {9, 9, 9, 9}};
+__constant__ unsigned char c_from_of_to[16][4] = {
+    {9, 9, 9, 9}, {9, 9, 0, 9}, {3, 9, 9, 9}, {9, 9, 3, 9}, {9, 2, 9, 9}, {9, 0, 9, 9}, {3, 2, 9, 9}, {9, 3, 9, 9},
+    {9, 9, 9, 1}, {9, 9, 0, 1}, {1, 9, 9, 9}, {9, 9, 1, 9}, {9, 9, 9, 2}, {9, 9, 9, 0}, {2, 9, 9, 9}, {9, 9, 9, 9}};
+// from-edge of the FIRST segment a cell generates (cases 6 and 9 generate two)
+__constant__ unsigned char c_first_from[16] = {9, 0, 3, 3, 2, 0, 3, 3, 1, 0, 1, 1, 2, 0, 2, 9};
+
+__device__ __forceinline__ int mask_bit(const uint32_t* __restrict__ m, int r, int c) {
+    return (m[r * 8 + (c >> 5)] >> (c & 31)) & 1u;
+}
+__device__ __forceinline__ int cell_case(const uint32_t* __restrict__ m, int r0, int c0) {
+    return mask_bit(m, r0, c0) | (mask_bit(m, r0, c0 + 1) << 1) | (mask_bit(m, r0 + 1, c0) << 2) | (mask_bit(m, r0 + 1, c0 + 1) << 3);
+}
+// a cell's second segment (saddle cases): the one starting at L (case 6) / B (case 9)
+__device__ __forceinline__ int seg_rank(int cs, int from_edge) {
+    return (cs == 6 && from_edge == 2) || (cs == 9 && from_edge == 1);
+}
+__device__ __forceinline__ uint32_t edge_point(int r0, int c0, int e) {
+    // half-pixel units: top (2r0, 2c0+1), bottom (2r0+2, 2c0+1), left (2r0+1, 2c0), right (2r0+1, 2c0+2)
+    const int r2 = 2 * r0 + (e == 0 ? 0 : e == 1 ? 2 : 1);
+    const int c2 = 2 * c0 + (e == 2 ? 0 : e == 3 ? 2 : 1);
+    return (uint32_t)r2 | ((uint32_t)c2 << 16);
+}
+
+// ---------------------------------------------------------------- S1: contour tracing, one thread per mask
+__global__ void __launch_bounds__(128)
+contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, uint32_t* __restrict__ pts, int32_t* __restrict__ npts) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_masks) return;
+    const uint32_t* m = masks + g * CUB200_MASK_WORDS;
+    uint32_t* out = pts + g * SP_NMAX;
+    // raster-first cell that generates a segment
+    int fr = -1, fc = -1;
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a[w] = m[w];
+    for (int r0 = 0; r0 < 255 && fr < 0; ++r0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) b[w] = m[(r0 + 1) * 8 + w];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t a1 = (a[w] >> 1) | ((w < 7 ? a[w < 7 ? w + 1 : 7] : 0u) << 31);
+            const uint32_t b1 = (b[w] >> 1) | ((w < 7 ? b[w < 7 ? w + 1 : 7] : 0u) << 31);
+            uint32_t nu = (a[w] ^ b[w]) | (a[w] ^ a1) | (b[w] ^ b1);
+            if (w == 7) nu &= 0x7fffffffu;                       // there is no cell at c0 = 255
+            if (nu && fr < 0) { fr = r0; fc = 32 * w + __ffs(nu) - 1; }
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a[w] = b[w];
+    }
+    if (fr < 0) { npts[g] = 0; return; }                          // find_contours() == [] -> IndexError
+    // pass A: walk backwards from the first segment to the chain start, or around the loop
+    const int cs0 = cell_case(m, fr, fc);
+    const int f0 = c_first_from[cs0];
+    int r0 = fr, c0 = fc, fe = f0;                                // current segment = (cell, from-edge)
+    int sr = fr, sc = fc, sf = f0;                                // start segment of pass B
+    bool closed = false;
+    int last_key = -1, lr = 0, lc = 0, lt = 0;                    // raster-last segment of the loop
+    for (int it = 0; it < 4 * SP_NMAX; ++it) {
+        const int cs = cell_case(m, r0, c0);
+        const int te = c_to_of_from[cs][fe];
+        const int key = ((r0 * 255 + c0) << 1) | seg_rank(cs, fe);
+        if (key > last_key) { last_key = key; lr = r0; lc = c0; lt = te; }
+        // predecessor: the cell across the from-edge, whose segment ends on the shared edge
+        int pr = r0, pc = c0, pe;
+        if (fe == 0) { pr = r0 - 1; pe = 1; } else if (fe == 1) { pr = r0 + 1; pe = 0; }
+        else if (fe == 2) { pc = c0 - 1; pe = 3; } else { pc = c0 + 1; pe = 2; }
+        if (pr < 0 || pr > 254 || pc < 0 || pc > 254) { sr = r0; sc = c0; sf = fe; break; }   // open chain start
+        const int pf = c_from_of_to[cell_case(m, pr, pc)][pe];
+        r0 = pr; c0 = pc; fe = pf;
+        if (r0 == fr && c0 == fc && fe == f0) { closed = true; break; }
+    }
+    if (closed) {
+        // the loop starts at the to-point of its raster-last segment: first segment of pass B is the one after it
+        int nr = lr, nc = lc, ne;
+        if (lt == 0) { nr = lr - 1; ne = 1; } else if (lt == 1) { nr = lr + 1; ne = 0; }
+        else if (lt == 2) { nc = lc - 1; ne = 3; } else { nc = lc + 1; ne = 2; }
+        sr = nr; sc = nc; sf = ne;
+    }
+    // pass B: forward, recording points
+    int n = 0;
+    r0 = sr; c0 = sc; fe = sf;
+    out[n++] = edge_point(r0, c0, fe);
+    bool overflow = false;
+    for (;;) {
+        const int cs = cell_case(m, r0, c0);
+        const int te = c_to_of_from[cs][fe];
+        if (n >= SP_NMAX) { overflow = true; break; }
+        out[n++] = edge_point(r0, c0, te);
+        int nr = r0, nc = c0, ne;
+        if (te == 0) { nr = r0 - 1; ne = 1; } else if (te == 1) { nr = r0 + 1; ne = 0; }
+        else if (te == 2) { nc = c0 - 1; ne = 3; } else { nc = c0 + 1; ne = 2; }
+        if (nr < 0 || nr > 254 || nc < 0 || nc > 254) break;       // open chain end
+        r0 = nr; c0 = nc; fe = ne;
+        if (closed && r0 == sr && c0 == sc && fe == sf) break;
+    }
+    npts[g] = overflow ? -1 : n;
+}
+
+// ---------------------------------------------------------------- S2: base chord, apex, discs; one warp per mask
+struct Chord {
+    int len2;   // squared length in half-pixel units
+    int i, j;
+};
+__device__ __forceinline__ bool chord_better(const Chord& a, const Chord& b) {   // is a better than b
+    if (a.len2 != b.len2) return a.len2 > b.len2;
+    if (a.i != b.i) return a.i < b.i;                 // first in (i, j) loop order wins ties (strict '<' in the reference)
+    return a.j < b.j;
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict__ pts_g, const int32_t* __restrict__ npts,
+                         int64_t n_masks, double spacing, double* __restrict__ diam_out, double* __restrict__ step_out) {
+    __shared__ uint32_t s_pts[SP_WARPS][SP_NMAX];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int64_t g = blockIdx.x * (int64_t)SP_WARPS + wid;
+    if (g >= n_masks) return;
+    const int n = npts[g];
+    double* dout = diam_out + g * 20;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (n < 3) {                                       // no contour / no chord: the reference raises
+        if (lane < 20) dout[lane] = qnan;
+        if (lane == 0) step_out[g] = qnan;
+        return;
+    }
+    uint32_t* P = s_pts[wid];
+    for (int k = lane; k < n; k += 32) P[k] = pts_g[g * SP_NMAX + k];
+    __syncwarp();
+    // ---- longest admissible chord (heart_us.py:127-146)
+    Chord best{0, 0x7fffffff, 0x7fffffff};
+    for (int i = 2; i < n; ++i) {
+        const int ir = P[i] & 0xffff, ic = P[i] >> 16;
+        for (int j = lane; j < i; j += 32) {
+            const int ar = (int)(P[j] & 0xffff) - ir, ac = (int)(P[j] >> 16) - ic;     // contour[j] - contour[i]
+            // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
+            if (!(ac > 0 && abs(ar) <= ac)) continue;
+            const int len2 = ar * ar + ac * ac;
+            if (len2 <= best.len2) continue;           // cannot beat this lane's best: skip the intermediate test
+            const int64_t lim = 256ll * len2;          // (8 px)^2 * len2 in half-pixel units: cross^2 <= 256 len2
+            bool ok = true;
+            {   // most far-away chords fail at the middle of the span: test it first
+                const int k = (i + j) >> 1;
+                if (k > j) {
+                    const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);
+                    const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
+                    ok = cr * cr <= lim;
+                }
+            }
+            for (int k = j + 1; ok && k < i; ++k) {
+                const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);  // contour[i] - contour[k]
+                const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
+                ok = cr * cr <= lim;
+            }
+            if (ok) { best.len2 = len2; best.i = i; best.j = j; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Chord t{__shfl_xor_sync(FULL, best.len2, o), __shfl_xor_sync(FULL, best.i, o), __shfl_xor_sync(FULL, best.j, o)};
+        if (chord_better(t, best)) best = t;
+    }
+    if (best.len2 <= 0) {                               // best_j never assigned -> UnboundLocalError
+        if (lane < 20) dout[lane] = qnan;
+        if (lane == 0) step_out[g] = qnan;
+        return;
+    }
+    // mid_point = int(best_j + round((best_i - best_j) / 2))   (Python round: half to even)
+    const int diff = best.i - best.j;
+    int half = diff >> 1;
+    if ((diff & 1) && (half & 1)) half += 1;
+    const int mid = best.j + half;
+    const int mr = P[mid] & 0xffff, mc = P[mid] >> 16;
+    // apex = first farthest contour point from the mid point
+    int a_len2 = 0, a_idx = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+        const int dr = (int)(P[i] & 0xffff) - mr, dc = (int)(P[i] >> 16) - mc;
+        const int l2 = dr * dr + dc * dc;
+        if (l2 > a_len2) { a_len2 = l2; a_idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int l2 = __shfl_xor_sync(FULL, a_len2, o), ix = __shfl_xor_sync(FULL, a_idx, o);
+        if (l2 > a_len2 || (l2 == a_len2 && ix < a_idx)) { a_len2 = l2; a_idx = ix; }
+    }
+    if (a_len2 == 0) a_idx = 0;                          // all points coincide: apex stays 0, direction 0 -> NaN normal
+    const double dir_r = 0.5 * (double)((int)(P[a_idx] & 0xffff) - mr), dir_c = 0.5 * (double)((int)(P[a_idx] >> 16) - mc);
+    const double nrm = sqrt(__dadd_rn(__dmul_rn(dir_c, dir_c), __dmul_rn(dir_r, dir_r)));
+    const double nr = -dir_c / nrm, nc = dir_r / nrm;    // normal_direction = (-direction[1], direction[0]) / |.|
+    const double mid_r = 0.5 * (double)mr, mid_c = 0.5 * (double)mc;
+    const uint32_t* m = masks + g * CUB200_MASK_WORDS;
+    // 20 discs x 2 directions (heart_us.py:158-164)
+    double d_pos = 0.0, d_neg = 0.0, d_neg2 = 0.0;
+    for (int ray = lane; ray < 40; ray += 32) {
+        const int k = ray % 20;
+        const double sgn = ray < 20 ? 1.0 : -1.0;
+        const double frac = __dmul_rn((double)k, 0.05);                         // np.linspace(0, 1, 20, endpoint=False)
+        const double pr = __dadd_rn(mid_r, __dmul_rn(dir_r, frac)), pc = __dadd_rn(mid_c, __dmul_rn(dir_c, frac));
+        const double vr = sgn * nr, vc = sgn * nc;
+        double dist = 8.0;
+        for (;;) {
+            const double y = rint(__dadd_rn(pr, __dmul_rn(dist, vr))), x = rint(__dadd_rn(pc, __dmul_rn(dist, vc)));
+            if (!(y >= 0.0 && y < 256.0 && x >= 0.0 && x < 256.0)) break;        // out of bounds (NaN too: the reference raises there)
+            if (!mask_bit(m, (int)y, (int)x)) break;
+            dist += 0.5;
+        }
+        if (ray < 20) d_pos = dist; else if (ray < 32) d_neg = dist; else d_neg2 = dist;
+    }
+    // lane k < 20 holds d_pos of disc k; d_neg of disc k sits in lane 20 + k (k < 12) or lane k - 12 (second round)
+    const double neg_a = __shfl_sync(FULL, d_neg, (lane + 20) & 31);
+    const double neg_b = __shfl_sync(FULL, d_neg2, (lane + 20) & 31);            // lane k - 12 == (k + 20) & 31 for k >= 12
+    if (lane < 20) dout[lane] = __dmul_rn(__dadd_rn(d_pos, lane < 12 ? neg_a : neg_b), spacing);
+    if (lane == 0) step_out[g] = __dmul_rn(0.5 * sqrt((double)a_len2), spacing) / 20.0;
+}
+
+// ---------------------------------------------------------------- S3: volumes per Monte-Carlo sample
+// np.sum of 20 doubles: pairwise_sum with 8 accumulators over the first 16, then the last 4 in order
+__device__ __forceinline__ double np_sum20(const double* v) {
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(v[k], v[8 + k]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int k = 16; k < 20; ++k) res = __dadd_rn(res, v[k]);
+    return res;
+}
+
+__device__ __forceinline__ double simpson_volume(const double* a2c, const double* a4c, double step) {
+    double prod[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) prod[k] = __dmul_rn(a2c[k] / 1000.0, a4c[k] / 1000.0);
+    const double v = __dmul_rn(__dmul_rn(np_sum20(prod), step / 1000.0), 3.141592653589793) / 4.0;
+    return rint(__dmul_rn(v, 1e6));                               // Python round(): half to even
+}
+
+__global__ void simpson_volumes_kernel(const double* __restrict__ diam, const double* __restrict__ step, int64_t n_patients,
+                                       int64_t n_samples, double* __restrict__ edv, double* __restrict__ esv,
+                                       double* __restrict__ ef) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_patients * n_samples) return;
+    const int64_t p = g / n_samples, t = g % n_samples;
+    // masks of a patient: [A2C-ED, A2C-ES, A4C-ED, A4C-ES][sample]
+    const double* d[4];
+    double st[4];
+    bool ok = true;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int64_t mi = (p * 4 + v) * n_samples + t;
+        d[v] = diam + mi * 20;
+        st[v] = step[mi];
+        ok = ok && (st[v] == st[v]);
+    }
+    double v_ed = 0.0, v_es = 0.0, e = 0.0;
+    if (ok) {                                                     // an exception anywhere leaves the sample at zero (patient.py:186)
+        const double s = fmax(fmax(st[0], st[1]), fmax(st[2], st[3]));
+        v_ed = simpson_volume(d[0], d[2], s);
+        v_es = simpson_volume(d[1], d[3], s);
+        if (!(v_ed == v_ed) || !(v_es == v_es)) { v_ed = 0.0; v_es = 0.0; }     // round(nan) raises
+        else if (v_ed != 0.0) e = (v_ed - v_es) / v_ed;           // ZeroDivisionError keeps EF at zero
+    }
+    edv[g] = v_ed;
+    esv[g] = v_es;
+    ef[g] = (e < 0.0 || e > 1.0) ? __longlong_as_double(0x7ff8000000000000LL) : e;   // patient.py:189-190
+}
+
+}  // namespace cub200
+
+extern "C" int64_t cub200_simpson_workspace_bytes(int64_t n_masks) {
+    if (n_masks < 0) return CUB200_EINVAL;
+    return n_masks * (int64_t)(cub200::SP_NMAX * sizeof(uint32_t) + sizeof(int32_t));
+}
+
+extern "C" int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spacing, double* diam_out,
+                                        double* step_out, int32_t* npts_out, void* workspace, void* stream) {
+    using namespace cub200;
+    if (n_masks == 0) return 0;
+    if (!masks || !diam_out || !step_out || !workspace || n_masks < 0 || !(spacing > 0.0)) return CUB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* pts = reinterpret_cast<uint32_t*>(workspace);
+    int32_t* npts = reinterpret_cast<int32_t*>(pts + n_masks * SP_NMAX);
+    contour_trace_kernel<<<(unsigned)((n_masks + 127) / 128), 128, 0, st>>>(masks, n_masks, pts, npts);
+    int rc = check_launch("contour_trace_kernel");
+    if (rc) return rc;
+    simpson_diameters_kernel<<<(unsigned)((n_masks + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, 0, st>>>(
+        masks, pts, npts, n_masks, spacing, diam_out, step_out);
+    rc = check_launch("simpson_diameters_kernel");
+    if (rc) return rc;
+    if (npts_out) CUB200_CUDA_OK(cudaMemcpyAsync(npts_out, npts, sizeof(int32_t) * n_masks, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int cub200_simpson_volumes(const double* diam, const double* step, int64_t n_patients, int64_t n_samples,
+                                      double* edv_out, double* esv_out, double* ef_out, void* stream) {
+    using namespace cub200;
+    if (n_patients == 0 || n_samples == 0) return 0;
+    if (!diam || !step || !edv_out || !esv_out || !ef_out || n_patients < 0 || n_samples < 0) return CUB200_EINVAL;
+    const int64_t n = n_patients * n_samples;
+    simpson_volumes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(diam, step, n_patients, n_samples,
+                                                                                          edv_out, esv_out, ef_out);
+    return check_launch("simpson_volumes_kernel");
+}

@@ -409,6 +409,58 @@ def skew_sample(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor,
 
 
 # --------------------------------------------------------------------------------------------------
+# Simpson's biplane volumes (uncertainty propagation)
+# --------------------------------------------------------------------------------------------------
+def simpson_diameters(masks: torch.Tensor, spacing: float, return_npts: bool = False):
+    """_compute_diameters (vital heart_us.py:107-167) per bit-packed mask: masks (..., 2048) int32 ->
+    (diameters (..., 20) fp64 mm, step (...) fp64); NaN where the reference raises."""
+    masks = nat.require_cuda(masks, torch.int32, "masks")
+    if masks.shape[-1] != MASK_WORDS:
+        raise ValueError(f"masks must be (..., {MASK_WORDS}) int32 bit-packed")
+    lead = tuple(masks.shape[:-1])
+    n = int(np.prod(lead)) if lead else 1
+    dev = masks.device
+    diam = torch.empty(lead + (20,), dtype=torch.float64, device=dev)
+    step = torch.empty(lead, dtype=torch.float64, device=dev)
+    npts = torch.empty(lead, dtype=torch.int32, device=dev) if return_npts else None
+    ws = torch.empty((max(int(nat.lib().cub200_simpson_workspace_bytes(n)), 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_simpson_diameters(nat.ptr(masks), n, float(spacing), nat.ptr(diam), nat.ptr(step), nat.ptr(npts),
+                                                nat.ptr(ws), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_simpson_diameters")
+    return (diam, step, npts) if return_npts else (diam, step)
+
+
+def simpson_volumes(diam: torch.Tensor, step: torch.Tensor):
+    """compute_left_ventricle_volumes + the Monte-Carlo loop of Volume.compute (heart_us.py:13-71,
+    patient.py:166-190): diam (P,4,T,20), step (P,4,T) [A2C-ED, A2C-ES, A4C-ED, A4C-ES] -> edv, esv, ef (P,T) fp64."""
+    diam = nat.require_cuda(diam, torch.float64, "diam")
+    step = nat.require_cuda(step, torch.float64, "step")
+    if diam.dim() != 4 or diam.shape[1] != 4 or diam.shape[3] != 20 or tuple(step.shape) != tuple(diam.shape[:3]):
+        raise ValueError("diam (P,4,T,20) / step (P,4,T) expected")
+    P_, T = diam.shape[0], diam.shape[2]
+    out = [torch.empty((P_, T), dtype=torch.float64, device=diam.device) for _ in range(3)]
+    with torch.cuda.device(diam.device):
+        rc = nat.lib().cub200_simpson_volumes(nat.ptr(diam), nat.ptr(step), P_, T, nat.ptr(out[0]), nat.ptr(out[1]), nat.ptr(out[2]),
+                                              nat.stream_ptr(diam.device))
+    nat.check(rc, "cub200_simpson_volumes")
+    return tuple(out)
+
+
+def biplane_volumes_from_contours(contours: torch.Tensor, spacing: float):
+    """contours (P,4,T,21,2) fp32 [A2C-ED, A2C-ES, A4C-ED, A4C-ES] -> (edv, esv, ef (P,T), area (P,4,T)).
+    Rasterise every sampled contour (bit-packed masks), then Simpson's biplane rule per sample."""
+    contours = nat.require_cuda(contours, torch.float32, "contours")
+    if contours.dim() != 5 or contours.shape[1] != 4 or contours.shape[3:] != (K, 2):
+        raise ValueError("contours (P,4,T,21,2) expected")
+    P_, _, T = contours.shape[:3]
+    masks, area = rasterize_contours(contours.reshape(-1, K, 2), return_masks=True)
+    diam, step = simpson_diameters(masks.reshape(P_, 4, T, MASK_WORDS), spacing)
+    edv, esv, ef = simpson_volumes(diam, step)
+    return edv, esv, ef, area.reshape(P_, 4, T)
+
+
+# --------------------------------------------------------------------------------------------------
 # End-to-end engine
 # --------------------------------------------------------------------------------------------------
 @dataclass

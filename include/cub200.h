@@ -30,6 +30,7 @@ extern "C" {
 #define CUB200_HW 256        /* frame height = width                         */
 #define CUB200_ZMAX 42       /* max number of standard-normal draws / sample */
 #define CUB200_MASK_WORDS 2048 /* 256 rows x 8 uint32 (bit x&31 of word x>>5) */
+#define CUB200_SIMPSON_MAX_POINTS 2048 /* marching-squares contour points kept per mask */
 
 #define CUB200_EINVAL (-1)
 #define CUB200_ECUDA (-2)
@@ -215,6 +216,33 @@ int cub200_psm_conditionals(const double* model_c0, const double* model_xbar, co
 int cub200_skew_sample(const float* mu, const float* cov, const float* alpha, const float* pdfs, const double* mc_t,
                        const double* covc, const float* z, const float* expo, uint64_t seed, int64_t n_img,
                        int64_t n_samples, float* contours_out, int32_t* indices_out, void* stream);
+
+/*
+ * Simpson's biplane rule, step 1: per mask, the marching-squares contour (find_contours(mask, 0.5)[0]), the longest
+ * admissible base chord, the apex and the 20 disc diameters.
+ *   replaces  _compute_diameters (+ helpers)      vital/vital/metrics/evaluate/clinical/heart_us.py:74-167
+ *             skimage.measure.find_contours        (third party, restated; oracle/port.py::find_contours)
+ *   masks (n_masks, 2048) uint32 bit-packed (cub200_rasterize_contours / cub200_sample_raster_aggregate)
+ *   spacing: isotropic pixel size in mm (anisotropic spacing = PIL nearest-neighbour stretch first: not done here)
+ *   diam_out (n_masks, 20) fp64 mm; step_out (n_masks) fp64 = mid-line length * spacing / 20; both NaN when the
+ *   reference would raise (empty mask, no admissible chord, contour longer than CUB200_SIMPSON_MAX_POINTS)
+ *   npts_out optional (n_masks) int32 contour length (0 none, -1 too long)
+ *   workspace: cub200_simpson_workspace_bytes(n_masks) bytes of device memory
+ */
+int64_t cub200_simpson_workspace_bytes(int64_t n_masks);
+int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spacing, double* diam_out, double* step_out,
+                             int32_t* npts_out, void* workspace, void* stream);
+
+/*
+ * Simpson's biplane rule, step 2: EDV / ESV (mL, integers stored as fp64) and EF per Monte-Carlo sample.
+ *   replaces  compute_left_ventricle_volumes / _compute_left_ventricle_volume_by_instant   heart_us.py:13-71
+ *             the sample loop of Volume.compute                cu/results/clinical/patient.py:166-190
+ *   diam (n_patients, 4, n_samples, 20), step (n_patients, 4, n_samples): masks ordered [A2C-ED, A2C-ES, A4C-ED, A4C-ES]
+ *   edv_out, esv_out, ef_out (n_patients, n_samples) fp64; a sample with any NaN input stays (0, 0, 0) like the
+ *   reference's bare except; EF outside [0, 1] -> NaN.
+ */
+int cub200_simpson_volumes(const double* diam, const double* step, int64_t n_patients, int64_t n_samples,
+                           double* edv_out, double* esv_out, double* ef_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,12 @@ class _StubLoader(importlib.abc.Loader):
         name = module.__name__
         if name == "skimage.draw":
             module.line = bresenham_line
+        if name == "skimage.measure":
+            # restated marching squares (scikit-image is absent): parity unpinned, see oracle/port.py
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+            from oracle.port import find_contours
+
+            module.find_contours = find_contours
         if name == "strenum":
             import enum
 

@@ -267,6 +267,61 @@ def golden_skew():
     print("skew.npz", outs["f32"].shape)
 
 
+def _simpson_contours(T):
+    """(4, T, 21, 2) fp32 contour samples of one patient: [A2C-ED, A2C-ES, A4C-ED, A4C-ES] (ES = ED shrunk
+    to 0.8 about its centroid, A4C = A2C x 1.05) + per-sample jitter; the last samples are
+    adversarial: a tiny blob, an all-empty mask (degenerate contour far off-frame), a contour pushed
+    against the right frame border (open marching-squares contour) and a self-intersecting one."""
+    rng = np.random.default_rng(91)
+    b = synth.LV_EXAMPLE_SHAPE
+    ctr = b.mean(0)
+    base = [b, ctr + (b - ctr) * 0.8, ctr + (b - ctr) * 1.05, ctr + (b - ctr) * 0.84]
+    out = np.zeros((4, T, 21, 2))
+    for v in range(4):
+        for t in range(T):
+            out[v, t] = base[v] + rng.normal(0, 2.5, (21, 2)) + rng.normal(0, 3.0, (1, 2))
+    out[1, T - 4] = ctr + (b - ctr) * 0.001                     # one-pixel ES blob: no admissible chord -> exception -> zeros
+    out[0, T - 3] = b + np.array([-700.0, 0.0])                 # IndexError path: nothing but the clipped closing line
+    out[2, T - 2] = b + np.array([85.0, 0.0])                   # clipped at the right border
+    out[3, T - 1] = b + rng.normal(0, 14.0, (21, 2))            # self-intersecting
+    return out.astype(np.float32)
+
+
+def golden_simpson():
+    """compute_left_ventricle_volumes / _compute_diameters (vital heart_us.py) and the Monte-Carlo loop of
+    Volume.compute (cu/results/clinical/patient.py:166-190) on rasterised contour samples.
+    skimage.measure.find_contours is the restated one (oracle/port.py): parity unpinned for it."""
+    from contour_uncertainty.data.camus.utils import USContourToMask
+    from vital.metrics.evaluate.clinical.heart_us import compute_left_ventricle_volumes, _compute_diameters
+
+    T = 10
+    contours = _simpson_contours(T)
+    vs = (0.5, 0.5)
+    masks = np.array([[USContourToMask.__call__(contours[v, t], (256, 256), labels=[], apply_argmax=True) for t in range(T)]
+                      for v in range(4)]).astype(bool)
+    diam = np.full((4, T, 20), np.nan)
+    step = np.full((4, T), np.nan)
+    for v in range(4):
+        for t in range(T):
+            try:
+                diam[v, t], step[v, t] = _compute_diameters(masks[v, t], vs)
+            except Exception as e:  # the reference's callers swallow these
+                print("  _compute_diameters raised", v, t, type(e).__name__)
+    edv, esv, ef = np.zeros(T), np.zeros(T), np.zeros(T)
+    for t in range(T):                                          # patient.py:166-187
+        try:
+            lv_edv, lv_esv = compute_left_ventricle_volumes(masks[0, t], masks[1, t], vs, masks[2, t], masks[3, t], vs)
+            edv[t] = lv_edv
+            esv[t] = lv_esv
+            ef[t] = (lv_edv - lv_esv) / lv_edv
+        except:  # noqa: E722  (as the reference)
+            pass
+    ef[np.logical_or(ef < 0, ef > 1)] = np.nan
+    np.savez_compressed(os.path.join(HERE, "simpson.npz"), contours=contours, voxelspacing=np.array(vs),
+                        areas=masks.sum((2, 3)), diameters=diam, step=step, edv=edv, esv=esv, ef=ef)
+    print("simpson.npz edv", edv, "esv", esv, "ef", ef)
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -305,6 +360,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson"]
     for w in which:
         globals()["golden_" + w]()

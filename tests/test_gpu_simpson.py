@@ -1,0 +1,91 @@
+"""GPU parity tests of Simpson's biplane volumes (contour tracing, base chord, discs, EDV/ESV/EF) through the
+C ABI, against the goldens made by executing the reference (tests/golden/simpson.npz) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _pack(masks):
+    """(..., 256, 256) 0/1 -> (..., 2048) int32 bit-packed (bit x & 31 of word x >> 5)."""
+    b = np.packbits(masks.astype(np.uint8), axis=-1, bitorder="little")
+    return np.ascontiguousarray(b).view(np.uint32).reshape(masks.shape[:-2] + (2048,)).view(np.int32)
+
+
+def test_simpson_golden_exact(dev):
+    """Diameters / step are fp64-identical to the executed reference, EDV / ESV integer-identical, EF identical
+    (same two integers divided), NaN where the reference rejects."""
+    from contouring_uncertainty_b200 import engine as E
+
+    g = np.load(os.path.join(G, "simpson.npz"))
+    contours = torch.from_numpy(g["contours"]).to(dev)               # (4, T, 21, 2)
+    T = contours.shape[1]
+    spacing = float(g["voxelspacing"][0])
+    masks, area = E.rasterize_contours(contours.reshape(-1, 21, 2), return_masks=True)
+    assert np.array_equal(area.cpu().numpy().reshape(4, T), g["areas"])
+    diam, step, npts = E.simpson_diameters(masks.reshape(4, T, 2048), spacing, return_npts=True)
+    assert np.array_equal(diam.cpu().numpy(), g["diameters"])
+    assert np.array_equal(step.cpu().numpy(), g["step"])
+    edv, esv, ef = E.simpson_volumes(diam[None], step[None])
+    assert np.array_equal(edv.cpu().numpy()[0], g["edv"]) and np.array_equal(esv.cpu().numpy()[0], g["esv"])
+    assert np.array_equal(ef.cpu().numpy()[0], g["ef"], equal_nan=True)
+    e2 = E.biplane_volumes_from_contours(contours[None].contiguous(), spacing)
+    assert torch.equal(e2[0], edv) and torch.equal(e2[1], esv)
+    # contour lengths = the oracle's marching squares
+    m_np = E.unpack_masks(masks).cpu().numpy().reshape(4, T, 256, 256)
+    for v, t in ((0, 0), (2, T - 2), (3, T - 1), (1, T - 4)):
+        assert npts[v, t].item() == len(port.find_contours(m_np[v, t], 0.5)[0])
+
+
+def test_simpson_random_masks_vs_oracle(dev):
+    """PSM samples of a synthetic patient + hand-made masks (empty, full frame, two blobs, frame-cut blob)."""
+    from contouring_uncertainty_b200 import engine as E
+
+    rng = np.random.default_rng(17)
+    b = synth.LV_EXAMPLE_SHAPE
+    T = 6
+    cont = np.stack([np.stack([b.mean(0) + (b - b.mean(0)) * s + rng.normal(0, 3.0, (21, 2)) for _ in range(T)])
+                     for s in (1.0, 0.8, 1.05, 0.85)]).astype(np.float32)
+    masks = port.convert_to_mask(cont)                                # (4, T, 256, 256)
+    masks[0, 0] = 0                                                    # empty: no contour -> zeros
+    masks[1, 1] = 1                                                    # full frame: no contour either
+    masks[2, 2] = 0
+    masks[2, 2, 40:90, 50:100] = 1
+    masks[2, 2, 150:220, 120:200] = 1                                  # two blobs: [0] is the raster-first one
+    masks[3, 3] = 0
+    masks[3, 3, 200:256, 60:140] = 1                                   # cut by the bottom border: open contour
+    masks[0, 4] = 0
+    masks[0, 4, 100, 100] = 1                                          # single pixel
+    pk = torch.from_numpy(_pack(masks)).to(dev)
+    diam, step, npts = E.simpson_diameters(pk, 0.5, return_npts=True)
+    edv, esv, ef = E.simpson_volumes(diam[None], step[None])
+    o_edv, o_esv, o_ef = port.volumes_mc(masks[0], masks[1], masks[2], masks[3], (0.5, 0.5), (0.5, 0.5))
+    assert np.array_equal(edv.cpu().numpy()[0], o_edv) and np.array_equal(esv.cpu().numpy()[0], o_esv)
+    assert np.array_equal(ef.cpu().numpy()[0], o_ef, equal_nan=True)
+    dn, sn, nn = diam.cpu().numpy(), step.cpu().numpy(), npts.cpu().numpy()
+    for v in range(4):
+        for t in range(T):
+            try:
+                d, s = port.compute_diameters(masks[v, t], (0.5, 0.5))
+            except Exception:
+                assert np.isnan(dn[v, t]).all() and np.isnan(sn[v, t])
+                continue
+            assert np.array_equal(dn[v, t], d) and sn[v, t] == s, (v, t)
+            assert nn[v, t] == len(port.find_contours(masks[v, t], 0.5)[0])
+    assert nn[0, 0] == 0 and nn[1, 1] == 0

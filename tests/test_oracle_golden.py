@@ -151,3 +151,41 @@ def test_skew_pdf_table_matches_reference():
         assert np.abs(tab - ref).max() < 2e-8
         big = ref > 1e-6
         assert (np.abs(tab - ref) / ref)[big].max() < 5e-5       # fp32 exp of a fp32 exponent of magnitude ~15
+
+
+def test_simpson_matches_reference():
+    """heart_us.py executed on rasterised contour samples (with the restated find_contours: parity unpinned for
+    that third-party function).  The oracle restates _compute_diameters / the volume formula / the MC loop."""
+    g = np.load(os.path.join(G, "simpson.npz"))
+    contours = g["contours"]
+    vs = tuple(g["voxelspacing"])
+    T = contours.shape[1]
+    masks = port.convert_to_mask(contours).astype(bool)
+    assert np.array_equal(masks.sum((2, 3)), g["areas"])
+    for v, t in ((0, 0), (1, T - 4), (0, T - 3), (2, T - 2), (3, T - 1)):      # ordinary + the adversarial ones
+        d, s = port.compute_diameters(masks[v, t], vs)
+        assert np.array_equal(d, g["diameters"][v, t]) and s == g["step"][v, t]
+    sel = [0, T - 4, T - 3, T - 2, T - 1]
+    edv, esv, ef = port.volumes_mc(masks[0][sel], masks[1][sel], masks[2][sel], masks[3][sel], vs, vs)
+    assert np.array_equal(edv, g["edv"][sel]) and np.array_equal(esv, g["esv"][sel])
+    assert np.array_equal(ef, g["ef"][sel], equal_nan=True)
+    # an empty mask has no contour: the reference raises inside the bare except -> zeros
+    e = np.zeros((1, 256, 256), dtype=bool)
+    z = port.volumes_mc(e, masks[1][:1], masks[2][:1], masks[3][:1], vs, vs)
+    assert z[0][0] == 0 and z[1][0] == 0 and z[2][0] == 0
+
+
+def test_find_contours_closed_and_open():
+    """Structure of the restated marching squares: a closed blob gives one closed contour starting at the to-point
+    of its raster-last segment; a blob cut by the frame gives an open contour; creation order is raster order."""
+    m = np.zeros((16, 16))
+    m[3:8, 4:9] = 1
+    c = port.find_contours(m, 0.5)
+    assert len(c) == 1 and np.array_equal(c[0][0], c[0][-1]) and len(c[0]) == 21
+    assert tuple(c[0][0]) == (7.5, 8.0)      # raster-last cell (7, 8) is case 1: top -> left
+    m2 = np.zeros((16, 16))
+    m2[5:9, 12:16] = 1                       # touches the right border
+    m2[1:3, 1:3] = 1
+    c2 = port.find_contours(m2, 0.5)
+    assert len(c2) == 2 and np.array_equal(c2[0][0], c2[0][-1]) and c2[0][:, 0].max() < 3   # raster-first blob first
+    assert not np.array_equal(c2[1][0], c2[1][-1]) and c2[1][0][1] == 15 and c2[1][-1][1] == 15
