@@ -36,6 +36,11 @@ SIGNATURES = {
     "cub200_skew_sample": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _vp, _vp],
     "cub200_simpson_diameters": [_vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_simpson_volumes": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
+    "cub200_rasterize_contours_f64": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
+    "cub200_projected_uncertainty": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],
+    "cub200_umap_analytic": [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp],
+    "cub200_skew_umap_contours": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cub200_weighted_mask_entropy": [_vp, _vp, _i64, _i32, C.c_double, _i32, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes")
 

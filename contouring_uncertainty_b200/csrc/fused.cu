@@ -27,6 +27,7 @@
 // Shared memory per warp: the 256x256 boundary bitmap (8 rows per lane, padded band stride 68
 // words so the 128-bit band loads are bank-conflict free) + ~2 KB of spline scratch.
 #include "common.cuh"
+#include "spline.cuh"
 
 namespace cub200 {
 
@@ -47,8 +48,7 @@ constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px be
 
 struct __align__(16) WarpScratch {
     uint32_t bmp[BMP_WORDS];
-    double u[24];          // chord parameters u_0..u_20
-    double piece[20][10];  // piece i on [u_i, u_{i+1}]: {u_{i+1}, u_i, x c0..c3, y c0..c3} (powers of u - u_i)
+    SplineScratch sp;
     float z[CUB200_ZMAX + 2];
 };
 
@@ -172,7 +172,7 @@ __device__ __forceinline__ uint32_t flood_sweep(uint32_t (&R)[8][8], const uint4
 // ---------------------------------------------------------------- one sample, one warp
 // Lane k < 21 holds landmark k as (fx, fy).  Returns the mask area; accumulates run boundaries
 // into diff_img (may be null) and stores the packed mask (may be null).
-__device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_landmarks,
+__device__ int raster_sample(WarpScratch& ws, double fx, double fy, bool round_landmarks,
                              int32_t* __restrict__ diff_img, uint32_t* __restrict__ mask_out) {
     const int lane = lane_id();
     uint32_t* bmp = ws.bmp;
@@ -187,96 +187,17 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
     __syncwarp();
 
     // 2. rounded landmarks (closing line always uses them; the spline too when round_landmarks)
-    fx = fminf(fmaxf(fx, -(float)COORD_CLAMP), (float)COORD_CLAMP);
-    fy = fminf(fmaxf(fy, -(float)COORD_CLAMP), (float)COORD_CLAMP);
-    const int rix = (int)rintf(fx), riy = (int)rintf(fy);
-    const double X = round_landmarks ? (double)rix : (double)fx;
-    const double Y = round_landmarks ? (double)riy : (double)fy;
+    fx = fmin(fmax(fx, -(double)COORD_CLAMP), (double)COORD_CLAMP);
+    fy = fmin(fmax(fy, -(double)COORD_CLAMP), (double)COORD_CLAMP);
+    const int rix = __double2int_rn(fx), riy = __double2int_rn(fy);
+    const double X = round_landmarks ? (double)rix : fx;
+    const double Y = round_landmarks ? (double)riy : fy;
 
-    // 3a. chord-length parameter (FITPACK parcur)
-    const double Xp = __shfl_up_sync(FULL, X, 1), Yp = __shfl_up_sync(FULL, Y, 1);
-    double dch = 0.0;
-    if (lane >= 1 && lane < KP) dch = sqrt((X - Xp) * (X - Xp) + (Y - Yp) * (Y - Yp));
-    double cum = dch;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(FULL, cum, o);
-        if (lane >= o) cum += t;
-    }
-    const double total = __shfl_sync(FULL, cum, KP - 1);
-    double u = (lane == KP - 1) ? 1.0 : cum / total;
-    if (lane == 0) u = 0.0;
-    const double uprev = __shfl_up_sync(FULL, u, 1);
-    // FITPACK rejects non-increasing parameters (zero chord) -> ValueError -> raw points drawn
-    const bool bad = __any_sync(FULL, lane >= 1 && lane < KP && (dch == 0.0 || !(u > uprev))) || !(total > 0.0);
-    __syncwarp();
+    // 3a/3b. chord-length parameter + not-a-knot cubic spline (spline.cuh)
+    const bool bad = fit_spline(ws.sp, X, Y, lane);
 
     bool oob = false;
     if (!bad) {
-        // 3b. not-a-knot cubic spline: tridiagonal system for the second derivatives M_1..M_19
-        const double unext = __shfl_down_sync(FULL, u, 1);
-        const double Xn = __shfl_down_sync(FULL, X, 1), Yn = __shfl_down_sync(FULL, Y, 1);
-        const double h = unext - u;                         // h_k, k < 20
-        const double ih = 1.0 / h;
-        const double dxk = (Xn - X) * ih, dyk = (Yn - Y) * ih;  // divided differences delta_k
-        const double hm = __shfl_up_sync(FULL, h, 1);
-        const double dxm = __shfl_up_sync(FULL, dxk, 1), dym = __shfl_up_sync(FULL, dyk, 1);
-        if (lane < KP) ws.u[lane] = u;
-        // rows 1..19 (lane = row), normalised to unit diagonal; other lanes hold identity rows
-        double ta = 0.0, tc = 0.0, tx = 0.0, ty = 0.0;
-        if (lane >= 1 && lane <= KP - 2) {
-            double a = hm, b = 2.0 * (hm + h), c = h;
-            double r1 = 6.0 * (dxk - dxm), r2 = 6.0 * (dyk - dym);
-            if (lane == 1) {                                 // M_0 eliminated (not-a-knot at u_1)
-                const double f = h / (hm + h);
-                a = 0.0; b = hm + 2.0 * h; c = h - hm; r1 *= f; r2 *= f;
-            } else if (lane == KP - 2) {                     // M_20 eliminated (not-a-knot at u_19)
-                const double f = hm / (hm + h);
-                a = hm - h; b = h + 2.0 * hm; c = 0.0; r1 *= f; r2 *= f;
-            }
-            const double ib = 1.0 / b;
-            ta = a * ib; tc = c * ib; tx = r1 * ib; ty = r2 * ib;
-        }
-        // parallel cyclic reduction: 5 steps decouple the 19 equations (x and y share the matrix)
-#pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            double am = __shfl_up_sync(FULL, ta, sft), cm = __shfl_up_sync(FULL, tc, sft);
-            double xm = __shfl_up_sync(FULL, tx, sft), ym = __shfl_up_sync(FULL, ty, sft);
-            double ap = __shfl_down_sync(FULL, ta, sft), cp = __shfl_down_sync(FULL, tc, sft);
-            double xp = __shfl_down_sync(FULL, tx, sft), yp = __shfl_down_sync(FULL, ty, sft);
-            if (lane < sft) { am = cm = xm = ym = 0.0; }
-            if (lane + sft > 31) { ap = cp = xp = yp = 0.0; }
-            const double r = 1.0 / (1.0 - ta * cm - tc * ap);
-            tx = (tx - ta * xm - tc * xp) * r;
-            ty = (ty - ta * ym - tc * yp) * r;
-            ta = -ta * am * r;
-            tc = -tc * cp * r;
-        }
-        // second derivatives: lane i holds M_i (i = 1..19); M_0, M_20 from the not-a-knot relations
-        double Mx = tx, My = ty;
-        {
-            const double m1x = __shfl_down_sync(FULL, Mx, 1), m2x = __shfl_down_sync(FULL, Mx, 2);
-            const double m1y = __shfl_down_sync(FULL, My, 1), m2y = __shfl_down_sync(FULL, My, 2);
-            const double h1 = __shfl_down_sync(FULL, h, 1);
-            const double p1x = __shfl_up_sync(FULL, Mx, 1), p2x = __shfl_up_sync(FULL, Mx, 2);
-            const double p1y = __shfl_up_sync(FULL, My, 1), p2y = __shfl_up_sync(FULL, My, 2);
-            const double hm2 = __shfl_up_sync(FULL, h, 2);
-            if (lane == 0) { const double q = h / h1; Mx = m1x - q * (m2x - m1x); My = m1y - q * (m2y - m1y); }
-            if (lane == KP - 1) { const double q = hm / hm2; Mx = p1x + q * (p1x - p2x); My = p1y + q * (p1y - p2y); }
-        }
-        {
-            const double m1x = __shfl_down_sync(FULL, Mx, 1), m1y = __shfl_down_sync(FULL, My, 1);
-            if (lane < KP - 1) {                             // piece coefficients
-                double2* c = reinterpret_cast<double2*>(ws.piece[lane]);
-                c[0] = make_double2(unext, u);
-                c[1] = make_double2(X, dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0));
-                c[2] = make_double2(0.5 * Mx, (m1x - Mx) * ih * (1.0 / 6.0));
-                c[3] = make_double2(Y, dyk - h * (2.0 * My + m1y) * (1.0 / 6.0));
-                c[4] = make_double2(0.5 * My, (m1y - My) * ih * (1.0 / 6.0));
-            }
-        }
-        __syncwarp();
-
         // 3c/4. evaluate 1000 points (32 consecutive per lane), round half-even, apply the index
         //       rules and set the pixels on the fly (consecutive points falling into the same
         //       32-pixel word are merged into one shared-memory atomic).  An index < -256 makes the
@@ -288,12 +209,12 @@ __device__ int raster_sample(WarpScratch& ws, float fx, float fy, bool round_lan
         {
             const double us = (double)j0 * step;
 #pragma unroll
-            for (int k = 1; k <= KP - 2; ++k) piece = (us >= ws.u[k]) ? k : piece;
+            for (int k = 1; k <= KP - 2; ++k) piece = (us >= ws.sp.u[k]) ? k : piece;
         }
         double un, ub, c0, c1, c2, c3, e0, e1, e2, e3;
 #define CUB200_LOAD_PIECE()                                                              \
         {                                                                                \
-            const double2* pc = reinterpret_cast<const double2*>(ws.piece[piece]);       \
+            const double2* pc = reinterpret_cast<const double2*>(ws.sp.piece[piece]);       \
             const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];    \
             un = q0.x; ub = q0.y; c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;            \
             e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                  \
@@ -456,7 +377,7 @@ template <bool FROM_CONTOURS>
 __global__ void __launch_bounds__(FW_THREADS, FW_MINBLOCKS)
 sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim,
                      const float* __restrict__ z, uint64_t seed, int64_t n_img, int64_t n_samples,
-                     int round_landmarks, const float* __restrict__ contours_in,
+                     int round_landmarks, const float* __restrict__ contours_in, const double* __restrict__ contours_in64,
                      float* __restrict__ contours_out, int32_t* __restrict__ area_out,
                      int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -468,13 +389,19 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
     const int64_t g_end = min(total, (int64_t)(blockIdx.x + 1) * chunk);
     for (int64_t g = (int64_t)blockIdx.x * chunk + (threadIdx.x >> 5); g < g_end; g += FW_WARPS) {
         float fx = 0.f, fy = 0.f;
+        double dx = 0.0, dy = 0.0;
         int64_t img, map;
         if (FROM_CONTOURS) {
             img = per_image > 0 ? g / per_image : 0;
             map = img;
             if (lane < KP) {
-                const float2 p = reinterpret_cast<const float2*>(contours_in)[g * KP + lane];
-                fx = p.x; fy = p.y;
+                if (contours_in64) {
+                    const double2 p = reinterpret_cast<const double2*>(contours_in64)[g * KP + lane];
+                    dx = p.x; dy = p.y;
+                } else {
+                    const float2 p = reinterpret_cast<const float2*>(contours_in)[g * KP + lane];
+                    dx = p.x; dy = p.y;
+                }
             }
         } else {
             img = g / n_samples;
@@ -511,7 +438,8 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
             __syncwarp();
             if (!diff && !area_out && !masks_out) continue;     // sample-only call
         }
-        const int area = raster_sample(ws, fx, fy, round_landmarks != 0,
+        if (!FROM_CONTOURS) { dx = fx; dy = fy; }
+        const int area = raster_sample(ws, dx, dy, round_landmarks != 0,
                                        diff ? diff + map * 65536 : nullptr,
                                        masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
         if (area_out && lane == 0) area_out[g] = area;
@@ -548,7 +476,7 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
     int rc = launch_cfg(total, (const void*)sample_raster_kernel<false>, &grid);
     if (rc) return rc;
     sample_raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
-        mu, a_t, zdim, z, seed, n_img, n_samples, round_landmarks, nullptr, contours_out, area_out, diff, masks_out, images_per_map);
+        mu, a_t, zdim, z, seed, n_img, n_samples, round_landmarks, nullptr, nullptr, contours_out, area_out, diff, masks_out, images_per_map);
     return check_launch("sample_raster_kernel");
 }
 
@@ -561,6 +489,19 @@ extern "C" int cub200_rasterize_contours(const float* contours, int64_t n, int r
     int rc = launch_cfg(n, (const void*)sample_raster_kernel<true>, &grid);
     if (rc) return rc;
     sample_raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
-        nullptr, nullptr, 0, nullptr, 0, 0, n, round_landmarks, contours, nullptr, area_out, diff, masks_out, per_image);
+        nullptr, nullptr, 0, nullptr, 0, 0, n, round_landmarks, contours, nullptr, nullptr, area_out, diff, masks_out, per_image);
     return check_launch("sample_raster_kernel<contours>");
+}
+
+extern "C" int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
+                                             int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
+    using namespace cub200;
+    if (n == 0) return 0;
+    if (!contours || n < 0 || (diff && per_image <= 0)) return CUB200_EINVAL;
+    int grid = 0;
+    int rc = launch_cfg(n, (const void*)sample_raster_kernel<true>, &grid);
+    if (rc) return rc;
+    sample_raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
+        nullptr, nullptr, 0, nullptr, 0, 0, n, round_landmarks, nullptr, contours, nullptr, area_out, diff, masks_out, per_image);
+    return check_launch("sample_raster_kernel<contours f64>");
 }

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from ... import engine as E
-from ..utils import ContourToMask
+from ..utils import ContourToMask, UMap, SkewUMap
 
 
 class USContourToMask(ContourToMask):
@@ -32,3 +32,34 @@ class USContourToMask(ContourToMask):
             out = out[0]
             return out if apply_argmax else out[None]
         return out if apply_argmax else out[:, None]
+
+
+class USUMap(UMap):
+    """cu/data/camus/utils.py:101-124 (LV-only labels): uncertainty_map(mu, cov) / max -> (256,256) float64."""
+
+    @staticmethod
+    def __call__(mu, cov, labels=None):
+        if labels is not None and any(str(l).lower().endswith("myo") for l in labels):
+            raise NotImplementedError("the MYO (two-structure) branch is out of scope")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        m = torch.as_tensor(np.asarray(mu, dtype=np.float32)).reshape(-1, E.K, 2).to(dev)
+        c = torch.as_tensor(np.asarray(cov, dtype=np.float32)).reshape(-1, E.K, 2, 2).to(dev)
+        out = E.umap_analytic(m, c, normalize=True).cpu().numpy()
+        return out[0] if np.asarray(mu).ndim == 2 else out
+
+
+class USSkewUmap(SkewUMap):
+    """cu/data/camus/utils.py:127-153 (LV-only labels): skew_umap(mu, cov, alpha, linear_close=True), umap / max
+    -> (projected_mode (21,2) float32, umap (256,256) float64)."""
+
+    @staticmethod
+    def __call__(mu, cov, alpha, labels=None):
+        if labels is not None and any(str(l).lower().endswith("myo") for l in labels):
+            raise NotImplementedError("the MYO (two-structure) branch is out of scope")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        m = torch.as_tensor(np.asarray(mu, dtype=np.float32)).reshape(-1, E.K, 2).to(dev)
+        c = torch.as_tensor(np.asarray(cov, dtype=np.float32)).reshape(-1, E.K, 2, 2).to(dev)
+        a = torch.as_tensor(np.asarray(alpha, dtype=np.float32)).reshape(-1, E.K, 2).to(dev)
+        mode, out = E.skew_umap(m, c, a, linear_close=True, normalize=True)
+        mode, out = mode.cpu().numpy(), out.cpu().numpy()
+        return (mode[0], out[0]) if np.asarray(mu).ndim == 2 else (mode, out)

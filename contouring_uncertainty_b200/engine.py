@@ -173,8 +173,9 @@ def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Opti
 
 def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, return_masks: bool = True,
                        diff: Optional[torch.Tensor] = None, per_image: int = 0):
-    """Rasteriser alone: contours (M,21,2) fp32 -> (masks (M,2048) int32 bit-packed | None, area (M) int32)."""
-    contours = nat.require_cuda(contours, torch.float32, "contours")
+    """Rasteriser alone: contours (M,21,2) fp32 or fp64 -> (masks (M,2048) int32 bit-packed | None, area (M) int32)."""
+    f64 = isinstance(contours, torch.Tensor) and contours.dtype == torch.float64
+    contours = nat.require_cuda(contours, torch.float64 if f64 else torch.float32, "contours")
     if contours.dim() != 3 or contours.shape[1:] != (K, 2):
         raise ValueError(f"contours must be (M,{K},2), got {tuple(contours.shape)}")
     m = contours.shape[0]
@@ -182,8 +183,9 @@ def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, ret
     masks = torch.empty((m, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
     area = torch.empty((m,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = nat.lib().cub200_rasterize_contours(nat.ptr(contours), m, int(round_landmarks), nat.ptr(masks), nat.ptr(area),
-                                                 nat.ptr(diff), int(per_image), nat.stream_ptr(dev))
+        fn = nat.lib().cub200_rasterize_contours_f64 if f64 else nat.lib().cub200_rasterize_contours
+        rc = fn(nat.ptr(contours), m, int(round_landmarks), nat.ptr(masks), nat.ptr(area), nat.ptr(diff), int(per_image),
+                nat.stream_ptr(dev))
     nat.check(rc, "cub200_rasterize_contours")
     return masks, area
 
@@ -458,6 +460,80 @@ def biplane_volumes_from_contours(contours: torch.Tensor, spacing: float):
     diam, step = simpson_diameters(masks.reshape(P_, 4, T, MASK_WORDS), spacing)
     edv, esv, ef = simpson_volumes(diam, step)
     return edv, esv, ef, area.reshape(P_, 4, T)
+
+
+# --------------------------------------------------------------------------------------------------
+# Analytic uncertainty maps
+# --------------------------------------------------------------------------------------------------
+_SQRT_2PI = np.sqrt(2 * np.pi)
+# norm.pdf(np.linspace(-2, 2, 100))  (cu/utils/umap.py:21,29; scipy: exp(-x**2/2) / sqrt(2 pi))
+UMAP_PDF_TABLE = np.exp(-np.linspace(-2, 2, 100) ** 2 / 2.0) / _SQRT_2PI
+# norm.pdf(i, loc=0, scale=50) for i = 0..99, laid out as skew_umap's umap_weights (cu/utils/skew_umap.py:50-51)
+_w = np.exp(-(np.arange(100) / 50.0) ** 2 / 2.0) / _SQRT_2PI / 50.0
+SKEW_UMAP_WEIGHTS = np.concatenate([_w[::-1], _w])
+# the denominator of np.average(rec, axis=0, weights=w): the weights broadcast to (200,1,1) and summed over axis 0
+SKEW_UMAP_WEIGHT_SUM = float(np.broadcast_to(SKEW_UMAP_WEIGHTS, (1, 1, 200)).swapaxes(-1, 0).sum(axis=0)[0, 0])
+
+
+def projected_uncertainty(mu: torch.Tensor, cov: torch.Tensor, alpha: Optional[torch.Tensor] = None, all: bool = False,
+                          linear_close: bool = False):
+    """cu/utils/uncertainty_projection.py:17-125 for a batch: mu (N,21,2), cov (N,21,2,2) [, alpha (N,21,2)] fp32 ->
+    (uncertainties (N,21) fp32, projections (N,21,2) fp64 [, alpha_proj (N,21) fp32])."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    if mu.dim() != 3 or mu.shape[1:] != (K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,):
+        raise ValueError("mu (N,21,2) / cov (N,21,2,2) expected")
+    n, dev = mu.shape[0], mu.device
+    ap = None
+    if alpha is not None:
+        alpha = nat.require_cuda(alpha, torch.float32, "alpha")
+        if alpha.shape != mu.shape:
+            raise ValueError("alpha must be (N,21,2)")
+        ap = torch.empty((n, K), dtype=torch.float32, device=dev)
+    unc = torch.empty((n, K), dtype=torch.float32, device=dev)
+    proj = torch.empty((n, K, 2), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_projected_uncertainty(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, int(all), int(linear_close),
+                                                    nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_projected_uncertainty")
+    return (unc, proj) if alpha is None else (unc, proj, ap)
+
+
+def umap_analytic(mu: torch.Tensor, cov: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """uncertainty_map (cu/utils/umap.py:10-33) [/ max = USUMap, cu/data/camus/utils.py:113-115]: (N,256,256) fp64."""
+    unc, proj = projected_uncertainty(mu, cov, all=True)
+    n, dev = mu.shape[0], mu.device
+    table = torch.from_numpy(UMAP_PDF_TABLE).to(dev)
+    kmap = torch.empty((n, HW, HW), dtype=torch.int32, device=dev)
+    out = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_umap_analytic(nat.ptr(mu), nat.ptr(unc), nat.ptr(proj), n, nat.ptr(table), int(normalize),
+                                            nat.ptr(kmap), nat.ptr(out), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_umap_analytic")
+    return out
+
+
+def skew_umap(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, linear_close: bool = True, normalize: bool = True,
+              return_contours: bool = False):
+    """skew_umap (cu/utils/skew_umap.py:11-82) [USSkewUmap: linear_close=True, / max]: -> (projected_mode (N,21,2) fp32,
+    umap (N,256,256) fp64).  200 level contours per image are reconstructed (unrounded, fp64) by the rasteriser."""
+    unc, proj, ap = projected_uncertainty(mu, cov, alpha, all=True, linear_close=linear_close)
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    n, dev = mu.shape[0], mu.device
+    contours = torch.empty((n, 200, K, 2), dtype=torch.float64, device=dev)
+    mode = torch.empty((n, K, 2), dtype=torch.float32, device=dev)
+    L = nat.lib()
+    with torch.cuda.device(dev):
+        nat.check(L.cub200_skew_umap_contours(nat.ptr(mu), nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), n, nat.ptr(contours),
+                                              nat.ptr(mode), nat.stream_ptr(dev)), "cub200_skew_umap_contours")
+    masks, _ = rasterize_contours(contours.reshape(-1, K, 2), round_landmarks=False, return_masks=True)
+    w = torch.from_numpy(SKEW_UMAP_WEIGHTS).to(dev)
+    out = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(L.cub200_weighted_mask_entropy(nat.ptr(masks), nat.ptr(w), n, 200, SKEW_UMAP_WEIGHT_SUM, int(normalize),
+                                                 nat.ptr(out), nat.stream_ptr(dev)), "cub200_weighted_mask_entropy")
+    return (mode, out, contours) if return_contours else (mode, out)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -123,6 +123,11 @@ int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, 
 int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
                               int32_t* area_out, int32_t* diff, int64_t per_image, void* stream);
 
+/* Same as cub200_rasterize_contours with fp64 contours (n, 21, 2): the analytic skew u-map reconstructs unrounded
+ * fp64 level contours (cu/utils/skew_umap.py:62-64). */
+int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
+                                  int32_t* area_out, int32_t* diff, int64_t per_image, void* stream);
+
 /*
  * K4  Finalise the per-image maps from the difference map.
  *   replaces  pred = pred_samples.mean((1,2)).round()   cu/task/regression/aleatoric.py:111
@@ -243,6 +248,50 @@ int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spac
  */
 int cub200_simpson_volumes(const double* diam, const double* step, int64_t n_patients, int64_t n_samples,
                            double* edv_out, double* esv_out, double* ef_out, void* stream);
+
+/*
+ * Projected per-point uncertainty: spline normal at every landmark and the standard deviation of the point's law
+ * along it (skew-normal: also the projected skewness).
+ *   replaces  projected_uncertainty / projected_uncertainty_value     cu/utils/uncertainty_projection.py:11-125
+ *             BivariateNormal.marginal, BivariateSkewNormal.marginal  cu/distributions/bivariatenormal.py:67-86,
+ *                                                                     bivariateskewnormal.py:92-135
+ *   mu (n_img,21,2), cov (n_img,21,2,2) fp32; alpha (n_img,21,2) fp32 or NULL
+ *   all_points: `all=True` (else base / apex points 0, 10, 20 get sum(sqrt(eig(cov))));  linear_close as the reference
+ *   unc_out (n_img,21) fp32; proj_out (n_img,21,2) fp64; alpha_proj_out (n_img,21) fp32 (required with alpha)
+ *   projected_uncertainty_value = the sum of unc_out over the 21 points with all_points = 0.
+ */
+int cub200_projected_uncertainty(const float* mu, const float* cov, const float* alpha, int64_t n_img, int all_points,
+                                 int linear_close, float* unc_out, double* proj_out, float* alpha_proj_out, void* stream);
+
+/*
+ * Analytic uncertainty map: 100 offset contours mu + v u i, i = linspace(-2, 2, 100); a pixel takes the pdf value
+ * of the LAST offset whose spline / closing line touches it.
+ *   replaces  uncertainty_map        cu/utils/umap.py:10-33;   USUMap.__call__ (LV)   cu/data/camus/utils.py:101-124
+ *   unc, proj from cub200_projected_uncertainty(all_points = 1); pdf_table (100) fp64 = norm.pdf(linspace(-2,2,100));
+ *   normalize != 0 divides by the map maximum (USUMap); kmap_ws (n_img,256,256) int32 workspace;
+ *   umap_out (n_img,256,256) fp64.
+ */
+int cub200_umap_analytic(const float* mu, const float* unc, const double* proj, int64_t n_img, const double* pdf_table,
+                         int normalize, int32_t* kmap_ws, double* umap_out, void* stream);
+
+/*
+ * Skew u-map, step 1: per landmark the projected skew-normal on a 1000-point axis, its mode and the 2 x 100 level
+ * offsets -> 200 level contours per image.
+ *   replaces  skew_umap lines 13-58   cu/utils/skew_umap.py
+ *   unc, proj, alpha_proj from cub200_projected_uncertainty(alpha, all_points = 1, linear_close as wanted)
+ *   contours_out (n_img,200,21,2) fp64; mode_out (n_img,21,2) fp32 (projected_mode)
+ */
+int cub200_skew_umap_contours(const float* mu, const float* unc, const double* proj, const float* alpha_proj,
+                              int64_t n_img, double* contours_out, float* mode_out, void* stream);
+
+/*
+ * Skew u-map, step 2: weighted mean of bit-packed masks -> natural-log binary entropy (scipy.stats.entropy), optionally
+ * divided by its maximum.
+ *   replaces  skew_umap lines 76-80   cu/utils/skew_umap.py;   USSkewUmap.__call__ (LV)   cu/data/camus/utils.py:127-153
+ *   masks (n_img, n_masks, 2048) uint32; weights (n_masks) fp64; weight_sum = their sum as np.average forms it
+ */
+int cub200_weighted_mask_entropy(const uint32_t* masks, const double* weights, int64_t n_img, int n_masks,
+                                 double weight_sum, int normalize, double* out, void* stream);
 
 #ifdef __cplusplus
 }

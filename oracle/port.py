@@ -859,3 +859,136 @@ def volumes_mc(a2c_ed, a2c_es, a4c_ed, a4c_es, a2c_vs=(1.0, 1.0), a4c_vs=(1.0, 1
             pass
     ef[np.logical_or(ef < 0, ef > 1)] = np.nan
     return edv, esv, ef
+
+
+# --------------------------------------------------------------------------------------------------
+# Analytic uncertainty maps     cu/utils/uncertainty_projection.py, cu/utils/umap.py, cu/utils/skew_umap.py
+# --------------------------------------------------------------------------------------------------
+def _rot_cov_f32(cov: np.ndarray, v: np.ndarray):
+    """``rotate_cov(cov, -angle)`` (cu/distributions/utils.py:132-143) with angle = atan2(v_y, v_x): the reference
+    builds the rotation in fp32 torch, so its results carry fp32 rounding; here the exact fp64 value is formed and
+    rounded to fp32 once.  Returns (xx, xy, yy) of R cov R^T as np.float32 (R = [[c, s], [-s, c]], (c, s) = v)."""
+    c, s = float(v[0]), float(v[1])
+    xx, xy, yx, yy = (float(cov[0, 0]), float(cov[0, 1]), float(cov[1, 0]), float(cov[1, 1]))
+    r_xx = c * c * xx + c * s * (xy + yx) + s * s * yy
+    r_yy = s * s * xx - c * s * (xy + yx) + c * c * yy
+    r_xy = -c * s * xx + c * c * xy - s * s * yx + c * s * yy
+    return np.float32(r_xx), np.float32(r_xy), np.float32(r_yy)
+
+
+def projected_uncertainty(mu, cov, alpha=None, use_eigenvalue: bool = True, all: bool = False, linear_close: bool = False):
+    """cu/utils/uncertainty_projection.py:17-125.  mu (K,2), cov (K,2,2) [, alpha (K,2)] ->
+    (uncertainties (K,) fp32-valued, projections (K,2) fp64 [, alpha_proj (K,)])."""
+    mu = np.asarray(mu)
+    cov = np.asarray(cov)
+    K = mu.shape[0]
+    tck, u = interpolate.splprep([mu[:, 0], mu[:, 1]], k=3, s=0)
+    unew = np.linspace(0, 1.01, 1000)
+    der = np.stack(interpolate.splev(unew, tck, der=1), axis=1)
+    unc, proj, aproj = [], [], []
+    for index in range(K):
+        i = np.argmin(np.abs(u[index] - unew))
+        v = der[i] / np.linalg.norm(der[i])
+        v = np.array([v[1], -v[0]])                                  # flip, then negate the second component
+        if index in [0, K // 2, K - 1] and not all:
+            w = np.linalg.eigvals(cov[index].astype(np.float64))
+            unc.append(np.float32(np.sum(np.sqrt(w))))
+        else:
+            vr = v.copy()                                             # the angle is taken BEFORE linear_close replaces v
+            if linear_close and index in (0, K - 1):
+                a, b = (mu[1] - mu[0], mu[-1] - mu[0]) if index == 0 else (mu[-1] - mu[-2], mu[-1] - mu[0])
+                a = a / np.linalg.norm(a)
+                b = b / np.linalg.norm(b)
+                v = (a + b) / 2
+                v = v / np.linalg.norm(v)
+            r_xx, r_xy, r_yy = _rot_cov_f32(cov[index], vr)
+            if alpha is not None:                                      # BivariateSkewNormal.marginal, axis 0  (:92-135)
+                a0, a1 = float(alpha[index][0]), -float(alpha[index][1])
+                c, s = float(vr[0]), float(vr[1])
+                al0, al1 = np.float32(c * a0 + s * a1), np.float32(-s * a0 + c * a1)    # rotate_alpha(alpha, -angle)
+                std0, std1 = np.sqrt(r_xx), np.sqrt(r_yy)
+                corr_12 = r_xy / (std0 * std1)
+                corr_11 = r_xx / (std0 * std0)
+                corr_22 = r_yy / (std1 * std1)
+                corr_22_1 = corr_22 - corr_12 * corr_12 / corr_11
+                aproj.append(np.float32((al0 + (1 / corr_11) * corr_12 * al1) / np.sqrt(1 + al1 * corr_22_1 * al1)))
+            unc.append(np.sqrt(r_xx))
+        proj.append(v)
+    if alpha is not None:
+        return np.array(unc), np.array(proj), np.array(aproj)
+    return np.array(unc), np.array(proj)
+
+
+def projected_uncertainty_value(mu, cov) -> float:
+    """cu/utils/uncertainty_projection.py:11-14."""
+    return np.sum(projected_uncertainty(mu, cov)[0])
+
+
+def uncertainty_map(mu_p, cov_p, shape=(256, 256), close: bool = True) -> np.ndarray:
+    """cu/utils/umap.py:10-33: 100 offset contours mu + v u i, i in linspace(-2, 2, 100); every spline /
+    closing-line pixel is ASSIGNED norm.pdf(i), later offsets overwrite earlier ones."""
+    u, v = projected_uncertainty(mu_p, cov_p, all=True)
+    out = np.zeros(shape)
+    for i in np.linspace(-2, 2, 100):
+        m = mu_p + v * u[..., None] * i
+        c = contour_spline(m, close=False)
+        mi = m.astype(int)
+        rr, cc = bresenham_line(mi[-1, 1], mi[-1, 0], mi[0, 1], mi[0, 0])
+        c = c.round().astype(int).clip(max=255, min=0)
+        val = scipy.stats.norm.pdf(i, loc=0, scale=1)
+        out[c[:, 1], c[:, 0]] = val
+        if close:
+            out[rr.clip(max=255, min=0), cc.clip(max=255, min=0)] = val
+    return out
+
+
+def us_umap(mu, cov) -> np.ndarray:
+    """USUMap.__call__ (cu/data/camus/utils.py:101-124), LV-only labels: uncertainty_map / max."""
+    m = uncertainty_map(mu, cov)
+    return m / m.max()
+
+
+def skew_umap_contours(mu, cov, alpha, linear_close: bool = False):
+    """First half of ``skew_umap`` (cu/utils/skew_umap.py:11-58): projected mode (K,2) and the 200 level
+    contours (200,K,2) with their weights (200,)."""
+    mu = np.asarray(mu)
+    alpha = np.array(alpha)
+    u, v, alpha_proj = projected_uncertainty(mu, cov, alpha.copy(), all=True, linear_close=linear_close)
+    K, N, resolution, cov_width = len(mu), 100, 1000, 2
+    projected_mode = np.zeros_like(mu)
+    values = np.linspace(0, 0.95, N)
+    contours = np.zeros((2 * N, K, 2))
+    weights = np.zeros(2 * N)
+    for index in range(K):
+        p1 = mu[index] + v[index] * u[index] * cov_width
+        p2 = mu[index] - v[index] * u[index] * cov_width
+        x = np.linspace(-3 * u[index], 3 * u[index], resolution)
+        y = scipy.stats.skewnorm.pdf(x, alpha_proj[index], 0, u[index])
+        y = y / y.max()
+        mode_y = y.max()
+        am = y.argmax()
+        mode_x = x[am]
+        projected_mode[index] = p1 * (am / len(y)) + (1 - am / len(y)) * p2
+        right, left = y[x > mode_x], y[x < mode_x]
+        for i, val in enumerate(values):
+            val = mode_y - val
+            mode_plus = (np.argmin(np.abs(right - val)) + am) / len(y)
+            mode_minus = np.argmin(np.abs(left - val)) / len(y)
+            contours[N - i - 1, index] = p1 * mode_minus + (1 - mode_minus) * p2
+            contours[N + i, index] = p1 * mode_plus + (1 - mode_plus) * p2
+            weights[N - i - 1] = weights[N + i] = scipy.stats.norm.pdf(i, loc=0, scale=N / 2)
+    return projected_mode, contours, weights
+
+
+def skew_umap(mu, cov, alpha, linear_close: bool = False):
+    """cu/utils/skew_umap.py:11-82: weighted mean of the 200 reconstructed masks -> natural-log binary entropy."""
+    mode, contours, weights = skew_umap_contours(mu, cov, alpha, linear_close)
+    rec = np.array([reconstruction(c, 256, 256) for c in contours])
+    m = np.average(rec, axis=0, weights=weights)
+    return mode, scipy.stats.entropy(np.stack([m, 1 - m]), axis=0)
+
+
+def us_skew_umap(mu, cov, alpha):
+    """USSkewUmap.__call__ (cu/data/camus/utils.py:127-153), LV-only labels."""
+    mode, m = skew_umap(mu, cov, alpha, linear_close=True)
+    return mode, m / m.max()

@@ -322,6 +322,36 @@ def golden_simpson():
     print("simpson.npz edv", edv, "esv", esv, "ef", ef)
 
 
+def golden_umap():
+    """projected_uncertainty(_value), USUMap and USSkewUmap (cu/utils/{uncertainty_projection,umap,skew_umap}.py,
+    cu/data/camus/utils.py:101-153) on 3 synthetic images.  Maps are stored sparsely (indices + values)."""
+    from contour_uncertainty.data.camus.utils import USUMap, USSkewUmap
+    from contour_uncertainty.utils.uncertainty_projection import projected_uncertainty, projected_uncertainty_value
+
+    n = 3
+    mus, covs = synth.point_distributions(n, seed=101)
+    al = synth.skew_alphas(n, seed=102)
+    out = dict(mu=mus, cov=covs, alpha=al)
+    U, V, U0, VAL, U2, V2, AP, MODE = [], [], [], [], [], [], [], []
+    for i in range(n):
+        u, v = projected_uncertainty(mus[i], covs[i], all=True)
+        u0, _ = projected_uncertainty(mus[i], covs[i])
+        u2, v2, ap = projected_uncertainty(mus[i], covs[i], al[i].copy(), all=True, linear_close=True)
+        U.append(u); V.append(v); U0.append(u0); VAL.append(projected_uncertainty_value(mus[i], covs[i]))
+        U2.append(u2); V2.append(v2); AP.append(ap)
+        um = USUMap.__call__(mus[i], covs[i], labels=[])
+        mode, sk = USSkewUmap.__call__(mus[i], covs[i], al[i], labels=[])
+        MODE.append(mode)
+        for name, m in (("umap", um), ("skew_umap", sk)):
+            idx = np.flatnonzero(m)
+            out[f"{name}_idx_{i}"] = idx.astype(np.int32)
+            out[f"{name}_val_{i}"] = m.reshape(-1)[idx]
+    out.update(unc_all=np.array(U), proj_all=np.array(V), unc=np.array(U0), value=np.array(VAL), skew_unc=np.array(U2),
+               skew_proj=np.array(V2), alpha_proj=np.array(AP), mode=np.array(MODE))
+    np.savez_compressed(os.path.join(HERE, "umap.npz"), **out)
+    print("umap.npz", {k: np.asarray(v).shape for k, v in out.items() if not k[-1].isdigit()}, "value", VAL)
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -360,6 +390,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap"]
     for w in which:
         globals()["golden_" + w]()

@@ -189,3 +189,31 @@ def test_find_contours_closed_and_open():
     c2 = port.find_contours(m2, 0.5)
     assert len(c2) == 2 and np.array_equal(c2[0][0], c2[0][-1]) and c2[0][:, 0].max() < 3   # raster-first blob first
     assert not np.array_equal(c2[1][0], c2[1][-1]) and c2[1][0][1] == 15 and c2[1][-1][1] == 15
+
+
+def _sparse_map(g, name, i):
+    m = np.zeros(256 * 256)
+    m[g[f"{name}_idx_{i}"]] = g[f"{name}_val_{i}"]
+    return m.reshape(256, 256)
+
+
+def test_umaps_match_reference():
+    """projected_uncertainty / USUMap / USSkewUmap.  The reference rotates covariances in fp32 torch, so its projected
+    standard deviations are reproduced to 1 fp32 ulp; maps are compared pixel by pixel."""
+    g = np.load(os.path.join(G, "umap.npz"))
+    for i in range(3):
+        mu, cov, al = g["mu"][i], g["cov"][i], g["alpha"][i]
+        u, v = port.projected_uncertainty(mu, cov, all=True)
+        assert np.abs(u.view(np.int32) - g["unc_all"][i].view(np.int32)).max() <= 1 and np.abs(v - g["proj_all"][i]).max() < 1e-12
+        u0, _ = port.projected_uncertainty(mu, cov)
+        np.testing.assert_allclose(u0, g["unc"][i], rtol=3e-7)
+        np.testing.assert_allclose(port.projected_uncertainty_value(mu, cov), g["value"][i], rtol=3e-7)
+        u2, v2, ap = port.projected_uncertainty(mu, cov, al.copy(), all=True, linear_close=True)
+        assert np.abs(u2.view(np.int32) - g["skew_unc"][i].view(np.int32)).max() <= 1
+        assert np.abs(v2 - g["skew_proj"][i]).max() < 1e-12 and np.abs(ap - g["alpha_proj"][i]).max() < 2e-6
+        if i == 0:
+            um, ref = port.us_umap(mu, cov), _sparse_map(g, "umap", i)
+            assert (um != ref).sum() <= 8                       # 1-ulp differences of u can move a rounded spline pixel
+            mode, sk = port.us_skew_umap(mu, cov, al)
+            ref = _sparse_map(g, "skew_umap", i)
+            assert np.abs(mode - g["mode"][i]).max() < 1e-4 and (np.abs(sk - ref) > 1e-12).sum() <= 8
