@@ -56,6 +56,32 @@ def batch_result_from(res: E.UncertaintyResult, img, uncertainty_map=None, gt=No
         pred_samples=pred_samples, entropy_map=ent, sample_area=res.area.cpu().numpy().reshape(n, 1, T), **kw)
 
 
+def add_point_and_instant_uncertainty(res: BatchResult, mu_t: torch.Tensor, cov_t: torch.Tensor) -> BatchResult:
+    """ContourUncertaintyTask.predict_step, lines 85-128 of cu/task/regression/contour_uncertainty.py: per-point and
+    per-instant scalar uncertainties.  (N,K) algebra in numpy as in the reference; the spline-normal projection
+    (projected_uncertainty_value) runs on the GPU."""
+    LA = np.linalg
+    cov = res.cov
+    cov_det = LA.det(cov) ** 0.25
+    cov_eigval = np.sqrt(LA.eig(cov)[0])
+    res.point_uncertainty = {"cov_xx": cov[:, :, 0, 0] ** 0.5, "cov_yy": cov[:, :, 1, 1] ** 0.5, "cov_det": cov_det,
+                             "cov_eigval_sum": cov_eigval.sum(-1)}
+    if res.post_cov is not None:
+        pe = np.sqrt(LA.eig(res.post_cov)[0])
+        res.point_uncertainty.update({"post_cov_xx": res.post_cov[:, :, 0, 0] ** 0.5, "post_cov_yy": res.post_cov[:, :, 1, 1] ** 0.5,
+                                      "post_cov_det": LA.det(res.post_cov) ** 0.25, "post_cov_eigval_sum": pe.sum(-1)})
+    unc, _ = E.projected_uncertainty(mu_t.to(torch.float32).contiguous(), cov_t.to(torch.float32).contiguous())
+    mask = res.pred != 0                                               # Label.BG == 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        res.instant_uncertainty = {"cov_det_mean": np.mean(cov_det, axis=-1),
+                                   "cov_eigenvalue_mean": np.mean(cov_eigval, axis=(-1, -2)),
+                                   "cov_projection": unc.sum(1).cpu().numpy(),
+                                   "umap_mean": np.sum(res.uncertainty_map, axis=(-2, -1)) / np.sum(mask, axis=(-2, -1))}
+        if res.entropy_map is not None:
+            res.instant_uncertainty["entropy_mean"] = np.sum(res.entropy_map, axis=(-2, -1)) / np.sum(mask, axis=(-2, -1))
+    return res
+
+
 class ContourUncertaintyPipeline:
     """dsnt-al / dsnt-al2 predict path on logits.  ``covar`` = hparams.covar (config/task/dsnt-al.yaml)."""
 
@@ -122,10 +148,82 @@ class ContourUncertaintyPipeline:
         pred_samples = None
         if return_pred_samples:
             pred_samples = E.unpack_masks(r["masks"]).cpu().numpy().astype(np.int64).reshape(n, te, T, 1, E.HW, E.HW)
-        mu_np = mu.mean(1).cpu().numpy()
-        return BatchResult(
+        mu_mean_t = mu.mean(1).contiguous()
+        mu_np = mu_mean_t.cpu().numpy()
+        umap = kw.pop("uncertainty_map", None)
+        if umap is None:                                                # aleatoric.py:114: umap_fn = USUMap (analytic map / max)
+            umap = E.umap_analytic(mu_mean_t, cov_out.contiguous(), normalize=True).cpu().numpy()
+        res = BatchResult(
             id=kw.pop("id", ""), labels=kw.pop("labels", ("lv",)), img=np.asarray(img), gt=kw.pop("gt", None),
-            pred=pred.cpu().numpy().astype(np.int64), uncertainty_map=kw.pop("uncertainty_map", ent_np),
+            pred=pred.cpu().numpy().astype(np.int64), uncertainty_map=umap,
             mu=mu_np, mode=mu_np, cov=cov_out.cpu().numpy(), post_mu=pm.mean(1).cpu().numpy(), post_cov=post_cov.cpu().numpy(),
             contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent_np,
             sample_area=r["area"].reshape(n, te, T).cpu().numpy(), **kw)
+        return add_point_and_instant_uncertainty(res, mu_mean_t, cov_out)
+
+
+
+class SkewUncertaintyPipeline:
+    """dsnt-skew predict path: ``SkewUncertaintyTask._predict_step`` (cu/task/regression/aleatoric_skew.py:55-127) +
+    ``predict_step`` (contour_uncertainty.py:71-130) after the network forward.
+
+    The network gives heatmap logits and, from its bottleneck, the raw skewness vectors (``skew_block``); both stay
+    torch/cuDNN.  Everything after is here: DSNT moments, the numerical skew-PSM sampler (25 samples per pass in the
+    reference, aleatoric_skew.py:63), posterior moments, projected mode + skew u-map, mask of the mode, sample masks
+    -> entropy map."""
+
+    def __init__(self, psm_path: Optional[str] = None, t_a: int = 25, covar: bool = True, device="cuda"):
+        self.t_a = t_a
+        self.covar = covar
+        self.device = torch.device(device)
+        self.model = E.ShapeModelConstants(psm_path or E.DEFAULT_PSM, device=self.device)
+
+    def predict(self, logits_per_model: Sequence[torch.Tensor], alpha_per_model: Sequence[torch.Tensor], negate_alpha_y: bool = True):
+        """DSNTSkew.predict (dsnt_skew.py:153-199): -> S (N,T_e,K,2), cov (N,T_e,K,2,2), alpha (N,T_e,K,2); the raw
+        skew_block output has its y component negated (:164)."""
+        S, cov, al = [], [], []
+        for lg, a in zip(logits_per_model, alpha_per_model):
+            _, mu, sig = E.dsnt_moments(lg, is_logit=True, covar=self.covar)
+            a = a.to(mu.device, torch.float32)
+            if negate_alpha_y:
+                a = a * torch.tensor([1.0, -1.0], device=a.device)
+            S.append(mu); cov.append(sig); al.append(a)
+        return torch.stack(S, 1), torch.stack(cov, 1), torch.stack(al, 1)
+
+    def predict_step(self, logits, alpha, img=None, seed: int = 0, z=None, expo=None, return_pred_samples: bool = False,
+                     negate_alpha_y: bool = True, **kw) -> BatchResult:
+        passes = list(logits) if isinstance(logits, (list, tuple)) else [logits]
+        alphas = list(alpha) if isinstance(alpha, (list, tuple)) else [alpha]
+        te, n, T = len(passes), passes[0].shape[0], self.t_a
+        mu, cov, al = self.predict(passes, alphas, negate_alpha_y)
+        m2, c2, a2 = (t.reshape((n * te,) + t.shape[2:]).contiguous() for t in (mu, cov, al))
+        dev = mu.device
+        zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=dev).reshape(n * te, T, 3, 3).contiguous()
+        et = None if expo is None else torch.as_tensor(expo, dtype=torch.float32, device=dev).reshape(n * te, T, E.N_DRAW_SKEW, E.HW * E.HW).contiguous()
+        samples = E.skew_sample(self.model, m2, c2, a2, T, z=zt, expo=et, seed=seed).reshape(n, te, T, E.K, 2)
+        # aleatoric_skew.py:65-73
+        mu_mean = mu.mean(1, keepdim=True)
+        d = (mu - mu_mean)[..., None]
+        cov_out = (cov.mean(1) + (d * d.transpose(-1, -2)).mean(1)).contiguous()
+        mu_m, al_m = mu.mean(1).contiguous(), al.mean(1).contiguous()
+        # :75-79  post_mu over all passes and samples, post_cov = np.cov of the pooled samples
+        pm, pc = E.sample_moments(samples.reshape(n, te * T, E.K, 2).contiguous())
+        # :82-91  projected mode + skew u-map (USSkewUmap), mask of the mode, masks of the samples
+        mode, umap = E.skew_umap(mu_m, cov_out, al_m, linear_close=True, normalize=True)
+        pmask, _ = E.rasterize_contours(mode.contiguous(), round_landmarks=True, return_masks=True)
+        pred = E.unpack_masks(pmask).to(torch.int64)
+        diff = torch.zeros((n, E.HW, E.HW), dtype=torch.int32, device=dev)
+        masks, area = E.rasterize_contours(samples.reshape(-1, E.K, 2), return_masks=return_pred_samples, diff=diff, per_image=te * T)
+        _, _, ent, _ = E.finalize_maps(diff, te * T, want_count=False)
+        if img is None:
+            img = np.zeros((n, E.HW, E.HW), dtype=np.float32)
+        pred_samples = None
+        if return_pred_samples:
+            pred_samples = E.unpack_masks(masks).cpu().numpy().astype(np.int64).reshape(n, te, T, E.HW, E.HW)
+        res = BatchResult(
+            id=kw.pop("id", ""), labels=kw.pop("labels", ("lv",)), img=np.asarray(img), gt=kw.pop("gt", None),
+            pred=pred.cpu().numpy(), uncertainty_map=umap.cpu().numpy(), mu=mu_m.cpu().numpy(), mode=mode.cpu().numpy(),
+            cov=cov_out.cpu().numpy(), alpha=al_m.cpu().numpy(), post_mu=pm.cpu().numpy(), post_cov=pc.cpu().numpy(),
+            contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent.cpu().numpy(),
+            sample_area=area.reshape(n, te, T).cpu().numpy(), **kw)
+        return add_point_and_instant_uncertainty(res, mu_m, cov_out)

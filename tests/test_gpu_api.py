@@ -206,3 +206,58 @@ def test_pipeline_sequence_sampler_view():
     want[~((want >= 0) & (want <= 1))] = np.nan
     assert np.allclose(f, want, equal_nan=True)
     assert len(aleatoric_epistemic_uncertainty(f)) == 4
+
+
+def test_predict_step_umap_and_scalar_uncertainties():
+    """dsnt-al predict_step: uncertainty_map = USUMap(mu, cov), point / instant uncertainty dicts
+    (contour_uncertainty.py:85-128) against the oracle."""
+    from contouring_uncertainty_b200.task import ContourUncertaintyPipeline
+
+    pipe = ContourUncertaintyPipeline(t_a=16)
+    logits = torch.from_numpy(synth.heatmap_logits(2, seed=51)).cuda()
+    br = pipe.predict_step(logits, seed=9)
+    for i in range(2):
+        want = port.us_umap(br.mu[i], br.cov[i])
+        assert (br.uncertainty_map[i] != want).sum() <= 8
+        assert abs(br.instant_uncertainty["cov_projection"][i] - port.projected_uncertainty_value(br.mu[i], br.cov[i])) < 1e-4
+        mask = br.pred[i] != 0
+        assert np.isclose(br.instant_uncertainty["umap_mean"][i], br.uncertainty_map[i].sum() / mask.sum())
+        assert np.isclose(br.instant_uncertainty["entropy_mean"][i], br.entropy_map[i].sum() / mask.sum())
+    assert np.allclose(br.point_uncertainty["cov_det"], np.linalg.det(br.cov) ** 0.25)
+    assert br.point_uncertainty["post_cov_eigval_sum"].shape == (2, 21)
+    assert set(br.instant_uncertainty) == {"cov_det_mean", "cov_eigenvalue_mean", "cov_projection", "umap_mean", "entropy_mean"}
+
+
+def test_skew_pipeline_predict_step_vs_oracle():
+    """dsnt-skew: SkewUncertaintyTask._predict_step + predict_step with the reference's random draws replayed."""
+    from contouring_uncertainty_b200.task import SkewUncertaintyPipeline
+    from contouring_uncertainty_b200.sampler import SkewPosteriorShapeModelSampler
+
+    n, T = 2, 3
+    pipe = SkewUncertaintyPipeline(t_a=T)
+    logits = synth.heatmap_logits(n, seed=61)
+    raw_alpha = synth.skew_alphas(n, seed=62)                       # skew_block output (before the y negation of dsnt_skew.py:164)
+    z = np.random.default_rng(63).standard_normal((n, T, 3, 3)).astype(np.float32)
+    ex = np.stack([np.stack([np.stack([synth.exponential_field(64, (i * T + s) * 14 + d) for d in range(14)])
+                             for s in range(T)]) for i in range(n)])
+    br = pipe.predict_step(torch.from_numpy(logits).cuda(), torch.from_numpy(raw_alpha).cuda(), z=z, expo=ex,
+                           return_pred_samples=True)
+    assert br.contour_samples.shape == (n, 1, T, 21, 2) and br.alpha.shape == (n, 21, 2) and br.mode.shape == (n, 21, 2)
+    alpha = raw_alpha * np.array([1.0, -1.0], dtype=np.float32)
+    assert np.array_equal(br.alpha, alpha)
+    model = port.ShapeModel.load(pipe.model.path)
+    for i in range(n):
+        s = port.skew_psm_sample(model, br.mu[i], br.cov[i], alpha[i], z[i], lambda k, d, _i=i: ex[_i, k, d])
+        assert np.abs(s - br.contour_samples[i, 0]).max() < 2e-4
+        masks = port.convert_to_mask(br.contour_samples[i, 0])
+        assert np.array_equal(masks, br.pred_samples[i, 0])
+        o = port.maps_from_counts(masks.sum(0, dtype=np.int64), T)
+        assert np.abs(o[1] - br.entropy_map[i]).max() <= 1e-12
+        mode, um = port.us_skew_umap(br.mu[i], br.cov[i], alpha[i])
+        assert np.abs(mode - br.mode[i]).max() < 1e-4 and (np.abs(um - br.uncertainty_map[i]) > 1e-12).sum() <= 8
+        assert np.array_equal(br.pred[i], port.us_contour_to_mask(br.mode[i]))
+        assert np.allclose(br.post_mu[i], br.contour_samples[i].reshape(-1, 21, 2).mean(0), atol=1e-4)
+    # the sampler mirror gives the same contours through the reference's call signature
+    smp = SkewPosteriorShapeModelSampler()
+    out = smp(torch.from_numpy(br.mu), torch.from_numpy(br.cov), torch.from_numpy(alpha), n=T, z=z, expo=ex)
+    assert out.shape == (n, T, 21, 2) and np.array_equal(out.numpy(), br.contour_samples[:, 0])
