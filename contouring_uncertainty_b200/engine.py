@@ -266,6 +266,11 @@ class SequenceModelConstants:
         t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=self.device)
         self.m2t, self.covc = t(m2t), t(covc)
         self.mu, self.mean, self.scale = t(f32(d["mu"]).reshape(-1)), t(f32(d["scaler_mean"]).reshape(-1)), t(scale)
+        # for the skew sequence sampler, which re-centres the 84-dim PCA on every predicted pair
+        # (psm_skew_sequence.py:66): pca() about any centre is C0 + d d^T
+        x = f32(d["X_train"])
+        xbar = x.mean(0)
+        self.c0, self.xbar = t((x - xbar).T @ (x - xbar) / x.shape[0]), t(xbar)
 
 
 def sequence_sample(model: ShapeModelConstants, seq: SequenceModelConstants, mu: torch.Tensor, cov: torch.Tensor,
@@ -407,6 +412,53 @@ def skew_sample(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor,
                                           nat.ptr(z), nat.ptr(expo), int(seed) & (2**64 - 1), n, T, nat.ptr(out), nat.ptr(idx),
                                           nat.stream_ptr(dev))
     nat.check(rc, "cub200_skew_sample")
+    return (out, idx) if return_indices else out
+
+
+def seq_skew_sample(model: ShapeModelConstants, seq: "SequenceModelConstants", mu: torch.Tensor, cov: torch.Tensor,
+                    alpha: torch.Tensor, n_samples: int, first_instant: Optional[torch.Tensor] = None,
+                    z: Optional[torch.Tensor] = None, expo: Optional[torch.Tensor] = None, seed: int = 0,
+                    return_indices: bool = False):
+    """SequenceSkewPSMSampler (psm_skew_sequence.py:34-104) for a batch of (ED, ES) pairs.
+
+    mu (Np,2,21,2), cov (Np,2,21,2,2), alpha (Np,2,21,2) fp32 CUDA; first_instant (Np,T) uint8 (else Bernoulli(1/2));
+    z (Np,T,3,3); expo (Np,T,31,65536).  Returns contours (Np, 2, T, 21, 2) [, indices (Np,T,31)]."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    alpha = nat.require_cuda(alpha, torch.float32, "alpha")
+    if mu.dim() != 4 or mu.shape[1:] != (2, K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,) or alpha.shape != mu.shape:
+        raise ValueError("mu (Np,2,21,2) / cov (Np,2,21,2,2) / alpha (Np,2,21,2) expected")
+    npair, T, dev = mu.shape[0], int(n_samples), mu.device
+    if first_instant is None:
+        first_instant = (torch.rand((npair, T), device=dev) < 0.5).to(torch.uint8)
+    first_instant = nat.require_cuda(first_instant, torch.uint8, "first_instant")
+    if tuple(first_instant.shape) != (npair, T):
+        raise ValueError(f"first_instant must be ({npair},{T})")
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (npair, T, 3, 3):
+            raise ValueError(f"z must be ({npair},{T},3,3)")
+    if expo is not None:
+        expo = nat.require_cuda(expo, torch.float32, "expo")
+        if tuple(expo.shape) != (npair, T, 31, HW * HW):
+            raise ValueError(f"expo must be ({npair},{T},31,{HW * HW})")
+    m2, c2, a2 = mu.reshape(2 * npair, K, 2), cov.reshape(2 * npair, K, 2, 2), alpha.reshape(2 * npair, K, 2)
+    tab_f = skew_pdf_grid(m2, c2, a2, flip_alpha_y=True)
+    tab_r = skew_pdf_grid(m2, c2, a2, flip_alpha_y=False)
+    mc, cc = psm_conditionals(model, m2)
+    m_seq = torch.empty((npair, 2, P, P), dtype=torch.float64, device=dev)
+    c_seq = torch.empty((npair, 2, K, 4), dtype=torch.float64, device=dev)
+    out = torch.empty((npair, 2, T, K, 2), dtype=torch.float32, device=dev)
+    idx = torch.empty((npair, T, 31), dtype=torch.int32, device=dev) if return_indices else None
+    L = nat.lib()
+    with torch.cuda.device(dev):
+        st = nat.stream_ptr(dev)
+        nat.check(L.cub200_seq_skew_conditionals(nat.ptr(seq.c0), nat.ptr(seq.xbar), nat.ptr(seq.mean), nat.ptr(seq.scale),
+                                                 nat.ptr(mu), npair, nat.ptr(m_seq), nat.ptr(c_seq), st), "cub200_seq_skew_conditionals")
+        nat.check(L.cub200_seq_skew_sample(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), nat.ptr(tab_f), nat.ptr(tab_r), nat.ptr(mc),
+                                           nat.ptr(cc), nat.ptr(m_seq), nat.ptr(c_seq), nat.ptr(first_instant), nat.ptr(z),
+                                           nat.ptr(expo), int(seed) & (2**64 - 1), npair, T, nat.ptr(out), nat.ptr(idx), st),
+                  "cub200_seq_skew_sample")
     return (out, idx) if return_indices else out
 
 

@@ -223,6 +223,36 @@ int cub200_skew_sample(const float* mu, const float* cov, const float* alpha, co
                        int64_t n_samples, float* contours_out, int32_t* indices_out, void* stream);
 
 /*
+ * Skew-normal SEQUENCE sampler (ED/ES pairs): per (pair, first instant) the conditional law of the other instant under
+ * the 84-dim sequence shape model re-centred on the predicted pair.
+ *   replaces  pca(seq_X_train, sequence_transform(mu)) + posterior_shape_model(.., sigma2=1) + rescaling
+ *             cu/sampler/posterior_shape_model/psm_skew_sequence.py:66,72-86
+ *   seq_c0 (84,84), seq_xbar, seq_mean, seq_scale (84) fp64; mu (n_pairs,2,21,2) fp32
+ *   m_seq (n_pairs,2,42,42) fp64 [pair][b][e][row]; cov_seq (n_pairs,2,21,4) fp64 [pair][b][landmark][2x2]
+ */
+int cub200_seq_skew_conditionals(const double* seq_c0, const double* seq_xbar, const double* seq_mean,
+                                 const double* seq_scale, const float* mu, int64_t n_pairs, double* m_seq, double* cov_seq,
+                                 void* stream);
+
+/*
+ * Skew-normal SEQUENCE sampler: first a skew-PSM sample of the randomly chosen instant, then the other instant from
+ * pdfs = normalise(skew pdf x N(grid; sequence conditional)) -- its three initial points by a multinomial over pdfs, its
+ * level points over pdfs x N(grid; shape-model conditional).
+ *   replaces  SequenceSkewPSMSampler.__call__ / sample_two_contours   psm_skew_sequence.py:34-104
+ *   mu, cov, alpha (n_pairs,2,21,..) fp32; pdfs_flipped / pdfs_raw (2 n_pairs,21,256,256): cub200_skew_pdf_grid with
+ *   flip_alpha_y = 1 / 0 (the second instant's tables use alpha as given, :91); mc_t, covc per image
+ *   (cub200_psm_conditionals on the 2 n_pairs images); m_seq, cov_seq from cub200_seq_skew_conditionals
+ *   first_instant (n_pairs, n_samples) uint8 (random.randint(0,1), :45); z optional (n_pairs, n_samples, 3, 3);
+ *   expo optional (n_pairs, n_samples, 31, 65536): 14 races of the first instant, then 3 + 14 of the second
+ *   contours_out (n_pairs, 2, n_samples, 21, 2) fp32; indices_out optional (n_pairs, n_samples, 31) int32
+ */
+int cub200_seq_skew_sample(const float* mu, const float* cov, const float* alpha, const float* pdfs_flipped,
+                           const float* pdfs_raw, const double* mc_t, const double* covc, const double* m_seq,
+                           const double* cov_seq, const uint8_t* first_instant, const float* z, const float* expo,
+                           uint64_t seed, int64_t n_pairs, int64_t n_samples, float* contours_out, int32_t* indices_out,
+                           void* stream);
+
+/*
  * Simpson's biplane rule, step 1: per mask, the marching-squares contour (find_contours(mask, 0.5)[0]), the longest
  * admissible base chord, the apex and the 20 disc diameters.
  *   replaces  _compute_diameters (+ helpers)      vital/vital/metrics/evaluate/clinical/heart_us.py:74-167

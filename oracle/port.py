@@ -534,12 +534,14 @@ class SequenceShapeModel:
     Q: np.ndarray       # (84, 84)
     mean: np.ndarray    # scaler_mean (84,)
     scale: np.ndarray   # scaler_scale (84,)
+    X_train: Optional[np.ndarray] = None   # (N, 84): used by the skew sequence sampler, which re-centres the model
 
     @staticmethod
     def load(path: str) -> "SequenceShapeModel":
         d = np.load(str(path), allow_pickle=True).item()
         f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
-        return SequenceShapeModel(f32(d["mu"]).reshape(-1), f32(d["Q"]), f32(d["scaler_mean"]), f32(d["scaler_scale"]))
+        return SequenceShapeModel(f32(d["mu"]).reshape(-1), f32(d["Q"]), f32(d["scaler_mean"]).reshape(-1),
+                                  f32(d["scaler_scale"]).reshape(-1), f32(d["X_train"]))
 
 
 def seq_psm_sample(model: ShapeModel, seq: SequenceShapeModel, mu: np.ndarray, cov: np.ndarray,
@@ -657,30 +659,44 @@ def skew_numerical_sampling(p1: np.ndarray, mu2: np.ndarray, cov2: np.ndarray, q
 
 
 def skew_psm_sample(model: ShapeModel, mu: np.ndarray, cov: np.ndarray, alpha: np.ndarray, z: np.ndarray,
-                    q_fn, store=np.float32, return_indices: bool = False):
+                    q_fn, store=np.float32, return_indices: bool = False, pdfs: Optional[np.ndarray] = None,
+                    use_initial_pdf: bool = False):
     """``SkewPosteriorShapeModelSampler.sample_one_instant`` + ``sample_contour`` (psm_skew.py:210-411)
     for one image, skew_indices = all points, random draws fed in.
 
     mu (K,2), cov (K,2,2), alpha (K,2) as predicted (the sampler's own alpha * [1,-1], :232, happens
     here); z (n, 3, 3): the (1,3) normals of ``rvs_fast`` for the initial points 0, 10, 20;
     ``q_fn(sample, draw)`` -> (65536,) Exp(1) field of the draw-th multinomial of the sample (14 per
-    sample, in level order).  Returns (n, K, 2) [, flat grid indices (n, 14), -1 = fallback to mu_c]."""
+    sample, in level order).  Returns (n, K, 2) [, flat grid indices (n, 14), -1 = fallback to mu_c].
+
+    ``pdfs`` (K,256,256) replaces the skew-normal tables and ``use_initial_pdf`` draws the three initial points
+    from them by multinomial too (``numerical_sample``, psm_skew.py:450-466; then ``z`` is unused, 17 draws per
+    sample, indices (n, 17)) -- the second instant of the sequence sampler (psm_skew_sequence.py:102-103)."""
     mu = np.asarray(mu, dtype=np.float64)
     cov = np.asarray(cov, dtype=np.float64)
     alpha = np.asarray(alpha, dtype=np.float64) * np.array([1.0, -1.0])     # psm_skew.py:232
     K = mu.shape[0]
     mu_t = (mu.reshape(-1) - model.mean) / model.scale
     S = pca_cov(model.X_train, mu_t)                                        # psm_skew.py:228
-    pdfs = skew_pdf_grid(mu, cov, alpha).astype(store)                      # psm_skew.py:234-238
+    if pdfs is None:
+        pdfs = skew_pdf_grid(mu, cov, alpha).astype(store)                  # psm_skew.py:234-238
     sigmas = [1, 1, 1, 1]
-    out = np.zeros((z.shape[0], K, 2))
-    indices = np.full((z.shape[0], 14), -1, dtype=np.int64)
-    for n in range(z.shape[0]):
+    n_s = len(z)
+    out = np.zeros((n_s, K, 2))
+    indices = np.full((n_s, 17 if use_initial_pdf else 14), -1, dtype=np.int64)
+    for n in range(n_s):
         s = np.zeros((K, 2))
         sampled = list(model.initial_points)
-        for zi, j in enumerate(model.initial_points):                       # :281 -> :414-448
-            s[j] = skew_rvs_fast(mu[j], cov[j], alpha[j], z[n, zi])
         di = 0
+        for zi, j in enumerate(model.initial_points):
+            if use_initial_pdf:                                             # :279 -> numerical_sample :450-466
+                with np.errstate(under="ignore", over="ignore", divide="ignore"):
+                    idx = int(np.argmax(np.asarray(pdfs[j]).astype(store).reshape(-1) / np.asarray(q_fn(n, di)).astype(store)))
+                s[j] = (idx // 256, idx % 256)
+                indices[n, di] = idx
+                di += 1
+            else:                                                           # :281 -> :414-448
+                s[j] = skew_rvs_fast(mu[j], cov[j], alpha[j], z[n, zi])
         for lvl, points in enumerate(model.points_order):
             sampled.sort()
             if len(sampled) == K:
@@ -992,3 +1008,47 @@ def us_skew_umap(mu, cov, alpha):
     """USSkewUmap.__call__ (cu/data/camus/utils.py:127-153), LV-only labels."""
     mode, m = skew_umap(mu, cov, alpha, linear_close=True)
     return mode, m / m.max()
+
+
+
+def seq_skew_psm_sample(model: ShapeModel, seq: "SequenceShapeModel", mu: np.ndarray, cov: np.ndarray, alpha: np.ndarray,
+                        first_instant: np.ndarray, z: np.ndarray, q_fn, store=np.float32, return_indices: bool = False):
+    """``SequenceSkewPSMSampler.__call__`` + ``sample_two_contours`` (psm_skew_sequence.py:34-104), draws fed in.
+
+    mu (2,K,2), cov (2,K,2,2), alpha (2,K,2); first_instant (n,); z (n,3,3): rvs_fast normals of the first-sampled
+    instant; ``q_fn(sample, draw)``: 31 Exp(1) fields per sample (14 of the first instant, then 3 + 14 of the second).
+    The 84-dim sequence model IS re-centred on the predicted pair here (:66), unlike sequence_sampler.py.
+    Returns (2, n, K, 2) [, indices (n, 31)]."""
+    mu = np.asarray(mu, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64)
+    alpha = np.asarray(alpha, dtype=np.float64)
+    K = mu.shape[1]
+    mu_t = (mu.reshape(-1) - seq.mean) / seq.scale
+    S = pca_cov(seq.X_train, mu_t)                                           # :66
+    grid = skew_grid()
+    out = np.zeros((2, len(first_instant), K, 2))
+    idx_all = np.full((len(first_instant), 31), -1, dtype=np.int64)
+    for n, b in enumerate(first_instant):
+        b = int(b)
+        o = 1 - b
+        s1, i1 = skew_psm_sample(model, mu[b], cov[b], alpha[b], z[n][None], lambda _n, d: q_fn(n, d), store, True)   # :70
+        s_g = np.zeros((2, K, 2))
+        s_g[b] = s1[0]
+        s_t = (s_g.reshape(-1) - seq.mean) / seq.scale
+        g = index_to_flat(range(K) if b == 0 else range(K, 2 * K))
+        mu_c, cov_c = posterior_shape_model(s_t, g, mu_t, S, 1.0)           # :78
+        mu_c = (mu_c * seq.scale + seq.mean).reshape(2, K, 2)
+        cov_c = cov_c * seq.scale[None, :]
+        cov_c = np.stack([cov_c[2 * i:2 * i + 2, 2 * i:2 * i + 2] for i in range(2 * K)]).reshape(2, K, 2, 2)
+        pdfs = []
+        for i in range(K):                                                   # :89-96 (alpha NOT sign-flipped here)
+            sp = np.exp(skew_logpdf(grid, mu[o, i], cov[o, i], alpha[o, i])).astype(store)
+            pp = np.exp(normal_logpdf(grid, mu_c[o, i], cov_c[o, i])).astype(store)
+            with np.errstate(under="ignore", invalid="ignore", divide="ignore"):
+                p = (sp * pp).astype(store)
+                pdfs.append((p / p.sum(dtype=store)).astype(store))
+        s2, i2 = skew_psm_sample(model, mu[o], cov[o], alpha[o], [None], lambda _n, d: q_fn(n, 14 + d), store, True,
+                                 pdfs=np.stack(pdfs), use_initial_pdf=True)                                            # :102
+        out[b, n], out[o, n] = s1[0], s2[0]
+        idx_all[n, :14], idx_all[n, 14:] = i1[0], i2[0]
+    return (out, idx_all) if return_indices else out

@@ -352,6 +352,83 @@ def golden_umap():
     print("umap.npz", {k: np.asarray(v).shape for k, v in out.items() if not k[-1].isdigit()}, "value", VAL)
 
 
+def golden_seqskew():
+    """SequenceSkewPSMSampler.__call__ (psm_skew_sequence.py) with first-instant bits, rvs_fast normals and the
+    31 multinomial races per sample replayed; fp32 and fp64 runs of the unmodified code."""
+    import random
+
+    from contour_uncertainty.sampler.posterior_shape_model.psm_skew_sequence import SequenceSkewPSMSampler
+
+    SEQ_PATH = os.path.join(_refstub.REFERENCE_ROOT, "camus-cont_sequence_psm_11_no_std.npy")
+    Q_SEED = 113
+    n_pair, n_s = 2, 3
+    mus, covs = synth.point_distributions(2 * n_pair, seed=111)
+    mus = mus.reshape(n_pair, 2, 21, 2).copy()
+    ctr = mus[:, 1].mean(1, keepdims=True)
+    mus[:, 1] = ctr + (mus[:, 0] - mus[:, 0].mean(1, keepdims=True)) * 0.8 + np.random.default_rng(5).normal(0, 1.0, (n_pair, 21, 2)).astype(np.float32)
+    covs = covs.reshape(n_pair, 2, 21, 2, 2)
+    alphas = synth.skew_alphas(2 * n_pair, seed=112).reshape(n_pair, 2, 21, 2)
+    rng = np.random.default_rng(114)
+    z = rng.standard_normal((n_pair, n_s, 3, 3)).astype(np.float32)
+    bits = rng.integers(0, 2, (n_pair, n_s))
+    bits[0, 0], bits[0, 1] = 0, 1
+    real_multinomial = torch.multinomial
+    outs, idxs = {}, {}
+    for mode in ("f32", "f64"):
+        if mode == "f64":
+            torch.set_default_dtype(torch.float64)
+        try:
+            smp = SequenceSkewPSMSampler(PSM_PATH, SEQ_PATH)
+            if mode == "f64":
+                for a in ("mean", "scale", "X_train", "mu", "Q", "seq_mu", "seq_Q", "seq_mean", "seq_scale", "seq_X_train"):
+                    setattr(smp, a, getattr(smp, a).double())
+            res = np.zeros((n_pair, 2, n_s, 21, 2))
+            index_log = []
+            for i in range(n_pair):
+                state = {"draw": 0}
+
+                def fake_multinomial(p, n, *a, _i=i, _st=state, **k):
+                    d = _st["draw"]
+                    _st["draw"] += 1
+                    stream = (_i * n_s + d // 31) * 31 + d % 31
+                    try:
+                        real_multinomial(p, n)
+                    except Exception:
+                        index_log.append(-1)
+                        raise
+                    q = torch.from_numpy(synth.exponential_field(Q_SEED, stream)).to(p.dtype)
+                    idx = torch.argmax(p / q).reshape(1)
+                    index_log.append(int(idx))
+                    return idx
+
+                dt = np.float64 if mode == "f64" else np.float32
+                draws = [z[i, s, d][None].astype(dt) for s in range(n_s) for d in range(3)]
+                it = iter(bits[i].tolist())
+                orig = random.randint
+                random.randint = lambda a, b, _it=it: int(next(_it))
+                torch.multinomial = fake_multinomial
+                try:
+                    with _refstub.replay_standard_normal(draws) as log:
+                        m, c, al = (torch.from_numpy(a[i]) for a in (mus, covs, alphas))
+                        if mode == "f64":
+                            m, c, al = m.double(), c.double(), al.double()
+                        r = smp(m, c, al, n=n_s)
+                finally:
+                    torch.multinomial = real_multinomial
+                    random.randint = orig
+                assert len(log) == 3 * n_s and state["draw"] == 31 * n_s, (len(log), state["draw"])
+                res[i] = r.detach().numpy()
+            outs[mode] = res
+            idxs[mode] = np.array(index_log).reshape(n_pair, n_s, 31)
+        finally:
+            torch.set_default_dtype(torch.float32)
+    print("seqskew: fp32-vs-fp64 identical draws", (idxs["f32"] == idxs["f64"]).mean(), "fallbacks", (idxs["f32"] < 0).sum(),
+          "max diff (px)", np.abs(outs["f32"] - outs["f64"]).max())
+    np.savez_compressed(os.path.join(HERE, "seqskew.npz"), mu=mus, cov=covs, alpha=alphas, z=z, bits=bits, q_seed=Q_SEED,
+                        samples=outs["f32"].astype(np.float32), samples_f64=outs["f64"], indices=idxs["f32"], indices_f64=idxs["f64"])
+    print("seqskew.npz", outs["f32"].shape)
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -390,6 +467,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew"]
     for w in which:
         globals()["golden_" + w]()

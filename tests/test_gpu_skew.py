@@ -174,3 +174,32 @@ def test_skew_sampler_philox_statistics(dev, model):
     zs = np.array(zs)                                   # standardised residuals: mean 0, variance 1
     assert np.abs(zs.mean(0)).max() < 4 / np.sqrt(400)
     assert np.abs(zs.var(0) - 1).max() < 0.25
+
+
+def test_sequence_skew_sampler_replay_vs_reference(dev, model):
+    """SequenceSkewPSMSampler with the reference's draws replayed: all 31 grid indices per sample equal the
+    reference's (fp32 and fp64 runs agree on them), float coordinates to 2e-4 px."""
+    from contouring_uncertainty_b200 import engine as E
+    from contouring_uncertainty_b200.sampler import SequenceSkewPSMSampler
+
+    g = np.load(os.path.join(G, "seqskew.npz"))
+    n_pair, n_s = g["z"].shape[:2]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ex = np.stack([np.stack([np.stack([synth.exponential_field(int(g["q_seed"]), (i * n_s + s) * 31 + d) for d in range(31)])
+                             for s in range(n_s)]) for i in range(n_pair)])
+    seq = E.SequenceModelConstants(device=dev)
+    out, idx = E.seq_skew_sample(model, seq, t(g["mu"]), t(g["cov"]), t(g["alpha"]), n_s, first_instant=t(g["bits"].astype(np.uint8)),
+                                 z=t(g["z"]), expo=t(ex), return_indices=True)
+    assert np.array_equal(idx.cpu().numpy(), g["indices_f64"])
+    assert np.abs(out.cpu().numpy() - g["samples_f64"]).max() < 2e-4
+    assert np.abs(out.cpu().numpy() - g["samples"]).max() < 5e-2          # the verbatim fp32 run's own noise on the filled points
+    smp = SequenceSkewPSMSampler()
+    o2 = smp(torch.from_numpy(g["mu"][0]), torch.from_numpy(g["cov"][0]), torch.from_numpy(g["alpha"][0]), n=n_s,
+             first_instant=g["bits"][0], z=g["z"][0], expo=ex[0])
+    assert o2.shape == (2, n_s, 21, 2) and np.array_equal(o2.numpy(), out[0].cpu().numpy())
+    # production RNG: seeded, both instants integer-valued on the level points, ED/ES areas correlated
+    o3 = E.seq_skew_sample(model, seq, t(g["mu"]), t(g["cov"]), t(g["alpha"]), 64, seed=3)
+    o4 = E.seq_skew_sample(model, seq, t(g["mu"]), t(g["cov"]), t(g["alpha"]), 64, seed=3)
+    assert o3.shape == (n_pair, 2, 64, 21, 2) and torch.isfinite(o3).all()
+    lvl = [5, 15, 2, 7, 13, 18, 1, 3, 6, 8, 12, 14, 17, 19]
+    assert torch.equal(o3[:, :, :, lvl], o3[:, :, :, lvl].round())

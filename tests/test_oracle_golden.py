@@ -217,3 +217,18 @@ def test_umaps_match_reference():
             mode, sk = port.us_skew_umap(mu, cov, al)
             ref = _sparse_map(g, "skew_umap", i)
             assert np.abs(mode - g["mode"][i]).max() < 1e-4 and (np.abs(sk - ref) > 1e-12).sum() <= 8
+
+
+def test_sequence_skew_sampler_matches_reference():
+    """psm_skew_sequence.py with first-instant bits, rvs_fast normals and all 31 multinomial races replayed."""
+    g = np.load(os.path.join(G, "seqskew.npz"))
+    D = os.path.join(os.path.dirname(G), "..", "contouring_uncertainty_b200", "data")
+    model = port.ShapeModel.load(os.path.join(D, "camus-cont_psm_11_no_std.npy"))
+    seq = port.SequenceShapeModel.load(os.path.join(D, "camus-cont_sequence_psm_11_no_std.npy"))
+    n_s = g["z"].shape[1]
+    i = 0
+    qf = lambda n, d: synth.exponential_field(int(g["q_seed"]), (i * n_s + n) * 31 + d)
+    s, idx = port.seq_skew_psm_sample(model, seq, g["mu"][i], g["cov"][i], g["alpha"][i], g["bits"][i], g["z"][i], qf,
+                                      store=np.float64, return_indices=True)
+    assert np.array_equal(idx, g["indices_f64"][i]) and np.abs(s - g["samples_f64"][i]).max() < 1e-9
+    assert np.array_equal(g["indices"], g["indices_f64"])          # the verbatim fp32 run drew the same cells
