@@ -160,12 +160,15 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     Chord best{0, 0x7fffffff, 0x7fffffff};
     for (int i = 2; i < n; ++i) {
         const int ir = P[i] & 0xffff, ic = P[i] >> 16;
+        // a chord shorter than the best one any lane holds can never be selected (equal ones still can: ties go to the
+        // first (i, j) in loop order)
+        const int wbest = __reduce_max_sync(FULL, best.len2);
         for (int j = lane; j < i; j += 32) {
             const int ar = (int)(P[j] & 0xffff) - ir, ac = (int)(P[j] >> 16) - ic;     // contour[j] - contour[i]
             // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
             if (!(ac > 0 && abs(ar) <= ac)) continue;
             const int len2 = ar * ar + ac * ac;
-            if (len2 <= best.len2) continue;           // cannot beat this lane's best: skip the intermediate test
+            if (len2 <= best.len2 || len2 < wbest) continue;   // cannot be selected: skip the intermediate test
             const int64_t lim = 256ll * len2;          // (8 px)^2 * len2 in half-pixel units: cross^2 <= 256 len2
             bool ok = true;
             {   // most far-away chords fail at the middle of the span: test it first
