@@ -54,3 +54,49 @@ def reduce_dataset_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats
+
+
+class StepExchange:
+    """The end-of-step exchange, overlapped with the next step's kernels.
+
+    Step i's per-image distributions (equal shard sizes) and dataset-level sums are copied into slot
+    ``i % depth`` and exchanged with ONE ``all_gather_into_tensor`` + one ``all_reduce`` issued with
+    ``async_op=True``: NCCL's stream waits for the producing kernels, the compute stream does not wait for
+    NCCL, so step i + 1 runs while step i's exchange is in flight.  A slot is reused only after its previous
+    exchange has completed (``wait`` before the copy).  ``finish()`` joins everything onto the current stream.
+    """
+
+    def __init__(self, n_local: int, tail_shape: Sequence[int], dtype, n_stats: int, device, depth: int = 2, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append({
+                "local": torch.empty((n_local,) + tuple(tail_shape), dtype=dtype, device=device),
+                "gathered": torch.empty((self.world * n_local,) + tuple(tail_shape), dtype=dtype, device=device),
+                "stats": torch.empty((n_stats,), dtype=torch.float64, device=device),
+                "works": [],
+            })
+        self.last = None
+
+    def submit(self, step: int, local: torch.Tensor, stats: torch.Tensor):
+        slot = self.slots[step % len(self.slots)]
+        for w in slot["works"]:
+            w.wait()
+        slot["local"].copy_(local, non_blocking=True)
+        slot["stats"].copy_(stats, non_blocking=True)
+        if self.world > 1:
+            slot["works"] = [dist.all_gather_into_tensor(slot["gathered"], slot["local"], group=self.group, async_op=True),
+                             dist.all_reduce(slot["stats"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)]
+        else:
+            slot["gathered"].copy_(slot["local"], non_blocking=True)
+        self.last = slot
+        return slot
+
+    def finish(self):
+        """Wait for every exchange in flight; returns (gathered, stats) of the last submitted step."""
+        for slot in self.slots:
+            for w in slot["works"]:
+                w.wait()
+            slot["works"] = []
+        return (self.last["gathered"], self.last["stats"]) if self.last is not None else (None, None)

@@ -67,3 +67,29 @@ def test_null_and_bad_sizes_return_einval():
     assert l.cub200_finalize_maps(None, 1, 10, None, None, None, None, None, None) == _native.EINVAL
     # zero-sized work is a no-op success even without a device
     assert l.cub200_rasterize_contours(None, 0, 1, None, None, None, 0, None) == 0
+
+
+def test_new_entry_points_validate_arguments():
+    """Skew / sequence / u-map / Simpson entry points: null pointers and bad sizes -> EINVAL, empty work -> 0."""
+    from contouring_uncertainty_b200 import _native
+
+    l, E = _native.lib(), _native.EINVAL
+    assert l.cub200_skew_pdf_grid(None, None, None, 1, 1, None, None) == E
+    assert l.cub200_psm_conditionals(None, None, None, None, None, 1, None, None, None) == E
+    assert l.cub200_skew_sample(None, None, None, None, None, None, None, None, 0, 1, 1, None, None, None) == E
+    assert l.cub200_seq_skew_conditionals(None, None, None, None, None, 1, None, None, None) == E
+    assert l.cub200_seq_skew_sample(*([None] * 12), 0, 1, 1, None, None, None) == E
+    assert l.cub200_projected_uncertainty(None, None, None, 1, 1, 0, None, None, None, None) == E
+    assert l.cub200_umap_analytic(None, None, None, 1, None, 1, None, None, None) == E
+    assert l.cub200_skew_umap_contours(None, None, None, None, 1, None, None, None) == E
+    assert l.cub200_weighted_mask_entropy(None, None, 1, 200, 1.0, 1, None, None) == E
+    assert l.cub200_simpson_diameters(None, 1, 0.5, None, None, None, None, None) == E
+    assert l.cub200_simpson_volumes(None, None, 1, 1, None, None, None, None) == E
+    assert l.cub200_rasterize_contours_f64(None, 1, 0, None, None, None, 0, None) == E
+    # empty work is a no-op
+    assert l.cub200_skew_pdf_grid(None, None, None, 0, 1, None, None) == E      # null pointers are refused first
+    assert l.cub200_simpson_diameters(None, 0, 0.5, None, None, None, None, None) == 0
+    assert l.cub200_simpson_volumes(None, None, 0, 10, None, None, None, None) == 0
+    assert l.cub200_projected_uncertainty(None, None, None, 0, 1, 0, None, None, None, None) == 0
+    assert l.cub200_rasterize_contours_f64(None, 0, 0, None, None, None, 0, None) == 0
+    assert l.cub200_simpson_workspace_bytes(10) == 10 * (2048 * 4 + 4)

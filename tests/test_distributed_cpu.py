@@ -47,3 +47,29 @@ def test_gather_and_reduce_world_size_2_gloo():
     s.close()
     # 5 patients x 2 images over 2 ranks -> ragged shards (6 and 4 images)
     mp.spawn(_worker, args=(2, port, 10, 7), nprocs=2, join=True)
+
+
+def _exchange_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_local, T = 3, 5
+        ex = P.StepExchange(n_local, (T,), torch.int32, 2, "cpu", depth=2)
+        for step in range(5):                                   # slots are reused: 5 steps over depth 2
+            local = torch.full((n_local, T), 100 * step + rank, dtype=torch.int32)
+            ex.submit(step, local, torch.tensor([float(step + rank), 1.0], dtype=torch.float64))
+        gathered, stats = ex.finish()
+        want = torch.cat([torch.full((n_local, T), 400 + r, dtype=torch.int32) for r in range(world)])
+        assert torch.equal(gathered, want)
+        assert stats.tolist() == [float(sum(4 + r for r in range(world))), float(world)]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_step_exchange_world_size_2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_exchange_worker, args=(2, port), nprocs=2, join=True)
