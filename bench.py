@@ -230,13 +230,14 @@ def run_ours(args):
     ws = eng.workspace(N_IMG, T_A)
     # the path's only exchange (NCCL): per-image area distributions (all_gather) + dataset-level sums (all_reduce),
     # issued asynchronously so that it overlaps the next step's kernels; joined before the timed region ends
-    exch = PAR.StepExchange(N_IMG, (T_A,), torch.int32, 2, dev, depth=2) if world > 1 else None
+    exch = PAR.StepExchange(N_IMG, (T_A,), torch.int32, 2, dev, depth=2, stats_dtype=torch.int64) if world > 1 else None
+    sums = torch.empty((2,), dtype=torch.int64, device=dev)
 
     def step(i):
         """One pass of the hot path over the batch: 6 launches of libcub200 into preallocated buffers."""
         eng.run_into(ws, logits, seed=1000 + i)
         if world > 1:
-            exch.submit(i, ws.area, torch.stack([ws.area.sum().double(), ws.mean.sum()]))
+            exch.submit(i, ws.area, E.metric_sums(ws.area, out=sums))
 
     def step_evented(i):
         """Same kernels through the allocating per-op API with an event between them (per-kernel times)."""
@@ -276,12 +277,13 @@ def run_ours(args):
     for i in range(args.steps):
         step(args.warmup + i)
     if exch is not None:
-        gathered, _ = exch.finish()          # the compute stream joins the last exchanges: inside the timed region
+        gathered, totals = exch.finish()     # the compute stream joins the last exchanges: inside the timed region
     t1.record(stream)
     sync_all()
     ms_total = t0.elapsed_time(t1)
     if exch is not None:
         assert gathered.shape == (world * N_IMG, T_A) and torch.equal(gathered[rank * N_IMG:(rank + 1) * N_IMG], ws.area)
+        assert int(totals[0]) == int(gathered.sum())
     clk = clocks.stop() if (rank == 0 and not args.no_clocks) else None
     evs = [step_evented(i) for i in range(min(args.steps, 20))]
     sync_all()
@@ -363,7 +365,7 @@ def run_ours(args):
         "roofline_dsnt": roof("dsnt"),
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 5 * args.steps,   # dsnt, psm_factor, fused, entropy_lut, finalize per step
+        "gpu_launches": (5 + (1 if world > 1 else 0)) * args.steps,   # dsnt, psm_factor, fused, entropy_lut, finalize (+ metric_sums) per step
         "clocks": clk,
         "parity_spot_check": parity_ok and e2e_check,
     }

@@ -43,6 +43,7 @@ SIGNATURES = {
     "cub200_weighted_mask_entropy": [_vp, _vp, _i64, _i32, C.c_double, _i32, _vp, _vp],
     "cub200_seq_skew_conditionals": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_seq_skew_sample": [_vp] * 12 + [_u64, _i64, _i64, _vp, _vp, _vp],
+    "cub200_metric_sums": [_vp, _i64, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes")
 

@@ -86,6 +86,21 @@ __global__ void fac_kernel(const int32_t* __restrict__ ed, const int32_t* __rest
     out[i] = f;
 }
 
+// Dataset-level accumulators of a per-sample integer metric (sum, sum of squares): exact in 64-bit integers, so the
+// result does not depend on the order of the atomics; these are what the ranks all_reduce at the end of a step.
+__global__ void __launch_bounds__(256)
+metric_sums_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0, s2 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long x = v[i];
+        s += (unsigned long long)x;
+        s2 += (unsigned long long)(x * x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(FULL, s, o); s2 += __shfl_xor_sync(FULL, s2, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicAdd(out + 1, s2); }
+}
+
 // post_mu / post_cov of aleatoric.py:96-102: thread (k, sg) streams the float2 of landmark k over the
 // samples sg, sg+12, ...; moments about the first sample (no cancellation), fp64, block reduction.
 constexpr int SM_GROUPS = 12;
@@ -154,4 +169,15 @@ extern "C" int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area
     if (n == 0) return 0;
     fac_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(area_ed, area_es, n, fac_out);
     return check_launch("fac_kernel");
+}
+
+extern "C" int cub200_metric_sums(const int32_t* values, int64_t n, int64_t* sums_out, void* stream) {
+    using namespace cub200;
+    if (!sums_out || n < 0 || (n > 0 && !values)) return CUB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUB200_CUDA_OK(cudaMemsetAsync(sums_out, 0, 2 * sizeof(int64_t), st));
+    if (n == 0) return 0;
+    const int64_t blocks = (n + 255) / 256;
+    metric_sums_kernel<<<(unsigned)(blocks < 592 ? blocks : 592), 256, 0, st>>>(values, n, reinterpret_cast<unsigned long long*>(sums_out));
+    return check_launch("metric_sums_kernel");
 }

@@ -236,6 +236,17 @@ def fac_from_areas(area_ed: torch.Tensor, area_es: torch.Tensor) -> torch.Tensor
     return out
 
 
+def metric_sums(values: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(sum, sum of squares) of an int32 per-sample metric as exact int64 (dataset-level accumulators)."""
+    values = nat.require_cuda(values, torch.int32, "values")
+    if out is None:
+        out = torch.empty((2,), dtype=torch.int64, device=values.device)
+    with torch.cuda.device(values.device):
+        rc = nat.lib().cub200_metric_sums(nat.ptr(values), values.numel(), nat.ptr(out), nat.stream_ptr(values.device))
+    nat.check(rc, "cub200_metric_sums")
+    return out
+
+
 class SequenceModelConstants:
     """Per-model constants of the 84-dim (ED, ES) sequence shape model (sequence_sampler.py:15-24).
 

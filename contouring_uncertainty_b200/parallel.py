@@ -66,7 +66,8 @@ class StepExchange:
     exchange has completed (``wait`` before the copy).  ``finish()`` joins everything onto the current stream.
     """
 
-    def __init__(self, n_local: int, tail_shape: Sequence[int], dtype, n_stats: int, device, depth: int = 2, group=None):
+    def __init__(self, n_local: int, tail_shape: Sequence[int], dtype, n_stats: int, device, depth: int = 2, group=None,
+                 stats_dtype=torch.float64):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.slots = []
@@ -74,7 +75,7 @@ class StepExchange:
             self.slots.append({
                 "local": torch.empty((n_local,) + tuple(tail_shape), dtype=dtype, device=device),
                 "gathered": torch.empty((self.world * n_local,) + tuple(tail_shape), dtype=dtype, device=device),
-                "stats": torch.empty((n_stats,), dtype=torch.float64, device=device),
+                "stats": torch.empty((n_stats,), dtype=stats_dtype, device=device),
                 "works": [],
             })
         self.last = None

@@ -152,6 +152,13 @@ int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_
                           void* stream);
 
 /*
+ * Dataset-level accumulators of a per-sample integer metric (LV areas): sums_out[0] = sum v, sums_out[1] = sum v^2,
+ * exact 64-bit integers (what the ranks all_reduce at the end of a step; mean / std of the pooled distribution follow).
+ *   replaces  the np.mean / np.std reductions over gathered per-sample metrics   cu/results/clinical/utils.py:3-18
+ */
+int cub200_metric_sums(const int32_t* values, int64_t n, int64_t* sums_out, void* stream);
+
+/*
  * Posterior moments of the sampled contours: per (image, landmark) the sample mean and the unbiased
  * 2x2 sample covariance over the T samples.
  *   replaces  post_mu = contour_samples.mean(axis=2); post_cov = np.cov(...)   cu/task/regression/aleatoric.py:96-102

@@ -267,3 +267,12 @@ def test_empty_and_bad_inputs(dev, eng):
         dsnt_moments(torch.zeros((1, 21, 256, 256)))          # CPU tensor: no fallback
     with pytest.raises(ValueError):
         rasterize_contours(torch.zeros((3, 20, 2), device=dev))
+
+
+def test_metric_sums_exact(dev):
+    from contouring_uncertainty_b200 import engine as E
+
+    a = torch.randint(0, 40000, (64, 1000), dtype=torch.int32, device=dev)
+    s = E.metric_sums(a)
+    assert s.tolist() == [int(a.sum()), int((a.long() * a.long()).sum())]
+    assert E.metric_sums(a[:0].contiguous()).tolist() == [0, 0]
