@@ -23,7 +23,8 @@ _vp, _i32, _i64, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
 # name -> argtypes; every function returns int except the three queries
 SIGNATURES = {
     "cub200_dsnt_moments": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
-    "cub200_psm_factor": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "cub200_psm_model_pack_host": [_vp, _vp, _vp, _vp, _vp],
+    "cub200_psm_factor": [_vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
     "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
@@ -32,7 +33,7 @@ SIGNATURES = {
     "cub200_sample_moments": [_vp, _i64, _i64, _vp, _vp, _vp],
     "cub200_seq_condition": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cub200_skew_pdf_grid": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],
-    "cub200_psm_conditionals": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cub200_psm_conditionals": [_vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_skew_sample": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _vp, _vp],
     "cub200_simpson_diameters": [_vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_simpson_volumes": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],

@@ -1,236 +1,264 @@
-// K2  psm_factor: the affine map of the hierarchical posterior-shape-model sampler, per image.
+// K2  psm_factor / psm_conditionals: the hierarchical posterior-shape-model sampler reduced to per-image
+// (or per-sample) constants, ONE WARP per image, no eigendecomposition, no factorisation at run time.
 //
-// The reference re-runs a 42x42 eigendecomposition per image and two 42x42 fp32 inverses per level
-// per SAMPLE (contour_uncertainty/sampler/posterior_shape_model/psm.py:91,265-352;
-// posteriorshapemodel.py:9-81).  The sampler is exactly affine in its standard-normal draws:
-//     contour = mu + A z,   z in R^34,  A in R^(42x34)            
-// so everything is hoisted to once per image and done eig-free with S = Q Q^T = C0 + d d^T,
-// d = xbar - transform(mu):
-//     mu_c  = mu + S[:,g] (S[g,g] + s2 I)^-1 (s_g - mu_g)
-//     Sig_c = S - S[:,g] (S[g,g] + s2 I)^-1 S[g,:]                (only 2x2 diagonal blocks used)
-//     merge_priors: G = cov_p (cov_p + cov_c)^-1, cov_f = G cov_c, mu_f - mu = G (mu_c - mu)
-//     draw: mu_f + chol(cov_f) z_slot
-// One CTA per image, fp64 throughout (34x34 Cholesky at most), result stored fp32 transposed
-// (draw-major) for the coalesced reads of the fused sampler.
+// The reference re-runs a 42x42 eigendecomposition per image and two 42x42 fp32 inverses per level per
+// SAMPLE (contour_uncertainty/sampler/posterior_shape_model/psm.py:91,265-352; posteriorshapemodel.py:9-81).
+// Facts used here:
+//   * pca() about the centre transform(mu) only enters through S = Q Q^T = C0 + d d^T, C0 = covariance of
+//     X_train about its own mean (a constant of the model), d = xbar - transform(mu);
+//   * the conditioning sets of the three levels and of the final fill are PREFIXES of the sampling order
+//     (points 0,10,20 | 5,15 | 2,7,13,18 | 1,3,6,8,12,14,17,19 | 4,9,11,16), with noise sigma2 = 1,1,1,1e-3;
+//   * so with B = C0[g,g] + sigma2 I (constant) Sherman-Morrison gives, for u = B^-1 d_g, gamma = 1/(1 + d_g^T u):
+//         M     = S[r,g] (S[g,g] + sigma2 I)^-1 = K + gamma (d_r - C0[r,g] u) u^T,          K = C0[r,g] B^-1
+//         Sig_c = S[r,r] - M S[g,r]             = Sig0 + d_r d_r^T - (K d_g) d_r^T - c w^T - (c s) d_r^T
+//     (c = gamma (d_r - w), w = C0[r,g] u, s = d_g^T u, Sig0 = C0[r,r] - K C0[g,r]); only 2x2 diagonal blocks are used.
+//   B^-1, K, C0[r,g] and Sig0 of the four levels are packed once per shape model (cub200_psm_model_pack_host);
+//   per image the work is a few mat-vecs and the (rows x n)(n x 34) product K At_g.
+//   * the Gaussian sampler is affine in its draws, contour = mu + A z (A: 42 x 34): per level
+//         mu_c - mu = scale M At_g z,  merge_priors: G = cov_p (cov_p + cov_c)^-1, cov_f = G cov_c,
+//         draw: mu_f + chol(cov_f) z_slot                                            psm.py:265-285, 424-440
+//     the skew sampler needs M itself (its level points are grid draws): psm_conditionals.
+#include <cmath>
+#include <utility>
+#include <vector>
 #include "common.cuh"
 
 namespace cub200 {
 
-constexpr int PF_THREADS = 256;
 constexpr int P = CUB200_P;   // 42
-constexpr int Z = 34;         // draws of the PSM sampler
+constexpr int Z = 34;         // draws of the PSM sampler = sampled coordinates
+constexpr int PF_WARPS = 4;
 
-// Landmarks in sampling order: initial [0,10,20], levels [5,15], [2,7,13,18], [1,3,6,8,12,14,17,19]
-// (get_points_order, psm.py:43-71), then the four posterior-mean-filled points.  The draw slot of
-// the landmark at position pi < 17 is pi.
+// Landmarks in sampling order (get_points_order, psm.py:43-71), then the four posterior-mean-filled points.
+// Everything below works on the permuted variables v = 2 * position + coordinate.
 __constant__ int c_order[21] = {0, 10, 20, 5, 15, 2, 7, 13, 18, 1, 3, 6, 8, 12, 14, 17, 19, 4, 9, 11, 16};
+static const int h_order[21] = {0, 10, 20, 5, 15, 2, 7, 13, 18, 1, 3, 6, 8, 12, 14, 17, 19, 4, 9, 11, 16};
 
-// Everything is done in the permuted variable order v = 2*pi + c, so every conditioning set is a
-// prefix [0, n) with n = 6, 10, 18, 34, and ONE right-looking Cholesky sweep serves all levels:
-// after eliminating the first n variables of T = S + s2 I_[0,n) the trailing block holds the
-// posterior covariance Sig_c = S22 - S21 G^-1 S12, and Acc = L21 (L11^-1 At_g) holds the posterior
-// mean map M At_g (At = A / scale, the sampled contour in the scaler's space).
-struct PFShared {
-    double T[P][P + 1];     // working matrix (lower part: L; trailing block: Schur complement)
-    double A[P][Z];         // pixel-space map of every variable (row v = permuted variable)
-    double Acc[P][Z];       // sum_k L[v][k] y_k
-    double y[Z];
-    double col[P];
-    double scale[P];
-    double d[P];
-    int perm[P];
+// level l: positions [p0, p1), observed prefix n = 2 p0 variables, rows = 2 (p1 - p0)
+struct LevelDef { int p0, p1, n, rows; double sigma2; int off_binv, off_k, off_crg, off_sig0; };
+// pack layout (doubles): [xbar_p 42][mean_p 42][scale_p 42] then per level Binv (n x n), K (rows x n), Crg (rows x n),
+// Sig0 (rows/2 x 4: the 2x2 diagonal blocks)
+constexpr int PK_XBAR = 0, PK_MEAN = 42, PK_SCALE = 84, PK_LEVELS = 126;
+constexpr int lvl_size(int n, int rows) { return n * n + 2 * rows * n + 2 * rows; }
+constexpr int L0 = PK_LEVELS, L1 = L0 + lvl_size(6, 4), L2 = L1 + lvl_size(10, 8), L3 = L2 + lvl_size(18, 16);
+constexpr int PACK_DOUBLES = L3 + lvl_size(34, 8);
+static_assert(PACK_DOUBLES == CUB200_PSM_PACK_DOUBLES, "include/cub200.h: CUB200_PSM_PACK_DOUBLES");
+__host__ __device__ constexpr LevelDef level_def(int l) {
+    return l == 0 ? LevelDef{3, 5, 6, 4, 1.0, L0, L0 + 36, L0 + 36 + 24, L0 + 36 + 48}
+         : l == 1 ? LevelDef{5, 9, 10, 8, 1.0, L1, L1 + 100, L1 + 100 + 80, L1 + 100 + 160}
+         : l == 2 ? LevelDef{9, 17, 18, 16, 1.0, L2, L2 + 324, L2 + 324 + 288, L2 + 324 + 576}
+                  : LevelDef{17, 21, 34, 8, 1e-3, L3, L3 + 1156, L3 + 1156 + 272, L3 + 1156 + 544};
+}
+
+struct __align__(16) PFWarp {
+    double A[Z][Z];        // pixel-space map of the sampled variables (row = permuted variable, col = draw)
+    double Acc[16][Z];     // M At_g of the current level
+    double d[P], u[Z], t[Z];
+    double w[16], kd[16], corr[16];
+    double sc[8][3];       // conditional covariance blocks of the current level: (c00, c10, c11)
 };
 
-__device__ __forceinline__ void pf_init_T(PFShared& s, const double* __restrict__ c0, double sigma2, int n_noise) {
-    for (int i = threadIdx.x; i < P * P; i += PF_THREADS) {
-        const int a = i / P, b = i % P;
-        // pca() covariance about transform(mu): C0 + d d^T          posteriorshapemodel.py:25-27
-        s.T[a][b] = c0[s.perm[a] * P + s.perm[b]] + s.d[a] * s.d[b] + ((a == b && a < n_noise) ? sigma2 : 0.0);
-    }
-}
+// An image is processed by one warp (large batches: per-sample factors of the sequence sampler) or by the whole
+// 4-warp CTA (small batches: a 64-image step would otherwise run on 64 warps of the GPU).
+template <int WPI> __device__ __forceinline__ void group_sync() { if (WPI == 1) __syncwarp(); else __syncthreads(); }
 
-// Eliminate variable k (right-looking): column of L, y_k, rank-1 updates of the trailing block of T
-// and of Acc.  `upto`: rows >= this bound are the only ones whose Acc is still needed (all rows > k
-// are updated in T).
-__device__ __forceinline__ void pf_eliminate(PFShared& s, int k) {
-    const int tid = threadIdx.x;
-    const double lkk = sqrt(s.T[k][k]);
-    const double ilkk = 1.0 / lkk;
-    if (tid < P) s.col[tid] = (tid > k) ? s.T[tid][k] * ilkk : 0.0;
-    else if (tid >= 64 && tid < 64 + Z) {
-        const int e = tid - 64;
-        s.y[e] = (s.A[k][e] / s.scale[k] - s.Acc[k][e]) * ilkk;
+// The per-level scalars and vectors of one image: ws.u, ws.w, ws.kd, ws.corr, ws.sc.  `lane` = thread index in the
+// image's group of NT = 32 WPI threads.
+template <int WPI>
+__device__ __forceinline__ void level_common(PFWarp& ws, const double* __restrict__ pk, const LevelDef L, int lane) {
+    constexpr int NT = 32 * WPI;
+    const double* Binv = pk + L.off_binv;
+    const double* K = pk + L.off_k;
+    const double* Crg = pk + L.off_crg;
+    const int n = L.n, rows = L.rows;
+    // u = B^-1 d_g
+    for (int i = lane; i < n; i += NT) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc = fma(Binv[i * n + k], ws.d[k], acc);
+        ws.u[i] = acc;
     }
-    __syncthreads();
-    // 2-D thread map (no integer division): lane -> column(s), warp -> rows k+1+w, k+1+w+8, ...
-    const int tx = tid & 31, ty = tid >> 5;
-    for (int a = k + 1 + ty; a < P; a += PF_THREADS / 32) {
-        const double ca = s.col[a];
-        const int b0 = k + 1 + tx, b1 = b0 + 32;
-        if (b0 < P) s.T[a][b0] -= ca * s.col[b0];
-        if (b1 < P) s.T[a][b1] -= ca * s.col[b1];
-        s.Acc[a][tx] += ca * s.y[tx];
-        if (tx + 32 < Z) s.Acc[a][tx + 32] += ca * s.y[tx + 32];
-    }
-    __syncthreads();
-}
-
-// Level: the points at positions [p0, p1) get  mu_f = mu + G (mu_c - mu) + chol(cov_f) z_slot  with
-// mu_c - mu = scale * Acc, cov_c = Sig_c * scale (columns), G = cov_p (cov_p + cov_c)^-1,
-// cov_f = G cov_c                                                   psm.py:265-285, 424-440
-__device__ __forceinline__ void pf_level(PFShared& s, int p0, int p1, const float* __restrict__ cov_img) {
-    const int n = (p1 - p0) * Z;
-    for (int i = threadIdx.x; i < n; i += PF_THREADS) {
-        const int pi = p0 + i / Z, e = i % Z;
-        const int v0 = 2 * pi, v1 = v0 + 1;
-        const int j = c_order[pi];
-        const double c00 = s.T[v0][v0] * s.scale[v0], c01 = s.T[v0][v1] * s.scale[v1];
-        const double c10 = s.T[v1][v0] * s.scale[v0], c11 = s.T[v1][v1] * s.scale[v1];
-        const double p00 = cov_img[4 * j + 0], p01 = cov_img[4 * j + 1], p10 = cov_img[4 * j + 2], p11 = cov_img[4 * j + 3];
-        const double t00 = p00 + c00, t01 = p01 + c01, t10 = p10 + c10, t11 = p11 + c11;
-        const double idet = 1.0 / (t00 * t11 - t01 * t10);
-        const double i00 = t11 * idet, i01 = -t01 * idet, i10 = -t10 * idet, i11 = t00 * idet;
-        const double g00 = p00 * i00 + p01 * i10, g01 = p00 * i01 + p01 * i11;
-        const double g10 = p10 * i00 + p11 * i10, g11 = p10 * i01 + p11 * i11;
-        const double b0 = s.scale[v0] * s.Acc[v0][e], b1 = s.scale[v1] * s.Acc[v1][e];
-        double a0 = g00 * b0 + g01 * b1, a1 = g10 * b0 + g11 * b1;
-        if (e == v0 || e == v1) {          // draw slot of position pi is columns (2 pi, 2 pi + 1)
-            // cov_f = G cov_c ; lower Cholesky reading the lower triangle (torch.linalg.cholesky)
-            const double f00 = g00 * c00 + g01 * c10;
-            const double f10 = g10 * c00 + g11 * c10;
-            const double f11 = g10 * c01 + g11 * c11;
-            const double l00 = sqrt(f00), l10 = f10 / l00, l11 = sqrt(f11 - l10 * l10);
-            if (e == v0) { a0 += l00; a1 += l10; }
-            else { a1 += l11; }
+    group_sync<WPI>();
+    double s = 0.0;                                      // every warp forms the same dot product
+    for (int k = lane & 31; k < n; k += 32) s = fma(ws.d[k], ws.u[k], s);
+    s = warp_sum(s);
+    const double gamma = 1.0 / (1.0 + s);
+    if (lane < rows) {
+        double w = 0.0, kd = 0.0;
+        for (int k = 0; k < n; ++k) {
+            w = fma(Crg[lane * n + k], ws.u[k], w);
+            kd = fma(K[lane * n + k], ws.d[k], kd);
         }
-        s.A[v0][e] = a0;
-        s.A[v1][e] = a1;
+        ws.w[lane] = w;
+        ws.kd[lane] = kd;
+        ws.corr[lane] = gamma * (ws.d[2 * L.p0 + lane] - w);
     }
-    __syncthreads();
+    group_sync<WPI>();
+    // conditional covariance blocks (levels with a draw): Sig_c * scale (columns)
+    if (L.sigma2 == 1.0 && lane < rows / 2) {
+        const double* sig0 = pk + L.off_sig0 + lane * 4;
+        const int a0 = 2 * lane, a1 = a0 + 1;
+        const double d0 = ws.d[2 * L.p0 + a0], d1 = ws.d[2 * L.p0 + a1];
+        const double s0 = pk[PK_SCALE + 2 * L.p0 + a0], s1 = pk[PK_SCALE + 2 * L.p0 + a1];
+        auto blk = [&](int a, int b, double da, double db, double s0ab) {
+            return s0ab + da * db - ws.kd[a] * db - ws.corr[a] * ws.w[b] - ws.corr[a] * s * db;
+        };
+        ws.sc[lane][0] = blk(a0, a0, d0, d0, sig0[0]) * s0;     // c00
+        ws.sc[lane][1] = blk(a1, a0, d1, d0, sig0[2]) * s0;     // c10 (the lower triangle is what Cholesky reads)
+        ws.sc[lane][2] = blk(a1, a1, d1, d1, sig0[3]) * s1;     // c11
+    }
+    group_sync<WPI>();
 }
 
-__global__ void __launch_bounds__(PF_THREADS)
-psm_factor_kernel(const double* __restrict__ c0, const double* __restrict__ xbar, const double* __restrict__ smean,
-                  const double* __restrict__ sscale, const float* __restrict__ mu, const float* __restrict__ cov,
+// ---------------------------------------------------------------- Gaussian sampler: affine factor
+template <int WPI>
+__global__ void __launch_bounds__(PF_WARPS * 32)
+psm_factor_kernel(const double* __restrict__ pack, const float* __restrict__ mu, const float* __restrict__ cov, int64_t n_img,
                   float* __restrict__ a_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PFShared& s = *reinterpret_cast<PFShared*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int64_t img = blockIdx.x;
-    const float* mu_i = mu + img * P;
-    const float* cov_i = cov + img * (CUB200_K * 4);
-
-    if (tid < P) {
-        const int o = 2 * c_order[tid >> 1] + (tid & 1);      // original flat index of permuted variable
-        s.perm[tid] = o;
-        s.scale[tid] = sscale[o];
-        s.d[tid] = xbar[o] - ((double)mu_i[o] - smean[o]) / sscale[o];  // xbar - transform(mu)
-    }
-    for (int i = tid; i < P * Z; i += PF_THREADS) { s.A[i / Z][i % Z] = 0.0; s.Acc[i / Z][i % Z] = 0.0; }
+    double* pk = reinterpret_cast<double*>(smem_raw);
+    PFWarp* warps = reinterpret_cast<PFWarp*>(pk + PACK_DOUBLES);
+    for (int i = threadIdx.x; i < PACK_DOUBLES; i += PF_WARPS * 32) pk[i] = pack[i];
     __syncthreads();
-    pf_init_T(s, c0, 1.0, 6);                                 // sigmas = [1, 1, 1, 1]   psm.py:225
-    // initial points: independent draws mu_j + chol(cov_j) z                       psm.py:239
-    if (tid < 3) {
-        const int j = c_order[tid];
-        const double p00 = cov_i[4 * j], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
-        const double l00 = sqrt(p00), l10 = p10 / l00, l11 = sqrt(p11 - l10 * l10);
-        s.A[2 * tid][2 * tid] = l00;
-        s.A[2 * tid + 1][2 * tid] = l10;
-        s.A[2 * tid + 1][2 * tid + 1] = l11;
-    }
-    __syncthreads();
-    // sweep 1: sigma2 = 1; levels at n = 6, 10, 18
-    for (int k = 0; k < 18; ++k) {
-        if (k == 6 || k == 10) {
-            const int p0 = k >> 1, p1 = (k == 6) ? 5 : 9;
-            pf_level(s, p0, p1, cov_i);
-            if (tid >= 2 * p0 && tid < 2 * p1) s.T[tid][tid] += 1.0;   // the new points join the conditioning set
-            __syncthreads();
+    constexpr int NT = 32 * WPI, IPC = PF_WARPS / WPI;       // threads per image, images per CTA pass
+    const int lane = threadIdx.x % NT, wid = threadIdx.x / NT;
+    PFWarp& ws = warps[wid];
+    // every group of a CTA runs the same number of passes (the group syncs of WPI > 1 are CTA barriers)
+    for (int64_t img0 = (int64_t)blockIdx.x * IPC; img0 < n_img; img0 += (int64_t)gridDim.x * IPC) {
+        const int64_t img = img0 + wid;
+        if (WPI == 1 && img >= n_img) break;
+        const float* mu_i = mu + img * P;
+        const float* cov_i = cov + img * (CUB200_K * 4);
+        for (int v = lane; v < P; v += NT) {
+            const int o = 2 * c_order[v >> 1] + (v & 1);
+            ws.d[v] = pk[PK_XBAR + v] - ((double)mu_i[o] - pk[PK_MEAN + v]) / pk[PK_SCALE + v];   // xbar - transform(mu)
         }
-        pf_eliminate(s, k);
-    }
-    pf_level(s, 9, 17, cov_i);
-    // sweep 2: posterior mean of the remaining points given all 17 sampled ones, sigma2 = 0.001   psm.py:355-368
-    pf_init_T(s, c0, 0.001, Z);
-    for (int i = tid; i < P * Z; i += PF_THREADS) s.Acc[i / Z][i % Z] = 0.0;
-    __syncthreads();
-    for (int k = 0; k < Z; ++k) pf_eliminate(s, k);
-    for (int i = tid; i < 8 * Z; i += PF_THREADS) {
-        const int v = Z + i / Z, e = i % Z;
-        s.A[v][e] = s.scale[v] * s.Acc[v][e];
-    }
-    __syncthreads();
-    float* out = a_out + img * (Z * P);
-    for (int i = tid; i < Z * P; i += PF_THREADS) {
-        const int e = i / P, v = i % P;
-        out[e * P + s.perm[v]] = (float)s.A[v][e];            // out[e][d], d = original flat index
+        for (int i = lane; i < Z * Z; i += NT) (&ws.A[0][0])[i] = 0.0;
+        group_sync<WPI>();
+        // initial points: independent draws mu_j + chol(cov_j) z                       psm.py:239
+        if (lane < 3) {
+            const int j = c_order[lane];
+            const double p00 = cov_i[4 * j], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
+            const double l00 = sqrt(p00), l10 = p10 / l00, l11 = sqrt(p11 - l10 * l10);
+            ws.A[2 * lane][2 * lane] = l00;
+            ws.A[2 * lane + 1][2 * lane] = l10;
+            ws.A[2 * lane + 1][2 * lane + 1] = l11;
+        }
+        group_sync<WPI>();
+        float* out = a_out + img * (Z * P);
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l) {
+            const LevelDef L = level_def(l);
+            level_common<WPI>(ws, pk, L, lane);
+            const int n = L.n, rows = L.rows;
+            const double* K = pk + L.off_k;
+            // t = u^T At_g ; Acc = K At_g + corr t^T      (At = A / scale: the sampled contour in the scaler's space)
+            for (int e = lane; e < Z; e += NT) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) acc = fma(ws.u[k] / pk[PK_SCALE + k], ws.A[k][e], acc);
+                ws.t[e] = acc;
+            }
+            group_sync<WPI>();
+            for (int idx = lane; idx < rows * Z; idx += NT) {
+                const int a = idx / Z, e = idx - a * Z;
+                double acc = ws.corr[a] * ws.t[e];
+                for (int k = 0; k < n; ++k) acc = fma(K[a * n + k] / pk[PK_SCALE + k], ws.A[k][e], acc);
+                ws.Acc[a][e] = acc;
+            }
+            group_sync<WPI>();
+            if (l < 3) {
+                // merge with the predicted law and colour: rows of A for the level's points
+                for (int idx = lane; idx < (rows / 2) * Z; idx += NT) {
+                    const int q = idx / Z, e = idx - q * Z;
+                    const int pi = L.p0 + q, v0 = 2 * pi, v1 = v0 + 1, j = c_order[pi];
+                    const double c00 = ws.sc[q][0], c10 = ws.sc[q][1], c11 = ws.sc[q][2];
+                    // c01 = Sig_c[v0][v1] * scale[v1] and Sig_c is symmetric
+                    const double c01 = c10 / pk[PK_SCALE + v0] * pk[PK_SCALE + v1];
+                    const double p00 = cov_i[4 * j + 0], p01 = cov_i[4 * j + 1], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
+                    const double t00 = p00 + c00, t01 = p01 + c01, t10 = p10 + c10, t11 = p11 + c11;
+                    const double idet = 1.0 / (t00 * t11 - t01 * t10);
+                    const double i00 = t11 * idet, i01 = -t01 * idet, i10 = -t10 * idet, i11 = t00 * idet;
+                    const double g00 = p00 * i00 + p01 * i10, g01 = p00 * i01 + p01 * i11;
+                    const double g10 = p10 * i00 + p11 * i10, g11 = p10 * i01 + p11 * i11;
+                    const double b0 = pk[PK_SCALE + v0] * ws.Acc[2 * q][e], b1 = pk[PK_SCALE + v1] * ws.Acc[2 * q + 1][e];
+                    double a0 = g00 * b0 + g01 * b1, a1 = g10 * b0 + g11 * b1;
+                    if (e == v0 || e == v1) {          // draw slot of position pi is columns (2 pi, 2 pi + 1)
+                        // cov_f = G cov_c ; lower Cholesky reading the lower triangle (torch.linalg.cholesky)
+                        const double f00 = g00 * c00 + g01 * c10;
+                        const double f10 = g10 * c00 + g11 * c10;
+                        const double f11 = g10 * c01 + g11 * c11;
+                        const double l00 = sqrt(f00), l10 = f10 / l00, l11 = sqrt(f11 - l10 * l10);
+                        if (e == v0) { a0 += l00; a1 += l10; }
+                        else { a1 += l11; }
+                    }
+                    ws.A[v0][e] = a0;
+                    ws.A[v1][e] = a1;
+                }
+                group_sync<WPI>();
+            } else {
+                // the remaining points: posterior mean given all 17 sampled ones, sigma2 = 1e-3      psm.py:355-368
+                for (int idx = lane; idx < rows * Z; idx += NT) {
+                    const int a = idx / Z, e = idx - a * Z, v = Z + a;
+                    const int o = 2 * c_order[v >> 1] + (v & 1);
+                    out[e * P + o] = (float)(pk[PK_SCALE + v] * ws.Acc[a][e]);
+                }
+            }
+        }
+        for (int idx = lane; idx < Z * Z; idx += NT) {
+            const int v = idx / Z, e = idx - v * Z;
+            const int o = 2 * c_order[v >> 1] + (v & 1);
+            out[e * P + o] = (float)ws.A[v][e];              // out[e][d], d = original flat index
+        }
+        group_sync<WPI>();
     }
 }
 
 // ---------------------------------------------------------------- conditional maps (skew path)
-// The skew-normal sampler (psm_skew.py:247-411) draws every level point from a GRID pdf, so its contour
-// is not affine in Gaussian draws; what stays constant per image is the shape model's conditional law
-// of each level given the already-sampled points (compute_psm, psm_skew.py:469-491):
-//     mu_c[v] = mu[v] + sum_{e < n} Mc[v][e] (s[e] - mu[e]),      cov_c = 2x2 blocks of Sig_c * scale
-// The same right-looking sweep as above with A = identity (the sampled values themselves are the
-// free variables) yields Mc; rows/columns are in the permuted (sampling) order.
-//   mc_t (n_img, 34, 36) fp64: [e][v - 6], v = 6..41 (level points at positions 3..16, then the four
-//        posterior-mean-filled points with sigma2 = 1e-3); zero for e >= the level's prefix
-//   covc (n_img, 14, 3) fp64: (c00, c10, c11) of positions 3..16 (MultivariateNormal reads the lower
-//        triangle, psm_skew.py:78)
-__device__ __forceinline__ void pc_emit(PFShared& s, int p0, int p1, int n, double* __restrict__ mc, double* __restrict__ cc) {
-    const int rows = 2 * (p1 - p0);
-    for (int i = threadIdx.x; i < rows * Z; i += PF_THREADS) {
-        const int v = 2 * p0 + i / Z, e = i % Z;
-        mc[e * 36 + (v - 6)] = (e < n) ? s.scale[v] * s.Acc[v][e] : 0.0;
-    }
-    if (cc) {
-        for (int pi = p0 + threadIdx.x; pi < p1; pi += PF_THREADS) {
-            const int v0 = 2 * pi, v1 = v0 + 1;
-            cc[(pi - 3) * 3 + 0] = s.T[v0][v0] * s.scale[v0];
-            cc[(pi - 3) * 3 + 1] = s.T[v1][v0] * s.scale[v0];
-            cc[(pi - 3) * 3 + 2] = s.T[v1][v1] * s.scale[v1];
-        }
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(PF_THREADS)
-psm_cond_kernel(const double* __restrict__ c0, const double* __restrict__ xbar, const double* __restrict__ smean,
-                const double* __restrict__ sscale, const float* __restrict__ mu, double* __restrict__ mc_t,
+//   mc_t (n_img, 34, 36) fp64: [e][v - 6], v = 6..41; zero for e >= the level's prefix
+//   covc (n_img, 14, 3) fp64: (c00, c10, c11) of positions 3..16 (MultivariateNormal reads the lower triangle)
+template <int WPI>
+__global__ void __launch_bounds__(PF_WARPS * 32)
+psm_cond_kernel(const double* __restrict__ pack, const float* __restrict__ mu, int64_t n_img, double* __restrict__ mc_t,
                 double* __restrict__ covc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PFShared& s = *reinterpret_cast<PFShared*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int64_t img = blockIdx.x;
-    const float* mu_i = mu + img * P;
-    double* mc = mc_t + img * (Z * 36);
-    double* cc = covc + img * (14 * 3);
-    if (tid < P) {
-        const int o = 2 * c_order[tid >> 1] + (tid & 1);
-        s.perm[tid] = o;
-        s.scale[tid] = sscale[o];
-        s.d[tid] = xbar[o] - ((double)mu_i[o] - smean[o]) / sscale[o];
-    }
-    for (int i = tid; i < P * Z; i += PF_THREADS) { s.A[i / Z][i % Z] = (i / Z == i % Z) ? 1.0 : 0.0; s.Acc[i / Z][i % Z] = 0.0; }
+    double* pk = reinterpret_cast<double*>(smem_raw);
+    PFWarp* warps = reinterpret_cast<PFWarp*>(pk + PACK_DOUBLES);
+    for (int i = threadIdx.x; i < PACK_DOUBLES; i += PF_WARPS * 32) pk[i] = pack[i];
     __syncthreads();
-    pf_init_T(s, c0, 1.0, 6);                                 // sigmas = [1, 1, 1, 1]   psm_skew.py:270
-    __syncthreads();
-    for (int k = 0; k < 18; ++k) {
-        if (k == 6 || k == 10) {
-            const int p0 = k >> 1, p1 = (k == 6) ? 5 : 9;
-            pc_emit(s, p0, p1, k, mc, cc);
-            if (tid >= 2 * p0 && tid < 2 * p1) s.T[tid][tid] += 1.0;
-            __syncthreads();
+    constexpr int NT = 32 * WPI, IPC = PF_WARPS / WPI;       // threads per image, images per CTA pass
+    const int lane = threadIdx.x % NT, wid = threadIdx.x / NT;
+    PFWarp& ws = warps[wid];
+    // every group of a CTA runs the same number of passes (the group syncs of WPI > 1 are CTA barriers)
+    for (int64_t img0 = (int64_t)blockIdx.x * IPC; img0 < n_img; img0 += (int64_t)gridDim.x * IPC) {
+        const int64_t img = img0 + wid;
+        if (WPI == 1 && img >= n_img) break;
+        const float* mu_i = mu + img * P;
+        double* mc = mc_t + img * (Z * 36);
+        double* cc = covc + img * (14 * 3);
+        for (int v = lane; v < P; v += NT) {
+            const int o = 2 * c_order[v >> 1] + (v & 1);
+            ws.d[v] = pk[PK_XBAR + v] - ((double)mu_i[o] - pk[PK_MEAN + v]) / pk[PK_SCALE + v];
         }
-        pf_eliminate(s, k);
+        group_sync<WPI>();
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l) {
+            const LevelDef L = level_def(l);
+            level_common<WPI>(ws, pk, L, lane);
+            const int n = L.n, rows = L.rows;
+            const double* K = pk + L.off_k;
+            // mu_c[v] - mu[v] = scale_v sum_e M[v][e] (s_e - mu_e) / scale_e      (compute_psm, psm_skew.py:469-491)
+            for (int idx = lane; idx < rows * Z; idx += NT) {
+                const int a = idx / Z, e = idx - a * Z, v = 2 * L.p0 + a;
+                mc[e * 36 + (v - 6)] = (e < n) ? pk[PK_SCALE + v] * (K[a * n + e] + ws.corr[a] * ws.u[e]) / pk[PK_SCALE + e] : 0.0;
+            }
+            if (l < 3 && lane < rows / 2) {
+                const int pi = L.p0 + lane;
+                cc[(pi - 3) * 3 + 0] = ws.sc[lane][0];
+                cc[(pi - 3) * 3 + 1] = ws.sc[lane][1];
+                cc[(pi - 3) * 3 + 2] = ws.sc[lane][2];
+            }
+            group_sync<WPI>();
+        }
     }
-    pc_emit(s, 9, 17, 18, mc, cc);
-    pf_init_T(s, c0, 0.001, Z);                               // psm_skew.py:388
-    for (int i = tid; i < P * Z; i += PF_THREADS) s.Acc[i / Z][i % Z] = 0.0;
-    __syncthreads();
-    for (int k = 0; k < Z; ++k) pf_eliminate(s, k);
-    pc_emit(s, 17, 21, Z, mc, nullptr);
 }
 
 __global__ void naive_factor_kernel(const float* __restrict__ cov, int64_t n_img, float* __restrict__ a_out) {
@@ -246,23 +274,125 @@ __global__ void naive_factor_kernel(const float* __restrict__ cov, int64_t n_img
     out[(2 * k + 1) * P + 2 * k + 1] = (float)l11;
 }
 
+static int pf_launch_cfg(int64_t n_img, const void* kernel, int images_per_cta, int* grid, size_t* smem) {
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        CUB200_CUDA_OK(cudaGetDevice(&dev));
+        CUB200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    *smem = sizeof(double) * PACK_DOUBLES + sizeof(PFWarp) * PF_WARPS;
+    CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    const int64_t need = (n_img + images_per_cta - 1) / images_per_cta;
+    const int64_t cap = (int64_t)num_sms * 2;
+    *grid = (int)(need < cap ? need : cap);
+    return 0;
+}
+// one CTA per image while that still fills the GPU, one warp per image beyond
+static bool pf_cta_per_image(int64_t n_img) { return n_img <= 4096; }
+
+// Gauss-Jordan inverse of an n x n symmetric positive-definite matrix (host, fp64, partial pivoting).
+static bool invert_spd(std::vector<double>& a, int n) {
+    std::vector<double> inv((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (std::fabs(a[(size_t)r * n + c]) > std::fabs(a[(size_t)piv * n + c])) piv = r;
+        if (a[(size_t)piv * n + c] == 0.0) return false;
+        if (piv != c)
+            for (int k = 0; k < n; ++k) {
+                std::swap(a[(size_t)piv * n + k], a[(size_t)c * n + k]);
+                std::swap(inv[(size_t)piv * n + k], inv[(size_t)c * n + k]);
+            }
+        const double ip = 1.0 / a[(size_t)c * n + c];
+        for (int k = 0; k < n; ++k) { a[(size_t)c * n + k] *= ip; inv[(size_t)c * n + k] *= ip; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = a[(size_t)r * n + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < n; ++k) { a[(size_t)r * n + k] -= f * a[(size_t)c * n + k]; inv[(size_t)r * n + k] -= f * inv[(size_t)c * n + k]; }
+        }
+    }
+    a.swap(inv);
+    return true;
+}
+
 }  // namespace cub200
 
-extern "C" int cub200_psm_factor(const double* model_c0, const double* model_xbar, const double* scaler_mean,
-                                 const double* scaler_scale, const float* mu, const float* cov, int64_t n_img,
-                                 float* a_out, void* stream) {
+extern "C" int cub200_psm_model_pack_host(const double* c0_host, const double* xbar_host, const double* mean_host,
+                                          const double* scale_host, double* pack_out_host) {
     using namespace cub200;
-    if (!model_c0 || !model_xbar || !scaler_mean || !scaler_scale || !mu || !cov || !a_out || n_img < 0) return CUB200_EINVAL;
-    if (n_img == 0) return 0;
-    if (n_img > 0x7fffffff) return CUB200_EINVAL;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUB200_CUDA_OK(cudaFuncSetAttribute(psm_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PFShared)));
-        attr_set = true;
+    if (!c0_host || !xbar_host || !mean_host || !scale_host || !pack_out_host) return CUB200_EINVAL;
+    int perm[P];
+    for (int v = 0; v < P; ++v) perm[v] = 2 * h_order[v >> 1] + (v & 1);
+    for (int v = 0; v < P; ++v) {
+        pack_out_host[PK_XBAR + v] = xbar_host[perm[v]];
+        pack_out_host[PK_MEAN + v] = mean_host[perm[v]];
+        pack_out_host[PK_SCALE + v] = scale_host[perm[v]];
     }
-    psm_factor_kernel<<<(unsigned)n_img, PF_THREADS, sizeof(PFShared), (cudaStream_t)stream>>>(
-        model_c0, model_xbar, scaler_mean, scaler_scale, mu, cov, a_out);
+    auto C = [&](int a, int b) { return c0_host[perm[a] * P + perm[b]]; };
+    for (int l = 0; l < 4; ++l) {
+        const LevelDef L = level_def(l);
+        const int n = L.n, rows = L.rows, r0 = 2 * L.p0;
+        std::vector<double> B((size_t)n * n);
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) B[(size_t)i * n + k] = C(i, k) + (i == k ? L.sigma2 : 0.0);
+        if (!invert_spd(B, n)) return CUB200_EINVAL;
+        double* binv = pack_out_host + L.off_binv;
+        double* K = pack_out_host + L.off_k;
+        double* crg = pack_out_host + L.off_crg;
+        double* sig0 = pack_out_host + L.off_sig0;
+        for (int i = 0; i < n * n; ++i) binv[i] = B[i];
+        for (int a = 0; a < rows; ++a)
+            for (int k = 0; k < n; ++k) {
+                crg[a * n + k] = C(r0 + a, k);
+                double acc = 0.0;
+                for (int m = 0; m < n; ++m) acc += C(r0 + a, m) * B[(size_t)m * n + k];
+                K[a * n + k] = acc;
+            }
+        for (int q = 0; q < rows / 2; ++q)
+            for (int i = 0; i < 2; ++i)
+                for (int k = 0; k < 2; ++k) {
+                    const int a = 2 * q + i, b = 2 * q + k;
+                    double acc = C(r0 + a, r0 + b);
+                    for (int m = 0; m < n; ++m) acc -= K[a * n + m] * C(m, r0 + b);
+                    sig0[q * 4 + i * 2 + k] = acc;
+                }
+    }
+    return 0;
+}
+
+extern "C" int cub200_psm_factor(const double* model_pack, const float* mu, const float* cov, int64_t n_img, float* a_out,
+                                 void* stream) {
+    using namespace cub200;
+    if (!model_pack || !mu || !cov || !a_out || n_img < 0) return CUB200_EINVAL;
+    if (n_img == 0) return 0;
+    int grid = 0;
+    size_t smem = 0;
+    const bool wide = pf_cta_per_image(n_img);
+    int rc = wide ? pf_launch_cfg(n_img, (const void*)psm_factor_kernel<PF_WARPS>, 1, &grid, &smem)
+                  : pf_launch_cfg(n_img, (const void*)psm_factor_kernel<1>, PF_WARPS, &grid, &smem);
+    if (rc) return rc;
+    if (wide) psm_factor_kernel<PF_WARPS><<<grid, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(model_pack, mu, cov, n_img, a_out);
+    else psm_factor_kernel<1><<<grid, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(model_pack, mu, cov, n_img, a_out);
     return check_launch("psm_factor_kernel");
+}
+
+extern "C" int cub200_psm_conditionals(const double* model_pack, const float* mu, int64_t n_img, double* mc_t, double* covc,
+                                       void* stream) {
+    using namespace cub200;
+    if (!model_pack || !mu || !mc_t || !covc || n_img < 0) return CUB200_EINVAL;
+    if (n_img == 0) return 0;
+    int grid = 0;
+    size_t smem = 0;
+    const bool wide = pf_cta_per_image(n_img);
+    int rc = wide ? pf_launch_cfg(n_img, (const void*)psm_cond_kernel<PF_WARPS>, 1, &grid, &smem)
+                  : pf_launch_cfg(n_img, (const void*)psm_cond_kernel<1>, PF_WARPS, &grid, &smem);
+    if (rc) return rc;
+    if (wide) psm_cond_kernel<PF_WARPS><<<grid, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(model_pack, mu, n_img, mc_t, covc);
+    else psm_cond_kernel<1><<<grid, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(model_pack, mu, n_img, mc_t, covc);
+    return check_launch("psm_cond_kernel");
 }
 
 extern "C" int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* stream) {
@@ -274,21 +404,4 @@ extern "C" int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out
     const int64_t n = n_img * CUB200_K;
     naive_factor_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cov, n_img, a_out);
     return check_launch("naive_factor_kernel");
-}
-
-extern "C" int cub200_psm_conditionals(const double* model_c0, const double* model_xbar, const double* scaler_mean,
-                                       const double* scaler_scale, const float* mu, int64_t n_img, double* mc_t,
-                                       double* covc, void* stream) {
-    using namespace cub200;
-    if (!model_c0 || !model_xbar || !scaler_mean || !scaler_scale || !mu || !mc_t || !covc || n_img < 0) return CUB200_EINVAL;
-    if (n_img == 0) return 0;
-    if (n_img > 0x7fffffff) return CUB200_EINVAL;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUB200_CUDA_OK(cudaFuncSetAttribute(psm_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PFShared)));
-        attr_set = true;
-    }
-    psm_cond_kernel<<<(unsigned)n_img, PF_THREADS, sizeof(PFShared), (cudaStream_t)stream>>>(
-        model_c0, model_xbar, scaler_mean, scaler_scale, mu, mc_t, covc);
-    return check_launch("psm_cond_kernel");
 }

@@ -20,6 +20,7 @@ HW = 256
 Z_PSM = 34
 Z_NAIVE = 42
 MASK_WORDS = 2048
+PSM_PACK_DOUBLES = 3142     # CUB200_PSM_PACK_DOUBLES
 
 DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 DEFAULT_PSM = os.path.join(DATA_DIR, "camus-cont_psm_11_no_std.npy")
@@ -75,6 +76,12 @@ class ShapeModelConstants:
         self.xbar = torch.tensor(xbar, dtype=torch.float64, device=self.device)
         self.mean = torch.tensor(f32(d["scaler_mean"]), dtype=torch.float64, device=self.device)
         self.scale = torch.tensor(f32(d["scaler_scale"]), dtype=torch.float64, device=self.device)
+        # per-level constants of the Sherman-Morrison form (B^-1, K, ...), packed by the library's host helper
+        h = [np.ascontiguousarray(a, dtype=np.float64) for a in (c0, xbar, f32(d["scaler_mean"]).reshape(-1), f32(d["scaler_scale"]).reshape(-1))]
+        pack = np.empty((PSM_PACK_DOUBLES,), dtype=np.float64)
+        rc = nat.lib().cub200_psm_model_pack_host(*(a.ctypes.data for a in h), pack.ctypes.data)
+        nat.check(rc, "cub200_psm_model_pack_host")
+        self.pack = torch.from_numpy(pack).to(self.device)
 
 
 def psm_factor(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor) -> torch.Tensor:
@@ -86,9 +93,7 @@ def psm_factor(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor) 
     n = int(np.prod(mu.shape[:-2])) if mu.dim() > 2 else 1
     a = torch.empty(tuple(mu.shape[:-2]) + (Z_PSM, P), dtype=torch.float32, device=mu.device)
     with torch.cuda.device(mu.device):
-        rc = nat.lib().cub200_psm_factor(nat.ptr(model.c0), nat.ptr(model.xbar), nat.ptr(model.mean),
-                                         nat.ptr(model.scale), nat.ptr(mu), nat.ptr(cov), n, nat.ptr(a),
-                                         nat.stream_ptr(mu.device))
+        rc = nat.lib().cub200_psm_factor(nat.ptr(model.pack), nat.ptr(mu), nat.ptr(cov), n, nat.ptr(a), nat.stream_ptr(mu.device))
     nat.check(rc, "cub200_psm_factor")
     return a
 
@@ -383,8 +388,7 @@ def psm_conditionals(model: ShapeModelConstants, mu: torch.Tensor):
     mc = torch.empty((n, Z_PSM, 36), dtype=torch.float64, device=mu.device)
     cc = torch.empty((n, N_DRAW_SKEW, 3), dtype=torch.float64, device=mu.device)
     with torch.cuda.device(mu.device):
-        rc = nat.lib().cub200_psm_conditionals(nat.ptr(model.c0), nat.ptr(model.xbar), nat.ptr(model.mean), nat.ptr(model.scale),
-                                               nat.ptr(mu), n, nat.ptr(mc), nat.ptr(cc), nat.stream_ptr(mu.device))
+        rc = nat.lib().cub200_psm_conditionals(nat.ptr(model.pack), nat.ptr(mu), n, nat.ptr(mc), nat.ptr(cc), nat.stream_ptr(mu.device))
     nat.check(rc, "cub200_psm_conditionals")
     return mc, cc
 
@@ -684,8 +688,8 @@ class UncertaintyEngine:
                                             ws.cov.data_ptr(), st), "cub200_dsnt_moments")
             if self.sampler == "psm":
                 m = self.model
-                nat.check(L.cub200_psm_factor(m.c0.data_ptr(), m.xbar.data_ptr(), m.mean.data_ptr(), m.scale.data_ptr(),
-                                              ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "cub200_psm_factor")
+                nat.check(L.cub200_psm_factor(m.pack.data_ptr(), ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st),
+                          "cub200_psm_factor")
             else:
                 nat.check(L.cub200_naive_factor(ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "cub200_naive_factor")
             if stream is None:

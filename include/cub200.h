@@ -60,23 +60,32 @@ int cub200_dsnt_moments(const float* heat, int64_t n_maps, int h, int w, int is_
                         float* norm_out, float* pix_mu, float* pix_sigma, void* stream);
 
 /*
+ * Shape-model constants, packed once per model ON THE HOST (plain C++, no device work): the sampling-order
+ * permutation of xbar / scaler mean / scaler scale and, for the four conditioning prefixes of the hierarchical sampler
+ * (6, 10, 18 coordinates with sigma2 = 1; 34 with sigma2 = 1e-3), B^-1 = (C0[g,g] + sigma2 I)^-1, K = C0[r,g] B^-1,
+ * C0[r,g] and the 2x2 diagonal blocks of C0[r,r] - K C0[g,r].
+ *   c0_host (42,42) fp64: covariance of X_train about its own mean (biased, /N) -- pca() about any centre is C0 + d d^T
+ *   xbar_host (42): mean of X_train; mean_host, scale_host (42): the StandardScaler of the model file
+ *   pack_out_host: CUB200_PSM_PACK_DOUBLES doubles; copy them to the device and pass as `model_pack` below.
+ */
+#define CUB200_PSM_PACK_DOUBLES 3142
+int cub200_psm_model_pack_host(const double* c0_host, const double* xbar_host, const double* mean_host,
+                               const double* scale_host, double* pack_out_host);
+
+/*
  * K2  Posterior-shape-model factor: per image, the affine map of the hierarchical PSM sampler,
  *     contour = mu + A z,  z in R^34 (17 draws of shape (1,2): points 0,10,20 | 5,15 | 2,7,13,18 |
- *     1,3,6,8,12,14,17,19),  A in R^(42 x 34).
+ *     1,3,6,8,12,14,17,19),  A in R^(42 x 34).  One warp per image; Sherman-Morrison on the packed constants.
  *   replaces  pca                     cu/sampler/posterior_shape_model/posteriorshapemodel.py:9-46
  *             posterior_shape_model   .../posteriorshapemodel.py:49-81
  *             PosteriorShapeModelSampler.__call__ / sample_endo_contour / merge_priors / transform
  *                                     cu/sampler/posterior_shape_model/psm.py:73-93,199-384,424-450
- *   model_c0   (42,42) fp64: covariance of X_train about its own mean (biased, /N)
- *   model_xbar (42)    fp64: mean of X_train
- *   scaler_mean, scaler_scale (42) fp64
+ *   model_pack (CUB200_PSM_PACK_DOUBLES) fp64 device copy of cub200_psm_model_pack_host's output
  *   mu (n_img, 21, 2) fp32, cov (n_img, 21, 2, 2) fp32
  *   a_out (n_img, 34, 42) fp32, stored TRANSPOSED (draw-major) so that a sample is
  *         contour[d] = mu[d] + sum_e a_out[e][d] * z[e].
  */
-int cub200_psm_factor(const double* model_c0, const double* model_xbar, const double* scaler_mean,
-                      const double* scaler_scale, const float* mu, const float* cov, int64_t n_img,
-                      float* a_out, void* stream);
+int cub200_psm_factor(const double* model_pack, const float* mu, const float* cov, int64_t n_img, float* a_out, void* stream);
 
 /*
  * Independent-Gaussian (naive) sampler factor: block-diagonal A (42 draws), 2x2 Cholesky colouring.
@@ -208,9 +217,7 @@ int cub200_skew_pdf_grid(const float* mu, const float* cov, const float* alpha, 
  *   mu (n_img,21,2) fp32;  mc_t (n_img,34,36) fp64 = [e][v-6] in sampling order (points 0,10,20 | 5,15 | 2,7,13,18 |
  *   1,3,6,8,12,14,17,19 | 4,9,11,16; variable v = 2*position + coordinate);  covc (n_img,14,3) fp64 = (c00,c10,c11).
  */
-int cub200_psm_conditionals(const double* model_c0, const double* model_xbar, const double* scaler_mean,
-                            const double* scaler_scale, const float* mu, int64_t n_img, double* mc_t, double* covc,
-                            void* stream);
+int cub200_psm_conditionals(const double* model_pack, const float* mu, int64_t n_img, double* mc_t, double* covc, void* stream);
 
 /*
  * Skew-normal posterior-shape-model sampler, one warp per sample.

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in cub200.h but not exported"
     assert set(names) == set(_native.SIGNATURES) | set(_native.QUERIES)
-    assert _native.lib().cub200_abi_version() == 7
+    assert _native.lib().cub200_abi_version() == 8
     assert _native.lib().cub200_built_for_sm() == 100
 
 
@@ -75,7 +75,9 @@ def test_new_entry_points_validate_arguments():
 
     l, E = _native.lib(), _native.EINVAL
     assert l.cub200_skew_pdf_grid(None, None, None, 1, 1, None, None) == E
-    assert l.cub200_psm_conditionals(None, None, None, None, None, 1, None, None, None) == E
+    assert l.cub200_psm_conditionals(None, None, 1, None, None, None) == E
+    assert l.cub200_psm_factor(None, None, None, 1, None, None) == E
+    assert l.cub200_psm_model_pack_host(None, None, None, None, None) == E
     assert l.cub200_skew_sample(None, None, None, None, None, None, None, None, 0, 1, 1, None, None, None) == E
     assert l.cub200_seq_skew_conditionals(None, None, None, None, None, 1, None, None, None) == E
     assert l.cub200_seq_skew_sample(*([None] * 12), 0, 1, 1, None, None, None) == E
