@@ -45,8 +45,9 @@ SIGNATURES = {
     "cub200_seq_skew_conditionals": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_seq_skew_sample": [_vp] * 12 + [_u64, _i64, _i64, _vp, _vp, _vp],
     "cub200_metric_sums": [_vp, _i64, _vp, _vp],
+    "cub200_calibration_bins": [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp],
 }
-QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes")
+QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes")
 
 
 class NativeError(RuntimeError):
@@ -70,6 +71,8 @@ def lib() -> C.CDLL:
         l.cub200_last_error.argtypes = []
         l.cub200_simpson_workspace_bytes.restype = C.c_int64
         l.cub200_simpson_workspace_bytes.argtypes = [_i64]
+        l.cub200_calibration_workspace_bytes.restype = C.c_int64
+        l.cub200_calibration_workspace_bytes.argtypes = []
         l.cub200_abi_version.restype = C.c_int
         l.cub200_built_for_sm.restype = C.c_int
         _lib = l

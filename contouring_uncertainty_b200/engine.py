@@ -604,6 +604,42 @@ def skew_umap(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, linear_c
 
 
 # --------------------------------------------------------------------------------------------------
+# Dataset-level pixel calibration (results processor reduction)
+# --------------------------------------------------------------------------------------------------
+def calibration_bins(umap: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, nb_bins: int = 20) -> torch.Tensor:
+    """Binned (count, sum confidence, sum accuracy) over the foreground pixels (cu/results/calibration.py:94-113,197-250):
+    umap fp64, pred / gt uint8, any equal shapes -> (nb_bins + 1, 3) fp64; row nb_bins = (foreground pixel count, 0, 0).
+    The rows are additive: ranks all_reduce them before ``ece_from_bins``."""
+    umap = nat.require_cuda(umap, torch.float64, "umap")
+    pred = nat.require_cuda(pred, torch.uint8, "pred")
+    gt = nat.require_cuda(gt, torch.uint8, "gt")
+    if pred.shape != umap.shape or gt.shape != umap.shape:
+        raise ValueError("umap / pred / gt shapes differ")
+    dev = umap.device
+    bounds = torch.from_numpy(np.linspace(0, 1, nb_bins + 1)).to(dev)
+    out = torch.empty((nb_bins + 1, 3), dtype=torch.float64, device=dev)
+    ws = torch.empty((int(nat.lib().cub200_calibration_workspace_bytes()),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_calibration_bins(nat.ptr(umap), nat.ptr(pred), nat.ptr(gt), umap.numel(), nat.ptr(bounds), int(nb_bins),
+                                               nat.ptr(out), nat.ptr(ws), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_calibration_bins")
+    return out
+
+
+def ece_from_bins(bins) -> tuple:
+    """(ece, mce) from calibration bins as ``Calibration.ece`` forms them (cu/results/calibration.py:94-117)."""
+    b = np.asarray(bins.cpu() if isinstance(bins, torch.Tensor) else bins, dtype=np.float64)
+    total = b[-1, 0]
+    ece, gaps = 0.0, []
+    for count, s_conf, s_acc in b[:-1]:
+        if count > 0 and count / total > 0:
+            gap = abs(s_conf / count - s_acc / count)
+            ece += gap * (count / total)
+            gaps.append(gap)
+    return ece, (max(gaps) if gaps else float("nan"))
+
+
+# --------------------------------------------------------------------------------------------------
 # End-to-end engine
 # --------------------------------------------------------------------------------------------------
 @dataclass

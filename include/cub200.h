@@ -337,6 +337,20 @@ int cub200_skew_umap_contours(const float* mu, const float* unc, const double* p
 int cub200_weighted_mask_entropy(const uint32_t* masks, const double* weights, int64_t n_img, int n_masks,
                                  double weight_sum, int normalize, double* out, void* stream);
 
+/*
+ * Dataset-level pixel calibration bins (the accumulators the ranks all_reduce).
+ *   replaces  Calibration.get_pixel_confidences_and_accuracies / get_confidences_and_accuracies / ece (bin loop)
+ *             cu/results/calibration.py:94-113,197-250
+ *   umap (n_pixels) fp64 uncertainty (confidence = 1 - umap); pred, gt (n_pixels) uint8 labels; pixels with pred + gt == 0
+ *   are dropped; bin b holds the pixels with bounds[b] < confidence < bounds[b+1] (strict, as the reference).
+ *   bounds (nb_bins + 1) fp64 (np.linspace(0, 1, nb_bins + 1)); nb_bins <= 64
+ *   bins_out ((nb_bins + 1) * 3) fp64: per bin (count, sum confidence, sum accuracy); the last triple's first entry is the
+ *   number of foreground pixels (the denominator of prop_in_bin).  workspace: cub200_calibration_workspace_bytes().
+ */
+int64_t cub200_calibration_workspace_bytes(void);
+int cub200_calibration_bins(const double* umap, const uint8_t* pred, const uint8_t* gt, int64_t n_pixels, const double* bounds,
+                            int nb_bins, double* bins_out, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

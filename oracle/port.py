@@ -1052,3 +1052,32 @@ def seq_skew_psm_sample(model: ShapeModel, seq: "SequenceShapeModel", mu: np.nda
         out[b, n], out[o, n] = s1[0], s2[0]
         idx_all[n, :14], idx_all[n, 14:] = i1[0], i2[0]
     return (out, idx_all) if return_indices else out
+
+
+
+# --------------------------------------------------------------------------------------------------
+# Pixel calibration                                              cu/results/calibration.py
+# --------------------------------------------------------------------------------------------------
+def pixel_confidences_and_accuracies(umap: np.ndarray, pred: np.ndarray, gt: np.ndarray):
+    """``get_pixel_confidences_and_accuracies`` + ``get_confidences_and_accuracies`` (calibration.py:197-250):
+    confidence = 1 - uncertainty, accuracy = (pred == gt), background-in-both pixels dropped."""
+    conf = 1 - np.asarray(umap)
+    acc = np.equal(pred, gt).astype(int)
+    not_bg = (np.asarray(pred).astype(int) + np.asarray(gt).astype(int)) != 0
+    return conf[not_bg], acc[not_bg]
+
+
+def calibration_ece(confidences: np.ndarray, accuracies: np.ndarray, nb_bins: int = 20):
+    """``Calibration.ece`` (calibration.py:94-117, 147): strict bin membership, ECE and MCE."""
+    bounds = np.linspace(0, 1, nb_bins + 1)
+    ece = np.zeros(1)
+    conf_b, acc_b = [], []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        in_bin = np.greater(confidences, lo) * np.less(confidences, hi)
+        prop = in_bin.mean()
+        if prop.item() > 0:
+            a, c = accuracies[in_bin].mean(), confidences[in_bin].mean()
+            ece += np.abs(c - a) * prop
+            conf_b.append(c)
+            acc_b.append(a)
+    return ece.item(), float(np.max(np.abs(np.array(conf_b) - np.array(acc_b))))

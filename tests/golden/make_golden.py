@@ -429,6 +429,34 @@ def golden_seqskew():
     print("seqskew.npz", outs["f32"].shape)
 
 
+def calibration_inputs(seed=3):
+    """(umap (3,256,256) fp64 in [0,1] with runs exactly on bin boundaries, pred, gt uint8)."""
+    rng = np.random.default_rng(seed)
+    um = rng.uniform(0, 1, (3, 256, 256))
+    um[0, :50] = 0.05 * 3
+    um[1, :20] = 0.0
+    um[2, 100:120] = 1.0
+    pred = (rng.uniform(size=um.shape) < 0.4).astype(np.uint8)
+    gt = (rng.uniform(size=um.shape) < 0.4).astype(np.uint8)
+    return um, pred, gt
+
+
+def golden_calibration():
+    """Calibration.get_confidences_and_accuracies + Calibration.ece (cu/results/calibration.py) on synthetic maps."""
+    from contour_uncertainty.results.calibration import Calibration
+
+    um, pred, gt = calibration_inputs()
+    res = [SimpleNamespace(pred=pred[i], gt=gt[i], uncertainty_map=um[i]) for i in range(3)]
+    bb = np.linspace(0, 1, 21)
+    fake = SimpleNamespace(nb_bins=20, bin_lowers=bb[:-1], bin_uppers=bb[1:],
+                           get_pixel_confidences_and_accuracies=Calibration.get_pixel_confidences_and_accuracies)
+    c, a = Calibration.get_confidences_and_accuracies(fake, res, "uncertainty_map")
+    ece, mce = Calibration.ece(fake, c, a, name=None)
+    np.savez_compressed(os.path.join(HERE, "calibration.npz"), seed=3, ece=float(np.asarray(ece).reshape(-1)[0]), mce=float(mce),
+                        n_fg=len(c))
+    print("calibration.npz ece", ece, "mce", mce, "foreground pixels", len(c))
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -467,6 +495,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration"]
     for w in which:
         globals()["golden_" + w]()

@@ -276,3 +276,27 @@ def test_metric_sums_exact(dev):
     s = E.metric_sums(a)
     assert s.tolist() == [int(a.sum()), int((a.long() * a.long()).sum())]
     assert E.metric_sums(a[:0].contiguous()).tolist() == [0, 0]
+
+
+def test_calibration_bins_vs_oracle_and_reference(dev):
+    """Dataset-level pixel calibration: bins are additive over images (what ranks all_reduce); ECE / MCE equal the
+    executed reference's to 1e-12 (fp64 sums in a different order); boundary confidences belong to no bin."""
+    from contouring_uncertainty_b200 import engine as E
+    from test_oracle_golden import _calibration_inputs
+
+    g = np.load(os.path.join(G, "calibration.npz"))
+    um, pred, gt = _calibration_inputs(int(g["seed"]))
+    t = lambda a: torch.from_numpy(a).to(dev)
+    bins = E.calibration_bins(t(um), t(pred), t(gt), 20)
+    ece, mce = E.ece_from_bins(bins)
+    assert abs(ece - float(g["ece"])) < 1e-12 and abs(mce - float(g["mce"])) < 1e-12
+    assert int(bins[-1, 0]) == int(g["n_fg"])
+    conf, acc = port.pixel_confidences_and_accuracies(um, pred, gt)
+    bounds = np.linspace(0, 1, 21)
+    for b in range(20):
+        inb = (conf > bounds[b]) & (conf < bounds[b + 1])
+        assert int(bins[b, 0]) == int(inb.sum()) and int(bins[b, 2]) == int(acc[inb].sum())
+        assert abs(float(bins[b, 1]) - conf[inb].sum()) < 1e-9
+    assert int(bins[:-1, 0].sum()) < int(bins[-1, 0])          # the runs sitting exactly on boundaries are in no bin
+    parts = sum(E.calibration_bins(t(um[i]), t(pred[i]), t(gt[i]), 20) for i in range(3))
+    assert torch.equal(parts[:, [0, 2]], bins[:, [0, 2]]) and torch.allclose(parts[:, 1], bins[:, 1], rtol=1e-13, atol=0)

@@ -232,3 +232,23 @@ def test_sequence_skew_sampler_matches_reference():
                                       store=np.float64, return_indices=True)
     assert np.array_equal(idx, g["indices_f64"][i]) and np.abs(s - g["samples_f64"][i]).max() < 1e-9
     assert np.array_equal(g["indices"], g["indices_f64"])          # the verbatim fp32 run drew the same cells
+
+
+def _calibration_inputs(seed=3):
+    rng = np.random.default_rng(seed)
+    um = rng.uniform(0, 1, (3, 256, 256))
+    um[0, :50] = 0.05 * 3
+    um[1, :20] = 0.0
+    um[2, 100:120] = 1.0
+    pred = (rng.uniform(size=um.shape) < 0.4).astype(np.uint8)
+    gt = (rng.uniform(size=um.shape) < 0.4).astype(np.uint8)
+    return um, pred, gt
+
+
+def test_calibration_matches_reference():
+    g = np.load(os.path.join(G, "calibration.npz"))
+    um, pred, gt = _calibration_inputs(int(g["seed"]))
+    c, a = port.pixel_confidences_and_accuracies(um, pred, gt)
+    assert len(c) == int(g["n_fg"])
+    ece, mce = port.calibration_ece(c, a)
+    assert ece == float(g["ece"]) and mce == float(g["mce"])
