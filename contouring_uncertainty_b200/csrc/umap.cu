@@ -336,7 +336,55 @@ weighted_entropy_kernel(const uint32_t* __restrict__ masks, const double* __rest
         for (int b = 0; b < 32; ++b) o[w * 32 + b] = o[w * 32 + b] / mx;
 }
 
+// ---------------------------------------------------------------- contour perimeter (spline arc length), one warp per contour
+// perimeter() / global_longitudinal_strain() of cu/utils/clinical.py:30-71: contour_spline(contour) (n = 1001 points,
+// unrounded landmarks) and the sum of its 1000 chord lengths; the 21 raw points when FITPACK rejects the input.
+__global__ void __launch_bounds__(UM_WARPS * 32)
+contour_perimeter_kernel(const float* __restrict__ contours, int64_t n, double* __restrict__ out) {
+    __shared__ SplineScratch s_sp[UM_WARPS];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int64_t g = blockIdx.x * (int64_t)UM_WARPS + wid;
+    if (g >= n) return;
+    SplineScratch& sp = s_sp[wid];
+    double X = 0.0, Y = 0.0;
+    if (lane < KP) { X = contours[(g * KP + lane) * 2]; Y = contours[(g * KP + lane) * 2 + 1]; }
+    const bool bad = fit_spline(sp, X, Y, lane);
+    double len = 0.0;
+    if (!bad) {
+        // lane L owns segments 32 L .. 32 L + 31 (of 1000): points 32 L .. 32 L + 32
+        const int j0 = 32 * lane;
+        double px = 0.0, py = 0.0;
+        for (int jj = 0; jj <= 32; ++jj) {
+            const int j = j0 + jj;
+            if (j > 1000) break;
+            const double uj = (j == 1000) ? 1.0 : (double)j * 0.001;
+            int p = 0;
+#pragma unroll
+            for (int q = 1; q <= KP - 2; ++q) p = (uj >= sp.u[q]) ? q : p;
+            const double* c = sp.piece[p];
+            const double sv = uj - c[1];
+            const double xv = fma(fma(fma(c[5], sv, c[4]), sv, c[3]), sv, c[2]);
+            const double yv = fma(fma(fma(c[9], sv, c[8]), sv, c[7]), sv, c[6]);
+            if (jj > 0) len += sqrt((xv - px) * (xv - px) + (yv - py) * (yv - py));
+            px = xv; py = yv;
+        }
+    } else {
+        const double Xn = __shfl_down_sync(FULL, X, 1), Yn = __shfl_down_sync(FULL, Y, 1);
+        if (lane < KP - 1) len = sqrt((Xn - X) * (Xn - X) + (Yn - Y) * (Yn - Y));
+    }
+    len = warp_sum(len);
+    if (lane == 0) out[g] = len;
+}
+
 }  // namespace cub200
+
+extern "C" int cub200_contour_perimeter(const float* contours, int64_t n, double* perimeter_out, void* stream) {
+    using namespace cub200;
+    if (n == 0) return 0;
+    if (!contours || !perimeter_out || n < 0) return CUB200_EINVAL;
+    contour_perimeter_kernel<<<(unsigned)((n + UM_WARPS - 1) / UM_WARPS), UM_WARPS * 32, 0, (cudaStream_t)stream>>>(contours, n, perimeter_out);
+    return check_launch("contour_perimeter_kernel");
+}
 
 extern "C" int cub200_projected_uncertainty(const float* mu, const float* cov, const float* alpha, int64_t n_img,
                                             int all_points, int linear_close, float* unc_out, double* proj_out,

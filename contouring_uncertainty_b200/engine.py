@@ -606,6 +606,26 @@ def skew_umap(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, linear_c
 # --------------------------------------------------------------------------------------------------
 # Dataset-level pixel calibration (results processor reduction)
 # --------------------------------------------------------------------------------------------------
+def contour_perimeter(contours: torch.Tensor) -> torch.Tensor:
+    """perimeter() (cu/utils/clinical.py:30-47): contours (..., 21, 2) fp32 -> spline arc lengths (...) fp64."""
+    contours = nat.require_cuda(contours, torch.float32, "contours")
+    if contours.dim() < 2 or contours.shape[-2:] != (K, 2):
+        raise ValueError(f"contours must be (..., {K}, 2)")
+    lead = tuple(contours.shape[:-2])
+    n = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead, dtype=torch.float64, device=contours.device)
+    with torch.cuda.device(contours.device):
+        rc = nat.lib().cub200_contour_perimeter(nat.ptr(contours), n, nat.ptr(out), nat.stream_ptr(contours.device))
+    nat.check(rc, "cub200_contour_perimeter")
+    return out
+
+
+def global_longitudinal_strain(ed_contours: torch.Tensor, es_contours: torch.Tensor) -> torch.Tensor:
+    """global_longitudinal_strain (cu/utils/clinical.py:50-71) per sample: (len_ED - len_ES) / len_ED, fp64."""
+    led, les = contour_perimeter(ed_contours), contour_perimeter(es_contours)
+    return (led - les) / led
+
+
 def calibration_bins(umap: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, nb_bins: int = 20) -> torch.Tensor:
     """Binned (count, sum confidence, sum accuracy) over the foreground pixels (cu/results/calibration.py:94-113,197-250):
     umap fp64, pred / gt uint8, any equal shapes -> (nb_bins + 1, 3) fp64; row nb_bins = (foreground pixel count, 0, 0).

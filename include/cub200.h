@@ -338,6 +338,14 @@ int cub200_weighted_mask_entropy(const uint32_t* masks, const double* weights, i
                                  double weight_sum, int normalize, double* out, void* stream);
 
 /*
+ * Spline arc length of sampled contours (longitudinal length of the endocardium): contour_spline(contour) with 1001
+ * points on the unrounded landmarks, sum of the 1000 chord lengths.  GLS of a sample = (len_ED - len_ES) / len_ED.
+ *   replaces  perimeter, global_longitudinal_strain, compute_gls   cu/utils/clinical.py:30-78
+ *   contours (n, 21, 2) fp32 -> perimeter_out (n) fp64 (pixels)
+ */
+int cub200_contour_perimeter(const float* contours, int64_t n, double* perimeter_out, void* stream);
+
+/*
  * Dataset-level pixel calibration bins (the accumulators the ranks all_reduce).
  *   replaces  Calibration.get_pixel_confidences_and_accuracies / get_confidences_and_accuracies / ece (bin loop)
  *             cu/results/calibration.py:94-113,197-250

@@ -1081,3 +1081,21 @@ def calibration_ece(confidences: np.ndarray, accuracies: np.ndarray, nb_bins: in
             conf_b.append(c)
             acc_b.append(a)
     return ece.item(), float(np.max(np.abs(np.array(conf_b) - np.array(acc_b))))
+
+
+
+def perimeter(contours: np.ndarray) -> np.ndarray:
+    """cu/utils/clinical.py:30-47: spline (n = 1001) chord-length sum per contour; contours (..., K, 2)."""
+    c = np.asarray(contours)
+    flat = c.reshape((-1,) + c.shape[-2:])
+    out = np.zeros(len(flat))
+    for i, contour in enumerate(flat):
+        s = contour_spline(contour)
+        out[i] = np.sum([np.sqrt(np.dot(s[k] - s[k + 1], s[k] - s[k + 1])) for k in range(s.shape[0] - 1)])
+    return out.reshape(c.shape[:-2])
+
+
+def global_longitudinal_strain(ed_contour: np.ndarray, es_contour: np.ndarray) -> float:
+    """cu/utils/clinical.py:50-71."""
+    ed_len, es_len = perimeter(ed_contour), perimeter(es_contour)
+    return (ed_len - es_len) / ed_len

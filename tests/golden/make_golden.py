@@ -457,6 +457,21 @@ def golden_calibration():
     print("calibration.npz ece", ece, "mce", mce, "foreground pixels", len(c))
 
 
+def golden_gls():
+    """perimeter / global_longitudinal_strain (cu/utils/clinical.py:30-71) on contour samples (incl. a zero-chord one)."""
+    from contour_uncertainty.utils.clinical import perimeter, global_longitudinal_strain
+
+    rng = np.random.default_rng(121)
+    b = synth.LV_EXAMPLE_SHAPE
+    ed = (b + rng.normal(0, 2.5, (12, 21, 2))).astype(np.float32)
+    es = (b.mean(0) + (b - b.mean(0)) * 0.8 + rng.normal(0, 2.5, (12, 21, 2))).astype(np.float32)
+    ed[3, 8] = ed[3, 7]                                     # zero chord: FITPACK raises -> raw points
+    p_ed, p_es = perimeter(ed), perimeter(es)
+    gls = np.array([global_longitudinal_strain(ed[i], es[i]) for i in range(12)])
+    np.savez_compressed(os.path.join(HERE, "gls.npz"), ed=ed, es=es, perimeter_ed=p_ed, perimeter_es=p_es, gls=gls)
+    print("gls.npz perimeter", p_ed[:4], "gls", gls[:4])
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -495,6 +510,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls"]
     for w in which:
         globals()["golden_" + w]()

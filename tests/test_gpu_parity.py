@@ -300,3 +300,19 @@ def test_calibration_bins_vs_oracle_and_reference(dev):
     assert int(bins[:-1, 0].sum()) < int(bins[-1, 0])          # the runs sitting exactly on boundaries are in no bin
     parts = sum(E.calibration_bins(t(um[i]), t(pred[i]), t(gt[i]), 20) for i in range(3))
     assert torch.equal(parts[:, [0, 2]], bins[:, [0, 2]]) and torch.allclose(parts[:, 1], bins[:, 1], rtol=1e-13, atol=0)
+
+
+def test_contour_perimeter_and_gls_vs_reference(dev):
+    """Spline arc length (perimeter) and per-sample GLS against the executed reference: 1e-10 relative (fp64 spline
+    evaluated piecewise instead of through FITPACK's B-spline recurrence; different summation order)."""
+    from contouring_uncertainty_b200 import engine as E
+
+    g = np.load(os.path.join(G, "gls.npz"))
+    ed, es = torch.from_numpy(g["ed"]).to(dev), torch.from_numpy(g["es"]).to(dev)
+    got = E.contour_perimeter(ed).cpu().numpy()
+    ok = np.arange(12) != 3          # contour 3 has a zero chord: the reference then sums its raw float32 points in fp32
+    np.testing.assert_allclose(got[ok], g["perimeter_ed"][ok], rtol=1e-10)
+    np.testing.assert_allclose(got[3], g["perimeter_ed"][3], rtol=2e-7)
+    np.testing.assert_allclose(E.contour_perimeter(es).cpu().numpy(), g["perimeter_es"], rtol=1e-10)
+    np.testing.assert_allclose(E.global_longitudinal_strain(ed, es).cpu().numpy()[ok], g["gls"][ok], rtol=1e-8, atol=1e-10)
+    assert E.contour_perimeter(ed.reshape(3, 4, 21, 2)).shape == (3, 4)

@@ -252,3 +252,11 @@ def test_calibration_matches_reference():
     assert len(c) == int(g["n_fg"])
     ece, mce = port.calibration_ece(c, a)
     assert ece == float(g["ece"]) and mce == float(g["mce"])
+
+
+def test_perimeter_and_gls_match_reference():
+    g = np.load(os.path.join(G, "gls.npz"))
+    np.testing.assert_allclose(port.perimeter(g["ed"]), g["perimeter_ed"], rtol=1e-13)
+    np.testing.assert_allclose(port.perimeter(g["es"]), g["perimeter_es"], rtol=1e-13)
+    got = np.array([port.global_longitudinal_strain(g["ed"][i], g["es"][i]) for i in range(len(g["ed"]))])
+    np.testing.assert_allclose(got, g["gls"], rtol=1e-11)
