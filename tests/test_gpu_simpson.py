@@ -89,3 +89,38 @@ def test_simpson_random_masks_vs_oracle(dev):
             assert np.array_equal(dn[v, t], d) and sn[v, t] == s, (v, t)
             assert nn[v, t] == len(port.find_contours(masks[v, t], 0.5)[0])
     assert nn[0, 0] == 0 and nn[1, 1] == 0
+
+
+def test_simpson_full_size_properties(dev):
+    """BASELINE config 4 sample count (10 000 per image) for one patient: size-independent invariants."""
+    from contouring_uncertainty_b200 import engine as E
+
+    T = 10000
+    mus, covs = synth.point_distributions(4, seed=401)
+    ctr = mus[0].mean(0)
+    for v, s in enumerate((1.0, 0.8, 1.05, 0.84)):
+        mus[v] = ctr + (mus[0] - ctr) * s
+    model = E.ShapeModelConstants(device=dev)
+    m, c = torch.from_numpy(mus).to(dev), torch.from_numpy(covs).to(dev)
+    contours = E.sample_contours(m, E.psm_factor(model, m, c), T, seed=3)               # (4, T, 21, 2)
+    edv, esv, ef, area = E.biplane_volumes_from_contours(contours[None].contiguous(), 0.5)
+    edv, esv, ef = edv[0], esv[0], ef[0]
+    ok = ~ef.isnan()
+    assert float(ok.float().mean()) > 0.99
+    # volumes are integers (Python round), EF is the ratio of the two integers, NaN exactly outside [0, 1]
+    assert torch.equal(edv, edv.round()) and torch.equal(esv, esv.round()) and float(edv.min()) > 0
+    assert torch.equal(ef[ok], ((edv - esv) / edv)[ok])
+    bad = ((edv - esv) / edv < 0) | ((edv - esv) / edv > 1)
+    assert torch.equal(bad, ~ok)
+    # larger masks give larger volumes: sample volumes correlate with the product of the two ED areas
+    a = (area[0, 0].double() * area[0, 2].double())
+    assert float(torch.corrcoef(torch.stack([a, edv]))[0, 1]) > 0.8
+    # sub-sample through the mask entry points (order / indexing): same diameters
+    sel = contours[:, ::1000].contiguous()
+    masks, _ = E.rasterize_contours(sel.reshape(-1, 21, 2), return_masks=True)
+    d1, s1 = E.simpson_diameters(masks.reshape(4, 10, 2048), 0.5)
+    e1 = E.simpson_volumes(d1[None], s1[None])
+    assert torch.equal(e1[0][0], edv[::1000]) and torch.equal(e1[1][0], esv[::1000])
+    # spacing is a pure scale: diameters and step scale linearly
+    d2, s2 = E.simpson_diameters(masks.reshape(4, 10, 2048), 1.0)
+    assert torch.allclose(d2, 2 * d1, rtol=1e-15) and torch.allclose(s2, 2 * s1, rtol=1e-15)

@@ -204,3 +204,34 @@ def test_sequence_skew_sampler_replay_vs_reference(dev, model):
     assert o3.shape == (n_pair, 2, 64, 21, 2) and torch.isfinite(o3).all()
     lvl = [5, 15, 2, 7, 13, 18, 1, 3, 6, 8, 12, 14, 17, 19]
     assert torch.equal(o3[:, :, :, lvl], o3[:, :, :, lvl].round())
+
+
+def test_skew_full_size_properties(dev, model):
+    """BASELINE config 3 shape per GPU, scaled to 64 images x 1000 skew-PSM samples: size-independent invariants."""
+    from contouring_uncertainty_b200 import engine as E
+
+    n, T = 64, 1000
+    mus, covs = synth.point_distributions(n, seed=301)
+    al = synth.skew_alphas(n, seed=302)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    out, idx = E.skew_sample(model, t(mus), t(covs), t(al), T, seed=17, return_indices=True)
+    lvl = [5, 15, 2, 7, 13, 18, 1, 3, 6, 8, 12, 14, 17, 19]
+    # every level point is a grid cell, equal to its recorded flat index; no fallback on ordinary inputs
+    assert int(idx.min()) >= 0 and int(idx.max()) < 65536
+    assert torch.equal(out[:, :, lvl, 0], (idx // 256).float()) and torch.equal(out[:, :, lvl, 1], (idx % 256).float())
+    # idempotence / seeding: same seed -> same contours; the pdf tables can be passed in
+    tabs = E.skew_pdf_grid(t(mus), t(covs), t(al), flip_alpha_y=True)
+    assert torch.equal(E.skew_sample(model, t(mus), t(covs), t(al), T, seed=17, pdfs=tabs), out)
+    # the sampled clouds sit on the predictions: a skew-normal's mean is at most sqrt(2/pi) sigma (<= 4.8 px here) from its
+    # location parameter; spread bounded by the prediction's
+    d = out.mean(1) - t(mus)
+    assert float(d.abs().max()) < 6.0
+    sd = out.std(1)
+    lim = torch.sqrt(torch.stack([t(covs)[..., 0, 0], t(covs)[..., 1, 1]], -1)) * 1.6 + 0.6
+    assert bool((sd[:, lvl] < lim[:, lvl]).all())
+    # checksum of checksums through the rasteriser: per-image count-map sum == sum of per-sample areas
+    diff = torch.zeros((n, 256, 256), dtype=torch.int32, device=dev)
+    _, area = E.rasterize_contours(out.reshape(-1, 21, 2), return_masks=False, diff=diff, per_image=T)
+    count, mean, ent, pred = E.finalize_maps(diff, T)
+    assert torch.equal(count.long().sum((1, 2)), area.reshape(n, T).long().sum(1))
+    assert torch.all(pred == (2 * count > T).to(torch.uint8))
