@@ -359,10 +359,12 @@ def sample_moments(contours: torch.Tensor):
 N_DRAW_SKEW = 14      # multinomial draws per sample (level points)
 
 
-def skew_pdf_grid(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, flip_alpha_y: bool = False) -> torch.Tensor:
+def skew_pdf_grid(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, flip_alpha_y: bool = False,
+                  sampled_only: bool = False) -> torch.Tensor:
     """BivariateSkewNormal.pdf on the 256x256 integer grid (bivariateskewnormal.py:20-49; the ``pdfs``
     loop of psm_skew.py:234-238).  mu (...,2), cov (...,2,2), alpha (...,2) -> (...,256,256) fp32,
-    table[x, y] (``indexing='ij'``)."""
+    table[x, y] (``indexing='ij'``).  ``sampled_only`` (inputs shaped (...,21,*)) leaves the tables of landmarks
+    4, 9, 11, 16 unwritten: the samplers never read them."""
     mu = nat.require_cuda(mu, torch.float32, "mu")
     cov = nat.require_cuda(cov, torch.float32, "cov")
     alpha = nat.require_cuda(alpha, torch.float32, "alpha")
@@ -372,8 +374,8 @@ def skew_pdf_grid(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, flip
     n = int(np.prod(lead)) if lead else 1
     out = torch.empty(lead + (HW, HW), dtype=torch.float32, device=mu.device)
     with torch.cuda.device(mu.device):
-        rc = nat.lib().cub200_skew_pdf_grid(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, int(flip_alpha_y), nat.ptr(out),
-                                            nat.stream_ptr(mu.device))
+        rc = nat.lib().cub200_skew_pdf_grid(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, int(flip_alpha_y) | (2 if sampled_only else 0),
+                                            nat.ptr(out), nat.stream_ptr(mu.device))
     nat.check(rc, "cub200_skew_pdf_grid")
     return out
 
@@ -416,7 +418,7 @@ def skew_sample(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor,
         if tuple(expo.shape) != (n, T, N_DRAW_SKEW, HW * HW):
             raise ValueError(f"expo must be ({n},{T},{N_DRAW_SKEW},{HW * HW})")
     if pdfs is None:
-        pdfs = skew_pdf_grid(mu, cov, alpha, flip_alpha_y=True)
+        pdfs = skew_pdf_grid(mu, cov, alpha, flip_alpha_y=True, sampled_only=True)
     elif tuple(pdfs.shape) != (n, K, HW, HW):
         raise ValueError("pdfs must be (N,21,256,256)")
     mc, cc = psm_conditionals(model, mu)
@@ -458,8 +460,8 @@ def seq_skew_sample(model: ShapeModelConstants, seq: "SequenceModelConstants", m
         if tuple(expo.shape) != (npair, T, 31, HW * HW):
             raise ValueError(f"expo must be ({npair},{T},31,{HW * HW})")
     m2, c2, a2 = mu.reshape(2 * npair, K, 2), cov.reshape(2 * npair, K, 2, 2), alpha.reshape(2 * npair, K, 2)
-    tab_f = skew_pdf_grid(m2, c2, a2, flip_alpha_y=True)
-    tab_r = skew_pdf_grid(m2, c2, a2, flip_alpha_y=False)
+    tab_f = skew_pdf_grid(m2, c2, a2, flip_alpha_y=True, sampled_only=True)
+    tab_r = skew_pdf_grid(m2, c2, a2, flip_alpha_y=False, sampled_only=True)
     mc, cc = psm_conditionals(model, m2)
     m_seq = torch.empty((npair, 2, P, P), dtype=torch.float64, device=dev)
     c_seq = torch.empty((npair, 2, K, 4), dtype=torch.float64, device=dev)

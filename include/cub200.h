@@ -202,10 +202,11 @@ int cub200_seq_condition(const float* mu, const float* cov, const float* first_s
  *             BivariateNormal.logpdf                                          cu/distributions/bivariatenormal.py:15-32
  *             batch_matrix_pow(cov, -0.5)                                     cu/distributions/utils.py:100-129
  *             the `pdfs` loop of sample_one_instant                           cu/sampler/posterior_shape_model/psm_skew.py:234-238
- *   mu (n_dist,2), cov (n_dist,2,2), alpha (n_dist,2) fp32; flip_alpha_y != 0 applies the sampler's
- *   alpha * [1,-1] (psm_skew.py:232); pdf_out (n_dist,256,256) fp32.
+ *   mu (n_dist,2), cov (n_dist,2,2), alpha (n_dist,2) fp32; pdf_out (n_dist,256,256) fp32.
+ *   flags: bit 0 applies the sampler's alpha * [1,-1] (psm_skew.py:232); bit 1 (n_dist a multiple of 21: whole images)
+ *   leaves the tables of landmarks 4, 9, 11, 16 unwritten -- the samplers never read them (posterior-mean-filled points).
  */
-int cub200_skew_pdf_grid(const float* mu, const float* cov, const float* alpha, int64_t n_dist, int flip_alpha_y,
+int cub200_skew_pdf_grid(const float* mu, const float* cov, const float* alpha, int64_t n_dist, int flags,
                          float* pdf_out, void* stream);
 
 /*

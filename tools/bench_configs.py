@@ -57,7 +57,7 @@ def config3(steps, scale):
         ev[0].record()
         _, mu, cov = E.dsnt_moments(logits)
         ev[1].record()
-        tabs = E.skew_pdf_grid(mu, cov, alpha, flip_alpha_y=True)
+        tabs = E.skew_pdf_grid(mu, cov, alpha, flip_alpha_y=True, sampled_only=True)
         ev[2].record()
         s = E.skew_sample(model, mu, cov, alpha, T, seed=i, pdfs=tabs)
         ev[3].record()
