@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32)
 simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict__ pts_g, const int32_t* __restrict__ npts,
                          int64_t n_masks, double spacing, double* __restrict__ diam_out, double* __restrict__ step_out) {
     __shared__ uint32_t s_pts[SP_WARPS][SP_NMAX];
+    __shared__ uint32_t s_bmax[SP_WARPS][SP_NMAX / 32];
     const int lane = lane_id(), wid = threadIdx.x >> 5;
     const int64_t g = blockIdx.x * (int64_t)SP_WARPS + wid;
     if (g >= n_masks) return;
@@ -156,35 +157,64 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     uint32_t* P = s_pts[wid];
     for (int k = lane; k < n; k += 32) P[k] = pts_g[g * SP_NMAX + k];
     __syncwarp();
-    // ---- longest admissible chord (heart_us.py:127-146)
+    // ---- longest admissible chord (heart_us.py:127-146).  The reference keeps the first (i, j) in loop order among the
+    //      longest valid chords, so pairs may be visited in any order as long as ties are broken by (i, j): a coarse
+    //      pass over every 4th point first finds a long valid chord, and the full pass then skips, 32 candidates at a
+    //      time, the blocks of j whose columns cannot give a chord that long (|d_row| <= d_col  =>  len^2 <= 2 d_col^2).
+    uint32_t* bmax = s_bmax[wid];                        // max column (half-pixel units) of each block of 32 points
+    for (int jb = lane; jb < (n + 31) / 32; jb += 32) {
+        int m = 0;
+        for (int k = 32 * jb; k < min(32 * jb + 32, n); ++k) m = max(m, (int)(P[k] >> 16));
+        bmax[jb] = (uint32_t)m;
+    }
+    __syncwarp();
     Chord best{0, 0x7fffffff, 0x7fffffff};
+    auto try_pair = [&](int i, int ir, int ic, int j, int wbest) {
+        const int ar = (int)(P[j] & 0xffff) - ir, ac = (int)(P[j] >> 16) - ic;         // contour[j] - contour[i]
+        // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
+        if (!(ac > 0 && abs(ar) <= ac)) return;
+        const Chord cand{ar * ar + ac * ac, i, j};
+        if (cand.len2 < wbest || !chord_better(cand, best)) return;                    // cannot be selected
+        const int64_t lim = 256ll * cand.len2;           // (8 px)^2 * len2 in half-pixel units: cross^2 <= 256 len2
+        bool ok = true;
+        {   // most far-away chords fail at the middle of the span: test it first
+            const int k = (i + j) >> 1;
+            if (k > j) {
+                const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);
+                const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
+                ok = cr * cr <= lim;
+            }
+        }
+        for (int k = j + 1; ok && k < i; ++k) {
+            const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);      // contour[i] - contour[k]
+            const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
+            ok = cr * cr <= lim;
+        }
+        if (ok) best = cand;
+    };
+    // coarse pass: i and j on every 4th point (validity is always checked on ALL intermediate points)
+    for (int i = 4; i < n; i += 4) {
+        const int ir = P[i] & 0xffff, ic = P[i] >> 16;
+        const int wbest = __reduce_max_sync(FULL, best.len2);
+        for (int j = 4 * lane; j < i; j += 128) try_pair(i, ir, ic, j, wbest);
+    }
+    // full pass
     for (int i = 2; i < n; ++i) {
         const int ir = P[i] & 0xffff, ic = P[i] >> 16;
         // a chord shorter than the best one any lane holds can never be selected (equal ones still can: ties go to the
         // first (i, j) in loop order)
         const int wbest = __reduce_max_sync(FULL, best.len2);
-        for (int j = lane; j < i; j += 32) {
-            const int ar = (int)(P[j] & 0xffff) - ir, ac = (int)(P[j] >> 16) - ic;     // contour[j] - contour[i]
-            // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
-            if (!(ac > 0 && abs(ar) <= ac)) continue;
-            const int len2 = ar * ar + ac * ac;
-            if (len2 <= best.len2 || len2 < wbest) continue;   // cannot be selected: skip the intermediate test
-            const int64_t lim = 256ll * len2;          // (8 px)^2 * len2 in half-pixel units: cross^2 <= 256 len2
-            bool ok = true;
-            {   // most far-away chords fail at the middle of the span: test it first
-                const int k = (i + j) >> 1;
-                if (k > j) {
-                    const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);
-                    const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
-                    ok = cr * cr <= lim;
-                }
+        const int dmin = max(1, (int)ceil(sqrt(0.5 * (double)wbest) - 1e-9));           // d_col needed for len^2 >= wbest
+        const int nblk = (i + 31) >> 5;
+        for (int jb0 = 0; jb0 < nblk; jb0 += 32) {
+            const int jb = jb0 + lane;
+            unsigned live = __ballot_sync(FULL, jb < nblk && (int)bmax[jb < nblk ? jb : 0] - ic >= dmin);
+            while (live) {
+                const int b = __ffs(live) - 1;
+                live &= live - 1;
+                const int j = 32 * (jb0 + b) + lane;
+                if (j < i) try_pair(i, ir, ic, j, wbest);
             }
-            for (int k = j + 1; ok && k < i; ++k) {
-                const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);  // contour[i] - contour[k]
-                const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
-                ok = cr * cr <= lim;
-            }
-            if (ok) { best.len2 = len2; best.i = i; best.j = j; }
         }
     }
 #pragma unroll
