@@ -299,6 +299,7 @@ def run_ours(args):
 
     # ---- e2e: public host-buffer API (HostPipeline): pinned host logits in, pinned host results out;
     #      H2D + kernels + D2H all inside the timed region, every step
+    numa_bound = PAR.bind_to_gpu_numa_node(local) if world > 1 else False   # pinned buffers on the GPU's NUMA node
     pipe = E.HostPipeline(eng, N_IMG, T_A, chunk=8, n_streams=2)
     h_logits = torch.empty(logits.shape, dtype=torch.float32, pin_memory=True)
     h_logits.copy_(logits)
@@ -364,7 +365,7 @@ def run_ours(args):
         "roofline": roof(dominant),
         "roofline_dsnt": roof("dsnt"),
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "numa_bound": numa_bound},
         "gpu_launches": (5 + (1 if world > 1 else 0)) * args.steps,   # dsnt, psm_factor, fused, entropy_lut, finalize (+ metric_sums) per step
         "clocks": clk,
         "parity_spot_check": parity_ok and e2e_check,

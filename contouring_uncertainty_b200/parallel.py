@@ -101,3 +101,18 @@ class StepExchange:
                 w.wait()
             slot["works"] = []
         return (self.last["gathered"], self.last["stats"]) if self.last is not None else (None, None)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (so that pinned host
+    buffers allocated afterwards are first-touched on the GPU's NUMA node and H2D / D2H copies do not cross sockets).
+    Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
