@@ -45,7 +45,9 @@ BYTES_FINAL_PER_IMG = HW * HW * (4 + 4 + 8 + 8 + 1)
 NCU_TRAFFIC = {"dsnt": 352339968 + 4504832, "fused": 5135104 + 450560, "finalize": 19132160 + 35917056, "psm_factor": 113664}
 ROOF_NOTES = {
     "fused": "NOT HBM-bound by construction (masks never leave shared memory): binding resources are issue slots / ALU "
-             "pipe -- ncu: IPC 2.2 of 4, ALU pipe 39 %, 4875 warp-instructions per sample (DESIGN.md section 3, profiles/r01d_*)",
+             "pipe -- ncu: IPC 2.2 of 4 (56 % of issue slots), ALU pipe 39 %, 4875 warp-instructions per sample, shared memory "
+             "43.05 M wavefronts per launch = 86 KB / sample = 28 % of the 148 SM x 1 wavefront/clk peak "
+             "(DESIGN.md section 3, profiles/r01d_*)",
     "dsnt": "HBM-bound: every logit read once; DRAM traffic == algorithmic bytes",
 }
 

@@ -366,8 +366,8 @@ extern "C" int cub200_psm_model_pack_host(const double* c0_host, const double* x
 extern "C" int cub200_psm_factor(const double* model_pack, const float* mu, const float* cov, int64_t n_img, float* a_out,
                                  void* stream) {
     using namespace cub200;
-    if (!model_pack || !mu || !cov || !a_out || n_img < 0) return CUB200_EINVAL;
     if (n_img == 0) return 0;
+    if (!model_pack || !mu || !cov || !a_out || n_img < 0) return CUB200_EINVAL;
     int grid = 0;
     size_t smem = 0;
     const bool wide = pf_cta_per_image(n_img);
@@ -382,8 +382,8 @@ extern "C" int cub200_psm_factor(const double* model_pack, const float* mu, cons
 extern "C" int cub200_psm_conditionals(const double* model_pack, const float* mu, int64_t n_img, double* mc_t, double* covc,
                                        void* stream) {
     using namespace cub200;
-    if (!model_pack || !mu || !mc_t || !covc || n_img < 0) return CUB200_EINVAL;
     if (n_img == 0) return 0;
+    if (!model_pack || !mu || !mc_t || !covc || n_img < 0) return CUB200_EINVAL;
     int grid = 0;
     size_t smem = 0;
     const bool wide = pf_cta_per_image(n_img);
@@ -397,8 +397,8 @@ extern "C" int cub200_psm_conditionals(const double* model_pack, const float* mu
 
 extern "C" int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* stream) {
     using namespace cub200;
-    if (!cov || !a_out || n_img < 0) return CUB200_EINVAL;
     if (n_img == 0) return 0;
+    if (!cov || !a_out || n_img < 0) return CUB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     CUB200_CUDA_OK(cudaMemsetAsync(a_out, 0, sizeof(float) * P * P * n_img, st));
     const int64_t n = n_img * CUB200_K;

@@ -261,3 +261,32 @@ def test_skew_pipeline_predict_step_vs_oracle():
     smp = SkewPosteriorShapeModelSampler()
     out = smp(torch.from_numpy(br.mu), torch.from_numpy(br.cov), torch.from_numpy(alpha), n=T, z=z, expo=ex)
     assert out.shape == (n, T, 21, 2) and np.array_equal(out.numpy(), br.contour_samples[:, 0])
+
+
+def test_new_paths_refuse_bad_inputs_and_handle_empty_batches():
+    """Error behaviour of the skew / u-map / Simpson host layer: shape errors raise ValueError, CPU tensors are refused,
+    empty batches return empty results."""
+    from contouring_uncertainty_b200 import engine as E
+
+    dev = torch.device("cuda:0")
+    model = E.ShapeModelConstants(device=dev)
+    mu = torch.zeros((0, 21, 2), device=dev)
+    cov = torch.zeros((0, 21, 2, 2), device=dev)
+    al = torch.zeros((0, 21, 2), device=dev)
+    assert E.skew_sample(model, mu, cov, al, 4).shape == (0, 4, 21, 2)
+    assert E.skew_pdf_grid(mu, cov, al).shape == (0, 21, 256, 256)
+    assert E.umap_analytic(mu, cov).shape == (0, 256, 256)
+    assert E.projected_uncertainty(mu, cov)[0].shape == (0, 21)
+    assert E.contour_perimeter(torch.zeros((0, 21, 2), device=dev)).shape == (0,)
+    d, s = E.simpson_diameters(torch.zeros((0, 2048), dtype=torch.int32, device=dev), 0.5)
+    assert d.shape == (0, 20) and s.shape == (0,)
+    with pytest.raises(ValueError):
+        E.skew_sample(model, torch.zeros((2, 20, 2), device=dev), torch.zeros((2, 20, 2, 2), device=dev), torch.zeros((2, 20, 2), device=dev), 4)
+    with pytest.raises(ValueError):
+        E.simpson_volumes(torch.zeros((1, 3, 4, 20), dtype=torch.float64, device=dev), torch.zeros((1, 3, 4), dtype=torch.float64, device=dev))
+    with pytest.raises(ValueError, match="no CPU implementation"):
+        E.umap_analytic(torch.zeros((1, 21, 2)), torch.zeros((1, 21, 2, 2)))
+    with pytest.raises(ValueError):
+        E.simpson_diameters(torch.zeros((4, 100), dtype=torch.int32, device=dev), 0.5)
+    with pytest.raises(ValueError):
+        E.simpson_diameters(torch.zeros((4, 2048), dtype=torch.int32, device=dev), -1.0)
