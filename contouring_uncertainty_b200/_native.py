@@ -36,6 +36,7 @@ SIGNATURES = {
     "cub200_psm_conditionals": [_vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_skew_sample": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _i64, _vp, _vp, _vp],
     "cub200_simpson_diameters": [_vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp],
+    "cub200_simpson_diameters_stretched": [_vp, _i64, _vp, _vp, _i32, _i32, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_simpson_volumes": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "cub200_rasterize_contours_f64": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
     "cub200_projected_uncertainty": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -35,12 +35,22 @@ __constant__ unsigned char c_from_of_to[16][4] = {
 // from-edge of the FIRST segment a cell generates (cases 6 and 9 generate two)
 __constant__ unsigned char c_first_from[16] = {9, 0, 3, 3, 2, 0, 3, 3, 1, 0, 1, 1, 2, 0, 2, 9};
 
-__device__ __forceinline__ int mask_bit(const uint32_t* __restrict__ m, int r, int c) {
-    return (m[r * 8 + (c >> 5)] >> (c & 31)) & 1u;
-}
-__device__ __forceinline__ int cell_case(const uint32_t* __restrict__ m, int r0, int c0) {
-    return mask_bit(m, r0, c0) | (mask_bit(m, r0, c0 + 1) << 1) | (mask_bit(m, r0 + 1, c0) << 2) | (mask_bit(m, r0 + 1, c0 + 1) << 3);
-}
+// A mask as the Simpson code sees it: the 256 x 256 bit-packed mask itself, or (anisotropic voxel spacing) its
+// nearest-neighbour stretch to H x W -- resize_image_to_isotropic (vital/vital/utils/image/transform.py:52-66) through
+// PIL's NEAREST resize, whose source index per output row / column is precomputed by the host (ri, ci).
+struct MaskView {
+    const uint32_t* m;
+    const uint16_t* ri;    // source row of each virtual row (nullptr: identity)
+    const uint16_t* ci;    // source column of each virtual column
+    int H, W;
+    __device__ __forceinline__ int bit(int r, int c) const {
+        if (ri) { r = ri[r]; c = ci[c]; }
+        return (m[r * 8 + (c >> 5)] >> (c & 31)) & 1u;
+    }
+    __device__ __forceinline__ int cell(int r0, int c0) const {
+        return bit(r0, c0) | (bit(r0, c0 + 1) << 1) | (bit(r0 + 1, c0) << 2) | (bit(r0 + 1, c0 + 1) << 3);
+    }
+};
 // a cell's second segment (saddle cases): the one starting at L (case 6) / B (case 9)
 __device__ __forceinline__ int seg_rank(int cs, int from_edge) {
     return (cs == 6 && from_edge == 2) || (cs == 9 && from_edge == 1);
@@ -54,49 +64,74 @@ __device__ __forceinline__ uint32_t edge_point(int r0, int c0, int e) {
 
 // ---------------------------------------------------------------- S1: contour tracing, one thread per mask
 __global__ void __launch_bounds__(128)
-contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, uint32_t* __restrict__ pts, int32_t* __restrict__ npts) {
+contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const uint16_t* __restrict__ row_index,
+                     const uint16_t* __restrict__ col_index, int vh, int vw, uint32_t* __restrict__ pts, int32_t* __restrict__ npts) {
+    extern __shared__ uint16_t s_idx[];                           // [vh rows][vw columns] source indices (stretched view)
+    if (row_index) {
+        for (int i = threadIdx.x; i < vh; i += blockDim.x) s_idx[i] = row_index[i];
+        for (int i = threadIdx.x; i < vw; i += blockDim.x) s_idx[vh + i] = col_index[i];
+        __syncthreads();
+    }
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g >= n_masks) return;
     const uint32_t* m = masks + g * CUB200_MASK_WORDS;
+    const MaskView mv{m, row_index ? s_idx : nullptr, row_index ? s_idx + vh : nullptr, vh, vw};
+    const int RM = vh - 2, CM = vw - 2;                           // last cell row / column
     uint32_t* out = pts + g * SP_NMAX;
     // raster-first cell that generates a segment
     int fr = -1, fc = -1;
-    uint32_t a[8], b[8];
+    if (!row_index) {
+        uint32_t a[8], b[8];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) a[w] = m[w];
-    for (int r0 = 0; r0 < 255 && fr < 0; ++r0) {
+        for (int w = 0; w < 8; ++w) a[w] = m[w];
+        for (int r0 = 0; r0 < 255 && fr < 0; ++r0) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) b[w] = m[(r0 + 1) * 8 + w];
+            for (int w = 0; w < 8; ++w) b[w] = m[(r0 + 1) * 8 + w];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t a1 = (a[w] >> 1) | ((w < 7 ? a[w < 7 ? w + 1 : 7] : 0u) << 31);
-            const uint32_t b1 = (b[w] >> 1) | ((w < 7 ? b[w < 7 ? w + 1 : 7] : 0u) << 31);
-            uint32_t nu = (a[w] ^ b[w]) | (a[w] ^ a1) | (b[w] ^ b1);
-            if (w == 7) nu &= 0x7fffffffu;                       // there is no cell at c0 = 255
-            if (nu && fr < 0) { fr = r0; fc = 32 * w + __ffs(nu) - 1; }
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t a1 = (a[w] >> 1) | ((w < 7 ? a[w < 7 ? w + 1 : 7] : 0u) << 31);
+                const uint32_t b1 = (b[w] >> 1) | ((w < 7 ? b[w < 7 ? w + 1 : 7] : 0u) << 31);
+                uint32_t nu = (a[w] ^ b[w]) | (a[w] ^ a1) | (b[w] ^ b1);
+                if (w == 7) nu &= 0x7fffffffu;                   // there is no cell at c0 = 255
+                if (nu && fr < 0) { fr = r0; fc = 32 * w + __ffs(nu) - 1; }
+            }
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a[w] = b[w];
         }
+    } else {
+        // stretched view: skip the row pairs whose source rows are both empty, then scan the cells of the first other one
+        for (int r0 = 0; r0 <= RM && fr < 0; ++r0) {
+            const uint32_t* ra = m + mv.ri[r0] * 8;
+            const uint32_t* rb = m + mv.ri[r0 + 1] * 8;
+            uint32_t any = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a[w] = b[w];
+            for (int w = 0; w < 8; ++w) any |= ra[w] | rb[w];
+            if (!any) continue;
+            for (int c0 = 0; c0 <= CM; ++c0) {
+                const int cs = mv.cell(r0, c0);
+                if (cs != 0 && cs != 15) { fr = r0; fc = c0; break; }
+            }
+        }
     }
     if (fr < 0) { npts[g] = 0; return; }                          // find_contours() == [] -> IndexError
     // pass A: walk backwards from the first segment to the chain start, or around the loop
-    const int cs0 = cell_case(m, fr, fc);
+    const int cs0 = mv.cell(fr, fc);
     const int f0 = c_first_from[cs0];
     int r0 = fr, c0 = fc, fe = f0;                                // current segment = (cell, from-edge)
     int sr = fr, sc = fc, sf = f0;                                // start segment of pass B
     bool closed = false;
     int last_key = -1, lr = 0, lc = 0, lt = 0;                    // raster-last segment of the loop
     for (int it = 0; it < 4 * SP_NMAX; ++it) {
-        const int cs = cell_case(m, r0, c0);
+        const int cs = mv.cell(r0, c0);
         const int te = c_to_of_from[cs][fe];
-        const int key = ((r0 * 255 + c0) << 1) | seg_rank(cs, fe);
+        const int key = ((r0 * (CM + 1) + c0) << 1) | seg_rank(cs, fe);
         if (key > last_key) { last_key = key; lr = r0; lc = c0; lt = te; }
         // predecessor: the cell across the from-edge, whose segment ends on the shared edge
         int pr = r0, pc = c0, pe;
         if (fe == 0) { pr = r0 - 1; pe = 1; } else if (fe == 1) { pr = r0 + 1; pe = 0; }
         else if (fe == 2) { pc = c0 - 1; pe = 3; } else { pc = c0 + 1; pe = 2; }
-        if (pr < 0 || pr > 254 || pc < 0 || pc > 254) { sr = r0; sc = c0; sf = fe; break; }   // open chain start
-        const int pf = c_from_of_to[cell_case(m, pr, pc)][pe];
+        if (pr < 0 || pr > RM || pc < 0 || pc > CM) { sr = r0; sc = c0; sf = fe; break; }     // open chain start
+        const int pf = c_from_of_to[mv.cell(pr, pc)][pe];
         r0 = pr; c0 = pc; fe = pf;
         if (r0 == fr && c0 == fc && fe == f0) { closed = true; break; }
     }
@@ -113,14 +148,14 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, uint32
     out[n++] = edge_point(r0, c0, fe);
     bool overflow = false;
     for (;;) {
-        const int cs = cell_case(m, r0, c0);
+        const int cs = mv.cell(r0, c0);
         const int te = c_to_of_from[cs][fe];
         if (n >= SP_NMAX) { overflow = true; break; }
         out[n++] = edge_point(r0, c0, te);
         int nr = r0, nc = c0, ne;
         if (te == 0) { nr = r0 - 1; ne = 1; } else if (te == 1) { nr = r0 + 1; ne = 0; }
         else if (te == 2) { nc = c0 - 1; ne = 3; } else { nc = c0 + 1; ne = 2; }
-        if (nr < 0 || nr > 254 || nc < 0 || nc > 254) break;       // open chain end
+        if (nr < 0 || nr > RM || nc < 0 || nc > CM) break;         // open chain end
         r0 = nr; c0 = nc; fe = ne;
         if (closed && r0 == sr && c0 == sc && fe == sf) break;
     }
@@ -140,9 +175,16 @@ __device__ __forceinline__ bool chord_better(const Chord& a, const Chord& b) {  
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
 simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict__ pts_g, const int32_t* __restrict__ npts,
-                         int64_t n_masks, double spacing, double* __restrict__ diam_out, double* __restrict__ step_out) {
+                         int64_t n_masks, const uint16_t* __restrict__ row_index, const uint16_t* __restrict__ col_index, int vh,
+                         int vw, double spacing, double* __restrict__ diam_out, double* __restrict__ step_out) {
     __shared__ uint32_t s_pts[SP_WARPS][SP_NMAX];
     __shared__ uint32_t s_bmax[SP_WARPS][SP_NMAX / 32];
+    extern __shared__ uint16_t s_idx[];
+    if (row_index) {
+        for (int i = threadIdx.x; i < vh; i += blockDim.x) s_idx[i] = row_index[i];
+        for (int i = threadIdx.x; i < vw; i += blockDim.x) s_idx[vh + i] = col_index[i];
+        __syncthreads();
+    }
     const int lane = lane_id(), wid = threadIdx.x >> 5;
     const int64_t g = blockIdx.x * (int64_t)SP_WARPS + wid;
     if (g >= n_masks) return;
@@ -250,7 +292,7 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     const double nrm = sqrt(__dadd_rn(__dmul_rn(dir_c, dir_c), __dmul_rn(dir_r, dir_r)));
     const double nr = -dir_c / nrm, nc = dir_r / nrm;    // normal_direction = (-direction[1], direction[0]) / |.|
     const double mid_r = 0.5 * (double)mr, mid_c = 0.5 * (double)mc;
-    const uint32_t* m = masks + g * CUB200_MASK_WORDS;
+    const MaskView mv{masks + g * CUB200_MASK_WORDS, row_index ? s_idx : nullptr, row_index ? s_idx + vh : nullptr, vh, vw};
     // 20 discs x 2 directions (heart_us.py:158-164)
     double d_pos = 0.0, d_neg = 0.0, d_neg2 = 0.0;
     for (int ray = lane; ray < 40; ray += 32) {
@@ -262,8 +304,8 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
         double dist = 8.0;
         for (;;) {
             const double y = rint(__dadd_rn(pr, __dmul_rn(dist, vr))), x = rint(__dadd_rn(pc, __dmul_rn(dist, vc)));
-            if (!(y >= 0.0 && y < 256.0 && x >= 0.0 && x < 256.0)) break;        // out of bounds (NaN too: the reference raises there)
-            if (!mask_bit(m, (int)y, (int)x)) break;
+            if (!(y >= 0.0 && y < (double)vh && x >= 0.0 && x < (double)vw)) break;   // out of bounds (NaN too: the reference raises there)
+            if (!mv.bit((int)y, (int)x)) break;
             dist += 0.5;
         }
         if (ray < 20) d_pos = dist; else if (ray < 32) d_neg = dist; else d_neg2 = dist;
@@ -332,23 +374,40 @@ extern "C" int64_t cub200_simpson_workspace_bytes(int64_t n_masks) {
     return n_masks * (int64_t)(cub200::SP_NMAX * sizeof(uint32_t) + sizeof(int32_t));
 }
 
-extern "C" int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spacing, double* diam_out,
-                                        double* step_out, int32_t* npts_out, void* workspace, void* stream) {
+static int simpson_launch(const uint32_t* masks, int64_t n_masks, const uint16_t* row_index, const uint16_t* col_index, int vh, int vw,
+                          double spacing, double* diam_out, double* step_out, int32_t* npts_out, void* workspace, cudaStream_t st) {
     using namespace cub200;
-    if (n_masks == 0) return 0;
-    if (!masks || !diam_out || !step_out || !workspace || n_masks < 0 || !(spacing > 0.0)) return CUB200_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
     uint32_t* pts = reinterpret_cast<uint32_t*>(workspace);
     int32_t* npts = reinterpret_cast<int32_t*>(pts + n_masks * SP_NMAX);
-    contour_trace_kernel<<<(unsigned)((n_masks + 127) / 128), 128, 0, st>>>(masks, n_masks, pts, npts);
+    const size_t idx_smem = row_index ? sizeof(uint16_t) * (size_t)(vh + vw) : 0;
+    contour_trace_kernel<<<(unsigned)((n_masks + 127) / 128), 128, idx_smem, st>>>(masks, n_masks, row_index, col_index, vh, vw, pts, npts);
     int rc = check_launch("contour_trace_kernel");
     if (rc) return rc;
-    simpson_diameters_kernel<<<(unsigned)((n_masks + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, 0, st>>>(
-        masks, pts, npts, n_masks, spacing, diam_out, step_out);
+    simpson_diameters_kernel<<<(unsigned)((n_masks + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, idx_smem, st>>>(
+        masks, pts, npts, n_masks, row_index, col_index, vh, vw, spacing, diam_out, step_out);
     rc = check_launch("simpson_diameters_kernel");
     if (rc) return rc;
     if (npts_out) CUB200_CUDA_OK(cudaMemcpyAsync(npts_out, npts, sizeof(int32_t) * n_masks, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+extern "C" int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spacing, double* diam_out,
+                                        double* step_out, int32_t* npts_out, void* workspace, void* stream) {
+    if (n_masks == 0) return 0;
+    if (!masks || !diam_out || !step_out || !workspace || n_masks < 0 || !(spacing > 0.0)) return CUB200_EINVAL;
+    return simpson_launch(masks, n_masks, nullptr, nullptr, 256, 256, spacing, diam_out, step_out, npts_out, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int cub200_simpson_diameters_stretched(const uint32_t* masks, int64_t n_masks, const uint16_t* row_index,
+                                                  const uint16_t* col_index, int height, int width, double spacing,
+                                                  double* diam_out, double* step_out, int32_t* npts_out, void* workspace,
+                                                  void* stream) {
+    if (n_masks == 0) return 0;
+    if (!masks || !row_index || !col_index || !diam_out || !step_out || !workspace || n_masks < 0 || !(spacing > 0.0) ||
+        height < 2 || width < 2 || height > CUB200_SIMPSON_MAX_SIDE || width > CUB200_SIMPSON_MAX_SIDE)
+        return CUB200_EINVAL;
+    return simpson_launch(masks, n_masks, row_index, col_index, height, width, spacing, diam_out, step_out, npts_out, workspace,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int cub200_simpson_volumes(const double* diam, const double* step, int64_t n_patients, int64_t n_samples,

@@ -482,12 +482,42 @@ def seq_skew_sample(model: ShapeModelConstants, seq: "SequenceModelConstants", m
 # --------------------------------------------------------------------------------------------------
 # Simpson's biplane volumes (uncertainty propagation)
 # --------------------------------------------------------------------------------------------------
-def simpson_diameters(masks: torch.Tensor, spacing: float, return_npts: bool = False):
+def pil_nearest_index(n_in: int, n_out: int) -> np.ndarray:
+    """Source index of every output index of PIL's NEAREST resize (ImagingScaleAffine): (int)(0.5 a + k a), a = n_in / n_out,
+    with the sum formed by repeated double additions exactly as Pillow does (it differs from (k + 0.5) a at exact ties)."""
+    a = n_in / n_out
+    xo = a * 0.5
+    out = np.empty(n_out, dtype=np.uint16)
+    for k in range(n_out):
+        out[k] = min(int(xo), n_in - 1)
+        xo += a
+    return out
+
+
+def isotropic_view(voxelspacing) -> tuple:
+    """resize_image_to_isotropic (vital/vital/utils/image/transform.py:52-66) for a 256 x 256 mask: (height, width,
+    row_index, col_index, isotropic spacing) of the nearest-neighbour stretch; (256, 256, None, None, s) when isotropic."""
+    sy, sx = float(voxelspacing[0]), float(voxelspacing[1])
+    iso = min(sy, sx)
+    scaling = np.array((sy, sx)) / np.array((iso, iso))
+    nh, nw = (np.array((HW, HW)) * scaling).round().astype(int)
+    if nh == HW and nw == HW:
+        return HW, HW, None, None, iso
+    return int(nh), int(nw), pil_nearest_index(HW, int(nh)), pil_nearest_index(HW, int(nw)), iso
+
+
+def simpson_diameters(masks: torch.Tensor, spacing, return_npts: bool = False):
     """_compute_diameters (vital heart_us.py:107-167) per bit-packed mask: masks (..., 2048) int32 ->
-    (diameters (..., 20) fp64 mm, step (...) fp64); NaN where the reference raises."""
+    (diameters (..., 20) fp64 mm, step (...) fp64); NaN where the reference raises.  ``spacing``: a float (isotropic) or
+    (height, width) voxel sizes -- anisotropic masks are seen through their nearest-neighbour stretch to isotropic
+    spacing, as the reference's PIL resize produces it."""
     masks = nat.require_cuda(masks, torch.int32, "masks")
     if masks.shape[-1] != MASK_WORDS:
         raise ValueError(f"masks must be (..., {MASK_WORDS}) int32 bit-packed")
+    vs = (float(spacing), float(spacing)) if np.isscalar(spacing) else (float(spacing[0]), float(spacing[1]))
+    if not (vs[0] > 0 and vs[1] > 0):
+        raise ValueError("voxel spacing must be positive")
+    nh, nw, ri, ci, iso = isotropic_view(vs)
     lead = tuple(masks.shape[:-1])
     n = int(np.prod(lead)) if lead else 1
     dev = masks.device
@@ -496,8 +526,16 @@ def simpson_diameters(masks: torch.Tensor, spacing: float, return_npts: bool = F
     npts = torch.empty(lead, dtype=torch.int32, device=dev) if return_npts else None
     ws = torch.empty((max(int(nat.lib().cub200_simpson_workspace_bytes(n)), 1),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = nat.lib().cub200_simpson_diameters(nat.ptr(masks), n, float(spacing), nat.ptr(diam), nat.ptr(step), nat.ptr(npts),
-                                                nat.ptr(ws), nat.stream_ptr(dev))
+        if ri is None:
+            rc = nat.lib().cub200_simpson_diameters(nat.ptr(masks), n, iso, nat.ptr(diam), nat.ptr(step), nat.ptr(npts),
+                                                    nat.ptr(ws), nat.stream_ptr(dev))
+        else:
+            if max(nh, nw) > 1024:
+                raise ValueError("voxel spacing ratio too large: the isotropic view would exceed 1024 pixels")
+            rit = torch.from_numpy(ri.astype(np.int16)).to(dev)
+            cit = torch.from_numpy(ci.astype(np.int16)).to(dev)
+            rc = nat.lib().cub200_simpson_diameters_stretched(nat.ptr(masks), n, nat.ptr(rit), nat.ptr(cit), nh, nw, iso, nat.ptr(diam),
+                                                              nat.ptr(step), nat.ptr(npts), nat.ptr(ws), nat.stream_ptr(dev))
     nat.check(rc, "cub200_simpson_diameters")
     return (diam, step, npts) if return_npts else (diam, step)
 
@@ -518,15 +556,22 @@ def simpson_volumes(diam: torch.Tensor, step: torch.Tensor):
     return tuple(out)
 
 
-def biplane_volumes_from_contours(contours: torch.Tensor, spacing: float):
+def biplane_volumes_from_contours(contours: torch.Tensor, spacing, spacing_a4c=None):
     """contours (P,4,T,21,2) fp32 [A2C-ED, A2C-ES, A4C-ED, A4C-ES] -> (edv, esv, ef (P,T), area (P,4,T)).
-    Rasterise every sampled contour (bit-packed masks), then Simpson's biplane rule per sample."""
+    Rasterise every sampled contour (bit-packed masks), then Simpson's biplane rule per sample.  ``spacing`` (float or
+    (height, width)) is the A2C voxel spacing, ``spacing_a4c`` the A4C one (default: the same)."""
     contours = nat.require_cuda(contours, torch.float32, "contours")
     if contours.dim() != 5 or contours.shape[1] != 4 or contours.shape[3:] != (K, 2):
         raise ValueError("contours (P,4,T,21,2) expected")
     P_, _, T = contours.shape[:3]
     masks, area = rasterize_contours(contours.reshape(-1, K, 2), return_masks=True)
-    diam, step = simpson_diameters(masks.reshape(P_, 4, T, MASK_WORDS), spacing)
+    masks = masks.reshape(P_, 4, T, MASK_WORDS)
+    if spacing_a4c is None:
+        diam, step = simpson_diameters(masks, spacing)
+    else:
+        d2, s2 = simpson_diameters(masks[:, :2].contiguous(), spacing)
+        d4, s4 = simpson_diameters(masks[:, 2:].contiguous(), spacing_a4c)
+        diam, step = torch.cat([d2, d4], 1), torch.cat([s2, s4], 1)
     edv, esv, ef = simpson_volumes(diam, step)
     return edv, esv, ef, area.reshape(P_, 4, T)
 

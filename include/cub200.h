@@ -31,6 +31,7 @@ extern "C" {
 #define CUB200_ZMAX 42       /* max number of standard-normal draws / sample */
 #define CUB200_MASK_WORDS 2048 /* 256 rows x 8 uint32 (bit x&31 of word x>>5) */
 #define CUB200_SIMPSON_MAX_POINTS 2048 /* marching-squares contour points kept per mask */
+#define CUB200_SIMPSON_MAX_SIDE 1024    /* largest side of a stretched (isotropic) mask view */
 
 #define CUB200_EINVAL (-1)
 #define CUB200_ECUDA (-2)
@@ -282,6 +283,18 @@ int cub200_seq_skew_sample(const float* mu, const float* cov, const float* alpha
 int64_t cub200_simpson_workspace_bytes(int64_t n_masks);
 int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spacing, double* diam_out, double* step_out,
                              int32_t* npts_out, void* workspace, void* stream);
+
+/*
+ * The same on masks with ANISOTROPIC voxel spacing: the reference first stretches the mask to isotropic spacing with PIL's
+ * nearest-neighbour resize (resize_image_to_isotropic, vital/vital/utils/image/transform.py:52-66; heart_us.py:117).  The
+ * stretched mask is never materialised: row_index (height) / col_index (width) uint16 device arrays give the source row /
+ * column of every row / column of the stretched view (PIL's ImagingScaleAffine rule: index = (int)(0.5 a + k a) with the
+ * sum formed by repeated double additions, a = 256 / size); height, width <= CUB200_SIMPSON_MAX_SIDE; spacing = the
+ * isotropic (smaller) spacing.
+ */
+int cub200_simpson_diameters_stretched(const uint32_t* masks, int64_t n_masks, const uint16_t* row_index,
+                                       const uint16_t* col_index, int height, int width, double spacing, double* diam_out,
+                                       double* step_out, int32_t* npts_out, void* workspace, void* stream);
 
 /*
  * Simpson's biplane rule, step 2: EDV / ESV (mL, integers stored as fp64) and EF per Monte-Carlo sample.

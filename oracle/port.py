@@ -805,13 +805,18 @@ def _find_distance_to_edge(seg: np.ndarray, point: np.ndarray, normal: np.ndarra
 
 
 def compute_diameters(segmentation: np.ndarray, voxelspacing=(1.0, 1.0)):
-    """``_compute_diameters`` (heart_us.py:107-167) for isotropic spacing (the PIL nearest-neighbour stretch of
-    ``resize_image_to_isotropic`` is the identity then).  Returns (diameters (20,), step_size); raises like the
-    reference when no contour / no admissible base chord exists (the caller's bare except zeroes the sample)."""
-    if voxelspacing[0] != voxelspacing[1]:
-        raise NotImplementedError("anisotropic spacing (PIL nearest resize) is a 'next' row")
+    """``_compute_diameters`` (heart_us.py:107-167); anisotropic masks are stretched to isotropic spacing by PIL's
+    nearest-neighbour resize first, as ``resize_image_to_isotropic`` does.  Returns (diameters (20,), step_size); raises like
+    the reference when no contour / no admissible base chord exists (the caller's bare except zeroes the sample)."""
     spacing = min(voxelspacing)
     seg = np.asarray(segmentation)
+    if voxelspacing[0] != voxelspacing[1]:
+        # resize_image_to_isotropic -> resize_image_to_voxelspacing -> PIL NEAREST (transform.py:14-66), called as the reference does
+        from PIL import Image
+
+        scaling = np.array(voxelspacing) / np.array((spacing, spacing))
+        new_h, new_w = (np.array(seg.shape[-2:]) * scaling).round().astype(int)
+        seg = np.array(Image.fromarray(seg.astype(bool)).resize((int(new_w), int(new_h)), resample=Image.NEAREST))
     contour = find_contours(seg, 0.5)[0]
     n = len(contour)
     best_length, best_i, best_j = 0, None, None

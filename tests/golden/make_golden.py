@@ -317,8 +317,26 @@ def golden_simpson():
         except:  # noqa: E722  (as the reference)
             pass
     ef[np.logical_or(ef < 0, ef > 1)] = np.nan
+    # anisotropic voxel spacing (the real CAMUS case): PIL nearest-neighbour stretch inside _compute_diameters
+    vs2, vs4 = (0.5, 0.35), (0.31, 0.42)
+    diam_a = np.full((4, T, 20), np.nan)
+    step_a = np.full((4, T), np.nan)
+    for v in range(4):
+        for t in range(T):
+            try:
+                diam_a[v, t], step_a[v, t] = _compute_diameters(masks[v, t], vs2 if v < 2 else vs4)
+            except Exception as e:
+                print("  _compute_diameters (anisotropic) raised", v, t, type(e).__name__)
+    edv_a, esv_a = np.zeros(T), np.zeros(T)
+    for t in range(T):
+        try:
+            edv_a[t], esv_a[t] = compute_left_ventricle_volumes(masks[0, t], masks[1, t], vs2, masks[2, t], masks[3, t], vs4)
+        except:  # noqa: E722
+            pass
     np.savez_compressed(os.path.join(HERE, "simpson.npz"), contours=contours, voxelspacing=np.array(vs),
-                        areas=masks.sum((2, 3)), diameters=diam, step=step, edv=edv, esv=esv, ef=ef)
+                        areas=masks.sum((2, 3)), diameters=diam, step=step, edv=edv, esv=esv, ef=ef,
+                        vs_a2c=np.array(vs2), vs_a4c=np.array(vs4), diameters_aniso=diam_a, step_aniso=step_a,
+                        edv_aniso=edv_a, esv_aniso=esv_a)
     print("simpson.npz edv", edv, "esv", esv, "ef", ef)
 
 

@@ -124,3 +124,37 @@ def test_simpson_full_size_properties(dev):
     # spacing is a pure scale: diameters and step scale linearly
     d2, s2 = E.simpson_diameters(masks.reshape(4, 10, 2048), 1.0)
     assert torch.allclose(d2, 2 * d1, rtol=1e-15) and torch.allclose(s2, 2 * s1, rtol=1e-15)
+
+
+def test_simpson_anisotropic_spacing_vs_reference(dev):
+    """Anisotropic voxel spacing (the real CAMUS case): the reference stretches every mask with PIL's nearest-neighbour
+    resize before measuring it; the kernels see the stretched mask through index tables.  Diameters / step fp64-identical
+    to the executed reference, EDV / ESV identical."""
+    from contouring_uncertainty_b200 import engine as E
+    from PIL import Image
+
+    g = np.load(os.path.join(G, "simpson.npz"))
+    contours = torch.from_numpy(g["contours"]).to(dev)
+    T = contours.shape[1]
+    vs2, vs4 = tuple(g["vs_a2c"]), tuple(g["vs_a4c"])
+    masks, _ = E.rasterize_contours(contours.reshape(-1, 21, 2), return_masks=True)
+    masks = masks.reshape(4, T, 2048)
+    d2, s2 = E.simpson_diameters(masks[:2].contiguous(), vs2)
+    d4, s4 = E.simpson_diameters(masks[2:].contiguous(), vs4)
+    diam, step = torch.cat([d2, d4]), torch.cat([s2, s4])
+    assert np.array_equal(diam.cpu().numpy(), g["diameters_aniso"])
+    assert np.array_equal(step.cpu().numpy(), g["step_aniso"])
+    edv, esv, ef = E.simpson_volumes(diam[None], step[None])
+    assert np.array_equal(edv.cpu().numpy()[0], g["edv_aniso"]) and np.array_equal(esv.cpu().numpy()[0], g["esv_aniso"])
+    e2 = E.biplane_volumes_from_contours(contours[None].contiguous(), vs2, vs4)
+    assert torch.equal(e2[0], edv) and torch.equal(e2[1], esv)
+    # the index tables ARE PIL's nearest-neighbour resize
+    rng = np.random.default_rng(0)
+    img = rng.uniform(size=(256, 256)) < 0.5
+    for nh, nw in ((366, 256), (256, 347), (300, 411)):
+        want = np.array(Image.fromarray(img).resize((nw, nh), resample=Image.NEAREST))
+        assert np.array_equal(img[np.ix_(E.pil_nearest_index(256, nh), E.pil_nearest_index(256, nw))], want)
+    # isotropic spacing given as a pair takes the plain path
+    d0, s0 = E.simpson_diameters(masks[:1].contiguous(), (0.5, 0.5))
+    d1, s1 = E.simpson_diameters(masks[:1].contiguous(), 0.5)
+    assert torch.equal(d0, d1) and torch.equal(s0, s1)
