@@ -51,7 +51,7 @@ __host__ __device__ constexpr LevelDef level_def(int l) {
 }
 
 struct __align__(16) PFWarp {
-    double A[Z][Z];        // pixel-space map of the sampled variables (row = permuted variable, col = draw)
+    double A[Z][Z];        // map of the sampled variables IN THE SCALER'S SPACE, At = A / scale (row = permuted variable, col = draw)
     double Acc[16][Z];     // M At_g of the current level
     double d[P], u[Z], t[Z];
     double w[16], kd[16], corr[16];
@@ -139,9 +139,9 @@ psm_factor_kernel(const double* __restrict__ pack, const float* __restrict__ mu,
             const int j = c_order[lane];
             const double p00 = cov_i[4 * j], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
             const double l00 = sqrt(p00), l10 = p10 / l00, l11 = sqrt(p11 - l10 * l10);
-            ws.A[2 * lane][2 * lane] = l00;
-            ws.A[2 * lane + 1][2 * lane] = l10;
-            ws.A[2 * lane + 1][2 * lane + 1] = l11;
+            ws.A[2 * lane][2 * lane] = l00 / pk[PK_SCALE + 2 * lane];
+            ws.A[2 * lane + 1][2 * lane] = l10 / pk[PK_SCALE + 2 * lane + 1];
+            ws.A[2 * lane + 1][2 * lane + 1] = l11 / pk[PK_SCALE + 2 * lane + 1];
         }
         group_sync<WPI>();
         float* out = a_out + img * (Z * P);
@@ -154,14 +154,14 @@ psm_factor_kernel(const double* __restrict__ pack, const float* __restrict__ mu,
             // t = u^T At_g ; Acc = K At_g + corr t^T      (At = A / scale: the sampled contour in the scaler's space)
             for (int e = lane; e < Z; e += NT) {
                 double acc = 0.0;
-                for (int k = 0; k < n; ++k) acc = fma(ws.u[k] / pk[PK_SCALE + k], ws.A[k][e], acc);
+                for (int k = 0; k < n; ++k) acc = fma(ws.u[k], ws.A[k][e], acc);
                 ws.t[e] = acc;
             }
             group_sync<WPI>();
             for (int idx = lane; idx < rows * Z; idx += NT) {
                 const int a = idx / Z, e = idx - a * Z;
                 double acc = ws.corr[a] * ws.t[e];
-                for (int k = 0; k < n; ++k) acc = fma(K[a * n + k] / pk[PK_SCALE + k], ws.A[k][e], acc);
+                for (int k = 0; k < n; ++k) acc = fma(K[a * n + k], ws.A[k][e], acc);
                 ws.Acc[a][e] = acc;
             }
             group_sync<WPI>();
@@ -190,8 +190,8 @@ psm_factor_kernel(const double* __restrict__ pack, const float* __restrict__ mu,
                         if (e == v0) { a0 += l00; a1 += l10; }
                         else { a1 += l11; }
                     }
-                    ws.A[v0][e] = a0;
-                    ws.A[v1][e] = a1;
+                    ws.A[v0][e] = a0 / pk[PK_SCALE + v0];
+                    ws.A[v1][e] = a1 / pk[PK_SCALE + v1];
                 }
                 group_sync<WPI>();
             } else {
@@ -206,7 +206,7 @@ psm_factor_kernel(const double* __restrict__ pack, const float* __restrict__ mu,
         for (int idx = lane; idx < Z * Z; idx += NT) {
             const int v = idx / Z, e = idx - v * Z;
             const int o = 2 * c_order[v >> 1] + (v & 1);
-            out[e * P + o] = (float)ws.A[v][e];              // out[e][d], d = original flat index
+            out[e * P + o] = (float)(ws.A[v][e] * pk[PK_SCALE + v]);   // out[e][d], d = original flat index
         }
         group_sync<WPI>();
     }
@@ -275,16 +275,18 @@ __global__ void naive_factor_kernel(const float* __restrict__ cov, int64_t n_img
 }
 
 static int pf_launch_cfg(int64_t n_img, const void* kernel, int images_per_cta, int* grid, size_t* smem) {
+    const bool warp_per_image = images_per_cta > 1;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
         CUB200_CUDA_OK(cudaGetDevice(&dev));
         CUB200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    *smem = sizeof(double) * PACK_DOUBLES + sizeof(PFWarp) * PF_WARPS;
+    // (reading the constants through L1 instead of staging them, to fit a third CTA per SM, was slower: 9.3 vs 7.9 ms)
+    *smem = sizeof(double) * PACK_DOUBLES + sizeof(PFWarp) * (warp_per_image ? PF_WARPS : 1);
     CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     const int64_t need = (n_img + images_per_cta - 1) / images_per_cta;
-    const int64_t cap = (int64_t)num_sms * 2;
+    const int64_t cap = (int64_t)num_sms * (warp_per_image ? 2 : 4);
     *grid = (int)(need < cap ? need : cap);
     return 0;
 }
