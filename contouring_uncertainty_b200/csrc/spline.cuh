@@ -9,6 +9,16 @@
 
 namespace cub200 {
 
+// 1 / x to ~1 ulp: hardware seed (20 bits) + two Newton steps.  The IEEE division sequence costs ~3x as many issue slots
+// and the solve is not bit-identical to FITPACK's anyway (different algorithm, agreement ~1e-13).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 struct __align__(16) SplineScratch {
     double u[24];          // chord parameters u_0..u_20
     double piece[20][10];  // piece i on [u_i, u_{i+1}]: {u_{i+1}, u_i, x c0..c3, y c0..c3} (powers of u - u_i)
@@ -41,7 +51,7 @@ __device__ __forceinline__ bool fit_spline(SplineScratch& sp, const double X, co
     const double unext = __shfl_down_sync(FULL, u, 1);
     const double Xn = __shfl_down_sync(FULL, X, 1), Yn = __shfl_down_sync(FULL, Y, 1);
     const double h = unext - u;                         // h_k, k < 20
-    const double ih = 1.0 / h;
+    const double ih = fast_rcp(h);
     const double dxk = (Xn - X) * ih, dyk = (Yn - Y) * ih;  // divided differences delta_k
     const double hm = __shfl_up_sync(FULL, h, 1);
     const double dxm = __shfl_up_sync(FULL, dxk, 1), dym = __shfl_up_sync(FULL, dyk, 1);
@@ -58,7 +68,7 @@ __device__ __forceinline__ bool fit_spline(SplineScratch& sp, const double X, co
             const double f = hm / (hm + h);
             a = hm - h; b = h + 2.0 * hm; c = 0.0; r1 *= f; r2 *= f;
         }
-        const double ib = 1.0 / b;
+        const double ib = fast_rcp(b);
         ta = a * ib; tc = c * ib; tx = r1 * ib; ty = r2 * ib;
     }
     // parallel cyclic reduction: 5 steps decouple the 19 equations (x and y share the matrix)
@@ -70,7 +80,7 @@ __device__ __forceinline__ bool fit_spline(SplineScratch& sp, const double X, co
         double xp = __shfl_down_sync(FULL, tx, sft), yp = __shfl_down_sync(FULL, ty, sft);
         if (lane < sft) { am = cm = xm = ym = 0.0; }
         if (lane + sft > 31) { ap = cp = xp = yp = 0.0; }
-        const double r = 1.0 / (1.0 - ta * cm - tc * ap);
+        const double r = fast_rcp(1.0 - ta * cm - tc * ap);
         tx = (tx - ta * xm - tc * xp) * r;
         ty = (ty - ta * ym - tc * yp) * r;
         ta = -ta * am * r;
