@@ -48,6 +48,8 @@ SIGNATURES = {
     "cub200_metric_sums": [_vp, _i64, _vp, _vp],
     "cub200_calibration_bins": [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp],
     "cub200_contour_perimeter": [_vp, _i64, _vp, _vp],
+    "cub200_bivariate_pdf": [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    "cub200_skew_rvs_fast": [_vp, _vp, _vp, _vp, _u64, _i64, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes")
 

@@ -380,6 +380,48 @@ def skew_pdf_grid(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, flip
     return out
 
 
+def bivariate_pdf(x: torch.Tensor, mu: torch.Tensor, cov: torch.Tensor, alpha: Optional[torch.Tensor] = None, log: bool = False):
+    """BivariateNormal / BivariateSkewNormal pdf or logpdf at points x (..., 2) (bivariatenormal.py:15-36,
+    bivariateskewnormal.py:20-49); one law (mu (2,), cov (2,2), alpha (2,)) or one per point.  Returns x.shape[:-1] fp32."""
+    x = nat.require_cuda(x, torch.float32, "x")
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    if alpha is not None:
+        alpha = nat.require_cuda(alpha, torch.float32, "alpha")
+    if x.shape[-1] != 2:
+        raise ValueError("last dim of x must be 2")
+    lead = tuple(x.shape[:-1])
+    n = int(np.prod(lead)) if lead else 1
+    nd = mu.numel() // 2
+    if cov.numel() != 4 * nd or (alpha is not None and alpha.numel() != 2 * nd) or nd not in (1, n):
+        raise ValueError("mu / cov / alpha must describe one law or one law per point")
+    out = torch.empty(lead, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = nat.lib().cub200_bivariate_pdf(nat.ptr(x), n, nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), nd, int(log), nat.ptr(out),
+                                            nat.stream_ptr(x.device))
+    nat.check(rc, "cub200_bivariate_pdf")
+    return out
+
+
+def skew_rvs_fast(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, n: int, z: Optional[torch.Tensor] = None, seed: int = 0):
+    """BivariateSkewNormal.rvs_fast (bivariateskewnormal.py:160-191): n draws (n,2) of one law; z (n,3) replays the normals."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    alpha = nat.require_cuda(alpha, torch.float32, "alpha")
+    if mu.numel() != 2 or cov.numel() != 4 or alpha.numel() != 2:
+        raise ValueError("mu (2,), cov (2,2), alpha (2,) expected")
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (n, 3):
+            raise ValueError(f"z must be ({n},3)")
+    out = torch.empty((int(n), 2), dtype=torch.float32, device=mu.device)
+    with torch.cuda.device(mu.device):
+        rc = nat.lib().cub200_skew_rvs_fast(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), nat.ptr(z), int(seed) & (2**64 - 1), int(n),
+                                            nat.ptr(out), nat.stream_ptr(mu.device))
+    nat.check(rc, "cub200_skew_rvs_fast")
+    return out
+
+
 def psm_conditionals(model: ShapeModelConstants, mu: torch.Tensor):
     """Per-image conditional maps of the shape model (compute_psm, psm_skew.py:469-491):
     mu (N,21,2) -> (mc_t (N,34,36) fp64, covc (N,14,3) fp64), see include/cub200.h."""

@@ -211,6 +211,25 @@ int cub200_skew_pdf_grid(const float* mu, const float* cov, const float* alpha, 
                          float* pdf_out, void* stream);
 
 /*
+ * Bivariate normal / skew-normal pdf or logpdf at arbitrary points.
+ *   replaces  BivariateNormal.logpdf / pdf            cu/distributions/bivariatenormal.py:15-36
+ *             BivariateSkewNormal.logpdf / pdf        cu/distributions/bivariateskewnormal.py:20-49
+ *   x (n_points,2) fp32; mu (n_dist,2), cov (n_dist,2,2), alpha (n_dist,2) fp32, alpha NULL = plain normal;
+ *   n_dist = 1 (one law for all points) or n_points (paired); out (n_points) fp32.
+ */
+int cub200_bivariate_pdf(const float* x, int64_t n_points, const float* mu, const float* cov, const float* alpha,
+                         int64_t n_dist, int want_log, float* out, void* stream);
+
+/*
+ * n draws of one bivariate skew-normal law.
+ *   replaces  BivariateSkewNormal.rvs_fast            cu/distributions/bivariateskewnormal.py:160-191
+ *   mu (2), cov (2,2), alpha (2) fp32; z optional (n,3) fp32 standard normals to replay (MultivariateNormal.sample of the
+ *   3x3 augmented law), else Philox with `seed`; out (n,2) fp32.
+ */
+int cub200_skew_rvs_fast(const float* mu, const float* cov, const float* alpha, const float* z, uint64_t seed, int64_t n,
+                         float* out, void* stream);
+
+/*
  * Conditional maps of the posterior shape model per image (the part of compute_psm that does not depend
  * on the sampled values): mu_c = mu + Mc (s - mu) over the already-sampled coordinates, and the 2x2
  * conditional covariances of the 14 level points.

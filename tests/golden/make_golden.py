@@ -490,6 +490,34 @@ def golden_gls():
     print("gls.npz perimeter", p_ed[:4], "gls", gls[:4])
 
 
+def golden_distributions():
+    """BivariateNormal / BivariateSkewNormal classmethods (cu/distributions/*.py) on random points; rvs_fast replayed."""
+    from contour_uncertainty.distributions.bivariatenormal import BivariateNormal
+    from contour_uncertainty.distributions.bivariateskewnormal import BivariateSkewNormal
+
+    rng = np.random.default_rng(131)
+    mus, covs = synth.point_distributions(1, seed=132)
+    mu, cov = torch.from_numpy(mus[0, 3]), torch.from_numpy(covs[0, 3])
+    alpha = torch.tensor([1.7, -2.3])
+    x = torch.from_numpy((mus[0, 3] + rng.normal(0, 6.0, (200, 2))).astype(np.float32))
+    out = dict(mu=mu.numpy(), cov=cov.numpy(), alpha=alpha.numpy(), x=x.numpy(),
+               n_logpdf=BivariateNormal.logpdf(x, mu, cov).numpy(), n_pdf=BivariateNormal.pdf(x, mu, cov).numpy(),
+               s_logpdf=BivariateSkewNormal.logpdf(x, mu, cov, alpha).numpy(), s_pdf=BivariateSkewNormal.pdf(x, mu, cov, alpha).numpy())
+    # paired laws (one per point)
+    mu_n = torch.from_numpy(mus[0, :20]); cov_n = torch.from_numpy(covs[0, :20]); al_n = torch.from_numpy(synth.skew_alphas(1, 133)[0, :20])
+    x_n = mu_n + torch.from_numpy(rng.normal(0, 4.0, (20, 2)).astype(np.float32))
+    out.update(mu_n=mu_n.numpy(), cov_n=cov_n.numpy(), alpha_n=al_n.numpy(), x_n=x_n.numpy(),
+               s_logpdf_n=BivariateSkewNormal.logpdf(x_n, mu_n, cov_n, al_n).numpy())
+    z = rng.standard_normal((16, 3)).astype(np.float32)
+    with _refstub.replay_standard_normal([z]) as log:
+        r = BivariateSkewNormal.rvs_fast(mu, cov, alpha, size=(16,))
+    assert log == [(16, 3)], log
+    m0, v0, a0 = BivariateSkewNormal.marginal(mu, cov, alpha.numpy(), axis=0, angle=torch.tensor(0.4))
+    out.update(z=z, rvs=r.numpy(), marginal=np.array([float(m0), float(v0), float(a0)]))
+    np.savez_compressed(os.path.join(HERE, "distributions.npz"), **out)
+    print("distributions.npz", {k: v.shape for k, v in out.items()})
+
+
 def golden_naive():
     """NaiveSampler.__call__ under np.random.seed; the draws are re-derived from the same seed."""
     from contour_uncertainty.sampler.naive import NaiveSampler
@@ -528,6 +556,6 @@ def golden_maps():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions"]
     for w in which:
         globals()["golden_" + w]()

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in cub200.h but not exported"
     assert set(names) == set(_native.SIGNATURES) | set(_native.QUERIES)
-    assert _native.lib().cub200_abi_version() == 11
+    assert _native.lib().cub200_abi_version() == 12
     assert _native.lib().cub200_built_for_sm() == 100
 
 

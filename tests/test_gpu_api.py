@@ -290,3 +290,81 @@ def test_new_paths_refuse_bad_inputs_and_handle_empty_batches():
         E.simpson_diameters(torch.zeros((4, 100), dtype=torch.int32, device=dev), 0.5)
     with pytest.raises(ValueError):
         E.simpson_diameters(torch.zeros((4, 2048), dtype=torch.int32, device=dev), -1.0)
+
+
+def test_distribution_mirrors_vs_reference():
+    """contour_uncertainty.distributions classmethods: logpdf / pdf (kernel, fp64 inside) against the reference's fp32
+    torch evaluation; rvs_fast with replayed normals; marginal."""
+    from contouring_uncertainty_b200.distributions import BivariateNormal, BivariateSkewNormal
+
+    g = np.load(os.path.join(G, "distributions.npz"))
+    t = torch.from_numpy
+    x, mu, cov, al = t(g["x"]), t(g["mu"]), t(g["cov"]), t(g["alpha"])
+    # the reference evaluates the exponent in fp32: |d logpdf| ~ 1e-5 at |logpdf| ~ 50
+    assert np.abs(BivariateNormal.logpdf(x, mu, cov).numpy() - g["n_logpdf"]).max() < 2e-5
+    # skew factor: the reference forms 0.5 (1 + erf) in fp32, which cancels catastrophically once Phi < ~1e-4 (its values
+    # are then quantised to 3e-8 under the + 1e-7 floor): compare logpdf where Phi is resolved, pdf (absolute) everywhere
+    sl = BivariateSkewNormal.logpdf(x, mu, cov, al).numpy()
+    resolved = (g["s_logpdf"] - g["n_logpdf"] - np.log(2)) > -9
+    assert resolved.sum() > 100 and np.abs(sl - g["s_logpdf"])[resolved].max() < 2e-4
+    np.testing.assert_allclose(BivariateNormal.pdf(x, mu, cov).numpy(), g["n_pdf"], rtol=3e-5, atol=1e-12)
+    assert np.abs(BivariateSkewNormal.pdf(x, mu, cov, al).numpy() - g["s_pdf"]).max() < 2e-4 * g["s_pdf"].max()
+    got = BivariateSkewNormal.logpdf(t(g["x_n"]), t(g["mu_n"]), t(g["cov_n"]), t(g["alpha_n"])).numpy()
+    res_n = g["s_logpdf_n"] > -12
+    assert np.abs(got - g["s_logpdf_n"])[res_n].max() < 2e-4
+    # tighter: against the fp64 oracle
+    want = port.skew_logpdf(g["x"].astype(np.float64), g["mu"], g["cov"], g["alpha"].astype(np.float64))
+    assert np.abs(BivariateSkewNormal.logpdf(x, mu, cov, al).numpy() - want).max() < 5e-6
+    r = BivariateSkewNormal.rvs_fast(mu, cov, al, size=(16,), z=g["z"])
+    assert r.shape == (16, 2) and np.abs(r.numpy() - g["rvs"]).max() < 1e-4
+    m0, v0, a0 = BivariateSkewNormal.marginal(mu, cov, g["alpha"], axis=0, angle=torch.tensor(0.4))
+    np.testing.assert_allclose([float(m0), float(v0), float(a0)], g["marginal"], rtol=2e-6)
+    big = BivariateSkewNormal.rvs_fast(mu, cov, al, size=20000, seed=3).numpy()
+    # mean of a skew normal: mu + sqrt(2/pi) delta, delta = cov alpha / sqrt(1 + alpha^T cov alpha)
+    c, a = g["cov"].astype(np.float64), g["alpha"].astype(np.float64)
+    delta = c @ a / np.sqrt(1 + a @ c @ a)
+    assert np.abs(big.mean(0) - (g["mu"] + np.sqrt(2 / np.pi) * delta)).max() < 0.15
+
+
+def test_numpy_mirrors_of_utils_and_task_classes():
+    """utils.{umap, skew_umap, uncertainty_projection, contour, clinical} and the DSNT task classes: reference call
+    signatures, numpy in / numpy out."""
+    from contouring_uncertainty_b200.task.regression.contour_uncertainty import convert_to_mask
+    from contouring_uncertainty_b200.task.regression.dsnt.dsnt_al import DSNTAleatoric
+    from contouring_uncertainty_b200.task.regression.dsnt.dsnt_skew import DSNTSkew
+    from contouring_uncertainty_b200.utils import clinical, contour, skew_umap, umap, uncertainty_projection
+
+    g = np.load(os.path.join(G, "umap.npz"))
+    mu, cov, al = g["mu"][0], g["cov"][0], g["alpha"][0]
+    u, v = uncertainty_projection.projected_uncertainty(mu, cov, all=True)
+    assert np.abs(u - g["unc_all"][0]).max() < 1e-5 and np.abs(v - g["proj_all"][0]).max() < 1e-11
+    assert abs(uncertainty_projection.projected_uncertainty_value(mu, cov) - g["value"][0]) < 1e-3
+    um = umap.uncertainty_map(mu, cov)
+    assert (um != port.uncertainty_map(mu, cov)).sum() <= 8
+    mode, sk = skew_umap.skew_umap(mu, cov, al, linear_close=True)
+    assert np.abs(mode - g["mode"][0]).max() < 1e-4 and sk.shape == (256, 256)
+    r = np.load(os.path.join(G, "raster.npz"))
+    c = r["contours"][5].astype(np.float64)
+    assert np.array_equal(contour.reconstruction(c, 256, 256), port.reconstruction(c, 256, 256))
+    gl = np.load(os.path.join(G, "gls.npz"))
+    assert abs(clinical.perimeter(gl["ed"][0]) - gl["perimeter_ed"][0]) < 1e-7
+    assert abs(clinical.global_longitudinal_strain(gl["ed"][0], gl["es"][0]) - gl["gls"][0]) < 1e-8
+    s = np.load(os.path.join(G, "simpson.npz"))
+    masks = port.convert_to_mask(s["contours"][:, 0])
+    edv, esv = clinical.compute_left_ventricle_volumes(masks[0], masks[1], tuple(s["voxelspacing"]), masks[2], masks[3], tuple(s["voxelspacing"]))
+    assert (edv, esv) == (int(s["edv"][0]), int(s["esv"][0]))
+    with pytest.raises(ValueError):
+        clinical.compute_left_ventricle_volumes(np.zeros((256, 256)), masks[1], (0.5, 0.5), masks[2], masks[3], (0.5, 0.5))
+    pred, ps = convert_to_mask(s["contours"][:2, 0], (2, 1, 256, 256), s["contours"][:2, :3].reshape(2, 1, 3, 21, 2))
+    assert pred.shape == (2, 256, 256) and ps.shape == (2, 1, 3, 1, 256, 256) and np.array_equal(pred[0], masks[0])
+    # task classes around a fake "network"
+    logits = torch.from_numpy(synth.heatmap_logits(2, seed=71)).cuda()
+    task = DSNTAleatoric([lambda img: logits, lambda img: logits * 0.9])
+    S, cv = task.predict(None)
+    assert S.shape == (2, 2, 21, 2) and cv.shape == (2, 2, 21, 2, 2)
+    mu_o, _ = port.dsnt_predict_on_batch(logits.cpu().numpy())
+    assert np.abs(S[:, 0].cpu().numpy() - mu_o).max() < 1e-3
+    raw = torch.from_numpy(synth.skew_alphas(2, seed=72)).cuda()
+    sk_task = DSNTSkew(lambda img: (logits, raw), t_e=2)
+    S2, c2, a2 = sk_task.predict(None)
+    assert a2.shape == (2, 2, 21, 2) and torch.equal(a2[:, 0, :, 1], -raw[..., 1]) and torch.equal(a2[:, 0, :, 0], raw[..., 0])
