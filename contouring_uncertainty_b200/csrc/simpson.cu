@@ -241,12 +241,16 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
         for (int j = 4 * lane; j < i; j += 128) try_pair(i, ir, ic, j, wbest);
     }
     // full pass
+    int dmin_for = -1, dmin = 1;
     for (int i = 2; i < n; ++i) {
         const int ir = P[i] & 0xffff, ic = P[i] >> 16;
         // a chord shorter than the best one any lane holds can never be selected (equal ones still can: ties go to the
         // first (i, j) in loop order)
         const int wbest = __reduce_max_sync(FULL, best.len2);
-        const int dmin = max(1, (int)ceil(sqrt(0.5 * (double)wbest) - 1e-9));           // d_col needed for len^2 >= wbest
+        if (wbest != dmin_for) {                                                        // d_col needed for len^2 >= wbest
+            dmin = max(1, (int)ceil(sqrt(0.5 * (double)wbest) - 1e-9));
+            dmin_for = wbest;
+        }
         const int nblk = (i + 31) >> 5;
         for (int jb0 = 0; jb0 < nblk; jb0 += 32) {
             const int jb = jb0 + lane;
