@@ -234,8 +234,10 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
         }
         if (ok) best = cand;
     };
-    // coarse pass: i and j on every 4th point (validity is always checked on ALL intermediate points)
-    for (int i = 4; i < n; i += 4) {
+    // coarse pass: i and j on every 4th point (validity is always checked on ALL intermediate points), i DESCENDING: a
+    // straight stretch of the contour then meets its far end first, i.e. its longest chord, and the bound it sets prunes
+    // the O(L^2) shorter chords of the same stretch that an ascending scan would have validated one after the other
+    for (int i = (n - 1) & ~3; i >= 4; i -= 4) {
         const int ir = P[i] & 0xffff, ic = P[i] >> 16;
         const int wbest = __reduce_max_sync(FULL, best.len2);
         for (int j = 4 * lane; j < i; j += 128) try_pair(i, ir, ic, j, wbest);
@@ -296,7 +298,17 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     const double nrm = sqrt(__dadd_rn(__dmul_rn(dir_c, dir_c), __dmul_rn(dir_r, dir_r)));
     const double nr = -dir_c / nrm, nc = dir_r / nrm;    // normal_direction = (-direction[1], direction[0]) / |.|
     const double mid_r = 0.5 * (double)mr, mid_c = 0.5 * (double)mc;
-    const MaskView mv{masks + g * CUB200_MASK_WORDS, row_index ? s_idx : nullptr, row_index ? s_idx + vh : nullptr, vh, vw};
+    // the contour points are no longer needed: their shared-memory buffer now holds the mask, so that the ~50 dependent
+    // steps of every ray read shared memory instead of global memory
+    static_assert(SP_NMAX >= CUB200_MASK_WORDS, "the point buffer must be able to hold a mask");
+    __syncwarp();
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(masks + g * CUB200_MASK_WORDS);
+        uint4* dst = reinterpret_cast<uint4*>(P);
+        for (int k = lane; k < CUB200_MASK_WORDS / 4; k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+    const MaskView mv{P, row_index ? s_idx : nullptr, row_index ? s_idx + vh : nullptr, vh, vw};
     // 20 discs x 2 directions (heart_us.py:158-164)
     double d_pos = 0.0, d_neg = 0.0, d_neg2 = 0.0;
     for (int ray = lane; ray < 40; ray += 32) {
