@@ -67,8 +67,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
-    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    // (k + 1/2) 2^-23 with a 23-bit k is an exact fp32 number in [2^-24, 1 - 2^-24]; a 24-bit k + 1/2 would round up to 1
+    const float u1 = ((float)(a >> 9) + 0.5f) * (1.0f / 8388608.0f);
+    const float u2 = ((float)(b >> 9) + 0.5f) * (1.0f / 8388608.0f);
     const float r = sqrtf(-2.0f * logf(u1));
     float s, c;
     sincospif(2.0f * u2, &s, &c);
