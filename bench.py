@@ -41,13 +41,13 @@ BYTES_FINAL_PER_IMG = HW * HW * (4 + 4 + 8 + 8 + 1)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01a_ncu_full_summary.csv for dsnt / finalize, profiles/r01d_ncu_full_summary_fused.csv)
-NCU_TRAFFIC = {"dsnt": 352339968 + 4504832, "fused": 5135104 + 450560, "finalize": 19132160 + 35917056, "psm_factor": 113664}
+# (profiles/r01k_ncu_full_summary_dsnt_psm_finalize.csv, profiles/r01i_ncu_full_summary_fused.csv)
+NCU_TRAFFIC = {"dsnt": 352339200 + 3981824, "fused": 5050112 + 688128, "finalize": 17550848 + 35057920, "psm_factor": 88576}
 ROOF_NOTES = {
     "fused": "NOT HBM-bound by construction (masks never leave shared memory): binding resources are issue slots / ALU "
-             "pipe -- ncu: IPC 2.2 of 4 (56 % of issue slots), ALU pipe 39 %, 4875 warp-instructions per sample, shared memory "
-             "43.05 M wavefronts per launch = 86 KB / sample = 28 % of the 148 SM x 1 wavefront/clk peak "
-             "(DESIGN.md section 3, profiles/r01d_*)",
+             "pipe -- ncu: IPC 2.2 of 4 (56 % of issue slots), ALU pipe 40 %, 4912 warp-instructions per sample, shared memory "
+             "43.07 M wavefronts per launch = 86 KB / sample = 28 % of the 148 SM x 1 wavefront/clk peak "
+             "(DESIGN.md section 3, profiles/r01i_*, r01d_*)",
     "dsnt": "HBM-bound: every logit read once; DRAM traffic == algorithmic bytes",
 }
 
