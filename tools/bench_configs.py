@@ -13,25 +13,52 @@ import numpy as np, torch, synth
 import bench as B
 from contouring_uncertainty_b200 import engine as E
 
-dev = torch.device("cuda:0")
+import torch.distributed as dist
+
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(LOCAL)
+dev = torch.device("cuda", LOCAL)
+if WORLD > 1:      # one process per GPU (torchrun); every rank runs its own shard of images / patients / pairs (weak scaling)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
 
 def timed(fn, steps, warmup=2):
+    """ms per step: barrier + synchronize on both sides, CUDA events, max over ranks."""
     for i in range(warmup):
         fn(i)
+    if WORLD > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         fn(warmup + i)
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    e1.record()
+    if WORLD > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if WORLD > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def exchange(local: torch.Tensor):
+    """The path's only collective: all_gather of the per-sample metric distributions (end of a step)."""
+    if WORLD == 1:
+        return local
+    out = torch.empty((WORLD * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out
 
 
 def line(cfg, workload, units, unit, ms, steps, **extra):
-    print(json.dumps({"config_id": cfg, "metric": "mc_contour_samples_per_s", "value": units / (ms * 1e-3), "unit": unit,
-                      "n_gpus": 1, "steps": steps, "warmup": 2, "ms_per_step": ms, "data": "synthetic",
-                      "config": {"workload": workload}, **extra}), flush=True)
+    if RANK != 0:
+        return
+    print(json.dumps({"config_id": cfg, "metric": "mc_contour_samples_per_s", "value": WORLD * units / (ms * 1e-3), "unit": unit,
+                      "n_gpus": WORLD, "steps": steps, "warmup": 2, "ms_per_step": ms, "scaling": "weak", "data": "synthetic",
+                      "config": {"workload": workload + (f" (x {WORLD} GPUs, image-sharded)" if WORLD > 1 else "")}, **extra}), flush=True)
 
 
 def config1(steps, scale):
@@ -47,7 +74,7 @@ def config3(steps, scale):
     """dsnt-skew: 512 images x 1000 skew-PSM samples per GPU."""
     n, T = max(8, int(512 * scale)), 1000
     model = E.ShapeModelConstants(device=dev)
-    logits = B.make_logits_on_device(torch, dev, n, seed=1003)
+    logits = B.make_logits_on_device(torch, dev, n, seed=1003 + RANK)
     alpha = torch.from_numpy(synth.skew_alphas(n, seed=1103)).to(dev)
     diff = torch.zeros((n, 256, 256), dtype=torch.int32, device=dev)
     parts = {}
@@ -62,10 +89,11 @@ def config3(steps, scale):
         s = E.skew_sample(model, mu, cov, alpha, T, seed=i, pdfs=tabs)
         ev[3].record()
         diff.zero_()
-        E.rasterize_contours(s.reshape(-1, 21, 2), return_masks=False, diff=diff, per_image=T)
+        _, area = E.rasterize_contours(s.reshape(-1, 21, 2), return_masks=False, diff=diff, per_image=T)
         ev[4].record()
         E.finalize_maps(diff, T, want_count=False)
         ev[5].record()
+        exchange(area.reshape(n, T))
         parts["ev"] = ev
 
     ms = timed(step, steps)
@@ -99,6 +127,7 @@ def config4(steps, scale):
         ev[3].record()
         out["v"] = E.simpson_volumes(diam, stp)
         ev[4].record()
+        exchange(torch.stack(out["v"], -1))
         parts["ev"] = ev
 
     ms = timed(step, steps)
@@ -114,7 +143,7 @@ def config5(steps, scale):
     """camus-cont_sequence: (ED, ES) pairs x 1000 sequence-PSM samples, streaming aggregation."""
     npair, T = max(4, int(256 * scale)), 1000
     model, seq = E.ShapeModelConstants(device=dev), E.SequenceModelConstants(device=dev)
-    logits = B.make_logits_on_device(torch, dev, 2 * npair, seed=1005)
+    logits = B.make_logits_on_device(torch, dev, 2 * npair, seed=1005 + RANK)
     diff = torch.zeros((2 * npair, 256, 256), dtype=torch.int32, device=dev)
 
     def step(i):
@@ -124,7 +153,8 @@ def config5(steps, scale):
         diff.zero_()
         _, area = E.rasterize_contours(c, return_masks=False, diff=diff, per_image=T)
         E.finalize_maps(diff, T, want_count=False)
-        E.fac_from_areas(area.reshape(npair, 2, T)[:, 0].contiguous(), area.reshape(npair, 2, T)[:, 1].contiguous())
+        fac = E.fac_from_areas(area.reshape(npair, 2, T)[:, 0].contiguous(), area.reshape(npair, 2, T)[:, 1].contiguous())
+        exchange(fac)
 
     ms = timed(step, steps)
     line(5, f"camus-cont_sequence: {npair} (ED, ES) pairs x {T} sequence-PSM samples per GPU -> maps + FAC", 2 * npair * T,
@@ -140,3 +170,5 @@ if __name__ == "__main__":
     for c in a.configs.split(","):
         globals()["config" + c.strip()](a.steps, a.scale)
         torch.cuda.empty_cache()
+    if WORLD > 1:
+        dist.destroy_process_group()
