@@ -141,8 +141,9 @@ def cpu_arm(n_images, n_samples, workers):
     with ctx.Pool(workers, initializer=_cpu_init) as pool:
         pool.map(_cpu_worker, [(900 + i, 2) for i in range(workers)])   # warm the workers (imports, model)
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(1000 + i, n_samples) for i in range(n_images)], chunksize=1)
+        res = pool.map(_cpu_worker, [(1000 + i, n_samples) for i in range(n_images)], chunksize=1)
         wall = time.perf_counter() - t0
+    cpu_arm.single_core = n_samples / float(np.mean([r[0] for r in res]))     # samples/s of ONE process on one core
     return n_images * n_samples / wall, wall
 
 
@@ -166,7 +167,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 spline / u8 masks (numpy, scipy)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "single_core_value": cpu_arm.single_core},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -353,7 +355,7 @@ def run_ours(args):
         workers = max(1, min(cores, 64))
         n_images, n_samples = 2 * workers, 250
         v, wall = cpu_arm(n_images, n_samples, workers)
-        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port", "single_core_value": cpu_arm.single_core,
                "sample": f"{n_images} images x {n_samples} PSM samples (of 64 x 1000), {workers} processes x 1 thread, {wall:.1f} s"}
 
     line = {

@@ -368,3 +368,28 @@ def test_numpy_mirrors_of_utils_and_task_classes():
     sk_task = DSNTSkew(lambda img: (logits, raw), t_e=2)
     S2, c2, a2 = sk_task.predict(None)
     assert a2.shape == (2, 2, 21, 2) and torch.equal(a2[:, 0, :, 1], -raw[..., 1]) and torch.equal(a2[:, 0, :, 0], raw[..., 0])
+
+
+def test_skew_pipeline_with_epistemic_passes():
+    """dsnt-skew with T_e = 2 passes (ensemble): samples of both passes aggregate into one map per image."""
+    from contouring_uncertainty_b200.task import SkewUncertaintyPipeline
+
+    n, T = 2, 5
+    pipe = SkewUncertaintyPipeline(t_a=T)
+    l1 = torch.from_numpy(synth.heatmap_logits(n, seed=81)).cuda()
+    l2 = torch.from_numpy(synth.heatmap_logits(n, seed=82)).cuda()
+    a1 = torch.from_numpy(synth.skew_alphas(n, seed=83)).cuda()
+    a2 = torch.from_numpy(synth.skew_alphas(n, seed=84)).cuda()
+    br = pipe.predict_step([l1, l2], [a1, a2], seed=2, return_pred_samples=True)
+    assert br.contour_samples.shape == (n, 2, T, 21, 2) and br.pred_samples.shape == (n, 2, T, 256, 256)
+    assert br.sample_area.shape == (n, 2, T) and np.array_equal(br.sample_area, br.pred_samples.sum((-2, -1)))
+    for i in range(n):
+        masks = port.convert_to_mask(br.contour_samples[i].reshape(-1, 21, 2))
+        assert np.array_equal(masks.reshape(2, T, 256, 256), br.pred_samples[i])
+        o = port.maps_from_counts(masks.sum(0, dtype=np.int64), 2 * T)
+        assert np.abs(o[1] - br.entropy_map[i]).max() <= 1e-12
+    # epistemic + aleatoric covariance split (aleatoric_skew.py:65-73)
+    mu, cov, al = pipe.predict([l1, l2], [a1, a2])
+    want_mu, want_cov = port.aleatoric_epistemic_moments(mu.cpu().numpy(), cov.cpu().numpy())
+    assert np.allclose(br.mu, want_mu, atol=1e-4) and np.allclose(br.cov, want_cov, rtol=1e-4, atol=1e-4)
+    assert np.allclose(br.alpha, al.mean(1).cpu().numpy())
