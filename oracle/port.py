@@ -10,8 +10,13 @@ executed in the build container by ``tests/golden/make_golden.py`` and committed
 ``tests/golden/*.npz`` (checked by ``tests/test_oracle_golden.py``).  Third-party arithmetic the
 reference calls and that is present in this image is called the same way here
 (``scipy.interpolate.splprep/splev``, ``scipy.ndimage.binary_fill_holes``, ``scipy.stats.entropy``);
-``skimage.draw.line`` is absent from the image and restated (``bresenham_line``) -- "parity
-unpinned" for that one function (it draws the <= ~80 px base line between landmarks 20 and 0).
+``skimage.draw.line`` and ``skimage.measure.find_contours`` are absent from the image and restated
+from memory of scikit-image's sources (``bresenham_line``, ``find_contours``) -- "PARITY UNPINNED" for
+these two third-party functions: the first draws the <= ~80 px base line between landmarks 20 and 0,
+the second decides the point order of the contour that Simpson's base-chord search walks.  Everything
+else is pinned: the goldens were made by executing the reference's own code (with these two
+restatements standing in for scikit-image) and its third-party calls that exist here (scipy FITPACK
+splines, ``binary_fill_holes``, ``scipy.stats``, torch, numpy, PIL) run unmodified.
 
 Every function cites the reference file:line it follows (paths relative to the reference root;
 ``cu/`` = ``contour_uncertainty/``).
