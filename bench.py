@@ -324,6 +324,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N_IMG * T_A / (float(te.item()) / n_e2e * 1e-3)
+    e2e_h2d_gbs = h2d / (float(te.item()) / n_e2e * 1e-3) / 1e9      # per rank; a lone pinned H2D copy reaches ~55 GB/s here
     e2e_check = bool(torch.equal(h_out["area"][-8:], pipe.ws[(N_IMG // 8 - 1) % 2].area.cpu()))
 
     if rank != 0:
@@ -369,7 +370,8 @@ def run_ours(args):
         "roofline": roof(dominant),
         "roofline_dsnt": roof("dsnt"),
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "numa_bound": numa_bound},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "numa_bound": numa_bound,
+                "h2d_gb_per_s_per_gpu": e2e_h2d_gbs, "bound": "PCIe host-to-device copy of the fp32 logits"},
         "gpu_launches": (5 + (1 if world > 1 else 0)) * args.steps,   # dsnt, psm_factor, fused, entropy_lut, finalize (+ metric_sums) per step
         "clocks": clk,
         "parity_spot_check": parity_ok and e2e_check,
