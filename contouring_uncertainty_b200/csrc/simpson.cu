@@ -179,6 +179,7 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
                          int vw, double spacing, double* __restrict__ diam_out, double* __restrict__ step_out) {
     __shared__ uint32_t s_pts[SP_WARPS][SP_NMAX];
     __shared__ uint32_t s_bmax[SP_WARPS][SP_NMAX / 32];
+    __shared__ uint32_t s_brow[SP_WARPS][SP_NMAX / 32];
     extern __shared__ uint16_t s_idx[];
     if (row_index) {
         for (int i = threadIdx.x; i < vh; i += blockDim.x) s_idx[i] = row_index[i];
@@ -204,10 +205,16 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     //      pass over every 4th point first finds a long valid chord, and the full pass then skips, 32 candidates at a
     //      time, the blocks of j whose columns cannot give a chord that long (|d_row| <= d_col  =>  len^2 <= 2 d_col^2).
     uint32_t* bmax = s_bmax[wid];                        // max column (half-pixel units) of each block of 32 points
+    uint32_t* brow = s_brow[wid];                        // its row range: min | max << 16
     for (int jb = lane; jb < (n + 31) / 32; jb += 32) {
-        int m = 0;
-        for (int k = 32 * jb; k < min(32 * jb + 32, n); ++k) m = max(m, (int)(P[k] >> 16));
+        int m = 0, r0 = 0xffff, r1 = 0;
+        for (int k = 32 * jb; k < min(32 * jb + 32, n); ++k) {
+            m = max(m, (int)(P[k] >> 16));
+            r0 = min(r0, (int)(P[k] & 0xffff));
+            r1 = max(r1, (int)(P[k] & 0xffff));
+        }
         bmax[jb] = (uint32_t)m;
+        brow[jb] = (uint32_t)r0 | ((uint32_t)r1 << 16);
     }
     __syncwarp();
     Chord best{0, 0x7fffffff, 0x7fffffff};
@@ -255,8 +262,13 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
         }
         const int nblk = (i + 31) >> 5;
         for (int jb0 = 0; jb0 < nblk; jb0 += 32) {
-            const int jb = jb0 + lane;
-            unsigned live = __ballot_sync(FULL, jb < nblk && (int)bmax[jb < nblk ? jb : 0] - ic >= dmin);
+            const int jb = jb0 + lane, jc = jb < nblk ? jb : 0;
+            // a block can hold a candidate only if its columns reach d_col >= dmin AND some row is within that d_col of
+            // row i (|d_row| <= d_col)
+            const int dcmax = (int)bmax[jc] - ic;
+            const int rlo = (int)(brow[jc] & 0xffff), rhi = (int)(brow[jc] >> 16);
+            const int rdist = max(0, max(rlo - ir, ir - rhi));
+            unsigned live = __ballot_sync(FULL, jb < nblk && dcmax >= dmin && rdist <= dcmax);
             while (live) {
                 const int b = __ffs(live) - 1;
                 live &= live - 1;
