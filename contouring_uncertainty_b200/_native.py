@@ -50,8 +50,11 @@ SIGNATURES = {
     "cub200_contour_perimeter": [_vp, _i64, _vp, _vp],
     "cub200_bivariate_pdf": [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
     "cub200_skew_rvs_fast": [_vp, _vp, _vp, _vp, _u64, _i64, _vp, _vp],
+    "cub200_seg_largest_blob": [_vp, _i64, _vp, _vp, _vp, _vp],
+    "cub200_seg_entropy": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
 }
-QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes")
+QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes",
+           "cub200_seg_blob_workspace_bytes")
 
 
 class NativeError(RuntimeError):
@@ -77,6 +80,8 @@ def lib() -> C.CDLL:
         l.cub200_simpson_workspace_bytes.argtypes = [_i64]
         l.cub200_calibration_workspace_bytes.restype = C.c_int64
         l.cub200_calibration_workspace_bytes.argtypes = []
+        l.cub200_seg_blob_workspace_bytes.restype = C.c_int64
+        l.cub200_seg_blob_workspace_bytes.argtypes = [_i64]
         l.cub200_abi_version.restype = C.c_int
         l.cub200_built_for_sm.restype = C.c_int
         _lib = l

@@ -1,0 +1,81 @@
+// Bit-packed 256x256 bitmaps owned by one warp (lane = a band of 8 rows) and the 4-connected flood over them.
+// Shared by the contour rasteriser (fused.cu: binary_fill_holes of a drawn contour) and the segmentation
+// post-processing (segpost.cu: binary_fill_holes of a rounded probability map).
+#pragma once
+#include "common.cuh"
+
+namespace cub200 {
+
+constexpr int BAND_STRIDE = 68;                 // 8 rows x 8 words + 4 pad words: 128-bit band loads are conflict free
+constexpr int BMP_WORDS = 32 * BAND_STRIDE;     // 2176
+
+__device__ __forceinline__ int bmp_addr(int row, int word) { return row * 8 + word + (row >> 3) * 4; }
+
+// Fill complete runs of F that contain a seed (seeds subset of F).  256-bit rows as 8 words,
+// bit b of word w = column 32w + b.  Add-with-carry trick, once upward and once on the
+// bit-reversed row (rare path: only rows where the flood actually advances vertically).
+static __device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8]) {
+    uint32_t X[8];
+    // upward: X = F + r
+    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(F[0]), "r"(r[0]));
+#pragma unroll
+    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(F[w]), "r"(r[w]));
+    uint32_t up[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) up[w] = (F[w] & ~X[w]) | r[w];
+    // downward: same on reversed bits (word w <-> 7-w, brev)
+    uint32_t Fr[8], rr[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { Fr[w] = __brev(F[7 - w]); rr[w] = __brev(r[7 - w]); }
+    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(Fr[0]), "r"(rr[0]));
+#pragma unroll
+    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(Fr[w]), "r"(rr[w]));
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t dn = Fr[7 - w] & ~X[7 - w];
+        r[w] = up[w] | __brev(dn);
+    }
+}
+
+// One Gauss-Seidel sweep of the vertical flood over the lane's 8-row band (UP = 0: rows 0->7,
+// UP = 1: rows 7->0).  A row advances where a free, unreached pixel has a reached vertical
+// neighbour; the whole run containing it is then filled.  Returns the bitmask of rows advanced.
+template <int UP>
+__device__ __forceinline__ uint32_t flood_sweep(uint32_t (&R)[8][8], const uint4* band4, int lane) {
+    uint32_t changed = 0u;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+        const int i = UP ? 7 - ii : ii;
+        uint32_t nb[8];                                      // the row across the band edge
+        if (i == 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { nb[w] = __shfl_up_sync(FULL, R[7][w], 1); if (lane == 0) nb[w] = 0u; }
+        }
+        if (i == 7) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { nb[w] = __shfl_down_sync(FULL, R[0][w], 1); if (lane == 31) nb[w] = 0u; }
+        }
+        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
+        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t cand[8], any = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t above = (i == 0) ? nb[w] : R[i > 0 ? i - 1 : 0][w];
+            const uint32_t below = (i == 7) ? nb[w] : R[i < 7 ? i + 1 : 7][w];
+            cand[w] = ~(B[w] | R[i][w]) & (above | below);
+            any |= cand[w];
+        }
+        if (any) {
+            uint32_t F[8], r[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { F[w] = ~B[w]; r[w] = R[i][w] | cand[w]; }
+            run_fill(F, r);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) R[i][w] = r[w];
+            changed |= 1u << i;
+        }
+    }
+    return changed;
+}
+
+}  // namespace cub200

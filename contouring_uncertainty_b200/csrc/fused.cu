@@ -27,6 +27,7 @@
 // Shared memory per warp: the 256x256 boundary bitmap (8 rows per lane, padded band stride 68
 // words so the 128-bit band loads are bank-conflict free) + ~2 KB of spline scratch.
 #include "common.cuh"
+#include "flood.cuh"
 #include "spline.cuh"
 
 namespace cub200 {
@@ -40,8 +41,6 @@ namespace cub200 {
 constexpr int FW_WARPS = CUB200_FW_WARPS;
 constexpr int FW_MINBLOCKS = CUB200_FW_MINBLOCKS;
 constexpr int FW_THREADS = FW_WARPS * 32;
-constexpr int BAND_STRIDE = 68;                 // 8 rows x 8 words + 4 pad words
-constexpr int BMP_WORDS = 32 * BAND_STRIDE;     // 2176
 constexpr int NPTS = 1000;                      // contour_spline(points, n=1000)   contour.py:30
 constexpr int KP = CUB200_K;                    // 21
 constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px behave as +-8192
@@ -53,36 +52,8 @@ struct __align__(16) WarpScratch {
 };
 
 // ---------------------------------------------------------------- bitmap helpers
-__device__ __forceinline__ int bmp_addr(int row, int word) { return row * 8 + word + (row >> 3) * 4; }
-
 __device__ __forceinline__ void set_pixel(uint32_t* bmp, int row, int col) {
     atomicOr(&bmp[bmp_addr(row, col >> 5)], 1u << (col & 31));
-}
-
-// Fill complete runs of F that contain a seed (seeds subset of F).  256-bit rows as 8 words,
-// bit b of word w = column 32w + b.  Add-with-carry trick, once upward and once on the
-// bit-reversed row (rare path: only rows where the flood actually advances vertically).
-__device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8]) {
-    uint32_t X[8];
-    // upward: X = F + r
-    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(F[0]), "r"(r[0]));
-#pragma unroll
-    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(F[w]), "r"(r[w]));
-    uint32_t up[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) up[w] = (F[w] & ~X[w]) | r[w];
-    // downward: same on reversed bits (word w <-> 7-w, brev)
-    uint32_t Fr[8], rr[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { Fr[w] = __brev(F[7 - w]); rr[w] = __brev(r[7 - w]); }
-    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(Fr[0]), "r"(rr[0]));
-#pragma unroll
-    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(Fr[w]), "r"(rr[w]));
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const uint32_t dn = Fr[7 - w] & ~X[7 - w];
-        r[w] = up[w] | __brev(dn);
-    }
 }
 
 // Generic run extraction of one mask row (mask = ~R): every transition of R along the row (virtual
@@ -125,48 +96,6 @@ __device__ __noinline__ int undo_row_span(const uint32_t* brow, int32_t* drow) {
         if (xe < 256) atomicAdd(drow + xe, 1);
     }
     return xe - xs;
-}
-
-// One Gauss-Seidel sweep of the vertical flood over the lane's 8-row band (UP = 0: rows 0->7,
-// UP = 1: rows 7->0).  A row advances where a free, unreached pixel has a reached vertical
-// neighbour; the whole run containing it is then filled.  Returns the bitmask of rows advanced.
-template <int UP>
-__device__ __forceinline__ uint32_t flood_sweep(uint32_t (&R)[8][8], const uint4* band4, int lane) {
-    uint32_t changed = 0u;
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {
-        constexpr int dummy = 0; (void)dummy;
-        const int i = UP ? 7 - ii : ii;
-        uint32_t nb[8];                                      // the row across the band edge
-        if (i == 0) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { nb[w] = __shfl_up_sync(FULL, R[7][w], 1); if (lane == 0) nb[w] = 0u; }
-        }
-        if (i == 7) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { nb[w] = __shfl_down_sync(FULL, R[0][w], 1); if (lane == 31) nb[w] = 0u; }
-        }
-        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
-        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t cand[8], any = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t above = (i == 0) ? nb[w] : R[i > 0 ? i - 1 : 0][w];
-            const uint32_t below = (i == 7) ? nb[w] : R[i < 7 ? i + 1 : 7][w];
-            cand[w] = ~(B[w] | R[i][w]) & (above | below);
-            any |= cand[w];
-        }
-        if (any) {
-            uint32_t F[8], r[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { F[w] = ~B[w]; r[w] = R[i][w] | cand[w]; }
-            run_fill(F, r);
-#pragma unroll
-            for (int w = 0; w < 8; ++w) R[i][w] = r[w];
-            changed |= 1u << i;
-        }
-    }
-    return changed;
 }
 
 // ---------------------------------------------------------------- one sample, one warp

@@ -749,6 +749,56 @@ def ece_from_bins(bins) -> tuple:
 
 
 # --------------------------------------------------------------------------------------------------
+# Segmentation-sample post-processing
+# --------------------------------------------------------------------------------------------------
+def seg_largest_blob(probs: torch.Tensor, return_area: bool = False):
+    """Hole-filled largest blob of every rounded sample (segmentation_uncertainty.py:104-113, utils.py:12-32):
+    probs (..., 256, 256) fp32 -> bit-packed masks (..., 2048) int32 [, areas (...) int32]."""
+    probs = nat.require_cuda(probs, torch.float32, "probs")
+    if probs.ndim < 2 or tuple(probs.shape[-2:]) != (256, 256):
+        raise ValueError("probs must be (..., 256, 256)")
+    lead = tuple(probs.shape[:-2])
+    n = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    dev = probs.device
+    masks = torch.empty(lead + (MASK_WORDS,), dtype=torch.int32, device=dev)
+    area = torch.empty(lead, dtype=torch.int32, device=dev) if return_area else None
+    ws = torch.empty((int(nat.lib().cub200_seg_blob_workspace_bytes(n)),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_seg_largest_blob(nat.ptr(probs), n, nat.ptr(masks), nat.ptr(area), nat.ptr(ws), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_seg_largest_blob")
+    return (masks, area) if return_area else masks
+
+
+def seg_entropy(probs: torch.Tensor, masks: torch.Tensor, pad: int = 10, return_mean: bool = False,
+                return_pred_samples: bool = False, return_samples: bool = False) -> dict:
+    """Entropy map of the post-processed samples (segmentation_uncertainty.py:115-126, uncertainty.py:107-133):
+    probs (N, T, 256, 256) fp32 + masks (N, T, 2048) -> dict(entropy (N,256,256) fp32 [, mean, pred_samples, samples])."""
+    probs = nat.require_cuda(probs, torch.float32, "probs")
+    masks = nat.require_cuda(masks, torch.int32, "masks")
+    if probs.ndim != 4 or tuple(probs.shape[-2:]) != (256, 256):
+        raise ValueError("probs must be (N, T, 256, 256)")
+    n, T = int(probs.shape[0]), int(probs.shape[1])
+    if tuple(masks.shape) != (n, T, MASK_WORDS):
+        raise ValueError(f"masks must be ({n}, {T}, {MASK_WORDS})")
+    if T == 0:
+        raise ValueError("no samples")
+    dev = probs.device
+    out = {"entropy": torch.empty((n, 256, 256), dtype=torch.float32, device=dev)}
+    if return_mean:
+        out["mean"] = torch.empty((n, 256, 256), dtype=torch.float32, device=dev)
+    if return_pred_samples:
+        out["pred_samples"] = torch.empty((n, T, MASK_WORDS), dtype=torch.int32, device=dev)
+    if return_samples:
+        out["samples"] = torch.empty((n, T, 256, 256), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_seg_entropy(nat.ptr(probs), nat.ptr(masks), n, T, int(pad), nat.ptr(out["entropy"]),
+                                          nat.ptr(out.get("mean")), nat.ptr(out.get("pred_samples")), nat.ptr(out.get("samples")),
+                                          nat.stream_ptr(dev))
+    nat.check(rc, "cub200_seg_entropy")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # End-to-end engine
 # --------------------------------------------------------------------------------------------------
 @dataclass

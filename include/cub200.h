@@ -392,6 +392,28 @@ int64_t cub200_calibration_workspace_bytes(void);
 int cub200_calibration_bins(const double* umap, const uint8_t* pred, const uint8_t* gt, int64_t n_pixels, const double* bounds,
                             int nb_bins, double* bins_out, void* workspace, void* stream);
 
+/*
+ * Segmentation-sample post-processing: fill holes, keep the largest blob, entropy of the masked mean.
+ * Replaces the per-sample loop of SegmentationUncertaintyTask.predict_step
+ *             cu/task/segmentation/segmentation_uncertainty.py:98-140  (ndimage.binary_fill_holes + big_blob,
+ *             cu/task/segmentation/utils.py:12-32) and UncertaintyTask.sample_entropy (C == 1) cu/task/uncertainty.py:107-133.
+ *
+ * cub200_seg_largest_blob: probs (n_samples, 256, 256) fp32, 16-byte aligned.  A pixel is foreground iff round(p) != 0,
+ *   i.e. |p| > 0.5.  masks_out (n_samples, 2048) u32 = the largest 4-connected component of the hole-filled foreground,
+ *   bit b of word 8 r + w = pixel (r, 32 w + b); ties go to the component met first in raster order (np.argmax).
+ *   area_out (n_samples) i32 = its pixel count, may be NULL.  workspace: cub200_seg_blob_workspace_bytes(n_samples).
+ * cub200_seg_entropy: probs (n_img, n_samples, 256, 256) fp32 and the masks of cub200_seg_largest_blob ->
+ *   entropy_out (n_img, 256, 256) fp32 = binary entropy (bits) of mean_t(probs * mask), non-finite -> 0, a frame of
+ *   `pad` pixels zeroed (the reference uses 10).  Optional (NULL to skip): mean_out (n_img, 256, 256) fp32,
+ *   pred_samples_out (n_img * n_samples, 2048) u32 = round(probs * mask) != 0 (BatchResult.pred_samples),
+ *   samples_out (n_img, n_samples, 256, 256) fp32 = probs * mask.
+ */
+int64_t cub200_seg_blob_workspace_bytes(int64_t n_samples);
+int cub200_seg_largest_blob(const float* probs, int64_t n_samples, uint32_t* masks_out, int32_t* area_out, void* workspace,
+                            void* stream);
+int cub200_seg_entropy(const float* probs, const uint32_t* masks, int64_t n_img, int n_samples, int pad, float* entropy_out,
+                       float* mean_out, uint32_t* pred_samples_out, float* samples_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

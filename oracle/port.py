@@ -1109,3 +1109,67 @@ def global_longitudinal_strain(ed_contour: np.ndarray, es_contour: np.ndarray) -
     """cu/utils/clinical.py:50-71."""
     ed_len, es_len = perimeter(ed_contour), perimeter(es_contour)
     return (ed_len - es_len) / ed_len
+
+
+# --------------------------------------------------------------------------------------------------
+# Segmentation-sample post-processing (SURVEY.md 8f-4)
+# --------------------------------------------------------------------------------------------------
+def big_blob(seg: np.ndarray) -> np.ndarray:
+    """cu/task/segmentation/utils.py:12-32: keep the largest 4-connected component of ``seg == 1``.
+
+    ``scipy.ndimage.label`` (default cross structure) numbers the components in raster order of their first
+    pixel and ``np.argmax`` keeps the first of equally large ones.  No component -> ``seg`` itself.
+    """
+    from scipy import ndimage
+
+    lbl, _ = ndimage.label(np.isin(seg, 1))
+    count = np.bincount(lbl.flat)
+    if not np.any(count[1:]):
+        return seg
+    out = np.zeros_like(seg)
+    out[lbl == np.argmax(count[1:]) + 1] = 1
+    return out
+
+
+def seg_postprocess(samples: np.ndarray, pad: int = 10):
+    """cu/task/segmentation/segmentation_uncertainty.py:98-140 for one batch of binary-segmentation samples.
+
+    samples (N, T_e, T_a, 1, H, W) float32 probabilities ->
+      samples_post (same shape, float32) = raw * largest_blob(fill_holes(round(raw)))   (:101-115)
+      entropy (N, H, W) float32, frame of ``pad`` pixels zeroed                          (:125-132)
+      pred_samples (N, T_e, T_a, H, W) bool = round(samples_post)                        (:136,152)
+    """
+    raw = np.asarray(samples)
+    post = raw.round()
+    for i in range(post.shape[0]):
+        for j in range(post.shape[1]):
+            for k in range(post.shape[2]):
+                s = binary_fill_holes(post[i, j, k].squeeze())[None]
+                post[i, j, k] = big_blob(s)
+    post = raw * post
+    ent = np.array([_sample_entropy_f32(post[i]) for i in range(post.shape[0])])
+    ent[:, 0:pad] = 0
+    ent[:, -pad:] = 0
+    ent[:, :, 0:pad] = 0
+    ent[:, :, -pad:] = 0
+    pred_samples = post.round().astype(int).squeeze(axis=3).astype(bool)
+    return post, ent, pred_samples
+
+
+def seg_blob_masks(samples: np.ndarray) -> np.ndarray:
+    """The masks of ``seg_postprocess`` alone: largest_blob(fill_holes(round(sample))), samples (..., H, W) -> bool."""
+    raw = np.asarray(samples)
+    flat = raw.reshape((-1,) + raw.shape[-2:])
+    out = np.zeros(flat.shape, dtype=bool)
+    for i in range(len(flat)):
+        out[i] = big_blob(binary_fill_holes(flat[i].round())[None])[0].astype(bool)
+    return out.reshape(raw.shape)
+
+
+def _sample_entropy_f32(samples: np.ndarray) -> np.ndarray:
+    """cu/task/uncertainty.py:107-133 in the dtype it is given (float32 samples stay float32 end to end)."""
+    s = samples.reshape((-1,) + samples.shape[2:])
+    y = s.mean(0, dtype=s.dtype)
+    umap = scipy.stats.entropy(np.concatenate([y, 1 - y], axis=0), axis=0, base=2)
+    umap[~np.isfinite(umap)] = 0
+    return umap

@@ -555,7 +555,40 @@ def golden_maps():
     print("maps.npz", ent.shape, ent.dtype, "entropy max", ent.max(), "areas", area[0, :4])
 
 
+def golden_segpost():
+    """SegmentationUncertaintyTask.predict_step executed verbatim on synthetic samples (a subclass supplies
+    ``predict`` = the recorded samples; everything after it is the reference's own code)."""
+    from contour_uncertainty.task.segmentation.segmentation_uncertainty import SegmentationUncertaintyTask
+    from vital.data.config import Tags
+
+    n, Te, Ta = 3, 2, 8
+    samples = synth.segmentation_samples(n, Te * Ta, seed=41).reshape(n, Te, Ta, 1, 256, 256)
+
+    class Recorded(SegmentationUncertaintyTask):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+
+        def predict(self, img):
+            s = torch.from_numpy(samples)
+            return s.mean((1, 2)), np.zeros((n, 256, 256)), s
+
+        @staticmethod
+        def get_voxelspacing_and_instants(batch):
+            return None, None
+
+    task = Recorded()
+    task.hparams = SimpleNamespace(data_params=SimpleNamespace(labels=["bg", "lv"]))
+    batch = {Tags.img: torch.zeros((n, 1, 256, 256)), Tags.gt: torch.zeros((n, 256, 256)), Tags.id: [str(i) for i in range(n)]}
+    res = task.predict_step(batch, 0)
+    np.savez_compressed(os.path.join(HERE, "segpost.npz"), seed=41, shape=np.array([n, Te, Ta]),
+                        entropy=res.entropy_map.astype(np.float32),
+                        pred_samples=np.packbits(res.pred_samples.reshape(n, Te * Ta, 256, 256), axis=-1, bitorder="little"),
+                        pred=res.pred.astype(np.uint8), entropy_mean=res.instant_uncertainty["entropy_mean"])
+    print("segpost.npz", res.entropy_map.shape, res.entropy_map.dtype, "entropy max", res.entropy_map.max(),
+          "pred_samples px", res.pred_samples.sum((-2, -1)).reshape(n, -1)[0])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost"]
     for w in which:
         globals()["golden_" + w]()

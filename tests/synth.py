@@ -127,3 +127,60 @@ def exponential_field(seed, stream, n=H * W):
 def skew_alphas(n_img, seed, scale=2.0):
     """(n_img, K, 2) fp32 skewness vectors ~ N(0, scale^2)."""
     return np.random.default_rng(seed).normal(0, scale, (n_img, K, 2)).astype(np.float32)
+
+
+def segmentation_samples(n_img, T, seed, adversarial=True, speckle=0.002):
+    """(n_img, T, 256, 256) float32 'network probabilities' of a binary segmentation: a soft blob per sample with
+    dips (holes to fill), spurious islands (blobs to drop) and speckle.  With ``adversarial`` the first samples of
+    image 0 are replaced by the corner cases of the post-processing (see the list below)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = np.empty((n_img, T, H, W), dtype=np.float32)
+    for i in range(n_img):
+        cy, cx = 128 + rng.normal(0, 12), 128 + rng.normal(0, 12)
+        for t in range(T):
+            a, b = rng.uniform(35, 70), rng.uniform(25, 50)
+            th = rng.uniform(0, np.pi)
+            u = (xx - cx - rng.normal(0, 3)) * np.cos(th) + (yy - cy - rng.normal(0, 3)) * np.sin(th)
+            v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+            field = 6.0 * (1.0 - np.sqrt((u / a) ** 2 + (v / b) ** 2))
+            for _ in range(rng.integers(0, 4)):                       # dips inside -> holes
+                hy, hx, hs = cy + rng.normal(0, 15), cx + rng.normal(0, 15), rng.uniform(1.5, 6)
+                field -= 9.0 * np.exp(-((yy - hy) ** 2 + (xx - hx) ** 2) / (2 * hs * hs))
+            for _ in range(rng.integers(0, 5)):                       # islands outside -> extra blobs
+                by, bx, bs = rng.uniform(5, 250), rng.uniform(5, 250), rng.uniform(1.0, 7)
+                field += 9.0 * np.exp(-((yy - by) ** 2 + (xx - bx) ** 2) / (2 * bs * bs))
+            p = 1.0 / (1.0 + np.exp(-field))
+            speck = rng.random((H, W)) < speckle
+            p = np.where(speck, 1.0 - p, p)
+            out[i, t] = p.astype(np.float32)
+    if adversarial and n_img > 0:
+        cases = []
+        cases.append(np.zeros((H, W)))                                  # nothing
+        cases.append(np.ones((H, W)))                                   # everything
+        c = np.zeros((H, W)); c[20:40, 30:50] = 0.9; c[100:120, 60:80] = 0.8    # two equal blobs -> the first one
+        cases.append(c)
+        c = np.zeros((H, W)); c[100:120, 60:80] = 0.8; c[20:40, 130:150] = 0.9; c[20, 150] = 0.7   # the later-met blob is larger
+        cases.append(c)
+        c = np.zeros((H, W)); c[50:100, 50:100] = 0.9; c[100:150, 100:150] = 0.9   # touching only diagonally
+        cases.append(c)
+        c = np.zeros((H, W)); c[60:200, 60:200] = 0.95; c[90:170, 90:170] = 0.1; c[120:140, 120:140] = 0.99   # ring with a core
+        cases.append(c)
+        c = np.zeros((H, W)); c[60:200, 60:200] = 0.95; c[90:170, 90:170] = 0.1; c[130, 170:200] = 0.2   # hole leaking through a channel
+        cases.append(c)
+        c = np.zeros((H, W)); c[60:200, 60:200] = 0.95; c[90:170, 90:170] = 0.1; c[89, 170] = 0.95; c[90, 170] = 0.1; c[89, 171] = 0.1
+        cases.append(c)                                                 # diagonal-only leak: still a hole for the cross structure
+        cases.append(rng.random((H, W)))                                # speckle: thousands of runs (overflow path)
+        c = (rng.random((H, W)) < 0.55) * 0.9                           # percolating noise
+        cases.append(c)
+        c = np.zeros((H, W)); c[0:256, 0:5] = 0.9; c[0:5, :] = 0.9; c[251:, :] = 0.9; c[:, 251:] = 0.9; c[100:130, 100:130] = 0.7
+        cases.append(c)                                                 # a frame along the border: the inside is a hole
+        c = np.full((H, W), 0.5); c[40:60, 40:60] = np.nextafter(np.float32(0.5), np.float32(1))   # exactly 0.5 rounds to 0
+        cases.append(c)
+        c = np.zeros((H, W)); c[30:90, 30:90] = -0.8; c[150:170, 150:170] = 1.7   # out-of-range values round to -1 / 2
+        cases.append(c)
+        c = np.zeros((H, W)); c[::2, 100:140] = 0.9; c[:, 120] = 0.9      # comb: many runs, one component
+        cases.append(c)
+        for k, c in enumerate(cases[:T]):
+            out[0, k] = c.astype(np.float32)
+    return out

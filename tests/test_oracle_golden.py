@@ -260,3 +260,18 @@ def test_perimeter_and_gls_match_reference():
     np.testing.assert_allclose(port.perimeter(g["es"]), g["perimeter_es"], rtol=1e-13)
     got = np.array([port.global_longitudinal_strain(g["ed"][i], g["es"][i]) for i in range(len(g["ed"]))])
     np.testing.assert_allclose(got, g["gls"], rtol=1e-11)
+
+
+def test_segmentation_postprocessing_matches_reference():
+    """oracle seg_postprocess vs SegmentationUncertaintyTask.predict_step executed on the same samples."""
+    import synth
+
+    g = np.load(os.path.join(G, "segpost.npz"))
+    n, Te, Ta = (int(v) for v in g["shape"])
+    samples = synth.segmentation_samples(n, Te * Ta, seed=int(g["seed"])).reshape(n, Te, Ta, 1, 256, 256)
+    post, ent, pred_samples = port.seg_postprocess(samples)
+    want = np.unpackbits(g["pred_samples"], axis=-1, bitorder="little").astype(bool)
+    assert np.array_equal(pred_samples.reshape(n, Te * Ta, 256, 256), want)
+    # torch's fp32 mean over the samples vs numpy's: a few ulp of the mean, amplified by |d entropy / d p| near 0 and 1
+    assert np.abs(ent - g["entropy"]).max() < 2e-6
+    assert ent.dtype == np.float32 and (ent[:, :10] == 0).all() and (ent[:, :, -10:] == 0).all()
