@@ -345,9 +345,11 @@ seg_blob_overflow_kernel(const float* __restrict__ probs, uint32_t* __restrict__
     }
 }
 
-// One warp per (image, row); lane = 8 consecutive pixels.  The probabilities are read only where the sample's
-// blob mask has a pixel in the lane's byte; the sum runs over the samples in order, in fp64.
-__global__ void __launch_bounds__(256)
+// One warp per (image, row).  Per chunk of 32 samples the lanes first look at one sample each (the 32 bytes of its
+// blob mask in this row): most (row, sample) pairs hold no blob pixel and are dismissed there, in one memory latency
+// per chunk.  The remaining samples are taken in order, four at a time, lane = 8 consecutive pixels: the probabilities
+// are read only under the lane's mask byte and summed in fp64.
+__global__ void __launch_bounds__(256, 3)
 seg_entropy_kernel(const float* __restrict__ probs, const uint32_t* __restrict__ masks, int64_t n_img, int n_samples, int pad,
                    float* __restrict__ entropy_out, float* __restrict__ mean_out, uint32_t* __restrict__ pred_samples_out,
                    float* __restrict__ samples_out) {
@@ -358,42 +360,74 @@ seg_entropy_kernel(const float* __restrict__ probs, const uint32_t* __restrict__
         const int64_t img = wr >> 8;
         const int row = (int)(wr & 255);
         double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint8_t* mrow = reinterpret_cast<const uint8_t*>(masks + img * n_samples * (int64_t)CUB200_MASK_WORDS + row * 8) + lane;
+        const uint32_t* mimg = masks + img * n_samples * (int64_t)CUB200_MASK_WORDS + row * 8;
+        const uint8_t* mrow = reinterpret_cast<const uint8_t*>(mimg) + lane;
         const float* prow = probs + img * n_samples * 65536LL + row * 256 + lane * 8;
-        uint8_t* orow = pred_samples_out
-                            ? reinterpret_cast<uint8_t*>(pred_samples_out + img * n_samples * (int64_t)CUB200_MASK_WORDS + row * 8) + lane
-                            : nullptr;
+        uint32_t* oimg = pred_samples_out ? pred_samples_out + img * n_samples * (int64_t)CUB200_MASK_WORDS + row * 8 : nullptr;
+        uint8_t* orow = oimg ? reinterpret_cast<uint8_t*>(oimg) + lane : nullptr;
         float* srow = samples_out ? samples_out + img * n_samples * 65536LL + row * 256 + lane * 8 : nullptr;
-        for (int t0 = 0; t0 < n_samples; t0 += 4) {
-            uint32_t mb[4];
-            float4 v[4][2];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mb[q] = (t0 + q < n_samples) ? (uint32_t)__ldg(mrow + (int64_t)(t0 + q) * (CUB200_MASK_WORDS * 4)) : 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mb[q]) {
-                    const float4* p = reinterpret_cast<const float4*>(prow + (int64_t)(t0 + q) * 65536);
-                    v[q][0] = ld_stream_f4(p);
-                    v[q][1] = ld_stream_f4(p + 1);
+        for (int tc = 0; tc < n_samples; tc += 32) {
+            const int ts = tc + lane;
+            bool any = false;
+            if (ts < n_samples) {
+                const uint4* mr = reinterpret_cast<const uint4*>(mimg + (int64_t)ts * CUB200_MASK_WORDS);
+                const uint4 a = __ldg(mr), b = __ldg(mr + 1);
+                any = ((a.x | a.y | a.z | a.w) | (b.x | b.y | b.z | b.w)) != 0u;
+                if (!any && oimg) {                   // nothing of this sample in the row: its pred_samples row is empty
+                    uint4* o = reinterpret_cast<uint4*>(oimg + (int64_t)ts * CUB200_MASK_WORDS);
+                    o[0] = o[1] = make_uint4(0, 0, 0, 0);
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (t0 + q >= n_samples) break;
-                float x[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w, v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
-                uint32_t kept = 0u;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    x[k] = ((mb[q] >> k) & 1u) ? x[k] : 0.f;
-                    acc[k] += (double)x[k];
-                    kept |= (fabsf(x[k]) <= 0.5f) ? 0u : (1u << k);        // round(samples) != 0
+            unsigned act = __ballot_sync(FULL, any);
+            if (srow) {
+                unsigned idle = __ballot_sync(FULL, ts < n_samples && !any);
+                while (idle) {
+                    const int t = tc + __ffs(idle) - 1;
+                    idle &= idle - 1;
+                    float4* o = reinterpret_cast<float4*>(srow + (int64_t)t * 65536);
+                    o[0] = o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (orow) orow[(int64_t)(t0 + q) * (CUB200_MASK_WORDS * 4)] = (uint8_t)kept;
-                if (srow) {
-                    float4* o = reinterpret_cast<float4*>(srow + (int64_t)(t0 + q) * 65536);
-                    o[0] = make_float4(x[0], x[1], x[2], x[3]);
-                    o[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
+            while (act) {
+                int tq[4];
+                uint32_t mb[4];
+                float4 v[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tq[q] = act ? tc + __ffs(act) - 1 : -1;
+                    act &= act - 1;                   // 0 & anything stays 0
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mb[q] = (tq[q] >= 0) ? (uint32_t)__ldg(mrow + (int64_t)tq[q] * (CUB200_MASK_WORDS * 4)) : 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q][0] = v[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mb[q]) {
+                        const float4* p = reinterpret_cast<const float4*>(prow + (int64_t)tq[q] * 65536);
+                        v[q][0] = ld_stream_f4(p);
+                        v[q][1] = ld_stream_f4(p + 1);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (tq[q] < 0) break;
+                    uint32_t kept = 0u;
+                    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (mb[q]) {
+                        const float r[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w, v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            x[k] = ((mb[q] >> k) & 1u) ? r[k] : 0.f;
+                            acc[k] += (double)x[k];
+                            kept |= (fabsf(x[k]) <= 0.5f) ? 0u : (1u << k);    // round(samples) != 0
+                        }
+                    }
+                    if (orow) orow[(int64_t)tq[q] * (CUB200_MASK_WORDS * 4)] = (uint8_t)kept;
+                    if (srow) {
+                        float4* o = reinterpret_cast<float4*>(srow + (int64_t)tq[q] * 65536);
+                        o[0] = make_float4(x[0], x[1], x[2], x[3]);
+                        o[1] = make_float4(x[4], x[5], x[6], x[7]);
+                    }
                 }
             }
         }
@@ -404,15 +438,18 @@ seg_entropy_kernel(const float* __restrict__ probs, const uint32_t* __restrict__
             const int col = lane * 8 + k;
             // y_hat = mean (fp32 tensor), [y, 1 - y] normalised by their fp32 sum, entr() summed, / ln 2
             const float y = (float)(acc[k] / (double)n_samples);
-            const float y1 = 1.0f - y;
-            const float sum = y + y1;
-            const double pa = (double)__fdiv_rn(y, sum), pb = (double)__fdiv_rn(y1, sum);
-            // scipy.special.entr: -x log x for x > 0, 0 at 0, -inf below
-            const double ea = pa > 0.0 ? -pa * log(pa) : (pa == 0.0 ? 0.0 : -INFINITY);
-            const double eb = pb > 0.0 ? -pb * log(pb) : (pb == 0.0 ? 0.0 : -INFINITY);
-            float h = (float)((ea + eb) * 1.4426950408889634);
-            if (!isfinite(h)) h = 0.f;
-            if (framed || col < pad || col >= 256 - pad) h = 0.f;
+            float h = 0.f;
+            // most pixels are never inside a blob (y == 0: entropy 0) or lie in the zeroed frame: no fp64 logarithms there
+            if (y != 0.f && !(framed || col < pad || col >= 256 - pad)) {
+                const float y1 = 1.0f - y;
+                const float sum = y + y1;
+                const float pa = __fdiv_rn(y, sum), pb = __fdiv_rn(y1, sum);
+                // scipy.special.entr in the array's own precision (fp32): -x log x for x > 0, 0 at 0, -inf below
+                const float ea = pa > 0.f ? -pa * logf(pa) : (pa == 0.f ? 0.f : -INFINITY);
+                const float eb = pb > 0.f ? -pb * logf(pb) : (pb == 0.f ? 0.f : -INFINITY);
+                h = __fdiv_rn(ea + eb, 0.6931471805599453f);
+                if (!isfinite(h)) h = 0.f;
+            }
             ent[k] = h;
             mean[k] = y;
         }
@@ -484,8 +521,8 @@ extern "C" int cub200_seg_entropy(const float* probs, const uint32_t* masks, int
     using namespace cub200;
     if (n_img == 0) return 0;
     if (!probs || !masks || !entropy_out || n_img < 0 || n_samples <= 0 || pad < 0 || pad > 128) return CUB200_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(probs) | reinterpret_cast<uintptr_t>(entropy_out) | reinterpret_cast<uintptr_t>(mean_out) |
-         reinterpret_cast<uintptr_t>(samples_out)) & 15)
+    if ((reinterpret_cast<uintptr_t>(probs) | reinterpret_cast<uintptr_t>(masks) | reinterpret_cast<uintptr_t>(entropy_out) |
+         reinterpret_cast<uintptr_t>(mean_out) | reinterpret_cast<uintptr_t>(pred_samples_out) | reinterpret_cast<uintptr_t>(samples_out)) & 15)
         return CUB200_EINVAL;
     if (n_img > (int64_t)0x7fffffff / 32) return CUB200_EINVAL;
     int sms = 0;
