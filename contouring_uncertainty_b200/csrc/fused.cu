@@ -101,9 +101,12 @@ __device__ __noinline__ int undo_row_span(const uint32_t* brow, int32_t* drow) {
 // ---------------------------------------------------------------- one sample, one warp
 // Lane k < 21 holds landmark k as (fx, fy).  Returns the mask area; accumulates run boundaries
 // into diff_img (may be null) and stores the packed mask (may be null).
-__device__ int raster_sample(WarpScratch& ws, double fx, double fy, bool round_landmarks,
+// flags: bit 0 = round the landmarks before the spline (USContourToMask), bit 1 = linear_reconstruction
+// (cu/utils/contour.py:43-53): no spline, the 21 rounded landmarks are joined by skimage.draw.line segments.
+__device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
                              int32_t* __restrict__ diff_img, uint32_t* __restrict__ mask_out) {
     const int lane = lane_id();
+    const bool round_landmarks = (flags & 1) != 0, linear = (flags & 2) != 0;
     uint32_t* bmp = ws.bmp;
 
     // zero the boundary bitmap (uint4 stores)
@@ -123,10 +126,12 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, bool round_l
     const double Y = round_landmarks ? (double)riy : fy;
 
     // 3a/3b. chord-length parameter + not-a-knot cubic spline (spline.cuh)
-    const bool bad = fit_spline(ws.sp, X, Y, lane);
+    const bool bad = linear ? false : fit_spline(ws.sp, X, Y, lane);
 
     bool oob = false;
-    if (!bad) {
+    if (linear) {
+        // polygon outline only: every edge is drawn by step 5
+    } else if (!bad) {
         // 3c/4. evaluate 1000 points (32 consecutive per lane), round half-even, apply the index
         //       rules and set the pixels on the fly (consecutive points falling into the same
         //       32-pixel word are merged into one shared-memory atomic).  An index < -256 makes the
@@ -192,10 +197,12 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, bool round_l
 
     // 5. closing line (r0,c0) = landmark 20 -> (r1,c1) = landmark 0, skimage.draw.line closed form:
     //    pixel i < dmaj: major = m0 + i*smaj, minor = n0 + smin * floor((2*dmin*i + dmaj) / (2*dmaj));
-    //    pixel dmaj = (r1, c1).
-    {
-        const int r0 = __shfl_sync(FULL, riy, KP - 1), c0 = __shfl_sync(FULL, rix, KP - 1);
-        const int r1 = __shfl_sync(FULL, riy, 0), c1 = __shfl_sync(FULL, rix, 0);
+    //    pixel dmaj = (r1, c1).  linear_reconstruction draws all 21 edges k -> k+1 this way.
+#pragma unroll 1
+    for (int e = linear ? 0 : KP - 1; e < KP; ++e) {
+        const int e1 = (e + 1 == KP) ? 0 : e + 1;
+        const int r0 = __shfl_sync(FULL, riy, e), c0 = __shfl_sync(FULL, rix, e);
+        const int r1 = __shfl_sync(FULL, riy, e1), c1 = __shfl_sync(FULL, rix, e1);
         const int dr = abs(r1 - r0), dc = abs(c1 - c0);
         const int sc = (c1 - c0) > 0 ? 1 : -1, sr = (r1 - r0) > 0 ? 1 : -1;
         const bool steep = dr > dc;
@@ -368,7 +375,7 @@ sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t
             if (!diff && !area_out && !masks_out) continue;     // sample-only call
         }
         if (!FROM_CONTOURS) { dx = fx; dy = fy; }
-        const int area = raster_sample(ws, dx, dy, round_landmarks != 0,
+        const int area = raster_sample(ws, dx, dy, round_landmarks,
                                        diff ? diff + map * 65536 : nullptr,
                                        masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
         if (area_out && lane == 0) area_out[g] = area;

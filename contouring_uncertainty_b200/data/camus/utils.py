@@ -14,10 +14,11 @@ class USContourToMask(ContourToMask):
                  reconstruction_type: Literal['spline', 'linear'] = 'spline'):
         """landmarks (K,2) [or (M,K,2)] -> int64 mask (H,W) [(M,H,W)]; channel axis added when not apply_argmax.
 
-        Rounds the landmarks first, then spline raster + closing line + hole fill (cu/utils/contour.py:28-40).
+        Rounds the landmarks first, then spline raster + closing line + hole fill (cu/utils/contour.py:28-40), or,
+        with reconstruction_type='linear', the polygon outline + hole fill (cu/utils/contour.py:43-53).
         """
-        if reconstruction_type != 'spline':
-            raise NotImplementedError("only reconstruction_type='spline' (the reference default) is on the GPU path")
+        if reconstruction_type not in ('spline', 'linear'):
+            raise ValueError
         if tuple(shape) != (E.HW, E.HW):
             raise ValueError("only 256x256 frames are supported")
         if labels is not None and any(str(l).lower().endswith("myo") for l in labels):
@@ -26,7 +27,7 @@ class USContourToMask(ContourToMask):
         single = lm.ndim == 2
         lm = lm.reshape(-1, E.K, 2)
         dev = torch.device("cuda", torch.cuda.current_device())
-        masks, _ = E.rasterize_contours(torch.from_numpy(lm).to(dev), round_landmarks=True)
+        masks, _ = E.rasterize_contours(torch.from_numpy(lm).to(dev), round_landmarks=True, reconstruction_type=reconstruction_type)
         out = E.unpack_masks(masks).cpu().numpy().astype(np.int64)
         if single:
             out = out[0]

@@ -177,8 +177,12 @@ def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Opti
 
 
 def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, return_masks: bool = True,
-                       diff: Optional[torch.Tensor] = None, per_image: int = 0):
-    """Rasteriser alone: contours (M,21,2) fp32 or fp64 -> (masks (M,2048) int32 bit-packed | None, area (M) int32)."""
+                       diff: Optional[torch.Tensor] = None, per_image: int = 0, reconstruction_type: str = "spline"):
+    """Rasteriser alone: contours (M,21,2) fp32 or fp64 -> (masks (M,2048) int32 bit-packed | None, area (M) int32).
+    reconstruction_type 'linear' = linear_reconstruction (cu/utils/contour.py:43-53): rounded landmarks joined by lines."""
+    if reconstruction_type not in ("spline", "linear"):
+        raise ValueError("reconstruction_type must be 'spline' or 'linear'")
+    flags = 3 if reconstruction_type == "linear" else int(bool(round_landmarks))
     f64 = isinstance(contours, torch.Tensor) and contours.dtype == torch.float64
     contours = nat.require_cuda(contours, torch.float64 if f64 else torch.float32, "contours")
     if contours.dim() != 3 or contours.shape[1:] != (K, 2):
@@ -189,7 +193,7 @@ def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, ret
     area = torch.empty((m,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         fn = nat.lib().cub200_rasterize_contours_f64 if f64 else nat.lib().cub200_rasterize_contours
-        rc = fn(nat.ptr(contours), m, int(round_landmarks), nat.ptr(masks), nat.ptr(area), nat.ptr(diff), int(per_image),
+        rc = fn(nat.ptr(contours), m, flags, nat.ptr(masks), nat.ptr(area), nat.ptr(diff), int(per_image),
                 nat.stream_ptr(dev))
     nat.check(rc, "cub200_rasterize_contours")
     return masks, area

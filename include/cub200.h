@@ -116,7 +116,9 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *                starts, -1 one past where it ends; the row prefix sum is the count map
  *   masks_out    optional (n_img, n_samples, 2048) uint32 bit-packed masks (debug / return_masks)
  *   round_landmarks: 1 = USContourToMask semantics (round landmarks first), 0 = reconstruction()
- *                on the raw float contour (cu/sampler/sampling_example3.py:127)
+ *                on the raw float contour (cu/sampler/sampling_example3.py:127); 3 = linear_reconstruction
+ *                (cu/utils/contour.py:43-53, reconstruction_type='linear'): the rounded landmarks joined by
+ *                skimage.draw.line segments instead of the spline.  Bit 0 = round, bit 1 = linear.
  *   images_per_map: consecutive (mu, a_t) entries that aggregate into ONE difference map (the T_e
  *                epistemic passes of an image, aleatoric.py:71-73); diff is (n_img / images_per_map, 256, 256)
  */

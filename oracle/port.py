@@ -177,6 +177,18 @@ def reconstruction(points: np.ndarray, height: int, width: int) -> np.ndarray:
     return binary_fill_holes(seg_map).astype(int)
 
 
+def linear_reconstruction(points: np.ndarray, height: int, width: int) -> np.ndarray:
+    """cu/utils/contour.py:43-53 -- the rounded points joined by ``skimage.draw.line`` segments (clipped to the frame),
+    closed from the last point to the first, hole fill."""
+    points = np.asarray(points).round().astype(int)
+    seg_map = np.zeros((height, width), dtype=int)
+    for i in range(len(points)):
+        j = (i + 1) % len(points)
+        rr, cc = bresenham_line(points[i, 1], points[i, 0], points[j, 1], points[j, 0])
+        seg_map[rr.clip(min=0, max=255), cc.clip(min=0, max=255)] = 1
+    return binary_fill_holes(seg_map).astype(int)
+
+
 def us_contour_to_mask(landmarks: np.ndarray, shape=(256, 256), apply_argmax: bool = True) -> np.ndarray:
     """cu/data/camus/utils.py:31-98, LV-only branch (:43, :85-90): round landmarks first."""
     landmarks = np.asarray(landmarks).round().astype(int).squeeze()

@@ -73,9 +73,14 @@ def golden_raster():
     unr = np.zeros((32, 256, 256), dtype=np.uint8)
     for i in range(32):
         unr[i] = reconstruction(contours[i].astype(np.float64), 256, 256)
+    # reconstruction_type='linear' (validation-step dice of dsnt_al.py:80-84): polygon outline + hole fill
+    lin = np.zeros((len(contours), 256, 256), dtype=np.uint8)
+    for i, c in enumerate(contours):
+        lin[i] = USContourToMask.__call__(c.astype(np.float32), (256, 256), labels=[], apply_argmax=True, reconstruction_type='linear')
     np.savez_compressed(os.path.join(HERE, "raster.npz"), contours=np.stack(contours).astype(np.float32),
                         tags=np.array(tags), masks=np.packbits(masks, axis=-1, bitorder="little"),
-                        masks_unrounded=np.packbits(unr, axis=-1, bitorder="little"))
+                        masks_unrounded=np.packbits(unr, axis=-1, bitorder="little"),
+                        masks_linear=np.packbits(lin, axis=-1, bitorder="little"))
     print("raster.npz", masks.shape, "areas", masks.sum((1, 2))[:8], "tags", sorted(set(tags)))
 
 

@@ -30,8 +30,10 @@ def test_us_contour_to_mask_functor():
     assert m.shape == (1, 256, 256) and np.array_equal(m[0], want[5])
     mm = USContourToMask.__call__(g["contours"][:16], (256, 256))
     assert mm.shape == (16, 256, 256) and np.array_equal(mm, want[:16])
-    with pytest.raises(NotImplementedError):
-        USContourToMask.__call__(g["contours"][0], reconstruction_type="linear")
+    lin = np.unpackbits(g["masks_linear"], axis=-1, bitorder="little")
+    assert np.array_equal(USContourToMask.__call__(g["contours"][0], reconstruction_type="linear"), lin[0])
+    with pytest.raises(ValueError):
+        USContourToMask.__call__(g["contours"][0], reconstruction_type="cubic")
 
 
 def test_psm_sampler_call_signature_and_replay():

@@ -100,6 +100,17 @@ def test_raster_golden_bit_exact(dev):
     want = _unpack_np(g["masks_unrounded"])
     bad = [(i, int((got[i] != want[i]).sum())) for i in range(32) if not np.array_equal(got[i], want[i])]
     assert not bad, bad
+    # reconstruction_type='linear': polygon outline + hole fill (incl. the off-frame / duplicate-point cases)
+    masks, area = rasterize_contours(contours, reconstruction_type="linear")
+    got = unpack_masks(masks).cpu().numpy()
+    want = _unpack_np(g["masks_linear"])
+    bad = [(i, str(g["tags"][i]), int((got[i] != want[i]).sum())) for i in range(len(want)) if not np.array_equal(got[i], want[i])]
+    assert not bad, bad
+    assert np.array_equal(area.cpu().numpy(), want.reshape(len(want), -1).sum(1))
+    from contouring_uncertainty_b200.data.camus.utils import USContourToMask
+
+    one = USContourToMask.__call__(g["contours"][3], (256, 256), labels=[], reconstruction_type="linear")
+    assert np.array_equal(one, want[3])
 
 
 def test_raster_random_vs_oracle_bit_exact(dev):

@@ -42,6 +42,10 @@ def test_raster_bit_exact():
     unr = _unpack(g["masks_unrounded"])
     for i in range(unr.shape[0]):
         assert np.array_equal(port.reconstruction(contours[i].astype(np.float64), 256, 256), unr[i])
+    lin = _unpack(g["masks_linear"])                 # reconstruction_type='linear'
+    bad = [(i, str(g["tags"][i])) for i, c in enumerate(contours)
+           if not np.array_equal(port.linear_reconstruction(c.round().astype(int), 256, 256), lin[i])]
+    assert not bad, bad
 
 
 def test_own_spline_matches_fitpack():
