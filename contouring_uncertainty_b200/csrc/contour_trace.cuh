@@ -1,0 +1,152 @@
+// Marching-squares contour tracing of a bit-packed mask: skimage.measure.find_contours(mask, level)[0] for a BINARY
+// mask (third party, restated: see oracle/port.py::find_contours -- parity unpinned for it).  Shared by the Simpson
+// kernels (simpson.cu, level 0.5) and the mask-based strain (gls.cu, level 0.9): for a 0/1 image every level in (0, 1)
+// crosses the same cell edges in the same order, only the position of a point along its edge depends on the level, so
+// the points are stored as half-pixel (2 row, 2 col) uint16 pairs naming the EDGE they lie on.
+#pragma once
+#include "common.cuh"
+
+namespace cub200 {
+
+constexpr int SP_NMAX = CUB200_SIMPSON_MAX_POINTS;   // contour points kept per mask
+
+// to-edge of the segment that STARTS at edge f (to_of_from) / from-edge of the segment that ENDS at
+// edge t (from_of_to), per square case (bit 0 ul, 1 ur, 2 ll, 3 lr; 'low' vertex connectivity).
+// Edges: 0 top, 1 bottom, 2 left, 3 right; 9 = no such segment.
+static __constant__ unsigned char c_to_of_from[16][4] = {
+    {9, 9, 9, 9}, {2, 9, 9, 9}, {9, 9, 9, 0}, {9, 9, 9, 2}, {9, 9, 1, 9}, {1, 9, 9, 9}, {9, 9, 1, 0}, {9, 9, 9, 1},
+    {9, 3, 9, 9}, {2, 3, 9, 9}, {9, 0, 9, 9}, {9, 2, 9, 9}, {9, 9, 3, 9}, {3, 9, 9, 9}, {9, 9, 0, 9}, {9, 9, 9, 9}};
+static __constant__ unsigned char c_from_of_to[16][4] = {
+    {9, 9, 9, 9}, {9, 9, 0, 9}, {3, 9, 9, 9}, {9, 9, 3, 9}, {9, 2, 9, 9}, {9, 0, 9, 9}, {3, 2, 9, 9}, {9, 3, 9, 9},
+    {9, 9, 9, 1}, {9, 9, 0, 1}, {1, 9, 9, 9}, {9, 9, 1, 9}, {9, 9, 9, 2}, {9, 9, 9, 0}, {2, 9, 9, 9}, {9, 9, 9, 9}};
+// from-edge of the FIRST segment a cell generates (cases 6 and 9 generate two)
+static __constant__ unsigned char c_first_from[16] = {9, 0, 3, 3, 2, 0, 3, 3, 1, 0, 1, 1, 2, 0, 2, 9};
+
+// A mask as the Simpson code sees it: the 256 x 256 bit-packed mask itself, or (anisotropic voxel spacing) its
+// nearest-neighbour stretch to H x W -- resize_image_to_isotropic (vital/vital/utils/image/transform.py:52-66) through
+// PIL's NEAREST resize, whose source index per output row / column is precomputed by the host (ri, ci).
+struct MaskView {
+    const uint32_t* m;
+    const uint16_t* ri;    // source row of each virtual row (nullptr: identity)
+    const uint16_t* ci;    // source column of each virtual column
+    int H, W;
+    __device__ __forceinline__ int bit(int r, int c) const {
+        if (ri) { r = ri[r]; c = ci[c]; }
+        return (m[r * 8 + (c >> 5)] >> (c & 31)) & 1u;
+    }
+    __device__ __forceinline__ int cell(int r0, int c0) const {
+        return bit(r0, c0) | (bit(r0, c0 + 1) << 1) | (bit(r0 + 1, c0) << 2) | (bit(r0 + 1, c0 + 1) << 3);
+    }
+};
+// a cell's second segment (saddle cases): the one starting at L (case 6) / B (case 9)
+__device__ __forceinline__ int seg_rank(int cs, int from_edge) {
+    return (cs == 6 && from_edge == 2) || (cs == 9 && from_edge == 1);
+}
+__device__ __forceinline__ uint32_t edge_point(int r0, int c0, int e) {
+    // half-pixel units: top (2r0, 2c0+1), bottom (2r0+2, 2c0+1), left (2r0+1, 2c0), right (2r0+1, 2c0+2)
+    const int r2 = 2 * r0 + (e == 0 ? 0 : e == 1 ? 2 : 1);
+    const int c2 = 2 * c0 + (e == 2 ? 0 : e == 3 ? 2 : 1);
+    return (uint32_t)r2 | ((uint32_t)c2 << 16);
+}
+
+// ---------------------------------------------------------------- S1: contour tracing, one thread per mask
+static __global__ void __launch_bounds__(128)
+contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const uint16_t* __restrict__ row_index,
+                     const uint16_t* __restrict__ col_index, int vh, int vw, uint32_t* __restrict__ pts, int32_t* __restrict__ npts) {
+    extern __shared__ uint16_t s_idx[];                           // [vh rows][vw columns] source indices (stretched view)
+    if (row_index) {
+        for (int i = threadIdx.x; i < vh; i += blockDim.x) s_idx[i] = row_index[i];
+        for (int i = threadIdx.x; i < vw; i += blockDim.x) s_idx[vh + i] = col_index[i];
+        __syncthreads();
+    }
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_masks) return;
+    const uint32_t* m = masks + g * CUB200_MASK_WORDS;
+    const MaskView mv{m, row_index ? s_idx : nullptr, row_index ? s_idx + vh : nullptr, vh, vw};
+    const int RM = vh - 2, CM = vw - 2;                           // last cell row / column
+    uint32_t* out = pts + g * SP_NMAX;
+    // raster-first cell that generates a segment
+    int fr = -1, fc = -1;
+    if (!row_index) {
+        uint32_t a[8], b[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a[w] = m[w];
+        for (int r0 = 0; r0 < 255 && fr < 0; ++r0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) b[w] = m[(r0 + 1) * 8 + w];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t a1 = (a[w] >> 1) | ((w < 7 ? a[w < 7 ? w + 1 : 7] : 0u) << 31);
+                const uint32_t b1 = (b[w] >> 1) | ((w < 7 ? b[w < 7 ? w + 1 : 7] : 0u) << 31);
+                uint32_t nu = (a[w] ^ b[w]) | (a[w] ^ a1) | (b[w] ^ b1);
+                if (w == 7) nu &= 0x7fffffffu;                   // there is no cell at c0 = 255
+                if (nu && fr < 0) { fr = r0; fc = 32 * w + __ffs(nu) - 1; }
+            }
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a[w] = b[w];
+        }
+    } else {
+        // stretched view: skip the row pairs whose source rows are both empty, then scan the cells of the first other one
+        for (int r0 = 0; r0 <= RM && fr < 0; ++r0) {
+            const uint32_t* ra = m + mv.ri[r0] * 8;
+            const uint32_t* rb = m + mv.ri[r0 + 1] * 8;
+            uint32_t any = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) any |= ra[w] | rb[w];
+            if (!any) continue;
+            for (int c0 = 0; c0 <= CM; ++c0) {
+                const int cs = mv.cell(r0, c0);
+                if (cs != 0 && cs != 15) { fr = r0; fc = c0; break; }
+            }
+        }
+    }
+    if (fr < 0) { npts[g] = 0; return; }                          // find_contours() == [] -> IndexError
+    // pass A: walk backwards from the first segment to the chain start, or around the loop
+    const int cs0 = mv.cell(fr, fc);
+    const int f0 = c_first_from[cs0];
+    int r0 = fr, c0 = fc, fe = f0;                                // current segment = (cell, from-edge)
+    int sr = fr, sc = fc, sf = f0;                                // start segment of pass B
+    bool closed = false;
+    int last_key = -1, lr = 0, lc = 0, lt = 0;                    // raster-last segment of the loop
+    for (int it = 0; it < 4 * SP_NMAX; ++it) {
+        const int cs = mv.cell(r0, c0);
+        const int te = c_to_of_from[cs][fe];
+        const int key = ((r0 * (CM + 1) + c0) << 1) | seg_rank(cs, fe);
+        if (key > last_key) { last_key = key; lr = r0; lc = c0; lt = te; }
+        // predecessor: the cell across the from-edge, whose segment ends on the shared edge
+        int pr = r0, pc = c0, pe;
+        if (fe == 0) { pr = r0 - 1; pe = 1; } else if (fe == 1) { pr = r0 + 1; pe = 0; }
+        else if (fe == 2) { pc = c0 - 1; pe = 3; } else { pc = c0 + 1; pe = 2; }
+        if (pr < 0 || pr > RM || pc < 0 || pc > CM) { sr = r0; sc = c0; sf = fe; break; }     // open chain start
+        const int pf = c_from_of_to[mv.cell(pr, pc)][pe];
+        r0 = pr; c0 = pc; fe = pf;
+        if (r0 == fr && c0 == fc && fe == f0) { closed = true; break; }
+    }
+    if (closed) {
+        // the loop starts at the to-point of its raster-last segment: first segment of pass B is the one after it
+        int nr = lr, nc = lc, ne;
+        if (lt == 0) { nr = lr - 1; ne = 1; } else if (lt == 1) { nr = lr + 1; ne = 0; }
+        else if (lt == 2) { nc = lc - 1; ne = 3; } else { nc = lc + 1; ne = 2; }
+        sr = nr; sc = nc; sf = ne;
+    }
+    // pass B: forward, recording points
+    int n = 0;
+    r0 = sr; c0 = sc; fe = sf;
+    out[n++] = edge_point(r0, c0, fe);
+    bool overflow = false;
+    for (;;) {
+        const int cs = mv.cell(r0, c0);
+        const int te = c_to_of_from[cs][fe];
+        if (n >= SP_NMAX) { overflow = true; break; }
+        out[n++] = edge_point(r0, c0, te);
+        int nr = r0, nc = c0, ne;
+        if (te == 0) { nr = r0 - 1; ne = 1; } else if (te == 1) { nr = r0 + 1; ne = 0; }
+        else if (te == 2) { nc = c0 - 1; ne = 3; } else { nc = c0 + 1; ne = 2; }
+        if (nr < 0 || nr > RM || nc < 0 || nc > CM) break;         // open chain end
+        r0 = nr; c0 = nc; fe = ne;
+        if (closed && r0 == sr && c0 == sc && fe == sf) break;
+    }
+    npts[g] = overflow ? -1 : n;
+}
+
+}  // namespace cub200

@@ -493,12 +493,9 @@ extern "C" int cub200_seg_largest_blob(const float* probs, int64_t n_samples, ui
     if ((reinterpret_cast<uintptr_t>(probs) | reinterpret_cast<uintptr_t>(masks_out) | reinterpret_cast<uintptr_t>(workspace)) & 15)
         return CUB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool configured = false;
     const int smem = SG_WARPS * (int)sizeof(SegScratch);
-    if (!configured) {
-        CUB200_CUDA_OK(cudaFuncSetAttribute(seg_blob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    // per device, so set on every call (a process may drive several GPUs)
+    CUB200_CUDA_OK(cudaFuncSetAttribute(seg_blob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int sms = 0;
     if (int rc = sm_count(&sms)) return rc;
     int32_t* overflow = reinterpret_cast<int32_t*>(workspace);

@@ -752,6 +752,64 @@ def ece_from_bins(bins) -> tuple:
     return ece, (max(gaps) if gaps else float("nan"))
 
 
+_GLS_TABLES = {}
+GLS_TABLE_STRIDE = 48
+SIMPSON_MAX_POINTS = 2048
+
+
+def gls_gauss_table(polar_smoothing_factor: float, device) -> torch.Tensor:
+    """Row n = the normalised Gaussian kernel values w[0..lw] of scipy.ndimage.gaussian_filter1d(sigma = n * factor),
+    formed exactly as scipy's _gaussian_kernel1d forms them (numpy exp, numpy sum); cached per (factor, device)."""
+    key = (float(polar_smoothing_factor), str(device))
+    if key not in _GLS_TABLES:
+        tab = np.zeros((SIMPSON_MAX_POINTS + 1, GLS_TABLE_STRIDE))
+        tab[:, 0] = 1.0
+        for n in range(1, SIMPSON_MAX_POINTS + 1):
+            sigma = n * float(polar_smoothing_factor)
+            lw = int(4.0 * sigma + 0.5)
+            if lw == 0 or sigma <= 0:
+                continue
+            x = np.arange(-lw, lw + 1)
+            phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+            phi = phi / phi.sum()
+            tab[n, :lw + 1] = phi[lw:]
+        _GLS_TABLES[key] = torch.from_numpy(tab).to(device)
+    return _GLS_TABLES[key]
+
+
+def mask_lv_length(masks: torch.Tensor, voxelspacing=(1.0, 1.0), polar_smoothing_factor: float = 5e-3, return_corners: bool = False):
+    """Longitudinal length of the LV endocardium of every mask (EchoMeasure._lv_longitudinal_length, myo_labels=None,
+    vital/vital/utils/image/us/measure.py:339-354): bit-packed masks (..., 2048) int32 -> lengths (...) fp64, NaN where the
+    reference raises [, base corners (..., 2, 2) as (row, col), points of the base-less contour (...) int32]."""
+    masks = nat.require_cuda(masks, torch.int32, "masks")
+    if masks.shape[-1] != MASK_WORDS:
+        raise ValueError(f"masks must be (..., {MASK_WORDS}) bit-packed")
+    lead = tuple(masks.shape[:-1])
+    n = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    dev = masks.device
+    length = torch.empty(lead, dtype=torch.float64, device=dev)
+    corners = torch.empty(lead + (2, 2), dtype=torch.float64, device=dev) if return_corners else None
+    npts = torch.empty(lead, dtype=torch.int32, device=dev) if return_corners else None
+    ws = torch.empty((max(int(nat.lib().cub200_simpson_workspace_bytes(n)), 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        table = gls_gauss_table(polar_smoothing_factor, dev) if polar_smoothing_factor > 0 else None
+        rc = nat.lib().cub200_mask_lv_length(nat.ptr(masks), n, float(polar_smoothing_factor), nat.ptr(table), float(voxelspacing[0]),
+                                             float(voxelspacing[1]), nat.ptr(length), nat.ptr(corners), nat.ptr(npts), nat.ptr(ws),
+                                             nat.stream_ptr(dev))
+    nat.check(rc, "cub200_mask_lv_length")
+    return (length, corners, npts) if return_corners else length
+
+
+def mask_gls(masks: torch.Tensor, voxelspacing=(1.0, 1.0)) -> torch.Tensor:
+    """EchoMeasure.gls (measure.py:320-366, myo_labels=None) on sequences of bit-packed masks (..., N_frames, 2048): strain in
+    percent of every frame against the first one (the ED frame), (..., N_frames) fp64; a frame the reference cannot measure
+    makes the whole sequence NaN (its exception leaves GLS.gls's try block, cu/results/clinical/view.py:86-96)."""
+    length = mask_lv_length(masks, voxelspacing)
+    ed = length[..., :1]
+    gls = (length - ed) / ed * 100
+    return torch.where(torch.isnan(length).any(-1, keepdim=True), torch.full_like(gls, float("nan")), gls)
+
+
 # --------------------------------------------------------------------------------------------------
 # Segmentation-sample post-processing (SURVEY 8f-4)
 # --------------------------------------------------------------------------------------------------

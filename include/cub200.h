@@ -416,6 +416,29 @@ int cub200_seg_largest_blob(const float* probs, int64_t n_samples, uint32_t* mas
 int cub200_seg_entropy(const float* probs, const uint32_t* masks, int64_t n_img, int n_samples, int pad, float* entropy_out,
                        float* mean_out, uint32_t* pred_samples_out, float* samples_out, void* stream);
 
+/*
+ * Mask-based longitudinal length of the LV endocardium: what EchoMeasure.gls compares between the
+ * frames of a sequence.  Replaces EchoMeasure.gls / _lv_longitudinal_length (myo_labels=None),
+ * _extract_landmarks_from_polar_contour (apex=False), _endo_epi_contour   vital/vital/utils/image/us/measure.py:22-195,320-366
+ * and the per-sample loop of GLS.compute   contour_uncertainty/results/clinical/view.py:146.
+ *   masks (n_masks, 2048) u32 bit-packed 256x256; smoothing_factor = polar_smoothing_factor (the reference uses 5e-3; 0 = none);
+ *   spacing_row / spacing_col = voxelspacing (the reference's callers leave it at (1, 1)).
+ *   gauss_table: optional device table (CUB200_SIMPSON_MAX_POINTS + 1, CUB200_GLS_TABLE_STRIDE) f64; row n holds the
+ *   normalised Gaussian kernel values w[0..lw] scipy.ndimage.gaussian_filter1d uses for sigma = n * smoothing_factor
+ *   (lw = int(4 sigma + 0.5)), made by the host with the same exp as scipy so that the smoothed signal, hence every
+ *   peak comparison, is bit-identical.  NULL: the kernel evaluates the weights itself (its exp may differ by an ulp,
+ *   which can only matter for peaks that tie to the last bit, e.g. on mirror-symmetric masks).
+ *   length_out (n_masks) f64: sum of the segment lengths of the base-less contour; NaN where the reference raises
+ *   (no contour, fewer than two base corners, more than CUB200_SIMPSON_MAX_POINTS contour points).
+ *   Optional: corners_out (n_masks, 2, 2) f64 = (left, right) base corners as (row, col); npts_out (n_masks) i32 = points
+ *   of the base-less contour.  workspace: cub200_simpson_workspace_bytes(n_masks).
+ * GLS of frame k vs frame 0 = (L_k - L_0) / L_0 * 100.
+ */
+#define CUB200_GLS_TABLE_STRIDE 48
+int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, double smoothing_factor, const double* gauss_table,
+                          double spacing_row, double spacing_col, double* length_out, double* corners_out, int32_t* npts_out,
+                          void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1185,3 +1185,79 @@ def _sample_entropy_f32(samples: np.ndarray) -> np.ndarray:
     umap = scipy.stats.entropy(np.concatenate([y, 1 - y], axis=0), axis=0, base=2)
     umap[~np.isfinite(umap)] = 0
     return umap
+
+
+# --------------------------------------------------------------------------------------------------
+# Mask-based GLS (second half): vital EchoMeasure.gls with myo_labels=None
+# --------------------------------------------------------------------------------------------------
+def polar_base_corners(mask: np.ndarray, polar_smoothing_factor: float = 5e-3):
+    """vital/vital/utils/image/us/measure.py:22-151 with apex=False, base=True: the two highest peaks of the smoothed
+    polar radius of the contour in the lower half (theta > 0), ordered by descending theta (left corner first).
+    Raises RuntimeError when fewer than two peaks are found (:93-97).  Returns (left, right, contour)."""
+    from scipy import ndimage
+    from scipy.ndimage import gaussian_filter1d
+    from scipy.signal import find_peaks
+
+    structure_mask = np.asarray(mask).astype(bool)
+    contour = find_contours(structure_mask, level=0.9)[0]                      # :52
+    centered = contour - ndimage.center_of_mass(structure_mask)                # :55
+    x, y = centered[:, 1], centered[:, 0]
+    rho = np.sqrt(x ** 2 + y ** 2)                                             # vital/utils/image/coord.py:31-38
+    theta = np.arctan2(y, x)
+    order = theta.argsort()
+    theta, rho = theta[order], rho[order]
+    if polar_smoothing_factor:
+        rho = gaussian_filter1d(rho, len(contour) * polar_smoothing_factor)    # :62
+    peaks, props = find_peaks(rho, height=0)                                   # :65
+    heights = props["peak_heights"]
+    keep = theta[peaks] > 0                                                    # :89
+    base_peaks, base_heights = peaks[keep], heights[keep]
+    if len(base_peaks) < 2:
+        raise RuntimeError("fewer than two base corners")
+    # NB equal heights (mirror-symmetric masks) are ordered by numpy's unstable quicksort: see base_corner_tie()
+    two = sorted(base_heights.argsort()[-2:], reverse=True)                    # :100-103
+    left, right = contour[order[base_peaks[two]]]
+    return left, right, contour
+
+
+def base_corner_tie(mask: np.ndarray, polar_smoothing_factor: float = 5e-3) -> bool:
+    """True when the choice of the two highest base peaks hinges on equal heights (argsort's tie order, which is an
+    implementation detail of numpy's unstable sort): parity of the corners is undefined for such a mask."""
+    from scipy import ndimage
+    from scipy.ndimage import gaussian_filter1d
+    from scipy.signal import find_peaks
+
+    structure_mask = np.asarray(mask).astype(bool)
+    contour = find_contours(structure_mask, level=0.9)[0]
+    centered = contour - ndimage.center_of_mass(structure_mask)
+    rho = np.sqrt(centered[:, 1] ** 2 + centered[:, 0] ** 2)
+    theta = np.arctan2(centered[:, 0], centered[:, 1])
+    order = theta.argsort()
+    rho = gaussian_filter1d(rho[order], len(contour) * polar_smoothing_factor)
+    peaks, props = find_peaks(rho, height=0)
+    h = np.sort(props["peak_heights"][theta[order][peaks] > 0])
+    return len(h) >= 3 and h[-3] == h[-2]
+
+
+def endo_contour_without_base(mask: np.ndarray) -> np.ndarray:
+    """measure.py:153-195 (_endo_epi_contour) with the polar base corners: the contour rolled to start at the point
+    closest to the left corner, cut after the point closest to the right corner."""
+    left, right, contour = polar_base_corners(mask)
+    contour = np.roll(contour, -np.argmin(np.linalg.norm(left - contour, axis=1)), axis=0)
+    return contour[: np.argmin(np.linalg.norm(right - contour, axis=1)) + 1]
+
+
+def lv_longitudinal_length(mask: np.ndarray, voxelspacing=(1, 1)) -> float:
+    """measure.py:339-354: sum of the distances between consecutive points of the base-less contour."""
+    c = endo_contour_without_base(mask)
+    vs = np.array(voxelspacing)
+    total = 0
+    for p0, p1 in zip(c[:-1], c[1:]):
+        total = total + np.linalg.norm((p1 - p0) * vs)
+    return float(total)
+
+
+def echo_gls(segmentation: np.ndarray, voxelspacing=(1, 1)) -> np.ndarray:
+    """measure.py:320-366 (EchoMeasure.gls, myo_labels=None): (N,H,W) masks, first frame = ED -> (N,) strain in percent."""
+    lengths = np.array([lv_longitudinal_length(f, voxelspacing) for f in segmentation])
+    return (lengths - lengths[0]) / lengths[0] * 100

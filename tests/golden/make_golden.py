@@ -593,7 +593,59 @@ def golden_segpost():
           "pred_samples px", res.pred_samples.sum((-2, -1)).reshape(n, -1)[0])
 
 
+def glsmask_extra_masks():
+    """Masks that stress the polar peak search: disc, square, small blob, thin bar, empty, two blobs."""
+    yy, xx = np.mgrid[0:256, 0:256]
+    out = []
+    out.append(((yy - 128) ** 2 + (xx - 128) ** 2 <= 50 ** 2))
+    m = np.zeros((256, 256), bool); m[60:200, 80:180] = True; out.append(m)
+    m = np.zeros((256, 256), bool); m[100:104, 100:103] = True; out.append(m)
+    m = np.zeros((256, 256), bool); m[30:230, 126:130] = True; out.append(m)
+    out.append(np.zeros((256, 256), bool))
+    m = np.zeros((256, 256), bool); m[20:60, 20:60] = True; m[120:220, 100:180] = True; out.append(m)
+    m = (((yy - 100) / 70.0) ** 2 + ((xx - 128) / 40.0) ** 2 <= 1) & (yy < 150); out.append(m)      # half ellipse, flat base
+    return np.array(out)
+
+
+def golden_glsmask():
+    """EchoMeasure.gls (vital/vital/utils/image/us/measure.py:320-366, myo_labels=None) and its pieces on rasterised
+    contour samples.  skimage.measure.find_contours is the restated one (oracle/port.py): parity unpinned for it."""
+    from contour_uncertainty.data.camus.utils import USContourToMask
+    from vital.data.camus.config import Label
+    from vital.utils.image.us.measure import EchoMeasure
+    import functools
+
+    T = 10
+    contours = _simpson_contours(T)
+    masks = np.array([[USContourToMask.__call__(contours[v, t], (256, 256), labels=[], apply_argmax=True) for t in range(T)]
+                      for v in range(4)]).astype(bool).reshape(4 * T, 256, 256)
+    masks = np.concatenate([masks, glsmask_extra_masks()])
+    base_fn = functools.partial(EchoMeasure._extract_landmarks_from_polar_contour, labels=Label.LV, polar_smoothing_factor=5e-3, apex=False)
+    n = len(masks)
+    corners = np.full((n, 2, 2), np.nan)
+    npts = np.zeros(n, dtype=np.int64)
+    length = np.full(n, np.nan)
+    for i, m in enumerate(masks):
+        try:
+            corners[i] = np.array(base_fn(m.astype(int)))
+            c = EchoMeasure._endo_epi_contour(m.astype(int), Label.LV, base_fn)
+            npts[i] = len(c)
+            length[i] = sum(np.linalg.norm((p1 - p0) * np.array((1, 1))) for p0, p1 in zip(c[:-1], c[1:]))   # measure.py:354
+        except Exception as e:
+            print("  mask", i, "raised", type(e).__name__, e)
+    gls = np.full((2, T), np.nan)
+    for v in range(2):
+        for t in range(T):
+            try:
+                gls[v, t] = EchoMeasure.gls(np.stack([masks[(2 * v) * T + t], masks[(2 * v + 1) * T + t]]).astype(int), Label.LV, None)[1]
+            except Exception as e:
+                print("  gls", v, t, "raised", type(e).__name__)
+    np.savez_compressed(os.path.join(HERE, "glsmask.npz"), masks=np.packbits(masks, axis=-1, bitorder="little"),
+                        corners=corners, npts=npts, length=length, gls=gls)
+    print("glsmask.npz", n, "masks; lengths", length[:4], "gls", gls[0, :4], "failed", int(np.isnan(length).sum()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask"]
     for w in which:
         globals()["golden_" + w]()

@@ -279,3 +279,27 @@ def test_segmentation_postprocessing_matches_reference():
     # torch's fp32 mean over the samples vs numpy's: a few ulp of the mean, amplified by |d entropy / d p| near 0 and 1
     assert np.abs(ent - g["entropy"]).max() < 2e-6
     assert ent.dtype == np.float32 and (ent[:, :10] == 0).all() and (ent[:, :, -10:] == 0).all()
+
+
+def test_mask_gls_matches_reference():
+    """oracle polar corners / base-less contour / EchoMeasure.gls vs the executed reference (find_contours restated)."""
+    g = np.load(os.path.join(G, "glsmask.npz"))
+    masks = _unpack(g["masks"]).astype(bool)
+    for i, m in enumerate(masks):
+        try:
+            left, right, _ = port.polar_base_corners(m)
+            c = port.endo_contour_without_base(m)
+            length = port.lv_longitudinal_length(m)
+        except (RuntimeError, IndexError):
+            assert np.isnan(g["length"][i]), i
+            continue
+        assert np.array_equal(np.array([left, right]), g["corners"][i]), i
+        assert len(c) == int(g["npts"][i]) and length == float(g["length"][i]), i
+    T = g["gls"].shape[1]
+    for v in range(2):
+        for t in range(T):
+            try:
+                got = port.echo_gls(np.stack([masks[(2 * v) * T + t], masks[(2 * v + 1) * T + t]]))[1]
+            except (RuntimeError, IndexError):
+                got = np.nan
+            assert (np.isnan(got) and np.isnan(g["gls"][v, t])) or got == g["gls"][v, t]
