@@ -46,6 +46,30 @@ int main(void) {
     for (int i = 0; i < 65536; ++i) { total += h_count[i]; pred += h_pred[i]; }
     printf("abi %d sm %d area %d %d %d count_sum %ld pred_sum %ld\n", cub200_abi_version(), cub200_built_for_sm(), h_area[0], h_area[1],
            h_area[2], total, pred);
+    /* mask-based LV length of the same three masks (weights evaluated in the kernel: no host table), then the largest
+     * blob of the masks fed back as 0/1 probabilities (must reproduce their areas) */
+    double* d_len; void* d_ws; float* d_prob; uint32_t* d_blob; int32_t* d_barea; void* d_ws2;
+    CK(cudaMalloc((void**)&d_len, n * 8));
+    CK(cudaMalloc(&d_ws, (size_t)cub200_simpson_workspace_bytes(n)));
+    rc = cub200_mask_lv_length(d_m, n, 5e-3, NULL, 1.0, 1.0, d_len, NULL, NULL, d_ws, NULL);
+    if (rc) { printf("lv_length rc %d %s\n", rc, cub200_last_error()); return 3; }
+    double h_len[3];
+    CK(cudaMemcpy(h_len, d_len, sizeof(h_len), cudaMemcpyDeviceToHost));
+    static uint32_t h_m[3 * CUB200_MASK_WORDS];
+    static float h_prob[3 * 65536];
+    CK(cudaMemcpy(h_m, d_m, sizeof(h_m), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i)
+        for (int p = 0; p < 65536; ++p) h_prob[i * 65536 + p] = (float)((h_m[i * CUB200_MASK_WORDS + (p >> 5)] >> (p & 31)) & 1u);
+    CK(cudaMalloc((void**)&d_prob, sizeof(h_prob)));
+    CK(cudaMalloc((void**)&d_blob, sizeof(h_m)));
+    CK(cudaMalloc((void**)&d_barea, n * 4));
+    CK(cudaMalloc(&d_ws2, (size_t)cub200_seg_blob_workspace_bytes(n)));
+    CK(cudaMemcpy(d_prob, h_prob, sizeof(h_prob), cudaMemcpyHostToDevice));
+    rc = cub200_seg_largest_blob(d_prob, n, d_blob, d_barea, d_ws2, NULL);
+    if (rc) { printf("largest_blob rc %d %s\n", rc, cub200_last_error()); return 3; }
+    int32_t h_barea[3];
+    CK(cudaMemcpy(h_barea, d_barea, sizeof(h_barea), cudaMemcpyDeviceToHost));
+    printf("lv_length %.12f %.12f %.12f blob_area %d %d %d\n", h_len[0], h_len[1], h_len[2], h_barea[0], h_barea[1], h_barea[2]);
     /* error behaviour: invalid arguments come back as codes, never as exceptions */
     printf("einval %d empty %d\n", cub200_rasterize_contours(NULL, 1, 1, NULL, NULL, NULL, 0, NULL),
            cub200_rasterize_contours(NULL, 0, 1, NULL, NULL, NULL, 0, NULL));

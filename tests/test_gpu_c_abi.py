@@ -40,3 +40,8 @@ def test_plain_c_consumer(tmp_path):
     masks = np.stack([port.us_contour_to_mask(lv + np.array([i, 0.0])) for i in range(3)])
     assert count_sum == int(masks.sum()) and pred_sum == int((masks.mean(0).round()).sum())
     assert "einval -1 empty 0" in out.stdout
+    line = [l for l in out.stdout.splitlines() if l.startswith("lv_length")][0].split()
+    lengths = [float(v) for v in line[1:4]]
+    want_len = [port.lv_longitudinal_length(m.astype(bool)) for m in masks]
+    np.testing.assert_allclose(lengths, want_len, rtol=1e-11)
+    assert [int(v) for v in line[5:8]] == want
