@@ -477,12 +477,19 @@ static int sm_count(int* out) {
 
 }  // namespace cub200
 
+// Workspace layout: overflow queue | run-table slots of the overflow kernel | per-warp slots of seg_blob_kernel, each
+// region sized by the number of CTAs that can actually be launched for n_samples.
+static int64_t seg_queue_bytes(int64_t n_samples) { return ((n_samples + 1) * 4 + 15) / 16 * 16; }
+static int64_t seg_overflow_ctas(int64_t n_samples) { return n_samples < cub200::SG_OVERFLOW_CTAS ? n_samples : cub200::SG_OVERFLOW_CTAS; }
+static int64_t seg_blob_ctas_max(int64_t n_samples) {
+    const int64_t need = (n_samples + cub200::SG_WARPS - 1) / cub200::SG_WARPS;
+    return need < cub200::SG_MAX_GRID ? need : cub200::SG_MAX_GRID;
+}
+
 extern "C" int64_t cub200_seg_blob_workspace_bytes(int64_t n_samples) {
     if (n_samples < 0) return CUB200_EINVAL;
-    // overflow queue (count + one id per sample, padded to 16 bytes) + the overflow kernel's run-table slots
-    const int64_t queue = ((n_samples + 1) * 4 + 15) / 16 * 16;
-    return queue + (int64_t)cub200::SG_OVERFLOW_CTAS * 3 * cub200::SG_MAX_RUNS * 4 +
-           (int64_t)cub200::SG_MAX_GRID * cub200::SG_WARPS * 3 * cub200::SG_WARP_SLOT * 4;
+    return seg_queue_bytes(n_samples) + seg_overflow_ctas(n_samples) * 3 * cub200::SG_MAX_RUNS * 4 +
+           seg_blob_ctas_max(n_samples) * cub200::SG_WARPS * 3 * cub200::SG_WARP_SLOT * 4;
 }
 
 extern "C" int cub200_seg_largest_blob(const float* probs, int64_t n_samples, uint32_t* masks_out, int32_t* area_out,
@@ -499,16 +506,15 @@ extern "C" int cub200_seg_largest_blob(const float* probs, int64_t n_samples, ui
     int sms = 0;
     if (int rc = sm_count(&sms)) return rc;
     int32_t* overflow = reinterpret_cast<int32_t*>(workspace);
-    const int64_t queue = ((n_samples + 1) * 4 + 15) / 16 * 16;
-    uint32_t* slots = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + queue);
-    uint32_t* warp_slots = slots + (int64_t)SG_OVERFLOW_CTAS * 3 * SG_MAX_RUNS;
+    uint32_t* slots = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + seg_queue_bytes(n_samples));
+    uint32_t* warp_slots = slots + seg_overflow_ctas(n_samples) * 3 * SG_MAX_RUNS;
     CUB200_CUDA_OK(cudaMemsetAsync(overflow, 0, 4, st));
-    const int64_t need = (n_samples + SG_WARPS - 1) / SG_WARPS;
-    const int64_t cap = sms * 4 < SG_MAX_GRID ? sms * 4 : SG_MAX_GRID;
+    const int64_t need = seg_blob_ctas_max(n_samples);
+    const int64_t cap = (int64_t)sms * 4;
     seg_blob_kernel<<<(unsigned)(need < cap ? need : cap), SG_THREADS, smem, st>>>(probs, n_samples, masks_out, area_out, overflow,
                                                                                   warp_slots);
     if (int rc = check_launch("seg_blob_kernel")) return rc;
-    seg_blob_overflow_kernel<<<SG_OVERFLOW_CTAS, 32, 0, st>>>(probs, masks_out, area_out, overflow, slots);
+    seg_blob_overflow_kernel<<<(unsigned)seg_overflow_ctas(n_samples), 32, 0, st>>>(probs, masks_out, area_out, overflow, slots);
     return check_launch("seg_blob_overflow_kernel");
 }
 

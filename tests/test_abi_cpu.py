@@ -101,4 +101,4 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_seg_largest_blob(None, 0, None, None, None, None) == 0
     assert l.cub200_seg_entropy(None, None, 1, 1, 10, None, None, None, None, None) == E
     assert l.cub200_seg_entropy(None, None, 0, 1, 10, None, None, None, None, None) == 0
-    assert l.cub200_seg_blob_workspace_bytes(3) == 16 + 64 * 3 * 32768 * 4 + 1024 * 4 * 3 * 2048 * 4
+    assert l.cub200_seg_blob_workspace_bytes(3) == 16 + 3 * 3 * 32768 * 4 + 1 * 4 * 3 * 2048 * 4

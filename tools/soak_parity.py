@@ -37,11 +37,31 @@ def _skew_one(args):
     return port.skew_psm_sample(model, mu, cov, al, z, qf, store=np.float32, return_indices=True)
 
 
+def _segblob_chunk(samples):
+    from oracle import port
+    return np.packbits(port.seg_blob_masks(samples), axis=-1, bitorder="little")
+
+
+def _gls_chunk(masks):
+    from oracle import port
+    out = []
+    for m in masks:
+        try:
+            left, right, _ = port.polar_base_corners(m)
+            tie = port.base_corner_tie(m)
+            out.append([port.lv_longitudinal_length(m), left[0], left[1], right[0], right[1], float(tie)])
+        except (RuntimeError, IndexError):
+            out.append([np.nan] * 5 + [0.0])
+    return np.array(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--contours", type=int, default=20000)
     ap.add_argument("--simpson", type=int, default=1600)
     ap.add_argument("--skew-images", type=int, default=24)
+    ap.add_argument("--seg-samples", type=int, default=0)
+    ap.add_argument("--gls-masks", type=int, default=0)
     a = ap.parse_args()
     import torch, synth
     from contouring_uncertainty_b200 import engine as E
@@ -51,8 +71,42 @@ def main():
     rng = np.random.default_rng(2026)
     b = synth.LV_EXAMPLE_SHAPE
 
+    # 4. segmentation samples: hole fill + largest blob bit-exact (speckled blobs, islands, dips; every 8th pure noise)
+    if a.seg_samples:
+        n = a.seg_samples
+        t0 = time.time()
+        seg = synth.segmentation_samples(n // 16, 16, seed=4242, adversarial=False)
+        seg[:, ::8] = (rng.random(seg[:, ::8].shape) < rng.uniform(0.05, 0.95, (n // 16, 2, 1, 1))).astype(np.float32) * 0.8
+        got = E.seg_largest_blob(torch.from_numpy(seg).to(dev)).cpu().numpy().view(np.uint8).reshape(-1, 256, 32)
+        want = np.concatenate(pool.map(_segblob_chunk, np.array_split(seg.reshape(-1, 256, 256), workers * 4)))
+        print(json.dumps({"check": "segmentation samples: largest blob of the hole-filled mask bit-exact vs oracle", "samples": int(len(want)),
+                          "mismatching_masks": int((got != want).any((1, 2)).sum()), "seconds": round(time.time() - t0, 1)}), flush=True)
+
+    # 5. mask-based LV length (EchoMeasure.gls pieces): same failures, same base corners, lengths to 1e-12
+    if a.gls_masks:
+        n = a.gls_masks
+        t0 = time.time()
+        c = b[None] + rng.normal(0, 3.0, (n, 21, 2)) + rng.normal(0, 8.0, (n, 1, 2))
+        c[n // 2:] = (c[n // 2:] - c[n // 2:].mean(1, keepdims=True)) * rng.uniform(0.4, 1.15, (n - n // 2, 1, 1)) + 128
+        masks, _ = E.rasterize_contours(torch.from_numpy(c.astype(np.float32)).to(dev))
+        length, corners, _ = E.mask_lv_length(masks, return_corners=True)
+        m_np = E.unpack_masks(masks).cpu().numpy().astype(bool)
+        w = np.concatenate(pool.map(_gls_chunk, np.array_split(m_np, workers * 4)))
+        g_len, g_cor = length.cpu().numpy(), corners.cpu().numpy().reshape(n, 4)
+        tie = w[:, 5] > 0
+        nan_mismatch = int((np.isnan(g_len) != np.isnan(w[:, 0])).sum())
+        ok = ~np.isnan(w[:, 0]) & ~np.isnan(g_len) & ~tie
+        print(json.dumps({"check": "mask LV length: failures / base corners identical, lengths <= 1e-12 rel vs oracle", "masks": n,
+                          "reference_raises": int(np.isnan(w[:, 0]).sum()), "nan_mismatches": nan_mismatch, "exact_ties_skipped": int(tie.sum()),
+                          "corner_mismatches": int((g_cor[ok] != w[ok, 1:5]).any(1).sum()),
+                          "max_rel_length_diff": float((np.abs(g_len[ok] - w[ok, 0]) / w[ok, 0]).max()) if ok.any() else 0.0,
+                          "seconds": round(time.time() - t0, 1)}), flush=True)
+
     # 1. rasteriser: random + wild + near-border + half-integer contours, masks bit-exact
     n = a.contours
+    if n == 0:
+        pool.close()
+        return
     kind = rng.integers(0, 5, n)
     c = b[None] + rng.normal(0, 3.0, (n, 21, 2)) + rng.normal(0, 6.0, (n, 1, 2))
     c[kind == 1] = b[None] + rng.normal(0, 11.0, ((kind == 1).sum(), 21, 2))                       # self-intersecting
