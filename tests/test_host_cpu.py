@@ -52,3 +52,36 @@ def test_batch_result_shape_asserts():
     BatchResult(id="x", img=z, gt=z, pred=z, labels=["lv"], uncertainty_map=z)
     with pytest.raises(AssertionError):
         BatchResult(id="x", img=z, gt=z, pred=z[0], labels=["lv"], uncertainty_map=z)
+
+
+def test_gls_gauss_table_is_scipys_kernel():
+    """The weight table handed to lv_length_kernel == scipy.ndimage's own Gaussian kernel (right half, centre first)."""
+    from scipy.ndimage._filters import _gaussian_kernel1d
+
+    from contouring_uncertainty_b200.engine import GLS_TABLE_STRIDE, SIMPSON_MAX_POINTS, gls_gauss_table
+
+    tab = gls_gauss_table(5e-3, "cpu").numpy()
+    assert tab.shape == (SIMPSON_MAX_POINTS + 1, GLS_TABLE_STRIDE)
+    for n in (3, 24, 25, 100, 333, 547, 1000, 2048):
+        sigma = n * 5e-3
+        lw = int(4.0 * sigma + 0.5)
+        assert lw < GLS_TABLE_STRIDE
+        if lw == 0:
+            assert tab[n, 0] == 1.0 and not tab[n, 1:].any()
+            continue
+        w = _gaussian_kernel1d(sigma, 0, lw)[::-1]
+        assert np.array_equal(tab[n, :lw + 1], w[lw:]) and not tab[n, lw + 1:].any()
+
+
+def test_seg_and_gls_wrappers_refuse_cpu_tensors():
+    import pytest
+    import torch
+
+    from contouring_uncertainty_b200 import engine as E
+
+    with pytest.raises(ValueError, match="no CPU implementation"):
+        E.seg_largest_blob(torch.zeros((1, 256, 256)))
+    with pytest.raises(ValueError, match="no CPU implementation"):
+        E.mask_lv_length(torch.zeros((1, 2048), dtype=torch.int32))
+    with pytest.raises(ValueError, match="no CPU implementation"):
+        E.seg_entropy(torch.zeros((1, 1, 256, 256)), torch.zeros((1, 1, 2048), dtype=torch.int32))
