@@ -95,8 +95,13 @@ __device__ __forceinline__ uint32_t nibble_of(const float4& v) {
 __device__ __forceinline__ void load_rows(const float4* __restrict__ src, int row0, float4 (&v)[4][2]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#ifdef CUB200_SG_LDG
+        v[i][0] = __ldg(src + (row0 + i) * 64);
+        v[i][1] = __ldg(src + (row0 + i) * 64 + 32);
+#else
         v[i][0] = ld_stream_f4(src + (row0 + i) * 64);
         v[i][1] = ld_stream_f4(src + (row0 + i) * 64 + 32);
+#endif
     }
 }
 
@@ -298,7 +303,10 @@ __device__ __forceinline__ void store_mask(const uint32_t* bmp, uint32_t* __rest
     }
 }
 
-__global__ void __launch_bounds__(SG_THREADS, 4)
+#ifndef CUB200_SG_MINBLOCKS
+#define CUB200_SG_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(SG_THREADS, CUB200_SG_MINBLOCKS)
 seg_blob_kernel(const float* __restrict__ probs, int64_t n_samples, uint32_t* __restrict__ masks_out,
                 int32_t* __restrict__ area_out, int32_t* __restrict__ overflow /* [0] = count, then sample ids */,
                 uint32_t* __restrict__ warp_slots) {
@@ -510,7 +518,7 @@ extern "C" int cub200_seg_largest_blob(const float* probs, int64_t n_samples, ui
     uint32_t* warp_slots = slots + seg_overflow_ctas(n_samples) * 3 * SG_MAX_RUNS;
     CUB200_CUDA_OK(cudaMemsetAsync(overflow, 0, 4, st));
     const int64_t need = seg_blob_ctas_max(n_samples);
-    const int64_t cap = (int64_t)sms * 4;
+    const int64_t cap = (int64_t)sms * CUB200_SG_MINBLOCKS;
     seg_blob_kernel<<<(unsigned)(need < cap ? need : cap), SG_THREADS, smem, st>>>(probs, n_samples, masks_out, area_out, overflow,
                                                                                   warp_slots);
     if (int rc = check_launch("seg_blob_kernel")) return rc;
