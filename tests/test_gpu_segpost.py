@@ -63,6 +63,21 @@ def test_random_samples_against_oracle():
     assert np.abs(out["mean"].cpu().numpy() - mean64).max() < 1e-7
 
 
+@pytest.mark.parametrize("T", [1, 5, 33, 70])
+def test_sample_counts_off_the_chunk_grid(T):
+    """The entropy kernel walks the samples in chunks of 32 and groups of 4: counts that fit neither."""
+    from contouring_uncertainty_b200 import engine as E
+
+    samples = synth.segmentation_samples(2, T, seed=100 + T, adversarial=False)
+    t = torch.from_numpy(samples).to(_dev())
+    masks = E.seg_largest_blob(t)
+    out = E.seg_entropy(t, masks, pad=10, return_pred_samples=True, return_samples=True, return_mean=True)
+    post, ent, pred_samples = port.seg_postprocess(samples.reshape(2, 1, T, 1, 256, 256))
+    assert np.array_equal(E.unpack_masks(out["pred_samples"]).cpu().numpy().astype(bool), pred_samples.reshape(2, T, 256, 256))
+    assert np.array_equal(out["samples"].cpu().numpy(), post.reshape(2, T, 256, 256))
+    assert np.abs(out["entropy"].cpu().numpy() - ent).max() < 2e-6
+
+
 def test_big_blob_mirror_and_edge_cases():
     from contouring_uncertainty_b200 import engine as E
     from contouring_uncertainty_b200.task.segmentation.utils import big_blob
