@@ -102,3 +102,40 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_seg_entropy(None, None, 1, 1, 10, None, None, None, None, None) == E
     assert l.cub200_seg_entropy(None, None, 0, 1, 10, None, None, None, None, None) == 0
     assert l.cub200_seg_blob_workspace_bytes(3) == 16 + 3 * 3 * 32768 * 4 + 1 * 4 * 3 * 2048 * 4
+
+
+def test_binding_tables_agree_with_the_header_and_the_integration_guide():
+    """Every prototype of cub200.h has as many parameters as its ctypes signature, with pointers / integers / doubles in the
+    same places; the stub printed in INTEGRATION.md is the same table."""
+    import ctypes as C
+
+    from contouring_uncertainty_b200 import _native
+
+    src = open(os.path.join(ROOT, "include", "cub200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\bint\s+(cub200_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    seen = 0
+    for name, params in protos:
+        if name not in _native.SIGNATURES:
+            continue
+        seen += 1
+        want = []
+        for p in [q.strip() for q in params.split(",")]:
+            if "*" in p:
+                want.append(C.c_void_p)
+            elif p.startswith("double"):
+                want.append(C.c_double)
+            elif p.startswith("uint64_t"):
+                want.append(C.c_uint64)
+            elif p.startswith("int64_t"):
+                want.append(C.c_int64)
+            elif p.startswith("int "):
+                want.append(C.c_int)
+            else:
+                raise AssertionError(f"{name}: unrecognised parameter '{p}'")
+        assert want == _native.SIGNATURES[name], name
+    assert seen == len(_native.SIGNATURES)
+    kinds = {"vp": C.c_void_p, "i32": C.c_int, "i64": C.c_int64, "u64": C.c_uint64, "C.c_double": C.c_double}
+    guide = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name, args in re.findall(r"lib\.(cub200_\w+)\.argtypes = \[([^\]]*)\]", guide):
+        assert [kinds[a.strip()] for a in args.split(",")] == _native.SIGNATURES[name], name
