@@ -19,11 +19,16 @@
 // Two kernels.  seg_blob_kernel: ONE WARP PER SAMPLE streams the sample once (HBM-bound: 256 KiB per sample),
 // packs it into a 256x256 bitmap in shared memory, floods the background (flood.cuh), extracts the row runs of
 // the filled mask and joins them with a lock-free union-find -- components of a segmentation output are a few
-// hundred runs, not 65 536 pixels.  It writes the bit-packed blob mask (8 KiB per sample).  Samples with more
-// runs than the shared-memory table holds (noise) are queued and redone by seg_blob_overflow_kernel with the
-// tables in a global-memory slot.  seg_entropy_kernel: one warp per (image, row) walks the samples, reads the
+// hundred runs, not 65 536 pixels.  It writes the bit-packed blob mask (8 KiB per sample).  Run tables: 1088 runs in
+// shared memory, up to 2048 in a per-warp slot of global memory, anything beyond (noise) is queued and redone by
+// seg_blob_overflow_kernel with full-size tables.  Three CTAs of four warps per SM: the kernel needs ~168 registers
+// and loses more to spills at 128 than to the fourth CTA it gives up (measured).  seg_entropy_kernel: one warp per (image, row) walks the samples, reads the
 // probabilities only where the blob mask has pixels, sums them in fp64 in sample order and writes the entropy.
 #include "flood.cuh"
+
+#ifndef CUB200_SG_MINBLOCKS
+#define CUB200_SG_MINBLOCKS 3
+#endif
 
 namespace cub200 {
 
@@ -32,7 +37,7 @@ constexpr int SG_THREADS = SG_WARPS * 32;
 constexpr int SG_CAP = BMP_WORDS / 2;            // 1088 runs per sample held in shared memory (see SegScratch)
 constexpr int SG_WARP_SLOT = 2048;               // runs per sample held in the warp's global-memory slot
 constexpr int SG_MAX_RUNS = 128 * 256;           // most runs a 256x256 mask can have
-constexpr int SG_MAX_GRID = 1024;                // CTAs of seg_blob_kernel at most (4 per SM)
+constexpr int SG_MAX_GRID = 1024;                // CTAs of seg_blob_kernel at most (it launches CUB200_SG_MINBLOCKS per SM)
 constexpr int SG_OVERFLOW_CTAS = 64;             // warps (one per CTA) of the overflow kernel, one global slot each
 
 struct __align__(16) SegScratch {
@@ -95,13 +100,8 @@ __device__ __forceinline__ uint32_t nibble_of(const float4& v) {
 __device__ __forceinline__ void load_rows(const float4* __restrict__ src, int row0, float4 (&v)[4][2]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#ifdef CUB200_SG_LDG
-        v[i][0] = __ldg(src + (row0 + i) * 64);
-        v[i][1] = __ldg(src + (row0 + i) * 64 + 32);
-#else
-        v[i][0] = ld_stream_f4(src + (row0 + i) * 64);
+        v[i][0] = ld_stream_f4(src + (row0 + i) * 64);           // (plain __ldg, allocating in L1: 5 % slower)
         v[i][1] = ld_stream_f4(src + (row0 + i) * 64 + 32);
-#endif
     }
 }
 
@@ -303,9 +303,6 @@ __device__ __forceinline__ void store_mask(const uint32_t* bmp, uint32_t* __rest
     }
 }
 
-#ifndef CUB200_SG_MINBLOCKS
-#define CUB200_SG_MINBLOCKS 3
-#endif
 __global__ void __launch_bounds__(SG_THREADS, CUB200_SG_MINBLOCKS)
 seg_blob_kernel(const float* __restrict__ probs, int64_t n_samples, uint32_t* __restrict__ masks_out,
                 int32_t* __restrict__ area_out, int32_t* __restrict__ overflow /* [0] = count, then sample ids */,
