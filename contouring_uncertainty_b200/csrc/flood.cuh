@@ -78,4 +78,66 @@ __device__ __forceinline__ uint32_t flood_sweep(uint32_t (&R)[8][8], const uint4
     return changed;
 }
 
+
+// binary_fill_holes' flood for the bitmap the warp holds (band4 = the lane's 8-row band of OBSTACLE pixels): R = the free
+// pixels reachable from outside the frame through 4-connected free pixels.  Rows are seeded from the left and right
+// frame borders (everything below the lowest / above the highest obstacle of the row; rows 0 and 255 everywhere), then
+// alternating Gauss-Seidel sweeps propagate vertically until no lane advances.
+__device__ __forceinline__ void flood_background(uint32_t (&R)[8][8], const uint4* band4, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
+        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t rowor = (B[0] | B[1] | B[2]) | (B[3] | B[4] | B[5]) | (B[6] | B[7]);
+        const bool border_row = (lane == 0 && i == 0) || (lane == 31 && i == 7);
+        if (rowor == 0u) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) R[i][w] = 0xffffffffu;
+        } else if (border_row) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) R[i][w] = ~B[w];
+        } else {
+            // seeded from the left and right frame borders: below the lowest / above the highest set bit of the row
+            uint32_t X[8];
+            asm("sub.cc.u32 %0, %1, 1;" : "=r"(X[0]) : "r"(B[0]));
+#pragma unroll
+            for (int w = 1; w < 8; ++w) asm("subc.cc.u32 %0, %1, 0;" : "=r"(X[w]) : "r"(B[w]));
+            bool seen = false;
+#pragma unroll
+            for (int w = 7; w >= 0; --w) {
+                const uint32_t smear = __funnelshift_rc(0xffffffffu, 0u, __clz(B[w]));
+                R[i][w] = (X[w] & ~B[w]) | (seen ? 0u : ~smear);
+                seen |= (B[w] != 0u);
+            }
+        }
+    }
+    for (;;) {
+        uint32_t touched = flood_sweep<0>(R, band4, lane);
+        if (!__any_sync(FULL, touched != 0u)) break;
+        touched = flood_sweep<1>(R, band4, lane);
+        if (!__any_sync(FULL, touched != 0u)) break;
+    }
+}
+
+// skimage.draw.line (Bresenham) from (r0, c0) to (r1, c1) in closed form, the pixels shared among the lanes and clipped to
+// the frame as the reference's rr.clip / cc.clip do: pixel i < dmaj has major = m0 + i * smaj,
+// minor = n0 + smin * floor((2 * dmin * i + dmaj) / (2 * dmaj)); pixel dmaj = (r1, c1).
+__device__ __forceinline__ void draw_line_clipped(uint32_t* bmp, int r0, int c0, int r1, int c1, int lane) {
+    const int dr = abs(r1 - r0), dc = abs(c1 - c0);
+    const int sc = (c1 - c0) > 0 ? 1 : -1, sr = (r1 - r0) > 0 ? 1 : -1;
+    const bool steep = dr > dc;
+    const int dmaj = steep ? dr : dc, dmin = steep ? dc : dr;
+    for (int i = lane; i <= dmaj; i += 32) {
+        int rr, cc;
+        if (i == dmaj) { rr = r1; cc = c1; }
+        else {
+            const int nmin = (2 * dmin * i + dmaj) / (2 * dmaj);
+            if (steep) { rr = r0 + i * sr; cc = c0 + nmin * sc; }
+            else { cc = c0 + i * sc; rr = r0 + nmin * sr; }
+        }
+        rr = min(max(rr, 0), 255); cc = min(max(cc, 0), 255);
+        atomicOr(&bmp[bmp_addr(rr, cc >> 5)], 1u << (cc & 31));
+    }
+}
+
 }  // namespace cub200

@@ -137,39 +137,7 @@ __device__ int fill_and_keep_largest(uint32_t* bmp, uint16_t* row_base, const Ru
     // ---- 2. background flood: R = reached from outside the frame
     uint32_t R[8][8];
     const uint4* band4 = reinterpret_cast<const uint4*>(bmp + lane * BAND_STRIDE);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
-        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const uint32_t rowor = (B[0] | B[1] | B[2]) | (B[3] | B[4] | B[5]) | (B[6] | B[7]);
-        const bool border_row = (lane == 0 && i == 0) || (lane == 31 && i == 7);
-        if (rowor == 0u) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) R[i][w] = 0xffffffffu;
-        } else if (border_row) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) R[i][w] = ~B[w];
-        } else {
-            // seeded from the left and right frame borders: below the lowest / above the highest set bit of the row
-            uint32_t X[8];
-            asm("sub.cc.u32 %0, %1, 1;" : "=r"(X[0]) : "r"(B[0]));
-#pragma unroll
-            for (int w = 1; w < 8; ++w) asm("subc.cc.u32 %0, %1, 0;" : "=r"(X[w]) : "r"(B[w]));
-            bool seen = false;
-#pragma unroll
-            for (int w = 7; w >= 0; --w) {
-                const uint32_t smear = __funnelshift_rc(0xffffffffu, 0u, __clz(B[w]));
-                R[i][w] = (X[w] & ~B[w]) | (seen ? 0u : ~smear);
-                seen |= (B[w] != 0u);
-            }
-        }
-    }
-    for (;;) {
-        uint32_t touched = flood_sweep<0>(R, band4, lane);
-        if (!__any_sync(FULL, touched != 0u)) break;
-        touched = flood_sweep<1>(R, band4, lane);
-        if (!__any_sync(FULL, touched != 0u)) break;
-    }
+    flood_background(R, band4, lane);
     // ---- the filled mask M = ~R replaces the foreground bitmap (frees the 64 registers of R)
     {
         uint4* band_w = reinterpret_cast<uint4*>(bmp + lane * BAND_STRIDE);

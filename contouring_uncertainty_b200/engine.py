@@ -199,6 +199,31 @@ def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, ret
     return masks, area
 
 
+RASTER_MAX_POINTS = 64
+
+
+def rasterize_contours_generic(contours: torch.Tensor, round_landmarks: bool = True, reconstruction_type: str = "spline",
+                               return_masks: bool = True):
+    """reconstruction / linear_reconstruction (cu/utils/contour.py:28-53) for contours of any size: contours (M, K, 2) fp32 or
+    fp64 with 4 <= K <= 64 -> (masks (M, 2048) int32 bit-packed | None, area (M) int32).  K == 21 may use rasterize_contours."""
+    if reconstruction_type not in ("spline", "linear"):
+        raise ValueError("reconstruction_type must be 'spline' or 'linear'")
+    f64 = isinstance(contours, torch.Tensor) and contours.dtype == torch.float64
+    contours = nat.require_cuda(contours, torch.float64 if f64 else torch.float32, "contours")
+    if contours.dim() != 3 or contours.shape[2] != 2 or not (4 <= contours.shape[1] <= RASTER_MAX_POINTS):
+        raise ValueError(f"contours must be (M, K, 2) with 4 <= K <= {RASTER_MAX_POINTS}, got {tuple(contours.shape)}")
+    m, k = int(contours.shape[0]), int(contours.shape[1])
+    dev = contours.device
+    masks = torch.empty((m, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
+    area = torch.empty((m,), dtype=torch.int32, device=dev)
+    flags = 3 if reconstruction_type == "linear" else int(bool(round_landmarks))
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_rasterize_contours_generic(nat.ptr(contours), int(f64), m, k, flags, nat.ptr(masks), nat.ptr(area),
+                                                         nat.stream_ptr(dev))
+    nat.check(rc, "cub200_rasterize_contours_generic")
+    return masks, area
+
+
 def unpack_masks(masks: torch.Tensor) -> torch.Tensor:
     """(..., 2048) int32 bit-packed -> (..., 256, 256) uint8 (host or device; plain torch bit ops)."""
     w = masks.reshape(masks.shape[:-1] + (HW, 8, 1))

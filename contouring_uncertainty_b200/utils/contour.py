@@ -6,12 +6,19 @@ from .. import engine as E
 
 
 def reconstruction(points, height, width):
-    """contour.py:28-40: spline raster of the UNROUNDED points + closing line + hole fill -> (256,256) int mask."""
+    """contour.py:28-40: spline raster of the UNROUNDED points + closing line + hole fill -> (256,256) int mask.
+    Any number of points from 4 to 64 (the 21-point LV contour takes the hot-path rasteriser)."""
     if (height, width) != (E.HW, E.HW):
         raise NotImplementedError("256 x 256 frames only")
     dev = torch.device("cuda", torch.cuda.current_device())
-    c = torch.as_tensor(np.asarray(points, dtype=np.float64)).reshape(1, E.K, 2).to(dev)
-    masks, _ = E.rasterize_contours(c, round_landmarks=False)
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[1] != 2:
+        raise ValueError("points must be (K, 2)")
+    c = torch.as_tensor(pts)[None].to(dev)
+    if len(pts) == E.K:
+        masks, _ = E.rasterize_contours(c, round_landmarks=False)
+    else:
+        masks, _ = E.rasterize_contours_generic(c, round_landmarks=False)
     return E.unpack_masks(masks)[0].cpu().numpy().astype(int)
 
 
@@ -20,6 +27,12 @@ def linear_reconstruction(points, height, width):
     if (height, width) != (E.HW, E.HW):
         raise NotImplementedError("256 x 256 frames only")
     dev = torch.device("cuda", torch.cuda.current_device())
-    c = torch.as_tensor(np.asarray(points, dtype=np.float64)).reshape(1, E.K, 2).to(dev)
-    masks, _ = E.rasterize_contours(c, reconstruction_type="linear")
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[1] != 2:
+        raise ValueError("points must be (K, 2)")
+    c = torch.as_tensor(pts)[None].to(dev)
+    if len(pts) == E.K:
+        masks, _ = E.rasterize_contours(c, reconstruction_type="linear")
+    else:
+        masks, _ = E.rasterize_contours_generic(c, reconstruction_type="linear")
     return E.unpack_masks(masks)[0].cpu().numpy().astype(int)

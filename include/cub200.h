@@ -439,6 +439,17 @@ int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, double smoothi
                           double spacing_row, double spacing_col, double* length_out, double* corners_out, int32_t* npts_out,
                           void* workspace, void* stream);
 
+/*
+ * Rasteriser for contours with any number of points: reconstruction / linear_reconstruction   cu/utils/contour.py:28-53
+ * as LungContourToMask (cu/data/lung/utils.py:25-69) uses them per structure (44 / 50 / 26 points).
+ *   contours (n, n_points, 2) (x, y), fp32 (is_f64 = 0) or fp64 (is_f64 = 1); 4 <= n_points <= CUB200_RASTER_MAX_POINTS;
+ *   flags as round_landmarks of cub200_rasterize_contours (bit 0 = round the points first, bit 1 = linear).
+ *   masks_out (n, 2048) u32 bit-packed and / or area_out (n) i32.
+ */
+#define CUB200_RASTER_MAX_POINTS 64
+int cub200_rasterize_contours_generic(const void* contours, int is_f64, int64_t n, int n_points, int flags, uint32_t* masks_out,
+                                      int32_t* area_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1261,3 +1261,17 @@ def echo_gls(segmentation: np.ndarray, voxelspacing=(1, 1)) -> np.ndarray:
     """measure.py:320-366 (EchoMeasure.gls, myo_labels=None): (N,H,W) masks, first frame = ED -> (N,) strain in percent."""
     lengths = np.array([lv_longitudinal_length(f, voxelspacing) for f in segmentation])
     return (lengths - lengths[0]) / lengths[0] * 100
+
+
+def lung_contour_to_mask(landmarks: np.ndarray, apply_argmax: bool = True, reconstruction_type: str = "spline") -> np.ndarray:
+    """cu/data/lung/utils.py:25-69: 120 rounded landmarks = right lung (44) + left lung (50) + heart (26) (config.py:35-37),
+    each through reconstruction / linear_reconstruction; the lungs ADD into channel 1, the heart is channel 2."""
+    rec = linear_reconstruction if reconstruction_type == "linear" else reconstruction
+    lm = np.asarray(landmarks).round().astype(int).squeeze()
+    rl, ll, h = lm[:44], lm[44:94], lm[94:120]
+    seg = np.zeros((3, 256, 256), dtype=int)
+    seg[1] += rec(rl, 256, 256)
+    seg[1] += rec(ll, 256, 256)
+    seg[2] = rec(h, 256, 256)
+    seg[0] = seg.sum(0) == 0
+    return seg.argmax(0) if apply_argmax else seg

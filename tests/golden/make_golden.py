@@ -645,7 +645,32 @@ def golden_glsmask():
     print("glsmask.npz", n, "masks; lengths", length[:4], "gls", gls[0, :4], "failed", int(np.isnan(length).sum()))
 
 
+def golden_generic():
+    """reconstruction / linear_reconstruction for contours that are not 21 points long, and LungContourToMask
+    (contour_uncertainty/data/lung/utils.py:25-69), executed as they are."""
+    from contour_uncertainty.data.lung.utils import LungContourToMask
+    from contour_uncertainty.utils.contour import linear_reconstruction, reconstruction
+
+    out = {}
+    for k in (4, 5, 8, 26, 44, 50, 64):
+        c = np.concatenate([synth.closed_contours(6, k, seed=300 + k), synth.closed_contours(6, k, seed=400 + k, wild=True)])
+        c[1] = np.round(c[1]) + 0.5                                  # rounding ties
+        c[2, 3] = c[2, 2]                                            # zero chord -> FITPACK raises -> raw points
+        spl = np.array([reconstruction(x, 256, 256) for x in c]).astype(np.uint8)
+        lin = np.array([linear_reconstruction(x, 256, 256) for x in c]).astype(np.uint8)
+        out[f"contours_{k}"] = c
+        out[f"spline_{k}"] = np.packbits(spl, axis=-1, bitorder="little")
+        out[f"linear_{k}"] = np.packbits(lin, axis=-1, bitorder="little")
+    lm = synth.lung_landmarks(4, seed=77)
+    out["lung_landmarks"] = lm
+    out["lung_argmax"] = np.array([LungContourToMask.__call__(x) for x in lm]).astype(np.uint8)
+    out["lung_stack_linear"] = np.array([LungContourToMask.__call__(x, apply_argmax=False, reconstruction_type="linear") for x in lm]).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "generic.npz"), **out)
+    print("generic.npz", {k: v.shape for k, v in out.items() if k.startswith("spline")}, "lung areas",
+          [(out["lung_argmax"] == l).sum() for l in (1, 2)])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic"]
     for w in which:
         globals()["golden_" + w]()

@@ -184,3 +184,31 @@ def segmentation_samples(n_img, T, seed, adversarial=True, speckle=0.002):
         for k, c in enumerate(cases[:T]):
             out[0, k] = c.astype(np.float32)
     return out
+
+
+def closed_contours(n, k, seed, wild=False):
+    """n open-ended contours of k points each ((n, k, 2) float64, (x, y)): a jittered arc of an ellipse from 200 to -20
+    degrees (like a lung / heart outline whose last point is joined to the first by the closing line)."""
+    rng = np.random.default_rng(seed)
+    t = np.deg2rad(np.linspace(200.0, -20.0, k))[None]
+    a, b = rng.uniform(25, 80, (n, 1)), rng.uniform(30, 100, (n, 1))
+    cx, cy = rng.uniform(70, 186, (n, 1)), rng.uniform(70, 186, (n, 1))
+    jit = rng.normal(0, 6.0 if wild else 1.2, (n, k, 2))
+    c = np.stack([cx + a * np.cos(t), cy - b * np.sin(t)], -1) + jit
+    if wild:
+        c[::3] += rng.choice([-1, 1], (len(c[::3]), 1, 2)) * rng.uniform(40, 140, (len(c[::3]), 1, 2))   # partly off frame
+    return c
+
+
+def lung_landmarks(n, seed):
+    """(n, 120, 2): right lung (44), left lung (50), heart (26) as LungContourToMask splits them."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 120, 2))
+    for i in range(n):
+        def arc(k, cx, cy, a, b):
+            t = np.deg2rad(np.linspace(250.0, -70.0, k))
+            return np.stack([cx + a * np.cos(t), cy - b * np.sin(t)], -1) + rng.normal(0, 1.0, (k, 2))
+        out[i, :44] = arc(44, 75 + rng.normal(0, 4), 125 + rng.normal(0, 4), 38, 85)
+        out[i, 44:94] = arc(50, 180 + rng.normal(0, 4), 130 + rng.normal(0, 4), 36, 80)
+        out[i, 94:] = arc(26, 140 + rng.normal(0, 4), 165 + rng.normal(0, 4), 45, 35)
+    return out

@@ -303,3 +303,16 @@ def test_mask_gls_matches_reference():
             except (RuntimeError, IndexError):
                 got = np.nan
             assert (np.isnan(got) and np.isnan(g["gls"][v, t])) or got == g["gls"][v, t]
+
+
+def test_generic_size_reconstruction_and_lung_masks_match_reference():
+    g = np.load(os.path.join(G, "generic.npz"))
+    for k in (4, 5, 8, 26, 44, 50, 64):
+        c = g[f"contours_{k}"]
+        spl, lin = _unpack(g[f"spline_{k}"]), _unpack(g[f"linear_{k}"])
+        for i in range(len(c)):
+            assert np.array_equal(port.reconstruction(c[i], 256, 256), spl[i]), (k, i)
+            assert np.array_equal(port.linear_reconstruction(c[i], 256, 256), lin[i]), (k, i)
+    for i, lm in enumerate(g["lung_landmarks"]):
+        assert np.array_equal(port.lung_contour_to_mask(lm), g["lung_argmax"][i])
+        assert np.array_equal(port.lung_contour_to_mask(lm, False, "linear"), g["lung_stack_linear"][i])
