@@ -48,7 +48,8 @@ ROOF_NOTES = {
              "pipe -- ncu: IPC 2.2 of 4 (56 % of issue slots), ALU pipe 40 %, 4912 warp-instructions per sample, shared memory "
              "43.07 M wavefronts per launch = 86 KB / sample = 28 % of the 148 SM x 1 wavefront/clk peak "
              "(DESIGN.md section 3, profiles/r01i_*, r01d_*)",
-    "dsnt": "HBM-bound: every logit read once; DRAM traffic == algorithmic bytes",
+    "dsnt": "HBM-bound: every logit read once; DRAM traffic == algorithmic bytes; 1344 CTAs = 3.03 waves of the 444 resident "
+            "ones, so ~10 % of this 69 us launch is tail -- the same kernel streams 6.7 TB/s at 512 images (profiles/r01r_configs_1_3_4_5.jsonl)",
 }
 
 
