@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --page source --csv` dump (SASS level) by CUDA source line.
 
-usage: ncu_by_line.py <src.csv from ncu -i rep --page source --csv --kernel-name regex:K> <nvdisasm -g -c dump> <function substring> [top]
+usage: ncu_by_line.py <src.csv from ncu -i rep --page source --csv --kernel-name regex:K> <nvdisasm -g -c dump> <function substring> [top [result]]
+A report with several captured launches prints one table after the other: `result` (default 0) picks the table.
 The n-th SASS instruction of the ncu dump is matched with the n-th instruction of the nvdisasm
 listing of the same function (identical binaries), whose `//## File "...", line N` markers give the line.
 """
@@ -33,10 +34,18 @@ def sass_lines(path, func):
 def main():
     src, dis, func = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    which = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     rows = list(csv.reader(open(src)))
     hdr = rows[1]
     idx = {n: i for i, n in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) > 10]
+    tables, cur = [], None
+    for r in rows[1:]:
+        if r == hdr:                                   # every captured launch repeats the header line
+            cur = []
+            tables.append(cur)
+        elif cur is not None and len(r) > 10:
+            cur.append(r)
+    data = tables[which]
     sl = sass_lines(dis, func)
     if len(sl) != len(data):
         print(f"warning: {len(data)} ncu instructions vs {len(sl)} nvdisasm instructions", file=sys.stderr)
