@@ -670,7 +670,29 @@ def golden_generic():
           [(out["lung_argmax"] == l).sum() for l in (1, 2)])
 
 
+def golden_dataset_calibration():
+    """Dataset-level UCE / A-UCE / correlation / MAE as ClinicalMetrics.plot_calibration / plot_correlation form them
+    (contour_uncertainty/results/clinical/clinical_metrics.py:156-226, results/utils/calibration.py:6-65)."""
+    import json
+
+    from contour_uncertainty.results.utils.calibration import compute_adaptive_calibration, compute_calibration
+    from scipy.stats import pearsonr
+    from sklearn.metrics import mean_absolute_error
+
+    std, err, reject = synth.dataset_calibration_inputs()
+    nas = np.isnan(std) | np.isnan(err)
+    filt = (~reject)[~nas]
+    g, p = np.where(reject, np.inf, err), std
+    ok = ~(np.isnan(p) | np.isnan(g) | np.isinf(p) | np.isinf(g))
+    want = {"uce": compute_calibration(err[20:], std[20:])[0], "a_uce": compute_adaptive_calibration(err[20:], std[20:], nb_bins=7)[0],
+            "m_uce": compute_calibration(err[~nas], std[~nas], filters=filt)[0],
+            "m_a_uce": compute_adaptive_calibration(err[~nas], std[~nas], filters=filt)[0],
+            "correlation": float(pearsonr(g[ok], p[ok])[0]), "mae": float(mean_absolute_error(g[ok], p[ok]))}
+    json.dump(want, open(os.path.join(HERE, "dataset_calibration.json"), "w"), indent=1)
+    print("dataset_calibration.json", want)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration"]
     for w in which:
         globals()["golden_" + w]()

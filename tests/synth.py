@@ -212,3 +212,14 @@ def lung_landmarks(n, seed):
         out[i, 44:94] = arc(50, 180 + rng.normal(0, 4), 130 + rng.normal(0, 4), 36, 80)
         out[i, 94:] = arc(26, 140 + rng.normal(0, 4), 165 + rng.normal(0, 4), 45, 35)
     return out
+
+
+def dataset_calibration_inputs(seed=12, n=400):
+    """(std, error, reject) of a clinical metric over a dataset: what the results processors calibrate."""
+    rng = np.random.default_rng(seed)
+    std = np.abs(rng.normal(0.05, 0.03, n))
+    err = np.abs(rng.normal(0, 1, n)) * std * 1.3
+    std[5] = np.nan
+    err[17] = np.nan
+    reject = rng.random(n) < 0.1
+    return std, err, reject

@@ -1,4 +1,6 @@
 """CPU tests of the host-side logic that needs no device."""
+import os
+
 import numpy as np
 
 from oracle import port
@@ -85,3 +87,20 @@ def test_seg_and_gls_wrappers_refuse_cpu_tensors():
         E.mask_lv_length(torch.zeros((1, 2048), dtype=torch.int32))
     with pytest.raises(ValueError, match="no CPU implementation"):
         E.seg_entropy(torch.zeros((1, 1, 256, 256)), torch.zeros((1, 1, 2048), dtype=torch.int32))
+
+
+def test_dataset_level_calibration_and_correlation_match_the_reference():
+    """results/utils/calibration.py mirror vs the numbers the reference's own compute_calibration /
+    compute_adaptive_calibration / pearsonr / mean_absolute_error gave (tests/golden/make_golden.py dataset_calibration)."""
+    import json
+
+    import synth
+    from contouring_uncertainty_b200.results.utils import calibration as C
+
+    std, err, reject = synth.dataset_calibration_inputs()
+    got = {"uce": C.compute_calibration(err[20:], std[20:])[0], "a_uce": C.compute_adaptive_calibration(err[20:], std[20:], nb_bins=7)[0],
+           **{f"m_{k}": v for k, v in C.metric_calibration(std, err, reject).items()},
+           **C.metric_correlation(np.where(reject, np.inf, err), std)}
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_calibration.json")))
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-12 * max(1.0, abs(v)), (k, got[k], v)
