@@ -1,4 +1,4 @@
-"""Mirror of contour_uncertainty/data/camus/utils.py::USContourToMask (LV-only branch :43, :85-90)."""
+"""Mirror of contour_uncertainty/data/camus/utils.py::USContourToMask (LV-only branch :43, :85-90; LV + MYO branch :47-82)."""
 from typing import Literal
 
 import numpy as np
@@ -21,8 +21,17 @@ class USContourToMask(ContourToMask):
             raise ValueError
         if tuple(shape) != (E.HW, E.HW):
             raise ValueError("only 256x256 frames are supported")
-        if labels is not None and any(str(l).lower().endswith("myo") for l in labels):
-            raise NotImplementedError("the MYO (two-structure) branch is out of scope (SURVEY.md section 2, #5)")
+        if labels is not None and any(str(getattr(l, "name", l)).lower().endswith("myo") or l == 2 for l in labels):
+            # two structures (:47-82): 42 landmarks = endocardium + epicardium -> BG / LV / MYO
+            lm = np.asarray(landmarks, dtype=np.float32).squeeze()
+            single = lm.ndim == 2
+            lm = lm.reshape(-1, 2 * E.K, 2)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            lv, myo, _ = E.us_myo_masks(torch.from_numpy(np.ascontiguousarray(lm)).to(dev), reconstruction_type=reconstruction_type)
+            lv, myo = E.unpack_masks(lv).to(torch.int64), E.unpack_masks(myo).to(torch.int64)
+            seg = torch.stack([((lv + myo) == 0).to(torch.int64), lv, myo], dim=1)       # Label.BG, Label.LV, Label.MYO
+            out = (seg.argmax(1) if apply_argmax else seg).cpu().numpy()
+            return out[0] if single else out
         lm = np.asarray(landmarks, dtype=np.float32).squeeze()
         single = lm.ndim == 2
         lm = lm.reshape(-1, E.K, 2)

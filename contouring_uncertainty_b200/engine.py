@@ -224,6 +224,26 @@ def rasterize_contours_generic(contours: torch.Tensor, round_landmarks: bool = T
     return masks, area
 
 
+def us_myo_masks(landmarks: torch.Tensor, reconstruction_type: str = "spline"):
+    """USContourToMask's two-structure branch (cu/data/camus/utils.py:47-82): landmarks (M, 42, 2) fp32 = 21 endocardial +
+    21 epicardial points -> (lv masks (M, 2048) int32, myo masks (M, 2048) int32, areas (M, 2) int32), bit-packed."""
+    if reconstruction_type not in ("spline", "linear"):
+        raise ValueError("reconstruction_type must be 'spline' or 'linear'")
+    landmarks = nat.require_cuda(landmarks, torch.float32, "landmarks")
+    if landmarks.dim() != 3 or tuple(landmarks.shape[1:]) != (2 * K, 2):
+        raise ValueError(f"landmarks must be (M, {2 * K}, 2), got {tuple(landmarks.shape)}")
+    m = int(landmarks.shape[0])
+    dev = landmarks.device
+    lv = torch.empty((m, MASK_WORDS), dtype=torch.int32, device=dev)
+    myo = torch.empty((m, MASK_WORDS), dtype=torch.int32, device=dev)
+    area = torch.empty((m, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_us_myo_masks(nat.ptr(landmarks), m, 2 if reconstruction_type == "linear" else 0, nat.ptr(lv),
+                                           nat.ptr(myo), nat.ptr(area), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_us_myo_masks")
+    return lv, myo, area
+
+
 def unpack_masks(masks: torch.Tensor) -> torch.Tensor:
     """(..., 2048) int32 bit-packed -> (..., 256, 256) uint8 (host or device; plain torch bit ops)."""
     w = masks.reshape(masks.shape[:-1] + (HW, 8, 1))

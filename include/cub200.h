@@ -450,6 +450,17 @@ int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, double smoothi
 int cub200_rasterize_contours_generic(const void* contours, int is_f64, int64_t n, int n_points, int flags, uint32_t* masks_out,
                                       int32_t* area_out, void* stream);
 
+/*
+ * Two-structure (LV + MYO) masks: USContourToMask when Label.MYO is among the labels   cu/data/camus/utils.py:47-82
+ * (split_landmarks, contour_spline x 2, poly2mask -> skimage.draw.polygon [restated, parity unpinned], reconstruction).
+ *   landmarks (n, 42, 2) fp32 (x, y): 21 endocardial then 21 epicardial points, rounded half to even by the call;
+ *   flags: bit 1 = reconstruction_type 'linear' for the LV mask (the polygon always follows the splines).
+ *   lv_out / myo_out (n, 2048) u32 bit-packed: seg_map[LV] and seg_map[MYO] = clip(myo_mask - lv_mask, 0, 1);
+ *   area_out (n, 2) i32 = their pixel counts.  Any of the three may be NULL (not all).
+ */
+int cub200_us_myo_masks(const float* landmarks, int64_t n, int flags, uint32_t* lv_out, uint32_t* myo_out, int32_t* area_out,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

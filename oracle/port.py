@@ -10,9 +10,9 @@ executed in the build container by ``tests/golden/make_golden.py`` and committed
 ``tests/golden/*.npz`` (checked by ``tests/test_oracle_golden.py``).  Third-party arithmetic the
 reference calls and that is present in this image is called the same way here
 (``scipy.interpolate.splprep/splev``, ``scipy.ndimage.binary_fill_holes``, ``scipy.stats.entropy``);
-``skimage.draw.line`` and ``skimage.measure.find_contours`` are absent from the image and restated
-from memory of scikit-image's sources (``bresenham_line``, ``find_contours``) -- "PARITY UNPINNED" for
-these two third-party functions: the first draws the <= ~80 px base line between landmarks 20 and 0,
+``skimage.draw.line``, ``skimage.measure.find_contours`` and ``skimage.draw.polygon`` are absent from the image and restated
+from memory of scikit-image's sources (``bresenham_line``, ``find_contours``, ``draw_polygon``) -- "PARITY UNPINNED" for
+these third-party functions (the polygon fill only serves the LV + MYO masks): the first draws the <= ~80 px base line between landmarks 20 and 0,
 the second decides the point order of the contour that Simpson's base-chord search walks.  Everything
 else is pinned: the goldens were made by executing the reference's own code (with these two
 restatements standing in for scikit-image) and its third-party calls that exist here (scipy FITPACK
@@ -1273,5 +1273,67 @@ def lung_contour_to_mask(landmarks: np.ndarray, apply_argmax: bool = True, recon
     seg[1] += rec(rl, 256, 256)
     seg[1] += rec(ll, 256, 256)
     seg[2] = rec(h, 256, 256)
+    seg[0] = seg.sum(0) == 0
+    return seg.argmax(0) if apply_argmax else seg
+
+
+# --------------------------------------------------------------------------------------------------
+# Two-structure (LV + MYO) masks: USContourToMask with Label.MYO among the labels
+# --------------------------------------------------------------------------------------------------
+def draw_polygon(r, c, shape=None):
+    """``skimage.draw.polygon(r, c, shape)`` restated from skimage/draw/_draw.pyx::_polygon and
+    skimage/_shared/geometry.pyx::point_in_polygon (scikit-image is absent from the image: PARITY UNPINNED; call site
+    cu/data/camus/utils.py:24-28).  Every pixel of the vertices' bounding box (clipped to ``shape``) whose centre is
+    inside the polygon, on an edge or on a vertex:
+
+        for every edge (i-1, i), seen from the pixel (x0 = xp[i] - x, ...):
+            vertex      if |x0|, |y0| < 1e-12
+            r_cross += 1 if (y0 > 0) != (y1 > 0) and (x0 y1 - x1 y0) / (y1 - y0) > 0
+            l_cross += 1 if (y0 < 0) != (y1 < 0) and (x0 y1 - x1 y0) / (y1 - y0) < 0
+        edge if the two parities differ, inside if r_cross is odd.
+
+    Vectorised over the pixels of a row; returns (rr, cc) in raster order like the original."""
+    r = np.asanyarray(r, dtype=np.float64)
+    c = np.asanyarray(c, dtype=np.float64)
+    minr, maxr = int(max(0, r.min())), int(math.ceil(r.max()))
+    minc, maxc = int(max(0, c.min())), int(math.ceil(c.max()))
+    if shape is not None:
+        maxr, maxc = min(shape[0] - 1, maxr), min(shape[1] - 1, maxc)
+    if maxr < minr or maxc < minc:
+        return np.zeros(0, dtype=np.intp), np.zeros(0, dtype=np.intp)
+    xs = np.arange(minc, maxc + 1, dtype=np.float64)
+    xp1, yp1 = np.roll(c, 1), np.roll(r, 1)                      # vertex i-1 of edge (i-1, i)
+    rr, cc = [], []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for y in range(minr, maxr + 1):
+            y0, y1 = (r - y)[:, None], (yp1 - y)[:, None]
+            x0, x1 = c[:, None] - xs[None], xp1[:, None] - xs[None]
+            vertex = ((np.abs(x0) < 1e-12) & (np.abs(y0) < 1e-12)).any(0)
+            q = (x0 * y1 - x1 * y0) / (y1 - y0)
+            r_cross = (((y0 > 0) != (y1 > 0)) & (q > 0)).sum(0)
+            l_cross = (((y0 < 0) != (y1 < 0)) & (q < 0)).sum(0)
+            inside = vertex | ((r_cross & 1) != (l_cross & 1)) | ((r_cross & 1) == 1)
+            cols = np.nonzero(inside)[0] + minc
+            rr.append(np.full(len(cols), y, dtype=np.intp))
+            cc.append(cols.astype(np.intp))
+    return np.concatenate(rr), np.concatenate(cc)
+
+
+def us_contour_to_mask_myo(landmarks: np.ndarray, apply_argmax: bool = True, reconstruction_type: str = "spline") -> np.ndarray:
+    """cu/data/camus/utils.py:31-98 with Label.MYO among the labels (:47-82): 42 rounded landmarks = endocardium (21) +
+    epicardium (21); LV = reconstruction(lv); MYO = polygon(lv spline + reversed epi spline) minus LV; BG the rest."""
+    rec = linear_reconstruction if reconstruction_type == "linear" else reconstruction
+    lm = np.asarray(landmarks).round().astype(int).squeeze()
+    lv, myo = lm[:21], lm[21:42]
+    lv_spline = contour_spline(lv, n=1000).round().astype(int)
+    myo_spline = contour_spline(myo, n=1000).round().astype(int)
+    polygon = np.concatenate([lv_spline, np.flip(myo_spline, axis=0)])
+    rr, cc = draw_polygon(polygon[:, 1], polygon[:, 0], (256, 256))
+    myo_mask = np.zeros((256, 256), dtype=int)
+    myo_mask[rr, cc] = 1
+    lv_mask = rec(lv, 256, 256)
+    seg = np.zeros((3, 256, 256), dtype=int)
+    seg[1] = lv_mask
+    seg[2] = np.clip(myo_mask - lv_mask, a_min=0, a_max=1)
     seg[0] = seg.sum(0) == 0
     return seg.argmax(0) if apply_argmax else seg

@@ -92,6 +92,11 @@ class _StubLoader(importlib.abc.Loader):
         name = module.__name__
         if name == "skimage.draw":
             module.line = bresenham_line
+            # restated point-in-polygon fill (scikit-image is absent): parity unpinned, see oracle/port.py
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+            from oracle.port import draw_polygon
+
+            module.polygon = draw_polygon
         if name == "skimage.measure":
             # restated marching squares (scikit-image is absent): parity unpinned, see oracle/port.py
             sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))

@@ -692,7 +692,23 @@ def golden_dataset_calibration():
     print("dataset_calibration.json", want)
 
 
+def golden_myo():
+    """USContourToMask with Label.MYO among the labels (cu/data/camus/utils.py:47-82), executed as it is;
+    skimage.draw.polygon is the restated one (oracle/port.py): parity unpinned for it."""
+    from contour_uncertainty.data.camus.utils import USContourToMask
+    from vital.data.camus.config import Label
+
+    lm = np.concatenate([synth.endo_epi_landmarks(10, seed=61), synth.endo_epi_landmarks(8, seed=62, wild=True)])
+    labels = [Label.BG, Label.LV, Label.MYO]
+    argmax = np.array([USContourToMask.__call__(x.astype(np.float32), (256, 256), labels=labels) for x in lm]).astype(np.uint8)
+    stack_lin = np.array([USContourToMask.__call__(x.astype(np.float32), (256, 256), labels=labels, apply_argmax=False,
+                                                   reconstruction_type="linear") for x in lm]).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "myo.npz"), landmarks=lm.astype(np.float32), argmax=argmax,
+                        stack_linear=np.packbits(stack_lin, axis=-1, bitorder="little"))
+    print("myo.npz", argmax.shape, "LV px", (argmax == 1).sum((1, 2))[:5], "MYO px", (argmax == 2).sum((1, 2))[:5])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo"]
     for w in which:
         globals()["golden_" + w]()

@@ -223,3 +223,16 @@ def dataset_calibration_inputs(seed=12, n=400):
     err[17] = np.nan
     reject = rng.random(n) < 0.1
     return std, err, reject
+
+
+def endo_epi_landmarks(n, seed, wild=False):
+    """(n, 42, 2): the 21 LV landmarks (jittered) followed by 21 epicardial ones = the same shape grown about its centroid."""
+    rng = np.random.default_rng(seed)
+    lv = LV_EXAMPLE_SHAPE[None] + rng.normal(0, 5.0 if wild else 1.5, (n, 21, 2)) + rng.normal(0, 6.0, (n, 1, 2))
+    cen = lv.mean(1, keepdims=True)
+    epi = cen + (lv - cen) * rng.uniform(1.15, 1.35, (n, 1, 1)) + rng.normal(0, 4.0 if wild else 1.0, (n, 21, 2))
+    out = np.concatenate([lv, epi], 1)
+    if wild:
+        out[::4] += rng.choice([-1, 1], (len(out[::4]), 1, 2)) * rng.uniform(50, 120, (len(out[::4]), 1, 2))     # partly off frame
+        out[1, 25] = out[1, 24]                                                                                   # zero chord in the epicardium
+    return out

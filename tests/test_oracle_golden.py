@@ -316,3 +316,13 @@ def test_generic_size_reconstruction_and_lung_masks_match_reference():
     for i, lm in enumerate(g["lung_landmarks"]):
         assert np.array_equal(port.lung_contour_to_mask(lm), g["lung_argmax"][i])
         assert np.array_equal(port.lung_contour_to_mask(lm, False, "linear"), g["lung_stack_linear"][i])
+
+
+def test_two_structure_masks_match_reference():
+    """oracle USContourToMask (LV + MYO) vs the executed reference (skimage.draw.polygon restated: parity unpinned)."""
+    g = np.load(os.path.join(G, "myo.npz"))
+    stack = _unpack(g["stack_linear"])
+    for i, lm in enumerate(g["landmarks"]):
+        assert np.array_equal(port.us_contour_to_mask_myo(lm), g["argmax"][i]), i
+        if i % 3 == 0:
+            assert np.array_equal(port.us_contour_to_mask_myo(lm, False, "linear"), stack[i]), i
