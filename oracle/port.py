@@ -14,7 +14,7 @@ reference calls and that is present in this image is called the same way here
 from memory of scikit-image's sources (``bresenham_line``, ``find_contours``, ``draw_polygon``) -- "PARITY UNPINNED" for
 these third-party functions (the polygon fill only serves the LV + MYO masks): the first draws the <= ~80 px base line between landmarks 20 and 0,
 the second decides the point order of the contour that Simpson's base-chord search walks.  Everything
-else is pinned: the goldens were made by executing the reference's own code (with these two
+else is pinned: the goldens were made by executing the reference's own code (with these
 restatements standing in for scikit-image) and its third-party calls that exist here (scipy FITPACK
 splines, ``binary_fill_holes``, ``scipy.stats``, torch, numpy, PIL) run unmodified.
 
