@@ -326,3 +326,28 @@ def test_two_structure_masks_match_reference():
         assert np.array_equal(port.us_contour_to_mask_myo(lm), g["argmax"][i]), i
         if i % 3 == 0:
             assert np.array_equal(port.us_contour_to_mask_myo(lm, False, "linear"), stack[i]), i
+
+
+def test_restated_skimage_functions_reproduce_their_published_docstring_examples():
+    """scikit-image is absent here, so its three functions on the path are restated (parity unpinned).  The examples
+    printed in their own docstrings -- quoted from memory, the only vectors of theirs available offline -- come out right."""
+    img = np.zeros((10, 10), dtype=np.uint8)
+    rr, cc = port.draw_polygon(np.array([1, 2, 8]), np.array([1, 7, 4]))          # skimage.draw.polygon docstring
+    img[rr, cc] = 1
+    want = np.array([[0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+                     [0, 1, 0, 0, 0, 0, 0, 0, 0, 0],
+                     [0, 0, 1, 1, 1, 1, 1, 1, 0, 0],
+                     [0, 0, 1, 1, 1, 1, 1, 0, 0, 0],
+                     [0, 0, 0, 1, 1, 1, 1, 0, 0, 0],
+                     [0, 0, 0, 1, 1, 1, 0, 0, 0, 0],
+                     [0, 0, 0, 0, 1, 1, 0, 0, 0, 0],
+                     [0, 0, 0, 0, 1, 0, 0, 0, 0, 0],
+                     [0, 0, 0, 0, 1, 0, 0, 0, 0, 0],
+                     [0, 0, 0, 0, 0, 0, 0, 0, 0, 0]], dtype=np.uint8)
+    assert np.array_equal(img, want)
+    a = np.zeros((3, 3))
+    a[0, 0] = 1
+    c = port.find_contours(a, 0.5)                                                 # skimage.measure.find_contours docstring
+    assert len(c) == 1 and np.array_equal(c[0], np.array([[0.0, 0.5], [0.5, 0.0]]))
+    rr, cc = port.bresenham_line(1, 1, 8, 8)                                       # skimage.draw.line docstring
+    assert np.array_equal(rr, np.arange(1, 9)) and np.array_equal(cc, np.arange(1, 9))
