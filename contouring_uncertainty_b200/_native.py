@@ -51,6 +51,7 @@ SIGNATURES = {
     "cub200_bivariate_pdf": [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
     "cub200_skew_rvs_fast": [_vp, _vp, _vp, _vp, _u64, _i64, _vp, _vp],
     "cub200_seg_largest_blob": [_vp, _i64, _vp, _vp, _vp, _vp],
+    "cub200_sample_entropy": [_vp, _i64, _i32, _i32, _i64, _vp, _vp],
     "cub200_us_myo_masks": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
     "cub200_rasterize_contours_generic": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp],
     "cub200_mask_lv_length": [_vp, _i64, C.c_double, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp],

@@ -181,3 +181,63 @@ extern "C" int cub200_metric_sums(const int32_t* values, int64_t n, int64_t* sum
     metric_sums_kernel<<<(unsigned)(blocks < 592 ? blocks : 592), 256, 0, st>>>(values, n, reinterpret_cast<unsigned long long*>(sums_out));
     return check_launch("metric_sums_kernel");
 }
+
+// ---------------------------------------------------------------- sample_entropy for probabilities of any class count
+// UncertaintyTask.sample_entropy (contour_uncertainty/task/uncertainty.py:107-133) in full: samples (T, C, P) fp32 per
+// image -> y_hat = mean over T; C == 1: entropy of [y, 1 - y] in bits, else entropy over the C classes in base C;
+// scipy.stats.entropy normalises by the class sum, sums entr() and divides by log(base), all in the array's fp32;
+// non-finite -> 0.  HBM-bound: every probability is read once, thread = pixel, coalesced along the pixels.
+namespace cub200 {
+constexpr int SE_MAXC = 8;
+
+__global__ void __launch_bounds__(256)
+sample_entropy_kernel(const float* __restrict__ samples, int64_t n_img, int T, int C, int64_t P, float* __restrict__ out) {
+    const int64_t total = n_img * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = i / P, p = i - img * P;
+        const float* base = samples + img * T * C * P + p;
+        double acc[SE_MAXC];
+#pragma unroll
+        for (int c = 0; c < SE_MAXC; ++c) acc[c] = 0.0;
+        for (int t = 0; t < T; ++t) {
+            float v[SE_MAXC];
+#pragma unroll
+            for (int c = 0; c < SE_MAXC; ++c) v[c] = (c < C) ? __ldcs(base + ((int64_t)t * C + c) * P) : 0.f;
+#pragma unroll
+            for (int c = 0; c < SE_MAXC; ++c) acc[c] += (double)v[c];
+        }
+        float y[SE_MAXC];
+#pragma unroll
+        for (int c = 0; c < SE_MAXC; ++c) y[c] = (float)(acc[c] / (double)T);
+        int nc = C;
+        float lb = logf((float)C);
+        if (C == 1) { y[1] = 1.0f - y[0]; nc = 2; lb = 0.6931471805599453f; }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < SE_MAXC; ++c) if (c < nc) sum += y[c];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < SE_MAXC; ++c)
+            if (c < nc) {
+                const float q = __fdiv_rn(y[c], sum);
+                s += q > 0.f ? -q * logf(q) : (q == 0.f ? 0.f : -INFINITY);
+            }
+        float h = __fdiv_rn(s, lb);
+        if (!isfinite(h)) h = 0.f;
+        out[i] = h;
+    }
+}
+}  // namespace cub200
+
+extern "C" int cub200_sample_entropy(const float* samples, int64_t n_img, int n_samples, int n_classes, int64_t n_pixels,
+                                     float* entropy_out, void* stream) {
+    using namespace cub200;
+    if (n_img == 0 || n_pixels == 0) return 0;
+    if (!samples || !entropy_out || n_img < 0 || n_pixels < 0 || n_samples < 1 || n_classes < 1 || n_classes > SE_MAXC)
+        return CUB200_EINVAL;
+    const int64_t total = n_img * n_pixels;
+    const int64_t blocks = (total + 255) / 256;
+    sample_entropy_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        samples, n_img, n_samples, n_classes, n_pixels, entropy_out);
+    return check_launch("sample_entropy_kernel");
+}

@@ -244,6 +244,20 @@ def us_myo_masks(landmarks: torch.Tensor, reconstruction_type: str = "spline"):
     return lv, myo, area
 
 
+def sample_entropy(samples: torch.Tensor) -> torch.Tensor:
+    """UncertaintyTask.sample_entropy (cu/task/uncertainty.py:107-133) for probabilities of any class count:
+    samples (N, T, C, H, W) fp32 with 1 <= C <= 8 -> (N, H, W) fp32 (C == 1: bits; else base C)."""
+    samples = nat.require_cuda(samples, torch.float32, "samples")
+    if samples.dim() != 5 or not (1 <= samples.shape[2] <= 8) or samples.shape[1] < 1:
+        raise ValueError(f"samples must be (N, T, C, H, W) with T >= 1 and 1 <= C <= 8, got {tuple(samples.shape)}")
+    n, t, c, h, w = (int(v) for v in samples.shape)
+    out = torch.empty((n, h, w), dtype=torch.float32, device=samples.device)
+    with torch.cuda.device(samples.device):
+        rc = nat.lib().cub200_sample_entropy(nat.ptr(samples), n, t, c, h * w, nat.ptr(out), nat.stream_ptr(samples.device))
+    nat.check(rc, "cub200_sample_entropy")
+    return out
+
+
 def unpack_masks(masks: torch.Tensor) -> torch.Tensor:
     """(..., 2048) int32 bit-packed -> (..., 256, 256) uint8 (host or device; plain torch bit ops)."""
     w = masks.reshape(masks.shape[:-1] + (HW, 8, 1))

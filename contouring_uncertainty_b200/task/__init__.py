@@ -17,16 +17,20 @@ from ..data.config import BatchResult
 
 
 def sample_entropy(samples) -> np.ndarray:
-    """UncertaintyTask.sample_entropy (cu/task/uncertainty.py:107-133) for C == 1.
+    """UncertaintyTask.sample_entropy (cu/task/uncertainty.py:107-133).
 
-    samples (T,1,H,W) or (T_e,T_a,1,H,W) of 0/1 values -> binary entropy (bits) of the sample mean.
-    The count map is formed by an exact integer sum; the entropy table runs on the GPU (K4).
+    samples (T,C,H,W) or (T_e,T_a,C,H,W).  0/1 masks with C == 1 (the contour path): binary entropy (bits) of the sample
+    mean in fp64 -- the count map is formed by an exact integer sum, the entropy table runs on the GPU (K4).  Probabilities
+    or C > 1: fp32 like the reference's tensors (base 2 for C == 1, base C otherwise).
     """
     s = np.asarray(samples)
     if s.ndim == 5:
         s = s.reshape((-1,) + s.shape[2:])
-    if s.shape[1] != 1:
-        raise NotImplementedError("multi-class entropy is out of scope (labels = [lv])")
+    if s.shape[1] != 1 or not np.isin(s, (0, 1)).all():
+        # probabilities / several classes: the general kernel (fp32 like the reference's tensors)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))[None].to(dev)
+        return E.sample_entropy(t)[0].cpu().numpy()
     T = s.shape[0]
     count = torch.from_numpy(s[:, 0].astype(np.int32).sum(0, dtype=np.int32))
     dev = torch.device("cuda", torch.cuda.current_device())

@@ -461,6 +461,16 @@ int cub200_rasterize_contours_generic(const void* contours, int is_f64, int64_t 
 int cub200_us_myo_masks(const float* landmarks, int64_t n, int flags, uint32_t* lv_out, uint32_t* myo_out, int32_t* area_out,
                         void* stream);
 
+/*
+ * UncertaintyTask.sample_entropy in full (cu/task/uncertainty.py:107-133): probabilities of any class count.
+ *   samples (n_img, n_samples, n_classes, n_pixels) fp32, 1 <= n_classes <= 8 -> entropy_out (n_img, n_pixels) fp32:
+ *   mean over the samples, then C == 1: entropy of [p, 1 - p] in bits, else entropy over the classes in base C
+ *   (scipy.stats.entropy: normalised by the class sum), non-finite -> 0.  For 0/1 masks of the contour path the count-map
+ *   route (cub200_finalize_maps) gives the same map in fp64.
+ */
+int cub200_sample_entropy(const float* samples, int64_t n_img, int n_samples, int n_classes, int64_t n_pixels,
+                          float* entropy_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

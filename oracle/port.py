@@ -1179,12 +1179,22 @@ def seg_blob_masks(samples: np.ndarray) -> np.ndarray:
 
 
 def _sample_entropy_f32(samples: np.ndarray) -> np.ndarray:
-    """cu/task/uncertainty.py:107-133 in the dtype it is given (float32 samples stay float32 end to end)."""
-    s = samples.reshape((-1,) + samples.shape[2:])
+    """cu/task/uncertainty.py:107-133 in the dtype it is given (float32 samples stay float32 end to end):
+    (T_e, T_a, C, H, W) or (T, C, H, W); C == 1 -> entropy of [y, 1 - y] in bits, else over the classes in base C."""
+    s = samples.reshape((-1,) + samples.shape[2:]) if samples.ndim == 5 else samples
     y = s.mean(0, dtype=s.dtype)
-    umap = scipy.stats.entropy(np.concatenate([y, 1 - y], axis=0), axis=0, base=2)
+    if s.shape[1] == 1:
+        y, base = np.concatenate([y, 1 - y], axis=0), 2
+    else:
+        base = s.shape[1]
+    umap = scipy.stats.entropy(y, axis=0, base=base)
     umap[~np.isfinite(umap)] = 0
     return umap
+
+
+def sample_entropy_general(samples: np.ndarray) -> np.ndarray:
+    """Public name of the above for probabilities / several classes."""
+    return _sample_entropy_f32(np.asarray(samples))
 
 
 # --------------------------------------------------------------------------------------------------

@@ -708,7 +708,21 @@ def golden_myo():
     print("myo.npz", argmax.shape, "LV px", (argmax == 1).sum((1, 2))[:5], "MYO px", (argmax == 2).sum((1, 2))[:5])
 
 
+from class_entropy_inputs import class_entropy_inputs  # noqa: E402
+
+
+def golden_class_entropy():
+    """UncertaintyTask.sample_entropy (cu/task/uncertainty.py:107-133) on probabilities: C = 3 (base 3) and C = 1."""
+    from contour_uncertainty.task.uncertainty import UncertaintyTask
+
+    p3, p1 = class_entropy_inputs()
+    e3 = np.array([UncertaintyTask.sample_entropy(x) for x in p3])
+    e1 = np.array([UncertaintyTask.sample_entropy(x.reshape(3, 4, 1, 64, 64)) for x in p1])
+    np.savez_compressed(os.path.join(HERE, "class_entropy.npz"), e3=e3, e1=e1)
+    print("class_entropy.npz", e3.dtype, e3.shape, float(e3.max()), float(e1.max()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy"]
     for w in which:
         globals()["golden_" + w]()

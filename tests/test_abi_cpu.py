@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in cub200.h but not exported"
     assert set(names) == set(_native.SIGNATURES) | set(_native.QUERIES)
-    assert _native.lib().cub200_abi_version() == 16
+    assert _native.lib().cub200_abi_version() == 17
     assert _native.lib().cub200_built_for_sm() == 100
 
 
@@ -96,6 +96,8 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_rasterize_contours_f64(None, 0, 0, None, None, None, 0, None) == 0
     assert l.cub200_simpson_workspace_bytes(10) == 10 * (2048 * 4 + 4)
     assert l.cub200_seg_largest_blob(None, 1, None, None, None, None) == E
+    assert l.cub200_sample_entropy(None, 1, 4, 3, 65536, None, None) == E
+    assert l.cub200_sample_entropy(None, 0, 4, 3, 65536, None, None) == 0
     assert l.cub200_us_myo_masks(None, 1, 0, None, None, None, None) == E
     assert l.cub200_us_myo_masks(None, 0, 0, None, None, None, None) == 0
     assert l.cub200_rasterize_contours_generic(None, 0, 1, 26, 1, None, None, None) == E

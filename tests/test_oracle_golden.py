@@ -351,3 +351,19 @@ def test_restated_skimage_functions_reproduce_their_published_docstring_examples
     assert len(c) == 1 and np.array_equal(c[0], np.array([[0.0, 0.5], [0.5, 0.0]]))
     rr, cc = port.bresenham_line(1, 1, 8, 8)                                       # skimage.draw.line docstring
     assert np.array_equal(rr, np.arange(1, 9)) and np.array_equal(cc, np.arange(1, 9))
+
+
+def test_class_entropy_matches_reference():
+    """sample_entropy on probabilities (C = 3 in base 3, C = 1 in bits) vs the executed reference."""
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_mk_inputs", os.path.join(sys_path, "class_entropy_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    p3, p1 = mod.class_entropy_inputs()
+    g = np.load(os.path.join(G, "class_entropy.npz"))
+    e3 = np.array([port.sample_entropy_general(x) for x in p3])
+    e1 = np.array([port.sample_entropy_general(x.reshape(3, 4, 1, 64, 64)) for x in p1])
+    # torch's fp32 mean vs numpy's: a few ulp of the mean
+    assert np.abs(e3 - g["e3"]).max() < 2e-6 and np.abs(e1 - g["e1"]).max() < 2e-6
