@@ -367,3 +367,46 @@ def test_class_entropy_matches_reference():
     e1 = np.array([port.sample_entropy_general(x.reshape(3, 4, 1, 64, 64)) for x in p1])
     # torch's fp32 mean vs numpy's: a few ulp of the mean
     assert np.abs(e3 - g["e3"]).max() < 2e-6 and np.abs(e1 - g["e1"]).max() < 2e-6
+
+
+def _point_in_polygon_scalar(xp, yp, x, y):
+    """The scalar loop draw_polygon's row-vectorised form stands for (0 outside, 1 inside, 2 vertex, 3 edge)."""
+    n = len(xp)
+    x1, y1 = xp[n - 1] - x, yp[n - 1] - y
+    l_cross = r_cross = 0
+    for i in range(n):
+        x0, y0 = xp[i] - x, yp[i] - y
+        if -1e-12 < x0 < 1e-12 and -1e-12 < y0 < 1e-12:
+            return 2
+        if (y0 > 0) != (y1 > 0) and (x0 * y1 - x1 * y0) / (y1 - y0) > 0:
+            r_cross += 1
+        if (y0 < 0) != (y1 < 0) and (x0 * y1 - x1 * y0) / (y1 - y0) < 0:
+            l_cross += 1
+        x1, y1 = x0, y0
+    if (r_cross & 1) != (l_cross & 1):
+        return 3
+    return 1 if r_cross & 1 else 0
+
+
+def test_polygon_fill_vectorisation_and_blob_filter_properties():
+    rng = np.random.default_rng(8)
+    for _ in range(60):
+        k = int(rng.integers(3, 9))
+        r, c = rng.integers(-5, 26, k).astype(float), rng.integers(-5, 26, k).astype(float)
+        rr, cc = port.draw_polygon(r, c, (20, 20))
+        got = np.zeros((20, 20), bool)
+        got[rr, cc] = True
+        want = np.zeros((20, 20), bool)
+        for y in range(int(max(0, r.min())), min(19, int(np.ceil(r.max()))) + 1):
+            for x in range(int(max(0, c.min())), min(19, int(np.ceil(c.max()))) + 1):
+                want[y, x] = _point_in_polygon_scalar(c, r, float(x), float(y)) != 0
+        assert np.array_equal(got, want)
+    for dens in (0.0, 0.3, 0.6, 1.0):
+        seg = (rng.random((1, 40, 40)) < dens).astype(float)
+        out = port.big_blob(seg)
+        assert np.array_equal(port.big_blob(out), out)                   # idempotent
+        assert not (out.astype(bool) & ~seg.astype(bool)).any()          # never adds pixels
+        if seg.any():
+            from scipy import ndimage
+
+            assert ndimage.label(out[0])[1] == 1                         # one component left
