@@ -190,42 +190,99 @@ extern "C" int cub200_metric_sums(const int32_t* values, int64_t n, int64_t* sum
 namespace cub200 {
 constexpr int SE_MAXC = 8;
 
+// entropy of one pixel from the class sums over the samples
+template <int CMAX>
+__device__ __forceinline__ float class_entropy(const double (&acc)[CMAX], int T, int C) {
+    constexpr int NY = CMAX < 2 ? 2 : CMAX;
+    float y[NY];
+#pragma unroll
+    for (int c = 0; c < NY; ++c) y[c] = (c < CMAX) ? (float)(acc[c < CMAX ? c : 0] / (double)T) : 0.f;
+    int nc = C;
+    float lb = logf((float)C);
+    if (C == 1) { y[1] = 1.0f - y[0]; nc = 2; lb = 0.6931471805599453f; }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NY; ++c) if (c < nc) sum += y[c];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NY; ++c)
+        if (c < nc) {
+            const float q = __fdiv_rn(y[c], sum);
+            s += q > 0.f ? -q * logf(q) : (q == 0.f ? 0.f : -INFINITY);
+        }
+    const float h = __fdiv_rn(s, lb);
+    return isfinite(h) ? h : 0.f;
+}
+
+// VEC pixels per thread (4: 128-bit loads; needs n_pixels % 4 == 0 and 16-byte aligned maps), classes held in CMAX
+// register slots, UNR samples in flight per thread -- the bytes in flight are what a streaming kernel lives on.
+template <int VEC, int CMAX, int UNR>
 __global__ void __launch_bounds__(256)
 sample_entropy_kernel(const float* __restrict__ samples, int64_t n_img, int T, int C, int64_t P, float* __restrict__ out) {
-    const int64_t total = n_img * P;
+    const int64_t groups = P / VEC, total = n_img * groups;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t img = i / P, p = i - img * P;
+        const int64_t img = i / groups, p = (i - img * groups) * VEC;
         const float* base = samples + img * T * C * P + p;
-        double acc[SE_MAXC];
+        double acc[VEC][CMAX];
 #pragma unroll
-        for (int c = 0; c < SE_MAXC; ++c) acc[c] = 0.0;
-        for (int t = 0; t < T; ++t) {
-            float v[SE_MAXC];
+        for (int k = 0; k < VEC; ++k)
 #pragma unroll
-            for (int c = 0; c < SE_MAXC; ++c) v[c] = (c < C) ? __ldcs(base + ((int64_t)t * C + c) * P) : 0.f;
-#pragma unroll
-            for (int c = 0; c < SE_MAXC; ++c) acc[c] += (double)v[c];
-        }
-        float y[SE_MAXC];
-#pragma unroll
-        for (int c = 0; c < SE_MAXC; ++c) y[c] = (float)(acc[c] / (double)T);
-        int nc = C;
-        float lb = logf((float)C);
-        if (C == 1) { y[1] = 1.0f - y[0]; nc = 2; lb = 0.6931471805599453f; }
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < SE_MAXC; ++c) if (c < nc) sum += y[c];
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < SE_MAXC; ++c)
-            if (c < nc) {
-                const float q = __fdiv_rn(y[c], sum);
-                s += q > 0.f ? -q * logf(q) : (q == 0.f ? 0.f : -INFINITY);
+            for (int c = 0; c < CMAX; ++c) acc[k][c] = 0.0;
+        auto load = [&](int t, int c, float (&v)[VEC]) {
+            const float* q = base + ((int64_t)t * C + c) * P;
+            if constexpr (VEC == 4) {
+                const float4 f = ld_stream_f4(reinterpret_cast<const float4*>(q));
+                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+            } else {
+                v[0] = __ldcs(q);
             }
-        float h = __fdiv_rn(s, lb);
-        if (!isfinite(h)) h = 0.f;
-        out[i] = h;
+        };
+        int t = 0;
+        for (; t + UNR <= T; t += UNR) {
+            float v[UNR][CMAX][VEC];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    if (c < C) load(t + u, c, v[u][c]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) v[u][c][k] = 0.f;
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)                    // sample order kept
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k][c] += (double)v[u][c][k];
+        }
+        for (; t < T; ++t) {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                if (c < C) {
+                    float v[VEC];
+                    load(t, c, v);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k][c] += (double)v[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) out[img * P + p + k] = class_entropy<CMAX>(acc[k], T, C);
     }
+}
+
+template <int VEC>
+static void launch_sample_entropy(const float* samples, int64_t n_img, int T, int C, int64_t P, float* out, cudaStream_t st) {
+    const int64_t total = n_img * (P / VEC);
+    const int64_t blocks = (total + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 148 * 32 ? blocks : 148 * 32);
+    if (C == 1) sample_entropy_kernel<VEC, 1, 4><<<grid, 256, 0, st>>>(samples, n_img, T, C, P, out);
+    else if (C == 2) sample_entropy_kernel<VEC, 2, 4><<<grid, 256, 0, st>>>(samples, n_img, T, C, P, out);
+    else if (C == 3) sample_entropy_kernel<VEC, 3, 4><<<grid, 256, 0, st>>>(samples, n_img, T, C, P, out);
+    else if (C == 4) sample_entropy_kernel<VEC, 4, 2><<<grid, 256, 0, st>>>(samples, n_img, T, C, P, out);
+    else sample_entropy_kernel<VEC, SE_MAXC, 1><<<grid, 256, 0, st>>>(samples, n_img, T, C, P, out);
 }
 }  // namespace cub200
 
@@ -235,9 +292,8 @@ extern "C" int cub200_sample_entropy(const float* samples, int64_t n_img, int n_
     if (n_img == 0 || n_pixels == 0) return 0;
     if (!samples || !entropy_out || n_img < 0 || n_pixels < 0 || n_samples < 1 || n_classes < 1 || n_classes > SE_MAXC)
         return CUB200_EINVAL;
-    const int64_t total = n_img * n_pixels;
-    const int64_t blocks = (total + 255) / 256;
-    sample_entropy_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-        samples, n_img, n_samples, n_classes, n_pixels, entropy_out);
+    const bool vec = (n_pixels % 4 == 0) && !((reinterpret_cast<uintptr_t>(samples) | reinterpret_cast<uintptr_t>(entropy_out)) & 15);
+    if (vec) launch_sample_entropy<4>(samples, n_img, n_samples, n_classes, n_pixels, entropy_out, (cudaStream_t)stream);
+    else launch_sample_entropy<1>(samples, n_img, n_samples, n_classes, n_pixels, entropy_out, (cudaStream_t)stream);
     return check_launch("sample_entropy_kernel");
 }

@@ -34,3 +34,21 @@ def test_class_entropy_golden_and_mirror():
     assert np.abs(m - g["e3"][0]).max() < 2e-6
     with pytest.raises(ValueError):
         E.sample_entropy(torch.zeros((1, 2, 9, 8, 8), device=dev))
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 3, 16, 16), (2, 7, 1, 8, 12), (1, 9, 2, 7, 9), (1, 6, 4, 8, 8), (1, 3, 6, 4, 4), (1, 1, 8, 5, 5)])
+def test_odd_sample_counts_class_counts_and_unaligned_maps(shape):
+    """Sample counts off the unroll factor, every class-count specialisation, maps whose size is not a multiple of 4."""
+    from contouring_uncertainty_b200 import engine as E
+    from oracle import port
+
+    rng = np.random.default_rng(sum(shape))
+    z = rng.normal(0, 2.0, shape).astype(np.float32)
+    if shape[2] == 1:
+        p = (1.0 / (1.0 + np.exp(-z))).astype(np.float32)
+    else:
+        p = np.exp(z - z.max(2, keepdims=True))
+        p = (p / p.sum(2, keepdims=True)).astype(np.float32)
+    got = E.sample_entropy(torch.from_numpy(p).to("cuda:0")).cpu().numpy()
+    want = np.array([port.sample_entropy_general(x) for x in p])
+    assert np.abs(got - want).max() < 2e-6
