@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CUB200_LIB") or os.path.join(_HERE, "lib", "libcub200.so")
 
 EINVAL, ECUDA = -1, -2
+EXPECTED_ABI = 18          # the version of include/cub200.h the SIGNATURES table below was written for
 
 _lib: Optional[C.CDLL] = None
 
@@ -26,7 +27,7 @@ SIGNATURES = {
     "cub200_psm_model_pack_host": [_vp, _vp, _vp, _vp, _vp],
     "cub200_psm_factor": [_vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
-    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
+    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
     "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],
@@ -74,6 +75,11 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                 "There is no CPU / PyTorch fallback for this path.")
         l = C.CDLL(LIB_PATH)
+        l.cub200_abi_version.restype = C.c_int
+        have = l.cub200_abi_version()
+        if have != EXPECTED_ABI:
+            raise NativeError(f"{LIB_PATH} has ABI version {have}, this package binds version {EXPECTED_ABI}: rebuild it "
+                              "(`python __graft_entry__.py --force`)")
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes

@@ -20,5 +20,5 @@ int check_launch(const char* what) {
 }  // namespace cub200
 
 extern "C" const char* cub200_last_error(void) { return cub200::g_err; }
-extern "C" int cub200_abi_version(void) { return 17; }
+extern "C" int cub200_abi_version(void) { return 18; }
 extern "C" int cub200_built_for_sm(void) { return 100; }

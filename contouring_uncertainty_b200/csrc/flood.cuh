@@ -11,15 +11,35 @@ constexpr int BMP_WORDS = 32 * BAND_STRIDE;     // 2176
 
 __device__ __forceinline__ int bmp_addr(int row, int word) { return row * 8 + word + (row >> 3) * 4; }
 
+// 256-bit add / subtract as ONE asm statement each: the carry flag lives only inside the statement, so the compiler cannot
+// schedule anything between the links of the chain (separate non-volatile asm statements have no dependence through CC.CF).
+__device__ __forceinline__ void add256(uint32_t (&x)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    asm volatile("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\taddc.cc.u32 %3, %11, %19;\n\t"
+                 "addc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\taddc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+                   "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+// x = a - 1 over 256 bits
+__device__ __forceinline__ void dec256(uint32_t (&x)[8], const uint32_t (&a)[8]) {
+    asm volatile("sub.cc.u32 %0, %8, 1;\n\tsubc.cc.u32 %1, %9, 0;\n\tsubc.cc.u32 %2, %10, 0;\n\tsubc.cc.u32 %3, %11, 0;\n\t"
+                 "subc.cc.u32 %4, %12, 0;\n\tsubc.cc.u32 %5, %13, 0;\n\tsubc.cc.u32 %6, %14, 0;\n\tsubc.u32 %7, %15, 0;"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+}
+
 // Fill complete runs of F that contain a seed (seeds subset of F).  256-bit rows as 8 words,
 // bit b of word w = column 32w + b.  Add-with-carry trick, once upward and once on the
 // bit-reversed row (rare path: only rows where the flood actually advances vertically).
 static __device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8]) {
     uint32_t X[8];
     // upward: X = F + r
-    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(F[0]), "r"(r[0]));
+    {
+        uint32_t Fc[8], rc[8];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(F[w]), "r"(r[w]));
+        for (int w = 0; w < 8; ++w) { Fc[w] = F[w]; rc[w] = r[w]; }
+        add256(X, Fc, rc);
+    }
     uint32_t up[8];
 #pragma unroll
     for (int w = 0; w < 8; ++w) up[w] = (F[w] & ~X[w]) | r[w];
@@ -27,9 +47,7 @@ static __device__ __noinline__ void run_fill(const uint32_t F[8], uint32_t r[8])
     uint32_t Fr[8], rr[8];
 #pragma unroll
     for (int w = 0; w < 8; ++w) { Fr[w] = __brev(F[7 - w]); rr[w] = __brev(r[7 - w]); }
-    asm("add.cc.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(Fr[0]), "r"(rr[0]));
-#pragma unroll
-    for (int w = 1; w < 8; ++w) asm("addc.cc.u32 %0, %1, %2;" : "=r"(X[w]) : "r"(Fr[w]), "r"(rr[w]));
+    add256(X, Fr, rr);
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
         const uint32_t dn = Fr[7 - w] & ~X[7 - w];
@@ -99,9 +117,7 @@ __device__ __forceinline__ void flood_background(uint32_t (&R)[8][8], const uint
         } else {
             // seeded from the left and right frame borders: below the lowest / above the highest set bit of the row
             uint32_t X[8];
-            asm("sub.cc.u32 %0, %1, 1;" : "=r"(X[0]) : "r"(B[0]));
-#pragma unroll
-            for (int w = 1; w < 8; ++w) asm("subc.cc.u32 %0, %1, 0;" : "=r"(X[w]) : "r"(B[w]));
+            dec256(X, B);
             bool seen = false;
 #pragma unroll
             for (int w = 7; w >= 0; --w) {

@@ -1,5 +1,5 @@
 // K3  sample_raster_aggregate: Monte-Carlo contour sampler -> spline rasteriser -> background
-// flood -> streaming aggregation, ONE WARP PER SAMPLE, masks never leave shared memory.
+// flood -> streaming aggregation.  Masks never leave shared memory.
 //
 // Replaces (reference paths, cu/ = contour_uncertainty/):
 //   AleatoricUncertaintyTask.sample            cu/task/regression/aleatoric.py:54-78
@@ -8,8 +8,11 @@
 //   reconstruction / contour_spline            cu/utils/contour.py:9-40
 //   lv_area                                    cu/utils/clinical.py:92-93
 //
-// The mask rule is NOT point-in-polygon.  Per sample:
-//   1. contour = mu + A z (z replayed from memory or Philox4x32-10 + Box-Muller), lane k = landmark k
+// Two kernels:
+//   sample_contours_kernel  ONE THREAD PER SAMPLE: contour = mu + A z (z replayed from memory or Philox4x32-10 +
+//       Box-Muller), the image's factor staged in shared memory, contours written coalesced.  contour_samples is an
+//       output of the API anyway (168 B / sample), so the rasteriser simply reads it back.
+//   raster_kernel           ONE WARP PER SAMPLE, lane k = landmark k:
 //   2. landmarks -> round half-even -> int                         (camus/utils.py:43)
 //   3. interpolating cubic B-spline of FITPACK splprep(k=3, s=0): chord-length parameter, knots at
 //      u_2..u_{m-3} == the not-a-knot cubic spline through (u_i, p_i); solved in fp64 as a
@@ -21,11 +24,21 @@
 //   5. Bresenham closing line landmark 20 -> 0 (skimage.draw.line), clipped to the frame (:36-38)
 //   6. scipy.ndimage.binary_fill_holes == complement of the 4-connected background reachable from
 //      outside the frame                                           (:39)
-//   7. area = popcount; every run boundary of every mask row becomes a +1 / -1 red.global into the
+//      FAST PATH (every sample of a well-behaved contour): the flood seeded from the left and right frame borders
+//      reaches, in every row, exactly the pixels outside [first, last boundary pixel]; it can only go further by
+//      stepping VERTICALLY onto a free pixel inside a row's span, i.e. onto a pixel of the span that lies outside the
+//      span of the row above or below.  So: per row the span [xs, xe) and the lengths of the boundary runs that start
+//      at xs and end at xe - 1; if in every row the part of the span not covered by both neighbour spans is covered by
+//      those runs, the seeded flood is the fixed point and the mask is the spans (lane = row, 8 x 32 rows, row groups
+//      without a boundary pixel are skipped by the whole warp).  Exact, not a heuristic.
+//      SLOW PATH (concave / self-intersecting samples, contours touching rows 0 / 255): the bit-parallel flood with
+//      Gauss-Seidel vertical sweeps (flood.cuh), lane = band of 8 rows.
+//   7. area = mask pixels; every run boundary of every mask row becomes a +1 / -1 red.global into the
 //      image's difference map (the row prefix sum of which is the per-pixel count).
 //
-// Shared memory per warp: the 256x256 boundary bitmap (8 rows per lane, padded band stride 68
-// words so the 128-bit band loads are bank-conflict free) + ~2 KB of spline scratch.
+// Shared memory per warp: the 256x256 boundary bitmap (band stride 68 words: the 128-bit row loads are bank-conflict
+// free) + 1.7 KB of spline pieces.
+#include <climits>
 #include "common.cuh"
 #include "flood.cuh"
 #include "spline.cuh"
@@ -33,7 +46,7 @@
 namespace cub200 {
 
 #ifndef CUB200_FW_WARPS
-#define CUB200_FW_WARPS 8
+#define CUB200_FW_WARPS 11
 #endif
 #ifndef CUB200_FW_MINBLOCKS
 #define CUB200_FW_MINBLOCKS 2
@@ -47,8 +60,7 @@ constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px be
 
 struct __align__(16) WarpScratch {
     uint32_t bmp[BMP_WORDS];
-    SplineScratch sp;
-    float z[CUB200_ZMAX + 2];
+    SplineScratchIdx sp;
 };
 
 // ---------------------------------------------------------------- bitmap helpers
@@ -58,7 +70,7 @@ __device__ __forceinline__ void set_pixel(uint32_t* bmp, int row, int col) {
 
 // Generic run extraction of one mask row (mask = ~R): every transition of R along the row (virtual
 // R = 1 left of column 0) is +1 where the mask starts, -1 one past where it ends.  Returns the row's
-// mask area.  Rare path (frame-border rows, rows of concave / self-intersecting samples).
+// mask area.  Slow path only.
 __device__ __noinline__ int emit_row_generic(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
                                              uint32_t r5, uint32_t r6, uint32_t r7, int32_t* drow) {
     const uint32_t Rw[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
@@ -80,22 +92,82 @@ __device__ __noinline__ int emit_row_generic(uint32_t r0, uint32_t r1, uint32_t 
     return area;
 }
 
-// Take back the single run [first, last boundary pixel] that step 6a emitted for this row (rare).
-__device__ __noinline__ int undo_row_span(const uint32_t* brow, int32_t* drow) {
-    int xs = -1, xe = 0;
-    for (int w = 0; w < 8; ++w) {
-        const uint32_t b = brow[w];
-        if (b) {
-            if (xs < 0) xs = 32 * w + __ffs(b) - 1;
-            xe = 32 * w + 32 - __clz(b);
+// Slow path of step 6/7: the bit-parallel flood of flood.cuh over the warp's bitmap, then the generic run extraction
+// of every row.  Lane owns rows 8*lane .. 8*lane+7.  Returns the lane's share of the mask area.
+__device__ __noinline__ int fill_slow(const uint32_t* bmp, int lane, int32_t* __restrict__ diff_img,
+                                      uint32_t* __restrict__ mask_out) {
+    uint32_t R[8][8];
+    const uint4* band4 = reinterpret_cast<const uint4*>(bmp + lane * BAND_STRIDE);
+    flood_background(R, band4, lane);
+    int area = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = lane * 8 + i;
+        if (mask_out) {
+            uint4* o = reinterpret_cast<uint4*>(mask_out + row * 8);
+            o[0] = make_uint4(~R[i][0], ~R[i][1], ~R[i][2], ~R[i][3]);
+            o[1] = make_uint4(~R[i][4], ~R[i][5], ~R[i][6], ~R[i][7]);
+        }
+        const uint32_t full = (R[i][0] & R[i][1] & R[i][2]) & (R[i][3] & R[i][4] & R[i][5]) & (R[i][6] & R[i][7]);
+        if (full != 0xffffffffu)
+            area += emit_row_generic(R[i][0], R[i][1], R[i][2], R[i][3], R[i][4], R[i][5], R[i][6], R[i][7],
+                                     diff_img ? diff_img + row * 256 : nullptr);
+    }
+    return area;
+}
+
+// Row descriptor of the fast path: xs | xe << 16; an empty row is xs = 256, xe = 0, which makes every min / max of the
+// neighbour test come out right without a special case.
+constexpr uint32_t ROW_EMPTY = 256u;
+
+// Span and end runs of one 256-bit row given as 8 words (bit b of word w = column 32 w + b), rowor != 0.
+// Returns xs | xe << 16 and lr = Lrun | Rrun << 16: Lrun = length of the run of set bits that starts at xs, Rrun = length of
+// the run that ends at xe - 1.  A run that reaches the end of its 32-bit word is continued through `brow` (shared memory).
+__device__ __forceinline__ uint32_t row_span(const uint4 b0, const uint4 b1, const uint32_t* brow, uint32_t& lr) {
+    // first non-zero word
+    const bool lo_half = (b0.x | b0.y | b0.z | b0.w) != 0u;
+    const uint32_t a0 = lo_half ? b0.x : b1.x, a1 = lo_half ? b0.y : b1.y, a2 = lo_half ? b0.z : b1.z, a3 = lo_half ? b0.w : b1.w;
+    int wf = lo_half ? 0 : 4;
+    const bool p01 = (a0 | a1) != 0u;
+    const uint32_t c0 = p01 ? a0 : a2, c1 = p01 ? a1 : a3;
+    wf += p01 ? 0 : 2;
+    const uint32_t fw = c0 ? c0 : c1;
+    wf += c0 ? 0 : 1;
+    // last non-zero word
+    const bool hi_half = (b1.x | b1.y | b1.z | b1.w) != 0u;
+    const uint32_t d0 = hi_half ? b1.x : b0.x, d1 = hi_half ? b1.y : b0.y, d2 = hi_half ? b1.z : b0.z, d3 = hi_half ? b1.w : b0.w;
+    int wl = hi_half ? 4 : 0;
+    const bool p23 = (d2 | d3) != 0u;
+    const uint32_t e0 = p23 ? d2 : d0, e1 = p23 ? d3 : d1;
+    wl += p23 ? 2 : 0;
+    const uint32_t lw = e1 ? e1 : e0;
+    wl += e1 ? 1 : 0;
+
+    const int bf = __ffs(fw) - 1;                              // fw != 0
+    int lrun = __ffs(~(fw >> bf)) - 1;                         // >> shifts zeros in: the complement is never 0 unless bf == 0 && fw == ~0
+    if (bf == 0 && fw == 0xffffffffu) lrun = 32;
+    const int cl = __clz(lw);
+    int rrun = __clz(~(lw << cl));
+    if (cl == 0 && lw == 0xffffffffu) rrun = 32;
+    const int xs = 32 * wf + bf, xe = 32 * wl + 32 - cl;
+    if (bf + lrun == 32) {                                     // the run goes on in the next word(s)
+        for (int w = wf + 1; w < 8; ++w) {
+            const uint32_t v = brow[w];
+            if (v == 0xffffffffu) { lrun += 32; continue; }
+            lrun += __ffs(~v) - 1;
+            break;
         }
     }
-    if (xs < 0) return 0;
-    if (drow) {
-        atomicAdd(drow + xs, -1);
-        if (xe < 256) atomicAdd(drow + xe, 1);
+    if (cl + rrun == 32) {
+        for (int w = wl - 1; w >= 0; --w) {
+            const uint32_t v = brow[w];
+            if (v == 0xffffffffu) { rrun += 32; continue; }
+            rrun += __clz(~v);
+            break;
+        }
     }
-    return xe - xs;
+    lr = (uint32_t)lrun | ((uint32_t)rrun << 16);
+    return (uint32_t)xs | ((uint32_t)xe << 16);
 }
 
 // ---------------------------------------------------------------- one sample, one warp
@@ -139,18 +211,15 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
         //       closing line is drawn afterwards).
         const int j0 = min(lane * 32, NPTS - 32);           // lane 31 re-draws 24 points of lane 30
         const double step = 1.0 / (double)(NPTS - 1);       // j * step == np.linspace(0, 1, 1000)[j] exactly
-        int piece = 0;
-        {
-            const double us = (double)j0 * step;
-#pragma unroll
-            for (int k = 1; k <= KP - 2; ++k) piece = (us >= ws.sp.u[k]) ? k : piece;
-        }
-        double un, ub, c0, c1, c2, c3, e0, e1, e2, e3;
+        int piece = ws.sp.start_piece[lane];
+        double ub, c0, c1, c2, c3, e0, e1, e2, e3;
+        int jnext;
 #define CUB200_LOAD_PIECE()                                                              \
         {                                                                                \
             const double2* pc = reinterpret_cast<const double2*>(ws.sp.piece[piece]);       \
             const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];    \
-            un = q0.x; ub = q0.y; c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;            \
+            jnext = __double_as_longlong(q0.x) & 0xffffffff; ub = q0.y;                  \
+            c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;                                  \
             e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                  \
         }
         CUB200_LOAD_PIECE();
@@ -158,16 +227,16 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
         int lowest = 0;
 #pragma unroll 4
         for (int jj = 0; jj < 32; ++jj) {
-            const double uj = (double)(j0 + jj) * step;
-            while (piece < KP - 2 && uj >= un) {
+            const int j = j0 + jj;
+            while (j >= jnext) {                             // jnext of the last piece is INT_MAX
                 ++piece;
                 CUB200_LOAD_PIECE();
             }
-            const double sv = uj - ub;
+            const double sv = (double)j * step - ub;
             const double xv = fma(fma(fma(c3, sv, c2), sv, c1), sv, c0);
             const double yv = fma(fma(fma(e3, sv, e2), sv, e1), sv, e0);
             const int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
-            lowest = min(lowest, min(ix, iy));
+            lowest = __vimin3_s32(lowest, ix, iy);
             // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
             const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
             if (cell != cur) {
@@ -194,113 +263,78 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
         oob = __any_sync(FULL, oob);
         if (!oob && lane < KP) set_pixel(bmp, iy & 255, ix & 255);
     }
+    __syncwarp();
 
-    // 5. closing line (r0,c0) = landmark 20 -> (r1,c1) = landmark 0, skimage.draw.line closed form:
-    //    pixel i < dmaj: major = m0 + i*smaj, minor = n0 + smin * floor((2*dmin*i + dmaj) / (2*dmaj));
-    //    pixel dmaj = (r1, c1).  linear_reconstruction draws all 21 edges k -> k+1 this way.
+    // 5. closing line (r0,c0) = landmark 20 -> (r1,c1) = landmark 0; linear_reconstruction draws all 21 edges k -> k+1
 #pragma unroll 1
     for (int e = linear ? 0 : KP - 1; e < KP; ++e) {
         const int e1 = (e + 1 == KP) ? 0 : e + 1;
-        const int r0 = __shfl_sync(FULL, riy, e), c0 = __shfl_sync(FULL, rix, e);
-        const int r1 = __shfl_sync(FULL, riy, e1), c1 = __shfl_sync(FULL, rix, e1);
-        const int dr = abs(r1 - r0), dc = abs(c1 - c0);
-        const int sc = (c1 - c0) > 0 ? 1 : -1, sr = (r1 - r0) > 0 ? 1 : -1;
-        const bool steep = dr > dc;
-        const int dmaj = steep ? dr : dc, dmin = steep ? dc : dr;
-        for (int i = lane; i <= dmaj; i += 32) {
-            int rr, cc;
-            if (i == dmaj) { rr = r1; cc = c1; }
-            else {
-                const int nmin = (2 * dmin * i + dmaj) / (2 * dmaj);
-                if (steep) { rr = r0 + i * sr; cc = c0 + nmin * sc; }
-                else { cc = c0 + i * sc; rr = r0 + nmin * sr; }
-            }
-            rr = min(max(rr, 0), 255); cc = min(max(cc, 0), 255);
-            set_pixel(bmp, rr, cc);
-        }
+        draw_line_clipped(bmp, __shfl_sync(FULL, riy, e), __shfl_sync(FULL, rix, e), __shfl_sync(FULL, riy, e1),
+                          __shfl_sync(FULL, rix, e1), lane);
     }
     __syncwarp();
 
-    // 6. background flood.  Lane owns rows 8*lane .. 8*lane+7; R = reached-from-outside.
-    uint32_t R[8][8];
-    uint32_t generic = 0;        // bit i: row i needs the generic run extraction (border rows, rows the
-                                 // vertical flood advanced in)
-    int area = 0;
-    const uint4* band4 = reinterpret_cast<const uint4*>(bmp + lane * BAND_STRIDE);
-    // 6a. rows are seeded from the left and right frame borders: everything left of the first and
-    //     right of the last boundary pixel of the row; rows 0 and 255 are seeded everywhere.
+    // 6. fast path: lane = row 32 i + lane.  Spans and end runs of the rows ...
+    uint32_t d[8], lr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint4 b0 = band4[2 * i], b1 = band4[2 * i + 1];
-        const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const uint32_t rowor = (B[0] | B[1] | B[2]) | (B[3] | B[4] | B[5]) | (B[6] | B[7]);
-        const bool border_row = (lane == 0 && i == 0) || (lane == 31 && i == 7);
-        if (rowor == 0u) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) R[i][w] = 0xffffffffu;
-        } else if (border_row) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) R[i][w] = ~B[w];
-            generic |= 1u << i;
-        } else {
-            // left part: bits below the lowest set bit of the 256-bit row = (B - 1) & ~B
-            uint32_t X[8];
-            asm("sub.cc.u32 %0, %1, 1;" : "=r"(X[0]) : "r"(B[0]));
-#pragma unroll
-            for (int w = 1; w < 8; ++w) asm("subc.cc.u32 %0, %1, 0;" : "=r"(X[w]) : "r"(B[w]));
-            // right part: bits above the highest set bit
-            bool seen = false;
-            int nlow = 0, nhigh = 0;
-#pragma unroll
-            for (int w = 7; w >= 0; --w) {
-                const uint32_t smear = __funnelshift_rc(0xffffffffu, 0u, __clz(B[w]));  // 0 when B[w] == 0
-                const uint32_t lo = X[w] & ~B[w], hi = seen ? 0u : ~smear;
-                R[i][w] = lo | hi;
-                nlow += __popc(lo);
-                nhigh += __popc(hi);
-                seen |= (B[w] != 0u);
-            }
-            // An ordinary row holds the single run [first, last boundary pixel] unless the vertical
-            // flood later advances in it: emit it now (+1 at its start, -1 one past its end).
-            const int xs = nlow, xe = 256 - nhigh;
-            area += xe - xs;
-            if (diff_img) {
-                int32_t* drow = diff_img + (lane * 8 + i) * 256;
-                atomicAdd(drow + xs, 1);
-                if (xe < 256) atomicAdd(drow + xe, -1);
-            }
+        const int row = 32 * i + lane;
+        const uint32_t* brow = bmp + bmp_addr(row, 0);
+        const uint4 b0 = reinterpret_cast<const uint4*>(brow)[0], b1 = reinterpret_cast<const uint4*>(brow)[1];
+        const uint32_t rowor = (b0.x | b0.y | b0.z) | (b0.w | b1.x | b1.y) | (b1.z | b1.w);
+        d[i] = ROW_EMPTY; lr[i] = 0u;
+        if (__any_sync(FULL, rowor != 0u)) {                 // warp-uniform: row groups outside the contour cost 8 instructions
+            if (rowor != 0u) d[i] = row_span(b0, b1, brow, lr[i]);
         }
     }
-    // 6b. vertical propagation to a fixed point: alternating Gauss-Seidel sweeps inside the band
-    //     (neighbour lanes' edge rows by shuffle), stopping after the first sweep in which no lane
-    //     advanced.  Convex-ish contours exit after one quiescent sweep.
-    for (;;) {
-        uint32_t touched = flood_sweep<0>(R, band4, lane);
-        generic |= touched;
-        if (!__any_sync(FULL, touched != 0u)) break;
-        touched = flood_sweep<1>(R, band4, lane);
-        generic |= touched;
-        if (!__any_sync(FULL, touched != 0u)) break;
+    // ... then the exact test that the border-seeded flood cannot advance vertically anywhere.
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        // spans of the rows above and below: neighbour lanes, across a row group lane 31 <-> lane 0 of the next group
+        uint32_t up = __shfl_up_sync(FULL, d[i], 1), dn = __shfl_down_sync(FULL, d[i], 1);
+        const uint32_t up_x = __shfl_sync(FULL, d[i > 0 ? i - 1 : 0], 31), dn_x = __shfl_sync(FULL, d[i < 7 ? i + 1 : 7], 0);
+        if (lane == 0) up = (i > 0) ? up_x : ROW_EMPTY;
+        if (lane == 31) dn = (i < 7) ? dn_x : ROW_EMPTY;
+        const int xs = d[i] & 0xffff, xe = d[i] >> 16;
+        const int need_l = min(max((int)(up & 0xffff), (int)(dn & 0xffff)), xe) - xs;
+        const int need_r = xe - max(min((int)(up >> 16), (int)(dn >> 16)), xs);
+        const bool row_ok = need_l <= (int)(lr[i] & 0xffff) && need_r <= (int)(lr[i] >> 16);
+        ok = ok && (d[i] == ROW_EMPTY || row_ok);
     }
+    // the frame-border rows 0 and 255 are seeded everywhere: a boundary pixel there needs the general flood
+    if ((lane == 0 && d[0] != ROW_EMPTY) || (lane == 31 && d[7] != ROW_EMPTY)) ok = false;
 
-    // 7. mask = not reached.  Ordinary rows were emitted in 6a.  Rows the vertical flood advanced in
-    //    (concave / self-intersecting samples) take their 6a run back and go, like the frame-border
-    //    rows, through the generic run extraction.
-    const bool top = (lane == 0), bottom = (lane == 31);
+    int area = 0;
+    if (__all_sync(FULL, ok)) {
+        // 7. mask rows = spans
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = lane * 8 + i;
-        if (mask_out) {
-            uint4* o = reinterpret_cast<uint4*>(mask_out + row * 8);
-            o[0] = make_uint4(~R[i][0], ~R[i][1], ~R[i][2], ~R[i][3]);
-            o[1] = make_uint4(~R[i][4], ~R[i][5], ~R[i][6], ~R[i][7]);
+        for (int i = 0; i < 8; ++i) {
+            const bool any = __any_sync(FULL, d[i] != ROW_EMPTY);
+            const int row = 32 * i + lane;
+            const int xs = d[i] & 0xffff, xe = d[i] >> 16;
+            if (any && d[i] != ROW_EMPTY) {
+                area += xe - xs;
+                if (diff_img) {
+                    int32_t* drow = diff_img + row * 256;
+                    atomicAdd(drow + xs, 1);
+                    if (xe < 256) atomicAdd(drow + xe, -1);
+                }
+            }
+            if (mask_out) {
+                uint32_t m[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const int lo = max(xs - 32 * w, 0), hi = min(xe - 32 * w, 32);
+                    m[w] = (hi > lo) ? ((0xffffffffu >> (32 - hi)) & (0xffffffffu << lo)) : 0u;
+                }
+                uint4* o = reinterpret_cast<uint4*>(mask_out + row * 8);
+                o[0] = make_uint4(m[0], m[1], m[2], m[3]);
+                o[1] = make_uint4(m[4], m[5], m[6], m[7]);
+            }
         }
-        if ((generic >> i) & 1u) {
-            int32_t* drow = diff_img ? diff_img + row * 256 : nullptr;
-            const bool border_row = (top && i == 0) || (bottom && i == 7);
-            if (!border_row) area -= undo_row_span(bmp + lane * BAND_STRIDE + i * 8, drow);
-            area += emit_row_generic(R[i][0], R[i][1], R[i][2], R[i][3], R[i][4], R[i][5], R[i][6], R[i][7], drow);
-        }
+    } else {
+        area = fill_slow(bmp, lane, diff_img, mask_out);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(FULL, area, o);
@@ -309,135 +343,220 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
 }
 
 // ---------------------------------------------------------------- kernels
-template <bool FROM_CONTOURS>
+// contour = mu + A z, one thread per sample, block = SC_THREADS samples of one image (blockIdx.x = image * chunks + chunk).
+constexpr int SC_THREADS = 64;
+constexpr int SC_PAD = CUB200_P + 1;            // staging row stride (floats): conflict-free column access
+
+// The draws of global sample gc (Philox counter (gc, q), key = seed): 4 normals per call, z[4q .. 4q+3].
+__device__ __forceinline__ void philox_normals4(uint64_t gc, int q, uint64_t seed, float& n0, float& n1, float& n2, float& n3) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)q, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    box_muller(r[0], r[1], n0, n1);
+    box_muller(r[2], r[3], n2, n3);
+}
+
+template <int ZD>
+__global__ void __launch_bounds__(SC_THREADS)
+sample_contours_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim, const float* __restrict__ z,
+                       uint64_t seed, uint64_t g_offset, int64_t n_samples, int chunks, float* __restrict__ contours_out) {
+    __shared__ __align__(16) float a_s[CUB200_ZMAX * CUB200_P];
+    __shared__ float out_s[SC_THREADS * SC_PAD];
+    const int64_t img = blockIdx.x / chunks;
+    const int64_t s0 = (int64_t)(blockIdx.x % chunks) * SC_THREADS;
+    const int tid = threadIdx.x;
+    const int nz = ZD > 0 ? ZD : zdim;
+    for (int e = tid; e < nz * CUB200_P; e += SC_THREADS) a_s[e] = a_t[img * (int64_t)nz * CUB200_P + e];
+    __syncthreads();
+    const int64_t s = s0 + tid;
+    const int n_here = (int)min((int64_t)SC_THREADS, n_samples - s0);
+    if (s < n_samples) {
+        const int64_t g = img * n_samples + s;
+        float zz[CUB200_ZMAX + 2];
+        if (z) {
+#pragma unroll
+            for (int e = 0; e < CUB200_ZMAX; ++e) zz[e] = (e < nz) ? z[g * nz + e] : 0.f;
+        } else {
+            const uint64_t gc = (uint64_t)g + g_offset;      // draws keyed by (seed, global sample index)
+#pragma unroll
+            for (int q = 0; q < (CUB200_ZMAX + 3) / 4; ++q) {
+                if (4 * q < nz) philox_normals4(gc, q, seed, zz[4 * q], zz[4 * q + 1], zz[4 * q + 2], zz[4 * q + 3]);
+                else zz[4 * q] = zz[4 * q + 1] = zz[4 * q + 2] = zz[4 * q + 3] = 0.f;
+            }
+        }
+        const float2* mu2 = reinterpret_cast<const float2*>(mu) + img * KP;
+        const float2* a2 = reinterpret_cast<const float2*>(a_s);
+#pragma unroll 3
+        for (int k = 0; k < KP; ++k) {
+            const float2 m = __ldg(mu2 + k);
+            float fx = m.x, fy = m.y;
+#pragma unroll
+            for (int e = 0; e < CUB200_ZMAX; ++e) {
+                if (e < nz) {                                 // same order as a sequential dot product over the draws
+                    const float2 a = a2[e * KP + k];
+                    fx = fmaf(a.x, zz[e], fx);
+                    fy = fmaf(a.y, zz[e], fy);
+                }
+            }
+            out_s[tid * SC_PAD + 2 * k] = fx;
+            out_s[tid * SC_PAD + 2 * k + 1] = fy;
+        }
+    }
+    __syncthreads();
+    float* dst = contours_out + (img * n_samples + s0) * CUB200_P;
+    for (int e = tid; e < n_here * CUB200_P; e += SC_THREADS) dst[e] = out_s[(e / CUB200_P) * SC_PAD + (e % CUB200_P)];
+}
+
+// Few samples per factor (the sequence sampler draws ONE contour from each of its per-sample factors): one warp per sample,
+// lane k = landmark k, the factor streamed from global memory (coalesced rows).  Same draws, same summation order.
+constexpr int SW_WARPS = 8;
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sample_contours_warp_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim, const float* __restrict__ z,
+                            uint64_t seed, uint64_t g_offset, int64_t n_img, int64_t n_samples, float* __restrict__ contours_out) {
+    __shared__ float z_s[SW_WARPS][CUB200_ZMAX + 2];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    float* zw = z_s[warp];
+    const int64_t total = n_img * n_samples;
+    for (int64_t g = (int64_t)blockIdx.x * SW_WARPS + warp; g < total; g += (int64_t)gridDim.x * SW_WARPS) {
+        const int64_t img = g / n_samples;
+        if (z) {
+            for (int e = lane; e < zdim; e += 32) zw[e] = z[g * zdim + e];
+        } else if (lane * 4 < zdim) {
+            philox_normals4((uint64_t)g + g_offset, lane, seed, zw[4 * lane], zw[4 * lane + 1], zw[4 * lane + 2], zw[4 * lane + 3]);
+        }
+        __syncwarp();
+        if (lane < KP) {
+            const float2 m = reinterpret_cast<const float2*>(mu)[img * KP + lane];
+            float fx = m.x, fy = m.y;
+            const float2* a = reinterpret_cast<const float2*>(a_t + img * (int64_t)zdim * CUB200_P) + lane;
+            for (int e0 = 0; e0 < zdim; e0 += 8) {            // 8 factor rows in flight
+                float2 av[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) av[q] = (e0 + q < zdim) ? __ldg(a + (e0 + q) * KP) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (e0 + q < zdim) {
+                        fx = fmaf(av[q].x, zw[e0 + q], fx);
+                        fy = fmaf(av[q].y, zw[e0 + q], fy);
+                    }
+                }
+            }
+            reinterpret_cast<float2*>(contours_out)[g * KP + lane] = make_float2(fx, fy);
+        }
+        __syncwarp();
+    }
+}
+
+template <bool F64>
 __global__ void __launch_bounds__(FW_THREADS, FW_MINBLOCKS)
-sample_raster_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim,
-                     const float* __restrict__ z, uint64_t seed, int64_t n_img, int64_t n_samples,
-                     int round_landmarks, const float* __restrict__ contours_in, const double* __restrict__ contours_in64,
-                     float* __restrict__ contours_out, int32_t* __restrict__ area_out,
-                     int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image) {
+raster_kernel(const void* __restrict__ contours_in, int64_t n, int flags, int32_t* __restrict__ area_out,
+              int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
-    const int64_t total = FROM_CONTOURS ? n_samples : n_img * n_samples;
-    // each CTA walks a contiguous chunk of samples, so its 8 warps share the image's factor in L1
-    const int64_t chunk = (total + gridDim.x - 1) / gridDim.x;
-    const int64_t g_end = min(total, (int64_t)(blockIdx.x + 1) * chunk);
-    for (int64_t g = (int64_t)blockIdx.x * chunk + (threadIdx.x >> 5); g < g_end; g += FW_WARPS) {
-        float fx = 0.f, fy = 0.f;
-        double dx = 0.0, dy = 0.0;
-        int64_t img, map;
-        if (FROM_CONTOURS) {
-            img = per_image > 0 ? g / per_image : 0;
-            map = img;
-            if (lane < KP) {
-                if (contours_in64) {
-                    const double2 p = reinterpret_cast<const double2*>(contours_in64)[g * KP + lane];
-                    dx = p.x; dy = p.y;
-                } else {
-                    const float2 p = reinterpret_cast<const float2*>(contours_in)[g * KP + lane];
-                    dx = p.x; dy = p.y;
-                }
+    const int64_t stride = (int64_t)gridDim.x * FW_WARPS;
+    int64_t g = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
+    auto load = [&](int64_t gg, double& x, double& y) {
+        x = 0.0; y = 0.0;
+        if (gg < n && lane < KP) {
+            if (F64) {
+                const double2 p = reinterpret_cast<const double2*>(contours_in)[gg * KP + lane];
+                x = p.x; y = p.y;
+            } else {
+                const float2 p = reinterpret_cast<const float2*>(contours_in)[gg * KP + lane];
+                x = p.x; y = p.y;
             }
-        } else {
-            img = g / n_samples;
-            map = img / per_image;                          // per_image = images_per_map here
-            // 1. draws
-            if (z) {
-                for (int e = lane; e < zdim; e += 32) ws.z[e] = z[g * zdim + e];
-            } else if (lane * 4 < zdim) {
-                uint32_t r[4];
-                philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)lane, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-                float n0, n1, n2, n3;
-                box_muller(r[0], r[1], n0, n1);
-                box_muller(r[2], r[3], n2, n3);
-                ws.z[4 * lane] = n0; ws.z[4 * lane + 1] = n1; ws.z[4 * lane + 2] = n2; ws.z[4 * lane + 3] = n3;
-            }
-            __syncwarp();
-            if (lane < KP) {
-                const float2 m = reinterpret_cast<const float2*>(mu)[img * KP + lane];
-                fx = m.x; fy = m.y;
-                const float2* a = reinterpret_cast<const float2*>(a_t + img * (int64_t)zdim * CUB200_P) + lane;
-                for (int e0 = 0; e0 < zdim; e0 += 8) {            // 8 factor rows in flight
-                    float2 av[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) av[q] = (e0 + q < zdim) ? __ldg(a + (e0 + q) * KP) : make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float ze = (e0 + q < zdim) ? ws.z[e0 + q] : 0.f;
-                        fx = fmaf(av[q].x, ze, fx);
-                        fy = fmaf(av[q].y, ze, fy);
-                    }
-                }
-                if (contours_out) reinterpret_cast<float2*>(contours_out)[g * KP + lane] = make_float2(fx, fy);
-            }
-            __syncwarp();
-            if (!diff && !area_out && !masks_out) continue;     // sample-only call
         }
-        if (!FROM_CONTOURS) { dx = fx; dy = fy; }
-        const int area = raster_sample(ws, dx, dy, round_landmarks,
-                                       diff ? diff + map * 65536 : nullptr,
+    };
+    double nx, ny;
+    load(g, nx, ny);
+    for (; g < n; g += stride) {
+        const double dx = nx, dy = ny;
+        load(g + stride, nx, ny);                            // the next contour is in flight while this one is rasterised
+        const int64_t map = per_image > 0 ? g / per_image : 0;
+        const int area = raster_sample(ws, dx, dy, flags, diff ? diff + map * 65536 : nullptr,
                                        masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
         if (area_out && lane == 0) area_out[g] = area;
     }
 }
 
-static int launch_cfg(int64_t total, const void* kernel, int* grid_out) {
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        CUB200_CUDA_OK(cudaGetDevice(&dev));
-        CUB200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+static int sm_count(int* out) {
+    // per device (the library serves several GPUs of one process), benign race: every thread writes the same value
+    static int cache[64] = {0};
+    int dev = 0;
+    CUB200_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !cache[dev]) {
+        int v = 0;
+        CUB200_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) cache[dev] = v;
+        *out = v;
+        return 0;
     }
-    CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
-    const int64_t need = (total + FW_WARPS - 1) / FW_WARPS;
-    const int64_t cap = (int64_t)num_sms * FW_MINBLOCKS;   // resident CTAs per SM; each walks a contiguous chunk
-    *grid_out = (int)(need < cap ? need : cap);
+    *out = cache[dev];
     return 0;
+}
+
+static int launch_raster(const void* contours, bool f64, int64_t n, int flags, int32_t* area_out, int32_t* diff,
+                         uint32_t* masks_out, int64_t per_image, cudaStream_t stream) {
+    int num_sms = 0;
+    int rc = sm_count(&num_sms);
+    if (rc) return rc;
+    const void* kernel = f64 ? (const void*)raster_kernel<true> : (const void*)raster_kernel<false>;
+    CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
+    const int64_t need = (n + FW_WARPS - 1) / FW_WARPS;
+    const int64_t cap = (int64_t)num_sms * FW_MINBLOCKS;   // resident CTAs; warps stride over the samples
+    const int grid = (int)(need < cap ? need : cap);
+    if (f64)
+        raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image);
+    else
+        raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image);
+    return check_launch("raster_kernel");
 }
 
 }  // namespace cub200
 
 extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
-                                              uint64_t seed, int64_t n_img, int64_t n_samples,
+                                              uint64_t seed, uint64_t sample_offset, int64_t n_img, int64_t n_samples,
                                               int round_landmarks, float* contours_out, int32_t* area_out,
                                               int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* stream) {
     using namespace cub200;
     if (!mu || !a_t || zdim < 1 || zdim > CUB200_ZMAX || n_img < 0 || n_samples < 0) return CUB200_EINVAL;
     if (images_per_map < 1 || n_img % images_per_map) return CUB200_EINVAL;
-    if (!diff && !area_out && !masks_out && !contours_out) return CUB200_EINVAL;
+    if (!contours_out) return CUB200_EINVAL;                 // also the staging buffer between the two kernels
     const int64_t total = n_img * n_samples;
     if (total == 0) return 0;
-    int grid = 0;
-    int rc = launch_cfg(total, (const void*)sample_raster_kernel<false>, &grid);
-    if (rc) return rc;
-    sample_raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
-        mu, a_t, zdim, z, seed, n_img, n_samples, round_landmarks, nullptr, nullptr, contours_out, area_out, diff, masks_out, images_per_map);
-    return check_launch("sample_raster_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_samples < SC_THREADS / 2) {
+        const int64_t need = (total + SW_WARPS - 1) / SW_WARPS;
+        const int grid = (int)(need < 148 * 16 ? need : 148 * 16);
+        sample_contours_warp_kernel<<<grid, SW_WARPS * 32, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_img, n_samples, contours_out);
+    } else {
+        const int64_t chunks = (n_samples + SC_THREADS - 1) / SC_THREADS;
+        if (n_img * chunks > 0x7fffffffLL) return CUB200_EINVAL;
+        const unsigned grid = (unsigned)(n_img * chunks);
+        if (zdim == 34)
+            sample_contours_kernel<34><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out);
+        else if (zdim == 42)
+            sample_contours_kernel<42><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out);
+        else
+            sample_contours_kernel<0><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out);
+    }
+    int rc = check_launch("sample_contours_kernel");
+    if (rc || (!diff && !area_out && !masks_out)) return rc;  // sample-only call
+    return launch_raster(contours_out, false, total, round_landmarks, area_out, diff, masks_out, n_samples * images_per_map, st);
 }
 
 extern "C" int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
                                          int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
     using namespace cub200;
     if (n == 0) return 0;
-    if (!contours || n < 0 || (diff && per_image <= 0)) return CUB200_EINVAL;
-    int grid = 0;
-    int rc = launch_cfg(n, (const void*)sample_raster_kernel<true>, &grid);
-    if (rc) return rc;
-    sample_raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
-        nullptr, nullptr, 0, nullptr, 0, 0, n, round_landmarks, contours, nullptr, nullptr, area_out, diff, masks_out, per_image);
-    return check_launch("sample_raster_kernel<contours>");
+    if (!contours || n < 0 || (diff && (per_image <= 0 || n % per_image))) return CUB200_EINVAL;
+    return launch_raster(contours, false, n, round_landmarks, area_out, diff, masks_out, per_image, (cudaStream_t)stream);
 }
 
 extern "C" int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
                                              int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
     using namespace cub200;
     if (n == 0) return 0;
-    if (!contours || n < 0 || (diff && per_image <= 0)) return CUB200_EINVAL;
-    int grid = 0;
-    int rc = launch_cfg(n, (const void*)sample_raster_kernel<true>, &grid);
-    if (rc) return rc;
-    sample_raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, (cudaStream_t)stream>>>(
-        nullptr, nullptr, 0, nullptr, 0, 0, n, round_landmarks, nullptr, contours, nullptr, area_out, diff, masks_out, per_image);
-    return check_launch("sample_raster_kernel<contours f64>");
+    if (!contours || n < 0 || (diff && (per_image <= 0 || n % per_image))) return CUB200_EINVAL;
+    return launch_raster(contours, true, n, round_landmarks, area_out, diff, masks_out, per_image, (cudaStream_t)stream);
 }

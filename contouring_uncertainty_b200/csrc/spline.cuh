@@ -5,6 +5,8 @@
 // u_2..u_{m-3} == the not-a-knot cubic spline through (u_i, p_i): solved as a tridiagonal system for the second
 // derivatives by parallel cyclic reduction in registers and stored as 20 polynomial pieces.
 #pragma once
+#include <climits>
+#include <type_traits>
 #include "common.cuh"
 
 namespace cub200 {
@@ -24,10 +26,32 @@ struct __align__(16) SplineScratch {
     double piece[20][10];  // piece i on [u_i, u_{i+1}]: {u_{i+1}, u_i, x c0..c3, y c0..c3} (powers of u - u_i)
 };
 
+// Layout of the rasteriser's hot loop (fused.cu): the knots are replaced by the INDEX of the first of the 1000 evaluation
+// points that belongs to a later piece, so the per-point piece test is an integer comparison.
+struct __align__(16) SplineScratchIdx {
+    double piece[20][10];  // {jnext (int32 in the low word), u_i, x c0..c3, y c0..c3}
+    int start_piece[32];   // piece of the first point (32 * lane, lane 31: 968) each lane of the rasteriser evaluates
+};
+
+constexpr int SPLINE_NPTS = 1000;   // contour_spline(points, n=1000)
+
+// Smallest j >= 0 with (double)j * (1/999) >= u: the first of the 1000 evaluation points np.linspace(0, 1, 1000) at or
+// after the knot u (the products are formed exactly as the evaluation loop forms them, so the piece a point falls into is
+// the one a comparison of the parameters picks).
+__device__ __forceinline__ int first_point_at_or_after(double u) {
+    const double step = 1.0 / (double)(SPLINE_NPTS - 1);
+    int j = max((int)ceil(u * (double)(SPLINE_NPTS - 1)), 0);
+    if (j > 0 && (double)(j - 1) * step >= u) --j;
+    if ((double)j * step < u) ++j;
+    return j;
+}
+
 // Lane k < 21 passes point k as (X, Y).  Returns true when FITPACK would raise (zero chord / non-increasing
 // parameter): the reference's bare except then falls back to the raw points.  On success sp is filled.
-__device__ __forceinline__ bool fit_spline(SplineScratch& sp, const double X, const double Y, const int lane) {
+template <class Scratch>
+__device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const double Y, const int lane) {
     constexpr int KP = CUB200_K;
+    constexpr bool INDEXED = std::is_same<Scratch, SplineScratchIdx>::value;
     // 3a. chord-length parameter (FITPACK parcur)
     const double Xp = __shfl_up_sync(FULL, X, 1), Yp = __shfl_up_sync(FULL, Y, 1);
     double dch = 0.0;
@@ -55,7 +79,21 @@ __device__ __forceinline__ bool fit_spline(SplineScratch& sp, const double X, co
     const double dxk = (Xn - X) * ih, dyk = (Yn - Y) * ih;  // divided differences delta_k
     const double hm = __shfl_up_sync(FULL, h, 1);
     const double dxm = __shfl_up_sync(FULL, dxk, 1), dym = __shfl_up_sync(FULL, dyk, 1);
-    if (lane < KP) sp.u[lane] = u;
+    int jnext = 0;
+    if constexpr (INDEXED) {
+        // evaluation points per piece: piece k holds the points j with jstart_k <= j < jstart_{k+1}; the last piece keeps the rest
+        const int jstart = (lane == 0) ? 0 : first_point_at_or_after(u);
+        jnext = __shfl_down_sync(FULL, jstart, 1);
+        if (lane >= KP - 2) jnext = INT_MAX;
+        if (lane < KP - 1) {
+            // lanes of the rasteriser whose first point 32 l (lane 31: 968) falls into this piece
+            const int l_lo = (jstart + 31) >> 5, l_hi = (jnext == INT_MAX) ? 31 : min((jnext + 31) >> 5, 31);
+            for (int l = l_lo; l < l_hi; ++l) sp.start_piece[l] = lane;
+            if (jstart <= SPLINE_NPTS - 32 && SPLINE_NPTS - 32 < jnext) sp.start_piece[31] = lane;
+        }
+    } else {
+        if (lane < KP) sp.u[lane] = u;
+    }
     // rows 1..19 (lane = row), normalised to unit diagonal; other lanes hold identity rows
     double ta = 0.0, tc = 0.0, tx = 0.0, ty = 0.0;
     if (lane >= 1 && lane <= KP - 2) {
@@ -102,7 +140,7 @@ __device__ __forceinline__ bool fit_spline(SplineScratch& sp, const double X, co
         const double m1x = __shfl_down_sync(FULL, Mx, 1), m1y = __shfl_down_sync(FULL, My, 1);
         if (lane < KP - 1) {                             // piece coefficients
             double2* c = reinterpret_cast<double2*>(sp.piece[lane]);
-            c[0] = make_double2(unext, u);
+            c[0] = make_double2(INDEXED ? __longlong_as_double((long long)(unsigned)jnext) : unext, u);
             c[1] = make_double2(X, dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0));
             c[2] = make_double2(0.5 * Mx, (m1x - Mx) * ih * (1.0 / 6.0));
             c[3] = make_double2(Y, dyk - h * (2.0 * My + m1y) * (1.0 / 6.0));

@@ -88,7 +88,7 @@ def psm_factor(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor) 
     """Affine map of the PSM sampler per image: (N,21,2),(N,21,2,2) -> A^T (N,34,42) fp32."""
     mu = nat.require_cuda(mu, torch.float32, "mu")
     cov = nat.require_cuda(cov, torch.float32, "cov")
-    if mu.shape[-2:] != (K, 2) or cov.shape[-3:] != (K, 2, 2) or mu.shape[:-2] != cov.shape[:-3]:
+    if mu.dim() < 2 or cov.dim() < 3 or mu.shape[-2:] != (K, 2) or cov.shape[-3:] != (K, 2, 2) or mu.shape[:-2] != cov.shape[:-3]:
         raise ValueError(f"mu (..,{K},2) / cov (..,{K},2,2) expected, got {tuple(mu.shape)} / {tuple(cov.shape)}")
     n = int(np.prod(mu.shape[:-2])) if mu.dim() > 2 else 1
     a = torch.empty(tuple(mu.shape[:-2]) + (Z_PSM, P), dtype=torch.float32, device=mu.device)
@@ -116,11 +116,14 @@ def naive_factor(cov: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Optional[torch.Tensor] = None,
                             seed: int = 0, round_landmarks: bool = True, return_contours: bool = True,
-                            return_masks: bool = False, diff: Optional[torch.Tensor] = None, images_per_map: int = 1):
-    """Fused sampler -> rasteriser -> aggregation.  mu (N,21,2); a_t (N,Z,42); z (N,T,Z) or None.
+                            return_masks: bool = False, diff: Optional[torch.Tensor] = None, images_per_map: int = 1,
+                            sample_offset: int = 0):
+    """Sampler -> rasteriser -> aggregation.  mu (N,21,2); a_t (N,Z,42); z (N,T,Z) or None.
 
-    Returns dict(contours (N,T,21,2) | None, area (N,T) int32, diff (N,256,256) int32,
+    Returns dict(contours (N,T,21,2), area (N,T) int32, diff (N,256,256) int32,
     masks (N,T,2048) uint32-as-int32 | None).  ``diff`` may be passed to keep accumulating.
+    ``sample_offset``: index of this call's first sample in a larger batch (generated draws are keyed by
+    (seed, sample_offset + image * T + sample), so chunked calls reproduce the unchunked one).
     """
     mu = nat.require_cuda(mu, torch.float32, "mu")
     a_t = nat.require_cuda(a_t, torch.float32, "a_t")
@@ -136,7 +139,7 @@ def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int,
         z = nat.require_cuda(z, torch.float32, "z")
         if tuple(z.shape) != (n, T, zdim):
             raise ValueError(f"z must be ({n},{T},{zdim}), got {tuple(z.shape)}")
-    contours = torch.empty((n, T, K, 2), dtype=torch.float32, device=dev) if return_contours else None
+    contours = torch.empty((n, T, K, 2), dtype=torch.float32, device=dev)   # also the hand-over between the two kernels
     area = torch.empty((n, T), dtype=torch.int32, device=dev)
     if images_per_map < 1 or n % images_per_map:
         raise ValueError("N must be a multiple of images_per_map")
@@ -150,20 +153,23 @@ def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int,
     masks = torch.empty((n, T, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
     with torch.cuda.device(dev):
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
-                                                      n, T, int(round_landmarks), nat.ptr(contours), nat.ptr(area),
-                                                      nat.ptr(diff), int(images_per_map), nat.ptr(masks), nat.stream_ptr(dev))
+                                                      int(sample_offset) & (2**64 - 1), n, T, int(round_landmarks),
+                                                      nat.ptr(contours), nat.ptr(area), nat.ptr(diff), int(images_per_map),
+                                                      nat.ptr(masks), nat.stream_ptr(dev))
     nat.check(rc, "cub200_sample_raster_aggregate")
     return dict(contours=contours, area=area, diff=diff, masks=masks)
 
 
 def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Optional[torch.Tensor] = None,
-                    seed: int = 0) -> torch.Tensor:
+                    seed: int = 0, sample_offset: int = 0) -> torch.Tensor:
     """Sampling only (K3 without rasterisation): contour = mu + A z -> (N,T,21,2) fp32."""
     mu = nat.require_cuda(mu, torch.float32, "mu")
     a_t = nat.require_cuda(a_t, torch.float32, "a_t")
-    n, zdim, T = mu.shape[0], a_t.shape[1], int(n_samples)
-    if mu.shape[1:] != (K, 2) or a_t.shape[0] != n or a_t.shape[2] != P:
+    if mu.dim() != 3 or a_t.dim() != 3:
         raise ValueError("mu (N,21,2) / a_t (N,Z,42) expected")
+    n, zdim, T = mu.shape[0], a_t.shape[1], int(n_samples)
+    if mu.shape[1:] != (K, 2) or a_t.shape[0] != n or a_t.shape[2] != P or not (1 <= zdim <= 42):
+        raise ValueError("mu (N,21,2) / a_t (N,1<=Z<=42,42) expected")
     if z is not None:
         z = nat.require_cuda(z, torch.float32, "z")
         if tuple(z.shape) != (n, T, zdim):
@@ -171,9 +177,24 @@ def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Opti
     out = torch.empty((n, T, K, 2), dtype=torch.float32, device=mu.device)
     with torch.cuda.device(mu.device):
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
-                                                      n, T, 1, nat.ptr(out), None, None, 1, None, nat.stream_ptr(mu.device))
+                                                      int(sample_offset) & (2**64 - 1), n, T, 1, nat.ptr(out), None, None, 1,
+                                                      None, nat.stream_ptr(mu.device))
     nat.check(rc, "cub200_sample_raster_aggregate(sample-only)")
     return out
+
+
+def _check_diff(diff: torch.Tensor, m: int, per_image: int, dev) -> torch.Tensor:
+    """A caller-supplied difference map for ``m`` contours, ``per_image`` consecutive ones per map."""
+    if not isinstance(diff, torch.Tensor) or not diff.is_cuda or diff.dtype != torch.int32 or not diff.is_contiguous():
+        raise ValueError("diff must be a contiguous int32 CUDA tensor")
+    if diff.device != dev:
+        raise ValueError(f"diff lives on {diff.device}, the contours on {dev}")
+    per_image = int(per_image)
+    if per_image < 1 or m % per_image:
+        raise ValueError(f"per_image must be >= 1 and divide the number of contours ({m}), got {per_image}")
+    if diff.dim() != 3 or tuple(diff.shape) != (m // per_image, HW, HW):
+        raise ValueError(f"diff must be ({m // per_image},{HW},{HW}) for {m} contours, {per_image} per image; got {tuple(diff.shape)}")
+    return diff
 
 
 def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, return_masks: bool = True,
@@ -189,6 +210,9 @@ def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, ret
         raise ValueError(f"contours must be (M,{K},2), got {tuple(contours.shape)}")
     m = contours.shape[0]
     dev = contours.device
+    if diff is not None:
+        # the kernel adds into diff[(i // per_image)]: a wrong dtype / shape / device would be an out-of-bounds device write
+        diff = _check_diff(diff, m, per_image, dev)
     masks = torch.empty((m, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
     area = torch.empty((m,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
@@ -373,6 +397,8 @@ def sequence_sample(model: ShapeModelConstants, seq: SequenceModelConstants, mu:
     if first_instant is None:
         first_instant = (torch.rand((npair, T), device=dev) < 0.5).to(torch.uint8)
     first_instant = nat.require_cuda(first_instant, torch.uint8, "first_instant")
+    if tuple(first_instant.shape) != (npair, T):
+        raise ValueError(f"first_instant must be ({npair},{T})")
     z1 = z2 = None
     if z is not None:
         z = nat.require_cuda(z, torch.float32, "z")
@@ -524,8 +550,10 @@ def skew_sample(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor,
             raise ValueError(f"expo must be ({n},{T},{N_DRAW_SKEW},{HW * HW})")
     if pdfs is None:
         pdfs = skew_pdf_grid(mu, cov, alpha, flip_alpha_y=True, sampled_only=True)
-    elif tuple(pdfs.shape) != (n, K, HW, HW):
-        raise ValueError("pdfs must be (N,21,256,256)")
+    else:
+        pdfs = nat.require_cuda(pdfs, torch.float32, "pdfs")
+        if tuple(pdfs.shape) != (n, K, HW, HW) or pdfs.device != dev:
+            raise ValueError("pdfs must be (N,21,256,256) fp32 on the device of mu")
     mc, cc = psm_conditionals(model, mu)
     out = torch.empty((n, T, K, 2), dtype=torch.float32, device=dev)
     idx = torch.empty((n, T, N_DRAW_SKEW), dtype=torch.int32, device=dev) if return_indices else None
@@ -945,7 +973,7 @@ class Workspace:
         self.mu = torch.empty((n_img, K, 2), dtype=f32, device=dev)
         self.cov = torch.empty((n_img, K, 2, 2), dtype=f32, device=dev)
         self.a_t = torch.empty((n_img, zdim, P), dtype=f32, device=dev)
-        self.contours = torch.empty((n_img, t_a, K, 2), dtype=f32, device=dev) if want_contours else None
+        self.contours = torch.empty((n_img, t_a, K, 2), dtype=f32, device=dev)   # always: the sampler -> rasteriser hand-over
         self.area = torch.empty((n_img, t_a), dtype=i32, device=dev)
         self.diff = torch.empty((n_img, HW, HW), dtype=i32, device=dev)
         self.count = torch.empty((n_img, HW, HW), dtype=i32, device=dev) if want_count else None
@@ -988,10 +1016,12 @@ class UncertaintyEngine:
     def workspace(self, n_img: int, t_a: int, **kw) -> Workspace:
         return Workspace(n_img, t_a, Z_PSM if self.sampler == "psm" else Z_NAIVE, self.device, **kw)
 
-    def run_into(self, ws: Workspace, logits: torch.Tensor, seed: int = 0, stream: Optional[torch.cuda.Stream] = None):
-        """The whole path into preallocated buffers: 6 launches (+1 memset), no allocation, no sync.
+    def run_into(self, ws: Workspace, logits: torch.Tensor, seed: int = 0, stream: Optional[torch.cuda.Stream] = None,
+                 sample_offset: int = 0):
+        """The whole path into preallocated buffers: 7 launches (+1 memset), no allocation, no sync.
 
-        ``logits`` must be (ws.n_img,21,256,256) fp32 CUDA contiguous.  Returns ``ws``.
+        ``logits`` must be (ws.n_img,21,256,256) fp32 CUDA contiguous.  ``sample_offset``: index of the first sample of this
+        call in a larger batch (chunked callers), see ``sample_raster_aggregate``.  Returns ``ws``.
         """
         if logits.dtype != torch.float32 or not logits.is_cuda or not logits.is_contiguous() or \
                 tuple(logits.shape) != (ws.n_img, K, HW, HW):
@@ -1014,7 +1044,8 @@ class UncertaintyEngine:
                 with torch.cuda.stream(stream):
                     ws.diff.zero_()
             nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
-                                                       int(seed) & (2**64 - 1), n, T, 1, nat.ptr(ws.contours),
+                                                       int(seed) & (2**64 - 1), int(sample_offset) & (2**64 - 1), n, T, 1,
+                                                       ws.contours.data_ptr(),
                                                        ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, st),
                       "cub200_sample_raster_aggregate")
             nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), ws.mean.data_ptr(),
@@ -1069,7 +1100,9 @@ class HostPipeline:
             st, ws = self.streams[si], self.ws[si]
             with torch.cuda.stream(st):
                 self.d_in[si].copy_(h_logits[c0:c0 + self.chunk], non_blocking=True)
-                self.engine.run_into(ws, self.d_in[si], seed=seed + ci, stream=st)
+                # one seed for the whole batch, the chunk's position as the Philox counter offset: the draws of an image
+                # do not depend on the chunk size and no two (step, chunk) pairs share a stream
+                self.engine.run_into(ws, self.d_in[si], seed=seed, stream=st, sample_offset=c0 * self.t_a)
                 for k in self.OUT_KEYS:
                     h_out[k][c0:c0 + self.chunk].copy_(getattr(ws, k), non_blocking=True)
         for st in self.streams:

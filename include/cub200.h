@@ -97,8 +97,8 @@ int cub200_psm_factor(const double* model_pack, const float* mu, const float* co
 int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* stream);
 
 /*
- * K3  Fused Monte-Carlo sampler -> rasteriser -> streaming aggregation.  One warp per sample:
- *     contour = mu + A z  ->  round  ->  cubic spline (fp64, 1000 points)  ->  pixel set + closing
+ * K3  Monte-Carlo sampler -> rasteriser -> streaming aggregation.  contour = mu + A z (one thread per sample), then
+ *     one warp per sample:  round  ->  cubic spline (fp64, 1000 points)  ->  pixel set + closing
  *     line  ->  4-connected background flood from the frame border  ->  per-sample area and
  *     run-boundary increments into the image's difference map.  Masks never leave shared memory.
  *   replaces  AleatoricUncertaintyTask.sample          cu/task/regression/aleatoric.py:54-78
@@ -108,8 +108,10 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *             lv_area                                  cu/utils/clinical.py:92-93
  *   mu (n_img, 42) fp32; a_t (n_img, zdim, 42) fp32 (transposed factor), zdim <= 42
  *   z  optional (n_img, n_samples, zdim) fp32 standard-normal draws to replay; NULL -> Philox4x32-10
- *      + Box-Muller keyed by (seed, image, sample)
- *   contours_out optional (n_img, n_samples, 21, 2) fp32 (the API's contour_samples).  When area_out,
+ *      + Box-Muller keyed by (seed, sample_offset + image * n_samples + sample): a caller that cuts a batch into
+ *      chunks passes the index of the chunk's first sample, so the draws do not depend on the chunking
+ *   contours_out (n_img, n_samples, 21, 2) fp32, REQUIRED: the API's contour_samples, and the hand-over between the
+ *                sampling kernel (one thread per sample) and the rasteriser (one warp per sample).  When area_out,
  *                diff and masks_out are all NULL the call only samples (no rasterisation).
  *   area_out     optional (n_img, n_samples) int32  mask pixel counts
  *   diff         (n_img, 256, 256) int32, ACCUMULATED into (caller zeroes): +1 where a mask run
@@ -123,7 +125,7 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *                epistemic passes of an image, aleatoric.py:71-73); diff is (n_img / images_per_map, 256, 256)
  */
 int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
-                                   uint64_t seed, int64_t n_img, int64_t n_samples,
+                                   uint64_t seed, uint64_t sample_offset, int64_t n_img, int64_t n_samples,
                                    int round_landmarks, float* contours_out, int32_t* area_out,
                                    int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* stream);
 

@@ -539,6 +539,77 @@ def posterior_moments(contour_samples: np.ndarray):
     return post_mu.mean(axis=1), post_cov_ep + post_cov_al
 
 
+def point_and_instant_uncertainty(mu, cov, pred, uncertainty_map, entropy_map=None, post_cov=None):
+    """ContourUncertaintyTask.predict_step after the entropy map (cu/task/regression/contour_uncertainty.py:84-128):
+    mu (N,K,2), cov (N,K,2,2), pred / uncertainty_map / entropy_map (N,H,W) -> (point_uncertainty, instant_uncertainty)
+    dicts of (N,K) / (N,) arrays.  Pinned by tests/golden/task_al.npz, task_skew.npz (the reference's own predict_step)."""
+    LA = np.linalg
+    cov = np.asarray(cov)
+    n = cov.shape[0]
+    cov_det = LA.det(cov) ** 0.25
+    cov_eigval = np.sqrt(LA.eig(cov)[0])
+    point = {"cov_xx": cov[:, :, 0, 0] ** 0.5, "cov_yy": cov[:, :, 1, 1] ** 0.5, "cov_det": cov_det,
+             "cov_eigval_sum": cov_eigval.sum(-1)}
+    if post_cov is not None:
+        post_cov = np.asarray(post_cov)
+        pe = np.sqrt(LA.eig(post_cov)[0])
+        point.update({"post_cov_xx": post_cov[:, :, 0, 0] ** 0.5, "post_cov_yy": post_cov[:, :, 1, 1] ** 0.5,
+                      "post_cov_det": LA.det(post_cov) ** 0.25, "post_cov_eigval_sum": pe.sum(-1)})
+    mask = np.asarray(pred) != 0                                       # Label.BG == 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        instant = {"cov_det_mean": np.mean(cov_det, axis=-1), "cov_eigenvalue_mean": np.mean(cov_eigval, axis=(-1, -2)),
+                   "cov_projection": np.array([projected_uncertainty_value(mu[i], cov[i]) for i in range(n)]),
+                   "umap_mean": np.sum(np.asarray(uncertainty_map).squeeze(), axis=(-2, -1)) / np.sum(mask, axis=(-2, -1))}
+        if entropy_map is not None:
+            instant["entropy_mean"] = np.sum(np.asarray(entropy_map).squeeze(), axis=(-2, -1)) / np.sum(mask, axis=(-2, -1))
+    return point, instant
+
+
+def _sample_maps(contour_samples: np.ndarray):
+    """convert_to_mask over (N,T_e,T_a,K,2) + the per-image entropy of contour_uncertainty.py:76-77:
+    -> (pred_samples (N,T_e,T_a,H,W) int, entropy (N,H,W))."""
+    n, te, ta = contour_samples.shape[:3]
+    masks = np.stack([convert_to_mask(contour_samples[i].reshape(te * ta, *contour_samples.shape[3:])) for i in range(n)])
+    ent = np.stack([sample_entropy(masks[i][:, None].astype(float)) for i in range(n)])
+    return masks.reshape(n, te, ta, *masks.shape[2:]).astype(np.int64), ent
+
+
+def aleatoric_predict_step(mu_te: np.ndarray, cov_te: np.ndarray, contour_samples: np.ndarray) -> dict:
+    """AleatoricUncertaintyTask._predict_step + ContourUncertaintyTask.predict_step after the sampler
+    (cu/task/regression/aleatoric.py:90-135, contour_uncertainty.py:71-130), LV-only labels: per-pass moments
+    mu_te (N,T_e,K,2), cov_te (N,T_e,K,2,2) and samples (N,T_e,T_a,K,2) -> every BatchResult field it fills."""
+    mu, cov = aleatoric_epistemic_moments(mu_te, cov_te)
+    post_mu, post_cov = posterior_moments(contour_samples)
+    pred_samples, ent = _sample_maps(contour_samples)
+    n = mu.shape[0]
+    pred = pred_samples.mean(axis=(1, 2)).round().astype(int)                        # aleatoric.py:111
+    umap = np.array([us_umap(mu[i], cov[i]) for i in range(n)])                      # :114
+    point, instant = point_and_instant_uncertainty(mu, cov, pred, umap, ent, post_cov)
+    return dict(mu=mu, mode=mu, cov=cov, post_mu=post_mu, post_cov=post_cov, pred_samples=pred_samples, pred=pred,
+                uncertainty_map=umap, entropy_map=ent, point_uncertainty=point, instant_uncertainty=instant)
+
+
+def skew_predict_step(mu_te: np.ndarray, cov_te: np.ndarray, alpha_te: np.ndarray, contour_samples: np.ndarray) -> dict:
+    """SkewUncertaintyTask._predict_step + predict_step after the sampler (cu/task/regression/aleatoric_skew.py:65-127,
+    contour_uncertainty.py:71-130): post_mu / post_cov pool ALL passes and samples (:75-79), pred is the mask of the
+    projected mode (:96), the uncertainty map is USSkewUmap's."""
+    mu, cov = aleatoric_epistemic_moments(mu_te, cov_te)
+    alpha = alpha_te.mean(axis=1)
+    n, te, ta, k, _ = contour_samples.shape
+    post_mu = contour_samples.mean(axis=(1, 2))
+    post_cov = np.zeros((n, k, 2, 2))
+    for idx in range(n):
+        for kk in range(k):
+            post_cov[idx, kk] = np.cov(contour_samples[idx, :, :, kk].reshape(-1, 2).T)
+    modes, umaps = zip(*[us_skew_umap(mu[i], cov[i], alpha[i]) for i in range(n)])
+    mode, umap = np.array(modes), np.array(umaps)
+    pred = np.array([us_contour_to_mask(mode[i]) for i in range(n)])
+    pred_samples, ent = _sample_maps(contour_samples)
+    point, instant = point_and_instant_uncertainty(mu, cov, pred, umap, ent, post_cov)
+    return dict(mu=mu, mode=mode, cov=cov, alpha=alpha, post_mu=post_mu, post_cov=post_cov, pred_samples=pred_samples, pred=pred,
+                uncertainty_map=umap, entropy_map=ent, point_uncertainty=point, instant_uncertainty=instant)
+
+
 # --------------------------------------------------------------------------------------------------
 # Sequence (ED/ES-coupled) sampler        cu/sampler/posterior_shape_model/sequence_sampler.py
 # --------------------------------------------------------------------------------------------------

@@ -708,6 +708,181 @@ def golden_myo():
     print("myo.npz", argmax.shape, "LV px", (argmax == 1).sum((1, 2))[:5], "MYO px", (argmax == 2).sum((1, 2))[:5])
 
 
+# ------------------------------------------------------------------------------------------------
+# The contour TASK end to end: the reference's own _predict_step + predict_step, executed verbatim
+# ------------------------------------------------------------------------------------------------
+TASK_N, TASK_TE, TASK_TA = 2, 2, 6          # N = 2 dodges the reference's .squeeze() bug at N = 1 (aleatoric.py:111)
+TASK_SEED = 700
+
+
+def _task_logits():
+    """(T_e, N, 21, 256, 256) synthetic logits: pass e = the 'network' e of a two-member ensemble on the same 2 images."""
+    base = synth.heatmap_logits(TASK_N, seed=TASK_SEED)
+    other = synth.heatmap_logits(TASK_N, seed=TASK_SEED + 1)
+    return np.stack([base, 0.7 * base + 0.3 * other]).astype(np.float32)
+
+
+def _bare_task(cls, **hparams):
+    """An instance of a reference task class without its Lightning / Hydra constructor (no checkpoint, no config tree):
+    the attributes the predict path reads are set by hand, the functors are fetched by the reference's own
+    on_predict_start() from a datamodule-like object (contour_uncertainty.py:59-63)."""
+    from contour_uncertainty.data.camus.utils import USContourToMask, USSkewUmap, USUMap
+    from vital.data.camus.config import Label
+
+    task = cls.__new__(cls)
+    torch.nn.Module.__init__(task)
+    task.hparams = SimpleNamespace(data_params=SimpleNamespace(labels=[Label.BG, Label.LV], out_shape=(21, 2)), **hparams)
+    task.trainer = SimpleNamespace(datamodule=SimpleNamespace(umap_fn=USUMap(), contour_to_mask_fn=USContourToMask(),
+                                                              skew_umap_fn=USSkewUmap()))
+    task.device = "cpu"
+    task.on_predict_start()
+    return task
+
+
+def _task_batch():
+    from contour_uncertainty.data.config import ContourTags
+    from vital.data.config import Tags
+
+    return {Tags.img: torch.zeros((TASK_N, 1, 256, 256)), Tags.gt: torch.zeros((TASK_N, 256, 256)),
+            ContourTags.contour: torch.zeros((TASK_N, 21, 2)), Tags.id: [f"patient{i:04d}" for i in range(TASK_N)]}
+
+
+def _store_result(out, tag, res):
+    n = TASK_N
+    for k in ("mu", "mode", "cov", "post_mu", "post_cov", "contour_samples", "pred", "uncertainty_map", "entropy_map", "alpha"):
+        v = getattr(res, k)
+        if v is not None:
+            out[f"{tag}_{k}"] = np.asarray(v)
+    out[f"{tag}_pred_samples"] = np.packbits(np.asarray(res.pred_samples).reshape(n, -1, 256, 256).astype(np.uint8), axis=-1, bitorder="little")
+    out[f"{tag}_pred_samples_shape"] = np.array(res.pred_samples.shape)
+    for k, v in res.point_uncertainty.items():
+        out[f"{tag}_point_{k}"] = np.asarray(v)
+    for k, v in res.instant_uncertainty.items():
+        out[f"{tag}_instant_{k}"] = np.asarray(v)
+
+
+def golden_task_al():
+    """dsnt-al: DSNTAleatoric.predict -> AleatoricUncertaintyTask._predict_step -> ContourUncertaintyTask.predict_step
+    (dsnt_al.py:118-151, aleatoric.py:54-135, contour_uncertainty.py:71-130), the reference's code from the network output
+    to the BatchResult, on synthetic logits through a two-member stub 'ensemble' with replayed PSM draws.
+
+    Two runs: 'f32' = everything as the reference runs it; 'f64' = the same code with the PSM sampler's members and inputs
+    cast to double (its fp32 42x42 inverses at sigma2 = 1e-3 carry ~3e-2 px of noise, see golden_psm)."""
+    from contour_uncertainty.sampler.posterior_shape_model.psm import PosteriorShapeModelSampler
+    from contour_uncertainty.task.regression.dsnt.dsnt_al import DSNTAleatoric
+
+    logits = _task_logits()
+    z = np.random.default_rng(TASK_SEED + 2).standard_normal((TASK_N, TASK_TE, TASK_TA, 17, 2)).astype(np.float32)
+    out = {"z": z, "shape": np.array([TASK_N, TASK_TE, TASK_TA]), "seed": TASK_SEED}
+
+    class DoubleSampler(PosteriorShapeModelSampler):
+        def __call__(self, mu, cov, *a, **k):
+            return super().__call__(mu.double(), cov.double(), *a, **k)
+
+    for mode in ("f32", "f64"):
+        task = _bare_task(DSNTAleatoric, covar=True, t_e=TASK_TE, t_a=TASK_TA, sequence_sampler=False)
+        task.ensembling = True
+        task.model = [lambda img, _e=e: torch.from_numpy(logits[_e]) for e in range(TASK_TE)]
+        if mode == "f64":
+            torch.set_default_dtype(torch.float64)
+        try:
+            task.sampler = (DoubleSampler if mode == "f64" else PosteriorShapeModelSampler)(PSM_PATH)
+            if mode == "f64":
+                for a in ("mean", "scale", "X_train", "X_val", "mu", "Q"):
+                    setattr(task.sampler, a, getattr(task.sampler, a).double())
+            # AleatoricUncertaintyTask.sample: images outer, passes inner, t_a samples of 17 draws each (aleatoric.py:71-73)
+            dt = np.float64 if mode == "f64" else np.float32
+            draws = [z[i, e, s, d][None].astype(dt) for i in range(TASK_N) for e in range(TASK_TE) for s in range(TASK_TA) for d in range(17)]
+            with _refstub.replay_standard_normal(draws) as log:
+                if mode == "f64":
+                    torch.set_default_dtype(torch.float32)      # the DSNT head stays fp32; only the sampler runs in double
+                    orig_call = DoubleSampler.__call__
+
+                    def in_double(self, mu, cov, *a, **k):
+                        torch.set_default_dtype(torch.float64)
+                        try:
+                            return orig_call(self, mu, cov, *a, **k).float()
+                        finally:
+                            torch.set_default_dtype(torch.float32)
+
+                    DoubleSampler.__call__ = in_double
+                with torch.no_grad():                           # Lightning's predict loop runs predict_step without autograd
+                    mu_te, cov_te = task.predict(_task_batch()["img"])
+                    res = task.predict_step(_task_batch(), 0)
+            assert len(log) == TASK_N * TASK_TE * TASK_TA * 17, len(log)
+        finally:
+            torch.set_default_dtype(torch.float32)
+        if mode == "f32":
+            out["mu_te"], out["cov_te"] = mu_te.numpy(), cov_te.numpy()
+        _store_result(out, mode, res)
+    d = np.abs(out["f32_contour_samples"] - out["f64_contour_samples"]).max()
+    print("task_al: fp32-vs-fp64 sampler max diff (px)", d, "pred_samples equal", np.array_equal(out["f32_pred_samples"], out["f64_pred_samples"]))
+    np.savez_compressed(os.path.join(HERE, "task_al.npz"), **out)
+    print("task_al.npz", {k: v.shape for k, v in out.items() if k.startswith("f64_") and v.ndim > 1})
+
+
+def golden_task_skew():
+    """dsnt-skew: DSNTSkew.predict -> SkewUncertaintyTask._predict_step -> ContourUncertaintyTask.predict_step
+    (dsnt_skew.py:153-199, aleatoric_skew.py:49-127, contour_uncertainty.py:71-130) verbatim: the stub networks return
+    (logits, raw skewness) and skew_block is the identity; rvs_fast normals replayed, torch.multinomial fed from
+    synth.exponential_field (checked equal to the real exponential race in golden_skew).  25 samples per pass are
+    hard-coded in the reference (aleatoric_skew.py:63)."""
+    from contour_uncertainty.sampler.posterior_shape_model.psm_skew import SkewPosteriorShapeModelSampler
+    from contour_uncertainty.task.regression.dsnt.dsnt_skew import DSNTSkew
+
+    T = 25
+    Q_SEED = TASK_SEED + 5
+    logits = _task_logits()
+    raw_alpha = np.stack([synth.skew_alphas(TASK_N, seed=TASK_SEED + 3), synth.skew_alphas(TASK_N, seed=TASK_SEED + 4)]).astype(np.float32)
+    z = np.random.default_rng(TASK_SEED + 6).standard_normal((TASK_N, TASK_TE, T, 3, 3)).astype(np.float32)
+    out = {"z": z, "raw_alpha": raw_alpha, "shape": np.array([TASK_N, TASK_TE, T]), "seed": TASK_SEED, "q_seed": Q_SEED}
+
+    task = _bare_task(DSNTSkew, covar=True, t_e=TASK_TE, t_a=T, sequence_sampler=False)
+    task.ensembling = True
+    task.model = [lambda img, _e=e: (torch.from_numpy(logits[_e]), torch.from_numpy(raw_alpha[_e])) for e in range(TASK_TE)]
+    task.skew_block = lambda features: features
+    task.skew_indices = list(range(21))
+    task.sampler = SkewPosteriorShapeModelSampler(PSM_PATH)
+    # SkewUncertaintyTask.sample: passes outer, images inner (aleatoric_skew.py:50-51, psm_skew.py:203-205), per sample 3
+    # (1,3) normals then 14 multinomial draws
+    order = [(i, e) for e in range(TASK_TE) for i in range(TASK_N)]
+    draws = [z[i, e, s, d][None] for (i, e) in order for s in range(T) for d in range(3)]
+    real_multinomial = torch.multinomial
+    state = {"draw": 0}
+    index_log = np.full((TASK_N, TASK_TE, T, 14), -2, dtype=np.int64)
+
+    def fake_multinomial(p, n, *a, **k):
+        c = state["draw"]
+        state["draw"] += 1
+        i, e = order[c // (14 * T)]
+        s, d = (c // 14) % T, c % 14
+        stream = ((i * TASK_TE + e) * T + s) * 14 + d
+        try:
+            real_multinomial(p, n)
+        except Exception:
+            index_log[i, e, s, d] = -1
+            raise
+        q = torch.from_numpy(synth.exponential_field(Q_SEED, stream)).to(p.dtype)
+        idx = torch.argmax(p / q).reshape(1)
+        index_log[i, e, s, d] = int(idx)
+        return idx
+
+    torch.multinomial = fake_multinomial
+    try:
+        with _refstub.replay_standard_normal(draws) as log:
+            with torch.no_grad():                               # Lightning's predict loop runs predict_step without autograd
+                mu_te, cov_te, alpha_te = task.predict(_task_batch()["img"])
+                res = task.predict_step(_task_batch(), 0)
+    finally:
+        torch.multinomial = real_multinomial
+    assert len(log) == TASK_N * TASK_TE * T * 3 and state["draw"] == TASK_N * TASK_TE * T * 14, (len(log), state["draw"])
+    out["mu_te"], out["cov_te"], out["alpha_te"] = mu_te.numpy(), cov_te.numpy(), alpha_te.numpy()
+    out["indices"] = index_log
+    _store_result(out, "f32", res)
+    np.savez_compressed(os.path.join(HERE, "task_skew.npz"), **out)
+    print("task_skew.npz", {k: v.shape for k, v in out.items() if k.startswith("f32_") and v.ndim > 1}, "fallbacks", int((index_log == -1).sum()))
+
+
 from class_entropy_inputs import class_entropy_inputs  # noqa: E402
 
 
@@ -723,6 +898,6 @@ def golden_class_entropy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew"]
     for w in which:
         globals()["golden_" + w]()

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in cub200.h but not exported"
     assert set(names) == set(_native.SIGNATURES) | set(_native.QUERIES)
-    assert _native.lib().cub200_abi_version() == 17
+    assert _native.lib().cub200_abi_version() == _native.EXPECTED_ABI == 18
     assert _native.lib().cub200_built_for_sm() == 100
 
 
@@ -63,7 +63,7 @@ def test_null_and_bad_sizes_return_einval():
     l = _native.lib()
     assert l.cub200_dsnt_moments(None, 1, 256, 256, 1, 1, None, None, None, None) == _native.EINVAL
     assert l.cub200_dsnt_moments(None, 1, 128, 128, 1, 1, None, None, None, None) == _native.EINVAL
-    assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 1, 1, 1, None, None, None, 1, None, None) == _native.EINVAL
+    assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 0, 1, 1, 1, None, None, None, 1, None, None) == _native.EINVAL
     assert l.cub200_finalize_maps(None, 1, 10, None, None, None, None, None, None) == _native.EINVAL
     # zero-sized work is a no-op success even without a device
     assert l.cub200_rasterize_contours(None, 0, 1, None, None, None, 0, None) == 0

@@ -121,17 +121,20 @@ def test_run_into_and_host_pipeline_match_allocating_path():
     for k in ("mu", "cov", "area", "count", "mean", "entropy", "pred"):
         assert torch.equal(getattr(ws, k), getattr(ref, k)), k
     assert torch.equal(ws.contours, ref.contour_samples)
-    # host pipeline: chunks of 2 images on 2 streams; chunk c uses seed + c and restarts the sample index
-    pipe = HostPipeline(eng, 4, 30, chunk=2, n_streams=2)
+    # host pipeline: the draws are keyed by (seed, global sample index), so the result does not depend on how the batch is
+    # cut into chunks: chunks of 2 images on 2 streams and chunks of 1 image on 3 streams both reproduce the whole-batch call
+    r = eng(logits, 30, seed=5)
     h_in = logits.cpu().pin_memory()
-    h_out = pipe.run(h_in, pipe.host_outputs(), seed=5)
-    torch.cuda.synchronize()
-    for c in range(2):
-        r = eng(logits[2 * c:2 * c + 2].contiguous(), 30, seed=5 + c)
-        assert torch.equal(h_out["area"][2 * c:2 * c + 2], r.area.cpu())
-        assert torch.equal(h_out["pred"][2 * c:2 * c + 2], r.pred.cpu())
-        assert torch.equal(h_out["entropy"][2 * c:2 * c + 2], r.entropy.cpu())
-        assert torch.equal(h_out["contours"][2 * c:2 * c + 2], r.contour_samples.cpu())
+    for chunk, n_streams in ((2, 2), (1, 3)):
+        pipe = HostPipeline(eng, 4, 30, chunk=chunk, n_streams=n_streams)
+        h_out = pipe.run(h_in, pipe.host_outputs(), seed=5)
+        torch.cuda.synchronize()
+        assert torch.equal(h_out["area"], r.area.cpu())
+        assert torch.equal(h_out["pred"], r.pred.cpu())
+        assert torch.equal(h_out["entropy"], r.entropy.cpu())
+        assert torch.equal(h_out["contours"], r.contour_samples.cpu())
+    # a different seed gives different draws
+    assert not torch.equal(eng(logits, 30, seed=6).area, r.area)
     with pytest.raises(ValueError):
         pipe.run(logits, h_out)                               # device tensor where host logits are expected
 
