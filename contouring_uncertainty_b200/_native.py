@@ -27,8 +27,8 @@ SIGNATURES = {
     "cub200_psm_model_pack_host": [_vp, _vp, _vp, _vp, _vp],
     "cub200_psm_factor": [_vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
-    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
-    "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
+    "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],
     "cub200_sample_moments": [_vp, _i64, _i64, _vp, _vp, _vp],
@@ -39,7 +39,7 @@ SIGNATURES = {
     "cub200_simpson_diameters": [_vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_simpson_diameters_stretched": [_vp, _i64, _vp, _vp, _i32, _i32, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_simpson_volumes": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
-    "cub200_rasterize_contours_f64": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp],
+    "cub200_rasterize_contours_f64": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_projected_uncertainty": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],
     "cub200_umap_analytic": [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp],
     "cub200_skew_umap_contours": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
@@ -59,7 +59,7 @@ SIGNATURES = {
     "cub200_seg_entropy": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes",
-           "cub200_seg_blob_workspace_bytes")
+           "cub200_seg_blob_workspace_bytes", "cub200_raster_workspace_bytes")
 
 
 class NativeError(RuntimeError):
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         l.cub200_calibration_workspace_bytes.argtypes = []
         l.cub200_seg_blob_workspace_bytes.restype = C.c_int64
         l.cub200_seg_blob_workspace_bytes.argtypes = [_i64]
+        l.cub200_raster_workspace_bytes.restype = C.c_int64
+        l.cub200_raster_workspace_bytes.argtypes = [_i64]
         l.cub200_abi_version.restype = C.c_int
         l.cub200_built_for_sm.restype = C.c_int
         _lib = l

@@ -31,14 +31,17 @@
 //      at xs and end at xe - 1; if in every row the part of the span not covered by both neighbour spans is covered by
 //      those runs, the seeded flood is the fixed point and the mask is the spans (lane = row, 8 x 32 rows, row groups
 //      without a boundary pixel are skipped by the whole warp).  Exact, not a heuristic.
-//      SLOW PATH (concave / self-intersecting samples, contours touching rows 0 / 255): the bit-parallel flood with
-//      Gauss-Seidel vertical sweeps (flood.cuh), lane = band of 8 rows.
+//      GENERAL PATH (concave / self-intersecting samples, contours touching rows 0 / 255): the bit-parallel flood with
+//      Gauss-Seidel vertical sweeps (flood.cuh), lane = band of 8 rows.  It runs as a SECOND KERNEL over the samples the
+//      first one queued (index list in the caller's workspace), so that its 64-register bitmap state does not set the
+//      register budget -- and with it the number of resident warps -- of the common path.
 //   7. area = mask pixels; every run boundary of every mask row becomes a +1 / -1 red.global into the
 //      image's difference map (the row prefix sum of which is the per-pixel count).
 //
 // Shared memory per warp: the 256x256 boundary bitmap (band stride 68 words: the 128-bit row loads are bank-conflict
 // free) + 1.7 KB of spline pieces.
 #include <climits>
+#include <type_traits>
 #include "common.cuh"
 #include "flood.cuh"
 #include "spline.cuh"
@@ -57,6 +60,7 @@ constexpr int FW_THREADS = FW_WARPS * 32;
 constexpr int NPTS = 1000;                      // contour_spline(points, n=1000)   contour.py:30
 constexpr int KP = CUB200_K;                    // 21
 constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px behave as +-8192
+constexpr int FG_WARPS = 8;                     // warps per CTA of the general-flood kernel (128 registers)
 
 struct __align__(16) WarpScratch {
     uint32_t bmp[BMP_WORDS];
@@ -92,9 +96,9 @@ __device__ __noinline__ int emit_row_generic(uint32_t r0, uint32_t r1, uint32_t 
     return area;
 }
 
-// Slow path of step 6/7: the bit-parallel flood of flood.cuh over the warp's bitmap, then the generic run extraction
+// General path of step 6/7: the bit-parallel flood of flood.cuh over the warp's bitmap, then the generic run extraction
 // of every row.  Lane owns rows 8*lane .. 8*lane+7.  Returns the lane's share of the mask area.
-__device__ __noinline__ int fill_slow(const uint32_t* bmp, int lane, int32_t* __restrict__ diff_img,
+__device__ __forceinline__ int fill_slow(const uint32_t* bmp, int lane, int32_t* __restrict__ diff_img,
                                       uint32_t* __restrict__ mask_out) {
     uint32_t R[8][8];
     const uint4* band4 = reinterpret_cast<const uint4*>(bmp + lane * BAND_STRIDE);
@@ -122,33 +126,18 @@ constexpr uint32_t ROW_EMPTY = 256u;
 
 // Span and end runs of one 256-bit row given as 8 words (bit b of word w = column 32 w + b), rowor != 0.
 // Returns xs | xe << 16 and lr = Lrun | Rrun << 16: Lrun = length of the run of set bits that starts at xs, Rrun = length of
-// the run that ends at xe - 1.  A run that reaches the end of its 32-bit word is continued through `brow` (shared memory).
+// the run that ends at xe - 1.  The first / last non-zero words are found through an 8-bit occupancy mask and re-read from
+// shared memory (`brow`), through which a run that reaches the end of its 32-bit word is continued as well.
 __device__ __forceinline__ uint32_t row_span(const uint4 b0, const uint4 b1, const uint32_t* brow, uint32_t& lr) {
-    // first non-zero word
-    const bool lo_half = (b0.x | b0.y | b0.z | b0.w) != 0u;
-    const uint32_t a0 = lo_half ? b0.x : b1.x, a1 = lo_half ? b0.y : b1.y, a2 = lo_half ? b0.z : b1.z, a3 = lo_half ? b0.w : b1.w;
-    int wf = lo_half ? 0 : 4;
-    const bool p01 = (a0 | a1) != 0u;
-    const uint32_t c0 = p01 ? a0 : a2, c1 = p01 ? a1 : a3;
-    wf += p01 ? 0 : 2;
-    const uint32_t fw = c0 ? c0 : c1;
-    wf += c0 ? 0 : 1;
-    // last non-zero word
-    const bool hi_half = (b1.x | b1.y | b1.z | b1.w) != 0u;
-    const uint32_t d0 = hi_half ? b1.x : b0.x, d1 = hi_half ? b1.y : b0.y, d2 = hi_half ? b1.z : b0.z, d3 = hi_half ? b1.w : b0.w;
-    int wl = hi_half ? 4 : 0;
-    const bool p23 = (d2 | d3) != 0u;
-    const uint32_t e0 = p23 ? d2 : d0, e1 = p23 ? d3 : d1;
-    wl += p23 ? 2 : 0;
-    const uint32_t lw = e1 ? e1 : e0;
-    wl += e1 ? 1 : 0;
-
+    const uint32_t nz = (min(b0.x, 1u) | (min(b0.y, 1u) << 1)) | ((min(b0.z, 1u) << 2) | (min(b0.w, 1u) << 3)) |
+                        ((min(b1.x, 1u) << 4) | (min(b1.y, 1u) << 5)) | ((min(b1.z, 1u) << 6) | (min(b1.w, 1u) << 7));
+    const int wf = __ffs(nz) - 1, wl = 31 - __clz(nz);
+    const uint32_t fw = brow[wf], lw = brow[wl];
     const int bf = __ffs(fw) - 1;                              // fw != 0
-    int lrun = __ffs(~(fw >> bf)) - 1;                         // >> shifts zeros in: the complement is never 0 unless bf == 0 && fw == ~0
-    if (bf == 0 && fw == 0xffffffffu) lrun = 32;
+    int lrun = __ffs(~(fw >> bf)) - 1;                         // >> shifts zeros in: the complement is 0 only for bf == 0, fw == ~0
+    if (lrun < 0) lrun = 32;
     const int cl = __clz(lw);
-    int rrun = __clz(~(lw << cl));
-    if (cl == 0 && lw == 0xffffffffu) rrun = 32;
+    int rrun = __clz(~(lw << cl));                             // clz(0) == 32: the whole word
     const int xs = 32 * wf + bf, xe = 32 * wl + 32 - cl;
     if (bf + lrun == 32) {                                     // the run goes on in the next word(s)
         for (int w = wf + 1; w < 8; ++w) {
@@ -175,8 +164,11 @@ __device__ __forceinline__ uint32_t row_span(const uint4 b0, const uint4 b1, con
 // into diff_img (may be null) and stores the packed mask (may be null).
 // flags: bit 0 = round the landmarks before the spline (USContourToMask), bit 1 = linear_reconstruction
 // (cu/utils/contour.py:43-53): no spline, the 21 rounded landmarks are joined by skimage.draw.line segments.
-__device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
-                             int32_t* __restrict__ diff_img, uint32_t* __restrict__ mask_out) {
+// GENERAL = false: the fast fill; returns RASTER_DEFERRED (nothing written) when the sample needs the general flood.
+constexpr int RASTER_DEFERRED = -1;
+template <bool GENERAL>
+__device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
+                                             int32_t* __restrict__ diff_img, uint32_t* __restrict__ mask_out) {
     const int lane = lane_id();
     const bool round_landmarks = (flags & 1) != 0, linear = (flags & 2) != 0;
     uint32_t* bmp = ws.bmp;
@@ -223,30 +215,32 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
             e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                  \
         }
         CUB200_LOAD_PIECE();
-        uint32_t cur = 0xffffffffu, bits = 0;
+        uint32_t cur = 0u, bits = 0u;                        // cur: physical word index of the pending (row, word) cell
         int lowest = 0;
+        double jd = (double)j0;
 #pragma unroll 4
         for (int jj = 0; jj < 32; ++jj) {
-            const int j = j0 + jj;
-            while (j >= jnext) {                             // jnext of the last piece is INT_MAX
+            while (j0 + jj >= jnext) {                       // jnext of the last piece is INT_MAX
                 ++piece;
                 CUB200_LOAD_PIECE();
             }
-            const double sv = (double)j * step - ub;
+            const double sv = jd * step - ub;                // jd * step == np.linspace(0, 1, 1000)[j] exactly
+            jd += 1.0;
             const double xv = fma(fma(fma(c3, sv, c2), sv, c1), sv, c0);
             const double yv = fma(fma(fma(e3, sv, e2), sv, e1), sv, e0);
             const int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
             lowest = __vimin3_s32(lowest, ix, iy);
             // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
             const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
-            if (cell != cur) {
-                if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
-                cur = cell; bits = 0;
-            }
-            bits |= 1u << (ix & 31);
+            const uint32_t phys = cell + ((cell >> 4) & ~3u);                                   // + (row >> 3) * 4
+            const uint32_t bit = 1u << (ix & 31);
+            const bool flush = phys != cur;
+            if (flush && bits != 0u) atomicOr(&bmp[cur], bits);
+            bits = flush ? bit : (bits | bit);
+            cur = phys;
         }
 #undef CUB200_LOAD_PIECE
-        if (bits) atomicOr(&bmp[cur + (cur >> 6) * 4], bits);
+        if (bits) atomicOr(&bmp[cur], bits);
         oob = __any_sync(FULL, lowest < -256);
         if (oob) {                                           // IndexError in the reference: nothing drawn
             __syncwarp();
@@ -274,39 +268,42 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
     }
     __syncwarp();
 
-    // 6. fast path: lane = row 32 i + lane.  Spans and end runs of the rows ...
-    uint32_t d[8], lr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = 32 * i + lane;
-        const uint32_t* brow = bmp + bmp_addr(row, 0);
-        const uint4 b0 = reinterpret_cast<const uint4*>(brow)[0], b1 = reinterpret_cast<const uint4*>(brow)[1];
-        const uint32_t rowor = (b0.x | b0.y | b0.z) | (b0.w | b1.x | b1.y) | (b1.z | b1.w);
-        d[i] = ROW_EMPTY; lr[i] = 0u;
-        if (__any_sync(FULL, rowor != 0u)) {                 // warp-uniform: row groups outside the contour cost 8 instructions
-            if (rowor != 0u) d[i] = row_span(b0, b1, brow, lr[i]);
-        }
-    }
-    // ... then the exact test that the border-seeded flood cannot advance vertically anywhere.
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        // spans of the rows above and below: neighbour lanes, across a row group lane 31 <-> lane 0 of the next group
-        uint32_t up = __shfl_up_sync(FULL, d[i], 1), dn = __shfl_down_sync(FULL, d[i], 1);
-        const uint32_t up_x = __shfl_sync(FULL, d[i > 0 ? i - 1 : 0], 31), dn_x = __shfl_sync(FULL, d[i < 7 ? i + 1 : 7], 0);
-        if (lane == 0) up = (i > 0) ? up_x : ROW_EMPTY;
-        if (lane == 31) dn = (i < 7) ? dn_x : ROW_EMPTY;
-        const int xs = d[i] & 0xffff, xe = d[i] >> 16;
-        const int need_l = min(max((int)(up & 0xffff), (int)(dn & 0xffff)), xe) - xs;
-        const int need_r = xe - max(min((int)(up >> 16), (int)(dn >> 16)), xs);
-        const bool row_ok = need_l <= (int)(lr[i] & 0xffff) && need_r <= (int)(lr[i] >> 16);
-        ok = ok && (d[i] == ROW_EMPTY || row_ok);
-    }
-    // the frame-border rows 0 and 255 are seeded everywhere: a boundary pixel there needs the general flood
-    if ((lane == 0 && d[0] != ROW_EMPTY) || (lane == 31 && d[7] != ROW_EMPTY)) ok = false;
-
     int area = 0;
-    if (__all_sync(FULL, ok)) {
+    if constexpr (GENERAL) {
+        area = fill_slow(bmp, lane, diff_img, mask_out);
+    } else {
+        // 6. fast path: lane = row 32 i + lane.  Spans and end runs of the rows ...
+        uint32_t d[8], lr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 32 * i + lane;
+            const uint32_t* brow = bmp + bmp_addr(row, 0);
+            const uint4 b0 = reinterpret_cast<const uint4*>(brow)[0], b1 = reinterpret_cast<const uint4*>(brow)[1];
+            const uint32_t rowor = (b0.x | b0.y | b0.z) | (b0.w | b1.x | b1.y) | (b1.z | b1.w);
+            d[i] = ROW_EMPTY; lr[i] = 0u;
+            if (__any_sync(FULL, rowor != 0u)) {             // warp-uniform: row groups outside the contour cost 8 instructions
+                if (rowor != 0u) d[i] = row_span(b0, b1, brow, lr[i]);
+            }
+        }
+        // ... then the exact test that the border-seeded flood cannot advance vertically anywhere.
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // spans of the rows above and below: neighbour lanes, across a row group lane 31 <-> lane 0 of the next group
+            uint32_t up = __shfl_up_sync(FULL, d[i], 1), dn = __shfl_down_sync(FULL, d[i], 1);
+            const uint32_t up_x = __shfl_sync(FULL, d[i > 0 ? i - 1 : 0], 31), dn_x = __shfl_sync(FULL, d[i < 7 ? i + 1 : 7], 0);
+            if (lane == 0) up = (i > 0) ? up_x : ROW_EMPTY;
+            if (lane == 31) dn = (i < 7) ? dn_x : ROW_EMPTY;
+            const int xs = d[i] & 0xffff, xe = d[i] >> 16;
+            const int need_l = min(max((int)(up & 0xffff), (int)(dn & 0xffff)), xe) - xs;
+            const int need_r = xe - max(min((int)(up >> 16), (int)(dn >> 16)), xs);
+            const bool row_ok = need_l <= (int)(lr[i] & 0xffff) && need_r <= (int)(lr[i] >> 16);
+            ok = ok && (d[i] == ROW_EMPTY || row_ok);
+        }
+        // the frame-border rows 0 and 255 are seeded everywhere: a boundary pixel there needs the general flood
+        if ((lane == 0 && d[0] != ROW_EMPTY) || (lane == 31 && d[7] != ROW_EMPTY)) ok = false;
+        if (!__all_sync(FULL, ok)) return RASTER_DEFERRED;
+
         // 7. mask rows = spans
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -333,8 +330,6 @@ __device__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
                 o[1] = make_uint4(m[4], m[5], m[6], m[7]);
             }
         }
-    } else {
-        area = fill_slow(bmp, lane, diff_img, mask_out);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(FULL, area, o);
@@ -446,38 +441,69 @@ sample_contours_warp_kernel(const float* __restrict__ mu, const float* __restric
     }
 }
 
+// Workspace of the rasteriser: ws[0] = number of queued samples, ws[1 + i] = index of the i-th sample that needs the general
+// flood (written by raster_kernel, consumed by raster_general_kernel).
+template <bool F64>
+__device__ __forceinline__ void load_landmark(const void* __restrict__ contours_in, int64_t g, int lane, double& x, double& y) {
+    x = 0.0; y = 0.0;
+    if (lane < KP) {
+        if (F64) {
+            const double2 p = reinterpret_cast<const double2*>(contours_in)[g * KP + lane];
+            x = p.x; y = p.y;
+        } else {
+            const float2 p = reinterpret_cast<const float2*>(contours_in)[g * KP + lane];
+            x = p.x; y = p.y;
+        }
+    }
+}
+
 template <bool F64>
 __global__ void __launch_bounds__(FW_THREADS, FW_MINBLOCKS)
 raster_kernel(const void* __restrict__ contours_in, int64_t n, int flags, int32_t* __restrict__ area_out,
-              int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image) {
+              int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image, uint32_t* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
     const int64_t stride = (int64_t)gridDim.x * FW_WARPS;
     int64_t g = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
-    auto load = [&](int64_t gg, double& x, double& y) {
-        x = 0.0; y = 0.0;
-        if (gg < n && lane < KP) {
-            if (F64) {
-                const double2 p = reinterpret_cast<const double2*>(contours_in)[gg * KP + lane];
-                x = p.x; y = p.y;
-            } else {
-                const float2 p = reinterpret_cast<const float2*>(contours_in)[gg * KP + lane];
-                x = p.x; y = p.y;
-            }
-        }
-    };
-    double nx, ny;
-    load(g, nx, ny);
+    // the next contour is in flight (as raw bits) while this one is rasterised
+    using Raw = typename std::conditional<F64, double2, float2>::type;
+    const Raw* src = reinterpret_cast<const Raw*>(contours_in);
+    Raw nxt = {};
+    if (g < n && lane < KP) nxt = src[g * KP + lane];
     for (; g < n; g += stride) {
-        const double dx = nx, dy = ny;
-        load(g + stride, nx, ny);                            // the next contour is in flight while this one is rasterised
+        const Raw cur = nxt;
+        if (g + stride < n && lane < KP) nxt = src[(g + stride) * KP + lane];
         const int64_t map = per_image > 0 ? g / per_image : 0;
-        const int area = raster_sample(ws, dx, dy, flags, diff ? diff + map * 65536 : nullptr,
-                                       masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
+        const int area = raster_sample<false>(ws, (double)cur.x, (double)cur.y, flags, diff ? diff + map * 65536 : nullptr,
+                                              masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
+        if (lane == 0) {
+            if (area == RASTER_DEFERRED) queue[1 + atomicAdd(queue, 1u)] = (uint32_t)g;
+            else if (area_out) area_out[g] = area;
+        }
+    }
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(FG_WARPS * 32, 2)
+raster_general_kernel(const void* __restrict__ contours_in, int flags, int32_t* __restrict__ area_out,
+                      int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image, const uint32_t* __restrict__ queue) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = lane_id();
+    const uint32_t count = queue[0];
+    for (uint32_t q = blockIdx.x * FG_WARPS + (threadIdx.x >> 5); q < count; q += gridDim.x * FG_WARPS) {
+        const int64_t g = queue[1 + q];
+        double x, y;
+        load_landmark<F64>(contours_in, g, lane, x, y);
+        const int64_t map = per_image > 0 ? g / per_image : 0;
+        const int area = raster_sample<true>(ws, x, y, flags, diff ? diff + map * 65536 : nullptr,
+                                             masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
         if (area_out && lane == 0) area_out[g] = area;
     }
 }
+
+__global__ void zero_queue_kernel(uint32_t* queue) { queue[0] = 0u; }
 
 static int sm_count(int* out) {
     // per device (the library serves several GPUs of one process), benign race: every thread writes the same value
@@ -496,19 +522,28 @@ static int sm_count(int* out) {
 }
 
 static int launch_raster(const void* contours, bool f64, int64_t n, int flags, int32_t* area_out, int32_t* diff,
-                         uint32_t* masks_out, int64_t per_image, cudaStream_t stream) {
+                         uint32_t* masks_out, int64_t per_image, uint32_t* queue, bool queue_is_zero, cudaStream_t stream) {
+    if (!queue || n > 0xfffffff0LL) return CUB200_EINVAL;
     int num_sms = 0;
     int rc = sm_count(&num_sms);
     if (rc) return rc;
+    if (!queue_is_zero) zero_queue_kernel<<<1, 1, 0, stream>>>(queue);
     const void* kernel = f64 ? (const void*)raster_kernel<true> : (const void*)raster_kernel<false>;
+    const void* general = f64 ? (const void*)raster_general_kernel<true> : (const void*)raster_general_kernel<false>;
     CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
+    CUB200_CUDA_OK(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FG_WARPS)));
     const int64_t need = (n + FW_WARPS - 1) / FW_WARPS;
     const int64_t cap = (int64_t)num_sms * FW_MINBLOCKS;   // resident CTAs; warps stride over the samples
     const int grid = (int)(need < cap ? need : cap);
-    if (f64)
-        raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image);
-    else
-        raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image);
+    const int64_t need_g = (n + FG_WARPS - 1) / FG_WARPS;
+    const int grid_g = (int)(need_g < 2 * num_sms ? need_g : 2 * num_sms);
+    if (f64) {
+        raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image, queue);
+        raster_general_kernel<true><<<grid_g, FG_WARPS * 32, sizeof(WarpScratch) * FG_WARPS, stream>>>(contours, flags, area_out, diff, masks_out, per_image, queue);
+    } else {
+        raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image, queue);
+        raster_general_kernel<false><<<grid_g, FG_WARPS * 32, sizeof(WarpScratch) * FG_WARPS, stream>>>(contours, flags, area_out, diff, masks_out, per_image, queue);
+    }
     return check_launch("raster_kernel");
 }
 
@@ -517,7 +552,8 @@ static int launch_raster(const void* contours, bool f64, int64_t n, int flags, i
 extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
                                               uint64_t seed, uint64_t sample_offset, int64_t n_img, int64_t n_samples,
                                               int round_landmarks, float* contours_out, int32_t* area_out,
-                                              int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* stream) {
+                                              int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* workspace,
+                                              void* stream) {
     using namespace cub200;
     if (!mu || !a_t || zdim < 1 || zdim > CUB200_ZMAX || n_img < 0 || n_samples < 0) return CUB200_EINVAL;
     if (images_per_map < 1 || n_img % images_per_map) return CUB200_EINVAL;
@@ -542,21 +578,28 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
     }
     int rc = check_launch("sample_contours_kernel");
     if (rc || (!diff && !area_out && !masks_out)) return rc;  // sample-only call
-    return launch_raster(contours_out, false, total, round_landmarks, area_out, diff, masks_out, n_samples * images_per_map, st);
+    if (!workspace) return CUB200_EINVAL;
+    zero_queue_kernel<<<1, 1, 0, st>>>((uint32_t*)workspace);
+    return launch_raster(contours_out, false, total, round_landmarks, area_out, diff, masks_out, n_samples * images_per_map,
+                         (uint32_t*)workspace, true, st);
 }
 
+extern "C" int64_t cub200_raster_workspace_bytes(int64_t n) { return n < 0 ? 0 : 4 * (n + 1); }
+
 extern "C" int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
-                                         int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
+                                         int32_t* area_out, int32_t* diff, int64_t per_image, void* workspace, void* stream) {
     using namespace cub200;
     if (n == 0) return 0;
     if (!contours || n < 0 || (diff && (per_image <= 0 || n % per_image))) return CUB200_EINVAL;
-    return launch_raster(contours, false, n, round_landmarks, area_out, diff, masks_out, per_image, (cudaStream_t)stream);
+    return launch_raster(contours, false, n, round_landmarks, area_out, diff, masks_out, per_image, (uint32_t*)workspace, false,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
-                                             int32_t* area_out, int32_t* diff, int64_t per_image, void* stream) {
+                                             int32_t* area_out, int32_t* diff, int64_t per_image, void* workspace, void* stream) {
     using namespace cub200;
     if (n == 0) return 0;
     if (!contours || n < 0 || (diff && (per_image <= 0 || n % per_image))) return CUB200_EINVAL;
-    return launch_raster(contours, true, n, round_landmarks, area_out, diff, masks_out, per_image, (cudaStream_t)stream);
+    return launch_raster(contours, true, n, round_landmarks, area_out, diff, masks_out, per_image, (uint32_t*)workspace, false,
+                         (cudaStream_t)stream);
 }

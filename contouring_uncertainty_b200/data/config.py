@@ -1,8 +1,62 @@
-"""Mirror of contour_uncertainty/data/config.py::BatchResult (:38-107), the output contract of the path."""
+"""Mirror of contour_uncertainty/data/config.py: BatchResult (:38-107), the output contract of the path, and the batch tags
+the task classes read (ContourTags :11-35 < vital CamusTags < vital Tags, vital/vital/data/config.py:66-90,
+vital/vital/data/camus/config.py:10-21,81-125)."""
 from dataclasses import dataclass
-from typing import Sequence, Tuple
+from enum import IntEnum, unique
+from typing import NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
+
+
+class LabelEnum(IntEnum):
+    def __str__(self):  # vital/vital/data/config.py:12-16
+        return self.name.lower()
+
+
+@unique
+class Label(LabelEnum):
+    """vital/vital/data/camus/config.py:10-21."""
+    BG = 0
+    LV = 1
+    MYO = 2
+    ATRIUM = 3
+
+
+@dataclass(frozen=True)
+class Tags:
+    id: str = "id"
+    group: str = "group"
+    neighbors: str = "neighbors"
+    img: str = "img"
+    gt: str = "gt"
+    pred: str = "pred"
+    post_pred: str = "post_pred"
+    encoding: str = "z"
+
+
+@dataclass(frozen=True)
+class CamusTags(Tags):
+    registered: str = "register"
+    full_sequence: str = "sequence"
+    instants: str = "instants"
+    img_proc: str = "img_proc"
+    gt_proc: str = "gt_proc"
+    metadata: str = "metadata"
+    voxelspacing: str = "voxelspacing"
+    raw: str = "raw"
+    post: str = "post"
+
+
+@dataclass(frozen=True)
+class ContourTags(CamusTags):
+    contour: str = "contour"  # Contour GT (K,2)
+
+
+class DataParameters(NamedTuple):
+    """vital/vital/data/config.py:96-110."""
+    in_shape: Optional[tuple] = None
+    out_shape: Optional[tuple] = None
+    labels: Optional[tuple] = None
 
 
 @dataclass

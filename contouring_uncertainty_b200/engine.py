@@ -151,11 +151,12 @@ def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int,
         if tuple(diff.shape) != (n_maps, HW, HW):
             raise ValueError("diff must be (N / images_per_map,256,256) int32")
     masks = torch.empty((n, T, MASK_WORDS), dtype=torch.int32, device=dev) if return_masks else None
+    rws = raster_workspace(n * T, dev)
     with torch.cuda.device(dev):
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
                                                       int(sample_offset) & (2**64 - 1), n, T, int(round_landmarks),
                                                       nat.ptr(contours), nat.ptr(area), nat.ptr(diff), int(images_per_map),
-                                                      nat.ptr(masks), nat.stream_ptr(dev))
+                                                      nat.ptr(masks), nat.ptr(rws), nat.stream_ptr(dev))
     nat.check(rc, "cub200_sample_raster_aggregate")
     return dict(contours=contours, area=area, diff=diff, masks=masks)
 
@@ -178,9 +179,14 @@ def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Opti
     with torch.cuda.device(mu.device):
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
                                                       int(sample_offset) & (2**64 - 1), n, T, 1, nat.ptr(out), None, None, 1,
-                                                      None, nat.stream_ptr(mu.device))
+                                                      None, None, nat.stream_ptr(mu.device))
     nat.check(rc, "cub200_sample_raster_aggregate(sample-only)")
     return out
+
+
+def raster_workspace(n: int, device) -> torch.Tensor:
+    """Device workspace of the rasteriser for ``n`` contours (the queue of samples that need the general flood)."""
+    return torch.empty((max(int(nat.lib().cub200_raster_workspace_bytes(int(n))), 4),), dtype=torch.uint8, device=device)
 
 
 def _check_diff(diff: torch.Tensor, m: int, per_image: int, dev) -> torch.Tensor:
@@ -218,7 +224,7 @@ def rasterize_contours(contours: torch.Tensor, round_landmarks: bool = True, ret
     with torch.cuda.device(dev):
         fn = nat.lib().cub200_rasterize_contours_f64 if f64 else nat.lib().cub200_rasterize_contours
         rc = fn(nat.ptr(contours), m, flags, nat.ptr(masks), nat.ptr(area), nat.ptr(diff), int(per_image),
-                nat.stream_ptr(dev))
+                nat.ptr(raster_workspace(m, dev)), nat.stream_ptr(dev))
     nat.check(rc, "cub200_rasterize_contours")
     return masks, area
 
@@ -981,6 +987,7 @@ class Workspace:
         self.entropy = torch.empty((n_img, HW, HW), dtype=f64, device=dev)
         self.pred = torch.empty((n_img, HW, HW), dtype=torch.uint8, device=dev)
         self.lut = torch.empty((t_a + 1,), dtype=f64, device=dev)
+        self.raster_ws = raster_workspace(n_img * t_a, dev)
 
     def result(self) -> "UncertaintyResult":
         return UncertaintyResult(self.mu, self.cov, self.contours, self.area, self.count, self.mean, self.entropy, self.pred)
@@ -1046,7 +1053,7 @@ class UncertaintyEngine:
             nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
                                                        int(seed) & (2**64 - 1), int(sample_offset) & (2**64 - 1), n, T, 1,
                                                        ws.contours.data_ptr(),
-                                                       ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, st),
+                                                       ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, ws.raster_ws.data_ptr(), st),
                       "cub200_sample_raster_aggregate")
             nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), ws.mean.data_ptr(),
                                              ws.entropy.data_ptr(), ws.pred.data_ptr(), ws.lut.data_ptr(), st),

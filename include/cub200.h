@@ -123,24 +123,29 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *                skimage.draw.line segments instead of the spline.  Bit 0 = round, bit 1 = linear.
  *   images_per_map: consecutive (mu, a_t) entries that aggregate into ONE difference map (the T_e
  *                epistemic passes of an image, aleatoric.py:71-73); diff is (n_img / images_per_map, 256, 256)
+ *   workspace:   cub200_raster_workspace_bytes(n_img * n_samples) bytes of device memory (not needed by a sample-only
+ *                call): the queue of samples whose fill needs the general flood (second kernel of the rasteriser)
  */
+int64_t cub200_raster_workspace_bytes(int64_t n_contours);
 int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
                                    uint64_t seed, uint64_t sample_offset, int64_t n_img, int64_t n_samples,
                                    int round_landmarks, float* contours_out, int32_t* area_out,
-                                   int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* stream);
+                                   int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* workspace,
+                                   void* stream);
 
 /*
  * Rasteriser alone (the same device code as K3, contours given): bit-packed masks out.
  *   contours (n, 21, 2) fp32; masks_out (n, 2048) uint32 optional; area_out (n) int32 optional;
  *   diff optional (n_img, 256, 256) int32 accumulated, image of contour i = i / per_image.
+ *   workspace: cub200_raster_workspace_bytes(n) bytes of device memory.
  */
 int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
-                              int32_t* area_out, int32_t* diff, int64_t per_image, void* stream);
+                              int32_t* area_out, int32_t* diff, int64_t per_image, void* workspace, void* stream);
 
 /* Same as cub200_rasterize_contours with fp64 contours (n, 21, 2): the analytic skew u-map reconstructs unrounded
  * fp64 level contours (cu/utils/skew_umap.py:62-64). */
 int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
-                                  int32_t* area_out, int32_t* diff, int64_t per_image, void* stream);
+                                  int32_t* area_out, int32_t* diff, int64_t per_image, void* workspace, void* stream);
 
 /*
  * K4  Finalise the per-image maps from the difference map.

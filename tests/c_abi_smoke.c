@@ -31,7 +31,9 @@ int main(void) {
     CK(cudaMalloc((void**)&d_pred, 65536));
     CK(cudaMemcpy(d_c, h_c, sizeof(h_c), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_diff, 0, 65536 * 4));
-    int rc = cub200_rasterize_contours(d_c, n, 1, d_m, d_area, d_diff, n, NULL);
+    void* d_rws;
+    CK(cudaMalloc(&d_rws, (size_t)cub200_raster_workspace_bytes(n)));
+    int rc = cub200_rasterize_contours(d_c, n, 1, d_m, d_area, d_diff, n, d_rws, NULL);
     if (rc) { printf("rasterize rc %d %s\n", rc, cub200_last_error()); return 3; }
     rc = cub200_finalize_maps(d_diff, 1, n, d_count, d_mean, d_ent, d_pred, d_lut, NULL);
     if (rc) { printf("finalize rc %d %s\n", rc, cub200_last_error()); return 3; }
@@ -71,7 +73,7 @@ int main(void) {
     CK(cudaMemcpy(h_barea, d_barea, sizeof(h_barea), cudaMemcpyDeviceToHost));
     printf("lv_length %.12f %.12f %.12f blob_area %d %d %d\n", h_len[0], h_len[1], h_len[2], h_barea[0], h_barea[1], h_barea[2]);
     /* error behaviour: invalid arguments come back as codes, never as exceptions */
-    printf("einval %d empty %d\n", cub200_rasterize_contours(NULL, 1, 1, NULL, NULL, NULL, 0, NULL),
-           cub200_rasterize_contours(NULL, 0, 1, NULL, NULL, NULL, 0, NULL));
+    printf("einval %d empty %d\n", cub200_rasterize_contours(NULL, 1, 1, NULL, NULL, NULL, 0, NULL, NULL),
+           cub200_rasterize_contours(NULL, 0, 1, NULL, NULL, NULL, 0, NULL, NULL));
     return 0;
 }

@@ -63,10 +63,10 @@ def test_null_and_bad_sizes_return_einval():
     l = _native.lib()
     assert l.cub200_dsnt_moments(None, 1, 256, 256, 1, 1, None, None, None, None) == _native.EINVAL
     assert l.cub200_dsnt_moments(None, 1, 128, 128, 1, 1, None, None, None, None) == _native.EINVAL
-    assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 0, 1, 1, 1, None, None, None, 1, None, None) == _native.EINVAL
+    assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 0, 1, 1, 1, None, None, None, 1, None, None, None) == _native.EINVAL
     assert l.cub200_finalize_maps(None, 1, 10, None, None, None, None, None, None) == _native.EINVAL
     # zero-sized work is a no-op success even without a device
-    assert l.cub200_rasterize_contours(None, 0, 1, None, None, None, 0, None) == 0
+    assert l.cub200_rasterize_contours(None, 0, 1, None, None, None, 0, None, None) == 0
 
 
 def test_new_entry_points_validate_arguments():
@@ -87,13 +87,13 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_weighted_mask_entropy(None, None, 1, 200, 1.0, 1, None, None) == E
     assert l.cub200_simpson_diameters(None, 1, 0.5, None, None, None, None, None) == E
     assert l.cub200_simpson_volumes(None, None, 1, 1, None, None, None, None) == E
-    assert l.cub200_rasterize_contours_f64(None, 1, 0, None, None, None, 0, None) == E
+    assert l.cub200_rasterize_contours_f64(None, 1, 0, None, None, None, 0, None, None) == E
     # empty work is a no-op
     assert l.cub200_skew_pdf_grid(None, None, None, 0, 1, None, None) == 0
     assert l.cub200_simpson_diameters(None, 0, 0.5, None, None, None, None, None) == 0
     assert l.cub200_simpson_volumes(None, None, 0, 10, None, None, None, None) == 0
     assert l.cub200_projected_uncertainty(None, None, None, 0, 1, 0, None, None, None, None) == 0
-    assert l.cub200_rasterize_contours_f64(None, 0, 0, None, None, None, 0, None) == 0
+    assert l.cub200_rasterize_contours_f64(None, 0, 0, None, None, None, 0, None, None) == 0
     assert l.cub200_simpson_workspace_bytes(10) == 10 * (2048 * 4 + 4)
     assert l.cub200_seg_largest_blob(None, 1, None, None, None, None) == E
     assert l.cub200_sample_entropy(None, 1, 4, 3, 65536, None, None) == E

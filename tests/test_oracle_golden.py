@@ -410,3 +410,64 @@ def test_polygon_fill_vectorisation_and_blob_filter_properties():
             from scipy import ndimage
 
             assert ndimage.label(out[0])[1] == 1                         # one component left
+
+
+# ------------------------------------------------------------------------------------------------
+# The contour task end to end: tests/golden/task_al.npz / task_skew.npz hold every BatchResult field of the reference's own
+# predict_step (DSNTAleatoric / DSNTSkew -> _predict_step -> ContourUncertaintyTask.predict_step, executed verbatim)
+# ------------------------------------------------------------------------------------------------
+def _check_task_result(g, tag, r, umap_exact=True):
+    ps = _unpack(g[f"{tag}_pred_samples"]).reshape(g[f"{tag}_pred_samples_shape"])
+    assert np.array_equal(ps, r["pred_samples"])
+    assert np.array_equal(r["pred"], g[f"{tag}_pred"])
+    for k in ("mu", "mode", "cov", "post_mu", "post_cov"):
+        np.testing.assert_allclose(r[k], g[f"{tag}_{k}"], rtol=1e-12, atol=1e-12, err_msg=k)
+    assert np.abs(r["entropy_map"] - g[f"{tag}_entropy_map"]).max() <= 1e-15
+    assert (r["uncertainty_map"] != g[f"{tag}_uncertainty_map"]).sum() == 0          # 0 differing pixels
+    for k, v in r["point_uncertainty"].items():
+        np.testing.assert_allclose(v, g[f"{tag}_point_{k}"], rtol=1e-12, atol=0, err_msg=k)
+    for k, v in r["instant_uncertainty"].items():
+        # cov_projection: the reference sums 21 fp32 values in fp32 (np.sum of a float32 array)
+        np.testing.assert_allclose(v, g[f"{tag}_instant_{k}"], rtol=2e-7 if k == "cov_projection" else 1e-12, atol=0, err_msg=k)
+    assert set(r["instant_uncertainty"]) == {"cov_det_mean", "cov_eigenvalue_mean", "cov_projection", "umap_mean", "entropy_mean"}
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_aleatoric_task_predict_step_matches_reference(tag):
+    """aleatoric.py:90-135 + contour_uncertainty.py:71-130 restated == the executed reference, given its own per-pass moments
+    and contour samples; pins port.aleatoric_epistemic_moments / posterior_moments / point_and_instant_uncertainty."""
+    g = np.load(os.path.join(G, "task_al.npz"))
+    mu, cov = port.aleatoric_epistemic_moments(g["mu_te"], g["cov_te"])
+    assert np.array_equal(mu, g[f"{tag}_mu"]) and np.array_equal(cov, g[f"{tag}_cov"])
+    pm, pc = port.posterior_moments(g[f"{tag}_contour_samples"])
+    np.testing.assert_allclose(pm, g[f"{tag}_post_mu"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(pc, g[f"{tag}_post_cov"], rtol=1e-12, atol=1e-12)
+    _check_task_result(g, tag, port.aleatoric_predict_step(g["mu_te"], g["cov_te"], g[f"{tag}_contour_samples"]))
+
+
+def test_aleatoric_task_sampler_and_heads_match_reference():
+    """The parts before the orchestration, on the task's own inputs: DSNT heads of both passes and the PSM samples with
+    the task's draw order (images outer, passes inner, aleatoric.py:71-73)."""
+    g = np.load(os.path.join(G, "task_al.npz"))
+    n, te, ta = (int(v) for v in g["shape"])
+    base, other = synth.heatmap_logits(n, seed=int(g["seed"])), synth.heatmap_logits(n, seed=int(g["seed"]) + 1)
+    logits = np.stack([base, 0.7 * base + 0.3 * other]).astype(np.float32)
+    for e in range(te):
+        mu, sig = port.dsnt_predict_on_batch(logits[e])
+        np.testing.assert_allclose(mu, g["mu_te"][:, e], rtol=0, atol=8e-4)
+        np.testing.assert_allclose(sig, g["cov_te"][:, e], rtol=2e-5, atol=2e-4)
+    model = port.ShapeModel.load(os.path.join(os.path.dirname(G), "..", "contouring_uncertainty_b200", "data", "camus-cont_psm_11_no_std.npy"))
+    s = np.stack([[port.psm_sample(model, g["mu_te"][i, e], g["cov_te"][i, e], g["z"][i, e]) for e in range(te)] for i in range(n)])
+    assert np.abs(s - g["f64_contour_samples"]).max() < 1e-4       # vs the reference's sampler executed in fp64
+    assert np.abs(s - g["f32_contour_samples"]).max() < 6e-2       # vs its fp32 run (its own noise: 4.3e-2 px here)
+    assert np.array_equal(np.round(s), np.round(g["f64_contour_samples"]))   # hence the same masks as the fp64 run
+
+
+def test_skew_task_predict_step_matches_reference():
+    """aleatoric_skew.py:65-127 + contour_uncertainty.py:71-130 restated == the executed reference."""
+    g = np.load(os.path.join(G, "task_skew.npz"))
+    r = port.skew_predict_step(g["mu_te"], g["cov_te"], g["alpha_te"], g["f32_contour_samples"])
+    np.testing.assert_allclose(r["alpha"], g["f32_alpha"], rtol=1e-12, atol=0)
+    _check_task_result(g, "f32", r)
+    # DSNTSkew.predict_on_batch negates the y component of the raw skewness (dsnt_skew.py:164)
+    assert np.array_equal(g["alpha_te"], np.swapaxes(g["raw_alpha"], 0, 1) * np.array([1.0, -1.0], dtype=np.float32))
