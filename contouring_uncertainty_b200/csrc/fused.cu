@@ -49,7 +49,7 @@
 namespace cub200 {
 
 #ifndef CUB200_FW_WARPS
-#define CUB200_FW_WARPS 11
+#define CUB200_FW_WARPS 10
 #endif
 #ifndef CUB200_FW_MINBLOCKS
 #define CUB200_FW_MINBLOCKS 2
@@ -289,6 +289,7 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+            if (!__any_sync(FULL, d[i] != ROW_EMPTY)) continue;   // warp-uniform
             // spans of the rows above and below: neighbour lanes, across a row group lane 31 <-> lane 0 of the next group
             uint32_t up = __shfl_up_sync(FULL, d[i], 1), dn = __shfl_down_sync(FULL, d[i], 1);
             const uint32_t up_x = __shfl_sync(FULL, d[i > 0 ? i - 1 : 0], 31), dn_x = __shfl_sync(FULL, d[i < 7 ? i + 1 : 7], 0);
@@ -471,10 +472,11 @@ raster_kernel(const void* __restrict__ contours_in, int64_t n, int flags, int32_
     const Raw* src = reinterpret_cast<const Raw*>(contours_in);
     Raw nxt = {};
     if (g < n && lane < KP) nxt = src[g * KP + lane];
+    const bool small = n <= 0x7fffffffLL && per_image <= 0x7fffffffLL;   // 32-bit division for the map index
     for (; g < n; g += stride) {
         const Raw cur = nxt;
         if (g + stride < n && lane < KP) nxt = src[(g + stride) * KP + lane];
-        const int64_t map = per_image > 0 ? g / per_image : 0;
+        const int64_t map = per_image <= 0 ? 0 : small ? (int64_t)((uint32_t)g / (uint32_t)per_image) : g / per_image;
         const int area = raster_sample<false>(ws, (double)cur.x, (double)cur.y, flags, diff ? diff + map * 65536 : nullptr,
                                               masks_out ? masks_out + g * CUB200_MASK_WORDS : nullptr);
         if (lane == 0) {

@@ -63,7 +63,7 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         if (lane >= o) cum += t;
     }
     const double total = __shfl_sync(FULL, cum, KP - 1);
-    double u = (lane == KP - 1) ? 1.0 : cum / total;
+    double u = (lane == KP - 1) ? 1.0 : cum * fast_rcp(total);
     if (lane == 0) u = 0.0;
     const double uprev = __shfl_up_sync(FULL, u, 1);
     // FITPACK rejects non-increasing parameters (zero chord) -> ValueError -> raw points drawn
@@ -85,12 +85,23 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         const int jstart = (lane == 0) ? 0 : first_point_at_or_after(u);
         jnext = __shfl_down_sync(FULL, jstart, 1);
         if (lane >= KP - 2) jnext = INT_MAX;
-        if (lane < KP - 1) {
-            // lanes of the rasteriser whose first point 32 l (lane 31: 968) falls into this piece
-            const int l_lo = (jstart + 31) >> 5, l_hi = (jnext == INT_MAX) ? 31 : min((jnext + 31) >> 5, 31);
-            for (int l = l_lo; l < l_hi; ++l) sp.start_piece[l] = lane;
-            if (jstart <= SPLINE_NPTS - 32 && SPLINE_NPTS - 32 < jnext) sp.start_piece[31] = lane;
+        // piece of the first point each lane of the rasteriser evaluates (32 l; lane 31: 968): the number of knots
+        // u_1..u_19 at or before it.  Knot k counts for the lanes l >= ceil(jstart_k / 32): one ballot per bit of that
+        // threshold would do; cheaper is a 32-bin histogram in shared memory and a warp prefix sum.
+        sp.start_piece[lane] = 0;
+        __syncwarp();
+        if (lane >= 1 && lane <= KP - 2) {
+            const int first_lane = (jstart <= SPLINE_NPTS - 32) ? ((jstart + 31) >> 5) : 32;
+            if (first_lane < 32) atomicAdd(&sp.start_piece[first_lane], 1);
         }
+        __syncwarp();
+        int cnt = sp.start_piece[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, cnt, o);
+            if (lane >= o) cnt += t;
+        }
+        sp.start_piece[lane] = cnt;
     } else {
         if (lane < KP) sp.u[lane] = u;
     }
@@ -100,10 +111,10 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         double a = hm, b = 2.0 * (hm + h), c = h;
         double r1 = 6.0 * (dxk - dxm), r2 = 6.0 * (dyk - dym);
         if (lane == 1) {                                 // M_0 eliminated (not-a-knot at u_1)
-            const double f = h / (hm + h);
+            const double f = h * fast_rcp(hm + h);
             a = 0.0; b = hm + 2.0 * h; c = h - hm; r1 *= f; r2 *= f;
         } else if (lane == KP - 2) {                     // M_20 eliminated (not-a-knot at u_19)
-            const double f = hm / (hm + h);
+            const double f = hm * fast_rcp(hm + h);
             a = hm - h; b = h + 2.0 * hm; c = 0.0; r1 *= f; r2 *= f;
         }
         const double ib = fast_rcp(b);
@@ -116,8 +127,9 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         double xm = __shfl_up_sync(FULL, tx, sft), ym = __shfl_up_sync(FULL, ty, sft);
         double ap = __shfl_down_sync(FULL, ta, sft), cp = __shfl_down_sync(FULL, tc, sft);
         double xp = __shfl_down_sync(FULL, tx, sft), yp = __shfl_down_sync(FULL, ty, sft);
-        if (lane < sft) { am = cm = xm = ym = 0.0; }
-        if (lane + sft > 31) { ap = cp = xp = yp = 0.0; }
+        // A shuffle from beyond the warp returns the lane's own (finite) values; no masking is needed: the coupling of row i
+        // to a row that does not exist is exactly 0 (ta == 0 for lane < sft, tc == 0 for lane + sft > 31: rows 0 and 20..31
+        // are identity rows, a_1 = c_19 = 0, and ta' = -ta am r, tc' = -tc cp r carry the zeros outwards step by step).
         const double r = fast_rcp(1.0 - ta * cm - tc * ap);
         tx = (tx - ta * xm - tc * xp) * r;
         ty = (ty - ta * ym - tc * yp) * r;
@@ -133,8 +145,8 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         const double p1x = __shfl_up_sync(FULL, Mx, 1), p2x = __shfl_up_sync(FULL, Mx, 2);
         const double p1y = __shfl_up_sync(FULL, My, 1), p2y = __shfl_up_sync(FULL, My, 2);
         const double hm2 = __shfl_up_sync(FULL, h, 2);
-        if (lane == 0) { const double q = h / h1; Mx = m1x - q * (m2x - m1x); My = m1y - q * (m2y - m1y); }
-        if (lane == KP - 1) { const double q = hm / hm2; Mx = p1x + q * (p1x - p2x); My = p1y + q * (p1y - p2y); }
+        if (lane == 0) { const double q = h * fast_rcp(h1); Mx = m1x - q * (m2x - m1x); My = m1y - q * (m2y - m1y); }
+        if (lane == KP - 1) { const double q = hm * fast_rcp(hm2); Mx = p1x + q * (p1x - p2x); My = p1y + q * (p1y - p2y); }
     }
     {
         const double m1x = __shfl_down_sync(FULL, Mx, 1), m1y = __shfl_down_sync(FULL, My, 1);

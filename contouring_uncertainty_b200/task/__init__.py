@@ -114,8 +114,18 @@ class ContourUncertaintyPipeline:
         aggregated per image, epistemic + aleatoric covariance, posterior moments of the samples.
         """
         passes = list(logits) if isinstance(logits, (list, tuple)) else [logits]
-        te, n, T = len(passes), passes[0].shape[0], self.t_a
         mu, cov = self.predict(passes)                                  # (N,T_e,K,2), (N,T_e,K,2,2)
+        return self.from_moments(mu, cov, img=img, seed=seed, z=z, return_pred_samples=return_pred_samples, **kw)
+
+    def from_moments(self, mu: torch.Tensor, cov: torch.Tensor, img=None, seed: int = 0, z=None,
+                     return_pred_samples: bool = False, first_instant=None, **kw) -> BatchResult:
+        """Everything of _predict_step / predict_step after ``predict`` (aleatoric.py:88-135, contour_uncertainty.py:71-130):
+        per-pass moments mu (N,T_e,K,2), cov (N,T_e,K,2,2) fp32 CUDA -> BatchResult."""
+        mu = E.nat.require_cuda(mu, torch.float32, "mu")
+        cov = E.nat.require_cuda(cov, torch.float32, "cov")
+        if mu.dim() != 4 or mu.shape[2:] != (E.K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,):
+            raise ValueError("mu (N,T_e,21,2) / cov (N,T_e,21,2,2) expected")
+        n, te, T = mu.shape[0], mu.shape[1], self.t_a
         m2, c2 = mu.reshape(n * te, E.K, 2).contiguous(), cov.reshape(n * te, E.K, 2, 2).contiguous()
         if self.seq is not None:
             # aleatoric.py:66-69: per pass, the (ED, ES) pairs are sampled jointly; (n,2,K,2) per pair -> (N,T_e,T_a,K,2)
@@ -124,8 +134,9 @@ class ContourUncertaintyPipeline:
             per_pass = []
             for e in range(te):
                 zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=mu.device).reshape(te, n // 2, T, 2, E.Z_PSM)[e].contiguous()
+                fi = None if first_instant is None else torch.as_tensor(first_instant, device=mu.device).to(torch.uint8).reshape(te, n // 2, T)[e].contiguous()
                 sp = E.sequence_sample(self.engine.model, self.seq, mu[:, e].reshape(n // 2, 2, E.K, 2).contiguous(),
-                                       cov[:, e].reshape(n // 2, 2, E.K, 2, 2).contiguous(), T, z=zt, seed=seed + 7919 * e)
+                                       cov[:, e].reshape(n // 2, 2, E.K, 2, 2).contiguous(), T, z=zt, first_instant=fi, seed=seed + 7919 * e)
                 per_pass.append(sp.permute(0, 2, 1, 3, 4).reshape(n, T, E.K, 2))         # (Np,T,2,..) -> (N,T,..)
             samples = torch.stack(per_pass, 1).contiguous()                                # (N,T_e,T_a,K,2)
             diff = torch.zeros((n, E.HW, E.HW), dtype=torch.int32, device=mu.device)
@@ -198,8 +209,19 @@ class SkewUncertaintyPipeline:
                      negate_alpha_y: bool = True, **kw) -> BatchResult:
         passes = list(logits) if isinstance(logits, (list, tuple)) else [logits]
         alphas = list(alpha) if isinstance(alpha, (list, tuple)) else [alpha]
-        te, n, T = len(passes), passes[0].shape[0], self.t_a
         mu, cov, al = self.predict(passes, alphas, negate_alpha_y)
+        return self.from_moments(mu, cov, al, img=img, seed=seed, z=z, expo=expo, return_pred_samples=return_pred_samples, **kw)
+
+    def from_moments(self, mu: torch.Tensor, cov: torch.Tensor, al: torch.Tensor, img=None, seed: int = 0, z=None, expo=None,
+                     return_pred_samples: bool = False, **kw) -> BatchResult:
+        """Everything of SkewUncertaintyTask._predict_step / predict_step after ``predict`` (aleatoric_skew.py:63-127,
+        contour_uncertainty.py:71-130): mu (N,T_e,K,2), cov (N,T_e,K,2,2), alpha (N,T_e,K,2) fp32 CUDA -> BatchResult."""
+        mu = E.nat.require_cuda(mu, torch.float32, "mu")
+        cov = E.nat.require_cuda(cov, torch.float32, "cov")
+        al = E.nat.require_cuda(al, torch.float32, "alpha")
+        if mu.dim() != 4 or mu.shape[2:] != (E.K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,) or al.shape != mu.shape:
+            raise ValueError("mu (N,T_e,21,2) / cov (N,T_e,21,2,2) / alpha (N,T_e,21,2) expected")
+        n, te, T = mu.shape[0], mu.shape[1], self.t_a
         m2, c2, a2 = (t.reshape((n * te,) + t.shape[2:]).contiguous() for t in (mu, cov, al))
         dev = mu.device
         zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=dev).reshape(n * te, T, 3, 3).contiguous()

@@ -1,8 +1,15 @@
-"""Mirror of contour_uncertainty/task/regression/contour_uncertainty.py::ContourUncertaintyTask.convert_to_mask."""
+"""Mirror of contour_uncertainty/task/regression/contour_uncertainty.py::ContourUncertaintyTask (:23-130)."""
+from __future__ import annotations
+
+from typing import Any, Tuple
+
 import numpy as np
 import torch
 
 from ... import engine as E
+from ...data.config import BatchResult, Label
+from .. import add_point_and_instant_uncertainty
+from ..uncertainty import UncertaintyTask
 
 
 def convert_to_mask(mu, image_shape, contour_samples=None, soft_mask: bool = False):
@@ -23,3 +30,56 @@ def convert_to_mask(mu, image_shape, contour_samples=None, soft_mask: bool = Fal
         sm, _ = E.rasterize_contours(cs.reshape(-1, E.K, 2), round_landmarks=True)
         pred_samples = E.unpack_masks(sm).cpu().numpy().astype(np.int64).reshape(tuple(cs.shape[:3]) + (1, E.HW, E.HW))
     return pred, pred_samples
+
+
+class ContourUncertaintyTask(UncertaintyTask):
+    """contour_uncertainty.py:23-130.  ``return_pred_samples`` (extension, default True = the reference's behaviour):
+    materialise ``BatchResult.pred_samples`` (N,T_e,T_a,H,W) int64; the maps never need it here (they come from the
+    on-device count map), so large sample counts can switch it off."""
+
+    def __init__(self, *args, return_pred_samples: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.hparams.return_pred_samples = return_pred_samples
+        self.umap_fn = self.contour_to_mask_fn = self.skew_umap_fn = None
+
+    def convert_to_mask(self, mu: np.ndarray, image_shape: Tuple, contour_samples=None, soft_mask: bool = False):
+        """contour_uncertainty.py:26-57."""
+        if Label.MYO in tuple(self.hparams.data_params.labels):
+            raise NotImplementedError("two-structure (LV + MYO) sample stacks: see engine.us_myo_masks")
+        return convert_to_mask(mu, image_shape, contour_samples, soft_mask)
+
+    def _fetch_functors(self):
+        from ...data.camus.datamodule import CamusContourDataModule
+
+        dm = getattr(self.trainer, "datamodule", None) if self.trainer is not None else None
+        dm = dm if dm is not None else CamusContourDataModule
+        self.umap_fn = staticmethod(dm.umap_fn)
+        self.contour_to_mask_fn = staticmethod(dm.contour_to_mask_fn)
+        self.skew_umap_fn = staticmethod(dm.skew_umap_fn)
+
+    def on_predict_start(self):
+        """contour_uncertainty.py:59-63: the functors come from the datamodule (``self.trainer.datamodule``; without a
+        trainer: ``CamusContourDataModule``'s)."""
+        self._fetch_functors()
+
+    def on_fit_start(self):
+        self._fetch_functors()
+
+    def predict_step(self, batch: Any, batch_idx: int = 0, dataloader_idx: int = 0, **replay) -> BatchResult:
+        """contour_uncertainty.py:71-130.  ``replay``: optional recorded draws handed to ``_predict_step`` (``z``,
+        ``expo``, ``first_instant``, ``seed``) -- the reference draws from torch's / Python's global generators."""
+        if self.umap_fn is None:
+            self.on_predict_start()
+        res, mu_t, cov_t = self._predict_step(batch, **replay)
+        n = res.img.shape[0]
+        if res.pred_samples is not None:
+            if res.entropy_map is None:                             # :76-77 (here the entropy map comes from the count map)
+                res.entropy_map = np.array([self.sample_entropy(res.pred_samples[i].astype(float)) for i in range(n)])
+            if len(self.hparams.data_params.labels) <= 2:            # :79-82
+                res.pred_samples = res.pred_samples.squeeze(3) if res.pred_samples.ndim == 6 else res.pred_samples
+            else:
+                res.pred_samples = res.pred_samples.argmax(3)
+        return add_point_and_instant_uncertainty(res, mu_t, cov_t)     # :84-128
+
+    def _predict_step(self, batch: Any, **replay):
+        raise NotImplementedError
