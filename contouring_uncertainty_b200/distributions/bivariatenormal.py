@@ -53,3 +53,23 @@ class BivariateNormal:
         R = torch.tensor([[c, -s], [s, c]]).float()
         cov = R @ torch.as_tensor(cov, dtype=torch.float32) @ R.T
         return mu[axis], cov[axis, axis]
+
+    @classmethod
+    def rvs(cls, mu, cov, size=(1,), z=None, seed: int = 0):
+        """bivariatenormal.py:88-90: ``MultivariateNormal(mu, cov).sample(size)`` = mu + chol(cov) z -> (n, 2).  The draw runs
+        through the sampling kernel (a one-landmark "contour" whose factor is the 2x2 Cholesky factor); ``z`` (n, 2) replays
+        the standard normals, otherwise Philox with ``seed``."""
+        n = int(size[0]) if isinstance(size, (tuple, list, torch.Size)) else int(size)
+        d = _dev(mu)
+        m = torch.as_tensor(mu, dtype=torch.float32).to(d).reshape(2)
+        c = torch.as_tensor(cov, dtype=torch.float32).to(d).reshape(2, 2)
+        l00 = torch.sqrt(c[0, 0])
+        l10 = c[1, 0] / l00
+        l11 = torch.sqrt(c[1, 1] - l10 * l10)
+        mu21 = torch.zeros((1, E.K, 2), dtype=torch.float32, device=d)
+        mu21[0, 0] = m
+        a_t = torch.zeros((1, 2, E.P), dtype=torch.float32, device=d)       # A^T: draw e -> coordinates of landmark 0
+        a_t[0, 0, 0], a_t[0, 0, 1], a_t[0, 1, 1] = l00, l10, l11
+        zt = None if z is None else torch.as_tensor(z, dtype=torch.float32).to(d).reshape(1, n, 2).contiguous()
+        out = E.sample_contours(mu21, a_t, n, z=zt, seed=seed)[0, :, 0]
+        return out.to(mu.device if isinstance(mu, torch.Tensor) else d)

@@ -49,6 +49,24 @@ class BivariateSkewNormal:
         return 0.5 * term1 + 0.5 * term2 - term3, term1, term2, term3
 
     @classmethod
+    def mode(cls, mu, cov, alpha):
+        """bivariateskewnormal.py:73-81 (+ m0 / skewness / delta :195-215, cov2corr distributions/utils.py:38-73): closed-form
+        approximation of the mode, a handful of scalar operations on (2,) / (2,2) tensors as in the reference."""
+        mu, cov, alpha = (torch.as_tensor(t, dtype=torch.float32) for t in (mu, cov, alpha))
+        c = cov.reshape(-1, 2, 2)
+        std = torch.sqrt(torch.diagonal(c, dim1=1, dim2=2))
+        corr = c / torch.bmm(std.unsqueeze(2), std.unsqueeze(1))
+        alpha_star = torch.sqrt(alpha.T @ corr @ alpha)
+        x = torch.tensor(2 / torch.pi)
+        delta = alpha_star / torch.sqrt(1 + torch.square(alpha_star))
+        mu_z = torch.sqrt(x) * delta
+        sigma_z = torch.sqrt(1 - torch.square(mu_z))
+        skew = ((4 - torch.pi) / 2) * torch.pow(delta * torch.sqrt(x), 3) / torch.pow(1 - 2 * torch.square(delta) / torch.pi, 3 / 2)
+        m0 = mu_z - skew * sigma_z / 2 - torch.sign(alpha_star) / 2 * torch.exp(-2 * torch.pi / torch.abs(alpha_star))
+        mode = mu + m0 / alpha_star * std @ corr @ alpha
+        return mode.squeeze()
+
+    @classmethod
     def marginal(cls, mu, cov, alpha, axis: int, angle=torch.tensor(0), *args, **kwargs):
         """bivariateskewnormal.py:92-135: (mu[axis], rotated variance, projected skewness)."""
         assert axis == 0 or axis == 1

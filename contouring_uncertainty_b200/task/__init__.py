@@ -117,10 +117,17 @@ class ContourUncertaintyPipeline:
         mu, cov = self.predict(passes)                                  # (N,T_e,K,2), (N,T_e,K,2,2)
         return self.from_moments(mu, cov, img=img, seed=seed, z=z, return_pred_samples=return_pred_samples, **kw)
 
-    def from_moments(self, mu: torch.Tensor, cov: torch.Tensor, img=None, seed: int = 0, z=None,
-                     return_pred_samples: bool = False, first_instant=None, **kw) -> BatchResult:
+    def from_moments(self, mu: torch.Tensor, cov: torch.Tensor, **kw) -> BatchResult:
         """Everything of _predict_step / predict_step after ``predict`` (aleatoric.py:88-135, contour_uncertainty.py:71-130):
         per-pass moments mu (N,T_e,K,2), cov (N,T_e,K,2,2) fp32 CUDA -> BatchResult."""
+        return add_point_and_instant_uncertainty(*self.moments_to_result(mu, cov, **kw))
+
+    def moments_to_result(self, mu: torch.Tensor, cov: torch.Tensor, img=None, seed: int = 0, z=None,
+                          return_pred_samples: bool = False, first_instant=None, umap_fn=None, **kw):
+        """AleatoricUncertaintyTask._predict_step after ``predict`` (aleatoric.py:88-135) with the entropy map of
+        predict_step (contour_uncertainty.py:76-77) already filled from the on-device count map.  Returns
+        (BatchResult, mu (N,K,2), cov (N,K,2,2) device tensors).  ``umap_fn``: a per-image functor (mu, cov, labels) ->
+        (H,W) to use instead of the batched analytic u-map kernel."""
         mu = E.nat.require_cuda(mu, torch.float32, "mu")
         cov = E.nat.require_cuda(cov, torch.float32, "cov")
         if mu.dim() != 4 or mu.shape[2:] != (E.K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,):
@@ -166,15 +173,19 @@ class ContourUncertaintyPipeline:
         mu_mean_t = mu.mean(1).contiguous()
         mu_np = mu_mean_t.cpu().numpy()
         umap = kw.pop("uncertainty_map", None)
+        labels = kw.pop("labels", ("lv",))
+        cov_np = cov_out.cpu().numpy()
+        if umap is None and umap_fn is not None:                        # aleatoric.py:114, a caller-supplied functor
+            umap = np.array([umap_fn(mu_np[i], cov_np[i], labels) for i in range(n)])
         if umap is None:                                                # aleatoric.py:114: umap_fn = USUMap (analytic map / max)
             umap = E.umap_analytic(mu_mean_t, cov_out.contiguous(), normalize=True).cpu().numpy()
         res = BatchResult(
-            id=kw.pop("id", ""), labels=kw.pop("labels", ("lv",)), img=np.asarray(img), gt=kw.pop("gt", None),
+            id=kw.pop("id", ""), labels=labels, img=np.asarray(img), gt=kw.pop("gt", None),
             pred=pred.cpu().numpy().astype(np.int64), uncertainty_map=umap,
-            mu=mu_np, mode=mu_np, cov=cov_out.cpu().numpy(), post_mu=pm.mean(1).cpu().numpy(), post_cov=post_cov.cpu().numpy(),
+            mu=mu_np, mode=mu_np, cov=cov_np, post_mu=pm.mean(1).cpu().numpy(), post_cov=post_cov.cpu().numpy(),
             contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent_np,
             sample_area=r["area"].reshape(n, te, T).cpu().numpy(), **kw)
-        return add_point_and_instant_uncertainty(res, mu_mean_t, cov_out)
+        return res, mu_mean_t, cov_out.contiguous()
 
 
 
@@ -212,10 +223,15 @@ class SkewUncertaintyPipeline:
         mu, cov, al = self.predict(passes, alphas, negate_alpha_y)
         return self.from_moments(mu, cov, al, img=img, seed=seed, z=z, expo=expo, return_pred_samples=return_pred_samples, **kw)
 
-    def from_moments(self, mu: torch.Tensor, cov: torch.Tensor, al: torch.Tensor, img=None, seed: int = 0, z=None, expo=None,
-                     return_pred_samples: bool = False, **kw) -> BatchResult:
+    def from_moments(self, mu: torch.Tensor, cov: torch.Tensor, al: torch.Tensor, **kw) -> BatchResult:
         """Everything of SkewUncertaintyTask._predict_step / predict_step after ``predict`` (aleatoric_skew.py:63-127,
         contour_uncertainty.py:71-130): mu (N,T_e,K,2), cov (N,T_e,K,2,2), alpha (N,T_e,K,2) fp32 CUDA -> BatchResult."""
+        return add_point_and_instant_uncertainty(*self.moments_to_result(mu, cov, al, **kw))
+
+    def moments_to_result(self, mu: torch.Tensor, cov: torch.Tensor, al: torch.Tensor, img=None, seed: int = 0, z=None, expo=None,
+                          return_pred_samples: bool = False, skew_umap_fn=None, **kw):
+        """SkewUncertaintyTask._predict_step after ``predict`` (aleatoric_skew.py:63-127) + the entropy map of predict_step.
+        Returns (BatchResult, mu (N,K,2), cov (N,K,2,2) device tensors)."""
         mu = E.nat.require_cuda(mu, torch.float32, "mu")
         cov = E.nat.require_cuda(cov, torch.float32, "cov")
         al = E.nat.require_cuda(al, torch.float32, "alpha")
@@ -235,7 +251,14 @@ class SkewUncertaintyPipeline:
         # :75-79  post_mu over all passes and samples, post_cov = np.cov of the pooled samples
         pm, pc = E.sample_moments(samples.reshape(n, te * T, E.K, 2).contiguous())
         # :82-91  projected mode + skew u-map (USSkewUmap), mask of the mode, masks of the samples
-        mode, umap = E.skew_umap(mu_m, cov_out, al_m, linear_close=True, normalize=True)
+        labels = kw.pop("labels", ("lv",))
+        if skew_umap_fn is not None:                                    # a caller-supplied per-image functor (:85-88)
+            mu_np, cov_np, al_np = mu_m.cpu().numpy(), cov_out.cpu().numpy(), al_m.cpu().numpy()
+            mode_l, umap_l = zip(*[skew_umap_fn(mu_np[i], cov_np[i], al_np[i], labels) for i in range(n)])
+            mode = torch.as_tensor(np.array(mode_l), dtype=torch.float32, device=dev)
+            umap = torch.as_tensor(np.array(umap_l), device=dev)
+        else:
+            mode, umap = E.skew_umap(mu_m, cov_out, al_m, linear_close=True, normalize=True)
         pmask, _ = E.rasterize_contours(mode.contiguous(), round_landmarks=True, return_masks=True)
         pred = E.unpack_masks(pmask).to(torch.int64)
         diff = torch.zeros((n, E.HW, E.HW), dtype=torch.int32, device=dev)
@@ -247,9 +270,9 @@ class SkewUncertaintyPipeline:
         if return_pred_samples:
             pred_samples = E.unpack_masks(masks).cpu().numpy().astype(np.int64).reshape(n, te, T, E.HW, E.HW)
         res = BatchResult(
-            id=kw.pop("id", ""), labels=kw.pop("labels", ("lv",)), img=np.asarray(img), gt=kw.pop("gt", None),
+            id=kw.pop("id", ""), labels=labels, img=np.asarray(img), gt=kw.pop("gt", None),
             pred=pred.cpu().numpy(), uncertainty_map=umap.cpu().numpy(), mu=mu_m.cpu().numpy(), mode=mode.cpu().numpy(),
             cov=cov_out.cpu().numpy(), alpha=al_m.cpu().numpy(), post_mu=pm.cpu().numpy(), post_cov=pc.cpu().numpy(),
             contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent.cpu().numpy(),
             sample_area=area.reshape(n, te, T).cpu().numpy(), **kw)
-        return add_point_and_instant_uncertainty(res, mu_m, cov_out)
+        return res, mu_m, cov_out

@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from ... import engine as E
+from ...data.camus.utils import USUMap
 from ...data.config import ContourTags, Tags
 from ...sampler.posterior_shape_model.psm import PosteriorShapeModelSampler
 from ...sampler.posterior_shape_model.sequence_sampler import SequencePSMSampler
@@ -66,12 +67,12 @@ class AleatoricUncertaintyTask(ContourUncertaintyTask):
         mu, cov = self.predict(img)                               # (N, T_e, K, 2), (N, T_e, K, 2, 2)
         self._pipe.t_a = self.hparams.t_a
         voxelspacing, instants = self.get_voxelspacing_and_instants(batch)
-        res = self._pipe.moments_to_result(
+        fn = getattr(self.umap_fn, "__func__", self.umap_fn)
+        return self._pipe.moments_to_result(
             mu, cov, img=_np(img), seed=seed, z=z, first_instant=first_instant,
             return_pred_samples=self.hparams.return_pred_samples, id=batch[Tags.id] if Tags.id in batch.keys() else "",
             labels=self.hparams.data_params.labels, gt=gt, contour=_np(contour), instants=instants, voxelspacing=voxelspacing,
-            umap_fn=self.umap_fn)
-        return res
+            umap_fn=None if isinstance(fn, USUMap) else fn)             # the stock functor = the batched kernel
 
     def get_cov_matrix(self, var_x, var_y, covar_xy=0):
         """aleatoric.py:138-144."""

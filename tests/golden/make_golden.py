@@ -519,6 +519,14 @@ def golden_distributions():
     assert log == [(16, 3)], log
     m0, v0, a0 = BivariateSkewNormal.marginal(mu, cov, alpha.numpy(), axis=0, angle=torch.tensor(0.4))
     out.update(z=z, rvs=r.numpy(), marginal=np.array([float(m0), float(v0), float(a0)]))
+    # BivariateNormal.rvs (replayed draws), BivariateSkewNormal.mode / BivariateNormal.mode
+    z2 = rng.standard_normal((16, 2)).astype(np.float32)
+    with _refstub.replay_standard_normal([z2]) as log:
+        r2 = BivariateNormal.rvs(mu, cov, size=(16,))
+    assert log == [(16, 2)], log
+    al_m = torch.from_numpy(synth.skew_alphas(1, 134)[0, :8])
+    modes = np.stack([BivariateSkewNormal.mode(mu_n[k], cov_n[k], al_m[k]).numpy() for k in range(8)])
+    out.update(z2=z2, n_rvs=r2.numpy(), alpha_mode=al_m.numpy(), s_mode=modes)
     np.savez_compressed(os.path.join(HERE, "distributions.npz"), **out)
     print("distributions.npz", {k: v.shape for k, v in out.items()})
 

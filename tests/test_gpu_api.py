@@ -324,6 +324,15 @@ def test_distribution_mirrors_vs_reference():
     assert r.shape == (16, 2) and np.abs(r.numpy() - g["rvs"]).max() < 1e-4
     m0, v0, a0 = BivariateSkewNormal.marginal(mu, cov, g["alpha"], axis=0, angle=torch.tensor(0.4))
     np.testing.assert_allclose([float(m0), float(v0), float(a0)], g["marginal"], rtol=2e-6)
+    # BivariateNormal.rvs with replayed normals, BivariateSkewNormal.mode / BivariateNormal.mode
+    r2 = BivariateNormal.rvs(mu, cov, size=(16,), z=g["z2"])
+    assert r2.shape == (16, 2) and np.abs(r2.numpy() - g["n_rvs"]).max() < 1e-4
+    emp = BivariateNormal.rvs(mu, cov, size=(40000,), seed=9).numpy()
+    assert np.abs(emp.mean(0) - g["mu"]).max() < 0.1 and np.abs(np.cov(emp.T) - g["cov"]).max() < 0.05 * np.abs(g["cov"]).max()
+    for k in range(8):
+        m = BivariateSkewNormal.mode(t(g["mu_n"][k]), t(g["cov_n"][k]), t(g["alpha_mode"][k])).numpy()
+        np.testing.assert_allclose(m, g["s_mode"][k], rtol=1e-6)
+    assert torch.equal(BivariateNormal.mode(mu, cov), mu)
     big = BivariateSkewNormal.rvs_fast(mu, cov, al, size=20000, seed=3).numpy()
     # mean of a skew normal: mu + sqrt(2/pi) delta, delta = cov alpha / sqrt(1 + alpha^T cov alpha)
     c, a = g["cov"].astype(np.float64), g["alpha"].astype(np.float64)
@@ -364,13 +373,13 @@ def test_numpy_mirrors_of_utils_and_task_classes():
     assert pred.shape == (2, 256, 256) and ps.shape == (2, 1, 3, 1, 256, 256) and np.array_equal(pred[0], masks[0])
     # task classes around a fake "network"
     logits = torch.from_numpy(synth.heatmap_logits(2, seed=71)).cuda()
-    task = DSNTAleatoric([lambda img: logits, lambda img: logits * 0.9])
+    task = DSNTAleatoric(model=[lambda img: logits, lambda img: logits * 0.9])
     S, cv = task.predict(None)
     assert S.shape == (2, 2, 21, 2) and cv.shape == (2, 2, 21, 2, 2)
     mu_o, _ = port.dsnt_predict_on_batch(logits.cpu().numpy())
     assert np.abs(S[:, 0].cpu().numpy() - mu_o).max() < 1e-3
     raw = torch.from_numpy(synth.skew_alphas(2, seed=72)).cuda()
-    sk_task = DSNTSkew(lambda img: (logits, raw), t_e=2)
+    sk_task = DSNTSkew(model=lambda img: (logits, raw), t_e=2)
     S2, c2, a2 = sk_task.predict(None)
     assert a2.shape == (2, 2, 21, 2) and torch.equal(a2[:, 0, :, 1], -raw[..., 1]) and torch.equal(a2[:, 0, :, 0], raw[..., 0])
 
