@@ -28,7 +28,7 @@ __global__ void entropy_lut_kernel(double* __restrict__ lut, int64_t T) {
 __global__ void __launch_bounds__(256)
 finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T, int32_t* __restrict__ count_out,
                      double* __restrict__ mean_out, double* __restrict__ entropy_out, uint8_t* __restrict__ pred_out,
-                     const double* __restrict__ lut) {
+                     const double* __restrict__ lut, double* __restrict__ variance_out, uint16_t* __restrict__ count16_out) {
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -52,7 +52,20 @@ finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T
         o[0] = make_int4(c[0], c[1], c[2], c[3]);
         o[1] = make_int4(c[4], c[5], c[6], c[7]);
     }
+    if (count16_out) {                                   // T <= 65535 (checked by the caller): 2 B / pixel instead of 4
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = ((uint32_t)c[2 * j] & 0xffffu) | ((uint32_t)c[2 * j + 1] << 16);
+        reinterpret_cast<uint4*>(count16_out + base)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     const double dT = (double)T;
+    if (variance_out) {                                  // p (1 - p), p = count / T: the per-pixel Bernoulli variance of the samples
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const double p0 = (double)c[j] / dT, p1 = (double)c[j + 1] / dT;
+            reinterpret_cast<double2*>(variance_out + base)[j >> 1] = make_double2(p0 * (1.0 - p0), p1 * (1.0 - p1));
+        }
+    }
     if (mean_out) {
 #pragma unroll
         for (int j = 0; j < 8; j += 2)
@@ -84,6 +97,79 @@ __global__ void fac_kernel(const int32_t* __restrict__ ed, const int32_t* __rest
     double f = (a - b) / a;                              // clinical.py:29
     if (!(f >= 0.0 && f <= 1.0)) f = nan("");            // view.py: samples outside [0, 1] are rejected
     out[i] = f;
+}
+
+// Aleatoric / epistemic split of Monte-Carlo metric distributions (results/clinical/utils.py:3-18 and the reject rule of
+// FAC / GLS / Volume.compute, view.py:52-53, patient.py:192-193): one warp per item, values (T_e, T_a) fp64.
+//   v < lo or v > hi (NaN compares false, as in numpy) -> rejected: the value becomes NaN
+//   means_e = nanmean_a, stds_e = nanstd_a (ddof 0); mean = nanmean_e(means), epistemic = nanstd_e(means),
+//   aleatoric = nanmean_e(stds), total = epistemic + aleatoric.  A row / item without a finite value gives NaN.
+__device__ __forceinline__ double ae_value(const double* v, int64_t i, int apply_range, double lo, double hi, bool& rej) {
+    double x = v[i];
+    rej = apply_range && (x < lo || x > hi);
+    return rej ? nan("") : x;
+}
+
+// nanmean over one pass (a row of t_a values) by the whole warp; cnt = number of finite values
+__device__ __forceinline__ double ae_row_mean(const double* row, int t_a, int apply_range, double lo, double hi, int lane, int& cnt) {
+    double s = 0.0;
+    cnt = 0;
+    for (int a = lane; a < t_a; a += 32) {
+        bool rej;
+        const double x = ae_value(row, a, apply_range, lo, hi, rej);
+        if (x == x) { s += x; ++cnt; }
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    return cnt ? s / (double)cnt : nan("");
+}
+
+__global__ void __launch_bounds__(128)
+metric_ae_split_kernel(const double* __restrict__ values, int64_t n_items, int t_e, int t_a, int apply_range, double lo, double hi,
+                       double* __restrict__ values_out, uint8_t* __restrict__ reject_out, double* __restrict__ stats_out,
+                       int32_t* __restrict__ n_reject_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int64_t off = item * (int64_t)t_e * t_a;
+    const double* v = values + off;
+    double sum_m = 0.0, sum_s = 0.0;                     // over the passes that hold a finite value
+    int n_m = 0, n_rej = 0;
+    for (int e = 0; e < t_e; ++e) {
+        const double* row = v + (int64_t)e * t_a;
+        int cnt;
+        const double m = ae_row_mean(row, t_a, apply_range, lo, hi, lane, cnt);
+        double q = 0.0;
+        for (int a = lane; a < t_a; a += 32) {
+            bool rej;
+            const double x = ae_value(row, a, apply_range, lo, hi, rej);
+            n_rej += rej;
+            if (values_out) values_out[off + (int64_t)e * t_a + a] = x;
+            if (reject_out) reject_out[off + (int64_t)e * t_a + a] = rej ? 1 : 0;
+            if (x == x) { const double d = x - m; q += d * d; }
+        }
+        q = warp_sum(q);
+        if (cnt) { sum_m += m; sum_s += sqrt(q / (double)cnt); ++n_m; }
+    }
+    const double mean = n_m ? sum_m / (double)n_m : nan("");
+    double q = 0.0;                                      // epistemic: std (ddof 0) of the per-pass means about their mean
+    for (int e = 0; e < t_e; ++e) {
+        int cnt;
+        const double m = ae_row_mean(v + (int64_t)e * t_a, t_a, apply_range, lo, hi, lane, cnt);
+        if (cnt) { const double d = m - mean; q += d * d; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_rej += __shfl_xor_sync(FULL, n_rej, o);
+    if (lane == 0) {
+        const double epi = n_m ? sqrt(q / (double)n_m) : nan("");
+        const double ale = n_m ? sum_s / (double)n_m : nan("");
+        stats_out[item * 4 + 0] = mean;
+        stats_out[item * 4 + 1] = ale;
+        stats_out[item * 4 + 2] = epi;
+        stats_out[item * 4 + 3] = epi + ale;
+        if (n_reject_out) n_reject_out[item] = n_rej;
+    }
 }
 
 // Dataset-level accumulators of a per-sample integer metric (sum, sum of squares): exact in 64-bit integers, so the
@@ -145,9 +231,10 @@ extern "C" int cub200_sample_moments(const float* contours, int64_t n_img, int64
 
 extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
                                     double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,
-                                    void* stream) {
+                                    double* variance_out, uint16_t* count16_out, void* stream) {
     using namespace cub200;
     if (!diff || n_img < 0 || n_samples < 1 || n_samples > 0x3fffffff) return CUB200_EINVAL;
+    if (count16_out && n_samples > 65535) return CUB200_EINVAL;
     if (entropy_out && !lut_ws) return CUB200_EINVAL;
     if (n_img == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -158,8 +245,19 @@ extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t 
     }
     const int64_t rows = n_img * 256;
     finalize_maps_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(diff, rows, n_samples, count_out, mean_out,
-                                                                    entropy_out, pred_out, lut_ws);
+                                                                    entropy_out, pred_out, lut_ws, variance_out, count16_out);
     return check_launch("finalize_maps_kernel");
+}
+
+extern "C" int cub200_metric_ae_split(const double* values, int64_t n_items, int64_t t_e, int64_t t_a, int apply_range, double lo,
+                                      double hi, double* values_out, uint8_t* reject_out, double* stats_out, int32_t* n_reject_out,
+                                      void* stream) {
+    using namespace cub200;
+    if (!values || !stats_out || n_items < 0 || t_e < 1 || t_a < 1 || t_e > 0x7fffffff || t_a > 0x7fffffff) return CUB200_EINVAL;
+    if (n_items == 0) return 0;
+    metric_ae_split_kernel<<<(unsigned)((n_items + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        values, n_items, (int)t_e, (int)t_a, apply_range, lo, hi, values_out, reject_out, stats_out, n_reject_out);
+    return check_launch("metric_ae_split_kernel");
 }
 
 extern "C" int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_t n, double* fac_out,

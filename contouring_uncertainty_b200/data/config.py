@@ -90,6 +90,11 @@ class BatchResult:
     sample_validity: np.ndarray = None
     # extension: exact per-sample LV pixel counts (what lv_area(pred_samples[...]) returns)
     sample_area: np.ndarray = None  # [N, T_e, T_a]
+    # extension: the sample masks bit-packed (256 rows x 8 uint32 words, bit x & 31 of word x >> 5), 8 KiB / sample instead of
+    # the 512 KiB / sample of the int64 pred_samples; what the metric processors (Volume, GLS) read when present
+    packed_samples: np.ndarray = None  # [N, T_e, T_a, 2048] int32
+    # extension: p (1 - p) of the sample mean (the reference has no variance map)
+    variance_map: np.ndarray = None  # [N, H, W]
 
     def __post_init__(self):
         assert self.img.ndim in [3, 4]

@@ -298,26 +298,80 @@ def unpack_masks(masks: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # K4
 # --------------------------------------------------------------------------------------------------
-def finalize_maps(diff: torch.Tensor, n_samples: int, want_count: bool = True):
-    """difference map -> (count int32 | None, mean fp64, entropy fp64 [bits], pred uint8), all (N,256,256).
+def finalize_maps(diff: torch.Tensor, n_samples: int, want_count: bool = True, want_variance: bool = False,
+                  want_count16: bool = False, want_maps: bool = True):
+    """difference map -> (count int32 | None, mean fp64, entropy fp64 [bits], pred uint8), all (N,256,256)
+    [, variance fp64 = p (1 - p) when ``want_variance``] [, count uint16 when ``want_count16``, n_samples <= 65535].
 
-    aleatoric.py:111 (pred) and uncertainty.py:107-133 (sample_entropy).
+    aleatoric.py:111 (pred) and uncertainty.py:107-133 (sample_entropy).  ``want_maps=False`` skips the fp64 mean / entropy
+    maps (they are functions of the count map: ``maps_from_count`` expands them on the host from 2 B / pixel).
     """
     diff = nat.require_cuda(diff, torch.int32, "diff")
     if diff.dim() != 3 or diff.shape[1:] != (HW, HW):
         raise ValueError("diff must be (N,256,256) int32")
+    if want_count16 and int(n_samples) > 65535:
+        raise ValueError("a uint16 count map needs n_samples <= 65535")
     n = diff.shape[0]
     dev = diff.device
     count = torch.empty_like(diff) if want_count else None
-    mean = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
-    ent = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
+    mean = torch.empty((n, HW, HW), dtype=torch.float64, device=dev) if want_maps else None
+    ent = torch.empty((n, HW, HW), dtype=torch.float64, device=dev) if want_maps else None
+    var = torch.empty((n, HW, HW), dtype=torch.float64, device=dev) if want_variance else None
+    c16 = torch.empty((n, HW, HW), dtype=torch.uint16, device=dev) if want_count16 else None
     pred = torch.empty((n, HW, HW), dtype=torch.uint8, device=dev)
     lut = torch.empty((int(n_samples) + 1,), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         rc = nat.lib().cub200_finalize_maps(nat.ptr(diff), n, int(n_samples), nat.ptr(count), nat.ptr(mean), nat.ptr(ent),
-                                            nat.ptr(pred), nat.ptr(lut), nat.stream_ptr(dev))
+                                            nat.ptr(pred), nat.ptr(lut), nat.ptr(var), nat.ptr(c16), nat.stream_ptr(dev))
     nat.check(rc, "cub200_finalize_maps")
-    return count, mean, ent, pred
+    out = (count, mean, ent, pred)
+    if want_variance:
+        out += (var,)
+    if want_count16:
+        out += (c16,)
+    return out
+
+
+def maps_from_count(count: np.ndarray, n_samples: int) -> dict:
+    """Host-side expansion of a count map (any integer dtype) into the maps the device would write: mean = c / T,
+    entropy = scipy.stats.entropy([p, 1 - p], base=2) evaluated as the kernel's table does, pred = round-half-even(mean),
+    variance = p (1 - p).  Bit-identical to ``finalize_maps`` (same fp64 operations on the same integers)."""
+    T = int(n_samples)
+    c = np.arange(T + 1, dtype=np.float64)
+    p = c / T
+    q = 1.0 - p
+    s = p + q
+    pn, qn = p / s, q / s
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = (np.where(pn > 0, -pn * np.log(pn), 0.0) + np.where(qn > 0, -qn * np.log(qn), 0.0)) / np.log(2.0)
+    e[~np.isfinite(e)] = 0.0
+    idx = np.asarray(count).astype(np.int64)
+    return dict(mean=p[idx], entropy=e[np.clip(idx, 0, T)], pred=(2 * idx > T).astype(np.uint8), variance=(p * (1.0 - p))[idx])
+
+
+def metric_ae_split(values: torch.Tensor, value_range=None, return_values: bool = False):
+    """Aleatoric / epistemic split of Monte-Carlo metric distributions (results/clinical/utils.py:3-18), batched:
+    values (B, T_e, T_a) fp64 CUDA -> dict(stats (B,4) [mean, aleatoric_std, epistemic_std, total], n_reject (B) int32
+    [, values (B,T_e,T_a) with the rejected samples as NaN, reject (B,T_e,T_a) uint8]).  ``value_range`` = (lo, hi): the
+    reject rule of FAC / GLS / EF (values outside become NaN before the statistics)."""
+    values = nat.require_cuda(values, torch.float64, "values")
+    if values.dim() != 3 or values.shape[1] < 1 or values.shape[2] < 1:
+        raise ValueError(f"values must be (B, T_e >= 1, T_a >= 1), got {tuple(values.shape)}")
+    b, te, ta = (int(v) for v in values.shape)
+    dev = values.device
+    stats = torch.empty((b, 4), dtype=torch.float64, device=dev)
+    nrej = torch.empty((b,), dtype=torch.int32, device=dev)
+    vout = torch.empty_like(values) if return_values else None
+    rej = torch.empty((b, te, ta), dtype=torch.uint8, device=dev) if return_values else None
+    lo, hi = (0.0, 0.0) if value_range is None else (float(value_range[0]), float(value_range[1]))
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_metric_ae_split(nat.ptr(values), b, te, ta, int(value_range is not None), lo, hi, nat.ptr(vout),
+                                              nat.ptr(rej), nat.ptr(stats), nat.ptr(nrej), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_metric_ae_split")
+    out = dict(stats=stats, n_reject=nrej)
+    if return_values:
+        out.update(values=vout, reject=rej)
+    return out
 
 
 def fac_from_areas(area_ed: torch.Tensor, area_es: torch.Tensor) -> torch.Tensor:
@@ -972,7 +1026,8 @@ class UncertaintyResult:
 class Workspace:
     """Preallocated device buffers for ``UncertaintyEngine.run_into`` (no allocation per step)."""
 
-    def __init__(self, n_img: int, t_a: int, zdim: int, device, want_count: bool = True, want_contours: bool = True):
+    def __init__(self, n_img: int, t_a: int, zdim: int, device, want_count: bool = True, want_contours: bool = True,
+                 want_maps: bool = True, want_variance: bool = False, want_count16: bool = False):
         dev = torch.device(device)
         f32, i32, f64 = torch.float32, torch.int32, torch.float64
         self.n_img, self.t_a, self.zdim, self.device = n_img, t_a, zdim, dev
@@ -983,8 +1038,10 @@ class Workspace:
         self.area = torch.empty((n_img, t_a), dtype=i32, device=dev)
         self.diff = torch.empty((n_img, HW, HW), dtype=i32, device=dev)
         self.count = torch.empty((n_img, HW, HW), dtype=i32, device=dev) if want_count else None
-        self.mean = torch.empty((n_img, HW, HW), dtype=f64, device=dev)
-        self.entropy = torch.empty((n_img, HW, HW), dtype=f64, device=dev)
+        self.mean = torch.empty((n_img, HW, HW), dtype=f64, device=dev) if want_maps else None
+        self.entropy = torch.empty((n_img, HW, HW), dtype=f64, device=dev) if want_maps else None
+        self.variance = torch.empty((n_img, HW, HW), dtype=f64, device=dev) if want_variance else None
+        self.count16 = torch.empty((n_img, HW, HW), dtype=torch.uint16, device=dev) if want_count16 else None
         self.pred = torch.empty((n_img, HW, HW), dtype=torch.uint8, device=dev)
         self.lut = torch.empty((t_a + 1,), dtype=f64, device=dev)
         self.raster_ws = raster_workspace(n_img * t_a, dev)
@@ -1055,8 +1112,9 @@ class UncertaintyEngine:
                                                        ws.contours.data_ptr(),
                                                        ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, ws.raster_ws.data_ptr(), st),
                       "cub200_sample_raster_aggregate")
-            nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), ws.mean.data_ptr(),
-                                             ws.entropy.data_ptr(), ws.pred.data_ptr(), ws.lut.data_ptr(), st),
+            nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), nat.ptr(ws.mean),
+                                             nat.ptr(ws.entropy), ws.pred.data_ptr(), ws.lut.data_ptr(), nat.ptr(ws.variance),
+                                             nat.ptr(ws.count16), st),
                       "cub200_finalize_maps")
         return ws
 

@@ -1,34 +1,43 @@
-"""Mirror of contour_uncertainty/results/utils/calibration.py (numbers only, no plotting): dataset-level uncertainty
-calibration of a clinical metric from the per-image / per-patient (error, std) pairs every rank holds after the end-of-step
-all_gather (``parallel.gather_metric_distributions``).  Host arithmetic on a few thousand scalars, numpy like the reference."""
+"""Mirrored helper (NOT an accelerated component): contour_uncertainty/results/utils/calibration.py, numbers only.
+
+Dataset-level uncertainty calibration of a clinical metric from the per-image / per-patient (error, std) pairs every rank holds
+after the end-of-step all_gather (``parallel.gather_metric_distributions``): a few thousand scalars, so this is host numpy by
+design.  Same results as the reference's loops (fixture tests/golden/dataset_calibration.json), computed with one
+searchsorted / bincount pass instead of a Python loop per bin.  The pixel-level calibration, which is the heavy reduction, is the
+kernel ``engine.calibration_bins``."""
 import numpy as np
 
 
 def _filtered(error, uncertainty, filters):
-    error, uncertainty = np.asarray(error), np.asarray(uncertainty)
+    error, uncertainty = np.asarray(error, dtype=float), np.asarray(uncertainty, dtype=float)
     if filters is not None:
-        idx = np.where(np.asarray(filters).astype(bool))[0]
-        uncertainty, error = uncertainty[idx], error[idx]
+        keep = np.flatnonzero(np.asarray(filters).astype(bool))
+        uncertainty, error = uncertainty[keep], error[keep]
     return error, uncertainty
 
 
+def _binned_uce(error, uncertainty, bin_of, n_bins, weight_den):
+    """sum over the non-empty bins of |mean uncertainty - mean error| * (bin size / weight_den); samples with bin_of < 0
+    belong to no bin."""
+    ok = bin_of >= 0
+    size = np.bincount(bin_of[ok], minlength=n_bins)
+    conf = np.bincount(bin_of[ok], weights=uncertainty[ok], minlength=n_bins)
+    acc = np.bincount(bin_of[ok], weights=error[ok], minlength=n_bins)
+    nz = size > 0
+    conf, acc, size = conf[nz] / size[nz], acc[nz] / size[nz], size[nz]
+    return float(np.sum(np.abs(conf - acc) * (size / weight_den))), list(conf), list(acc), list(size)
+
+
 def compute_calibration(error, uncertainty, nb_bins: int = 10, filters=None):
-    """calibration.py:6-34: equal-width bins over [min, max] of the uncertainty (open at both ends, like the reference:
-    a value sitting exactly on a boundary belongs to no bin) -> (uce, mean uncertainty, mean error, size) per non-empty bin."""
+    """calibration.py:6-34: equal-width bins over [min, max] of the uncertainty, OPEN at both ends like the reference (a value
+    sitting exactly on a boundary -- the minimum and the maximum always do -- belongs to no bin, yet counts in the
+    denominator of the bin weights) -> (uce, mean uncertainty, mean error, size per non-empty bin)."""
     error, uncertainty = _filtered(error, uncertainty, filters)
     bounds = np.linspace(uncertainty.min(), uncertainty.max(), nb_bins + 1)
-    uce = np.zeros(1)
-    conf, acc, size = [], [], []
-    for lo, hi in zip(bounds[:-1], bounds[1:]):
-        in_bin = np.greater(uncertainty, lo) * np.less(uncertainty, hi)
-        prop = in_bin.mean()
-        if prop.item() > 0:
-            a, c = error[in_bin].mean(), uncertainty[in_bin].mean()
-            uce += np.abs(c - a) * prop
-            conf.append(c)
-            acc.append(a)
-            size.append(in_bin.sum())
-    return uce.item(), conf, acc, size
+    k = np.searchsorted(bounds, uncertainty, side="left") - 1           # bounds[k] < u <= bounds[k + 1]
+    on_boundary = bounds[np.clip(k + 1, 0, nb_bins)] == uncertainty
+    bin_of = np.where(on_boundary | (k < 0) | (k >= nb_bins), -1, k)
+    return _binned_uce(error, uncertainty, bin_of, nb_bins, len(uncertainty))
 
 
 def compute_adaptive_calibration(error, uncertainty, nb_bins: int = 10, filters=None):
@@ -36,18 +45,11 @@ def compute_adaptive_calibration(error, uncertainty, nb_bins: int = 10, filters=
     len(bin) / nb_bins, exactly as the reference writes it."""
     error, uncertainty = _filtered(error, uncertainty, filters)
     order = np.argsort(uncertainty)
-    us, es = np.array_split(uncertainty[order], nb_bins), np.array_split(error[order], nb_bins)
-    uce = np.zeros(1)
-    conf, acc, size = [], [], []
-    for u, e in zip(us, es):
-        prop = len(u) / nb_bins
-        if prop > 0:
-            a, c = e.mean(), u.mean()
-            uce += np.abs(c - a) * prop
-            conf.append(c)
-            acc.append(a)
-            size.append(len(u))
-    return uce.item(), conf, acc, size
+    n = len(order)
+    big, small = n % nb_bins, n // nb_bins                             # array_split: the first n % nb_bins bins get one more
+    sizes = np.array([small + 1] * big + [small] * (nb_bins - big))
+    bin_sorted = np.repeat(np.arange(nb_bins), sizes)
+    return _binned_uce(error[order], uncertainty[order], bin_sorted, nb_bins, nb_bins)
 
 
 def metric_calibration(std, error, reject=None):

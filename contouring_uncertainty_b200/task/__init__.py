@@ -155,7 +155,7 @@ class ContourUncertaintyPipeline:
             zt = None if z is None else torch.as_tensor(z, dtype=torch.float32, device=mu.device).reshape(n * te, T, a_t.shape[1])
             r = E.sample_raster_aggregate(m2, a_t, T, z=zt, seed=seed, return_masks=return_pred_samples, images_per_map=te)
             samples = r["contours"].reshape(n, te, T, E.K, 2)
-        count, mean, ent, pred = E.finalize_maps(r["diff"], te * T)
+        count, mean, ent, pred, var = E.finalize_maps(r["diff"], te * T, want_variance=True)
         # aleatoric.py:90-94 (tiny (N,T_e,K) tensors: plain tensor algebra)
         mu_mean = mu.mean(1, keepdim=True)
         d = (mu - mu_mean)[..., None]
@@ -184,7 +184,8 @@ class ContourUncertaintyPipeline:
             pred=pred.cpu().numpy().astype(np.int64), uncertainty_map=umap,
             mu=mu_np, mode=mu_np, cov=cov_np, post_mu=pm.mean(1).cpu().numpy(), post_cov=post_cov.cpu().numpy(),
             contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent_np,
-            sample_area=r["area"].reshape(n, te, T).cpu().numpy(), **kw)
+            sample_area=r["area"].reshape(n, te, T).cpu().numpy(), variance_map=var.cpu().numpy(),
+            packed_samples=None if r["masks"] is None else r["masks"].reshape(n, te, T, E.MASK_WORDS).cpu().numpy(), **kw)
         return res, mu_mean_t, cov_out.contiguous()
 
 
@@ -263,7 +264,7 @@ class SkewUncertaintyPipeline:
         pred = E.unpack_masks(pmask).to(torch.int64)
         diff = torch.zeros((n, E.HW, E.HW), dtype=torch.int32, device=dev)
         masks, area = E.rasterize_contours(samples.reshape(-1, E.K, 2), return_masks=return_pred_samples, diff=diff, per_image=te * T)
-        _, _, ent, _ = E.finalize_maps(diff, te * T, want_count=False)
+        _, _, ent, _, var = E.finalize_maps(diff, te * T, want_count=False, want_variance=True)
         if img is None:
             img = np.zeros((n, E.HW, E.HW), dtype=np.float32)
         pred_samples = None
@@ -274,5 +275,6 @@ class SkewUncertaintyPipeline:
             pred=pred.cpu().numpy(), uncertainty_map=umap.cpu().numpy(), mu=mu_m.cpu().numpy(), mode=mode.cpu().numpy(),
             cov=cov_out.cpu().numpy(), alpha=al_m.cpu().numpy(), post_mu=pm.cpu().numpy(), post_cov=pc.cpu().numpy(),
             contour_samples=samples.cpu().numpy(), pred_samples=pred_samples, entropy_map=ent.cpu().numpy(),
-            sample_area=area.reshape(n, te, T).cpu().numpy(), **kw)
+            sample_area=area.reshape(n, te, T).cpu().numpy(), variance_map=var.cpu().numpy(),
+            packed_samples=None if masks is None else masks.reshape(n, te, T, E.MASK_WORDS).cpu().numpy(), **kw)
         return res, mu_m, cov_out

@@ -156,10 +156,29 @@ int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_l
  *   entropy_out optional fp64 binary entropy in bits (scipy.stats.entropy([p,1-p], base=2));
  *   pred_out optional uint8 = round-half-even(count/T)
  *   lut_ws: device workspace of (n_samples + 1) doubles (entropy of c/T), written by the call.
+ *   variance_out optional fp64 = p (1 - p), p = count/T: the per-pixel variance of the 0/1 samples (the reference has no
+ *                variance map; this is the Bernoulli variance its mean map implies)
+ *   count16_out optional uint16 count map (n_samples <= 65535): mean / entropy / pred / variance are functions of the count,
+ *                so a host that wants them can fetch 2 B / pixel and index a (T+1)-entry table
  */
 int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
                          double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,
-                         void* stream);
+                         double* variance_out, uint16_t* count16_out, void* stream);
+
+/*
+ * Aleatoric / epistemic split of Monte-Carlo metric distributions, batched: one result per item (instant, view or patient).
+ *   replaces  aleatoric_epistemic_uncertainty            cu/results/clinical/utils.py:3-18
+ *             the sample_reject rule of FAC / GLS / Volume.compute   cu/results/clinical/view.py:52-53,165-166,
+ *                                                                     cu/results/clinical/patient.py:192-193
+ *   values (n_items, t_e, t_a) fp64, NaN allowed.  apply_range != 0: v < lo or v > hi -> rejected (becomes NaN; a NaN input
+ *   is not "rejected", as numpy's comparisons are false for it).
+ *   values_out optional (n_items, t_e, t_a) fp64: the values with the rejected ones as NaN ('mc' of the reference's dicts)
+ *   reject_out optional (n_items, t_e, t_a) uint8: 'sample_reject';  n_reject_out optional (n_items) int32: their number
+ *   stats_out (n_items, 4) fp64: mean = nanmean_e(nanmean_a), aleatoric = nanmean_e(nanstd_a), epistemic = nanstd_e(nanmean_a),
+ *   total = epistemic + aleatoric (standard deviations, ddof 0, whatever the reference's variable names say).
+ */
+int cub200_metric_ae_split(const double* values, int64_t n_items, int64_t t_e, int64_t t_a, int apply_range, double lo, double hi,
+                           double* values_out, uint8_t* reject_out, double* stats_out, int32_t* n_reject_out, void* stream);
 
 /*
  * Per-view clinical reductions from per-sample areas.

@@ -891,6 +891,78 @@ def golden_task_skew():
     print("task_skew.npz", {k: v.shape for k, v in out.items() if k.startswith("f32_") and v.ndim > 1}, "fallbacks", int((index_log == -1).sum()))
 
 
+
+def golden_metrics():
+    """The clinical metric processors on stored BatchResults: AreaError.compute (cu/results/clinical/instant.py:31-57),
+    FAC.compute (view.py:35-78) and Volume.compute (patient.py:75-225), executed as they are on a synthetic patient
+    (views 2CH / 4CH, instants ED / ES, T_e = 2, T_a = 6, anisotropic voxel spacing), plus
+    aleatoric_epistemic_uncertainty on arrays with NaNs.  The sample masks come from USContourToMask on stored contours, so
+    the test rebuilds the same BatchResults.  find_contours (inside Volume) is the restated one: parity unpinned for it."""
+    from contour_uncertainty.data.camus.utils import USContourToMask
+    from contour_uncertainty.data.config import BatchResult
+    from contour_uncertainty.results.clinical.instant import AreaError
+    from contour_uncertainty.results.clinical.patient import Volume
+    from contour_uncertainty.results.clinical.utils import aleatoric_epistemic_uncertainty
+    from contour_uncertainty.results.clinical.view import FAC
+    from vital.data.camus.config import Label
+
+    te, ta = 2, 6
+    rng = np.random.default_rng(171)
+    b = synth.LV_EXAMPLE_SHAPE
+    ctr = b.mean(0)
+    scale = {"2CH": (1.0, 0.8), "4CH": (1.05, 0.84)}
+    vs = {"2CH": (0.5, 0.35), "4CH": (0.31, 0.42)}
+    out = {"shape": np.array([te, ta])}
+    views = {}
+    for name in ("2CH", "4CH"):
+        mu = np.stack([ctr + (b - ctr) * s for s in scale[name]]).astype(np.float32)                       # (2, 21, 2): ED, ES
+        gt_c = (mu + rng.normal(0, 1.5, mu.shape)).astype(np.float32)
+        cs = (mu[:, None, None] + rng.normal(0, 2.5, (2, te, ta, 21, 2)) + rng.normal(0, 2.0, (2, te, ta, 1, 2))).astype(np.float32)
+        # adversarial samples: ES larger than ED (FAC < 0 -> rejected), an empty ED mask (FAC = nan), a tiny ES blob
+        cs[1, 0, 1] = ctr + (b - ctr) * 1.2
+        cs[0, 1, 2] = b + np.array([-700.0, 0.0])
+        cs[1, 1, 4] = ctr + (b - ctr) * 0.02
+        mask = lambda c, **k: USContourToMask.__call__(c, (256, 256), labels=[Label.BG, Label.LV], **k)
+        pred = np.array([mask(mu[i]) for i in range(2)])
+        gt = np.array([mask(gt_c[i]) for i in range(2)])
+        ps = np.array([[[mask(cs[i, e, a]) for a in range(ta)] for e in range(te)] for i in range(2)])
+        views[name] = BatchResult(id=f"patient0001/{name}", img=np.zeros((2, 256, 256)), gt=gt, pred=pred, labels=[Label.BG, Label.LV],
+                                  uncertainty_map=np.zeros((2, 256, 256)), instants={"ED": 0, "ES": 1}, voxelspacing=vs[name],
+                                  mu=mu, mode=mu, cov=np.tile(np.eye(2), (2, 21, 1, 1)), contour=gt_c, contour_samples=cs, pred_samples=ps)
+        out.update({f"{name}_mu": mu, f"{name}_gt_contour": gt_c, f"{name}_contour_samples": cs, f"{name}_voxelspacing": np.array(vs[name])})
+    scalars = ("pred", "gt", "error", "std", "mean", "aleatoric_std", "epistemic_std")
+    for name, v in views.items():
+        for key, inst in v.instants.items():
+            r = AreaError().compute(v, key, inst)
+            out[f"area_{name}_{key}"] = np.array([r[k] for k in scalars], dtype=np.float64)
+            out[f"area_{name}_{key}_mc"] = np.array(r["mc"], dtype=np.float64)
+        r = FAC().compute(v)
+        out[f"fac_{name}"] = np.array([r[k] for k in scalars], dtype=np.float64)
+        out[f"fac_{name}_mc"] = np.array(r["mc"], dtype=np.float64)
+        out[f"fac_{name}_reject"] = np.array(r["reject"])
+        out[f"fac_{name}_sample_reject"] = np.array(r["sample_reject"])
+    r = Volume().compute(views)
+    for m in ("EF", "EDV", "ESV"):
+        out[f"vol_{m}"] = np.array([r[f"{m}_{k}"] for k in scalars], dtype=np.float64)
+        out[f"vol_{m}_mc"] = np.array(r[f"{m}_mc"], dtype=np.float64)
+    out["vol_EF_reject"] = np.array(r["EF_reject"])
+    out["vol_EF_sample_reject"] = np.array(r["EF_sample_reject"])
+    # the split itself on arrays with NaN rows / columns
+    mcs = rng.normal(50, 5, (5, 3, 8))
+    mcs[0, 1, :] = np.nan
+    mcs[1, :, 2:5] = np.nan
+    mcs[2] = np.nan
+    mcs[3, 0, 0] = np.nan
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out["ae_in"] = mcs
+            out["ae_out"] = np.array([aleatoric_epistemic_uncertainty(m) for m in mcs], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+    print("metrics.npz", {k: v.tolist() for k, v in out.items() if k.startswith(("fac_2CH", "vol_EF")) and v.size < 8})
+
+
 from class_entropy_inputs import class_entropy_inputs  # noqa: E402
 
 
@@ -906,6 +978,6 @@ def golden_class_entropy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics"]
     for w in which:
         globals()["golden_" + w]()
