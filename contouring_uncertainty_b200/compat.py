@@ -24,10 +24,12 @@ class _AliasLoader(importlib.abc.Loader):
         self.target = target
 
     def create_module(self, spec):
-        return importlib.import_module(self.target)      # the very same module object under a second name
+        mod = importlib.import_module(self.target)       # the very same module object under a second name
+        self.real_spec = mod.__spec__
+        return mod
 
     def exec_module(self, module):
-        pass
+        module.__spec__ = self.real_spec                 # the import machinery stamped the alias spec on it: put the real one back
 
 
 class _AliasFinder(importlib.abc.MetaPathFinder):

@@ -7,7 +7,8 @@
 namespace cub200 {
 
 void set_last_error(const char* what, cudaError_t e);
-int check_launch(const char* what);
+int check_launch(const char* what);     // after a kernel launch: error check; counts ONE launch (cub200_launch_count)
+void note_launches(int n);              // further launches of the same entry point that share one check
 
 #define CUB200_CUDA_OK(expr)                                   \
     do {                                                       \

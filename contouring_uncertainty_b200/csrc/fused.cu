@@ -530,6 +530,7 @@ static int launch_raster(const void* contours, bool f64, int64_t n, int flags, i
     int rc = sm_count(&num_sms);
     if (rc) return rc;
     if (!queue_is_zero) zero_queue_kernel<<<1, 1, 0, stream>>>(queue);
+    note_launches(queue_is_zero ? 1 : 2);                    // + raster_general_kernel (+ zero_queue_kernel); check_launch counts raster_kernel
     const void* kernel = f64 ? (const void*)raster_kernel<true> : (const void*)raster_kernel<false>;
     const void* general = f64 ? (const void*)raster_general_kernel<true> : (const void*)raster_general_kernel<false>;
     CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
@@ -582,6 +583,7 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
     if (rc || (!diff && !area_out && !masks_out)) return rc;  // sample-only call
     if (!workspace) return CUB200_EINVAL;
     zero_queue_kernel<<<1, 1, 0, st>>>((uint32_t*)workspace);
+    note_launches(1);
     return launch_raster(contours_out, false, total, round_landmarks, area_out, diff, masks_out, n_samples * images_per_map,
                          (uint32_t*)workspace, true, st);
 }

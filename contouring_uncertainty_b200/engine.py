@@ -1132,26 +1132,35 @@ class HostPipeline:
     copy of chunk i+1 and the device->host copy of chunk i-1 overlap the kernels of chunk i (PCIe is
     the bottleneck of this entry: 5.5 MB of logits per image).  What the reference does at this
     boundary is the opposite copy (``S.cpu()``, dsnt_al.py:147-148) followed by seconds of Python.
+
+    ``compact=True`` (needs t_a <= 65535) ships the uint16 COUNT map (128 KiB / image) instead of the fp64 mean and entropy
+    maps and the uint8 pred (1.06 MiB / image): all three are functions of the count, ``expand()`` rebuilds them on the host
+    bit for bit (``maps_from_count``).
     """
 
-    OUT_KEYS = ("mu", "cov", "contours", "area", "mean", "entropy", "pred")
-
-    def __init__(self, engine: UncertaintyEngine, n_img: int, t_a: int, chunk: int = 8, n_streams: int = 2):
+    def __init__(self, engine: UncertaintyEngine, n_img: int, t_a: int, chunk: int = 8, n_streams: int = 2, compact: bool = False):
         if n_img % chunk:
             raise ValueError("n_img must be a multiple of chunk")
-        self.engine, self.n_img, self.t_a, self.chunk = engine, n_img, t_a, chunk
+        if compact and t_a > 65535:
+            raise ValueError("compact results need t_a <= 65535")
+        self.engine, self.n_img, self.t_a, self.chunk, self.compact = engine, n_img, t_a, chunk, compact
+        self.out_keys = ("mu", "cov", "contours", "area", "count16") if compact else ("mu", "cov", "contours", "area", "mean", "entropy", "pred")
         dev = engine.device
         self.streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
         self.d_in = [torch.empty((chunk, K, HW, HW), dtype=torch.float32, device=dev) for _ in range(n_streams)]
-        self.ws = [engine.workspace(chunk, t_a, want_count=False) for _ in range(n_streams)]
+        self.ws = [engine.workspace(chunk, t_a, want_count=False, want_maps=not compact, want_count16=compact) for _ in range(n_streams)]
 
     def host_outputs(self):
         n, T = self.n_img, self.t_a
         spec = {"mu": ((n, K, 2), torch.float32), "cov": ((n, K, 2, 2), torch.float32),
                 "contours": ((n, T, K, 2), torch.float32), "area": ((n, T), torch.int32),
                 "mean": ((n, HW, HW), torch.float64), "entropy": ((n, HW, HW), torch.float64),
-                "pred": ((n, HW, HW), torch.uint8)}
-        return {k: torch.empty(s, dtype=d, pin_memory=True) for k, (s, d) in spec.items()}
+                "pred": ((n, HW, HW), torch.uint8), "count16": ((n, HW, HW), torch.uint16)}
+        return {k: torch.empty(*[spec[k][0]], dtype=spec[k][1], pin_memory=True) for k in self.out_keys}
+
+    def expand(self, h_out: dict) -> dict:
+        """mean / entropy / pred / variance maps of a compact result (host, exact)."""
+        return maps_from_count(h_out["count16"].numpy(), self.t_a)
 
     def run(self, h_logits: torch.Tensor, h_out: dict, seed: int = 0):
         """Asynchronous: returns after enqueueing; the caller's current stream waits for the result."""
@@ -1168,7 +1177,7 @@ class HostPipeline:
                 # one seed for the whole batch, the chunk's position as the Philox counter offset: the draws of an image
                 # do not depend on the chunk size and no two (step, chunk) pairs share a stream
                 self.engine.run_into(ws, self.d_in[si], seed=seed, stream=st, sample_offset=c0 * self.t_a)
-                for k in self.OUT_KEYS:
+                for k in self.out_keys:
                     h_out[k][c0:c0 + self.chunk].copy_(getattr(ws, k), non_blocking=True)
         for st in self.streams:
             cur.wait_stream(st)

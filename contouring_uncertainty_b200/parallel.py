@@ -103,6 +103,74 @@ class StepExchange:
         return (self.last["gathered"], self.last["stats"]) if self.last is not None else (None, None)
 
 
+class MetricExchange:
+    """The path's exchange as ONE collective per block of ``every`` steps (default: one per predict epoch).
+
+    The reference gathers nothing per batch: its clinical metric processors run at the END of the predict epoch over all
+    BatchResults (cu/results/clinical/clinical_metrics.py:51-66).  So a rank only buffers what those processors need --
+    per step the per-image metric distributions (n_local, T) int32 and the exact int64 dataset sums -- in a device ring of
+    ``every`` slots, and one ``all_gather_into_tensor`` ships a whole block: [every][n_local * T + 4] int32 words per rank, the
+    two int64 sums riding in the last 4 words of each slot (no separate all_reduce: every rank adds the gathered sums
+    itself, exactly, in int64).  Blocks are double-buffered and the collective is asynchronous, so block b is on the wire
+    while block b + 1 fills; ``finish()`` flushes a partial block and joins everything onto the current stream.
+    """
+
+    def __init__(self, n_local: int, n_per_image: int, every: int, device, group=None, n_blocks: int = 2):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.every = max(1, int(every))
+        self.n_local, self.n_per_image = int(n_local), int(n_per_image)
+        self.payload = self.n_local * self.n_per_image + 4
+        self.blocks = [{"local": torch.zeros((self.every, self.payload), dtype=torch.int32, device=device),
+                        "gathered": torch.zeros((self.world * self.every, self.payload), dtype=torch.int32, device=device),
+                        "work": None, "filled": 0} for _ in range(n_blocks)]
+        self.cur = 0
+        self.collectives = 0
+        self.last = None
+
+    def push(self, values: torch.Tensor, sums: torch.Tensor):
+        """values (n_local, n_per_image) int32, sums (2,) int64 of this step (device tensors, no synchronisation)."""
+        blk = self.blocks[self.cur]
+        if blk["filled"] == 0 and blk["work"] is not None:      # the block is being reused: its previous exchange must be done
+            blk["work"].wait()
+            blk["work"] = None
+        slot = blk["local"][blk["filled"]]
+        slot[:self.payload - 4].copy_(values.reshape(-1), non_blocking=True)
+        slot[self.payload - 4:].copy_(sums.view(torch.int32), non_blocking=True)
+        blk["filled"] += 1
+        if blk["filled"] == self.every:
+            self._ship(blk)
+
+    def _ship(self, blk):
+        if self.world > 1:
+            blk["work"] = dist.all_gather_into_tensor(blk["gathered"], blk["local"], group=self.group, async_op=True)
+            self.collectives += 1
+        else:
+            blk["gathered"].copy_(blk["local"], non_blocking=True)
+        blk["shipped"] = blk["filled"]
+        blk["filled"] = 0
+        self.last = blk
+        self.cur = (self.cur + 1) % len(self.blocks)
+
+    def finish(self):
+        """Ship a partial block, wait for everything in flight.  Returns (values (world, steps, n_local, n_per_image) int32,
+        sums (steps, 2) int64 summed over the ranks) of the LAST shipped block, or (None, None) if nothing was pushed."""
+        blk = self.blocks[self.cur]
+        if blk["filled"]:
+            self._ship(blk)
+        for b in self.blocks:
+            if b["work"] is not None:
+                b["work"].wait()
+                b["work"] = None
+        if self.last is None:
+            return None, None
+        k = self.last["shipped"]
+        g = self.last["gathered"].view(self.world, self.every, self.payload)[:, :k]
+        values = g[..., :self.payload - 4].reshape(self.world, k, self.n_local, self.n_per_image)
+        sums = g[..., self.payload - 4:].contiguous().view(torch.int64).sum(0)
+        return values, sums
+
+
 def bind_to_gpu_numa_node(device_index: int) -> bool:
     """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (so that pinned host
     buffers allocated afterwards are first-touched on the GPU's NUMA node and H2D / D2H copies do not cross sockets).

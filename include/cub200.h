@@ -41,6 +41,9 @@ const char* cub200_last_error(void);
 /* ABI version (bumped on any signature change) and the SM the kernels were built for (100). */
 int cub200_abi_version(void);
 int cub200_built_for_sm(void);
+/* Number of kernels this library has launched in this process so far (all threads, all streams): what a caller subtracts
+ * around a region to report how many of the library's kernels ran in it. */
+int64_t cub200_launch_count(void);
 
 /*
  * K1  DSNT heads: fused flat-softmax + coordinate expectation + 2x2 central second moments, one

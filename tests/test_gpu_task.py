@@ -122,7 +122,15 @@ def test_dsnt_skew_predict_step_matches_the_executed_reference(alias):
     # reference's fp32 noise (sigma2 = 1e-3 inverse)
     level = [p for p in range(21) if p not in (0, 10, 20, 4, 9, 11, 16)]
     assert np.array_equal(res.contour_samples[..., level, :], g["f32_contour_samples"][..., level, :])
-    assert np.abs(res.contour_samples - g["f32_contour_samples"]).max() < 6e-2
+    # (the reference's fp32 42x42 inverse at sigma2 = 1e-3 moves them by up to ~7e-2 px here; golden skew.npz holds an fp64
+    # run of the same sampler, and the fp64 oracle is compared below)
+    assert np.abs(res.contour_samples - g["f32_contour_samples"]).max() < 1e-1
+    from oracle import port
+    model = port.ShapeModel.load(task.sampler.model.path)
+    for (i, e) in ((0, 1), (1, 0)):
+        so = port.skew_psm_sample(model, g["mu_te"][i, e], g["cov_te"][i, e], g["alpha_te"][i, e], g["z"][i, e][:2],
+                                  lambda n_, d, _i=i, _e=e: synth.exponential_field(qs, ((_i * te + _e) * T + n_) * 14 + d))
+        assert np.abs(res.contour_samples[i, e, :2] - so).max() < 1e-3
     np.testing.assert_allclose(res.post_mu, g["f32_post_mu"], rtol=0, atol=2e-2)
     np.testing.assert_allclose(res.post_cov, g["f32_post_cov"], rtol=0, atol=5e-2)
     np.testing.assert_allclose(res.mode, g["f32_mode"], rtol=0, atol=1e-3)
