@@ -421,7 +421,8 @@ class Skew(PathConfig):
             self.h_c16[sl].copy_(out[-1], non_blocking=True)
 
     def e2e_check(self):
-        return bool(int(self.h_area[-1].min()) > 0 and int(self.h_c16[-1].max()) <= self.T)
+        torch = self.torch
+        return bool(int(self.h_area[-1].min()) > 0 and int(self.h_c16[-1].to(torch.int32).max()) <= self.T)
 
     def parity_spot_check(self):
         from oracle import port

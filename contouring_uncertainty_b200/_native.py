@@ -23,7 +23,7 @@ _vp, _i32, _i64, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
 
 # name -> argtypes; every function returns int except the three queries
 SIGNATURES = {
-    "cub200_dsnt_moments": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "cub200_dsnt_moments": [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "cub200_psm_model_pack_host": [_vp, _vp, _vp, _vp, _vp],
     "cub200_psm_factor": [_vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
@@ -60,7 +60,7 @@ SIGNATURES = {
     "cub200_seg_entropy": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes",
-           "cub200_seg_blob_workspace_bytes", "cub200_raster_workspace_bytes", "cub200_launch_count")
+           "cub200_seg_blob_workspace_bytes", "cub200_raster_workspace_bytes", "cub200_launch_count", "cub200_dsnt_workspace_bytes")
 
 
 class NativeError(RuntimeError):
@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
         l.cub200_calibration_workspace_bytes.argtypes = []
         l.cub200_seg_blob_workspace_bytes.restype = C.c_int64
         l.cub200_seg_blob_workspace_bytes.argtypes = [_i64]
+        l.cub200_dsnt_workspace_bytes.restype = C.c_int64
+        l.cub200_dsnt_workspace_bytes.argtypes = [_i64]
         l.cub200_launch_count.restype = C.c_int64
         l.cub200_launch_count.argtypes = []
         l.cub200_raster_workspace_bytes.restype = C.c_int64

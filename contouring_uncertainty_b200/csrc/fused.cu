@@ -54,6 +54,9 @@ namespace cub200 {
 #ifndef CUB200_FW_MINBLOCKS
 #define CUB200_FW_MINBLOCKS 2
 #endif
+#ifndef CUB200_EVAL_STRIDED
+#define CUB200_EVAL_STRIDED 1
+#endif
 constexpr int FW_WARPS = CUB200_FW_WARPS;
 constexpr int FW_MINBLOCKS = CUB200_FW_MINBLOCKS;
 constexpr int FW_THREADS = FW_WARPS * 32;
@@ -196,27 +199,50 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
     if (linear) {
         // polygon outline only: every edge is drawn by step 5
     } else if (!bad) {
-        // 3c/4. evaluate 1000 points (32 consecutive per lane), round half-even, apply the index
-        //       rules and set the pixels on the fly (consecutive points falling into the same
-        //       32-pixel word are merged into one shared-memory atomic).  An index < -256 makes the
+        // 3c/4. evaluate 1000 points, round half-even, apply the index rules and set the pixels on the fly.
+        //       An index < -256 makes the
         //       reference's whole assignment raise: then the bitmap is simply cleared again (the
         //       closing line is drawn afterwards).
-        const int j0 = min(lane * 32, NPTS - 32);           // lane 31 re-draws 24 points of lane 30
         const double step = 1.0 / (double)(NPTS - 1);       // j * step == np.linspace(0, 1, 1000)[j] exactly
-        int piece = ws.sp.start_piece[lane];
+        int lowest = 0;
+#if CUB200_EVAL_STRIDED
+        // Point j = 32 t + lane in iteration t: the 32 lanes always sit in the same one or two pieces, every iteration
+        // fetches its piece's coefficients (a broadcast read), nothing but the piece index is carried from one iteration to
+        // the next, so iterations overlap freely; each point is one shared-memory atomic.  Points 1000..1023 of the last
+        // iteration re-draw point 999.
+        int piece = 0;
+        int jnext = ws.sp.jnext[0];
+#pragma unroll 2
+        for (int t = 0; t < 32; ++t) {
+            const int j = min(32 * t + lane, NPTS - 1);
+            while (j >= jnext) jnext = ws.sp.jnext[++piece];  // jnext of the last piece is INT_MAX
+            const double2* pc = reinterpret_cast<const double2*>(ws.sp.piece[piece]);
+            const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];
+            const double sv = (double)j * step - q0.y;
+            const double xv = fma(fma(fma(q2.y, sv, q2.x), sv, q1.y), sv, q1.x);
+            const double yv = fma(fma(fma(q4.y, sv, q4.x), sv, q3.y), sv, q3.x);
+            const int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
+            lowest = __vimin3_s32(lowest, ix, iy);
+            // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
+            const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
+            atomicOr(&bmp[cell + ((cell >> 4) & ~3u)], 1u << (ix & 31));                        // + (row >> 3) * 4
+        }
+#else
+        const int j0 = min(lane * 32, NPTS - 32);           // lane 31 re-draws 24 points of lane 30
+        int piece = 0;
+        while (j0 >= ws.sp.jnext[piece]) ++piece;
         double ub, c0, c1, c2, c3, e0, e1, e2, e3;
         int jnext;
 #define CUB200_LOAD_PIECE()                                                              \
         {                                                                                \
             const double2* pc = reinterpret_cast<const double2*>(ws.sp.piece[piece]);       \
             const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];    \
-            jnext = __double_as_longlong(q0.x) & 0xffffffff; ub = q0.y;                  \
+            jnext = ws.sp.jnext[piece]; ub = q0.y;                                       \
             c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;                                  \
             e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                  \
         }
         CUB200_LOAD_PIECE();
         uint32_t cur = 0u, bits = 0u;                        // cur: physical word index of the pending (row, word) cell
-        int lowest = 0;
         double jd = (double)j0;
 #pragma unroll 4
         for (int jj = 0; jj < 32; ++jj) {
@@ -241,6 +267,7 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
         }
 #undef CUB200_LOAD_PIECE
         if (bits) atomicOr(&bmp[cur], bits);
+#endif
         oob = __any_sync(FULL, lowest < -256);
         if (oob) {                                           // IndexError in the reference: nothing drawn
             __syncwarp();

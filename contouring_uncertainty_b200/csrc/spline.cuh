@@ -29,8 +29,8 @@ struct __align__(16) SplineScratch {
 // Layout of the rasteriser's hot loop (fused.cu): the knots are replaced by the INDEX of the first of the 1000 evaluation
 // points that belongs to a later piece, so the per-point piece test is an integer comparison.
 struct __align__(16) SplineScratchIdx {
-    double piece[20][10];  // {jnext (int32 in the low word), u_i, x c0..c3, y c0..c3}
-    int start_piece[32];   // piece of the first point (32 * lane, lane 31: 968) each lane of the rasteriser evaluates
+    double piece[20][10];  // {unused, u_i, x c0..c3, y c0..c3}
+    int jnext[32];         // jnext[p] = first evaluation point of a piece after p (INT_MAX for the last piece, 19)
 };
 
 constexpr int SPLINE_NPTS = 1000;   // contour_spline(points, n=1000)
@@ -85,23 +85,7 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         const int jstart = (lane == 0) ? 0 : first_point_at_or_after(u);
         jnext = __shfl_down_sync(FULL, jstart, 1);
         if (lane >= KP - 2) jnext = INT_MAX;
-        // piece of the first point each lane of the rasteriser evaluates (32 l; lane 31: 968): the number of knots
-        // u_1..u_19 at or before it.  Knot k counts for the lanes l >= ceil(jstart_k / 32): one ballot per bit of that
-        // threshold would do; cheaper is a 32-bin histogram in shared memory and a warp prefix sum.
-        sp.start_piece[lane] = 0;
-        __syncwarp();
-        if (lane >= 1 && lane <= KP - 2) {
-            const int first_lane = (jstart <= SPLINE_NPTS - 32) ? ((jstart + 31) >> 5) : 32;
-            if (first_lane < 32) atomicAdd(&sp.start_piece[first_lane], 1);
-        }
-        __syncwarp();
-        int cnt = sp.start_piece[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, cnt, o);
-            if (lane >= o) cnt += t;
-        }
-        sp.start_piece[lane] = cnt;
+        if (lane < KP - 1) sp.jnext[lane] = jnext;
     } else {
         if (lane < KP) sp.u[lane] = u;
     }
@@ -152,7 +136,7 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         const double m1x = __shfl_down_sync(FULL, Mx, 1), m1y = __shfl_down_sync(FULL, My, 1);
         if (lane < KP - 1) {                             // piece coefficients
             double2* c = reinterpret_cast<double2*>(sp.piece[lane]);
-            c[0] = make_double2(INDEXED ? __longlong_as_double((long long)(unsigned)jnext) : unext, u);
+            c[0] = make_double2(unext, u);
             c[1] = make_double2(X, dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0));
             c[2] = make_double2(0.5 * Mx, (m1x - Mx) * ih * (1.0 / 6.0));
             c[3] = make_double2(Y, dyk - h * (2.0 * My + m1y) * (1.0 / 6.0));

@@ -30,6 +30,11 @@ DEFAULT_SEQ_PSM = os.path.join(DATA_DIR, "camus-cont_sequence_psm_11_no_std.npy"
 # --------------------------------------------------------------------------------------------------
 # K1
 # --------------------------------------------------------------------------------------------------
+def dsnt_workspace(n_maps: int, device) -> torch.Tensor:
+    """Zeroed workspace of ``cub200_dsnt_moments`` for ``n_maps`` heatmaps (row-slab partial moments + tickets)."""
+    return torch.zeros((max(int(nat.lib().cub200_dsnt_workspace_bytes(int(n_maps))), 16),), dtype=torch.uint8, device=device)
+
+
 def dsnt_moments(heat: torch.Tensor, is_logit: bool = True, covar: bool = True):
     """Fused flat_softmax + dsnt + pixel rescale (dsnt/utils.py:7-47,71-77,95-105; dsnt_al.py:118-131).
 
@@ -45,7 +50,8 @@ def dsnt_moments(heat: torch.Tensor, is_logit: bool = True, covar: bool = True):
     sig = torch.empty((n, k, 2, 2), dtype=torch.float32, device=heat.device)
     with torch.cuda.device(heat.device):
         rc = nat.lib().cub200_dsnt_moments(nat.ptr(heat), n * k, HW, HW, int(is_logit), int(covar), nat.ptr(norm),
-                                           nat.ptr(mu), nat.ptr(sig), nat.stream_ptr(heat.device))
+                                           nat.ptr(mu), nat.ptr(sig), nat.ptr(dsnt_workspace(n * k, heat.device)),
+                                           nat.stream_ptr(heat.device))
     nat.check(rc, "cub200_dsnt_moments")
     return norm, mu, sig
 
@@ -1045,6 +1051,7 @@ class Workspace:
         self.pred = torch.empty((n_img, HW, HW), dtype=torch.uint8, device=dev)
         self.lut = torch.empty((t_a + 1,), dtype=f64, device=dev)
         self.raster_ws = raster_workspace(n_img * t_a, dev)
+        self.dsnt_ws = dsnt_workspace(n_img * K, dev)
 
     def result(self) -> "UncertaintyResult":
         return UncertaintyResult(self.mu, self.cov, self.contours, self.area, self.count, self.mean, self.entropy, self.pred)
@@ -1095,7 +1102,7 @@ class UncertaintyEngine:
         n, T = ws.n_img, ws.t_a
         with torch.cuda.device(ws.device):
             nat.check(L.cub200_dsnt_moments(logits.data_ptr(), n * K, HW, HW, 1, int(self.covar), None, ws.mu.data_ptr(),
-                                            ws.cov.data_ptr(), st), "cub200_dsnt_moments")
+                                            ws.cov.data_ptr(), ws.dsnt_ws.data_ptr(), st), "cub200_dsnt_moments")
             if self.sampler == "psm":
                 m = self.model
                 nat.check(L.cub200_psm_factor(m.pack.data_ptr(), ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st),

@@ -59,9 +59,14 @@ int64_t cub200_launch_count(void);
  *   pix_mu    optional (n_maps, 2) fp32 pixel coordinates (x, y).
  *   pix_sigma optional (n_maps, 2, 2) fp32 pixel covariance; off-diagonals 0 when use_covar == 0
  *             (hparams.covar, dsnt_al.py:124).
+ *   workspace optional: cub200_dsnt_workspace_bytes(n_maps) bytes of device memory, ZERO before its first use (the call
+ *             leaves it zeroed again).  With it, small batches are cut into 2 / 4 / 8 row slabs per heatmap whose partial
+ *             moments the last-arriving CTA merges, so that the launch is >= 10 waves of resident CTAs instead of ending on
+ *             a nearly empty one; NULL = one CTA per heatmap.  A workspace must not be shared by concurrent calls.
  */
 int cub200_dsnt_moments(const float* heat, int64_t n_maps, int h, int w, int is_logit, int use_covar,
-                        float* norm_out, float* pix_mu, float* pix_sigma, void* stream);
+                        float* norm_out, float* pix_mu, float* pix_sigma, void* workspace, void* stream);
+int64_t cub200_dsnt_workspace_bytes(int64_t n_maps);
 
 /*
  * Shape-model constants, packed once per model ON THE HOST (plain C++, no device work): the sampling-order

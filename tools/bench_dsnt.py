@@ -1,18 +1,28 @@
-"""DSNT kernel alone at config-2 size: CUB200_DSNT_CLUSTER=1|2|4 python tools/bench_dsnt.py [n_img]"""
+"""Micro-benchmark of K1 (dsnt_moments) at the headline size and beyond, with and without the row-slab split."""
 import os, sys
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import bench as B
 from contouring_uncertainty_b200 import engine as E
 dev = torch.device("cuda:0")
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-logits = B.make_logits_on_device(torch, dev, n, seed=1)
-for _ in range(5): E.dsnt_moments(logits)
-torch.cuda.synchronize()
-ts = []
-for _ in range(50):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); r = E.dsnt_moments(logits); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-t = float(np.median(ts))
-print(f"cluster={os.environ.get('CUB200_DSNT_CLUSTER', '4')} n_img={n}: dsnt {t*1e3:.1f} us, {n*21*(65536*4+44)/t/1e6:.0f} GB/s, mu[0,0]={r[1][0,0].tolist()}")
+L = E.nat.lib(); st = torch.cuda.current_stream().cuda_stream
+for n in (1, 8, 64, 512):
+    logits = B.make_logits_on_device(torch, dev, n, seed=3)
+    mu = torch.empty((n, 21, 2), device=dev); sig = torch.empty((n, 21, 2, 2), device=dev)
+    mu0 = torch.empty_like(mu); sig0 = torch.empty_like(sig)
+    ws = E.dsnt_workspace(n * 21, dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    res = {}
+    for name, w, (m, s) in (("one CTA per heatmap", None, (mu0, sig0)), ("row-slab split", ws.data_ptr(), (mu, sig))):
+        ts = []
+        for i in range(25):
+            if n < 64: flush.zero_()                       # inputs smaller than L2: flush between iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            E.nat.check(L.cub200_dsnt_moments(logits.data_ptr(), n * 21, 256, 256, 1, 1, None, m.data_ptr(), s.data_ptr(), w, st), "dsnt")
+            e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        res[name] = float(np.median(ts[5:]))
+    gb = n * 21 * (256 * 256 * 4 + 44) / 1e9
+    print(f"n_img {n:4d}: " + ", ".join(f"{k} {v * 1e3:7.1f} us = {gb / (v * 1e-3):6.0f} GB/s" for k, v in res.items()),
+          "| max |d mu|", float((mu - mu0).abs().max()), "max rel d sigma", float(((sig - sig0).abs() / sig0.abs().clamp_min(1e-3)).max()),
+          "| workspace zero again:", bool((ws == 0).all()))
