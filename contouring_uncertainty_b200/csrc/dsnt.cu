@@ -14,11 +14,11 @@
 // one-pass kernel suffers (1e-4 rel) never builds up.  The x moments are recovered
 // at the end from the 8 column sums, and every cross-warp merge / final subtraction runs in fp64.
 //
-// Small batches (the headline's 64 images = 1344 heatmaps = 3.03 waves of the 444 resident CTAs) lose the time of one whole
-// heatmap to the last, nearly empty wave.  With a workspace the launch cuts every heatmap into SPLIT row slabs (2, 4 or 8,
-// chosen so that the grid is >= ~10 waves): a CTA reduces its slab to 6 fp64 moments about its own centre, publishes them,
-// takes a ticket, and the last CTA of a heatmap re-centres and adds the slabs in slab order (deterministic) -- the same
-// exact shift identities as the cross-warp merge.
+// With a workspace the launch is PERSISTENT: one wave of resident CTAs (3 per SM), each taking an equal, contiguous range
+// of the batch's rows (n_maps x 256).  A heatmap that straddles two ranges is reduced in two parts: each CTA reduces its
+// part to 6 fp64 moments about its own centre, publishes them, takes a ticket, and the CTA that arrives last re-centres and
+// adds the parts in part order (deterministic) -- the same exact shift identities as the cross-warp merge.  Without it the
+// headline's 1344 heatmaps are 3.03 waves of 444 CTAs and the last, nearly empty wave costs the time of a whole heatmap.
 #include "common.cuh"
 
 namespace cub200 {
@@ -44,150 +44,159 @@ template <bool IS_LOGIT>
 __global__ void __launch_bounds__(DSNT_THREADS, 3)
 dsnt_moments_kernel(const float* __restrict__ heat, int64_t n_maps, int use_covar,
                     float* __restrict__ norm_out, float* __restrict__ pix_mu, float* __restrict__ pix_sigma,
-                    int split, DsntSlot* __restrict__ slots) {
+                    int64_t rows_per_cta, DsntSlot* __restrict__ slots) {
     __shared__ float s_m[8];
     __shared__ int s_rc[8], s_cc[8];
     __shared__ double s_red[8][6];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t map = blockIdx.x / split;
-    const int part = blockIdx.x % split;
-    const int rows_per_warp = 32 / split;                    // 32, 16, 8 or 4 (a multiple of ROWS_PER_TILE)
-    const float4* base = reinterpret_cast<const float4*>(heat + map * (int64_t)(DSNT_W * DSNT_W));
-    const int row0 = part * (DSNT_W / split) + warp * rows_per_warp;
+    const int64_t total_rows = n_maps * DSNT_W;
+    const int64_t r_end = min((int64_t)(blockIdx.x + 1) * rows_per_cta, total_rows);
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_cta; r < r_end;) {
+        // rows [lo, hi) of heatmap `map` (lo, hi multiples of ROWS_PER_TILE)
+        const int64_t map = r / DSNT_W;
+        const int lo = (int)(r - map * DSNT_W);
+        const int hi = (int)min((int64_t)DSNT_W, lo + (r_end - r));
+        r += hi - lo;
+        const float4* base = reinterpret_cast<const float4*>(heat + map * (int64_t)(DSNT_W * DSNT_W));
 
-    float C[8], R[8], RR[8];
+        float C[8], R[8], RR[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) C[j] = R[j] = RR[j] = 0.f;
-    float m = -INFINITY;                   // running max (logit, or heat value when !IS_LOGIT)
-    int rc = row0;                         // row centre of the dy moments (warp-uniform)
-    int cc = 0;                            // column of the running max (warp-uniform)
+        for (int j = 0; j < 8; ++j) C[j] = R[j] = RR[j] = 0.f;
+        float m = -INFINITY;                   // running max (logit, or heat value when !IS_LOGIT)
+        int rc = lo;                           // row centre of the dy moments (warp-uniform)
+        int cc = 0;                            // column of the running max (warp-uniform)
 
-    for (int t = 0; t < rows_per_warp / ROWS_PER_TILE; ++t) {
-        const int r_tile = row0 + t * ROWS_PER_TILE;
-        float4 v[ROWS_PER_TILE][2];
+        // the 8 warps take the tiles of the part round robin: at any time the CTA streams 32 consecutive rows
+        for (int r_tile = lo + warp * ROWS_PER_TILE; r_tile < hi; r_tile += 8 * ROWS_PER_TILE) {
+            float4 v[ROWS_PER_TILE][2];
 #pragma unroll
-        for (int r = 0; r < ROWS_PER_TILE; ++r) {
-            const float4* rowp = base + (int64_t)(r_tile + r) * (DSNT_W / 4);
-            v[r][0] = ld_stream_f4(rowp + lane);
-            v[r][1] = ld_stream_f4(rowp + 32 + lane);
-        }
-        {
-            float tm = -INFINITY;
-#pragma unroll
-            for (int r = 0; r < ROWS_PER_TILE; ++r) {
-                tm = fmaxf(tm, fmaxf(fmaxf(v[r][0].x, v[r][0].y), fmaxf(v[r][0].z, v[r][0].w)));
-                tm = fmaxf(tm, fmaxf(fmaxf(v[r][1].x, v[r][1].y), fmaxf(v[r][1].z, v[r][1].w)));
+            for (int q = 0; q < ROWS_PER_TILE; ++q) {
+                const float4* rowp = base + (int64_t)(r_tile + q) * (DSNT_W / 4);
+                v[q][0] = ld_stream_f4(rowp + lane);
+                v[q][1] = ld_stream_f4(rowp + 32 + lane);
             }
-            const int wmax_i = __reduce_max_sync(FULL, float_ordered(tm));
-            const float wmax = ordered_float(wmax_i);
-            if (wmax > m) {  // warp-uniform
-                // which lane/column holds it (first lane wins); row centre moves to this tile
-                const unsigned who = __ballot_sync(FULL, tm == wmax);
-                const int src = __ffs(who) - 1;
-                int mycol = 0;
-                if (lane == src) {
+            {
+                float tm = -INFINITY;
 #pragma unroll
-                    for (int r = 0; r < ROWS_PER_TILE; ++r) {
-                        const float a[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w,
-                                            v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (a[j] == wmax) mycol = (j < 4) ? 4 * lane + j : 128 + 4 * lane + (j - 4);
-                    }
+                for (int q = 0; q < ROWS_PER_TILE; ++q) {
+                    tm = fmaxf(tm, fmaxf(fmaxf(v[q][0].x, v[q][0].y), fmaxf(v[q][0].z, v[q][0].w)));
+                    tm = fmaxf(tm, fmaxf(fmaxf(v[q][1].x, v[q][1].y), fmaxf(v[q][1].z, v[q][1].w)));
                 }
-                cc = __shfl_sync(FULL, mycol, src);
-                const float sc = IS_LOGIT ? ex2_approx((m - wmax) * LOG2E) : 1.f;  // m = -inf -> 0
-                const float d = (float)(r_tile - rc);             // new centre - old centre
+                const int wmax_i = __reduce_max_sync(FULL, float_ordered(tm));
+                const float wmax = ordered_float(wmax_i);
+                if (wmax > m) {  // warp-uniform
+                    // which lane/column holds it (first lane wins); row centre moves to this tile
+                    const unsigned who = __ballot_sync(FULL, tm == wmax);
+                    const int src = __ffs(who) - 1;
+                    int mycol = 0;
+                    if (lane == src) {
+#pragma unroll
+                        for (int q = 0; q < ROWS_PER_TILE; ++q) {
+                            const float a[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w,
+                                                v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (a[j] == wmax) mycol = (j < 4) ? 4 * lane + j : 128 + 4 * lane + (j - 4);
+                        }
+                    }
+                    cc = __shfl_sync(FULL, mycol, src);
+                    const float sc = IS_LOGIT ? ex2_approx((m - wmax) * LOG2E) : 1.f;  // m = -inf -> 0
+                    const float d = (float)(r_tile - rc);             // new centre - old centre
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        // moments about the new centre: dy' = dy - d
+                        const float c = C[j] * sc, r1 = R[j] * sc, r2 = RR[j] * sc;
+                        RR[j] = r2 - d * (2.f * r1 - d * c);
+                        R[j] = r1 - d * c;
+                        C[j] = c;
+                    }
+                    m = wmax;
+                    rc = r_tile;
+                }
+            }
+            const float mb = m * LOG2E;
+#pragma unroll
+            for (int q = 0; q < ROWS_PER_TILE; ++q) {
+                const float dy = (float)(r_tile + q - rc);
+                const float dy2 = dy * dy;
+                const float a[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w,
+                                    v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    // moments about the new centre: dy' = dy - d
-                    const float c = C[j] * sc, r1 = R[j] * sc, r2 = RR[j] * sc;
-                    RR[j] = r2 - d * (2.f * r1 - d * c);
-                    R[j] = r1 - d * c;
-                    C[j] = c;
+                    const float w = IS_LOGIT ? ex2_approx(fmaf(a[j], LOG2E, -mb)) : a[j];
+                    C[j] += w;
+                    R[j] = fmaf(w, dy, R[j]);
+                    RR[j] = fmaf(w, dy2, RR[j]);
                 }
-                m = wmax;
-                rc = r_tile;
             }
         }
-        const float mb = m * LOG2E;
-#pragma unroll
-        for (int r = 0; r < ROWS_PER_TILE; ++r) {
-            const float dy = (float)(r_tile + r - rc);
-            const float dy2 = dy * dy;
-            const float a[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w,
-                                v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float w = IS_LOGIT ? ex2_approx(fmaf(a[j], LOG2E, -mb)) : a[j];
-                C[j] += w;
-                R[j] = fmaf(w, dy, R[j]);
-                RR[j] = fmaf(w, dy2, RR[j]);
-            }
-        }
-    }
 
-    // ---- cross-warp merge in fp64 about the centre (rc*, cc*) of the warp holding the global max
-    if (lane == 0) { s_m[warp] = m; s_rc[warp] = rc; s_cc[warp] = cc; }
-    __syncthreads();
-    float mstar = s_m[0];
-    int best = 0;
+        // ---- cross-warp merge in fp64 about the centre (rc*, cc*) of the warp holding the part's max (a warp that had no
+        //      tile has m = -inf and zero moments: it contributes exactly 0)
+        __syncthreads();                                      // the previous part's readers of s_* are done
+        if (lane == 0) { s_m[warp] = m; s_rc[warp] = rc; s_cc[warp] = cc; }
+        __syncthreads();
+        float mstar = s_m[0];
+        int best = 0;
 #pragma unroll
-    for (int w = 1; w < 8; ++w)
-        if (s_m[w] > mstar) { mstar = s_m[w]; best = w; }
-    const int rcb = s_rc[best];
-    const int ccb = s_cc[best];
-    const double sc = IS_LOGIT ? (double)ex2_approx((m - mstar) * LOG2E) : 1.0;
-    const double d = (double)(rcb - rc);
-    double W = 0, Mx = 0, My = 0, Mxx = 0, Myy = 0, Mxy = 0;
+        for (int w = 1; w < 8; ++w)
+            if (s_m[w] > mstar) { mstar = s_m[w]; best = w; }
+        const int rcb = s_rc[best];
+        const int ccb = s_cc[best];
+        const double sc = IS_LOGIT ? (double)ex2_approx((m - mstar) * LOG2E) : 1.0;
+        const double d = (double)(rcb - rc);
+        double W = 0, Mx = 0, My = 0, Mxx = 0, Myy = 0, Mxy = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int col = (j < 4) ? 4 * lane + j : 128 + 4 * lane + (j - 4);
-        const double dx = (double)(col - ccb);
-        const double c = (double)C[j], r1 = (double)R[j], r2 = (double)RR[j];
-        const double r1s = r1 - d * c;                     // about rc*
-        const double r2s = r2 - d * (2.0 * r1 - d * c);
-        W += c;
-        Mx += c * dx;
-        Mxx += c * dx * dx;
-        My += r1s;
-        Myy += r2s;
-        Mxy += r1s * dx;
-    }
-    W = warp_sum(W * sc); Mx = warp_sum(Mx * sc); My = warp_sum(My * sc);
-    Mxx = warp_sum(Mxx * sc); Myy = warp_sum(Myy * sc); Mxy = warp_sum(Mxy * sc);
-    if (lane == 0) {
-        s_red[warp][0] = W; s_red[warp][1] = Mx; s_red[warp][2] = My;
-        s_red[warp][3] = Mxx; s_red[warp][4] = Myy; s_red[warp][5] = Mxy;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+        for (int j = 0; j < 8; ++j) {
+            const int col = (j < 4) ? 4 * lane + j : 128 + 4 * lane + (j - 4);
+            const double dx = (double)(col - ccb);
+            const double c = (double)C[j], r1 = (double)R[j], r2 = (double)RR[j];
+            const double r1s = r1 - d * c;                     // about rc*
+            const double r2s = r2 - d * (2.0 * r1 - d * c);
+            W += c;
+            Mx += c * dx;
+            Mxx += c * dx * dx;
+            My += r1s;
+            Myy += r2s;
+            Mxy += r1s * dx;
+        }
+        W = warp_sum(W * sc); Mx = warp_sum(Mx * sc); My = warp_sum(My * sc);
+        Mxx = warp_sum(Mxx * sc); Myy = warp_sum(Myy * sc); Mxy = warp_sum(Mxy * sc);
+        if (lane == 0) {
+            s_red[warp][0] = W; s_red[warp][1] = Mx; s_red[warp][2] = My;
+            s_red[warp][3] = Mxx; s_red[warp][4] = Myy; s_red[warp][5] = Mxy;
+        }
+        __syncthreads();
+        if (threadIdx.x != 0) continue;
+
         double a[6] = {0, 0, 0, 0, 0, 0};
         for (int w = 0; w < 8; ++w)
             for (int q = 0; q < 6; ++q) a[q] += s_red[w][q];
-        int rcs = s_rc[best], ccs = s_cc[best];                // centre of this CTA's moments (of the heatmap's after a merge)
-        if (split > 1) {
-            // publish this slab, take a ticket; the last slab of the heatmap merges all of them in slab order
+        int rcs = rcb, ccs = ccb;                              // centre of the moments (of the heatmap's after a merge)
+        if (hi - lo != DSNT_W) {
+            // a part of a heatmap: publish it, take a ticket; the last part to arrive merges all of them in part order
+            const int64_t first_cta = (map * DSNT_W) / rows_per_cta;
+            const int n_parts = (int)((map * DSNT_W + DSNT_W - 1) / rows_per_cta - first_cta) + 1;
             DsntSlot& slot = slots[map];
-            DsntPartial& me = slot.part[part];
+            DsntPartial& me = slot.part[blockIdx.x - first_cta];
 #pragma unroll
             for (int q = 0; q < 6; ++q) me.a[q] = a[q];
             me.m = mstar; me.rc = rcs; me.cc = ccs;
             __threadfence();
             const unsigned ticket = atomicAdd(&slot.ticket, 1u);
-            if (ticket != (unsigned)split - 1u) return;
+            if (ticket != (unsigned)n_parts - 1u) continue;
             __threadfence();
             slot.ticket = 0u;                                 // the workspace is ready for the next launch
             const volatile DsntPartial* pp = slot.part;
             float mg = pp[0].m;
             int bp = 0;
-            for (int p = 1; p < split; ++p)
+            for (int p = 1; p < n_parts; ++p)
                 if (pp[p].m > mg) { mg = pp[p].m; bp = p; }
             rcs = pp[bp].rc; ccs = pp[bp].cc;
 #pragma unroll
             for (int q = 0; q < 6; ++q) a[q] = 0.0;
-            for (int p = 0; p < split; ++p) {
+            for (int p = 0; p < n_parts; ++p) {
                 const double scp = IS_LOGIT ? (double)ex2_approx((pp[p].m - mg) * LOG2E) : 1.0;
                 const double dxc = (double)(pp[p].cc - ccs), dyc = (double)(pp[p].rc - rcs);
                 const double w = pp[p].a[0], mx = pp[p].a[1], my = pp[p].a[2];
@@ -233,10 +242,10 @@ dsnt_moments_kernel(const float* __restrict__ heat, int64_t n_maps, int use_cova
             pix_mu[map * 2 + 1] = (float)py;
         }
         if (pix_sigma) {
-            float* s = pix_sigma + map * 4;
-            s[0] = (float)vx;
-            s[1] = s[2] = use_covar ? (float)cxy : 0.f;
-            s[3] = (float)vy;
+            float* o = pix_sigma + map * 4;
+            o[0] = (float)vx;
+            o[1] = o[2] = use_covar ? (float)cxy : 0.f;
+            o[3] = (float)vy;
         }
     }
 }
@@ -254,18 +263,21 @@ extern "C" int cub200_dsnt_moments(const float* heat, int64_t n_maps, int h, int
     if (n_maps == 0) return 0;
     if (n_maps > 0x7fffffff / DSNT_MAX_SPLIT) return CUB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    // slabs per heatmap: the smallest power of two that makes the grid >= 10 waves of the resident CTAs (3 per SM)
-    int split = 1;
+    // with a workspace: one wave of resident CTAs over equal row ranges (multiples of the 4-row tile, >= 64 rows so that a
+    // heatmap has at most 5 parts); without: one CTA per heatmap
+    int64_t rows_per_cta = DSNT_W;
     if (workspace) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        while (split < DSNT_MAX_SPLIT && n_maps * split < 10LL * 3 * sms) split *= 2;
+        const int64_t total_rows = n_maps * DSNT_W, resident = 3LL * sms;
+        rows_per_cta = ((total_rows + resident - 1) / resident + ROWS_PER_TILE - 1) / ROWS_PER_TILE * ROWS_PER_TILE;
+        if (rows_per_cta < 64) rows_per_cta = 64;
     }
-    const unsigned grid = (unsigned)(n_maps * split);
+    const unsigned grid = (unsigned)((n_maps * DSNT_W + rows_per_cta - 1) / rows_per_cta);
     DsntSlot* slots = reinterpret_cast<DsntSlot*>(workspace);
     if (is_logit)
-        dsnt_moments_kernel<true><<<grid, DSNT_THREADS, 0, st>>>(heat, n_maps, use_covar, norm_out, pix_mu, pix_sigma, split, slots);
+        dsnt_moments_kernel<true><<<grid, DSNT_THREADS, 0, st>>>(heat, n_maps, use_covar, norm_out, pix_mu, pix_sigma, rows_per_cta, slots);
     else
-        dsnt_moments_kernel<false><<<grid, DSNT_THREADS, 0, st>>>(heat, n_maps, use_covar, norm_out, pix_mu, pix_sigma, split, slots);
+        dsnt_moments_kernel<false><<<grid, DSNT_THREADS, 0, st>>>(heat, n_maps, use_covar, norm_out, pix_mu, pix_sigma, rows_per_cta, slots);
     return check_launch("dsnt_moments_kernel");
 }

@@ -23,6 +23,8 @@ __global__ void entropy_lut_kernel(double* __restrict__ lut, int64_t T) {
     double e = (ep + eq) / log(2.0);
     if (!isfinite(e)) e = 0.0;
     lut[c] = e;
+    lut[(T + 1) + c] = p;                                  // mean = count / T
+    lut[2 * (T + 1) + c] = p * (1.0 - p);                  // Bernoulli variance of the samples
 }
 
 __global__ void __launch_bounds__(256)
@@ -58,24 +60,25 @@ finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T
         for (int j = 0; j < 4; ++j) w[j] = ((uint32_t)c[2 * j] & 0xffffu) | ((uint32_t)c[2 * j + 1] << 16);
         reinterpret_cast<uint4*>(count16_out + base)[0] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    const double dT = (double)T;
-    if (variance_out) {                                  // p (1 - p), p = count / T: the per-pixel Bernoulli variance of the samples
+    // the fp64 maps are functions of the count: three (T+1)-entry tables (entropy | mean | variance), L1-resident --
+    // a table read instead of an fp64 division per pixel
+    if (mean_out || entropy_out || variance_out) {
+        int cc[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            const double p0 = (double)c[j] / dT, p1 = (double)c[j + 1] / dT;
-            reinterpret_cast<double2*>(variance_out + base)[j >> 1] = make_double2(p0 * (1.0 - p0), p1 * (1.0 - p1));
+        for (int j = 0; j < 8; ++j) cc[j] = min(max(c[j], 0), (int)T);
+        const double* lm = lut + (T + 1);
+        const double* lv = lut + 2 * (T + 1);
+        if (variance_out) {                              // p (1 - p), p = count / T
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(variance_out + base)[j >> 1] = make_double2(lv[cc[j]], lv[cc[j + 1]]);
         }
-    }
-    if (mean_out) {
+        if (mean_out) {
 #pragma unroll
-        for (int j = 0; j < 8; j += 2)
-            reinterpret_cast<double2*>(mean_out + base)[j >> 1] = make_double2((double)c[j] / dT, (double)c[j + 1] / dT);
-    }
-    if (entropy_out) {
+            for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(mean_out + base)[j >> 1] = make_double2(lm[cc[j]], lm[cc[j + 1]]);
+        }
+        if (entropy_out) {
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            const int c0 = min(max(c[j], 0), (int)T), c1 = min(max(c[j + 1], 0), (int)T);
-            reinterpret_cast<double2*>(entropy_out + base)[j >> 1] = make_double2(lut[c0], lut[c1]);
+            for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(entropy_out + base)[j >> 1] = make_double2(lut[cc[j]], lut[cc[j + 1]]);
         }
     }
     if (pred_out) {
@@ -235,10 +238,10 @@ extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t 
     using namespace cub200;
     if (!diff || n_img < 0 || n_samples < 1 || n_samples > 0x3fffffff) return CUB200_EINVAL;
     if (count16_out && n_samples > 65535) return CUB200_EINVAL;
-    if (entropy_out && !lut_ws) return CUB200_EINVAL;
+    if ((entropy_out || mean_out || variance_out) && !lut_ws) return CUB200_EINVAL;
     if (n_img == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (entropy_out) {
+    if (entropy_out || mean_out || variance_out) {
         entropy_lut_kernel<<<(unsigned)((n_samples + 1 + 255) / 256), 256, 0, st>>>(lut_ws, n_samples);
         int rc = check_launch("entropy_lut_kernel");
         if (rc) return rc;

@@ -55,7 +55,7 @@ namespace cub200 {
 #define CUB200_FW_MINBLOCKS 2
 #endif
 #ifndef CUB200_EVAL_STRIDED
-#define CUB200_EVAL_STRIDED 1
+#define CUB200_EVAL_STRIDED 0
 #endif
 constexpr int FW_WARPS = CUB200_FW_WARPS;
 constexpr int FW_MINBLOCKS = CUB200_FW_MINBLOCKS;

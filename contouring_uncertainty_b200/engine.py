@@ -325,7 +325,7 @@ def finalize_maps(diff: torch.Tensor, n_samples: int, want_count: bool = True, w
     var = torch.empty((n, HW, HW), dtype=torch.float64, device=dev) if want_variance else None
     c16 = torch.empty((n, HW, HW), dtype=torch.uint16, device=dev) if want_count16 else None
     pred = torch.empty((n, HW, HW), dtype=torch.uint8, device=dev)
-    lut = torch.empty((int(n_samples) + 1,), dtype=torch.float64, device=dev)
+    lut = torch.empty((3 * (int(n_samples) + 1),), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         rc = nat.lib().cub200_finalize_maps(nat.ptr(diff), n, int(n_samples), nat.ptr(count), nat.ptr(mean), nat.ptr(ent),
                                             nat.ptr(pred), nat.ptr(lut), nat.ptr(var), nat.ptr(c16), nat.stream_ptr(dev))
@@ -1049,7 +1049,7 @@ class Workspace:
         self.variance = torch.empty((n_img, HW, HW), dtype=f64, device=dev) if want_variance else None
         self.count16 = torch.empty((n_img, HW, HW), dtype=torch.uint16, device=dev) if want_count16 else None
         self.pred = torch.empty((n_img, HW, HW), dtype=torch.uint8, device=dev)
-        self.lut = torch.empty((t_a + 1,), dtype=f64, device=dev)
+        self.lut = torch.empty((3 * (t_a + 1),), dtype=f64, device=dev)
         self.raster_ws = raster_workspace(n_img * t_a, dev)
         self.dsnt_ws = dsnt_workspace(n_img * K, dev)
 

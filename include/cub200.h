@@ -163,7 +163,8 @@ int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_l
  *   count_out optional (n_img,256,256) int32; mean_out optional fp64 = count/T;
  *   entropy_out optional fp64 binary entropy in bits (scipy.stats.entropy([p,1-p], base=2));
  *   pred_out optional uint8 = round-half-even(count/T)
- *   lut_ws: device workspace of (n_samples + 1) doubles (entropy of c/T), written by the call.
+ *   lut_ws: device workspace of 3 * (n_samples + 1) doubles (entropy, mean and variance of c/T, c = 0..T), written by the call;
+ *           needed when any of mean_out / entropy_out / variance_out is given.
  *   variance_out optional fp64 = p (1 - p), p = count/T: the per-pixel variance of the 0/1 samples (the reference has no
  *                variance map; this is the Bernoulli variance its mean map implies)
  *   count16_out optional uint16 count map (n_samples <= 65535): mean / entropy / pred / variance are functions of the count,

@@ -27,7 +27,7 @@ int main(void) {
     CK(cudaMalloc((void**)&d_count, 65536 * 4));
     CK(cudaMalloc((void**)&d_mean, 65536 * 8));
     CK(cudaMalloc((void**)&d_ent, 65536 * 8));
-    CK(cudaMalloc((void**)&d_lut, (n + 1) * 8));
+    CK(cudaMalloc((void**)&d_lut, 3 * (n + 1) * 8));
     CK(cudaMalloc((void**)&d_pred, 65536));
     CK(cudaMemcpy(d_c, h_c, sizeof(h_c), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_diff, 0, 65536 * 4));

@@ -137,7 +137,15 @@ def test_dsnt_skew_predict_step_matches_the_executed_reference(alias):
     np.testing.assert_allclose(level_cov, g["f32_post_cov"][:, level], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(res.mode, g["f32_mode"], rtol=0, atol=1e-3)
     assert np.array_equal(res.pred, g["f32_pred"])
-    assert np.abs(res.uncertainty_map - g["f32_uncertainty_map"]).max() <= 1e-12
+    # skew u-map: 200 level contours are rasterised per image; the task's own moments differ from the reference's fp32 DSNT
+    # by ~1e-5 relative, which can move a level contour across a pixel centre in one of the 200 masks (that pixel's weighted
+    # mean then changes by one weight).  On the task's moments: a handful of pixels; on the REFERENCE's moments: every pixel.
+    d = np.abs(res.uncertainty_map - g["f32_uncertainty_map"])
+    assert (d > 1e-12).sum() <= 32 and d.max() < 5e-2
+    from contour_uncertainty.data.camus.utils import USSkewUmap
+    for i in range(n):
+        mode_i, um_i = USSkewUmap()(g["f32_mu"][i], g["f32_cov"][i], g["f32_alpha"][i], labels=[])
+        assert np.abs(um_i - g["f32_uncertainty_map"][i]).max() <= 1e-12 and np.abs(mode_i - g["f32_mode"][i]).max() < 1e-4
     want_ps = _unpack(g["f32_pred_samples"]).reshape(g["f32_pred_samples_shape"])
     same = (np.round(res.contour_samples) == np.round(g["f32_contour_samples"])).all((-1, -2))
     assert same.mean() > 0.9                                   # the filled-in points may round differently (fp32 noise)
