@@ -270,8 +270,14 @@ extern "C" int cub200_dsnt_moments(const float* heat, int64_t n_maps, int h, int
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int64_t total_rows = n_maps * DSNT_W, resident = 3LL * sms;
-        rows_per_cta = ((total_rows + resident - 1) / resident + ROWS_PER_TILE - 1) / ROWS_PER_TILE * ROWS_PER_TILE;
-        if (rows_per_cta < 64) rows_per_cta = 64;
+        // measured (tools/bench_dsnt.py): equal row ranges win when the one-CTA-per-heatmap grid would be 1..6 waves (the
+        // headline: 1344 heatmaps, 66.0 -> 63.6 us) or a small fraction of one (21 heatmaps: 16.4 -> 14.4 us); with many
+        // waves the dynamic CTA scheduler already balances, and staggers the per-heatmap epilogues better (512 images: 404 us
+        // against 429 us)
+        if ((n_maps >= resident && n_maps < 6 * resident) || 4 * n_maps <= resident) {
+            rows_per_cta = ((total_rows + resident - 1) / resident + ROWS_PER_TILE - 1) / ROWS_PER_TILE * ROWS_PER_TILE;
+            if (rows_per_cta < 64) rows_per_cta = 64;
+        }
     }
     const unsigned grid = (unsigned)((n_maps * DSNT_W + rows_per_cta - 1) / rows_per_cta);
     DsntSlot* slots = reinterpret_cast<DsntSlot*>(workspace);
