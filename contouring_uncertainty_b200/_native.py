@@ -30,6 +30,7 @@ SIGNATURES = {
     "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cub200_soft_masks": [_vp, _i64, _vp, _vp, _vp],
     "cub200_metric_ae_split": [_vp, _i64, _i64, _i64, _i32, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],
     "cub200_sample_moments": [_vp, _i64, _i64, _vp, _vp, _vp],
@@ -55,6 +56,7 @@ SIGNATURES = {
     "cub200_seg_largest_blob": [_vp, _i64, _vp, _vp, _vp, _vp],
     "cub200_sample_entropy": [_vp, _i64, _i32, _i32, _i64, _vp, _vp],
     "cub200_us_myo_masks": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
+    "cub200_mask_class_entropy": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "cub200_rasterize_contours_generic": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp],
     "cub200_mask_lv_length": [_vp, _i64, C.c_double, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_seg_entropy": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],

@@ -102,6 +102,53 @@ __global__ void fac_kernel(const int32_t* __restrict__ ed, const int32_t* __rest
     out[i] = f;
 }
 
+// soft masks of ContourUncertaintyTask.convert_to_mask(soft_mask=True) (cu/task/regression/contour_uncertainty.py:44-49):
+// skimage.filters.gaussian(mask, sigma=(5, 5), truncate=1) -- which is scipy.ndimage.gaussian_filter(mode='nearest') on the
+// float image: an 11-tap normalised Gaussian along axis 0, then along axis 1, each sum formed as scipy's symmetric
+// correlate1d forms it (centre tap first, then the pairs from the outermost inwards) -- followed by the reference's
+// (mask - min) / (max - min).  One CTA per mask; the weights come from the host (numpy's exp, as scipy computes them).
+constexpr int SOFT_R = 5;
+__global__ void __launch_bounds__(256)
+soft_mask_kernel(const uint32_t* __restrict__ masks, const double* __restrict__ w /* w[0..5]: centre .. outermost */,
+                 double* __restrict__ out) {
+    __shared__ uint32_t bits[CUB200_MASK_WORDS];
+    __shared__ double row[256];
+    __shared__ double red[2][8];
+    const int x = threadIdx.x;
+    const uint32_t* m = masks + (int64_t)blockIdx.x * CUB200_MASK_WORDS;
+    double* o = out + (int64_t)blockIdx.x * 65536;
+    for (int i = x; i < CUB200_MASK_WORDS; i += 256) bits[i] = m[i];
+    __syncthreads();
+    double wk[SOFT_R + 1];
+#pragma unroll
+    for (int j = 0; j <= SOFT_R; ++j) wk[j] = w[j];
+    auto px = [&](int r, int c) { return (double)((bits[r * 8 + (c >> 5)] >> (c & 31)) & 1u); };
+    double vmin = 1e300, vmax = -1e300;
+    for (int y = 0; y < 256; ++y) {
+        // axis 0 (rows) for column x of row y, edge rows repeated (mode='nearest')
+        double t = px(y, x) * wk[0];
+#pragma unroll
+        for (int j = SOFT_R; j >= 1; --j) t += (px(max(y - j, 0), x) + px(min(y + j, 255), x)) * wk[j];
+        row[x] = t;
+        __syncthreads();
+        // axis 1 (columns) on the row just formed
+        double v = row[x] * wk[0];
+#pragma unroll
+        for (int j = SOFT_R; j >= 1; --j) v += (row[max(x - j, 0)] + row[min(x + j, 255)]) * wk[j];
+        o[y * 256 + x] = v;
+        vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { vmin = fmin(vmin, __shfl_xor_sync(FULL, vmin, s)); vmax = fmax(vmax, __shfl_xor_sync(FULL, vmax, s)); }
+    if ((x & 31) == 0) { red[0][x >> 5] = vmin; red[1][x >> 5] = vmax; }
+    __syncthreads();
+    vmin = red[0][0]; vmax = red[1][0];
+    for (int k = 1; k < 8; ++k) { vmin = fmin(vmin, red[0][k]); vmax = fmax(vmax, red[1][k]); }
+    const double den = vmax - vmin;
+    for (int y = 0; y < 256; ++y) o[y * 256 + x] = (o[y * 256 + x] - vmin) / den;   // 0 / 0 -> NaN for a constant mask, as numpy gives
+}
+
 // Aleatoric / epistemic split of Monte-Carlo metric distributions (results/clinical/utils.py:3-18 and the reject rule of
 // FAC / GLS / Volume.compute, view.py:52-53, patient.py:192-193): one warp per item, values (T_e, T_a) fp64.
 //   v < lo or v > hi (NaN compares false, as in numpy) -> rejected: the value becomes NaN
@@ -250,6 +297,14 @@ extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t 
     finalize_maps_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(diff, rows, n_samples, count_out, mean_out,
                                                                     entropy_out, pred_out, lut_ws, variance_out, count16_out);
     return check_launch("finalize_maps_kernel");
+}
+
+extern "C" int cub200_soft_masks(const uint32_t* masks, int64_t n, const double* weights, double* out, void* stream) {
+    using namespace cub200;
+    if (n == 0) return 0;
+    if (!masks || !weights || !out || n < 0 || n > 0x7fffffff) return CUB200_EINVAL;
+    soft_mask_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(masks, weights, out);
+    return check_launch("soft_mask_kernel");
 }
 
 extern "C" int cub200_metric_ae_split(const double* values, int64_t n_items, int64_t t_e, int64_t t_a, int apply_range, double lo,

@@ -206,7 +206,61 @@ us_myo_kernel(const float* __restrict__ landmarks, int64_t n, int flags, uint32_
     if (area_out && lane == 0) { area_out[2 * g] = a_lv; area_out[2 * g + 1] = a_myo; }
 }
 
+// Aggregation of LV + MYO sample stacks: per pixel the class counts over the T samples of an image (BG = neither bit) and
+// UncertaintyTask.sample_entropy of the one-hot stack (cu/task/uncertainty.py:107-133, C = 3): y_hat = mean over the samples
+// (counts / T, fp64), scipy.stats.entropy(y_hat, axis=0, base=3): pk = y_hat / sum(y_hat), S = sum(entr(pk)) / ln 3,
+// non-finite -> 0.  One thread per pixel; the 32 lanes of a warp read the same mask word (a broadcast).
+__global__ void __launch_bounds__(256)
+mask_class_entropy_kernel(const uint32_t* __restrict__ lv, const uint32_t* __restrict__ myo, int64_t n_img, int64_t T,
+                          double* __restrict__ entropy_out, int32_t* __restrict__ count_out, uint8_t* __restrict__ pred_out) {
+    const int64_t px = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;       // image * 65536 + row * 256 + col
+    if (px >= n_img * 65536) return;
+    const int64_t img = px >> 16;
+    const int word = (int)((px & 65535) >> 5), bit = (int)(px & 31);
+    const uint32_t* pl = lv + img * T * CUB200_MASK_WORDS + word;
+    const uint32_t* pm = myo + img * T * CUB200_MASK_WORDS + word;
+    int c1 = 0, c2 = 0;
+    for (int64_t t = 0; t < T; ++t) {
+        c1 += (pl[t * CUB200_MASK_WORDS] >> bit) & 1u;
+        c2 += (pm[t * CUB200_MASK_WORDS] >> bit) & 1u;
+    }
+    const int c0 = (int)T - c1 - c2;
+    if (count_out) {
+        count_out[(img * 3 + 0) * 65536 + (px & 65535)] = c0;
+        count_out[(img * 3 + 1) * 65536 + (px & 65535)] = c1;
+        count_out[(img * 3 + 2) * 65536 + (px & 65535)] = c2;
+    }
+    if (pred_out) {                                                           // argmax over (BG, LV, MYO), first maximum wins
+        int best = 0, cb = c0;
+        if (c1 > cb) { best = 1; cb = c1; }
+        if (c2 > cb) best = 2;
+        pred_out[px] = (uint8_t)best;
+    }
+    if (entropy_out) {
+        const double dT = (double)T;
+        const double p0 = (double)c0 / dT, p1 = (double)c1 / dT, p2 = (double)c2 / dT;
+        const double s = (p0 + p1) + p2;
+        const double q0 = p0 / s, q1 = p1 / s, q2 = p2 / s;
+        const double e0 = q0 > 0.0 ? -q0 * log(q0) : 0.0, e1 = q1 > 0.0 ? -q1 * log(q1) : 0.0, e2 = q2 > 0.0 ? -q2 * log(q2) : 0.0;
+        double e = ((e0 + e1) + e2) / log(3.0);
+        if (!isfinite(e)) e = 0.0;
+        entropy_out[px] = e;
+    }
+}
+
 }  // namespace cub200
+
+extern "C" int cub200_mask_class_entropy(const uint32_t* lv_masks, const uint32_t* myo_masks, int64_t n_img, int64_t n_samples,
+                                         double* entropy_out, int32_t* count_out, uint8_t* pred_out, void* stream) {
+    using namespace cub200;
+    if (n_img == 0) return 0;
+    if (!lv_masks || !myo_masks || n_img < 0 || n_samples < 1 || n_samples > 0x3fffffff || (!entropy_out && !count_out && !pred_out))
+        return CUB200_EINVAL;
+    const int64_t n = n_img * 65536;
+    mask_class_entropy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lv_masks, myo_masks, n_img, n_samples,
+                                                                                            entropy_out, count_out, pred_out);
+    return check_launch("mask_class_entropy_kernel");
+}
 
 extern "C" int cub200_us_myo_masks(const float* landmarks, int64_t n, int flags, uint32_t* lv_out, uint32_t* myo_out,
                                    int32_t* area_out, void* stream) {

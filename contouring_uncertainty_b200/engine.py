@@ -280,6 +280,31 @@ def us_myo_masks(landmarks: torch.Tensor, reconstruction_type: str = "spline"):
     return lv, myo, area
 
 
+def mask_class_entropy(lv_masks: torch.Tensor, myo_masks: torch.Tensor, want_counts: bool = False, want_pred: bool = False):
+    """sample_entropy of LV + MYO one-hot sample stacks (cu/task/uncertainty.py:107-133, base 3) from the bit-packed masks of
+    ``us_myo_masks``: lv_masks, myo_masks (N, T, 2048) int32 -> entropy (N,256,256) fp64 [, counts (N,3,256,256) int32]
+    [, pred (N,256,256) uint8 = argmax of the class counts]."""
+    lv_masks = nat.require_cuda(lv_masks, torch.int32, "lv_masks")
+    myo_masks = nat.require_cuda(myo_masks, torch.int32, "myo_masks")
+    if lv_masks.dim() != 3 or lv_masks.shape[2] != MASK_WORDS or lv_masks.shape != myo_masks.shape or lv_masks.shape[1] < 1:
+        raise ValueError(f"lv_masks / myo_masks must both be (N, T >= 1, {MASK_WORDS}) int32")
+    n, t = int(lv_masks.shape[0]), int(lv_masks.shape[1])
+    dev = lv_masks.device
+    ent = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
+    cnt = torch.empty((n, 3, HW, HW), dtype=torch.int32, device=dev) if want_counts else None
+    pred = torch.empty((n, HW, HW), dtype=torch.uint8, device=dev) if want_pred else None
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_mask_class_entropy(nat.ptr(lv_masks), nat.ptr(myo_masks), n, t, nat.ptr(ent), nat.ptr(cnt), nat.ptr(pred),
+                                                 nat.stream_ptr(dev))
+    nat.check(rc, "cub200_mask_class_entropy")
+    out = (ent,)
+    if want_counts:
+        out += (cnt,)
+    if want_pred:
+        out += (pred,)
+    return out if len(out) > 1 else ent
+
+
 def sample_entropy(samples: torch.Tensor) -> torch.Tensor:
     """UncertaintyTask.sample_entropy (cu/task/uncertainty.py:107-133) for probabilities of any class count:
     samples (N, T, C, H, W) fp32 with 1 <= C <= 8 -> (N, H, W) fp32 (C == 1: bits; else base C)."""
@@ -353,6 +378,35 @@ def maps_from_count(count: np.ndarray, n_samples: int) -> dict:
     e[~np.isfinite(e)] = 0.0
     idx = np.asarray(count).astype(np.int64)
     return dict(mean=p[idx], entropy=e[np.clip(idx, 0, T)], pred=(2 * idx > T).astype(np.uint8), variance=(p * (1.0 - p))[idx])
+
+
+def _gaussian_taps(sigma: float = 5.0, truncate: float = 1.0) -> np.ndarray:
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius), centre tap first."""
+    radius = int(truncate * float(sigma) + 0.5)
+    xs = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * xs ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:])
+
+
+def soft_masks(masks: torch.Tensor) -> torch.Tensor:
+    """convert_to_mask(soft_mask=True) (cu/task/regression/contour_uncertainty.py:44-49): bit-packed masks (..., 2048) int32 ->
+    (..., 256, 256) fp64 = min-max normalised Gaussian blur (sigma 5, truncate 1, edges repeated)."""
+    masks = nat.require_cuda(masks, torch.int32, "masks")
+    if masks.shape[-1] != MASK_WORDS:
+        raise ValueError(f"masks must be (..., {MASK_WORDS}) int32 bit-packed")
+    lead = tuple(masks.shape[:-1])
+    n = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    dev = masks.device
+    taps = _gaussian_taps()
+    if len(taps) != 6:
+        raise RuntimeError("the kernel is built for 11 taps")
+    w = torch.from_numpy(taps).to(dev)
+    out = torch.empty(lead + (HW, HW), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_soft_masks(nat.ptr(masks), n, nat.ptr(w), nat.ptr(out), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_soft_masks")
+    return out
 
 
 def metric_ae_split(values: torch.Tensor, value_range=None, return_values: bool = False):

@@ -29,10 +29,43 @@ class PosteriorShapeModelSampler(Sampler):
     def factor(self, mu: torch.Tensor, cov: torch.Tensor) -> torch.Tensor:
         return E.psm_factor(self.model, mu, cov)
 
+    def _call_with_alpha(self, m, c, alpha, n, z, seed):
+        """psm.py:231-237: with ``alpha`` the three initial points (0, 10, 20) are drawn from the bivariate skew-normal
+        ``rvs_fast(mu_j, cov_j, alpha_j * [1, -1])``; everything after them is the Gaussian hierarchy.  The sampler is affine in
+        the initial points' deviations, so the skew draws are turned into the equivalent first six normals
+        z_k = chol(cov_k)^-1 (s_k - mu_k) and the rest runs through the same factor.  ``z`` = (z3 (N,n,3,3), z2 (N,n,14,2))
+        replays the draws (rvs_fast normals, then the 14 level draws); otherwise Philox / torch's device generator."""
+        N = m.shape[0]
+        a = torch.as_tensor(alpha, dtype=torch.float32).to(self.device).reshape(N, E.K, 2) * torch.tensor([1.0, -1.0], device=self.device)
+        z3 = z2 = None
+        if z is not None:
+            z3 = torch.as_tensor(z[0], dtype=torch.float32).to(self.device).reshape(N, n, 3, 3)
+            z2 = torch.as_tensor(z[1], dtype=torch.float32).to(self.device).reshape(N, n, 28)
+        zfull = torch.empty((N, n, E.Z_PSM), dtype=torch.float32, device=self.device)
+        if z2 is None:
+            g = torch.Generator(device=self.device).manual_seed(int(seed) + 0x5EED)
+            zfull[:, :, 6:] = torch.randn((N, n, 28), generator=g, device=self.device)
+        else:
+            zfull[:, :, 6:] = z2
+        for i in range(N):
+            for d, k in enumerate(self.initial_points):
+                s = E.skew_rvs_fast(m[i, k].contiguous(), c[i, k].contiguous(), a[i, k].contiguous(), n,
+                                    z=None if z3 is None else z3[i, :, d].contiguous(), seed=seed + 7919 * (3 * i + d))
+                l00 = torch.sqrt(c[i, k, 0, 0]); l10 = c[i, k, 1, 0] / l00; l11 = torch.sqrt(c[i, k, 1, 1] - l10 * l10)
+                dx, dy = s[:, 0] - m[i, k, 0], s[:, 1] - m[i, k, 1]
+                zfull[i, :, 2 * d] = dx / l00
+                zfull[i, :, 2 * d + 1] = (dy - l10 * (dx / l00)) / l11
+        return E.sample_contours(m, self.factor(m, c), n, z=zfull.contiguous())
+
     def __call__(self, mu: torch.Tensor, cov: torch.Tensor, alpha=None, n: int = 1, debug_img=None, z=None,
                  seed: int = 0) -> torch.Tensor:
         if alpha is not None:
-            raise NotImplementedError("alpha (skew-normal initial points) belongs to the dsnt-skew row")
+            out_dev = mu.device
+            batched = mu.dim() == 3
+            m = mu.to(self.device, torch.float32).reshape(-1, E.K, 2).contiguous()
+            c = cov.to(self.device, torch.float32).reshape(-1, E.K, 2, 2).contiguous()
+            s = self._call_with_alpha(m, c, alpha, n, z, seed)
+            return (s if batched else s[0]).to(out_dev)
         out_dev = mu.device
         batched = mu.dim() == 3
         m = mu.to(self.device, torch.float32).reshape(-1, E.K, 2).contiguous()

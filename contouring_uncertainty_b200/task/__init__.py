@@ -26,6 +26,12 @@ def sample_entropy(samples) -> np.ndarray:
     s = np.asarray(samples)
     if s.ndim == 5:
         s = s.reshape((-1,) + s.shape[2:])
+    if s.shape[1] == 3 and tuple(s.shape[2:]) == (E.HW, E.HW) and np.isin(s, (0, 1)).all() and (s.sum(1) == 1).all():
+        # one-hot BG / LV / MYO stack (labels with Label.MYO): exact class counts, fp64 entropy in base 3
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pack = lambda m: torch.from_numpy(np.ascontiguousarray(np.packbits(m.astype(bool), axis=-1, bitorder="little")).view(np.int32)
+                                          .reshape(1, s.shape[0], E.MASK_WORDS)).to(dev)
+        return E.mask_class_entropy(pack(s[:, 1]), pack(s[:, 2]))[0].cpu().numpy()
     if s.shape[1] != 1 or not np.isin(s, (0, 1)).all():
         # probabilities / several classes: the general kernel (fp32 like the reference's tensors)
         dev = torch.device("cuda", torch.cuda.current_device())

@@ -12,11 +12,33 @@ from .. import add_point_and_instant_uncertainty
 from ..uncertainty import UncertaintyTask
 
 
+def convert_to_mask_myo(mu, image_shape, contour_samples=None):
+    """contour_uncertainty.py:26-57 when Label.MYO is among the labels: mu (N,42,2) = 21 endocardial + 21 epicardial
+    landmarks, contour_samples (N,T_e,T_a,42,2) -> (pred (N,H,W) int64 class map, pred_samples (N,T_e,T_a,3,H,W) int64 one-hot
+    BG / LV / MYO | None), as USContourToMask gives them (cu/data/camus/utils.py:47-98)."""
+    if tuple(image_shape[-2:]) != (E.HW, E.HW):
+        raise ValueError("only 256x256 frames are supported")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).to(dev).contiguous()
+
+    def one_hot(lm):
+        lv, myo, _ = E.us_myo_masks(lm.reshape(-1, 2 * E.K, 2))
+        lv, myo = E.unpack_masks(lv).to(torch.int64), E.unpack_masks(myo).to(torch.int64)
+        return torch.stack([((lv + myo) == 0).to(torch.int64), lv, myo], dim=1)           # (M, 3, H, W)
+
+    n = image_shape[0]
+    pred = one_hot(t(mu).reshape(n, 2 * E.K, 2)).argmax(1).cpu().numpy()
+    pred_samples = None
+    if contour_samples is not None:
+        cs = t(contour_samples)
+        pred_samples = one_hot(cs).cpu().numpy().reshape(tuple(cs.shape[:3]) + (3, E.HW, E.HW))
+    return pred, pred_samples
+
+
 def convert_to_mask(mu, image_shape, contour_samples=None, soft_mask: bool = False):
     """contour_uncertainty.py:26-57 for LV labels: mu (N,K,2), contour_samples (N,T_e,T_a,K,2) ->
-    (pred (N,H,W) int64, pred_samples (N,T_e,T_a,1,H,W) int64 | None).  One rasteriser launch for everything."""
-    if soft_mask:
-        raise NotImplementedError("soft_mask (skimage.filters.gaussian) is off by default and not provided")
+    (pred (N,H,W) int64, pred_samples (N,T_e,T_a,1,H,W) int64 [fp64 soft masks with ``soft_mask``] | None).  One rasteriser
+    launch for everything."""
     if tuple(image_shape[-2:]) != (E.HW, E.HW):
         raise ValueError("only 256x256 frames are supported")
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -28,7 +50,10 @@ def convert_to_mask(mu, image_shape, contour_samples=None, soft_mask: bool = Fal
     if contour_samples is not None:
         cs = t(contour_samples)
         sm, _ = E.rasterize_contours(cs.reshape(-1, E.K, 2), round_landmarks=True)
-        pred_samples = E.unpack_masks(sm).cpu().numpy().astype(np.int64).reshape(tuple(cs.shape[:3]) + (1, E.HW, E.HW))
+        if soft_mask:                                         # :44-49: blurred, min-max normalised float masks
+            pred_samples = E.soft_masks(sm).cpu().numpy().reshape(tuple(cs.shape[:3]) + (1, E.HW, E.HW))
+        else:
+            pred_samples = E.unpack_masks(sm).cpu().numpy().astype(np.int64).reshape(tuple(cs.shape[:3]) + (1, E.HW, E.HW))
     return pred, pred_samples
 
 
@@ -45,7 +70,9 @@ class ContourUncertaintyTask(UncertaintyTask):
     def convert_to_mask(self, mu: np.ndarray, image_shape: Tuple, contour_samples=None, soft_mask: bool = False):
         """contour_uncertainty.py:26-57."""
         if Label.MYO in tuple(self.hparams.data_params.labels):
-            raise NotImplementedError("two-structure (LV + MYO) sample stacks: see engine.us_myo_masks")
+            if soft_mask:
+                raise NotImplementedError("soft_mask is not provided")
+            return convert_to_mask_myo(mu, image_shape, contour_samples)
         return convert_to_mask(mu, image_shape, contour_samples, soft_mask)
 
     def _fetch_functors(self):

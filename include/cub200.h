@@ -175,6 +175,17 @@ int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, 
                          double* variance_out, uint16_t* count16_out, void* stream);
 
 /*
+ * Soft masks of convert_to_mask(soft_mask=True): Gaussian blur (sigma 5, truncate 1: 11 taps, edges repeated) of every
+ * bit-packed mask, then (m - min) / (max - min).
+ *   replaces  skimage.filters.gaussian(mask, sigma=(5,5), truncate=1) + the min-max normalisation
+ *             cu/task/regression/contour_uncertainty.py:44-49   (scikit-image is absent from the build image: restated as the
+ *             scipy.ndimage.gaussian_filter call it wraps -- parity unpinned for that third-party function)
+ *   masks (n, 2048) u32; weights (6) fp64: the normalised Gaussian taps w[0] (centre) .. w[5], formed on the host as scipy
+ *   forms them; out (n, 256, 256) fp64.
+ */
+int cub200_soft_masks(const uint32_t* masks, int64_t n, const double* weights, double* out, void* stream);
+
+/*
  * Aleatoric / epistemic split of Monte-Carlo metric distributions, batched: one result per item (instant, view or patient).
  *   replaces  aleatoric_epistemic_uncertainty            cu/results/clinical/utils.py:3-18
  *             the sample_reject rule of FAC / GLS / Volume.compute   cu/results/clinical/view.py:52-53,165-166,
@@ -493,6 +504,17 @@ int cub200_rasterize_contours_generic(const void* contours, int is_f64, int64_t 
  *   lv_out / myo_out (n, 2048) u32 bit-packed: seg_map[LV] and seg_map[MYO] = clip(myo_mask - lv_mask, 0, 1);
  *   area_out (n, 2) i32 = their pixel counts.  Any of the three may be NULL (not all).
  */
+/*
+ * Aggregation of LV + MYO sample stacks (three classes: BG = neither mask, LV, MYO).
+ *   replaces  UncertaintyTask.sample_entropy for one-hot (T, 3, H, W) stacks   cu/task/uncertainty.py:107-133 (base = C = 3)
+ *             the class-count / argmax bookkeeping around it                    cu/task/regression/contour_uncertainty.py:76-82
+ *   lv_masks, myo_masks (n_img, n_samples, 2048) u32 bit-packed (cub200_us_myo_masks)
+ *   entropy_out optional (n_img, 256, 256) fp64; count_out optional (n_img, 3, 256, 256) int32 class counts;
+ *   pred_out optional (n_img, 256, 256) uint8 = argmax of the counts (first maximum wins, like numpy).
+ */
+int cub200_mask_class_entropy(const uint32_t* lv_masks, const uint32_t* myo_masks, int64_t n_img, int64_t n_samples,
+                              double* entropy_out, int32_t* count_out, uint8_t* pred_out, void* stream);
+
 int cub200_us_myo_masks(const float* landmarks, int64_t n, int flags, uint32_t* lv_out, uint32_t* myo_out, int32_t* area_out,
                         void* stream);
 

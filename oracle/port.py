@@ -29,6 +29,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 from scipy import interpolate
+import scipy.ndimage
 from scipy.ndimage import binary_fill_holes
 import scipy.stats
 
@@ -210,6 +211,15 @@ def convert_to_mask(contour_samples: np.ndarray, shape=(256, 256)) -> np.ndarray
     for i in range(flat.shape[0]):
         out[i] = us_contour_to_mask(flat[i], shape)
     return out.reshape(lead + tuple(shape))
+
+
+def soft_mask(mask: np.ndarray) -> np.ndarray:
+    """The soft_mask branch of convert_to_mask (cu/task/regression/contour_uncertainty.py:44-49):
+    skimage.filters.gaussian(mask, sigma=(5, 5), truncate=1) then min-max normalisation.  scikit-image is absent: restated as
+    the scipy call it wraps (ndimage.gaussian_filter, mode='nearest') on the 0/1 float mask -- skimage first rescales an
+    integer image by a constant, which the min-max normalisation removes again.  PARITY UNPINNED for that function."""
+    m = scipy.ndimage.gaussian_filter(np.asarray(mask, dtype=np.float64), sigma=(5, 5), truncate=1, mode="nearest")
+    return (m - np.min(m)) / (np.max(m) - np.min(m))
 
 
 def sample_entropy(samples: np.ndarray) -> np.ndarray:

@@ -124,6 +124,48 @@ def golden_psm():
     print("psm.npz", out.shape, "max |s-mu|", np.abs(out - mus[:, None]).max())
 
 
+def golden_psm_alpha():
+    """PosteriorShapeModelSampler.__call__ WITH alpha (psm.py:231-237, 385-419): the three initial points come from
+    BivariateSkewNormal.rvs_fast(mu_j, cov_j, alpha_j * [1, -1]) (one (1,3) normal draw each), the 14 level points from the
+    Gaussian hierarchy ((1,2) draws).  fp32 as the reference runs it and the same code in fp64."""
+    from contour_uncertainty.sampler.posterior_shape_model.psm import PosteriorShapeModelSampler
+
+    rng = np.random.default_rng(36)
+    n_img, n_s = 3, 8
+    mus, covs = synth.point_distributions(n_img, seed=37)
+    alphas = synth.skew_alphas(n_img, seed=38)
+    z3 = rng.standard_normal((n_img, n_s, 3, 3)).astype(np.float32)
+    z2 = rng.standard_normal((n_img, n_s, 14, 2)).astype(np.float32)
+    outs = {}
+    for mode in ("f32", "f64"):
+        dt = np.float64 if mode == "f64" else np.float32
+        if mode == "f64":
+            torch.set_default_dtype(torch.float64)
+        try:
+            smp = PosteriorShapeModelSampler(PSM_PATH)
+            if mode == "f64":
+                for a in ("mean", "scale", "X_train", "X_val", "mu", "Q"):
+                    setattr(smp, a, getattr(smp, a).double())
+            res = np.zeros((n_img, n_s, 21, 2))
+            for i in range(n_img):
+                draws = []
+                for s_ in range(n_s):
+                    draws += [z3[i, s_, d][None].astype(dt) for d in range(3)] + [z2[i, s_, d][None].astype(dt) for d in range(14)]
+                with _refstub.replay_standard_normal(draws) as log, torch.no_grad():
+                    t = lambda a: torch.from_numpy(a.astype(dt))
+                    r = smp(t(mus[i]), t(covs[i]), t(alphas[i]), n=n_s)
+                assert len(log) == 17 * n_s and log[0] == (1, 3) and log[3] == (1, 2), log[:4]
+                res[i] = r.detach().numpy()
+            outs[mode] = res
+        finally:
+            torch.set_default_dtype(torch.float32)
+    print("psm_alpha fp32-vs-fp64 max diff (px)", np.abs(outs["f32"] - outs["f64"]).max())
+    np.savez_compressed(os.path.join(HERE, "psm_alpha.npz"), mu=mus, cov=covs, alpha=alphas, z3=z3, z2=z2,
+                        samples=outs["f32"].astype(np.float32), samples_f64=outs["f64"])
+    print("psm_alpha.npz", outs["f64"].shape)
+
+
+
 def golden_seq():
     """SequencePSMSampler.__call__ with replayed draws and first-instant bits (fp32 and fp64 runs)."""
     import random
@@ -963,6 +1005,29 @@ def golden_metrics():
     print("metrics.npz", {k: v.tolist() for k, v in out.items() if k.startswith(("fac_2CH", "vol_EF")) and v.size < 8})
 
 
+
+def golden_myo_task():
+    """Labels with Label.MYO: ContourUncertaintyTask.convert_to_mask (cu/task/regression/contour_uncertainty.py:26-57) on
+    42-landmark contour samples -> one-hot (N,T_e,T_a,3,H,W) stacks, then predict_step's per-image sample_entropy (base 3,
+    uncertainty.py:107-133) and the argmax of :81-82, executed as they are.  skimage.draw.polygon is the restated one."""
+    from contour_uncertainty.task.regression.contour_uncertainty import ContourUncertaintyTask
+    from vital.data.camus.config import Label
+
+    n, te, ta = 2, 2, 5
+    task = _bare_task(ContourUncertaintyTask)
+    task.hparams.data_params.labels = [Label.BG, Label.LV, Label.MYO]
+    mu = synth.endo_epi_landmarks(n, seed=91).astype(np.float32)
+    rng = np.random.default_rng(92)
+    cs = (mu[:, None, None] + rng.normal(0, 2.0, (n, te, ta, 42, 2)) + rng.normal(0, 2.0, (n, te, ta, 1, 2))).astype(np.float32)
+    # image_shape[1:] is what the reference reshapes the stack to (:52): it only works with a 3-channel "image" shape
+    pred, ps = task.convert_to_mask(mu, (n, 3, 256, 256), cs)
+    ent = np.array([task.sample_entropy(ps[i].astype(float)) for i in range(n)])
+    np.savez_compressed(os.path.join(HERE, "myo_task.npz"), mu=mu, contour_samples=cs, pred=pred.astype(np.uint8),
+                        pred_samples_argmax=ps.argmax(3).astype(np.uint8), entropy=ent,
+                        counts=ps.sum((1, 2)).astype(np.int32))
+    print("myo_task.npz", ps.shape, ent.dtype, float(ent.max()), "class px", [(pred == c).sum() for c in range(3)])
+
+
 from class_entropy_inputs import class_entropy_inputs  # noqa: E402
 
 
@@ -978,6 +1043,6 @@ def golden_class_entropy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics", "myo_task", "psm_alpha"]
     for w in which:
         globals()["golden_" + w]()

@@ -407,3 +407,36 @@ def test_skew_pipeline_with_epistemic_passes():
     want_mu, want_cov = port.aleatoric_epistemic_moments(mu.cpu().numpy(), cov.cpu().numpy())
     assert np.allclose(br.mu, want_mu, atol=1e-4) and np.allclose(br.cov, want_cov, rtol=1e-4, atol=1e-4)
     assert np.allclose(br.alpha, al.mean(1).cpu().numpy())
+
+
+def test_psm_sampler_with_alpha_soft_masks_and_small_api_holes():
+    """PosteriorShapeModelSampler(alpha=...) (psm.py:231-237) against the executed reference with replayed draws;
+    convert_to_mask(soft_mask=True) against the oracle (scipy restatement of skimage.filters.gaussian: parity unpinned)."""
+    from contouring_uncertainty_b200 import engine as E
+    from contouring_uncertainty_b200.sampler.posterior_shape_model.psm import PosteriorShapeModelSampler
+    from contouring_uncertainty_b200.task.regression.contour_uncertainty import convert_to_mask
+
+    g = np.load(os.path.join(G, "psm_alpha.npz"))
+    smp = PosteriorShapeModelSampler()
+    t = torch.from_numpy
+    n_img, n_s = g["samples"].shape[:2]
+    out = smp(t(g["mu"]), t(g["cov"]), t(g["alpha"]), n=n_s, z=(g["z3"], g["z2"]))
+    assert out.shape == (n_img, n_s, 21, 2)
+    assert np.abs(out.numpy() - g["samples_f64"]).max() < 1e-3          # vs the reference executed in fp64
+    assert np.abs(out.numpy() - g["samples"]).max() < 6e-2              # vs its fp32 run (its own noise: 1.8e-2 px)
+    one = smp(t(g["mu"][0]), t(g["cov"][0]), t(g["alpha"][0]), n=4, seed=3)    # single image, generated draws
+    assert one.shape == (4, 21, 2) and torch.isfinite(one).all()
+    # skewness moves the mean of the initial points: E[s] - mu = sqrt(2/pi) delta, delta = cov a / sqrt(1 + a^T cov a), a = alpha * [1, -1]
+    big = smp(t(g["mu"][0]), t(g["cov"][0]), t(g["alpha"][0]), n=20000, seed=5).numpy()
+    a = g["alpha"][0, 10].astype(np.float64) * np.array([1.0, -1.0]); c = g["cov"][0, 10].astype(np.float64)
+    want = np.sqrt(2 / np.pi) * c @ a / np.sqrt(1 + a @ c @ a)
+    assert np.abs(big[:, 10].mean(0) - g["mu"][0, 10] - want).max() < 0.15
+    # soft masks
+    r = np.load(os.path.join(G, "raster.npz"))
+    c4 = r["contours"][:4]
+    pred, ps = convert_to_mask(c4[:1], (1, 1, 256, 256), c4.reshape(1, 1, 4, 21, 2), soft_mask=True)
+    assert ps.shape == (1, 1, 4, 1, 256, 256) and ps.dtype == np.float64
+    for k in range(4):
+        want = port.soft_mask(port.us_contour_to_mask(c4[k]))
+        assert np.abs(ps[0, 0, k, 0] - want).max() <= 1e-12
+        assert ps[0, 0, k, 0].min() == 0.0 and ps[0, 0, k, 0].max() == 1.0
