@@ -672,6 +672,12 @@ def run_ours(args):
         assert torch.equal(gathered[rank, -1], mine), "exchange: own block of the last step"
         assert int(totals[-1, 0]) == int(gathered[:, -1].sum()), "exchange: dataset sum"
     clk = clocks.stop() if (rank == 0 and not args.no_clocks) else None
+    if args.device_only:
+        if rank == 0:
+            print(f"device-only run: {ms_total / args.steps:.4f} ms per step, {gpu_launches} library launches in the timed region")
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # per-phase device times of the same step (allocating per-op API, an event between the phases)
     n_ev = max(1, min(args.steps, 20 if cfg_id in (1, 2) else 3))
@@ -778,6 +784,7 @@ def main():
     ap.add_argument("--exchange-every", type=int, default=0, help="steps per all_gather of the metric distributions (0 = one per run)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (profiling runs)")
+    ap.add_argument("--device-only", action="store_true", help="profiling runs: only the device-resident steps (no per-phase, e2e, CPU or parity legs; no JSON line)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = {1: 200, 2: 100, 3: 10, 4: 3, 5: 10}[args.config] if args.impl == "ours" else 1

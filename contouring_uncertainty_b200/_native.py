@@ -29,7 +29,8 @@ SIGNATURES = {
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
     "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
-    "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "cub200_count_tables": [_i64, _vp, _vp],
     "cub200_soft_masks": [_vp, _i64, _vp, _vp, _vp],
     "cub200_metric_ae_split": [_vp, _i64, _i64, _i64, _i32, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_fac_from_areas": [_vp, _vp, _i64, _vp, _vp],

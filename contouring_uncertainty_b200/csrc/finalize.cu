@@ -27,69 +27,82 @@ __global__ void entropy_lut_kernel(double* __restrict__ lut, int64_t T) {
     lut[2 * (T + 1) + c] = p * (1.0 - p);                  // Bernoulli variance of the samples
 }
 
+// One warp per FM_ROWS consecutive rows: all the row loads are issued before the first scan, so a warp has FM_ROWS KiB in
+// flight instead of one (the kernel is latency-bound otherwise: 25 B / pixel, no reuse).
+constexpr int FM_ROWS = 4;
 __global__ void __launch_bounds__(256)
 finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T, int32_t* __restrict__ count_out,
                      double* __restrict__ mean_out, double* __restrict__ entropy_out, uint8_t* __restrict__ pred_out,
                      const double* __restrict__ lut, double* __restrict__ variance_out, uint16_t* __restrict__ count16_out) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int4* d4 = reinterpret_cast<const int4*>(diff + row * 256) + 2 * lane;
-    const int4 a = d4[0], b = d4[1];
-    int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int64_t row0 = (blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5)) * FM_ROWS;
+    if (row0 >= n_rows) return;
+    int4 va[FM_ROWS], vb[FM_ROWS];
 #pragma unroll
-    for (int j = 1; j < 8; ++j) c[j] += c[j - 1];
-    int incl = c[7];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
+    for (int q = 0; q < FM_ROWS; ++q) {
+        const int64_t row = min(row0 + q, n_rows - 1);
+        const int4* d4 = reinterpret_cast<const int4*>(diff + row * 256) + 2 * lane;
+        va[q] = d4[0]; vb[q] = d4[1];
     }
-    const int excl = incl - c[7];
+    const double* lm = lut + (T + 1);
+    const double* lv = lut + 2 * (T + 1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) c[j] += excl;
-    const int64_t base = row * 256 + 8 * lane;
-    if (count_out) {
-        int4* o = reinterpret_cast<int4*>(count_out + base);
-        o[0] = make_int4(c[0], c[1], c[2], c[3]);
-        o[1] = make_int4(c[4], c[5], c[6], c[7]);
-    }
-    if (count16_out) {                                   // T <= 65535 (checked by the caller): 2 B / pixel instead of 4
-        uint32_t w[4];
+    for (int q = 0; q < FM_ROWS; ++q) {
+        const int64_t row = row0 + q;
+        if (row >= n_rows) break;
+        int c[8] = {va[q].x, va[q].y, va[q].z, va[q].w, vb[q].x, vb[q].y, vb[q].z, vb[q].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = ((uint32_t)c[2 * j] & 0xffffu) | ((uint32_t)c[2 * j + 1] << 16);
-        reinterpret_cast<uint4*>(count16_out + base)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    // the fp64 maps are functions of the count: three (T+1)-entry tables (entropy | mean | variance), L1-resident --
-    // a table read instead of an fp64 division per pixel
-    if (mean_out || entropy_out || variance_out) {
-        int cc[8];
+        for (int j = 1; j < 8; ++j) c[j] += c[j - 1];
+        int incl = c[7];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cc[j] = min(max(c[j], 0), (int)T);
-        const double* lm = lut + (T + 1);
-        const double* lv = lut + 2 * (T + 1);
-        if (variance_out) {                              // p (1 - p), p = count / T
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(variance_out + base)[j >> 1] = make_double2(lv[cc[j]], lv[cc[j + 1]]);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
         }
-        if (mean_out) {
+        const int excl = incl - c[7];
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(mean_out + base)[j >> 1] = make_double2(lm[cc[j]], lm[cc[j + 1]]);
+        for (int j = 0; j < 8; ++j) c[j] += excl;
+        const int64_t base = row * 256 + 8 * lane;
+        if (count_out) {
+            int4* o = reinterpret_cast<int4*>(count_out + base);
+            o[0] = make_int4(c[0], c[1], c[2], c[3]);
+            o[1] = make_int4(c[4], c[5], c[6], c[7]);
         }
-        if (entropy_out) {
+        if (count16_out) {                                   // T <= 65535 (checked by the caller): 2 B / pixel instead of 4
+            uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(entropy_out + base)[j >> 1] = make_double2(lut[cc[j]], lut[cc[j + 1]]);
+            for (int j = 0; j < 4; ++j) w[j] = ((uint32_t)c[2 * j] & 0xffffu) | ((uint32_t)c[2 * j + 1] << 16);
+            reinterpret_cast<uint4*>(count16_out + base)[0] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-    }
-    if (pred_out) {
-        // round-half-even(count / T): 1 iff count/T > 0.5 (exactly 0.5 rounds to 0)
-        uint32_t lo = 0, hi = 0;
+        // the fp64 maps are functions of the count: three (T+1)-entry tables (entropy | mean | variance), L1-resident --
+        // a table read instead of an fp64 division per pixel
+        if (mean_out || entropy_out || variance_out) {
+            int cc[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            lo |= (uint32_t)(2 * (int64_t)c[j] > T) << (8 * j);
-            hi |= (uint32_t)(2 * (int64_t)c[j + 4] > T) << (8 * j);
+            for (int j = 0; j < 8; ++j) cc[j] = min(max(c[j], 0), (int)T);
+            if (variance_out) {                              // p (1 - p), p = count / T
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(variance_out + base)[j >> 1] = make_double2(lv[cc[j]], lv[cc[j + 1]]);
+            }
+            if (mean_out) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(mean_out + base)[j >> 1] = make_double2(lm[cc[j]], lm[cc[j + 1]]);
+            }
+            if (entropy_out) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(entropy_out + base)[j >> 1] = make_double2(lut[cc[j]], lut[cc[j + 1]]);
+            }
         }
-        reinterpret_cast<uint2*>(pred_out + base)[0] = make_uint2(lo, hi);
+        if (pred_out) {
+            // round-half-even(count / T): 1 iff count/T > 0.5 (exactly 0.5 rounds to 0)
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                lo |= (uint32_t)(2 * (int64_t)c[j] > T) << (8 * j);
+                hi |= (uint32_t)(2 * (int64_t)c[j + 4] > T) << (8 * j);
+            }
+            reinterpret_cast<uint2*>(pred_out + base)[0] = make_uint2(lo, hi);
+        }
     }
 }
 
@@ -279,8 +292,15 @@ extern "C" int cub200_sample_moments(const float* contours, int64_t n_img, int64
     return check_launch("sample_moments_kernel");
 }
 
+extern "C" int cub200_count_tables(int64_t n_samples, double* lut_ws, void* stream) {
+    using namespace cub200;
+    if (!lut_ws || n_samples < 1 || n_samples > 0x3fffffff) return CUB200_EINVAL;
+    entropy_lut_kernel<<<(unsigned)((n_samples + 1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lut_ws, n_samples);
+    return check_launch("entropy_lut_kernel");
+}
+
 extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
-                                    double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,
+                                    double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws, int lut_ready,
                                     double* variance_out, uint16_t* count16_out, void* stream) {
     using namespace cub200;
     if (!diff || n_img < 0 || n_samples < 1 || n_samples > 0x3fffffff) return CUB200_EINVAL;
@@ -288,13 +308,13 @@ extern "C" int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t 
     if ((entropy_out || mean_out || variance_out) && !lut_ws) return CUB200_EINVAL;
     if (n_img == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (entropy_out || mean_out || variance_out) {
+    if ((entropy_out || mean_out || variance_out) && !lut_ready) {
         entropy_lut_kernel<<<(unsigned)((n_samples + 1 + 255) / 256), 256, 0, st>>>(lut_ws, n_samples);
         int rc = check_launch("entropy_lut_kernel");
         if (rc) return rc;
     }
     const int64_t rows = n_img * 256;
-    finalize_maps_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(diff, rows, n_samples, count_out, mean_out,
+    finalize_maps_kernel<<<(unsigned)((rows + 8 * FM_ROWS - 1) / (8 * FM_ROWS)), 256, 0, st>>>(diff, rows, n_samples, count_out, mean_out,
                                                                     entropy_out, pred_out, lut_ws, variance_out, count16_out);
     return check_launch("finalize_maps_kernel");
 }

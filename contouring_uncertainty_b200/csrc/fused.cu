@@ -381,8 +381,10 @@ __device__ __forceinline__ void philox_normals4(uint64_t gc, int q, uint64_t see
 template <int ZD>
 __global__ void __launch_bounds__(SC_THREADS)
 sample_contours_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim, const float* __restrict__ z,
-                       uint64_t seed, uint64_t g_offset, int64_t n_samples, int chunks, float* __restrict__ contours_out) {
+                       uint64_t seed, uint64_t g_offset, int64_t n_samples, int chunks, float* __restrict__ contours_out,
+                       uint32_t* __restrict__ queue) {
     __shared__ __align__(16) float a_s[CUB200_ZMAX * CUB200_P];
+    if (queue && blockIdx.x == 0 && threadIdx.x == 0) queue[0] = 0u;   // the rasteriser that follows starts with an empty queue
     __shared__ float out_s[SC_THREADS * SC_PAD];
     const int64_t img = blockIdx.x / chunks;
     const int64_t s0 = (int64_t)(blockIdx.x % chunks) * SC_THREADS;
@@ -434,8 +436,10 @@ sample_contours_kernel(const float* __restrict__ mu, const float* __restrict__ a
 constexpr int SW_WARPS = 8;
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sample_contours_warp_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim, const float* __restrict__ z,
-                            uint64_t seed, uint64_t g_offset, int64_t n_img, int64_t n_samples, float* __restrict__ contours_out) {
+                            uint64_t seed, uint64_t g_offset, int64_t n_img, int64_t n_samples, float* __restrict__ contours_out,
+                            uint32_t* __restrict__ queue) {
     __shared__ float z_s[SW_WARPS][CUB200_ZMAX + 2];
+    if (queue && blockIdx.x == 0 && threadIdx.x == 0) queue[0] = 0u;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     float* zw = z_s[warp];
     const int64_t total = n_img * n_samples;
@@ -591,26 +595,26 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
     const int64_t total = n_img * n_samples;
     if (total == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool raster = diff || area_out || masks_out;
+    if (raster && !workspace) return CUB200_EINVAL;
+    uint32_t* queue = raster ? (uint32_t*)workspace : nullptr;
     if (n_samples < SC_THREADS / 2) {
         const int64_t need = (total + SW_WARPS - 1) / SW_WARPS;
         const int grid = (int)(need < 148 * 16 ? need : 148 * 16);
-        sample_contours_warp_kernel<<<grid, SW_WARPS * 32, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_img, n_samples, contours_out);
+        sample_contours_warp_kernel<<<grid, SW_WARPS * 32, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_img, n_samples, contours_out, queue);
     } else {
         const int64_t chunks = (n_samples + SC_THREADS - 1) / SC_THREADS;
         if (n_img * chunks > 0x7fffffffLL) return CUB200_EINVAL;
         const unsigned grid = (unsigned)(n_img * chunks);
         if (zdim == 34)
-            sample_contours_kernel<34><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out);
+            sample_contours_kernel<34><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out, queue);
         else if (zdim == 42)
-            sample_contours_kernel<42><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out);
+            sample_contours_kernel<42><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out, queue);
         else
-            sample_contours_kernel<0><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out);
+            sample_contours_kernel<0><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out, queue);
     }
     int rc = check_launch("sample_contours_kernel");
-    if (rc || (!diff && !area_out && !masks_out)) return rc;  // sample-only call
-    if (!workspace) return CUB200_EINVAL;
-    zero_queue_kernel<<<1, 1, 0, st>>>((uint32_t*)workspace);
-    note_launches(1);
+    if (rc || !raster) return rc;                              // sample-only call
     return launch_raster(contours_out, false, total, round_landmarks, area_out, diff, masks_out, n_samples * images_per_map,
                          (uint32_t*)workspace, true, st);
 }

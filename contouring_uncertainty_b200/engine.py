@@ -353,7 +353,7 @@ def finalize_maps(diff: torch.Tensor, n_samples: int, want_count: bool = True, w
     lut = torch.empty((3 * (int(n_samples) + 1),), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         rc = nat.lib().cub200_finalize_maps(nat.ptr(diff), n, int(n_samples), nat.ptr(count), nat.ptr(mean), nat.ptr(ent),
-                                            nat.ptr(pred), nat.ptr(lut), nat.ptr(var), nat.ptr(c16), nat.stream_ptr(dev))
+                                            nat.ptr(pred), nat.ptr(lut), 0, nat.ptr(var), nat.ptr(c16), nat.stream_ptr(dev))
     nat.check(rc, "cub200_finalize_maps")
     out = (count, mean, ent, pred)
     if want_variance:
@@ -1103,7 +1103,9 @@ class Workspace:
         self.variance = torch.empty((n_img, HW, HW), dtype=f64, device=dev) if want_variance else None
         self.count16 = torch.empty((n_img, HW, HW), dtype=torch.uint16, device=dev) if want_count16 else None
         self.pred = torch.empty((n_img, HW, HW), dtype=torch.uint8, device=dev)
-        self.lut = torch.empty((3 * (t_a + 1),), dtype=f64, device=dev)
+        self.lut = torch.empty((3 * (t_a + 1),), dtype=f64, device=dev)       # entropy | mean | variance of c / t_a: filled once, here
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().cub200_count_tables(int(t_a), self.lut.data_ptr(), nat.stream_ptr(dev)), "cub200_count_tables")
         self.raster_ws = raster_workspace(n_img * t_a, dev)
         self.dsnt_ws = dsnt_workspace(n_img * K, dev)
 
@@ -1174,7 +1176,7 @@ class UncertaintyEngine:
                                                        ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, ws.raster_ws.data_ptr(), st),
                       "cub200_sample_raster_aggregate")
             nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), nat.ptr(ws.mean),
-                                             nat.ptr(ws.entropy), ws.pred.data_ptr(), ws.lut.data_ptr(), nat.ptr(ws.variance),
+                                             nat.ptr(ws.entropy), ws.pred.data_ptr(), ws.lut.data_ptr(), 1, nat.ptr(ws.variance),
                                              nat.ptr(ws.count16), st),
                       "cub200_finalize_maps")
         return ws

@@ -163,7 +163,8 @@ int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_l
  *   count_out optional (n_img,256,256) int32; mean_out optional fp64 = count/T;
  *   entropy_out optional fp64 binary entropy in bits (scipy.stats.entropy([p,1-p], base=2));
  *   pred_out optional uint8 = round-half-even(count/T)
- *   lut_ws: device workspace of 3 * (n_samples + 1) doubles (entropy, mean and variance of c/T, c = 0..T), written by the call;
+ *   lut_ws: device workspace of 3 * (n_samples + 1) doubles (entropy, mean and variance of c/T, c = 0..T), written by the call
+ *           unless lut_ready != 0 (then it must hold the tables of the same n_samples: cub200_count_tables);
  *           needed when any of mean_out / entropy_out / variance_out is given.
  *   variance_out optional fp64 = p (1 - p), p = count/T: the per-pixel variance of the 0/1 samples (the reference has no
  *                variance map; this is the Bernoulli variance its mean map implies)
@@ -171,8 +172,11 @@ int cub200_rasterize_contours_f64(const double* contours, int64_t n, int round_l
  *                so a host that wants them can fetch 2 B / pixel and index a (T+1)-entry table
  */
 int cub200_finalize_maps(const int32_t* diff, int64_t n_img, int64_t n_samples, int32_t* count_out,
-                         double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws,
+                         double* mean_out, double* entropy_out, uint8_t* pred_out, double* lut_ws, int lut_ready,
                          double* variance_out, uint16_t* count16_out, void* stream);
+/* The tables alone (one small launch): a caller that finalises many batches with the same n_samples fills lut_ws once and
+ * passes lut_ready = 1 to cub200_finalize_maps afterwards. */
+int cub200_count_tables(int64_t n_samples, double* lut_ws, void* stream);
 
 /*
  * Soft masks of convert_to_mask(soft_mask=True): Gaussian blur (sigma 5, truncate 1: 11 taps, edges repeated) of every

@@ -35,7 +35,7 @@ int main(void) {
     CK(cudaMalloc(&d_rws, (size_t)cub200_raster_workspace_bytes(n)));
     int rc = cub200_rasterize_contours(d_c, n, 1, d_m, d_area, d_diff, n, d_rws, NULL);
     if (rc) { printf("rasterize rc %d %s\n", rc, cub200_last_error()); return 3; }
-    rc = cub200_finalize_maps(d_diff, 1, n, d_count, d_mean, d_ent, d_pred, d_lut, NULL, NULL, NULL);
+    rc = cub200_finalize_maps(d_diff, 1, n, d_count, d_mean, d_ent, d_pred, d_lut, 0, NULL, NULL, NULL);
     if (rc) { printf("finalize rc %d %s\n", rc, cub200_last_error()); return 3; }
     CK(cudaDeviceSynchronize());
     int32_t h_area[3];

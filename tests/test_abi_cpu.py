@@ -64,7 +64,7 @@ def test_null_and_bad_sizes_return_einval():
     assert l.cub200_dsnt_moments(None, 1, 256, 256, 1, 1, None, None, None, None, None) == _native.EINVAL
     assert l.cub200_dsnt_moments(None, 1, 128, 128, 1, 1, None, None, None, None, None) == _native.EINVAL
     assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 0, 1, 1, 1, None, None, None, 1, None, None, None) == _native.EINVAL
-    assert l.cub200_finalize_maps(None, 1, 10, None, None, None, None, None, None, None, None) == _native.EINVAL
+    assert l.cub200_finalize_maps(None, 1, 10, None, None, None, None, None, 0, None, None, None) == _native.EINVAL
     # zero-sized work is a no-op success even without a device
     assert l.cub200_rasterize_contours(None, 0, 1, None, None, None, 0, None, None) == 0
 
