@@ -27,8 +27,10 @@ __global__ void entropy_lut_kernel(double* __restrict__ lut, int64_t T) {
     lut[2 * (T + 1) + c] = p * (1.0 - p);                  // Bernoulli variance of the samples
 }
 
-// One warp per FM_ROWS consecutive rows: all the row loads are issued before the first scan, so a warp has FM_ROWS KiB in
-// flight instead of one (the kernel is latency-bound otherwise: 25 B / pixel, no reuse).
+// One warp per FM_ROWS consecutive rows, every access fully coalesced: in chunk k (64 columns) lane l owns columns
+// 64 k + 2 l, + 1, so a warp-wide load / store covers one contiguous 256 B (int2), 512 B (double2) or 64 B (uchar2) segment.
+// All row loads are issued before the first scan (FM_ROWS KiB in flight per warp); the row prefix sum is four 64-column
+// warp scans chained by a running total.
 constexpr int FM_ROWS = 4;
 __global__ void __launch_bounds__(256)
 finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T, int32_t* __restrict__ count_out,
@@ -37,12 +39,13 @@ finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T
     const int lane = threadIdx.x & 31;
     const int64_t row0 = (blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5)) * FM_ROWS;
     if (row0 >= n_rows) return;
-    int4 va[FM_ROWS], vb[FM_ROWS];
+    int2 v[FM_ROWS][4];
 #pragma unroll
     for (int q = 0; q < FM_ROWS; ++q) {
         const int64_t row = min(row0 + q, n_rows - 1);
-        const int4* d4 = reinterpret_cast<const int4*>(diff + row * 256) + 2 * lane;
-        va[q] = d4[0]; vb[q] = d4[1];
+        const int2* d2 = reinterpret_cast<const int2*>(diff + row * 256) + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[q][k] = d2[32 * k];
     }
     const double* lm = lut + (T + 1);
     const double* lv = lut + 2 * (T + 1);
@@ -50,58 +53,29 @@ finalize_maps_kernel(const int32_t* __restrict__ diff, int64_t n_rows, int64_t T
     for (int q = 0; q < FM_ROWS; ++q) {
         const int64_t row = row0 + q;
         if (row >= n_rows) break;
-        int c[8] = {va[q].x, va[q].y, va[q].z, va[q].w, vb[q].x, vb[q].y, vb[q].z, vb[q].w};
+        int carry = 0;
 #pragma unroll
-        for (int j = 1; j < 8; ++j) c[j] += c[j - 1];
-        int incl = c[7];
+        for (int k = 0; k < 4; ++k) {
+            const int a = v[q][k].x, b = a + v[q][k].y;      // inclusive within the lane's pair
+            int incl = b;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int excl = incl - c[7];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c[j] += excl;
-        const int64_t base = row * 256 + 8 * lane;
-        if (count_out) {
-            int4* o = reinterpret_cast<int4*>(count_out + base);
-            o[0] = make_int4(c[0], c[1], c[2], c[3]);
-            o[1] = make_int4(c[4], c[5], c[6], c[7]);
-        }
-        if (count16_out) {                                   // T <= 65535 (checked by the caller): 2 B / pixel instead of 4
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = ((uint32_t)c[2 * j] & 0xffffu) | ((uint32_t)c[2 * j + 1] << 16);
-            reinterpret_cast<uint4*>(count16_out + base)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        // the fp64 maps are functions of the count: three (T+1)-entry tables (entropy | mean | variance), L1-resident --
-        // a table read instead of an fp64 division per pixel
-        if (mean_out || entropy_out || variance_out) {
-            int cc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cc[j] = min(max(c[j], 0), (int)T);
-            if (variance_out) {                              // p (1 - p), p = count / T
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(variance_out + base)[j >> 1] = make_double2(lv[cc[j]], lv[cc[j + 1]]);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
             }
-            if (mean_out) {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(mean_out + base)[j >> 1] = make_double2(lm[cc[j]], lm[cc[j + 1]]);
-            }
-            if (entropy_out) {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) reinterpret_cast<double2*>(entropy_out + base)[j >> 1] = make_double2(lut[cc[j]], lut[cc[j + 1]]);
-            }
-        }
-        if (pred_out) {
-            // round-half-even(count / T): 1 iff count/T > 0.5 (exactly 0.5 rounds to 0)
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                lo |= (uint32_t)(2 * (int64_t)c[j] > T) << (8 * j);
-                hi |= (uint32_t)(2 * (int64_t)c[j + 4] > T) << (8 * j);
-            }
-            reinterpret_cast<uint2*>(pred_out + base)[0] = make_uint2(lo, hi);
+            const int excl = incl - b + carry;
+            const int c0 = a + excl, c1 = b + excl;
+            carry += __shfl_sync(FULL, incl, 31);
+            const int64_t base = row * 256 + 64 * k + 2 * lane;
+            if (count_out) *reinterpret_cast<int2*>(count_out + base) = make_int2(c0, c1);
+            if (count16_out) *reinterpret_cast<uint32_t*>(count16_out + base) = ((uint32_t)c0 & 0xffffu) | ((uint32_t)c1 << 16);
+            // the fp64 maps are functions of the count: three (T+1)-entry tables (entropy | mean | variance), L1-resident
+            const int i0 = min(max(c0, 0), (int)T), i1 = min(max(c1, 0), (int)T);
+            if (variance_out) *reinterpret_cast<double2*>(variance_out + base) = make_double2(lv[i0], lv[i1]);
+            if (mean_out) *reinterpret_cast<double2*>(mean_out + base) = make_double2(lm[i0], lm[i1]);
+            if (entropy_out) *reinterpret_cast<double2*>(entropy_out + base) = make_double2(lut[i0], lut[i1]);
+            // round-half-even(count / T): 1 iff count / T > 0.5 (exactly 0.5 rounds to 0)
+            if (pred_out) *reinterpret_cast<uchar2*>(pred_out + base) = make_uchar2((unsigned char)(2 * (int64_t)c0 > T), (unsigned char)(2 * (int64_t)c1 > T));
         }
     }
 }

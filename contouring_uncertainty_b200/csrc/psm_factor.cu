@@ -27,7 +27,10 @@ namespace cub200 {
 
 constexpr int P = CUB200_P;   // 42
 constexpr int Z = 34;         // draws of the PSM sampler = sampled coordinates
-constexpr int PF_WARPS = 4;
+#ifndef CUB200_PF_WARPS
+#define CUB200_PF_WARPS 4
+#endif
+constexpr int PF_WARPS = CUB200_PF_WARPS;
 
 // Landmarks in sampling order (get_points_order, psm.py:43-71), then the four posterior-mean-filled points.
 // Everything below works on the permuted variables v = 2 * position + coordinate.
