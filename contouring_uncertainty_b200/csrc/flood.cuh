@@ -10,6 +10,9 @@ constexpr int BAND_STRIDE = 68;                 // 8 rows x 8 words + 4 pad word
 constexpr int BMP_WORDS = 32 * BAND_STRIDE;     // 2176
 
 __device__ __forceinline__ int bmp_addr(int row, int word) { return row * 8 + word + (row >> 3) * 4; }
+// PADDED = false: plain row-major rows of 8 words (the rasteriser's fast path reads rows, not bands; one address add less per pixel)
+template <bool PADDED>
+__device__ __forceinline__ int bmp_addr_t(int row, int word) { return PADDED ? bmp_addr(row, word) : row * 8 + word; }
 
 // 256-bit add / subtract as ONE asm statement each: the carry flag lives only inside the statement, so the compiler cannot
 // schedule anything between the links of the chain (separate non-volatile asm statements have no dependence through CC.CF).
@@ -138,6 +141,7 @@ __device__ __forceinline__ void flood_background(uint32_t (&R)[8][8], const uint
 // skimage.draw.line (Bresenham) from (r0, c0) to (r1, c1) in closed form, the pixels shared among the lanes and clipped to
 // the frame as the reference's rr.clip / cc.clip do: pixel i < dmaj has major = m0 + i * smaj,
 // minor = n0 + smin * floor((2 * dmin * i + dmaj) / (2 * dmaj)); pixel dmaj = (r1, c1).
+template <bool PADDED = true>
 __device__ __forceinline__ void draw_line_clipped(uint32_t* bmp, int r0, int c0, int r1, int c1, int lane) {
     const int dr = abs(r1 - r0), dc = abs(c1 - c0);
     const int sc = (c1 - c0) > 0 ? 1 : -1, sr = (r1 - r0) > 0 ? 1 : -1;
@@ -152,7 +156,7 @@ __device__ __forceinline__ void draw_line_clipped(uint32_t* bmp, int r0, int c0,
             else { cc = c0 + i * sc; rr = r0 + nmin * sr; }
         }
         rr = min(max(rr, 0), 255); cc = min(max(cc, 0), 255);
-        atomicOr(&bmp[bmp_addr(rr, cc >> 5)], 1u << (cc & 31));
+        atomicOr(&bmp[bmp_addr_t<PADDED>(rr, cc >> 5)], 1u << (cc & 31));
     }
 }
 

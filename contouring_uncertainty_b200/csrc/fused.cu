@@ -54,9 +54,6 @@ namespace cub200 {
 #ifndef CUB200_FW_MINBLOCKS
 #define CUB200_FW_MINBLOCKS 2
 #endif
-#ifndef CUB200_EVAL_STRIDED
-#define CUB200_EVAL_STRIDED 0
-#endif
 constexpr int FW_WARPS = CUB200_FW_WARPS;
 constexpr int FW_MINBLOCKS = CUB200_FW_MINBLOCKS;
 constexpr int FW_THREADS = FW_WARPS * 32;
@@ -65,14 +62,16 @@ constexpr int KP = CUB200_K;                    // 21
 constexpr int COORD_CLAMP = 8192;               // landmarks beyond +-8192 px behave as +-8192
 constexpr int FG_WARPS = 8;                     // warps per CTA of the general-flood kernel (128 registers)
 
+template <bool GENERAL>
 struct __align__(16) WarpScratch {
-    uint32_t bmp[BMP_WORDS];
+    uint32_t bmp[GENERAL ? BMP_WORDS : 2048];   // general flood: padded bands (flood.cuh); fast path: plain rows of 8 words
     SplineScratchIdx sp;
 };
 
 // ---------------------------------------------------------------- bitmap helpers
+template <bool PADDED>
 __device__ __forceinline__ void set_pixel(uint32_t* bmp, int row, int col) {
-    atomicOr(&bmp[bmp_addr(row, col >> 5)], 1u << (col & 31));
+    atomicOr(&bmp[bmp_addr_t<PADDED>(row, col >> 5)], 1u << (col & 31));
 }
 
 // Generic run extraction of one mask row (mask = ~R): every transition of R along the row (virtual
@@ -162,6 +161,61 @@ __device__ __forceinline__ uint32_t row_span(const uint4 b0, const uint4 b1, con
     return (uint32_t)xs | ((uint32_t)xe << 16);
 }
 
+// 3c/4. The lane's 32 consecutive evaluation points of the fitted spline (np.linspace(0, 1, 1000)[j], j = 32 lane ..), each
+// rounded half-even, clipped at 255, wrapped like a numpy negative index and set in the bitmap.  Returns the lowest index seen
+// (< -256: the reference's assignment raises).
+// MAGIC: rint() through `v + 1.5 * 2^52`, whose low word is the integer for |v| < 2^31 (fit_spline's `wide` flag guarantees
+// 2^30): a DADD on the fp64 pipe instead of F2I.F64, which runs on the conversion unit (XU) at a fraction of the rate -- ncu had
+// the XU pipe at 56 % with F2I, the busiest unit of the kernel (profiles/r02c_*).
+template <bool GENERAL, bool MAGIC>
+__device__ __forceinline__ int eval_draw(const SplineScratchIdx& sp, uint32_t* bmp, int lane) {
+    const double step = 1.0 / (double)(NPTS - 1);       // j * step == np.linspace(0, 1, 1000)[j] exactly
+    const int j0 = min(lane * 32, NPTS - 32);           // lane 31 re-draws 24 points of lane 30
+    // number of pieces that end at or before j0: branch-free binary search (jnext is non-decreasing, entries 19..31 = INT_MAX)
+    int piece = 0;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) piece += (sp.jnext[piece + sft - 1] <= j0) ? sft : 0;
+    double ub, c0, c1, c2, c3, e0, e1, e2, e3;
+    int jnext;
+#define CUB200_LOAD_PIECE()                                                              \
+    {                                                                                    \
+        const double2* pc = reinterpret_cast<const double2*>(sp.piece[piece]);           \
+        const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];        \
+        jnext = sp.jnext[piece]; ub = q0.y;                                              \
+        c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;                                      \
+        e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                      \
+    }
+    CUB200_LOAD_PIECE();
+    int lowest = 0;
+    double jd = (double)j0;
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+        if (j0 + jj >= jnext) {                          // jnext of the last piece is INT_MAX
+            piece = sp.pnext[piece];
+            CUB200_LOAD_PIECE();
+        }
+        const double sv = jd * step - ub;
+        jd += 1.0;
+        const double xv = fma(fma(fma(c3, sv, c2), sv, c1), sv, c0);
+        const double yv = fma(fma(fma(e3, sv, e2), sv, e1), sv, e0);
+        int ix, iy;
+        if (MAGIC) {
+            ix = __double2loint(xv + 6755399441055744.0); iy = __double2loint(yv + 6755399441055744.0);
+        } else {
+            ix = __double2int_rn(xv); iy = __double2int_rn(yv);
+        }
+        ix = min(ix, 255); iy = min(iy, 255);
+        lowest = __vimin3_s32(lowest, ix, iy);
+        // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
+        const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
+        // one shared-memory atomic per point: merging the bits of consecutive points that share a word saved nothing (some lane
+        // of the warp changes word at nearly every point) and cost a compare, a select and a branch per point
+        atomicOr(&bmp[GENERAL ? cell + ((cell >> 4) & ~3u) : cell], 1u << (ix & 31));       // + (row >> 3) * 4 when padded
+    }
+#undef CUB200_LOAD_PIECE
+    return lowest;
+}
+
 // ---------------------------------------------------------------- one sample, one warp
 // Lane k < 21 holds landmark k as (fx, fy).  Returns the mask area; accumulates run boundaries
 // into diff_img (may be null) and stores the packed mask (may be null).
@@ -170,18 +224,20 @@ __device__ __forceinline__ uint32_t row_span(const uint4 b0, const uint4 b1, con
 // GENERAL = false: the fast fill; returns RASTER_DEFERRED (nothing written) when the sample needs the general flood.
 constexpr int RASTER_DEFERRED = -1;
 template <bool GENERAL>
-__device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double fy, int flags,
+__device__ __forceinline__ int raster_sample(WarpScratch<GENERAL>& ws, double fx, double fy, int flags,
                                              int32_t* __restrict__ diff_img, uint32_t* __restrict__ mask_out) {
     const int lane = lane_id();
     const bool round_landmarks = (flags & 1) != 0, linear = (flags & 2) != 0;
     uint32_t* bmp = ws.bmp;
 
-    // zero the boundary bitmap (uint4 stores)
+    // zero the boundary bitmap (uint4 stores).  The general flood reads bands of 8 rows per lane (padded band stride, flood.cuh);
+    // the fast path reads rows and keeps them plain row-major.
+    constexpr int WORDS = GENERAL ? BMP_WORDS : 2048;
     {
         uint4* b4 = reinterpret_cast<uint4*>(bmp);
         const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int i = 0; i < BMP_WORDS / 4 / 32; ++i) b4[lane + 32 * i] = zero;
+        for (int i = 0; i < WORDS / 4 / 32; ++i) b4[lane + 32 * i] = zero;
     }
     __syncwarp();
 
@@ -193,7 +249,8 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
     const double Y = round_landmarks ? (double)riy : fy;
 
     // 3a/3b. chord-length parameter + not-a-knot cubic spline (spline.cuh)
-    const bool bad = linear ? false : fit_spline(ws.sp, X, Y, lane);
+    bool wide = false;
+    const bool bad = linear ? false : fit_spline(ws.sp, X, Y, lane, &wide);
 
     bool oob = false;
     if (linear) {
@@ -203,76 +260,13 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
         //       An index < -256 makes the
         //       reference's whole assignment raise: then the bitmap is simply cleared again (the
         //       closing line is drawn afterwards).
-        const double step = 1.0 / (double)(NPTS - 1);       // j * step == np.linspace(0, 1, 1000)[j] exactly
-        int lowest = 0;
-#if CUB200_EVAL_STRIDED
-        // Point j = 32 t + lane in iteration t: the 32 lanes always sit in the same one or two pieces, every iteration
-        // fetches its piece's coefficients (a broadcast read), nothing but the piece index is carried from one iteration to
-        // the next, so iterations overlap freely; each point is one shared-memory atomic.  Points 1000..1023 of the last
-        // iteration re-draw point 999.
-        int piece = 0;
-        int jnext = ws.sp.jnext[0];
-#pragma unroll 2
-        for (int t = 0; t < 32; ++t) {
-            const int j = min(32 * t + lane, NPTS - 1);
-            while (j >= jnext) jnext = ws.sp.jnext[++piece];  // jnext of the last piece is INT_MAX
-            const double2* pc = reinterpret_cast<const double2*>(ws.sp.piece[piece]);
-            const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];
-            const double sv = (double)j * step - q0.y;
-            const double xv = fma(fma(fma(q2.y, sv, q2.x), sv, q1.y), sv, q1.x);
-            const double yv = fma(fma(fma(q4.y, sv, q4.x), sv, q3.y), sv, q3.x);
-            const int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
-            lowest = __vimin3_s32(lowest, ix, iy);
-            // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
-            const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
-            atomicOr(&bmp[cell + ((cell >> 4) & ~3u)], 1u << (ix & 31));                        // + (row >> 3) * 4
-        }
-#else
-        const int j0 = min(lane * 32, NPTS - 32);           // lane 31 re-draws 24 points of lane 30
-        int piece = 0;
-        while (j0 >= ws.sp.jnext[piece]) ++piece;
-        double ub, c0, c1, c2, c3, e0, e1, e2, e3;
-        int jnext;
-#define CUB200_LOAD_PIECE()                                                              \
-        {                                                                                \
-            const double2* pc = reinterpret_cast<const double2*>(ws.sp.piece[piece]);       \
-            const double2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3], q4 = pc[4];    \
-            jnext = ws.sp.jnext[piece]; ub = q0.y;                                       \
-            c0 = q1.x; c1 = q1.y; c2 = q2.x; c3 = q2.y;                                  \
-            e0 = q3.x; e1 = q3.y; e2 = q4.x; e3 = q4.y;                                  \
-        }
-        CUB200_LOAD_PIECE();
-        uint32_t cur = 0u, bits = 0u;                        // cur: physical word index of the pending (row, word) cell
-        double jd = (double)j0;
-#pragma unroll 4
-        for (int jj = 0; jj < 32; ++jj) {
-            while (j0 + jj >= jnext) {                       // jnext of the last piece is INT_MAX
-                ++piece;
-                CUB200_LOAD_PIECE();
-            }
-            const double sv = jd * step - ub;                // jd * step == np.linspace(0, 1, 1000)[j] exactly
-            jd += 1.0;
-            const double xv = fma(fma(fma(c3, sv, c2), sv, c1), sv, c0);
-            const double yv = fma(fma(fma(e3, sv, e2), sv, e1), sv, e0);
-            const int ix = min(__double2int_rn(xv), 255), iy = min(__double2int_rn(yv), 255);
-            lowest = __vimin3_s32(lowest, ix, iy);
-            // [-256,-1] wraps like a numpy negative index: (v + 256) == (v & 255) there
-            const uint32_t cell = ((uint32_t)(iy & 255) << 3) | ((uint32_t)(ix & 255) >> 5);   // row * 8 + word
-            const uint32_t phys = cell + ((cell >> 4) & ~3u);                                   // + (row >> 3) * 4
-            const uint32_t bit = 1u << (ix & 31);
-            const bool flush = phys != cur;
-            if (flush && bits != 0u) atomicOr(&bmp[cur], bits);
-            bits = flush ? bit : (bits | bit);
-            cur = phys;
-        }
-#undef CUB200_LOAD_PIECE
-        if (bits) atomicOr(&bmp[cur], bits);
-#endif
+        // (`wide`: a piece that may leave +-2^30 -- astronomically rare -- converts with F2I instead of the magic-number add)
+        const int lowest = wide ? eval_draw<GENERAL, false>(ws.sp, bmp, lane) : eval_draw<GENERAL, true>(ws.sp, bmp, lane);
         oob = __any_sync(FULL, lowest < -256);
         if (oob) {                                           // IndexError in the reference: nothing drawn
             __syncwarp();
             uint4* b4 = reinterpret_cast<uint4*>(bmp);
-            for (int i = 0; i < BMP_WORDS / 4 / 32; ++i) b4[lane + 32 * i] = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < WORDS / 4 / 32; ++i) b4[lane + 32 * i] = make_uint4(0, 0, 0, 0);
         }
     } else {
         // fallback of contour_spline(): spline = the 21 raw points (already ints when rounded)
@@ -282,7 +276,7 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
             oob = (ix < -256) | (iy < -256);
         }
         oob = __any_sync(FULL, oob);
-        if (!oob && lane < KP) set_pixel(bmp, iy & 255, ix & 255);
+        if (!oob && lane < KP) set_pixel<GENERAL>(bmp, iy & 255, ix & 255);
     }
     __syncwarp();
 
@@ -290,7 +284,7 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
 #pragma unroll 1
     for (int e = linear ? 0 : KP - 1; e < KP; ++e) {
         const int e1 = (e + 1 == KP) ? 0 : e + 1;
-        draw_line_clipped(bmp, __shfl_sync(FULL, riy, e), __shfl_sync(FULL, rix, e), __shfl_sync(FULL, riy, e1),
+        draw_line_clipped<GENERAL>(bmp, __shfl_sync(FULL, riy, e), __shfl_sync(FULL, rix, e), __shfl_sync(FULL, riy, e1),
                           __shfl_sync(FULL, rix, e1), lane);
     }
     __syncwarp();
@@ -304,7 +298,7 @@ __device__ __forceinline__ int raster_sample(WarpScratch& ws, double fx, double 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int row = 32 * i + lane;
-            const uint32_t* brow = bmp + bmp_addr(row, 0);
+            const uint32_t* brow = bmp + row * 8;
             const uint4 b0 = reinterpret_cast<const uint4*>(brow)[0], b1 = reinterpret_cast<const uint4*>(brow)[1];
             const uint32_t rowor = (b0.x | b0.y | b0.z) | (b0.w | b1.x | b1.y) | (b1.z | b1.w);
             d[i] = ROW_EMPTY; lr[i] = 0u;
@@ -494,7 +488,7 @@ __global__ void __launch_bounds__(FW_THREADS, FW_MINBLOCKS)
 raster_kernel(const void* __restrict__ contours_in, int64_t n, int flags, int32_t* __restrict__ area_out,
               int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image, uint32_t* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
+    WarpScratch<false>& ws = reinterpret_cast<WarpScratch<false>*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
     const int64_t stride = (int64_t)gridDim.x * FW_WARPS;
     int64_t g = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
@@ -522,7 +516,7 @@ __global__ void __launch_bounds__(FG_WARPS * 32, 2)
 raster_general_kernel(const void* __restrict__ contours_in, int flags, int32_t* __restrict__ area_out,
                       int32_t* __restrict__ diff, uint32_t* __restrict__ masks_out, int64_t per_image, const uint32_t* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
+    WarpScratch<true>& ws = reinterpret_cast<WarpScratch<true>*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
     const uint32_t count = queue[0];
     for (uint32_t q = blockIdx.x * FG_WARPS + (threadIdx.x >> 5); q < count; q += gridDim.x * FG_WARPS) {
@@ -564,19 +558,19 @@ static int launch_raster(const void* contours, bool f64, int64_t n, int flags, i
     note_launches(queue_is_zero ? 1 : 2);                    // + raster_general_kernel (+ zero_queue_kernel); check_launch counts raster_kernel
     const void* kernel = f64 ? (const void*)raster_kernel<true> : (const void*)raster_kernel<false>;
     const void* general = f64 ? (const void*)raster_general_kernel<true> : (const void*)raster_general_kernel<false>;
-    CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FW_WARPS)));
-    CUB200_CUDA_OK(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch) * FG_WARPS)));
+    CUB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch<false>) * FW_WARPS)));
+    CUB200_CUDA_OK(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpScratch<true>) * FG_WARPS)));
     const int64_t need = (n + FW_WARPS - 1) / FW_WARPS;
     const int64_t cap = (int64_t)num_sms * FW_MINBLOCKS;   // resident CTAs; warps stride over the samples
     const int grid = (int)(need < cap ? need : cap);
     const int64_t need_g = (n + FG_WARPS - 1) / FG_WARPS;
     const int grid_g = (int)(need_g < 2 * num_sms ? need_g : 2 * num_sms);
     if (f64) {
-        raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image, queue);
-        raster_general_kernel<true><<<grid_g, FG_WARPS * 32, sizeof(WarpScratch) * FG_WARPS, stream>>>(contours, flags, area_out, diff, masks_out, per_image, queue);
+        raster_kernel<true><<<grid, FW_THREADS, sizeof(WarpScratch<false>) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image, queue);
+        raster_general_kernel<true><<<grid_g, FG_WARPS * 32, sizeof(WarpScratch<true>) * FG_WARPS, stream>>>(contours, flags, area_out, diff, masks_out, per_image, queue);
     } else {
-        raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image, queue);
-        raster_general_kernel<false><<<grid_g, FG_WARPS * 32, sizeof(WarpScratch) * FG_WARPS, stream>>>(contours, flags, area_out, diff, masks_out, per_image, queue);
+        raster_kernel<false><<<grid, FW_THREADS, sizeof(WarpScratch<false>) * FW_WARPS, stream>>>(contours, n, flags, area_out, diff, masks_out, per_image, queue);
+        raster_general_kernel<false><<<grid_g, FG_WARPS * 32, sizeof(WarpScratch<true>) * FG_WARPS, stream>>>(contours, flags, area_out, diff, masks_out, per_image, queue);
     }
     return check_launch("raster_kernel");
 }

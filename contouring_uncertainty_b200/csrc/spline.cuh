@@ -31,6 +31,7 @@ struct __align__(16) SplineScratch {
 struct __align__(16) SplineScratchIdx {
     double piece[20][10];  // {unused, u_i, x c0..c3, y c0..c3}
     int jnext[32];         // jnext[p] = first evaluation point of a piece after p (INT_MAX for the last piece, 19)
+    int pnext[32];         // pnext[p] = the next piece after p that holds at least one evaluation point
 };
 
 constexpr int SPLINE_NPTS = 1000;   // contour_spline(points, n=1000)
@@ -48,8 +49,10 @@ __device__ __forceinline__ int first_point_at_or_after(double u) {
 
 // Lane k < 21 passes point k as (X, Y).  Returns true when FITPACK would raise (zero chord / non-increasing
 // parameter): the reference's bare except then falls back to the raw points.  On success sp is filled.
+// `wide` (optional): set when some piece may leave (-2^30, 2^30) on its interval (|c0| + h(|c1| + h(|c2| + h |c3|)), NaN
+// included) -- then `value + 1.5 * 2^52` no longer holds rint(value) in its low word and the caller must convert with F2I.
 template <class Scratch>
-__device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const double Y, const int lane) {
+__device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const double Y, const int lane, bool* wide = nullptr) {
     constexpr int KP = CUB200_K;
     constexpr bool INDEXED = std::is_same<Scratch, SplineScratchIdx>::value;
     // 3a. chord-length parameter (FITPACK parcur)
@@ -85,7 +88,10 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
         const int jstart = (lane == 0) ? 0 : first_point_at_or_after(u);
         jnext = __shfl_down_sync(FULL, jstart, 1);
         if (lane >= KP - 2) jnext = INT_MAX;
-        if (lane < KP - 1) sp.jnext[lane] = jnext;
+        sp.jnext[lane] = (lane < KP - 1) ? jnext : INT_MAX;   // padded: the binary search of the rasteriser reads all 32 entries
+        // pieces without an evaluation point (two knots inside one step of 1/999) are skipped in ONE move
+        const unsigned holds = __ballot_sync(FULL, lane < KP - 1 && jnext > jstart);
+        sp.pnext[lane] = lane + __ffs((holds >> lane) >> 1);   // the last piece always holds point 999
     } else {
         if (lane < KP) sp.u[lane] = u;
     }
@@ -141,6 +147,11 @@ __device__ __forceinline__ bool fit_spline(Scratch& sp, const double X, const do
             c[2] = make_double2(0.5 * Mx, (m1x - Mx) * ih * (1.0 / 6.0));
             c[3] = make_double2(Y, dyk - h * (2.0 * My + m1y) * (1.0 / 6.0));
             c[4] = make_double2(0.5 * My, (m1y - My) * ih * (1.0 / 6.0));
+        }
+        if (wide) {
+            const double bx = fabs(X) + h * (fabs(dxk - h * (2.0 * Mx + m1x) * (1.0 / 6.0)) + h * (fabs(0.5 * Mx) + h * fabs((m1x - Mx) * ih * (1.0 / 6.0))));
+            const double by = fabs(Y) + h * (fabs(dyk - h * (2.0 * My + m1y) * (1.0 / 6.0)) + h * (fabs(0.5 * My) + h * fabs((m1y - My) * ih * (1.0 / 6.0))));
+            *wide = __any_sync(FULL, lane < KP - 1 && !(fmax(bx, by) < 1073741824.0));
         }
     }
     __syncwarp();
