@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CUB200_LIB") or os.path.join(_HERE, "lib", "libcub200.so")
 
 EINVAL, ECUDA = -1, -2
-EXPECTED_ABI = 18          # the version of include/cub200.h the SIGNATURES table below was written for
+EXPECTED_ABI = 19          # the version of include/cub200.h the SIGNATURES table below was written for
 
 _lib: Optional[C.CDLL] = None
 
@@ -61,6 +61,8 @@ SIGNATURES = {
     "cub200_rasterize_contours_generic": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp],
     "cub200_mask_lv_length": [_vp, _i64, C.c_double, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp],
     "cub200_seg_entropy": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "cub200_endo_base_corners": [_vp, _vp, _i64, _vp, _vp],
+    "cub200_mask_lv_length_myo": [_vp, _vp, _i64, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp],
 }
 QUERIES = ("cub200_last_error", "cub200_abi_version", "cub200_built_for_sm", "cub200_simpson_workspace_bytes", "cub200_calibration_workspace_bytes",
            "cub200_seg_blob_workspace_bytes", "cub200_raster_workspace_bytes", "cub200_launch_count", "cub200_dsnt_workspace_bytes")

@@ -26,6 +26,6 @@ int check_launch(const char* what) {
 }  // namespace cub200
 
 extern "C" const char* cub200_last_error(void) { return cub200::g_err; }
-extern "C" int cub200_abi_version(void) { return 18; }
+extern "C" int cub200_abi_version(void) { return 19; }
 extern "C" int cub200_built_for_sm(void) { return 100; }
 extern "C" int64_t cub200_launch_count(void) { return cub200::g_launches.load(std::memory_order_relaxed); }

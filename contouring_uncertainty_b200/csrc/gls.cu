@@ -58,7 +58,7 @@ __device__ __forceinline__ void point_rc(uint32_t p, const uint32_t* __restrict_
 __global__ void __launch_bounds__(GL_THREADS)
 lv_length_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict__ pts_g, const int32_t* __restrict__ npts,
                  double smoothing_factor, const double* __restrict__ gauss_table, double vs_r, double vs_c,
-                 double* __restrict__ length_out,
+                 const int32_t* __restrict__ corners_in, double* __restrict__ length_out,
                  double* __restrict__ corners_out, int32_t* __restrict__ npts_out) {
     extern __shared__ __align__(16) unsigned char gl_smem[];
     GlsShared& S = *reinterpret_cast<GlsShared*>(gl_smem);
@@ -77,6 +77,46 @@ lv_length_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict_
     };
     if (n < 3) { fail(); return; }                   // find_contours() == [] -> IndexError; overflow (-1) is not supported
 
+    int lk, mr;                                      // roll offset (left corner) and rolled index of the right corner
+    uint32_t left_p = 0u, right_p = 0u;
+    if (corners_in) {
+        // ---- base markers given (EchoMeasure._endo_base, endo_base_corners_kernel): np.argmin of the distance to the contour
+        const int ly = corners_in[g * 4], lx = corners_in[g * 4 + 1], ry = corners_in[g * 4 + 2], rx = corners_in[g * 4 + 3];
+        if (ly < 0) { fail(); return; }              // fewer than two frontier pixels: RuntimeError (measure.py:203-207)
+        // np.linalg.norm(corner - contour, axis=1) = sqrt(dy * dy + dx * dx), every operation rounded; first minimum wins
+        auto block_argmin = [&](double cy, double cx, int roll) {
+            double bd = __longlong_as_double(0x7ff0000000000000LL);
+            int bq = 0x7fffffff;
+            for (int k = tid; k < n; k += GL_THREADS) {
+                double r, c;
+                point_rc(pts[k], m, r, c);
+                const double dy = __dsub_rn(cy, r), dx = __dsub_rn(cx, c);
+                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx)));
+                int q = k - roll;
+                if (q < 0) q += n;
+                if (d < bd || (d == bd && q < bq)) { bd = d; bq = q; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(FULL, bd, o);
+                const int oq = __shfl_xor_sync(FULL, bq, o);
+                if (od < bd || (od == bd && oq < bq)) { bd = od; bq = oq; }
+            }
+            __syncthreads();                         // the previous call's readers are done
+            if (lane == 0) { S.bestv[0][wid] = bd; S.best[0][wid] = bq; }
+            __syncthreads();
+            bd = S.bestv[0][0]; bq = S.best[0][0];
+            for (int w = 1; w < GL_THREADS / 32; ++w) {
+                const double od = S.bestv[0][w];
+                const int oq = S.best[0][w];
+                if (od < bd || (od == bd && oq < bq)) { bd = od; bq = oq; }
+            }
+            return bq;
+        };
+        lk = block_argmin((double)ly, (double)lx, 0);
+        mr = block_argmin((double)ry, (double)rx, lk);
+        __syncthreads();
+    } else {
     // ---- 1. centre of mass (scipy.ndimage.center_of_mass: float sums of integers / count)
     long long cnt = 0, sr = 0, sc = 0;
     for (int w = tid; w < CUB200_MASK_WORDS; w += GL_THREADS) {
@@ -225,17 +265,17 @@ lv_length_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict_
     if (p2 < 0) { fail(); return; }                  // fewer than two base peaks: RuntimeError (measure.py:93-97)
     // descending theta: the left corner is the peak at the larger sorted position
     const int left_i = S.idx[max(p1, p2)], right_i = S.idx[min(p1, p2)];
-    const uint32_t left_p = pts[left_i], right_p = pts[right_i];
+    left_p = pts[left_i]; right_p = pts[right_i];
     __syncthreads();                                 // everyone has read bestv / best before they are reused
     // ---- 5. np.argmin of the distance = the first point equal to the corner; roll, cut, sum
-    int lk = 0x7fffffff;
+    lk = 0x7fffffff;
     for (int k = tid; k < n; k += GL_THREADS) if (pts[k] == left_p) lk = min(lk, k);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lk = min(lk, __shfl_xor_sync(FULL, lk, o));
     if (lane == 0) S.best[0][wid] = lk;
     __syncthreads();
     lk = min(min(S.best[0][0], S.best[0][1]), min(S.best[0][2], S.best[0][3]));
-    int mr = 0x7fffffff;
+    mr = 0x7fffffff;
     for (int k = tid; k < n; k += GL_THREADS)
         if (pts[k] == right_p) { const int q = k - lk; mr = min(mr, q < 0 ? q + n : q); }
 #pragma unroll
@@ -243,6 +283,7 @@ lv_length_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict_
     if (lane == 0) S.best[1][wid] = mr;
     __syncthreads();
     mr = min(min(S.best[1][0], S.best[1][1]), min(S.best[1][2], S.best[1][3]));
+    }
     // segment q joins rolled points q and q + 1: np.linalg.norm of a 2-vector = sqrt(x . x)
     for (int q = tid; q < mr; q += GL_THREADS) {
         int k0 = q + lk, k1 = q + 1 + lk;
@@ -260,7 +301,9 @@ lv_length_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict_
         for (int q = 0; q < mr; ++q) total = __dadd_rn(total, S.key[q]);
         length_out[g] = total;
         if (npts_out) npts_out[g] = mr + 1;
-        if (corners_out) {
+        if (corners_out && corners_in) {
+            for (int k = 0; k < 4; ++k) corners_out[g * 4 + k] = (double)corners_in[g * 4 + k];
+        } else if (corners_out) {
             double r, c;
             point_rc(left_p, m, r, c);
             corners_out[g * 4] = r; corners_out[g * 4 + 1] = c;
@@ -270,7 +313,135 @@ lv_length_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict_
     }
 }
 
+// ---------------------------------------------------------------- EchoMeasure._endo_base          measure.py:177-222
+// One CTA per (LV mask, MYO mask) pair.  Frontier = LV & dilate8(MYO) & dilate8(~(LV | MYO)) (scipy.ndimage.binary_dilation,
+// 3 x 3 structure, zeros beyond the frame), formed word by word in the bit-packed rows; its pixel count and coordinate sums
+// are exact integers, so `x < x.mean()` is decided as x n < sum(x).  np.argmax / np.argmin over np.nonzero's raster order
+// = extreme row, then the smallest column: one atomicMax of a packed key per half.
+// corners_out (n, 4) int32 = (left row, left col, right row, right col); -1 when the reference raises (< 2 frontier pixels).
+__device__ __forceinline__ uint32_t dilate_row_word(const uint32_t* __restrict__ m, int r, int w) {
+    if (r < 0 || r > 255) return 0u;
+    const uint32_t* row = m + r * 8;
+    const uint32_t c = row[w], lo = w > 0 ? row[w - 1] : 0u, hi = w < 7 ? row[w + 1] : 0u;
+    return c | (c << 1) | (lo >> 31) | (c >> 1) | (hi << 31);
+}
+
+__global__ void __launch_bounds__(GL_THREADS)
+endo_base_corners_kernel(const uint32_t* __restrict__ lv_masks, const uint32_t* __restrict__ myo_masks,
+                         int32_t* __restrict__ corners_out) {
+    __shared__ uint32_t F[CUB200_MASK_WORDS];
+    __shared__ unsigned long long sums[3];           // count, sum of columns, sum of rows
+    __shared__ int ext[4];                           // min col, max col, best left key, best right key
+    const int tid = threadIdx.x;
+    const int64_t g = blockIdx.x;
+    const uint32_t* lv = lv_masks + g * CUB200_MASK_WORDS;
+    const uint32_t* my = myo_masks + g * CUB200_MASK_WORDS;
+    if (tid < 3) sums[tid] = 0ull;
+    if (tid == 0) { ext[0] = 256; ext[1] = -1; ext[2] = -1; ext[3] = -1; }
+    __syncthreads();
+    unsigned long long cnt = 0, sx = 0, sy = 0;
+    int xmin = 256, xmax = -1;
+    for (int i = tid; i < CUB200_MASK_WORDS; i += GL_THREADS) {
+        const int r = i >> 3, w = i & 7;
+        uint32_t f = lv[i];
+        if (f) {
+            uint32_t dm = 0u, dother = 0u;
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr) {
+                dm |= dilate_row_word(my, r + dr, w);
+                // others = ~(LV | MYO) inside the frame: dilate the complement, rows beyond the frame contribute nothing
+                const int rr = r + dr;
+                if (rr >= 0 && rr <= 255) {
+                    const uint32_t* a = lv + rr * 8;
+                    const uint32_t* b = my + rr * 8;
+                    const uint32_t c = ~(a[w] | b[w]);
+                    const uint32_t lo = w > 0 ? ~(a[w - 1] | b[w - 1]) : 0u, hi = w < 7 ? ~(a[w + 1] | b[w + 1]) : 0u;
+                    dother |= c | (c << 1) | (lo >> 31) | (c >> 1) | (hi << 31);
+                }
+            }
+            f &= dm & dother;
+        }
+        F[i] = f;
+        uint32_t v = f;
+        while (v) {
+            const int b = __ffs(v) - 1;
+            v &= v - 1;
+            const int x = 32 * w + b;
+            ++cnt; sx += x; sy += r;
+            xmin = min(xmin, x); xmax = max(xmax, x);
+        }
+    }
+    if (cnt) {
+        atomicAdd(&sums[0], cnt); atomicAdd(&sums[1], sx); atomicAdd(&sums[2], sy);
+        atomicMin(&ext[0], xmin); atomicMax(&ext[1], xmax);
+    }
+    __syncthreads();
+    const long long n = (long long)sums[0], SX = (long long)sums[1], SY = (long long)sums[2];
+    if (n < 2) {
+        if (tid < 4) corners_out[g * 4 + tid] = -1;
+        return;
+    }
+    const bool one_column = ext[0] == ext[1];
+    int kl = -1, kr = -1;
+    for (int i = tid; i < CUB200_MASK_WORDS; i += GL_THREADS) {
+        uint32_t v = F[i];
+        const int r = i >> 3;
+        while (v) {
+            const int b = __ffs(v) - 1;
+            v &= v - 1;
+            const int x = 32 * (i & 7) + b;
+            if (one_column) {
+                // coord_mask = y > y.mean(): left = the highest pixel below the mean row, right = the lowest at or above it
+                if ((long long)r * n > SY) kl = max(kl, ((255 - r) << 8) | (255 - x));
+                else kr = max(kr, (r << 8) | (255 - x));
+            } else {
+                // coord_mask = x < x.mean(): the lowest pixel of each half, raster-first among equals
+                if ((long long)x * n < SX) kl = max(kl, (r << 8) | (255 - x));
+                else kr = max(kr, (r << 8) | (255 - x));
+            }
+        }
+    }
+    if (kl >= 0) atomicMax(&ext[2], kl);
+    if (kr >= 0) atomicMax(&ext[3], kr);
+    __syncthreads();
+    if (tid == 0) {
+        const int a = ext[2], b = ext[3];
+        corners_out[g * 4 + 0] = one_column ? 255 - (a >> 8) : (a >> 8);
+        corners_out[g * 4 + 1] = 255 - (a & 255);
+        corners_out[g * 4 + 2] = b >> 8;
+        corners_out[g * 4 + 3] = 255 - (b & 255);
+    }
+}
+
 }  // namespace cub200
+
+extern "C" int cub200_endo_base_corners(const uint32_t* lv_masks, const uint32_t* myo_masks, int64_t n_masks, int32_t* corners_out,
+                                        void* stream) {
+    using namespace cub200;
+    if (n_masks == 0) return 0;
+    if (!lv_masks || !myo_masks || !corners_out || n_masks < 0 || n_masks > 0x7fffffff) return CUB200_EINVAL;
+    endo_base_corners_kernel<<<(unsigned)n_masks, GL_THREADS, 0, (cudaStream_t)stream>>>(lv_masks, myo_masks, corners_out);
+    return check_launch("endo_base_corners_kernel");
+}
+
+extern "C" int cub200_mask_lv_length_myo(const uint32_t* lv_masks, const uint32_t* myo_masks, int64_t n_masks, double spacing_row,
+                                         double spacing_col, double* length_out, int32_t* corners_out, int32_t* npts_out,
+                                         void* workspace, void* stream) {
+    using namespace cub200;
+    if (n_masks == 0) return 0;
+    if (!lv_masks || !myo_masks || !length_out || !corners_out || !workspace || n_masks < 0 || n_masks > 0x7fffffff) return CUB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* pts = reinterpret_cast<uint32_t*>(workspace);
+    int32_t* npts = reinterpret_cast<int32_t*>(pts + n_masks * SP_NMAX);
+    endo_base_corners_kernel<<<(unsigned)n_masks, GL_THREADS, 0, st>>>(lv_masks, myo_masks, corners_out);
+    if (int rc = check_launch("endo_base_corners_kernel")) return rc;
+    contour_trace_kernel<<<(unsigned)((n_masks + 127) / 128), 128, 0, st>>>(lv_masks, n_masks, nullptr, nullptr, 256, 256, pts, npts);
+    if (int rc = check_launch("contour_trace_kernel")) return rc;
+    CUB200_CUDA_OK(cudaFuncSetAttribute(lv_length_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GlsShared)));
+    lv_length_kernel<<<(unsigned)n_masks, GL_THREADS, sizeof(GlsShared), st>>>(lv_masks, pts, npts, 0.0, nullptr, spacing_row, spacing_col,
+                                                                              corners_out, length_out, nullptr, npts_out);
+    return check_launch("lv_length_kernel");
+}
 
 extern "C" int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, double smoothing_factor, const double* gauss_table,
                                      double spacing_row, double spacing_col, double* length_out, double* corners_out,
@@ -287,7 +458,7 @@ extern "C" int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, dou
     if (int rc = check_launch("contour_trace_kernel")) return rc;
     CUB200_CUDA_OK(cudaFuncSetAttribute(lv_length_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GlsShared)));
     lv_length_kernel<<<(unsigned)n_masks, GL_THREADS, sizeof(GlsShared), st>>>(masks, pts, npts, smoothing_factor, gauss_table,
-                                                                              spacing_row, spacing_col, length_out, corners_out,
+                                                                              spacing_row, spacing_col, nullptr, length_out, corners_out,
                                                                               npts_out);
     return check_launch("lv_length_kernel");
 }

@@ -1007,11 +1007,51 @@ def mask_lv_length(masks: torch.Tensor, voxelspacing=(1.0, 1.0), polar_smoothing
     return (length, corners, npts) if return_corners else length
 
 
-def mask_gls(masks: torch.Tensor, voxelspacing=(1.0, 1.0)) -> torch.Tensor:
-    """EchoMeasure.gls (measure.py:320-366, myo_labels=None) on sequences of bit-packed masks (..., N_frames, 2048): strain in
+def endo_base_corners(lv_masks: torch.Tensor, myo_masks: torch.Tensor) -> torch.Tensor:
+    """EchoMeasure._endo_base (vital/vital/utils/image/us/measure.py:177-222): bit-packed LV and MYO masks (..., 2048) int32 ->
+    (..., 2, 2) int32 = (left, right) base markers as (row, col); -1 where the reference raises (< 2 frontier pixels)."""
+    lv_masks = nat.require_cuda(lv_masks, torch.int32, "lv_masks")
+    myo_masks = nat.require_cuda(myo_masks, torch.int32, "myo_masks")
+    if lv_masks.shape[-1] != MASK_WORDS or myo_masks.shape != lv_masks.shape or myo_masks.device != lv_masks.device:
+        raise ValueError(f"lv_masks and myo_masks must be (..., {MASK_WORDS}) bit-packed, same shape and device")
+    lead = tuple(lv_masks.shape[:-1])
+    n = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    dev = lv_masks.device
+    corners = torch.empty(lead + (2, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_endo_base_corners(nat.ptr(lv_masks), nat.ptr(myo_masks), n, nat.ptr(corners), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_endo_base_corners")
+    return corners
+
+
+def mask_lv_length_myo(lv_masks: torch.Tensor, myo_masks: torch.Tensor, voxelspacing=(1.0, 1.0), return_corners: bool = False):
+    """EchoMeasure._lv_longitudinal_length with myo_labels (measure.py:339-354, base markers by _endo_base :177-222):
+    bit-packed LV and MYO masks (..., 2048) int32 -> lengths (...) fp64, NaN where the reference raises
+    [, base markers (..., 2, 2) int32 as (row, col), points of the base-less contour (...) int32]."""
+    lv_masks = nat.require_cuda(lv_masks, torch.int32, "lv_masks")
+    myo_masks = nat.require_cuda(myo_masks, torch.int32, "myo_masks")
+    if lv_masks.shape[-1] != MASK_WORDS or myo_masks.shape != lv_masks.shape or myo_masks.device != lv_masks.device:
+        raise ValueError(f"lv_masks and myo_masks must be (..., {MASK_WORDS}) bit-packed, same shape and device")
+    lead = tuple(lv_masks.shape[:-1])
+    n = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    dev = lv_masks.device
+    length = torch.empty(lead, dtype=torch.float64, device=dev)
+    corners = torch.empty(lead + (2, 2), dtype=torch.int32, device=dev)
+    npts = torch.empty(lead, dtype=torch.int32, device=dev) if return_corners else None
+    ws = torch.empty((max(int(nat.lib().cub200_simpson_workspace_bytes(n)), 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_mask_lv_length_myo(nat.ptr(lv_masks), nat.ptr(myo_masks), n, float(voxelspacing[0]), float(voxelspacing[1]),
+                                                 nat.ptr(length), nat.ptr(corners), nat.ptr(npts), nat.ptr(ws), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_mask_lv_length_myo")
+    return (length, corners, npts) if return_corners else length
+
+
+def mask_gls(masks: torch.Tensor, voxelspacing=(1.0, 1.0), myo_masks: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """EchoMeasure.gls (measure.py:320-366) on sequences of bit-packed masks (..., N_frames, 2048): strain in
     percent of every frame against the first one (the ED frame), (..., N_frames) fp64; a frame the reference cannot measure
-    makes the whole sequence NaN (its exception leaves GLS.gls's try block, cu/results/clinical/view.py:86-96)."""
-    length = mask_lv_length(masks, voxelspacing)
+    makes the whole sequence NaN (its exception leaves GLS.gls's try block, cu/results/clinical/view.py:86-96).
+    myo_masks None: base corners from the polar contour (myo_labels=None); else EchoMeasure._endo_base on (LV, MYO)."""
+    length = mask_lv_length(masks, voxelspacing) if myo_masks is None else mask_lv_length_myo(masks, myo_masks, voxelspacing)
     ed = length[..., :1]
     gls = (length - ed) / ed * 100
     return torch.where(torch.isnan(length).any(-1, keepdim=True), torch.full_like(gls, float("nan")), gls)

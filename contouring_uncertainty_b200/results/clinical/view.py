@@ -63,8 +63,9 @@ class FAC(ViewMetric):
 
 
 class GLS(ViewMetric):
-    """view.py:81-189, the mask-based part (EchoMeasure.gls on the LV masks, myo_labels=None) and the contour GLS of the
-    prediction / ground truth.  The reference's 'contour_mc' feeds MASKS to a function of contours (view.py:121-125), which has
+    """view.py:81-189, the mask-based part (EchoMeasure.gls on the LV masks; base corners from the polar contour, or from
+    EchoMeasure._endo_base when the view's labels hold Label.MYO, :90) and the contour GLS of the prediction / ground truth.
+    Like the reference, the mask GLS is measured in pixels (view.py:94 passes no voxelspacing).  The reference's 'contour_mc' feeds MASKS to a function of contours (view.py:121-125), which has
     no meaning; here the Monte-Carlo contour GLS is taken from ``contour_samples`` (what its commented-out code intended)."""
     PREFIX = "GLS_"
     MIN_VALUE = 0
@@ -73,10 +74,9 @@ class GLS(ViewMetric):
     @classmethod
     def gls(cls, segmentation, view: BatchResult):
         """view.py:86-96: strain (percent) of the ES frame of one (N_frames, H, W) sequence; NaN when it cannot be measured."""
-        if Label.MYO in tuple(view.labels):
-            raise NotImplementedError("myo_labels (EchoMeasure._endo_base) is not provided")
-        masks = packed_masks(np.asarray(segmentation))
-        return float(E.mask_gls(masks, view.voxelspacing if view.voxelspacing is not None else (1.0, 1.0))[view.instants[Instant.ES]].cpu())
+        seg = np.asarray(segmentation)
+        myo = packed_masks(seg == Label.MYO) if Label.MYO in tuple(view.labels) else None
+        return float(E.mask_gls(packed_masks(seg == Label.LV), myo_masks=myo)[view.instants[Instant.ES]].cpu())
 
     def compute(self, view: BatchResult):
         instants = view.instants
@@ -95,9 +95,12 @@ class GLS(ViewMetric):
             }
         pred = self.gls(view.pred, view) / -100
         gt = self.gls(view.gt, view) / -100
-        sm = view_sample_masks(view)                                                  # (N, T_e, T_a, 2048)
-        vs = view.voxelspacing if view.voxelspacing is not None else (1.0, 1.0)
-        g = E.mask_gls(sm.permute(1, 2, 0, 3).contiguous(), vs)[..., ES].cpu().numpy()  # per (T_e, T_a): the sequence of N frames
+        if Label.MYO in tuple(view.labels):                                           # label maps: LV = 1, MYO = 2
+            ps = np.asarray(view.pred_samples)
+            sm, smyo = packed_masks(ps == Label.LV), packed_masks(ps == Label.MYO).permute(1, 2, 0, 3).contiguous()
+        else:
+            sm, smyo = view_sample_masks(view), None                                  # (N, T_e, T_a, 2048)
+        g = E.mask_gls(sm.permute(1, 2, 0, 3).contiguous(), myo_masks=smyo)[..., ES].cpu().numpy()  # per (T_e, T_a): the sequence of N frames
         mc = g / -100
         mc[np.isinf(mc)] = np.nan
         s = ae_split(mc, (self.MIN_VALUE, self.MAX_VALUE))

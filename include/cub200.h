@@ -490,6 +490,25 @@ int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, double smoothi
                           void* workspace, void* stream);
 
 /*
+ * The same length with the base markers of EchoMeasure._endo_base            vv/utils/image/us/measure.py:177-222
+ * (EchoMeasure.gls with myo_labels, measure.py:339-352; GLS.gls passes Label.MYO when the view's labels hold it,
+ * cu/results/clinical/view.py:90-94): the LV pixels whose 8-neighbourhood meets both the myocardium and the rest, split at
+ * their mean column (mean row when they lie in one column), the lowest pixel of each half.
+ *   lv_masks, myo_masks (n_masks, 2048) u32 bit-packed (e.g. the two outputs of cub200_us_myo_masks).
+ *   cub200_endo_base_corners: corners_out (n_masks, 4) i32 = (left row, left col, right row, right col); -1 where the
+ *   reference raises (fewer than two frontier pixels).
+ *   cub200_mask_lv_length_myo: corners_out as above (required: also the staging buffer), length_out (n_masks) f64 = length
+ *   of the LV contour (level 0.9) from the point closest to the left marker to the point closest to the right one (first
+ *   minimum, np.argmin), NaN where the reference raises; optional npts_out (n_masks) i32.
+ *   workspace: cub200_simpson_workspace_bytes(n_masks).
+ */
+int cub200_endo_base_corners(const uint32_t* lv_masks, const uint32_t* myo_masks, int64_t n_masks, int32_t* corners_out,
+                             void* stream);
+int cub200_mask_lv_length_myo(const uint32_t* lv_masks, const uint32_t* myo_masks, int64_t n_masks, double spacing_row,
+                              double spacing_col, double* length_out, int32_t* corners_out, int32_t* npts_out,
+                              void* workspace, void* stream);
+
+/*
  * Rasteriser for contours with any number of points: reconstruction / linear_reconstruction   cu/utils/contour.py:28-53
  * as LungContourToMask (cu/data/lung/utils.py:25-69) uses them per structure (44 / 50 / 26 points).
  *   contours (n, n_points, 2) (x, y), fp32 (is_f64 = 0) or fp64 (is_f64 = 1); 4 <= n_points <= CUB200_RASTER_MAX_POINTS;

@@ -1354,6 +1354,56 @@ def echo_gls(segmentation: np.ndarray, voxelspacing=(1, 1)) -> np.ndarray:
     return (lengths - lengths[0]) / lengths[0] * 100
 
 
+def endo_base_corners(segmentation: np.ndarray, lv_label: int = 1, myo_label: int = 2):
+    """vital/vital/utils/image/us/measure.py:177-222 (EchoMeasure._endo_base): the LV pixels that touch (8-neighbourhood
+    dilation) both the myocardium and the rest; the frontier is split at its mean column (at its mean row when it is one
+    column) and the lowest pixel of each half (raster-first among equals: np.argmax) is the left / right base marker.
+    Raises RuntimeError with fewer than two frontier pixels (:203-207).  Returns ((row, col), (row, col)) int arrays."""
+    from scipy import ndimage
+
+    struct = ndimage.generate_binary_structure(2, 2)
+    seg = np.asarray(segmentation)
+    lv = np.isin(seg, lv_label)
+    myo = np.isin(seg, myo_label)
+    others = ~(lv + myo)
+    front = lv * ndimage.binary_dilation(myo, structure=struct) * ndimage.binary_dilation(others, structure=struct)
+    y, x = np.nonzero(front)
+    if len(y) < 2:
+        raise RuntimeError("fewer than two markers at the LV / MYO frontier")
+    if np.all(x == x.mean()):                                                  # :209-214 the frontier is one column
+        m = y > y.mean()
+        li, ri = y[m].argmin(), y[~m].argmax()
+    else:                                                                      # :215-220
+        m = x < x.mean()
+        li, ri = y[m].argmax(), y[~m].argmax()
+    return np.array([y[m][li], x[m][li]]), np.array([y[~m][ri], x[~m][ri]])
+
+
+def endo_contour_without_base_myo(segmentation: np.ndarray, lv_label: int = 1, myo_label: int = 2) -> np.ndarray:
+    """measure.py:153-175 (_endo_epi_contour) with base_fn = _endo_base: the LV contour at level 0.9 rolled to the point
+    closest to the left marker (first minimum: np.argmin) and cut after the point closest to the right marker."""
+    left, right = endo_base_corners(segmentation, lv_label, myo_label)
+    contour = find_contours(np.isin(np.asarray(segmentation), lv_label), level=0.9)[0]
+    contour = np.roll(contour, -np.argmin(np.linalg.norm(left - contour, axis=1)), axis=0)
+    return contour[: np.argmin(np.linalg.norm(right - contour, axis=1)) + 1]
+
+
+def lv_longitudinal_length_myo(segmentation: np.ndarray, voxelspacing=(1, 1), lv_label: int = 1, myo_label: int = 2) -> float:
+    """measure.py:339-354 with myo_labels given."""
+    c = endo_contour_without_base_myo(segmentation, lv_label, myo_label)
+    vs = np.array(voxelspacing)
+    total = 0
+    for p0, p1 in zip(c[:-1], c[1:]):
+        total = total + np.linalg.norm((p1 - p0) * vs)
+    return float(total)
+
+
+def echo_gls_myo(segmentation: np.ndarray, voxelspacing=(1, 1), lv_label: int = 1, myo_label: int = 2) -> np.ndarray:
+    """measure.py:320-366 (EchoMeasure.gls with myo_labels): (N,H,W) label maps, first frame = ED -> (N,) strain in percent."""
+    lengths = np.array([lv_longitudinal_length_myo(f, voxelspacing, lv_label, myo_label) for f in segmentation])
+    return (lengths - lengths[0]) / lengths[0] * 100
+
+
 def lung_contour_to_mask(landmarks: np.ndarray, apply_argmax: bool = True, reconstruction_type: str = "spline") -> np.ndarray:
     """cu/data/lung/utils.py:25-69: 120 rounded landmarks = right lung (44) + left lung (50) + heart (26) (config.py:35-37),
     each through reconstruction / linear_reconstruction; the lungs ADD into channel 1, the heart is channel 2."""

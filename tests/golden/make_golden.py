@@ -695,6 +695,53 @@ def golden_glsmask():
     print("glsmask.npz", n, "masks; lengths", length[:4], "gls", gls[0, :4], "failed", int(np.isnan(length).sum()))
 
 
+def glsmyo_extra_maps():
+    """Hand-made label maps for the corner cases of _endo_base: a one-column frontier (the vertical branch, :209-214) on the
+    left and on the right of the LV, a frontier in one place only, no myocardium at all (RuntimeError), one frontier pixel."""
+    out = np.zeros((5, 256, 256), dtype=np.uint8)
+    yy, xx = np.mgrid[:256, :256]
+    lv = ((yy - 120) / 60.0) ** 2 + ((xx - 128) / 35.0) ** 2 <= 1
+    out[0, 60:180, 94:160] = 1                     # LV block; MYO bar on its left edge: frontier = LV column 94 only
+    out[0, 100:141, 90:94] = 2
+    out[1][lv] = 1
+    out[1][70:75, 126:131] = np.where(out[1][70:75, 126:131] == 1, 1, 2)         # myocardium touching the LV in one place only
+    out[1][58:61, 128] = 2
+    out[2][lv] = 1                                                               # no myocardium
+    out[3, 60:180, 94:160] = 1                     # MYO bar on the right edge, off-centre: frontier = LV column 159 only
+    out[3, 70:90, 160:163] = 2
+    out[4, 60:180, 94:160] = 1                     # a myocardium pixel diagonal to the LV corner: one frontier pixel
+    out[4, 59, 93] = 2
+    return out
+
+
+def golden_glsmyo():
+    """EchoMeasure.gls with myo_labels (vital/vital/utils/image/us/measure.py:177-222 _endo_base, :153-175 _endo_epi_contour,
+    :320-366 gls) on LV + MYO label maps, executed as it is.  skimage.measure.find_contours is the restated one."""
+    import functools
+    from vital.data.camus.config import Label
+    from vital.utils.image.us.measure import EchoMeasure
+
+    maps = np.concatenate([np.load(os.path.join(HERE, "myo.npz"))["argmax"], np.load(os.path.join(HERE, "myo_task.npz"))["pred_samples_argmax"].reshape(-1, 256, 256),
+                           glsmyo_extra_maps()]).astype(np.uint8)
+    base_fn = functools.partial(EchoMeasure._endo_base, lv_labels=Label.LV, myo_labels=Label.MYO)
+    n = len(maps)
+    corners = np.full((n, 2, 2), -1, dtype=np.int64)
+    npts = np.zeros(n, dtype=np.int64)
+    length = np.full(n, np.nan)
+    for i, m in enumerate(maps):
+        try:
+            corners[i] = np.array(base_fn(m.astype(int)))
+            c = EchoMeasure._endo_epi_contour(m.astype(int), Label.LV, base_fn)
+            npts[i] = len(c)
+            length[i] = sum(np.linalg.norm((p1 - p0) * np.array((0.7, 0.4))) for p0, p1 in zip(c[:-1], c[1:]))   # measure.py:354
+        except Exception as e:
+            print("  map", i, "raised", type(e).__name__, e)
+    pairs = [(0, 1), (2, 3), (4, 5), (6, 7), (8, 9), (11, 13)]
+    gls = np.array([EchoMeasure.gls(np.stack([maps[a], maps[b]]).astype(int), Label.LV, Label.MYO, voxelspacing=(0.7, 0.4))[1] for a, b in pairs])
+    np.savez_compressed(os.path.join(HERE, "glsmyo.npz"), maps=maps, corners=corners, npts=npts, length=length, pairs=np.array(pairs), gls=gls)
+    print("glsmyo.npz", n, "maps; lengths", length[:4], "gls", gls[:4], "failed", int(np.isnan(length).sum()))
+
+
 def golden_generic():
     """reconstruction / linear_reconstruction for contours that are not 21 points long, and LungContourToMask
     (contour_uncertainty/data/lung/utils.py:25-69), executed as they are."""
@@ -1043,6 +1090,6 @@ def golden_class_entropy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics", "myo_task", "psm_alpha"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics", "myo_task", "psm_alpha", "glsmyo"]
     for w in which:
         globals()["golden_" + w]()

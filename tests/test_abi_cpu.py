@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in cub200.h but not exported"
     assert set(names) == set(_native.SIGNATURES) | set(_native.QUERIES)
-    assert _native.lib().cub200_abi_version() == _native.EXPECTED_ABI == 18
+    assert _native.lib().cub200_abi_version() == _native.EXPECTED_ABI == 19
     assert _native.lib().cub200_built_for_sm() == 100
 
 
@@ -104,6 +104,9 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_rasterize_contours_generic(None, 0, 0, 26, 1, None, None, None) == 0
     assert l.cub200_mask_lv_length(None, 1, 5e-3, None, 1.0, 1.0, None, None, None, None, None) == E
     assert l.cub200_mask_lv_length(None, 0, 5e-3, None, 1.0, 1.0, None, None, None, None, None) == 0
+    assert l.cub200_endo_base_corners(None, None, 1, None, None) == E
+    assert l.cub200_mask_lv_length_myo(None, None, 1, 1.0, 1.0, None, None, None, None, None) == E
+    assert l.cub200_mask_lv_length_myo(None, None, 0, 1.0, 1.0, None, None, None, None, None) == 0
     assert l.cub200_seg_largest_blob(None, 0, None, None, None, None) == 0
     assert l.cub200_seg_entropy(None, None, 1, 1, 10, None, None, None, None, None) == E
     assert l.cub200_seg_entropy(None, None, 0, 1, 10, None, None, None, None, None) == 0

@@ -85,3 +85,60 @@ def test_echo_measure_mirror_and_errors():
     assert got[0] == 0 and abs(got[1] - g["gls"][0, 0]) < 1e-10
     with pytest.raises(RuntimeError):
         EchoMeasure.gls(np.stack([masks[0], np.zeros((256, 256), dtype=np.int64)]), 1, None)
+
+
+def test_endo_base_golden_corners_lengths_gls():
+    """EchoMeasure.gls with myo_labels (_endo_base markers, measure.py:177-222) against the executed reference: LV + MYO label
+    maps incl. a one-column frontier (the vertical branch), a single frontier pixel and a map without myocardium."""
+    from contouring_uncertainty_b200 import engine as E
+    from contouring_uncertainty_b200.utils.measure import EchoMeasure
+
+    g = np.load(os.path.join(G, "glsmyo.npz"))
+    dev = torch.device("cuda:0")
+    maps = g["maps"]
+    lv = torch.from_numpy(_pack(maps == 1)).to(dev)
+    myo = torch.from_numpy(_pack(maps == 2)).to(dev)
+    corners = E.endo_base_corners(lv, myo).cpu().numpy()
+    assert np.array_equal(corners, g["corners"])                             # -1 where the reference raised
+    length, c2, npts = E.mask_lv_length_myo(lv, myo, voxelspacing=(0.7, 0.4), return_corners=True)
+    length, npts = length.cpu().numpy(), npts.cpu().numpy()
+    assert np.array_equal(c2.cpu().numpy(), g["corners"])
+    want = g["length"]
+    assert np.array_equal(np.isnan(length), np.isnan(want)) and np.isnan(want).sum() == 2
+    ok = ~np.isnan(want)
+    assert np.array_equal(npts[ok], g["npts"][ok])
+    np.testing.assert_allclose(length[ok], want[ok], rtol=1e-13)             # the reference's norms go through BLAS ddot
+    for (a, b), gl in zip(g["pairs"], g["gls"]):
+        got = E.mask_gls(torch.stack([lv[a], lv[b]]), (0.7, 0.4), myo_masks=torch.stack([myo[a], myo[b]]))[1].item()
+        assert abs(got - gl) <= 1e-11 * abs(gl)
+        np.testing.assert_allclose(EchoMeasure.gls(np.stack([maps[a], maps[b]]), 1, 2, (0.7, 0.4))[1], gl, rtol=1e-11)
+    l, r = EchoMeasure._endo_base(maps[0], 1, 2)
+    assert l.tolist() == g["corners"][0, 0].tolist() and r.tolist() == g["corners"][0, 1].tolist()
+    with pytest.raises(RuntimeError):
+        EchoMeasure._endo_base(maps[40], 1, 2)
+    with pytest.raises(RuntimeError):
+        EchoMeasure.gls(np.stack([maps[0], maps[40]]), 1, 2)
+
+
+def test_endo_base_random_landmark_sets_against_oracle():
+    """LV + MYO masks rasterised on the GPU from jittered 42-landmark sets; markers, point counts and lengths vs the oracle."""
+    from contouring_uncertainty_b200 import engine as E
+
+    dev = torch.device("cuda:0")
+    lm = np.concatenate([synth.endo_epi_landmarks(40, seed=5), synth.endo_epi_landmarks(8, seed=6, wild=True)]).astype(np.float32)
+    lv, myo, _ = E.us_myo_masks(torch.from_numpy(lm).to(dev))
+    length, corners, npts = E.mask_lv_length_myo(lv, myo, return_corners=True)
+    seg = E.unpack_masks(lv).cpu().numpy().astype(np.uint8) + 2 * E.unpack_masks(myo).cpu().numpy().astype(np.uint8)
+    bad = []
+    for i in range(len(lm)):
+        try:
+            want_c = np.array(port.endo_base_corners(seg[i]))
+            want_n = len(port.endo_contour_without_base_myo(seg[i]))
+            want = port.lv_longitudinal_length_myo(seg[i])
+        except (RuntimeError, IndexError):
+            if not np.isnan(length[i].item()):
+                bad.append((i, "expected NaN"))
+            continue
+        if not (np.array_equal(corners[i].cpu().numpy(), want_c) and npts[i].item() == want_n and abs(length[i].item() - want) <= 1e-12 * want):
+            bad.append((i, corners[i].tolist(), want_c.tolist(), length[i].item(), want))
+    assert not bad, bad

@@ -471,3 +471,24 @@ def test_skew_task_predict_step_matches_reference():
     _check_task_result(g, "f32", r)
     # DSNTSkew.predict_on_batch negates the y component of the raw skewness (dsnt_skew.py:164)
     assert np.array_equal(g["alpha_te"], np.swapaxes(g["raw_alpha"], 0, 1) * np.array([1.0, -1.0], dtype=np.float32))
+
+
+def test_endo_base_gls_matches_reference():
+    """EchoMeasure._endo_base / _endo_epi_contour / gls with myo_labels (measure.py:153-222, 320-366) executed verbatim on
+    43 LV + MYO label maps (glsmyo.npz): markers and point counts identical, lengths and strains bit-identical."""
+    g = np.load(os.path.join(G, "glsmyo.npz"))
+    maps = g["maps"]
+    raised = 0
+    for i, m in enumerate(maps):
+        try:
+            left, right = port.endo_base_corners(m)
+        except RuntimeError:
+            raised += 1
+            assert np.isnan(g["length"][i]) and (g["corners"][i] == -1).all()
+            continue
+        assert left.tolist() == g["corners"][i, 0].tolist() and right.tolist() == g["corners"][i, 1].tolist()
+        assert len(port.endo_contour_without_base_myo(m)) == g["npts"][i]
+        assert port.lv_longitudinal_length_myo(m, (0.7, 0.4)) == g["length"][i]
+    assert raised == 2
+    for (a, b), gl in zip(g["pairs"], g["gls"]):
+        assert port.echo_gls_myo(np.stack([maps[a], maps[b]]), (0.7, 0.4))[1] == gl
