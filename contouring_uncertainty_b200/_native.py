@@ -45,7 +45,8 @@ SIGNATURES = {
     "cub200_rasterize_contours_f64": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_projected_uncertainty": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],
     "cub200_umap_analytic": [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp],
-    "cub200_skew_umap_contours": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cub200_skew_umap_contours": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
+    "cub200_projected_uncertainty_generic": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "cub200_weighted_mask_entropy": [_vp, _vp, _i64, _i32, C.c_double, _i32, _vp, _vp],
     "cub200_seq_skew_conditionals": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cub200_seq_skew_sample": [_vp] * 12 + [_u64, _i64, _i64, _vp, _vp, _vp],

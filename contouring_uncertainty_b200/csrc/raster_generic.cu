@@ -12,6 +12,7 @@
 // 1000 evaluations at j / 999 -> round half even -> index rules (clip at 255, negative wrap, < -256 drops the whole
 // spline, zero chord -> the raw points) -> closing line -> binary_fill_holes (flood.cuh) -> bit-packed mask + area.
 #include "flood.cuh"
+#include "spline_generic.cuh"
 
 namespace cub200 {
 
@@ -22,11 +23,7 @@ constexpr int GK_CLAMP = 8192;
 
 struct __align__(16) GenericScratch {
     uint32_t bmp[BMP_WORDS];
-    double piece[GK_MAX][10];      // piece i on [u_i, u_{i+1}]: {u_{i+1}, u_i, x c0..c3, y c0..c3} (powers of u - u_i)
-    double u[GK_MAX];
-    double X[GK_MAX], Y[GK_MAX];   // the points the spline goes through (rounded or not)
-    double Mx[GK_MAX], My[GK_MAX]; // second derivatives
-    double cp[GK_MAX];             // Thomas: modified super-diagonal
+    GenericSpline sp;              // the points the spline goes through (rounded or not), parameters, pieces
     int rix[GK_MAX], riy[GK_MAX];  // rounded points (closing line, linear reconstruction)
 };
 
@@ -52,102 +49,28 @@ raster_generic_kernel(const T* __restrict__ contours, int64_t n, int K, int flag
         fy = fmin(fmax(fy, -(double)GK_CLAMP), (double)GK_CLAMP);
         const int rx = __double2int_rn(fx), ry = __double2int_rn(fy);
         S.rix[k] = rx; S.riy[k] = ry;
-        S.X[k] = round_landmarks ? (double)rx : fx;
-        S.Y[k] = round_landmarks ? (double)ry : fy;
+        S.sp.X[k] = round_landmarks ? (double)rx : fx;
+        S.sp.Y[k] = round_landmarks ? (double)ry : fy;
     }
     __syncwarp();
 
     bool bad = false, oob = false;
     if (!linear) {
-        // chord-length parameter (FITPACK parcur) and the not-a-knot system, by lane 0
-        int badflag = 0;
-        if (lane == 0) {
-            double cum = 0.0;
-            S.u[0] = 0.0;
-            for (int k = 1; k < K; ++k) {
-                const double dx = S.X[k] - S.X[k - 1], dy = S.Y[k] - S.Y[k - 1];
-                const double d = sqrt(dx * dx + dy * dy);
-                if (d == 0.0) badflag = 1;
-                cum += d;
-                S.u[k] = cum;
-            }
-            if (!(cum > 0.0)) badflag = 1;
-            if (!badflag) {
-                for (int k = 1; k < K - 1; ++k) {
-                    S.u[k] = S.u[k] / cum;
-                    if (!(S.u[k] > S.u[k - 1])) badflag = 1;
-                }
-                S.u[K - 1] = 1.0;
-                if (!(S.u[K - 1] > S.u[K - 2])) badflag = 1;
-            }
-            if (!badflag) {
-                // rows i = 1..K-2 of  h_{i-1} M_{i-1} + 2 (h_{i-1} + h_i) M_i + h_i M_{i+1} = 6 (delta_i - delta_{i-1}),
-                // with M_0 and M_{K-1} eliminated through the not-a-knot conditions at u_1 and u_{K-2}
-                const int last = K - 2;
-                double prev_cp = 0.0, prev_dx = 0.0, prev_dy = 0.0;
-                for (int i = 1; i <= last; ++i) {
-                    const double hm = S.u[i] - S.u[i - 1], h = S.u[i + 1] - S.u[i];
-                    const double dxk = (S.X[i + 1] - S.X[i]) / h, dyk = (S.Y[i + 1] - S.Y[i]) / h;
-                    const double dxm = (S.X[i] - S.X[i - 1]) / hm, dym = (S.Y[i] - S.Y[i - 1]) / hm;
-                    double a = hm, b = 2.0 * (hm + h), c = h;
-                    double r1 = 6.0 * (dxk - dxm), r2 = 6.0 * (dyk - dym);
-                    if (i == 1) {
-                        const double f = h / (hm + h);
-                        a = 0.0; b = hm + 2.0 * h; c = h - hm; r1 *= f; r2 *= f;
-                    }
-                    if (i == last) {
-                        const double f = hm / (hm + h);
-                        a = hm - h; b = h + 2.0 * hm; c = 0.0; r1 *= f; r2 *= f;
-                    }
-                    const double den = b - a * prev_cp;
-                    prev_cp = c / den;
-                    prev_dx = (r1 - a * prev_dx) / den;
-                    prev_dy = (r2 - a * prev_dy) / den;
-                    S.cp[i] = prev_cp; S.Mx[i] = prev_dx; S.My[i] = prev_dy;
-                }
-                for (int i = last - 1; i >= 1; --i) {
-                    S.Mx[i] -= S.cp[i] * S.Mx[i + 1];
-                    S.My[i] -= S.cp[i] * S.My[i + 1];
-                }
-                {
-                    const double h0 = S.u[1] - S.u[0], h1 = S.u[2] - S.u[1];
-                    const double q = h0 / h1;
-                    S.Mx[0] = S.Mx[1] - q * (S.Mx[2] - S.Mx[1]);
-                    S.My[0] = S.My[1] - q * (S.My[2] - S.My[1]);
-                    const double hl = S.u[K - 1] - S.u[K - 2], hl2 = S.u[K - 2] - S.u[K - 3];
-                    const double ql = hl / hl2;
-                    S.Mx[K - 1] = S.Mx[K - 2] + ql * (S.Mx[K - 2] - S.Mx[K - 3]);
-                    S.My[K - 1] = S.My[K - 2] + ql * (S.My[K - 2] - S.My[K - 3]);
-                }
-            }
-        }
-        bad = __shfl_sync(FULL, badflag, 0) != 0;
-        __syncwarp();
+        bad = fit_spline_generic(S.sp, K, lane);               // spline_generic.cuh
         if (!bad) {
-            for (int i = lane; i < K - 1; i += 32) {
-                const double h = S.u[i + 1] - S.u[i], ih = 1.0 / h;
-                const double dxk = (S.X[i + 1] - S.X[i]) * ih, dyk = (S.Y[i + 1] - S.Y[i]) * ih;
-                double* c = S.piece[i];
-                c[0] = S.u[i + 1]; c[1] = S.u[i];
-                c[2] = S.X[i]; c[3] = dxk - h * (2.0 * S.Mx[i] + S.Mx[i + 1]) * (1.0 / 6.0);
-                c[4] = 0.5 * S.Mx[i]; c[5] = (S.Mx[i + 1] - S.Mx[i]) * ih * (1.0 / 6.0);
-                c[6] = S.Y[i]; c[7] = dyk - h * (2.0 * S.My[i] + S.My[i + 1]) * (1.0 / 6.0);
-                c[8] = 0.5 * S.My[i]; c[9] = (S.My[i + 1] - S.My[i]) * ih * (1.0 / 6.0);
-            }
-            __syncwarp();
             // 1000 points, 32 consecutive per lane (lane 31 re-draws 24 points of lane 30)
             const int j0 = min(lane * 32, GK_NPTS - 32);
             const double step = 1.0 / (double)(GK_NPTS - 1);
             int piece = 0;
             {
                 const double us = (double)j0 * step;
-                for (int k = 1; k <= K - 2; ++k) piece = (us >= S.u[k]) ? k : piece;
+                for (int k = 1; k <= K - 2; ++k) piece = (us >= S.sp.u[k]) ? k : piece;
             }
             int lowest = 0;
             for (int jj = 0; jj < 32; ++jj) {
                 const double uj = (double)(j0 + jj) * step;
-                while (piece < K - 2 && uj >= S.piece[piece][0]) ++piece;
-                const double* c = S.piece[piece];
+                while (piece < K - 2 && uj >= S.sp.piece[piece][0]) ++piece;
+                const double* c = S.sp.piece[piece];
                 const double sv = uj - c[1];
                 const double xv = fma(fma(fma(c[5], sv, c[4]), sv, c[3]), sv, c[2]);
                 const double yv = fma(fma(fma(c[9], sv, c[8]), sv, c[7]), sv, c[6]);
@@ -166,13 +89,13 @@ raster_generic_kernel(const T* __restrict__ contours, int64_t n, int K, int flag
             // fallback of contour_spline(): the raw points
             bool o = false;
             for (int k = lane; k < K; k += 32) {
-                const int ix = min(__double2int_rn(S.X[k]), 255), iy = min(__double2int_rn(S.Y[k]), 255);
+                const int ix = min(__double2int_rn(S.sp.X[k]), 255), iy = min(__double2int_rn(S.sp.Y[k]), 255);
                 o |= (ix < -256) | (iy < -256);
             }
             oob = __any_sync(FULL, o);
             if (!oob)
                 for (int k = lane; k < K; k += 32) {
-                    const int ix = min(__double2int_rn(S.X[k]), 255), iy = min(__double2int_rn(S.Y[k]), 255);
+                    const int ix = min(__double2int_rn(S.sp.X[k]), 255), iy = min(__double2int_rn(S.sp.Y[k]), 255);
                     atomicOr(&bmp[bmp_addr(iy & 255, (ix & 255) >> 5)], 1u << (ix & 31));
                 }
         }

@@ -15,6 +15,7 @@
 // with the reference to 1 fp32 ulp.
 #include "common.cuh"
 #include "spline.cuh"
+#include "spline_generic.cuh"
 
 namespace cub200 {
 
@@ -33,33 +34,8 @@ __device__ __forceinline__ void spline_der(const SplineScratch& sp, double x, do
 }
 
 // ---------------------------------------------------------------- U1: projected uncertainty, one warp per image
-// unc (n,21) fp32, proj (n,21,2) fp64, alpha_proj (n,21) fp32 (only with alpha)
-__global__ void __launch_bounds__(UM_WARPS * 32)
-projected_uncertainty_kernel(const float* __restrict__ mu, const float* __restrict__ cov, const float* __restrict__ alpha,
-                             int64_t n_img, int all_points, int linear_close, float* __restrict__ unc,
-                             double* __restrict__ proj, float* __restrict__ alpha_proj) {
-    __shared__ SplineScratch s_sp[UM_WARPS];
-    const int lane = lane_id(), wid = threadIdx.x >> 5;
-    const int64_t img = blockIdx.x * (int64_t)UM_WARPS + wid;
-    if (img >= n_img) return;
-    SplineScratch& sp = s_sp[wid];
-    double X = 0.0, Y = 0.0;
-    if (lane < KP) { X = mu[(img * KP + lane) * 2]; Y = mu[(img * KP + lane) * 2 + 1]; }
-    const bool bad = fit_spline(sp, X, Y, lane);            // splprep raises in the reference: outputs NaN
-    const double X0 = __shfl_sync(FULL, X, 0), Y0 = __shfl_sync(FULL, Y, 0);
-    const double X1 = __shfl_sync(FULL, X, 1), Y1 = __shfl_sync(FULL, Y, 1);
-    const double XL = __shfl_sync(FULL, X, KP - 1), YL = __shfl_sync(FULL, Y, KP - 1);
-    const double XM = __shfl_sync(FULL, X, KP - 2), YM = __shfl_sync(FULL, Y, KP - 2);
-    if (lane >= KP) return;
-    const int64_t o = img * KP + lane;
-    if (bad) {
-        const float qn = __int_as_float(0x7fc00000);
-        unc[o] = qn; proj[2 * o] = qn; proj[2 * o + 1] = qn;
-        if (alpha_proj) alpha_proj[o] = qn;
-        return;
-    }
-    // i = argmin |u - linspace(0, 1.01, 1000)| (first minimum), derivative there
-    const double u = sp.u[lane];
+// Parameter of the node of np.linspace(0, 1.01, 1000) nearest to u (first minimum of |u - unew|)   uncertainty_projection.py:32,47
+__device__ __forceinline__ double nearest_node_param(double u) {
     const double step = 1.01 / 999.0;
     int j = (int)floor(u / step);
     j = max(0, min(j - 1, 999));
@@ -69,8 +45,19 @@ projected_uncertainty_kernel(const float* __restrict__ mu, const float* __restri
         const double d = fabs(u - un);
         if (d < bestd) { bestd = d; bi = k; }
     }
-    double dx, dy;
-    spline_der(sp, (bi == 999) ? 1.01 : (double)bi * step, dx, dy);
+    return (bi == 999) ? 1.01 : (double)bi * step;
+}
+
+// first, second, last-but-one and last point of the contour (the straight-line closure of linear_close)
+struct EndPoints { double X0, Y0, X1, Y1, XM, YM, XL, YL; };
+
+// One landmark `pt` of a contour of `npts` points given the spline derivative (dx, dy) at its node: projection vector,
+// projected standard deviation (or the eigenvalue sum at the base / apex points), projected skewness.
+// o = flat index of the landmark in unc / proj / alpha_proj / cov / alpha.               uncertainty_projection.py:46-123
+__device__ __forceinline__ void project_point(int pt, int npts, int64_t o, double dx, double dy, const EndPoints& e,
+                                              const float* __restrict__ cov, const float* __restrict__ alpha, int all_points,
+                                              int linear_close, float* __restrict__ unc, double* __restrict__ proj,
+                                              float* __restrict__ alpha_proj) {
     const double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
     // v = flip(der / |der|), v[1] = -v[1]
     double vx = dy / nrm, vy = -(dx / nrm);
@@ -78,19 +65,19 @@ projected_uncertainty_kernel(const float* __restrict__ mu, const float* __restri
     const float* cv = cov + o * 4;
     const double xx = cv[0], xy = cv[1], yx = cv[2], yy = cv[3];
     float out_u;
-    if (!all_points && (lane == 0 || lane == KP / 2 || lane == KP - 1)) {
+    if (!all_points && (pt == 0 || pt == npts / 2 || pt == npts - 1)) {
         // sum of sqrt(eigenvalues) of the 2x2 covariance
         const double tr = xx + yy, det = xx * yy - xy * yx;
         const double disc = sqrt(fmax(tr * tr * 0.25 - det, 0.0));
         out_u = (float)(sqrt(tr * 0.5 + disc) + sqrt(tr * 0.5 - disc));
         if (alpha_proj) alpha_proj[o] = __int_as_float(0x7fc00000);
     } else {
-        if (linear_close && (lane == 0 || lane == KP - 1)) {
+        if (linear_close && (pt == 0 || pt == npts - 1)) {
             // the reference does this on its fp32 numpy `mu`: fp32 arithmetic throughout (uncertainty_projection.py:55-68)
-            const float x0 = (float)X0, y0 = (float)Y0, x1 = (float)X1, y1 = (float)Y1;
-            const float xl = (float)XL, yl = (float)YL, xm = (float)XM, ym = (float)YM;
+            const float x0 = (float)e.X0, y0 = (float)e.Y0, x1 = (float)e.X1, y1 = (float)e.Y1;
+            const float xl = (float)e.XL, yl = (float)e.YL, xm = (float)e.XM, ym = (float)e.YM;
             float ax, ay, bx, by;
-            if (lane == 0) { ax = __fsub_rn(x1, x0); ay = __fsub_rn(y1, y0); bx = __fsub_rn(xl, x0); by = __fsub_rn(yl, y0); }
+            if (pt == 0) { ax = __fsub_rn(x1, x0); ay = __fsub_rn(y1, y0); bx = __fsub_rn(xl, x0); by = __fsub_rn(yl, y0); }
             else { ax = __fsub_rn(xl, xm); ay = __fsub_rn(yl, ym); bx = __fsub_rn(xl, x0); by = __fsub_rn(yl, y0); }
             const float na = sqrtf(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
             const float nb = sqrtf(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)));
@@ -120,6 +107,66 @@ projected_uncertainty_kernel(const float* __restrict__ mu, const float* __restri
     unc[o] = out_u;
     proj[2 * o] = vx;
     proj[2 * o + 1] = vy;
+}
+
+// unc (n,21) fp32, proj (n,21,2) fp64, alpha_proj (n,21) fp32 (only with alpha)
+__global__ void __launch_bounds__(UM_WARPS * 32)
+projected_uncertainty_kernel(const float* __restrict__ mu, const float* __restrict__ cov, const float* __restrict__ alpha,
+                             int64_t n_img, int all_points, int linear_close, float* __restrict__ unc,
+                             double* __restrict__ proj, float* __restrict__ alpha_proj) {
+    __shared__ SplineScratch s_sp[UM_WARPS];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int64_t img = blockIdx.x * (int64_t)UM_WARPS + wid;
+    if (img >= n_img) return;
+    SplineScratch& sp = s_sp[wid];
+    double X = 0.0, Y = 0.0;
+    if (lane < KP) { X = mu[(img * KP + lane) * 2]; Y = mu[(img * KP + lane) * 2 + 1]; }
+    const bool bad = fit_spline(sp, X, Y, lane);            // splprep raises in the reference: outputs NaN
+    EndPoints e;
+    e.X0 = __shfl_sync(FULL, X, 0); e.Y0 = __shfl_sync(FULL, Y, 0);
+    e.X1 = __shfl_sync(FULL, X, 1); e.Y1 = __shfl_sync(FULL, Y, 1);
+    e.XL = __shfl_sync(FULL, X, KP - 1); e.YL = __shfl_sync(FULL, Y, KP - 1);
+    e.XM = __shfl_sync(FULL, X, KP - 2); e.YM = __shfl_sync(FULL, Y, KP - 2);
+    if (lane >= KP) return;
+    const int64_t o = img * KP + lane;
+    if (bad) {
+        const float qn = __int_as_float(0x7fc00000);
+        unc[o] = qn; proj[2 * o] = qn; proj[2 * o + 1] = qn;
+        if (alpha_proj) alpha_proj[o] = qn;
+        return;
+    }
+    double dx, dy;
+    spline_der(sp, nearest_node_param(sp.u[lane]), dx, dy);
+    project_point(lane, KP, o, dx, dy, e, cov, alpha, all_points, linear_close, unc, proj, alpha_proj);
+}
+
+// The same for contours of any size (4 <= npts <= 64: the lung / heart contours of LungUMap, cu/data/lung/utils.py:72-114):
+// one warp per contour, spline_generic.cuh, lanes stride over the landmarks.
+__global__ void __launch_bounds__(UM_WARPS * 32)
+projected_uncertainty_generic_kernel(const float* __restrict__ mu, const float* __restrict__ cov, const float* __restrict__ alpha,
+                                     int64_t n_img, int npts, int all_points, int linear_close, float* __restrict__ unc,
+                                     double* __restrict__ proj, float* __restrict__ alpha_proj) {
+    extern __shared__ __align__(16) unsigned char um_smem[];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int64_t img = blockIdx.x * (int64_t)UM_WARPS + wid;
+    if (img >= n_img) return;
+    GenericSpline& S = reinterpret_cast<GenericSpline*>(um_smem)[wid];
+    for (int k = lane; k < npts; k += 32) { S.X[k] = mu[(img * npts + k) * 2]; S.Y[k] = mu[(img * npts + k) * 2 + 1]; }
+    __syncwarp();
+    const bool bad = fit_spline_generic(S, npts, lane);
+    const EndPoints e = {S.X[0], S.Y[0], S.X[1], S.Y[1], S.X[npts - 2], S.Y[npts - 2], S.X[npts - 1], S.Y[npts - 1]};
+    for (int k = lane; k < npts; k += 32) {
+        const int64_t o = img * npts + k;
+        if (bad) {
+            const float qn = __int_as_float(0x7fc00000);
+            unc[o] = qn; proj[2 * o] = qn; proj[2 * o + 1] = qn;
+            if (alpha_proj) alpha_proj[o] = qn;
+            continue;
+        }
+        double dx, dy;
+        spline_der_generic(S, npts, nearest_node_param(S.u[k]), dx, dy);
+        project_point(k, npts, o, dx, dy, e, cov, alpha, all_points, linear_close, unc, proj, alpha_proj);
+    }
 }
 
 // ---------------------------------------------------------------- U2: uncertainty_map, one warp per (image, offset)
@@ -210,17 +257,17 @@ umap_finalize_kernel(const int32_t* __restrict__ kmap, const double* __restrict_
 }
 
 // ---------------------------------------------------------------- U3: skew_umap level contours, one warp per (image, point)
-// contours (n, 200, 21, 2) fp64, mode (n, 21, 2) fp32
+// contours (n, 200, npts, 2) fp64, mode (n, npts, 2) fp32
 __global__ void __launch_bounds__(UM_WARPS * 32)
 skew_umap_contours_kernel(const float* __restrict__ mu, const float* __restrict__ unc, const double* __restrict__ proj,
-                          const float* __restrict__ alpha_proj, int64_t n_img, double* __restrict__ contours,
+                          const float* __restrict__ alpha_proj, int64_t n_img, int npts, double* __restrict__ contours,
                           float* __restrict__ mode) {
     __shared__ double s_y[UM_WARPS][1000];
     const int lane = lane_id(), wid = threadIdx.x >> 5;
     const int64_t g = blockIdx.x * (int64_t)UM_WARPS + wid;
-    if (g >= n_img * KP) return;
-    const int64_t img = g / KP;
-    const int pt = (int)(g % KP);
+    if (g >= n_img * npts) return;
+    const int64_t img = g / npts;
+    const int pt = (int)(g % npts);
     double* y = s_y[wid];
     const float uf = unc[g];
     const double u = uf, a = alpha_proj[g];
@@ -229,12 +276,14 @@ skew_umap_contours_kernel(const float* __restrict__ mu, const float* __restrict_
     // p1 = mu + v u cov_width, p2 = mu - v u cov_width   (cov_width = 2)
     const double ox = __dmul_rn(__dmul_rn(vx, u), 2.0), oy = __dmul_rn(__dmul_rn(vy, u), 2.0);
     const double p1x = __dadd_rn(mx, ox), p1y = __dadd_rn(my, oy), p2x = __dsub_rn(mx, ox), p2y = __dsub_rn(my, oy);
-    // x = np.linspace(-3u, 3u, 1000) with -3u, 3u formed in fp32; y = skewnorm.pdf(x, a, 0, u)
-    const double start = (double)__fmul_rn(-3.0f, uf), stop = (double)__fmul_rn(3.0f, uf);
-    const double step = (stop - start) / 999.0;
+    // x = np.linspace(-3u, 3u, 1000) is a FLOAT32 array in the reference (u is a float32 numpy scalar): step = fl(fl(stop -
+    // start) / 999), x_j = fl(fl(j step) + start), x_999 = stop.  scipy then forms (x - 0) / u in fp64.  The fp32 rounding of
+    // x decides the arg-max between the two centre samples of a symmetric law (alpha = 0: LungUMap), hence every level index.
+    const float start = __fmul_rn(-3.0f, uf), stop = __fmul_rn(3.0f, uf);
+    const float step = __fdiv_rn(__fsub_rn(stop, start), 999.0f);
     double ymax = -1.0; int am = 0x7fffffff;
     for (int j = lane; j < 1000; j += 32) {
-        const double x = (j == 999) ? stop : __dadd_rn(__dmul_rn((double)j, step), start);
+        const double x = (double)((j == 999) ? stop : __fadd_rn(__fmul_rn((float)j, step), start));
         const double t = x / u;
         const double pdf = exp(-(t * t) / 2.0) / 2.5066282746310002;
         const double v = (a == 0.0 ? pdf : 2.0 * pdf * normcdf(a * t)) / u;
@@ -275,8 +324,8 @@ skew_umap_contours_kernel(const float* __restrict__ mu, const float* __restrict_
             // an empty side makes np.argmin raise in the reference: NaN here
             const double qn = __longlong_as_double(0x7ff8000000000000LL);
             const double tp = nr > 0 ? (double)(bi + am) / 1000.0 : qn, tm = nl > 0 ? (double)ci / 1000.0 : qn;
-            double* cm = contours + ((img * 200 + (99 - i)) * KP + pt) * 2;      // umap_contours[N - i - 1]
-            double* cp = contours + ((img * 200 + (100 + i)) * KP + pt) * 2;     // umap_contours[N + i]
+            double* cm = contours + ((img * 200 + (99 - i)) * npts + pt) * 2;      // umap_contours[N - i - 1]
+            double* cp = contours + ((img * 200 + (100 + i)) * npts + pt) * 2;     // umap_contours[N + i]
             cm[0] = __dadd_rn(__dmul_rn(p1x, tm), __dmul_rn(1.0 - tm, p2x));
             cm[1] = __dadd_rn(__dmul_rn(p1y, tm), __dmul_rn(1.0 - tm, p2y));
             cp[0] = __dadd_rn(__dmul_rn(p1x, tp), __dmul_rn(1.0 - tp, p2x));
@@ -411,14 +460,29 @@ extern "C" int cub200_umap_analytic(const float* mu, const float* unc, const dou
     return check_launch("umap_finalize_kernel");
 }
 
-extern "C" int cub200_skew_umap_contours(const float* mu, const float* unc, const double* proj, const float* alpha_proj,
-                                         int64_t n_img, double* contours_out, float* mode_out, void* stream) {
+extern "C" int cub200_projected_uncertainty_generic(const float* mu, const float* cov, const float* alpha, int64_t n_img,
+                                                    int n_points, int all_points, int linear_close, float* unc_out,
+                                                    double* proj_out, float* alpha_proj_out, void* stream) {
     using namespace cub200;
     if (n_img == 0) return 0;
-    if (!mu || !unc || !proj || !alpha_proj || !contours_out || !mode_out || n_img < 0) return CUB200_EINVAL;
-    const int64_t n = n_img * KP;
+    if (!mu || !cov || !unc_out || !proj_out || n_img < 0 || (alpha && !alpha_proj_out) || n_points < 4 || n_points > GS_MAX)
+        return CUB200_EINVAL;
+    const int smem = UM_WARPS * (int)sizeof(GenericSpline);
+    CUB200_CUDA_OK(cudaFuncSetAttribute(projected_uncertainty_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    projected_uncertainty_generic_kernel<<<(unsigned)((n_img + UM_WARPS - 1) / UM_WARPS), UM_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        mu, cov, alpha, n_img, n_points, all_points, linear_close, unc_out, proj_out, alpha ? alpha_proj_out : nullptr);
+    return check_launch("projected_uncertainty_generic_kernel");
+}
+
+extern "C" int cub200_skew_umap_contours(const float* mu, const float* unc, const double* proj, const float* alpha_proj,
+                                         int64_t n_img, int n_points, double* contours_out, float* mode_out, void* stream) {
+    using namespace cub200;
+    if (n_img == 0) return 0;
+    if (!mu || !unc || !proj || !alpha_proj || !contours_out || !mode_out || n_img < 0 || n_points < 1 || n_points > GS_MAX)
+        return CUB200_EINVAL;
+    const int64_t n = n_img * n_points;
     skew_umap_contours_kernel<<<(unsigned)((n + UM_WARPS - 1) / UM_WARPS), UM_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        mu, unc, proj, alpha_proj, n_img, contours_out, mode_out);
+        mu, unc, proj, alpha_proj, n_img, n_points, contours_out, mode_out);
     return check_launch("skew_umap_contours_kernel");
 }
 

@@ -1,12 +1,14 @@
-"""Mirror of contour_uncertainty/data/lung/utils.py::LungContourToMask: three structures of 44 / 50 / 26 points, each
-rasterised by reconstruction() / linear_reconstruction() on the GPU (the generic-size rasteriser)."""
+"""Mirror of contour_uncertainty/data/lung/utils.py: LungContourToMask (three structures of 44 / 50 / 26 points, each
+rasterised by reconstruction() / linear_reconstruction() on the GPU, the generic-size rasteriser) and LungUMap /
+LungSkewUmap (skew_umap per structure, each map divided by its maximum, summed and clipped to [0, 1])."""
 from typing import Literal
 
 import numpy as np
 import torch
 
 from ... import engine as E
-from ..utils import ContourToMask
+from ...utils.skew_umap import skew_umap
+from ..utils import ContourToMask, SkewUMap, UMap
 from .config import HEART, LLUNG, RLUNG, Label
 
 
@@ -42,3 +44,35 @@ class LungContourToMask(ContourToMask):
         seg[:, Label.BG] = (seg.sum(1) == 0).to(torch.int64)
         out = (seg.argmax(1) if apply_argmax else seg).cpu().numpy()
         return out[0] if single else out
+
+
+def _structure_umaps(mu, cov, alpha):
+    """skew_umap of the three structures (lung/utils.py:75-81, 96-102): [(projected_mode, umap)] * 3."""
+    mu, cov, alpha = (np.asarray(a) for a in (mu, cov, alpha))
+    return [skew_umap(m, c, a) for m, c, a in zip(split_landmarks(mu), _split_cov(cov), split_landmarks(alpha))]
+
+
+def _split_cov(cov):
+    p1, p2, p3 = RLUNG, RLUNG + LLUNG, RLUNG + LLUNG + HEART
+    return cov[:p1], cov[p1:p2], cov[p2:p3]
+
+
+def _combine(umaps):
+    """np.clip(rl / rl.max() + ll / ll.max() + h / h.max(), 0, 1) (lung/utils.py:83, 104)."""
+    return np.clip(umaps[0] / umaps[0].max() + umaps[1] / umaps[1].max() + umaps[2] / umaps[2].max(), a_min=0, a_max=1)
+
+
+class LungUMap(UMap):
+    @staticmethod
+    def __call__(mu, cov, labels=None):
+        """lung/utils.py:72-92: mu (120, 2), cov (120, 2, 2) -> (256, 256) float64."""
+        mu = np.asarray(mu)
+        return _combine([u for _, u in _structure_umaps(mu, cov, np.zeros_like(mu))])
+
+
+class LungSkewUmap(SkewUMap):
+    @staticmethod
+    def __call__(mu, cov, alpha, labels=None):
+        """lung/utils.py:95-114: -> (projected_mode (120, 2), umap (256, 256) float64)."""
+        parts = _structure_umaps(mu, cov, alpha)
+        return np.concatenate([m for m, _ in parts], axis=0), _combine([u for _, u in parts])

@@ -844,24 +844,29 @@ SKEW_UMAP_WEIGHT_SUM = float(np.broadcast_to(SKEW_UMAP_WEIGHTS, (1, 1, 200)).swa
 
 def projected_uncertainty(mu: torch.Tensor, cov: torch.Tensor, alpha: Optional[torch.Tensor] = None, all: bool = False,
                           linear_close: bool = False):
-    """cu/utils/uncertainty_projection.py:17-125 for a batch: mu (N,21,2), cov (N,21,2,2) [, alpha (N,21,2)] fp32 ->
-    (uncertainties (N,21) fp32, projections (N,21,2) fp64 [, alpha_proj (N,21) fp32])."""
+    """cu/utils/uncertainty_projection.py:17-125 for a batch: mu (N,P,2), cov (N,P,2,2) [, alpha (N,P,2)] fp32 ->
+    (uncertainties (N,P) fp32, projections (N,P,2) fp64 [, alpha_proj (N,P) fp32]).  P = 21 (the LV contour of the hot path) or
+    any 4 <= P <= 64 (the lung / heart contours of cu/data/lung/utils.py)."""
     mu = nat.require_cuda(mu, torch.float32, "mu")
     cov = nat.require_cuda(cov, torch.float32, "cov")
-    if mu.dim() != 3 or mu.shape[1:] != (K, 2) or tuple(cov.shape) != tuple(mu.shape) + (2,):
-        raise ValueError("mu (N,21,2) / cov (N,21,2,2) expected")
-    n, dev = mu.shape[0], mu.device
+    if mu.dim() != 3 or mu.shape[2] != 2 or not (4 <= mu.shape[1] <= RASTER_MAX_POINTS) or tuple(cov.shape) != tuple(mu.shape) + (2,):
+        raise ValueError(f"mu (N,P,2) / cov (N,P,2,2) with 4 <= P <= {RASTER_MAX_POINTS} expected")
+    n, p, dev = mu.shape[0], int(mu.shape[1]), mu.device
     ap = None
     if alpha is not None:
         alpha = nat.require_cuda(alpha, torch.float32, "alpha")
         if alpha.shape != mu.shape:
-            raise ValueError("alpha must be (N,21,2)")
-        ap = torch.empty((n, K), dtype=torch.float32, device=dev)
-    unc = torch.empty((n, K), dtype=torch.float32, device=dev)
-    proj = torch.empty((n, K, 2), dtype=torch.float64, device=dev)
+            raise ValueError("alpha must have the shape of mu")
+        ap = torch.empty((n, p), dtype=torch.float32, device=dev)
+    unc = torch.empty((n, p), dtype=torch.float32, device=dev)
+    proj = torch.empty((n, p, 2), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        rc = nat.lib().cub200_projected_uncertainty(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, int(all), int(linear_close),
-                                                    nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), nat.stream_ptr(dev))
+        if p == K:
+            rc = nat.lib().cub200_projected_uncertainty(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, int(all), int(linear_close),
+                                                        nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), nat.stream_ptr(dev))
+        else:
+            rc = nat.lib().cub200_projected_uncertainty_generic(nat.ptr(mu), nat.ptr(cov), nat.ptr(alpha), n, p, int(all), int(linear_close),
+                                                                nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), nat.stream_ptr(dev))
     nat.check(rc, "cub200_projected_uncertainty")
     return (unc, proj) if alpha is None else (unc, proj, ap)
 
@@ -883,18 +888,22 @@ def umap_analytic(mu: torch.Tensor, cov: torch.Tensor, normalize: bool = True) -
 
 def skew_umap(mu: torch.Tensor, cov: torch.Tensor, alpha: torch.Tensor, linear_close: bool = True, normalize: bool = True,
               return_contours: bool = False):
-    """skew_umap (cu/utils/skew_umap.py:11-82) [USSkewUmap: linear_close=True, / max]: -> (projected_mode (N,21,2) fp32,
-    umap (N,256,256) fp64).  200 level contours per image are reconstructed (unrounded, fp64) by the rasteriser."""
+    """skew_umap (cu/utils/skew_umap.py:11-82) [USSkewUmap: linear_close=True, / max]: -> (projected_mode (N,P,2) fp32,
+    umap (N,256,256) fp64).  200 level contours per image are reconstructed (unrounded, fp64) by the rasteriser.
+    P = 21, or any 4 <= P <= 64 (LungUMap / LungSkewUmap call it per structure with 44, 50 and 26 points)."""
     unc, proj, ap = projected_uncertainty(mu, cov, alpha, all=True, linear_close=linear_close)
     mu = nat.require_cuda(mu, torch.float32, "mu")
-    n, dev = mu.shape[0], mu.device
-    contours = torch.empty((n, 200, K, 2), dtype=torch.float64, device=dev)
-    mode = torch.empty((n, K, 2), dtype=torch.float32, device=dev)
+    n, p, dev = mu.shape[0], int(mu.shape[1]), mu.device
+    contours = torch.empty((n, 200, p, 2), dtype=torch.float64, device=dev)
+    mode = torch.empty((n, p, 2), dtype=torch.float32, device=dev)
     L = nat.lib()
     with torch.cuda.device(dev):
-        nat.check(L.cub200_skew_umap_contours(nat.ptr(mu), nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), n, nat.ptr(contours),
+        nat.check(L.cub200_skew_umap_contours(nat.ptr(mu), nat.ptr(unc), nat.ptr(proj), nat.ptr(ap), n, p, nat.ptr(contours),
                                               nat.ptr(mode), nat.stream_ptr(dev)), "cub200_skew_umap_contours")
-    masks, _ = rasterize_contours(contours.reshape(-1, K, 2), round_landmarks=False, return_masks=True)
+    if p == K:
+        masks, _ = rasterize_contours(contours.reshape(-1, K, 2), round_landmarks=False, return_masks=True)
+    else:
+        masks, _ = rasterize_contours_generic(contours.reshape(-1, p, 2), round_landmarks=False, return_masks=True)
     w = torch.from_numpy(SKEW_UMAP_WEIGHTS).to(dev)
     out = torch.empty((n, HW, HW), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):

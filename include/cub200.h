@@ -391,6 +391,11 @@ int cub200_simpson_volumes(const double* diam, const double* step, int64_t n_pat
  */
 int cub200_projected_uncertainty(const float* mu, const float* cov, const float* alpha, int64_t n_img, int all_points,
                                  int linear_close, float* unc_out, double* proj_out, float* alpha_proj_out, void* stream);
+/* The same for contours of n_points landmarks, 4 <= n_points <= CUB200_RASTER_MAX_POINTS (the 44 / 50 / 26-point lung and
+ * heart contours of LungUMap / LungSkewUmap, cu/data/lung/utils.py:72-114; base / apex points 0, n_points / 2, n_points - 1). */
+int cub200_projected_uncertainty_generic(const float* mu, const float* cov, const float* alpha, int64_t n_img, int n_points,
+                                         int all_points, int linear_close, float* unc_out, double* proj_out,
+                                         float* alpha_proj_out, void* stream);
 
 /*
  * Analytic uncertainty map: 100 offset contours mu + v u i, i = linspace(-2, 2, 100); a pixel takes the pdf value
@@ -407,11 +412,12 @@ int cub200_umap_analytic(const float* mu, const float* unc, const double* proj, 
  * Skew u-map, step 1: per landmark the projected skew-normal on a 1000-point axis, its mode and the 2 x 100 level
  * offsets -> 200 level contours per image.
  *   replaces  skew_umap lines 13-58   cu/utils/skew_umap.py
- *   unc, proj, alpha_proj from cub200_projected_uncertainty(alpha, all_points = 1, linear_close as wanted)
- *   contours_out (n_img,200,21,2) fp64; mode_out (n_img,21,2) fp32 (projected_mode)
+ *   unc, proj, alpha_proj from cub200_projected_uncertainty[_generic](alpha, all_points = 1, linear_close as wanted)
+ *   n_points landmarks per contour (21 for the LV; 1..CUB200_RASTER_MAX_POINTS)
+ *   contours_out (n_img,200,n_points,2) fp64; mode_out (n_img,n_points,2) fp32 (projected_mode)
  */
 int cub200_skew_umap_contours(const float* mu, const float* unc, const double* proj, const float* alpha_proj,
-                              int64_t n_img, double* contours_out, float* mode_out, void* stream);
+                              int64_t n_img, int n_points, double* contours_out, float* mode_out, void* stream);
 
 /*
  * Skew u-map, step 2: weighted mean of bit-packed masks -> natural-log binary entropy (scipy.stats.entropy), optionally

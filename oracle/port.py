@@ -1418,6 +1418,19 @@ def lung_contour_to_mask(landmarks: np.ndarray, apply_argmax: bool = True, recon
     return seg.argmax(0) if apply_argmax else seg
 
 
+def lung_skew_umap(mu, cov, alpha):
+    """cu/data/lung/utils.py:95-114 (LungSkewUmap; LungUMap :72-92 is the same with alpha = 0): skew_umap of the right lung
+    (44 points), left lung (50) and heart (26), each divided by its maximum, summed and clipped to [0, 1].
+    Returns (projected_mode (120, 2), umap (256, 256))."""
+    mu, cov, alpha = np.asarray(mu), np.asarray(cov), np.asarray(alpha)
+    modes, total = [], 0
+    for a, b in ((0, 44), (44, 94), (94, 120)):
+        mode, um = skew_umap(mu[a:b], cov[a:b], alpha[a:b])
+        modes.append(mode)
+        total = total + um / um.max()
+    return np.concatenate(modes, axis=0), np.clip(total, a_min=0, a_max=1)
+
+
 # --------------------------------------------------------------------------------------------------
 # Two-structure (LV + MYO) masks (SURVEY.md 8f-3): USContourToMask with Label.MYO among the labels
 # --------------------------------------------------------------------------------------------------

@@ -417,6 +417,37 @@ def golden_umap():
     print("umap.npz", {k: np.asarray(v).shape for k, v in out.items() if not k[-1].isdigit()}, "value", VAL)
 
 
+def lung_point_laws(n, seed):
+    """(mu (n,120,2), cov (n,120,2,2), alpha (n,120,2)) fp32 for the lung u-maps."""
+    rng = np.random.default_rng(seed)
+    mu = synth.lung_landmarks(n, seed=seed).astype(np.float32)
+    cov = np.array([synth.random_spd(rng, 120, 2.0, 20.0) for _ in range(n)]).astype(np.float32)
+    alpha = rng.normal(0, 2.0, (n, 120, 2)).astype(np.float32)
+    return mu, cov, alpha
+
+
+def golden_lung_umap():
+    """LungUMap / LungSkewUmap (contour_uncertainty/data/lung/utils.py:72-114) executed as they are: skew_umap per structure
+    (44 / 50 / 26 points), each / max, summed, clipped.  Maps are stored sparsely (indices + values)."""
+    from contour_uncertainty.data.lung.utils import LungSkewUmap, LungUMap
+
+    n = 2
+    mu, cov, alpha = lung_point_laws(n, seed=131)
+    out = dict(mu=mu, cov=cov, alpha=alpha)
+    modes = []
+    for i in range(n):
+        um = LungUMap.__call__(mu[i], cov[i])
+        mode, sk = LungSkewUmap.__call__(mu[i], cov[i], alpha[i])
+        modes.append(mode)
+        for name, m in (("umap", um), ("skew_umap", sk)):
+            idx = np.flatnonzero(m)
+            out[f"{name}_idx_{i}"] = idx.astype(np.int32)
+            out[f"{name}_val_{i}"] = m.reshape(-1)[idx]
+    out["mode"] = np.array(modes)
+    np.savez_compressed(os.path.join(HERE, "lung_umap.npz"), **out)
+    print("lung_umap.npz", out["mode"].shape, [len(out[f"umap_idx_{i}"]) for i in range(n)])
+
+
 def golden_seqskew():
     """SequenceSkewPSMSampler.__call__ (psm_skew_sequence.py) with first-instant bits, rvs_fast normals and the
     31 multinomial races per sample replayed; fp32 and fp64 runs of the unmodified code."""
@@ -1090,6 +1121,6 @@ def golden_class_entropy():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics", "myo_task", "psm_alpha", "glsmyo"]
+    which = sys.argv[1:] or ["dsnt", "raster", "psm", "naive", "maps", "seq", "skew", "simpson", "umap", "seqskew", "calibration", "gls", "distributions", "segpost", "glsmask", "generic", "dataset_calibration", "myo", "class_entropy", "task_al", "task_skew", "metrics", "myo_task", "psm_alpha", "glsmyo", "lung_umap"]
     for w in which:
         globals()["golden_" + w]()

@@ -83,7 +83,8 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_seq_skew_sample(*([None] * 12), 0, 1, 1, None, None, None) == E
     assert l.cub200_projected_uncertainty(None, None, None, 1, 1, 0, None, None, None, None) == E
     assert l.cub200_umap_analytic(None, None, None, 1, None, 1, None, None, None) == E
-    assert l.cub200_skew_umap_contours(None, None, None, None, 1, None, None, None) == E
+    assert l.cub200_skew_umap_contours(None, None, None, None, 1, 21, None, None, None) == E
+    assert l.cub200_projected_uncertainty_generic(None, None, None, 1, 44, 1, 0, None, None, None, None) == E
     assert l.cub200_weighted_mask_entropy(None, None, 1, 200, 1.0, 1, None, None) == E
     assert l.cub200_simpson_diameters(None, 1, 0.5, None, None, None, None, None) == E
     assert l.cub200_simpson_volumes(None, None, 1, 1, None, None, None, None) == E

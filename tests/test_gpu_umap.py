@@ -97,3 +97,33 @@ def test_skew_umap_vs_reference_and_oracle(dev):
     mo, co, w = port.skew_umap_contours(g["mu"][0], g["cov"][0], g["alpha"][0], linear_close=True)
     assert np.abs(contours[0].cpu().numpy() - co).max() < 2e-5
     assert np.allclose(w, E.SKEW_UMAP_WEIGHTS, rtol=0, atol=0)
+
+
+def test_lung_umaps_vs_reference(dev):
+    """LungUMap / LungSkewUmap (cu/data/lung/utils.py:72-114, executed reference): the general-size projected uncertainty
+    (44 / 50 / 26-point splines), level contours, generic rasteriser and weighted entropy."""
+    from contouring_uncertainty_b200 import engine as E
+    from contouring_uncertainty_b200.data.lung.utils import LungSkewUmap, LungUMap
+
+    g = np.load(os.path.join(G, "lung_umap.npz"))
+    for i in range(2):
+        mu, cov, al = g["mu"][i], g["cov"][i], g["alpha"][i]
+        mode, sk = LungSkewUmap.__call__(mu, cov, al)
+        assert mode.shape == (120, 2) and np.abs(mode - g["mode"][i]).max() < 1e-4
+        # 1 fp32 ulp of a projected deviation (the reference rotates covariances in fp32 torch) can flip a pixel of ONE of the
+        # 200 level masks: <= 4 pixels may differ, by one mask's weight (< 1e-3)
+        d = np.abs(sk - _sparse_map(g, "skew_umap", i))
+        assert (d > 1e-12).sum() <= 4 and d.max() < 1e-3
+        um = LungUMap.__call__(mu, cov)
+        d = np.abs(um - _sparse_map(g, "umap", i))
+        assert (d > 1e-12).sum() <= 4 and d.max() < 1e-3 and um.max() <= 1.0
+    # the general-size kernel on 21 points = the specialised one (different solver: cyclic reduction vs Thomas)
+    mus, covs, als, tm, tc, ta = _inputs(dev, 3, 212)
+    u, v, ap = E.projected_uncertainty(tm, tc, ta, all=True, linear_close=True)
+    L = E.nat.lib()
+    u2, v2, ap2 = torch.empty_like(u), torch.empty_like(v), torch.empty_like(ap)
+    E.nat.check(L.cub200_projected_uncertainty_generic(tm.data_ptr(), tc.data_ptr(), ta.data_ptr(), 3, 21, 1, 1, u2.data_ptr(), v2.data_ptr(),
+                                                       ap2.data_ptr(), None), "generic")
+    torch.cuda.synchronize()
+    assert (u - u2).abs().max().item() <= 1e-6 * u.abs().max().item() and (v - v2).abs().max().item() < 1e-9
+    assert (ap - ap2).abs().max().item() < 1e-5

@@ -492,3 +492,17 @@ def test_endo_base_gls_matches_reference():
     assert raised == 2
     for (a, b), gl in zip(g["pairs"], g["gls"]):
         assert port.echo_gls_myo(np.stack([maps[a], maps[b]]), (0.7, 0.4))[1] == gl
+
+
+def test_lung_umaps_match_reference():
+    """LungUMap / LungSkewUmap (cu/data/lung/utils.py:72-114) executed verbatim: skew_umap on 44 / 50 / 26-point contours."""
+    g = np.load(os.path.join(G, "lung_umap.npz"))
+    i = 0
+    mu, cov, al = g["mu"][i], g["cov"][i], g["alpha"][i]
+    mode, sk = port.lung_skew_umap(mu, cov, al)
+    assert np.abs(mode - g["mode"][i]).max() < 1e-4 and (np.abs(sk - _sparse_map(g, "skew_umap", i)) > 1e-12).sum() == 0
+    _, um = port.lung_skew_umap(mu, cov, np.zeros_like(mu))
+    # the reference rotates the covariances in fp32 torch; the oracle forms the fp64 value and rounds once: a 1-ulp (fp32)
+    # difference of a projected deviation moves one level contour by ~1e-6 px, which can flip a pixel of ONE of the 200 masks
+    d = np.abs(um - _sparse_map(g, "umap", i))
+    assert (d > 1e-12).sum() <= 4 and d.max() < 1e-3
