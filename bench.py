@@ -310,23 +310,43 @@ class LogitsPSM(PathConfig):
         self.id = cfg
         self.n, self.T, sampler = (1, 100, "naive") if cfg == 1 else (64, 1000, "psm")
         self.eng = E.UncertaintyEngine(device=dev, sampler=sampler)
-        self.logits = make_logits_on_device(torch, dev, self.n, seed=1000 + cfg + rank)
+        # A rank cycles through POOL distinct batches (a predict epoch never sees the same images twice in a row); every rank
+        # holds the same pool and starts at its own phase, so over any POOL steps all ranks have done the same work.  (With one
+        # fixed batch per rank the max-over-ranks time measures which rank drew the heaviest 64 images -- the rasteriser's time
+        # varies by ~5 % between batches, tools/shard_weight.py -- not the system: profiles/r02d_scaling_attribution.txt.)
+        self.pool = [make_logits_on_device(torch, dev, self.n, seed=1000 + cfg + b) for b in range(self.POOL)]
+        self.logits = self.pool[0]
         self.ws = self.eng.workspace(self.n, self.T)
         self.sums = torch.empty((2,), dtype=torch.int64, device=dev)
+
+    POOL = 8
+    gs = None
 
     def contours_per_step(self):
         return self.n * self.T
 
+    def enable_graph(self, exch):
+        """The step (+ the metric buffering of the exchange) as ONE CUDA-graph launch per step: one engine.GraphedStep per
+        input batch of the pool, all advancing the same device-side step counter."""
+        ring = exch.ring if exch is not None else None
+        first = self.E.GraphedStep(self.eng, self.ws, self.pool[0], seed=1000, metric_ring=ring)
+        self.gs = [first] + [self.E.GraphedStep(self.eng, self.ws, lg, seed=1000, metric_ring=ring, step=first.step) for lg in self.pool[1:]]
+
     def step(self, i):
-        self.eng.run_into(self.ws, self.logits, seed=1000 + i)
+        b = (i + self.rank) % self.POOL
+        if self.gs is not None:
+            self.gs[b].replay()
+        else:
+            self.eng.run_into(self.ws, self.pool[b], seed=1000 + i)
 
     def metric_values(self):
         return self.ws.area, self.E.metric_sums(self.ws.area, out=self.sums)
 
     def step_evented(self, i, tm):
         E, ws = self.E, self.ws
+        logits = self.pool[(i + self.rank) % self.POOL]
         tm.mark("start")
-        _, mu, cov = E.dsnt_moments(self.logits, is_logit=True, covar=True)
+        _, mu, cov = E.dsnt_moments(logits, is_logit=True, covar=True)
         tm.mark("dsnt")
         a_t = self.eng.factor(mu, cov)
         tm.mark("factor")
@@ -654,12 +674,20 @@ def run_ours(args):
 
     every = args.exchange_every if args.exchange_every > 0 else args.steps
     vals0, _ = (cfg.step(0), cfg.metric_values())[1]
-    exch = PAR.MetricExchange(vals0.shape[0], vals0.shape[1], every, dev) if world > 1 else None
+    exch = PAR.MetricExchange(vals0.shape[0], vals0.shape[1], every, dev) if (world > 1 or args.force_exchange) else None
+    graphed = cfg_id in (1, 2) and not args.no_graph      # sub-millisecond steps: one graph launch instead of 8-12 launches
+    if graphed:
+        cfg.enable_graph(exch)
 
     def step(i):
-        cfg.step(i)
-        if exch is not None:
-            exch.push(*cfg.metric_values())
+        if exch is not None and graphed:
+            exch.prepare()                                # a ring block being reused must have left the wire
+            cfg.step(i)                                   # the graph writes the step's slot itself (device-side step counter)
+            exch.note_pushed()
+        else:
+            cfg.step(i)
+            if exch is not None:
+                exch.push(cfg.metric_values()[0])
 
     def sync_all():
         if world > 1:
@@ -673,35 +701,50 @@ def run_ours(args):
         clocks.start()
         t_wait = time.time()
         while len(clocks.lines) < 3 and time.time() - t_wait < 5.0 and clocks.proc is not None:
-            cfg.step(0)                               # local work only: no collective outside lock-step
+            cfg.eng.run_into(cfg.ws, cfg.logits, seed=0) if cfg_id in (1, 2) else cfg.step(0)   # local work only: no collective outside lock-step
             torch.cuda.synchronize(dev)
     for i in range(args.warmup):
         step(i)
+    collectives0 = 0
     if exch is not None:
-        exch.finish()
-        exch = PAR.MetricExchange(vals0.shape[0], vals0.shape[1], every, dev)
+        exch.finish()                                     # flush the warm-up block; the timed run starts on a fresh block
+        collectives0 = exch.collectives
+        if graphed:
+            cfg.gs[0].resync(exch.slot_index(), exch.ring.shape[0])
     sync_all()
     t0, t1 = ev(), ev()
     launches0 = E.nat.lib().cub200_launch_count()
     t0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
+    t_mid = ev()
+    t_mid.record(stream)                     # end of this rank's own steps; what follows is the join of the exchange
     if exch is not None:
         gathered, totals = exch.finish()     # the compute stream joins the exchange: inside the timed region
     t1.record(stream)
     gpu_launches = int(E.nat.lib().cub200_launch_count() - launches0)   # kernels of libcub200 launched in the timed region
+    if graphed:
+        gpu_launches += args.steps * cfg.gs[0].kernels_per_replay          # ... by the graph replays (counted at capture)
     sync_all()
     ms_total = t0.elapsed_time(t1)
     n_collectives = 0
     if exch is not None:
-        n_collectives = exch.collectives
+        n_collectives = exch.collectives - collectives0
         mine, sums = cfg.metric_values()
-        assert torch.equal(gathered[rank, -1], mine), "exchange: own block of the last step"
+        assert torch.equal(gathered[rank if world > 1 else 0, -1], mine), "exchange: own block of the last step"
         assert int(totals[-1, 0]) == int(gathered[:, -1].sum()), "exchange: dataset sum"
     clk = clocks.stop() if (rank == 0 and not args.no_clocks) else None
+    per_rank = [ms_total / args.steps]
+    per_rank_own = [t0.elapsed_time(t_mid) / args.steps]      # the rank's own steps, before it joins the exchange
+    if world > 1:
+        tl = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([per_rank[0], per_rank_own[0]], dtype=torch.float64, device=dev))
+        per_rank = [float(x[0].item()) for x in tl]
+        per_rank_own = [float(x[1].item()) for x in tl]
     if args.device_only:
         if rank == 0:
-            print(f"device-only run: {ms_total / args.steps:.4f} ms per step, {gpu_launches} library launches in the timed region")
+            print(f"device-only run: {max(per_rank):.4f} ms per step (per rank: {[round(x, 4) for x in per_rank]}; own steps before the "
+                  f"exchange join: {[round(x, 4) for x in per_rank_own]}), {gpu_launches} library launches in the timed region")
         if world > 1:
             dist.destroy_process_group()
         return
@@ -786,7 +829,8 @@ def run_ours(args):
                    "l2": ("inputs larger than L2 (%.0f MB of logits per step)" % (cfg.logits.numel() * 4 / 1e6)) if hasattr(cfg, "logits") and cfg.logits.numel() * 4 > 130e6
                          else "per-step working set (sampled contours / masks written and re-read, %.0f MB) larger than L2" % (units * 168 * 2 / 1e6) if units * 168 * 2 > 130e6
                          else "working set smaller than L2 (latency case): no flush",
-                   "rng": "in-kernel Philox4x32-10", "exchange": f"one all_gather per {every} steps ({n_collectives} in the timed run)" if world > 1 else "none (1 GPU)"},
+                   "inputs": (f"{cfg.POOL} distinct batches cycled per rank (same pool on every rank, phase-shifted by rank)" if cfg_id in (1, 2) else "one batch per rank"),
+                   "rng": "in-kernel Philox4x32-10", "launch": "CUDA graph replay (one launch per step)" if graphed else "eager (one launch per kernel)", "exchange": f"one all_gather per {every} steps ({n_collectives} in the timed run)" if world > 1 else "none (1 GPU)"},
         "contour_pixels_per_s": value * HW * HW,
         "kernel_ms": km,
         "roofline": roof(dominant),
@@ -795,6 +839,7 @@ def run_ours(args):
                 "numa_bound": numa_bound, "h2d_gb_per_s_per_gpu": h2d / (e2e_ms * 1e-3) / 1e9,
                 "result": "compact: uint16 count map (mean / entropy / pred are exact functions of it), contours, areas"},
         "gpu_launches": gpu_launches,
+        "ms_per_step_per_rank": per_rank, "ms_per_step_per_rank_before_exchange_join": per_rank_own,
         "clocks": clk,
         "parity_spot_check": bool(parity_ok and e2e_ok),
     }
@@ -813,12 +858,14 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange-every", type=int, default=0, help="steps per all_gather of the metric distributions (0 = one per run)")
+    ap.add_argument("--no-graph", action="store_true", help="configs 1 / 2: launch the step's kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--force-exchange", action="store_true", help="diagnostic: run the per-step metric push / block shipping on one GPU too")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (profiling runs)")
     ap.add_argument("--device-only", action="store_true", help="profiling runs: only the device-resident steps (no per-phase, e2e, CPU or parity legs; no JSON line)")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {1: 200, 2: 100, 3: 10, 4: 3, 5: 10}[args.config] if args.impl == "ours" else 1
+        args.steps = {1: 200, 2: 96, 3: 10, 4: 3, 5: 10}[args.config]      # config 2: a multiple of the batch pool (8) if args.impl == "ours" else 1
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

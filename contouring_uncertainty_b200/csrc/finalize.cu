@@ -224,6 +224,61 @@ metric_sums_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long*
     if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicAdd(out + 1, s2); }
 }
 
+// One launch for what a rank buffers per step for the epoch-end exchange: the per-sample metric values copied into a slot of
+// a device ring + their exact int64 (sum, sum of squares).  CUB200_METRIC_PACK_PARTS CTAs, each copies one contiguous part and
+// leaves ITS partial sums in its own four words of the slot's tail: no accumulator to zero, no atomics, no second pass -- the
+// consumer adds the parts (it adds over the ranks anyway).  slot = *step_dev % n_slots (a device-side step counter: the launch
+// is identical in every replay of a CUDA graph), or 0.
+constexpr int MP_PARTS = CUB200_METRIC_PACK_PARTS;
+__global__ void __launch_bounds__(1024)
+metric_pack_kernel(const int32_t* __restrict__ v, int64_t n, int32_t* __restrict__ ring, int64_t n_slots,
+                   const uint64_t* __restrict__ step_dev) {
+    __shared__ unsigned long long red[2][32];
+    const int64_t slot = step_dev ? (int64_t)(*step_dev % (uint64_t)n_slots) : 0;
+    int32_t* out = ring + slot * (n + 4 * MP_PARTS);
+    // part p = elements [p * per, min((p + 1) * per, n)), per a multiple of 4 so that 128-bit accesses stay aligned
+    const int64_t per = (((n + MP_PARTS - 1) / MP_PARTS) + 3) & ~3LL;
+    const int64_t lo = min((int64_t)blockIdx.x * per, n), hi = min(lo + per, n);
+    unsigned long long s = 0, s2 = 0;
+    auto acc = [&](int32_t x32) { const long long x = x32; s += (unsigned long long)x; s2 += (unsigned long long)(x * x); };
+    int64_t i0 = lo;
+    if (((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int4* v4 = reinterpret_cast<const int4*>(v);
+        int4* o4 = reinterpret_cast<int4*>(out);
+        const int64_t q_lo = lo >> 2, q_hi = hi >> 2;                 // whole quads of the part (lo is a multiple of 4)
+        for (int64_t base = q_lo; base < q_hi; base += 4 * 1024) {
+            int4 t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int64_t i = base + q * 1024 + threadIdx.x; t[q] = i < q_hi ? v4[i] : make_int4(0, 0, 0, 0); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t i = base + q * 1024 + threadIdx.x;
+                if (i < q_hi) { o4[i] = t[q]; acc(t[q].x); acc(t[q].y); acc(t[q].z); acc(t[q].w); }
+            }
+        }
+        i0 = q_hi << 2;
+    }
+    for (int64_t i = i0 + threadIdx.x; i < hi; i += 1024) {
+        const int32_t x32 = v[i];
+        out[i] = x32;
+        acc(x32);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(FULL, s, o); s2 += __shfl_xor_sync(FULL, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = red[0][threadIdx.x]; s2 = red[1][threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(FULL, s, o); s2 += __shfl_xor_sync(FULL, s2, o); }
+        if (threadIdx.x == 0) {
+            int32_t* tail = out + n + 4 * blockIdx.x;
+            tail[0] = (int32_t)(uint32_t)s; tail[1] = (int32_t)(uint32_t)(s >> 32);
+            tail[2] = (int32_t)(uint32_t)s2; tail[3] = (int32_t)(uint32_t)(s2 >> 32);
+        }
+    }
+}
+
 // post_mu / post_cov of aleatoric.py:96-102: thread (k, sg) streams the float2 of landmark k over the
 // samples sg, sg+12, ...; moments about the first sample (no cancellation), fp64, block reduction.
 constexpr int SM_GROUPS = 12;
@@ -330,6 +385,14 @@ extern "C" int cub200_metric_sums(const int32_t* values, int64_t n, int64_t* sum
     const int64_t blocks = (n + 255) / 256;
     metric_sums_kernel<<<(unsigned)(blocks < 592 ? blocks : 592), 256, 0, st>>>(values, n, reinterpret_cast<unsigned long long*>(sums_out));
     return check_launch("metric_sums_kernel");
+}
+
+extern "C" int cub200_metric_pack(const int32_t* values, int64_t n, int32_t* ring, int64_t n_slots, const uint64_t* step_dev,
+                                  void* stream) {
+    using namespace cub200;
+    if (!values || !ring || n < 0 || n_slots < 1) return CUB200_EINVAL;
+    metric_pack_kernel<<<MP_PARTS, 1024, 0, (cudaStream_t)stream>>>(values, n, ring, n_slots, step_dev);
+    return check_launch("metric_pack_kernel");
 }
 
 // ---------------------------------------------------------------- sample_entropy for probabilities of any class count

@@ -375,8 +375,8 @@ __device__ __forceinline__ void philox_normals4(uint64_t gc, int q, uint64_t see
 template <int ZD>
 __global__ void __launch_bounds__(SC_THREADS)
 sample_contours_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim, const float* __restrict__ z,
-                       uint64_t seed, uint64_t g_offset, int64_t n_samples, int chunks, float* __restrict__ contours_out,
-                       uint32_t* __restrict__ queue) {
+                       uint64_t seed, uint64_t g_offset, const uint64_t* __restrict__ step_dev, uint64_t step_stride,
+                       int64_t n_samples, int chunks, float* __restrict__ contours_out, uint32_t* __restrict__ queue) {
     __shared__ __align__(16) float a_s[CUB200_ZMAX * CUB200_P];
     if (queue && blockIdx.x == 0 && threadIdx.x == 0) queue[0] = 0u;   // the rasteriser that follows starts with an empty queue
     __shared__ float out_s[SC_THREADS * SC_PAD];
@@ -395,7 +395,8 @@ sample_contours_kernel(const float* __restrict__ mu, const float* __restrict__ a
 #pragma unroll
             for (int e = 0; e < CUB200_ZMAX; ++e) zz[e] = (e < nz) ? z[g * nz + e] : 0.f;
         } else {
-            const uint64_t gc = (uint64_t)g + g_offset;      // draws keyed by (seed, global sample index)
+            // draws keyed by (seed, global sample index); a device-side step counter (CUDA-graph replays) shifts the index range
+            const uint64_t gc = (uint64_t)g + g_offset + (step_dev ? *step_dev * step_stride : 0ull);
 #pragma unroll
             for (int q = 0; q < (CUB200_ZMAX + 3) / 4; ++q) {
                 if (4 * q < nz) philox_normals4(gc, q, seed, zz[4 * q], zz[4 * q + 1], zz[4 * q + 2], zz[4 * q + 3]);
@@ -430,13 +431,14 @@ sample_contours_kernel(const float* __restrict__ mu, const float* __restrict__ a
 constexpr int SW_WARPS = 8;
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sample_contours_warp_kernel(const float* __restrict__ mu, const float* __restrict__ a_t, int zdim, const float* __restrict__ z,
-                            uint64_t seed, uint64_t g_offset, int64_t n_img, int64_t n_samples, float* __restrict__ contours_out,
-                            uint32_t* __restrict__ queue) {
+                            uint64_t seed, uint64_t g_offset, const uint64_t* __restrict__ step_dev, uint64_t step_stride,
+                            int64_t n_img, int64_t n_samples, float* __restrict__ contours_out, uint32_t* __restrict__ queue) {
     __shared__ float z_s[SW_WARPS][CUB200_ZMAX + 2];
     if (queue && blockIdx.x == 0 && threadIdx.x == 0) queue[0] = 0u;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     float* zw = z_s[warp];
     const int64_t total = n_img * n_samples;
+    if (step_dev) g_offset += *step_dev * step_stride;
     for (int64_t g = (int64_t)blockIdx.x * SW_WARPS + warp; g < total; g += (int64_t)gridDim.x * SW_WARPS) {
         const int64_t img = g / n_samples;
         if (z) {
@@ -531,6 +533,7 @@ raster_general_kernel(const void* __restrict__ contours_in, int flags, int32_t* 
 }
 
 __global__ void zero_queue_kernel(uint32_t* queue) { queue[0] = 0u; }
+__global__ void step_counter_add_kernel(uint64_t* counter, uint64_t inc) { *counter += inc; }
 
 static int sm_count(int* out) {
     // per device (the library serves several GPUs of one process), benign race: every thread writes the same value
@@ -581,7 +584,7 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
                                               uint64_t seed, uint64_t sample_offset, int64_t n_img, int64_t n_samples,
                                               int round_landmarks, float* contours_out, int32_t* area_out,
                                               int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* workspace,
-                                              void* stream) {
+                                              const uint64_t* step_dev, void* stream) {
     using namespace cub200;
     if (!mu || !a_t || zdim < 1 || zdim > CUB200_ZMAX || n_img < 0 || n_samples < 0) return CUB200_EINVAL;
     if (images_per_map < 1 || n_img % images_per_map) return CUB200_EINVAL;
@@ -595,17 +598,17 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
     if (n_samples < SC_THREADS / 2) {
         const int64_t need = (total + SW_WARPS - 1) / SW_WARPS;
         const int grid = (int)(need < 148 * 16 ? need : 148 * 16);
-        sample_contours_warp_kernel<<<grid, SW_WARPS * 32, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_img, n_samples, contours_out, queue);
+        sample_contours_warp_kernel<<<grid, SW_WARPS * 32, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, step_dev, (uint64_t)total, n_img, n_samples, contours_out, queue);
     } else {
         const int64_t chunks = (n_samples + SC_THREADS - 1) / SC_THREADS;
         if (n_img * chunks > 0x7fffffffLL) return CUB200_EINVAL;
         const unsigned grid = (unsigned)(n_img * chunks);
         if (zdim == 34)
-            sample_contours_kernel<34><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out, queue);
+            sample_contours_kernel<34><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, step_dev, (uint64_t)total, n_samples, (int)chunks, contours_out, queue);
         else if (zdim == 42)
-            sample_contours_kernel<42><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out, queue);
+            sample_contours_kernel<42><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, step_dev, (uint64_t)total, n_samples, (int)chunks, contours_out, queue);
         else
-            sample_contours_kernel<0><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, n_samples, (int)chunks, contours_out, queue);
+            sample_contours_kernel<0><<<grid, SC_THREADS, 0, st>>>(mu, a_t, zdim, z, seed, sample_offset, step_dev, (uint64_t)total, n_samples, (int)chunks, contours_out, queue);
     }
     int rc = check_launch("sample_contours_kernel");
     if (rc || !raster) return rc;                              // sample-only call
@@ -614,6 +617,13 @@ extern "C" int cub200_sample_raster_aggregate(const float* mu, const float* a_t,
 }
 
 extern "C" int64_t cub200_raster_workspace_bytes(int64_t n) { return n < 0 ? 0 : 4 * (n + 1); }
+
+extern "C" int cub200_step_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+    using namespace cub200;
+    if (!counter) return CUB200_EINVAL;
+    step_counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+    return check_launch("step_counter_add_kernel");
+}
 
 extern "C" int cub200_rasterize_contours(const float* contours, int64_t n, int round_landmarks, uint32_t* masks_out,
                                          int32_t* area_out, int32_t* diff, int64_t per_image, void* workspace, void* stream) {

@@ -162,7 +162,7 @@ def sample_raster_aggregate(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int,
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
                                                       int(sample_offset) & (2**64 - 1), n, T, int(round_landmarks),
                                                       nat.ptr(contours), nat.ptr(area), nat.ptr(diff), int(images_per_map),
-                                                      nat.ptr(masks), nat.ptr(rws), nat.stream_ptr(dev))
+                                                      nat.ptr(masks), nat.ptr(rws), None, nat.stream_ptr(dev))
     nat.check(rc, "cub200_sample_raster_aggregate")
     return dict(contours=contours, area=area, diff=diff, masks=masks)
 
@@ -185,7 +185,7 @@ def sample_contours(mu: torch.Tensor, a_t: torch.Tensor, n_samples: int, z: Opti
     with torch.cuda.device(mu.device):
         rc = nat.lib().cub200_sample_raster_aggregate(nat.ptr(mu), nat.ptr(a_t), zdim, nat.ptr(z), int(seed) & (2**64 - 1),
                                                       int(sample_offset) & (2**64 - 1), n, T, 1, nat.ptr(out), None, None, 1,
-                                                      None, None, nat.stream_ptr(mu.device))
+                                                      None, None, None, nat.stream_ptr(mu.device))
     nat.check(rc, "cub200_sample_raster_aggregate(sample-only)")
     return out
 
@@ -1193,11 +1193,14 @@ class UncertaintyEngine:
         return Workspace(n_img, t_a, Z_PSM if self.sampler == "psm" else Z_NAIVE, self.device, **kw)
 
     def run_into(self, ws: Workspace, logits: torch.Tensor, seed: int = 0, stream: Optional[torch.cuda.Stream] = None,
-                 sample_offset: int = 0):
+                 sample_offset: int = 0, step_dev: Optional[torch.Tensor] = None, after_raster=None):
         """The whole path into preallocated buffers: 7 launches (+1 memset), no allocation, no sync.
 
         ``logits`` must be (ws.n_img,21,256,256) fp32 CUDA contiguous.  ``sample_offset``: index of the first sample of this
-        call in a larger batch (chunked callers), see ``sample_raster_aggregate``.  Returns ``ws``.
+        call in a larger batch (chunked callers), see ``sample_raster_aggregate``.  ``step_dev``: device step counter (one
+        int64) that shifts the draws on the device -- for steps replayed from a CUDA graph (``GraphedStep``).
+        ``after_raster``: callable invoked once the sampler / rasteriser launches are queued (contours and areas final), before
+        finalize_maps: the place to fork work that only needs the per-sample outputs.  Returns ``ws``.
         """
         if logits.dtype != torch.float32 or not logits.is_cuda or not logits.is_contiguous() or \
                 tuple(logits.shape) != (ws.n_img, K, HW, HW):
@@ -1222,8 +1225,11 @@ class UncertaintyEngine:
             nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
                                                        int(seed) & (2**64 - 1), int(sample_offset) & (2**64 - 1), n, T, 1,
                                                        ws.contours.data_ptr(),
-                                                       ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, ws.raster_ws.data_ptr(), st),
+                                                       ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, ws.raster_ws.data_ptr(),
+                                                       nat.ptr(step_dev), st),
                       "cub200_sample_raster_aggregate")
+            if after_raster is not None:
+                after_raster()
             nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, nat.ptr(ws.count), nat.ptr(ws.mean),
                                              nat.ptr(ws.entropy), ws.pred.data_ptr(), ws.lut.data_ptr(), 1, nat.ptr(ws.variance),
                                              nat.ptr(ws.count16), st),
@@ -1235,6 +1241,88 @@ class UncertaintyEngine:
         _, mu, cov = dsnt_moments(logits, is_logit=True, covar=self.covar)
         return self.from_moments(mu, cov, t_a, z=z, seed=seed, return_contours=return_contours,
                                  return_masks=return_masks, want_count=want_count)
+
+
+METRIC_PACK_PARTS = 16       # CUB200_METRIC_PACK_PARTS
+
+
+class GraphedStep:
+    """The whole device-resident step (``UncertaintyEngine.run_into`` [+ the per-step metric buffering of the epoch-end
+    exchange]) captured ONCE in a CUDA graph and replayed with one launch per step.
+
+    Eager, a step is 8 launches (+ 4 for the exchange buffer): on a box where several ranks share the host that is where the
+    multi-GPU step loses time (profiles/r02d_*: kernel times identical at 1 and 8 GPUs, the step 0.44 -> 0.50 ms; replayed
+    from a graph all ranks run at the single-GPU rate).  A captured launch's arguments are frozen, so what changes from step
+    to step lives on the device: ``self.step`` (one int64) shifts the Philox sample indices of the sampler and selects the
+    slot of the metric ring; the graph's last node increments it.  Step i of a GraphedStep draws the samples
+    ``UncertaintyEngine.run_into(..., seed, sample_offset=i * n_img * t_a)`` draws.
+    ``logits`` is read in place at every replay: refill the same buffer (``logits.copy_``) between replays.
+    """
+
+    def __init__(self, engine: "UncertaintyEngine", ws: Workspace, logits: torch.Tensor, seed: int = 0,
+                 metric_ring: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None):
+        """``step``: an existing device counter to share (several GraphedSteps over different input buffers that advance one
+        sequence of steps); by default the object owns a fresh one.  Capturing leaves the counter at 0."""
+        self.engine, self.ws, self.logits, self.seed, self.ring = engine, ws, logits, int(seed), metric_ring
+        dev = ws.device
+        if metric_ring is not None:
+            metric_ring = nat.require_cuda(metric_ring, torch.int32, "metric_ring")
+            if metric_ring.dim() != 2 or metric_ring.shape[1] != ws.area.numel() + 4 * METRIC_PACK_PARTS or metric_ring.device != dev:
+                raise ValueError(f"metric_ring must be (n_slots, {ws.area.numel() + 4 * METRIC_PACK_PARTS}) int32 on {dev}")
+        self.step = torch.zeros((1,), dtype=torch.int64, device=dev) if step is None else step
+        if self.step.dtype != torch.int64 or self.step.numel() != 1 or self.step.device != dev:
+            raise ValueError("step must be one int64 on the workspace's device")
+        self.stream = torch.cuda.Stream(dev)
+        self.side = torch.cuda.Stream(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            self._body()                                  # warm-up outside the capture (lazy attribute / module loads)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.step.zero_()
+        torch.cuda.synchronize(dev)
+        n0 = nat.lib().cub200_launch_count()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._body()
+        self.kernels_per_replay = int(nat.lib().cub200_launch_count() - n0)   # library kernels one replay launches
+        torch.cuda.synchronize(dev)
+
+    def _body(self):
+        L = nat.lib()
+        st = self.stream.cuda_stream
+
+        def fork_pack():
+            # the metric buffer only needs the areas: it runs on a side branch of the graph, beside finalize_maps (a one-CTA
+            # copy would otherwise hold the whole GPU for its ~8 us)
+            if self.ring is None:
+                return
+            self.side.wait_stream(self.stream)
+            with torch.cuda.device(self.ws.device):
+                nat.check(L.cub200_metric_pack(self.ws.area.data_ptr(), self.ws.area.numel(), self.ring.data_ptr(),
+                                               self.ring.shape[0], self.step.data_ptr(), self.side.cuda_stream), "cub200_metric_pack")
+
+        self.engine.run_into(self.ws, self.logits, seed=self.seed, stream=self.stream, step_dev=self.step, after_raster=fork_pack)
+        if self.ring is not None:
+            self.stream.wait_stream(self.side)
+        with torch.cuda.device(self.ws.device):
+            nat.check(L.cub200_step_counter_add(self.step.data_ptr(), 1, st), "cub200_step_counter_add")
+
+    def reset(self, step: int = 0):
+        """Set the device step counter."""
+        self.step.fill_(int(step))
+
+    def resync(self, slot_index: int, n_slots: int):
+        """Make the next replay write ring slot ``slot_index`` without re-using sample indices: the counter jumps forward to
+        the next value congruent to slot_index (mod n_slots).  Synchronises (reads the counter); for epoch boundaries."""
+        cur = int(self.step.item())
+        nxt = cur + ((int(slot_index) - cur) % int(n_slots))
+        self.step.fill_(nxt)
+
+    def replay(self):
+        """One step on the CURRENT stream: one cudaGraphLaunch."""
+        self.graph.replay()
+        return self.ws
 
 
 class HostPipeline:

@@ -103,14 +103,17 @@ class StepExchange:
         return (self.last["gathered"], self.last["stats"]) if self.last is not None else (None, None)
 
 
+PACK_PARTS = 16          # CUB200_METRIC_PACK_PARTS (include/cub200.h): partial int64 sums in a slot's tail
+
+
 class MetricExchange:
     """The path's exchange as ONE collective per block of ``every`` steps (default: one per predict epoch).
 
     The reference gathers nothing per batch: its clinical metric processors run at the END of the predict epoch over all
     BatchResults (cu/results/clinical/clinical_metrics.py:51-66).  So a rank only buffers what those processors need --
     per step the per-image metric distributions (n_local, T) int32 and the exact int64 dataset sums -- in a device ring of
-    ``every`` slots, and one ``all_gather_into_tensor`` ships a whole block: [every][n_local * T + 4] int32 words per rank, the
-    two int64 sums riding in the last 4 words of each slot (no separate all_reduce: every rank adds the gathered sums
+    ``every`` slots, and one ``all_gather_into_tensor`` ships a whole block: [every][n_local * T + 64] int32 words per rank, the
+    int64 sums riding (as 16 partial pairs) in the tail of each slot (no separate all_reduce: every rank adds the gathered sums
     itself, exactly, in int64).  Blocks are double-buffered and the collective is asynchronous, so block b is on the wire
     while block b + 1 fills; ``finish()`` flushes a partial block and joins everything onto the current stream.
     """
@@ -120,23 +123,52 @@ class MetricExchange:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.every = max(1, int(every))
         self.n_local, self.n_per_image = int(n_local), int(n_per_image)
-        self.payload = self.n_local * self.n_per_image + 4
-        self.blocks = [{"local": torch.zeros((self.every, self.payload), dtype=torch.int32, device=device),
+        self.payload = self.n_local * self.n_per_image + 4 * PACK_PARTS
+        # one ring of n_blocks * every slots: a step captured in a CUDA graph addresses it with its device-side step counter
+        # (slot = step % (n_blocks * every), engine.GraphedStep); block b = slots [b * every, (b + 1) * every)
+        self.ring = torch.zeros((n_blocks * self.every, self.payload), dtype=torch.int32, device=device)
+        self.blocks = [{"local": self.ring[b * self.every:(b + 1) * self.every],
                         "gathered": torch.zeros((self.world * self.every, self.payload), dtype=torch.int32, device=device),
-                        "work": None, "filled": 0} for _ in range(n_blocks)]
+                        "work": None, "filled": 0} for b in range(n_blocks)]
         self.cur = 0
         self.collectives = 0
         self.last = None
 
-    def push(self, values: torch.Tensor, sums: torch.Tensor):
-        """values (n_local, n_per_image) int32, sums (2,) int64 of this step (device tensors, no synchronisation)."""
+    def prepare(self):
+        """Call BEFORE the step that writes the next slot: a block that is being reused must have left the wire."""
         blk = self.blocks[self.cur]
-        if blk["filled"] == 0 and blk["work"] is not None:      # the block is being reused: its previous exchange must be done
+        if blk["filled"] == 0 and blk["work"] is not None:
             blk["work"].wait()
             blk["work"] = None
+        return blk
+
+    def push(self, values: torch.Tensor, sums: torch.Tensor = None):
+        """values (n_local, n_per_image) int32 [, sums (2,) int64] of this step (device tensors, no synchronisation).
+        On CUDA tensors: ONE launch (cub200_metric_pack copies the values and forms the exact int64 sums itself)."""
+        blk = self.prepare()
         slot = blk["local"][blk["filled"]]
-        slot[:self.payload - 4].copy_(values.reshape(-1), non_blocking=True)
-        slot[self.payload - 4:].copy_(sums.view(torch.int32), non_blocking=True)
+        if values.is_cuda:
+            from . import _native as nat
+            with torch.cuda.device(values.device):
+                nat.check(nat.lib().cub200_metric_pack(values.data_ptr(), values.numel(), slot.data_ptr(), 1, None,
+                                                       nat.stream_ptr(values.device)), "cub200_metric_pack")
+        else:                                               # host logic under gloo (CPU tests)
+            if sums is None:
+                v64 = values.reshape(-1).to(torch.int64)
+                sums = torch.stack([v64.sum(), (v64 * v64).sum()])
+            tail = self.payload - 4 * PACK_PARTS
+            slot[:tail].copy_(values.reshape(-1), non_blocking=True)
+            slot[tail:].zero_()                               # the sums ride as part 0, the other parts are zero
+            slot[tail:tail + 4].copy_(sums.view(torch.int32), non_blocking=True)
+        self.note_pushed()
+
+    def slot_index(self) -> int:
+        """Ring slot the next step writes (what a GraphedStep's counter must be congruent to, mod ring.shape[0])."""
+        return self.cur * self.every + self.blocks[self.cur]["filled"]
+
+    def note_pushed(self):
+        """The slot of this step has been written (by push(), or by a graph replay that addresses the ring itself)."""
+        blk = self.blocks[self.cur]
         blk["filled"] += 1
         if blk["filled"] == self.every:
             self._ship(blk)
@@ -166,8 +198,9 @@ class MetricExchange:
             return None, None
         k = self.last["shipped"]
         g = self.last["gathered"].view(self.world, self.every, self.payload)[:, :k]
-        values = g[..., :self.payload - 4].reshape(self.world, k, self.n_local, self.n_per_image)
-        sums = g[..., self.payload - 4:].contiguous().view(torch.int64).sum(0)
+        tail = self.payload - 4 * PACK_PARTS
+        values = g[..., :tail].reshape(self.world, k, self.n_local, self.n_per_image)
+        sums = g[..., tail:].contiguous().view(torch.int64).reshape(self.world, k, PACK_PARTS, 2).sum((0, 2))   # over ranks and parts
         return values, sums
 
 

@@ -133,13 +133,18 @@ int cub200_naive_factor(const float* cov, int64_t n_img, float* a_out, void* str
  *                epistemic passes of an image, aleatoric.py:71-73); diff is (n_img / images_per_map, 256, 256)
  *   workspace:   cub200_raster_workspace_bytes(n_img * n_samples) bytes of device memory (not needed by a sample-only
  *                call): the queue of samples whose fill needs the general flood (second kernel of the rasteriser)
+ *   step_dev:    optional DEVICE pointer to a step counter: *step_dev * n_img * n_samples is added to sample_offset on the
+ *                device, so a step captured in a CUDA graph draws fresh samples at every replay (the argument list of a
+ *                captured launch is frozen; the counter is advanced inside the graph with cub200_step_counter_add).
  */
 int64_t cub200_raster_workspace_bytes(int64_t n_contours);
 int cub200_sample_raster_aggregate(const float* mu, const float* a_t, int zdim, const float* z,
                                    uint64_t seed, uint64_t sample_offset, int64_t n_img, int64_t n_samples,
                                    int round_landmarks, float* contours_out, int32_t* area_out,
                                    int32_t* diff, int64_t images_per_map, uint32_t* masks_out, void* workspace,
-                                   void* stream);
+                                   const uint64_t* step_dev, void* stream);
+/* *counter += inc, as a (capturable) kernel launch on `stream`. */
+int cub200_step_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
 /*
  * Rasteriser alone (the same device code as K3, contours given): bit-packed masks out.
@@ -219,6 +224,16 @@ int cub200_fac_from_areas(const int32_t* area_ed, const int32_t* area_es, int64_
  *   replaces  the np.mean / np.std reductions over gathered per-sample metrics   cu/results/clinical/utils.py:3-18
  */
 int cub200_metric_sums(const int32_t* values, int64_t n, int64_t* sums_out, void* stream);
+/*
+ * What a rank buffers per step for the epoch-end exchange (cu/results/clinical/clinical_metrics.py:51-66 reads every
+ * BatchResult at the END of the predict epoch), in one launch: slot = ring + s * (n + 4 * CUB200_METRIC_PACK_PARTS) receives
+ * the n values and, in its tail, CUB200_METRIC_PACK_PARTS partial (sum, sum of squares) pairs as exact int64 (two int32 words
+ * each, low word first): the consumer adds the parts.  s = *step_dev % n_slots (device-side step counter, see
+ * cub200_sample_raster_aggregate) or 0 when step_dev is NULL.  ring (n_slots, n + 4 * CUB200_METRIC_PACK_PARTS) int32.
+ */
+#define CUB200_METRIC_PACK_PARTS 16
+int cub200_metric_pack(const int32_t* values, int64_t n, int32_t* ring, int64_t n_slots, const uint64_t* step_dev,
+                       void* stream);
 
 /*
  * Posterior moments of the sampled contours: per (image, landmark) the sample mean and the unbiased

@@ -63,7 +63,7 @@ def test_null_and_bad_sizes_return_einval():
     l = _native.lib()
     assert l.cub200_dsnt_moments(None, 1, 256, 256, 1, 1, None, None, None, None, None) == _native.EINVAL
     assert l.cub200_dsnt_moments(None, 1, 128, 128, 1, 1, None, None, None, None, None) == _native.EINVAL
-    assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 0, 1, 1, 1, None, None, None, 1, None, None, None) == _native.EINVAL
+    assert l.cub200_sample_raster_aggregate(None, None, 34, None, 0, 0, 1, 1, 1, None, None, None, 1, None, None, None, None) == _native.EINVAL
     assert l.cub200_finalize_maps(None, 1, 10, None, None, None, None, None, 0, None, None, None) == _native.EINVAL
     # zero-sized work is a no-op success even without a device
     assert l.cub200_rasterize_contours(None, 0, 1, None, None, None, 0, None, None) == 0
@@ -106,6 +106,8 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_mask_lv_length(None, 1, 5e-3, None, 1.0, 1.0, None, None, None, None, None) == E
     assert l.cub200_mask_lv_length(None, 0, 5e-3, None, 1.0, 1.0, None, None, None, None, None) == 0
     assert l.cub200_endo_base_corners(None, None, 1, None, None) == E
+    assert l.cub200_step_counter_add(None, 1, None) == E
+    assert l.cub200_metric_pack(None, 1, None, 1, None, None) == E
     assert l.cub200_mask_lv_length_myo(None, None, 1, 1.0, 1.0, None, None, None, None, None) == E
     assert l.cub200_mask_lv_length_myo(None, None, 0, 1.0, 1.0, None, None, None, None, None) == 0
     assert l.cub200_seg_largest_blob(None, 0, None, None, None, None) == 0

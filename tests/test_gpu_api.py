@@ -440,3 +440,35 @@ def test_psm_sampler_with_alpha_soft_masks_and_small_api_holes():
         want = port.soft_mask(port.us_contour_to_mask(c4[k]))
         assert np.abs(ps[0, 0, k, 0] - want).max() <= 1e-12
         assert ps[0, 0, k, 0].min() == 0.0 and ps[0, 0, k, 0].max() == 1.0
+
+
+def test_graphed_step_replays_match_eager_steps_and_fill_the_metric_ring():
+    """engine.GraphedStep: replay i of the captured step == the eager step with sample_offset = i * n_img * t_a (the device-side
+    step counter shifts the Philox sample indices), and cub200_metric_pack leaves areas + exact int64 sums in ring slot i % n_slots."""
+    import synth
+    from contouring_uncertainty_b200 import engine as E
+
+    dev = torch.device("cuda:0")
+    n, T, slots = 3, 40, 4
+    eng = E.UncertaintyEngine(device=dev)
+    logits = torch.from_numpy(synth.heatmap_logits(n, seed=17)).to(dev)
+    ws_g, ws_e = eng.workspace(n, T), eng.workspace(n, T)
+    ring = torch.zeros((slots, n * T + 4 * E.METRIC_PACK_PARTS), dtype=torch.int32, device=dev)
+    gs = E.GraphedStep(eng, ws_g, logits, seed=5, metric_ring=ring)
+    assert gs.kernels_per_replay >= 7
+    for i in range(6):
+        gs.replay()
+        eng.run_into(ws_e, logits, seed=5, sample_offset=i * n * T)
+        torch.cuda.synchronize()
+        assert torch.equal(ws_g.contours, ws_e.contours) and torch.equal(ws_g.area, ws_e.area)
+        assert torch.equal(ws_g.count, ws_e.count) and torch.equal(ws_g.entropy, ws_e.entropy)
+        slot = ring[i % slots]
+        assert torch.equal(slot[:n * T], ws_e.area.reshape(-1))
+        a = ws_e.area.reshape(-1).to(torch.int64)
+        assert slot[n * T:].view(torch.int64).reshape(-1, 2).sum(0).tolist() == [int(a.sum()), int((a * a).sum())]
+    assert int(gs.step.item()) == 6
+    gs.resync(1, slots)                                   # next replay writes slot 1 with sample indices never used before
+    assert int(gs.step.item()) == 9
+    gs.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(ring[1][:n * T], ws_g.area.reshape(-1))

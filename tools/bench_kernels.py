@@ -21,8 +21,8 @@ eng.run_into(ws, logits, seed=1)
 res = {
  "dsnt": timeit(lambda: E.nat.check(L.cub200_dsnt_moments(logits.data_ptr(), n * 21, 256, 256, 1, 1, None, ws.mu.data_ptr(), ws.cov.data_ptr(), ws.dsnt_ws.data_ptr(), st), "d")),
  "factor": timeit(lambda: E.nat.check(L.cub200_psm_factor(eng.model.pack.data_ptr(), ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "f")),
- "sample": timeit(lambda: E.nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), 34, None, 5, 0, n, T, 1, ws.contours.data_ptr(), None, None, 1, None, None, st), "s")),
- "raster(+general)": timeit(lambda: E.nat.check(L.cub200_rasterize_contours(ws.contours.data_ptr(), n * T, 1, None, ws.area.data_ptr(), ws.diff.data_ptr(), T, ws.raster_ws.data_ptr(), st), "r")),
+ "sample": timeit(lambda: E.nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), 34, None, 5, 0, n, T, 1, ws.contours.data_ptr(), None, None, 1, None, None, None, st), "s")),
+ "raster(+general)": timeit(lambda: E.nat.check(L.cub200_rasterize_contours(ws.contours.data_ptr(), n * T, 1, None, ws.area.data_ptr(), ws.diff.data_ptr(), T, ws.raster_ws.data_ptr(), None, st), "r")),
  "finalize": timeit(lambda: E.nat.check(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, ws.count.data_ptr(), ws.mean.data_ptr(), ws.entropy.data_ptr(), ws.pred.data_ptr(), ws.lut.data_ptr(), 1, None, None, st), "z")),
  "step (run_into)": timeit(lambda: eng.run_into(ws, logits, seed=3)),
 }
