@@ -205,7 +205,8 @@ def cpu_arm(cfg, workers, kind="port"):
     n_units, n_samples = CPU_UNITS_PER_WORKER[cfg] * workers, CPU_SAMPLES[cfg]
     ctx = mp.get_context("fork")
     with ctx.Pool(workers, initializer=_cpu_init, initargs=(kind,)) as pool:
-        pool.map(_cpu_worker, [(cfg, 900 + i, 1) for i in range(workers)])   # warm the workers (imports, model)
+        # warm the workers (imports, model); two samples: the reference's samplers squeeze a single one away (sampler.py:40)
+        pool.map(_cpu_worker, [(cfg, 900 + i, 2) for i in range(workers)])
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, [(cfg, 1000 + i, n_samples) for i in range(n_units)], chunksize=1)
         wall = time.perf_counter() - t0
@@ -343,19 +344,29 @@ class LogitsPSM(PathConfig):
         return self.ws.area, self.E.metric_sums(self.ws.area, out=self.sums)
 
     def step_evented(self, i, tm):
-        E, ws = self.E, self.ws
+        """The launches of engine.run_into, one by one, with an event between the phases (same buffers, no allocation)."""
+        E, ws, eng = self.E, self.ws, self.eng
         logits = self.pool[(i + self.rank) % self.POOL]
+        L, n, T = E.nat.lib(), self.n, self.T
+        st = self.torch.cuda.current_stream(self.dev).cuda_stream
+        chk = E.nat.check
         tm.mark("start")
-        _, mu, cov = E.dsnt_moments(logits, is_logit=True, covar=True)
+        chk(L.cub200_dsnt_moments(logits.data_ptr(), n * K, HW, HW, 1, 1, None, ws.mu.data_ptr(), ws.cov.data_ptr(), ws.dsnt_ws.data_ptr(), st), "dsnt")
         tm.mark("dsnt")
-        a_t = self.eng.factor(mu, cov)
+        if eng.sampler == "psm":
+            chk(L.cub200_psm_factor(eng.model.pack.data_ptr(), ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "factor")
+        else:
+            chk(L.cub200_naive_factor(ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "factor")
         tm.mark("factor")
-        s = E.sample_contours(mu, a_t, self.T, seed=1000 + i)
+        chk(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None, 1000 + i, 0, n, T, 1, ws.contours.data_ptr(),
+                                             None, None, 1, None, None, None, st), "sample")
         tm.mark("sample")
         ws.diff.zero_()
-        E.rasterize_contours(s.reshape(-1, K, 2), return_masks=False, diff=ws.diff, per_image=self.T)
+        chk(L.cub200_rasterize_contours(ws.contours.data_ptr(), n * T, 1, None, ws.area.data_ptr(), ws.diff.data_ptr(), T,
+                                        ws.raster_ws.data_ptr(), st), "raster")
         tm.mark("raster")
-        E.finalize_maps(ws.diff, self.T)
+        chk(L.cub200_finalize_maps(ws.diff.data_ptr(), n, T, E.nat.ptr(ws.count), E.nat.ptr(ws.mean), E.nat.ptr(ws.entropy), ws.pred.data_ptr(),
+                                   ws.lut.data_ptr(), 1, E.nat.ptr(ws.variance), E.nat.ptr(ws.count16), st), "finalize")
         tm.mark("finalize")
 
     def algorithmic_bytes(self):
@@ -804,10 +815,12 @@ def run_ours(args):
     def roof(k):
         ach = alg[k] / (km[k] * 1e-3) / 1e9
         n = notes.get(f"config{cfg_id}", {}).get(k, notes.get("kernels", {}).get(k, {}))
-        return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        return {"kernel": n.get("kernel", k), "phase": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": n.get("dram_bytes_per_launch"), "traffic_source": n.get("source"),
                 "ms_per_launch": km[k], "algorithmic_bytes": alg[k], "peak_source": peak_src, "binding_resource": n.get("binding"),
-                "note": n.get("note")}
+                "issue_active_pct": n.get("issue_active_pct"), "ipc": n.get("ipc"), "warp_instructions_per_launch": n.get("warp_instructions"),
+                "note": n.get("note") or ("a read-only stream runs a little above the measured peak, which is a copy (read + write): "
+                                          "B200_PROFILING.md" if ach > peak else None)}
 
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -29,6 +29,7 @@ SIGNATURES = {
     "cub200_naive_factor": [_vp, _i64, _vp, _vp],
     "cub200_sample_raster_aggregate": [_vp, _vp, _i32, _vp, _u64, _u64, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "cub200_step_counter_add": [_vp, _u64, _vp],
+    "cub200_psm_sample_direct": [_vp, _vp, _vp, _vp, _u64, _u64, _i64, _vp, _vp],
     "cub200_metric_pack": [_vp, _i64, _vp, _i64, _vp, _vp],
     "cub200_rasterize_contours": [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp],
     "cub200_finalize_maps": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],

@@ -364,13 +364,6 @@ __device__ __forceinline__ int raster_sample(WarpScratch<GENERAL>& ws, double fx
 constexpr int SC_THREADS = 64;
 constexpr int SC_PAD = CUB200_P + 1;            // staging row stride (floats): conflict-free column access
 
-// The draws of global sample gc (Philox counter (gc, q), key = seed): 4 normals per call, z[4q .. 4q+3].
-__device__ __forceinline__ void philox_normals4(uint64_t gc, int q, uint64_t seed, float& n0, float& n1, float& n2, float& n3) {
-    uint32_t r[4];
-    philox4x32_10((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)q, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-    box_muller(r[0], r[1], n0, n1);
-    box_muller(r[2], r[3], n2, n3);
-}
 
 template <int ZD>
 __global__ void __launch_bounds__(SC_THREADS)

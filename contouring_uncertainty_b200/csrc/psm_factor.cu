@@ -67,8 +67,8 @@ template <int WPI> __device__ __forceinline__ void group_sync() { if (WPI == 1) 
 
 // The per-level scalars and vectors of one image: ws.u, ws.w, ws.kd, ws.corr, ws.sc.  `lane` = thread index in the
 // image's group of NT = 32 WPI threads.
-template <int WPI>
-__device__ __forceinline__ void level_common(PFWarp& ws, const double* __restrict__ pk, const LevelDef L, int lane) {
+template <int WPI, class Scratch>
+__device__ __forceinline__ void level_common(Scratch& ws, const double* __restrict__ pk, const LevelDef L, int lane) {
     constexpr int NT = 32 * WPI;
     const double* Binv = pk + L.off_binv;
     const double* K = pk + L.off_k;
@@ -212,6 +212,123 @@ psm_factor_kernel(const double* __restrict__ pack, const float* __restrict__ mu,
             out[e * P + o] = (float)(ws.A[v][e] * pk[PK_SCALE + v]);   // out[e][d], d = original flat index
         }
         group_sync<WPI>();
+    }
+}
+
+
+// ---------------------------------------------------------------- Gaussian sampler: ONE sample per item, no factor
+// The sequence sampler draws exactly one contour from each of its per-(pair, sample) merged laws (sequence_sampler.py:94:
+// the second instant's PosteriorShapeModelSampler call, whose pca is re-centred per sample, psm.py:91).  Building the
+// 34 x 42 affine factor for that (psm_factor_kernel<1>) and applying it to one draw vector is 34 x the arithmetic and 5.7 KB of
+// traffic per sample for nothing: every formula of the factor is linear in its columns, so the same recursion runs on the
+// single column x = A z -- the deviation of the sampled variables from their predicted means in the scaler's space.
+// One warp per item; draws z (n_items, 34) replayed, or Philox keyed by (seed, item + sample_offset) exactly like
+// sample_contours_warp_kernel (same draws as the factor path; the result differs from it only by that path's fp32
+// rounding of the factor).  contours_out (n_items, 21, 2) fp32.
+struct __align__(16) PDWarp {
+    double x[Z], acc[16];
+    double d[P], u[Z];
+    double w[16], kd[16], corr[16];
+    double sc[8][3];
+    float z[Z + 2];
+};
+constexpr int PD_WARPS = 8;
+
+__global__ void __launch_bounds__(PD_WARPS * 32)
+psm_sample_direct_kernel(const double* __restrict__ pack, const float* __restrict__ mu, const float* __restrict__ cov,
+                         const float* __restrict__ z, uint64_t seed, uint64_t g_offset, int64_t n_items,
+                         float* __restrict__ contours_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* pk = reinterpret_cast<double*>(smem_raw);
+    PDWarp* warps = reinterpret_cast<PDWarp*>(pk + PACK_DOUBLES);
+    for (int i = threadIdx.x; i < PACK_DOUBLES; i += PD_WARPS * 32) pk[i] = pack[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    PDWarp& ws = warps[wid];
+    for (int64_t it = (int64_t)blockIdx.x * PD_WARPS + wid; it < n_items; it += (int64_t)gridDim.x * PD_WARPS) {
+        const float* mu_i = mu + it * P;
+        const float* cov_i = cov + it * (CUB200_K * 4);
+        for (int v = lane; v < P; v += 32) {
+            const int o = 2 * c_order[v >> 1] + (v & 1);
+            ws.d[v] = pk[PK_XBAR + v] - ((double)mu_i[o] - pk[PK_MEAN + v]) / pk[PK_SCALE + v];   // xbar - transform(mu)
+        }
+        if (z) {
+            for (int e = lane; e < Z; e += 32) ws.z[e] = z[it * Z + e];
+        } else if (lane * 4 < Z) {
+            philox_normals4((uint64_t)it + g_offset, lane, seed, ws.z[4 * lane], ws.z[4 * lane + 1], ws.z[4 * lane + 2], ws.z[4 * lane + 3]);
+        }
+        __syncwarp();
+        // initial points: independent draws mu_j + chol(cov_j) z                       psm.py:239
+        if (lane < 3) {
+            const int j = c_order[lane];
+            const double p00 = cov_i[4 * j], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
+            const double l00 = sqrt(p00), l10 = p10 / l00, l11 = sqrt(p11 - l10 * l10);
+            const double z0 = ws.z[2 * lane], z1 = ws.z[2 * lane + 1];
+            ws.x[2 * lane] = l00 * z0 / pk[PK_SCALE + 2 * lane];
+            ws.x[2 * lane + 1] = (l10 * z0 + l11 * z1) / pk[PK_SCALE + 2 * lane + 1];
+        }
+        __syncwarp();
+        float* out = contours_out + it * P;
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l) {
+            const LevelDef L = level_def(l);
+            level_common<1>(ws, pk, L, lane);
+            const int n = L.n, rows = L.rows;
+            const double* K = pk + L.off_k;
+            // t = u^T x_g ; acc = K x_g + corr t
+            double t = 0.0;
+            for (int k = lane; k < n; k += 32) t = fma(ws.u[k], ws.x[k], t);
+            t = warp_sum(t);
+            // rows x n mat-vec: two lanes per row, each half of the columns (rows <= 16)
+            {
+                const int a = lane >> 1, h = lane & 1;
+                double acc = 0.0;
+                if (a < rows) {
+                    const int k0 = h ? (n >> 1) : 0, k1 = h ? n : (n >> 1);
+                    for (int k = k0; k < k1; ++k) acc = fma(K[a * n + k], ws.x[k], acc);
+                }
+                acc += __shfl_xor_sync(FULL, acc, 1);
+                if (a < rows && h == 0) ws.acc[a] = fma(ws.corr[a], t, acc);
+            }
+            __syncwarp();
+            if (l < 3) {
+                // merge with the predicted law and colour with the position's own two draws
+                if (lane < rows / 2) {
+                    const int q = lane;
+                    const int pi = L.p0 + q, v0 = 2 * pi, v1 = v0 + 1, j = c_order[pi];
+                    const double c00 = ws.sc[q][0], c10 = ws.sc[q][1], c11 = ws.sc[q][2];
+                    const double c01 = c10 / pk[PK_SCALE + v0] * pk[PK_SCALE + v1];
+                    const double p00 = cov_i[4 * j + 0], p01 = cov_i[4 * j + 1], p10 = cov_i[4 * j + 2], p11 = cov_i[4 * j + 3];
+                    const double t00 = p00 + c00, t01 = p01 + c01, t10 = p10 + c10, t11 = p11 + c11;
+                    const double idet = 1.0 / (t00 * t11 - t01 * t10);
+                    const double i00 = t11 * idet, i01 = -t01 * idet, i10 = -t10 * idet, i11 = t00 * idet;
+                    const double g00 = p00 * i00 + p01 * i10, g01 = p00 * i01 + p01 * i11;
+                    const double g10 = p10 * i00 + p11 * i10, g11 = p10 * i01 + p11 * i11;
+                    const double b0 = pk[PK_SCALE + v0] * ws.acc[2 * q], b1 = pk[PK_SCALE + v1] * ws.acc[2 * q + 1];
+                    // cov_f = G cov_c ; lower Cholesky reading the lower triangle (torch.linalg.cholesky)
+                    const double f00 = g00 * c00 + g01 * c10;
+                    const double f10 = g10 * c00 + g11 * c10;
+                    const double f11 = g10 * c01 + g11 * c11;
+                    const double l00 = sqrt(f00), l10 = f10 / l00, l11 = sqrt(f11 - l10 * l10);
+                    const double z0 = ws.z[v0], z1 = ws.z[v1];
+                    const double a0 = g00 * b0 + g01 * b1 + l00 * z0;
+                    const double a1 = g10 * b0 + g11 * b1 + l10 * z0 + l11 * z1;
+                    ws.x[v0] = a0 / pk[PK_SCALE + v0];
+                    ws.x[v1] = a1 / pk[PK_SCALE + v1];
+                }
+                __syncwarp();
+            } else if (lane < rows) {
+                // the remaining points: posterior mean given all 17 sampled ones, sigma2 = 1e-3      psm.py:355-368
+                const int v = Z + lane;
+                const int o = 2 * c_order[v >> 1] + (v & 1);
+                out[o] = (float)((double)mu_i[o] + pk[PK_SCALE + v] * ws.acc[lane]);
+            }
+        }
+        for (int v = lane; v < Z; v += 32) {
+            const int o = 2 * c_order[v >> 1] + (v & 1);
+            out[o] = (float)((double)mu_i[o] + ws.x[v] * pk[PK_SCALE + v]);
+        }
+        __syncwarp();
     }
 }
 
@@ -382,6 +499,26 @@ extern "C" int cub200_psm_factor(const double* model_pack, const float* mu, cons
     if (wide) psm_factor_kernel<PF_WARPS><<<grid, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(model_pack, mu, cov, n_img, a_out);
     else psm_factor_kernel<1><<<grid, PF_WARPS * 32, smem, (cudaStream_t)stream>>>(model_pack, mu, cov, n_img, a_out);
     return check_launch("psm_factor_kernel");
+}
+
+extern "C" int cub200_psm_sample_direct(const double* model_pack, const float* mu, const float* cov, const float* z, uint64_t seed,
+                                        uint64_t sample_offset, int64_t n_items, float* contours_out, void* stream) {
+    using namespace cub200;
+    if (n_items == 0) return 0;
+    if (!model_pack || !mu || !cov || !contours_out || n_items < 0) return CUB200_EINVAL;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        CUB200_CUDA_OK(cudaGetDevice(&dev));
+        CUB200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t smem = sizeof(double) * PACK_DOUBLES + sizeof(PDWarp) * PD_WARPS;
+    CUB200_CUDA_OK(cudaFuncSetAttribute(psm_sample_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t need = (n_items + PD_WARPS - 1) / PD_WARPS;
+    const int64_t cap = (int64_t)num_sms * 6;                  // 6 CTAs x 8 warps per SM (32 KB of shared memory each)
+    psm_sample_direct_kernel<<<(int)(need < cap ? need : cap), PD_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        model_pack, mu, cov, z, seed, sample_offset, n_items, contours_out);
+    return check_launch("psm_sample_direct_kernel");
 }
 
 extern "C" int cub200_psm_conditionals(const double* model_pack, const float* mu, int64_t n_img, double* mc_t, double* covc,

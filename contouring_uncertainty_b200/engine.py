@@ -104,6 +104,28 @@ def psm_factor(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor) 
     return a
 
 
+def psm_sample_direct(model: ShapeModelConstants, mu: torch.Tensor, cov: torch.Tensor, z: Optional[torch.Tensor] = None,
+                      seed: int = 0, sample_offset: int = 0) -> torch.Tensor:
+    """ONE PosteriorShapeModelSampler sample per item, without the factor (what the sequence sampler's second instant needs):
+    mu (M,21,2), cov (M,21,2,2) fp32 [, z (M,34)] -> contours (M,21,2) fp32.  Same draws as
+    ``sample_contours(mu, psm_factor(model, mu, cov), 1, z, seed, sample_offset)``."""
+    mu = nat.require_cuda(mu, torch.float32, "mu")
+    cov = nat.require_cuda(cov, torch.float32, "cov")
+    if mu.dim() != 3 or mu.shape[1:] != (K, 2) or tuple(cov.shape) != (mu.shape[0], K, 2, 2):
+        raise ValueError("mu (M,21,2) / cov (M,21,2,2) expected")
+    m, dev = mu.shape[0], mu.device
+    if z is not None:
+        z = nat.require_cuda(z, torch.float32, "z")
+        if tuple(z.shape) != (m, Z_PSM):
+            raise ValueError(f"z must be ({m},{Z_PSM})")
+    out = torch.empty((m, K, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = nat.lib().cub200_psm_sample_direct(nat.ptr(model.pack), nat.ptr(mu), nat.ptr(cov), nat.ptr(z), int(seed) & (2**64 - 1),
+                                                int(sample_offset) & (2**64 - 1), m, nat.ptr(out), nat.stream_ptr(dev))
+    nat.check(rc, "cub200_psm_sample_direct")
+    return out
+
+
 def naive_factor(cov: torch.Tensor) -> torch.Tensor:
     """Block-diagonal Cholesky colouring of the independent sampler: (N,21,2,2) -> A^T (N,42,42)."""
     cov = nat.require_cuda(cov, torch.float32, "cov")
@@ -506,8 +528,8 @@ def sequence_sample(model: ShapeModelConstants, seq: SequenceModelConstants, mu:
     Bernoulli(1/2) from torch's generator).  Returns contours (Np, T, 2, 21, 2).
 
     Pipeline: K2 on both instants -> one PSM sample of every image (sample-only K3) -> seq_condition
-    (84-dim conditioning + merge) -> K2 per (pair, sample) on the merged distribution of the other
-    instant (its PCA is re-centred per sample, psm.py:91) -> sample-only K3.
+    (84-dim conditioning + merge) -> ONE direct PSM sample per (pair, sample) from the merged distribution of the other
+    instant (its PCA is re-centred per sample, psm.py:91: `psm_sample_direct`, no per-sample factor).
     """
     mu = nat.require_cuda(mu, torch.float32, "mu")
     cov = nat.require_cuda(cov, torch.float32, "cov")
@@ -538,8 +560,9 @@ def sequence_sample(model: ShapeModelConstants, seq: SequenceModelConstants, mu:
                                             nat.ptr(seq.scale), nat.ptr(first), nat.ptr(mu_f), nat.ptr(cov_f),
                                             nat.stream_ptr(dev))
     nat.check(rc, "cub200_seq_condition")
-    a2 = psm_factor(model, mu_f, cov_f)                                      # per (pair, sample)
-    second = sample_contours(mu_f, a2, 1, z=z2, seed=seed + 0x9E3779B9).reshape(npair, T, K, 2)
+    # one sample from each per-(pair, sample) law: drawn directly, without its 34 x 42 factor (same draws as the factor path)
+    second = psm_sample_direct(model, mu_f, cov_f, z=None if z2 is None else z2.reshape(npair * T, Z_PSM),
+                               seed=seed + 0x9E3779B9).reshape(npair, T, K, 2)
     fi = first_instant.bool()[..., None, None]
     out = torch.empty((npair, T, 2, K, 2), dtype=torch.float32, device=dev)
     out[:, :, 0] = torch.where(fi, second, first)                            # instant 0 is "first" when bit == 0

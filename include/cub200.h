@@ -297,6 +297,17 @@ int cub200_skew_rvs_fast(const float* mu, const float* cov, const float* alpha, 
                          float* out, void* stream);
 
 /*
+ * ONE PSM sample per item without building its factor: the second instant of the sequence sampler draws a single contour
+ * from every per-(pair, sample) merged law           cu/sampler/posterior_shape_model/sequence_sampler.py:94, psm.py:73-93
+ * (equivalent to cub200_psm_factor + cub200_sample_raster_aggregate(n_samples = 1, sample-only) with the same seed and
+ * sample_offset -- same draws -- at 1/34 of the arithmetic and without the 5.7 KB factor per item).
+ *   mu (n_items,21,2), cov (n_items,21,2,2) fp32; z (n_items,34) fp32 replayed draws or NULL (Philox keyed by
+ *   (seed, item + sample_offset)); contours_out (n_items,21,2) fp32.
+ */
+int cub200_psm_sample_direct(const double* model_pack, const float* mu, const float* cov, const float* z, uint64_t seed,
+                             uint64_t sample_offset, int64_t n_items, float* contours_out, void* stream);
+
+/*
  * Conditional maps of the posterior shape model per image (the part of compute_psm that does not depend
  * on the sampled values): mu_c = mu + Mc (s - mu) over the already-sampled coordinates, and the 2x2
  * conditional covariances of the 14 level points.

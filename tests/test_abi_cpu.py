@@ -107,6 +107,7 @@ def test_new_entry_points_validate_arguments():
     assert l.cub200_mask_lv_length(None, 0, 5e-3, None, 1.0, 1.0, None, None, None, None, None) == 0
     assert l.cub200_endo_base_corners(None, None, 1, None, None) == E
     assert l.cub200_step_counter_add(None, 1, None) == E
+    assert l.cub200_psm_sample_direct(None, None, None, None, 0, 0, 1, None, None) == E
     assert l.cub200_metric_pack(None, 1, None, 1, None, None) == E
     assert l.cub200_mask_lv_length_myo(None, None, 1, 1.0, 1.0, None, None, None, None, None) == E
     assert l.cub200_mask_lv_length_myo(None, None, 0, 1.0, 1.0, None, None, None, None, None) == 0

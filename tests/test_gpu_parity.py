@@ -147,6 +147,29 @@ def test_psm_samples_vs_golden(dev, eng):
     assert np.abs(s - g["samples"]).max() < 6e-2
 
 
+def test_psm_direct_single_samples_vs_golden_and_factor_path(dev, eng):
+    """cub200_psm_sample_direct (one sample per law, no factor: the sequence sampler's second instant) on the golden's laws,
+    every law repeated once per stored draw vector: against the reference executed in fp64, and against the factor path."""
+    from contouring_uncertainty_b200.engine import psm_factor, psm_sample_direct, sample_contours
+
+    g = np.load(os.path.join(G, "psm.npz"))
+    n, T = g["z"].shape[:2]
+    mu = torch.from_numpy(np.repeat(g["mu"], T, axis=0)).to(dev)                 # (n T, 21, 2): item = (law, draw)
+    cov = torch.from_numpy(np.repeat(g["cov"], T, axis=0)).to(dev)
+    z = torch.from_numpy(g["z"]).to(dev).reshape(n * T, 34)
+    s = psm_sample_direct(eng.model, mu, cov, z=z).cpu().numpy().astype(np.float64).reshape(n, T, 21, 2)
+    err = np.abs(s - g["samples_f64"]).max()
+    assert err < 2.56e-3 * 0.1, err                                               # the bound of the factor path's test: 1e-5 of the coordinate scale
+    assert np.abs(s - g["samples"]).max() < 6e-2                                  # verbatim fp32 reference (its own noise)
+    # generated draws: the same Philox stream as the factor path with one sample per law
+    m = min(64, n * T)
+    a_t = psm_factor(eng.model, mu[:m], cov[:m])
+    via_factor = sample_contours(mu[:m], a_t, 1, seed=77).reshape(m, 21, 2)
+    direct = psm_sample_direct(eng.model, mu[:m], cov[:m], seed=77)
+    gap = (via_factor - direct).abs().max().item()
+    assert gap < 5e-4, gap                                                        # the factor path stores A in fp32 and sums in fp32
+
+
 def test_naive_sampler_given_factor_vs_golden(dev):
     from contouring_uncertainty_b200.engine import sample_raster_aggregate, naive_factor
 
