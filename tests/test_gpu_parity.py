@@ -263,6 +263,13 @@ def test_full_size_properties(dev, eng):
     assert torch.all(res.pred == (2 * count > T).to(torch.uint8))
     assert float(res.entropy.max()) <= 1.0 + 1e-12 and float(res.entropy.min()) >= 0.0
     assert torch.all((res.entropy == 0) == ((count == 0) | (count == T)))
+    # the oracle at this size: all 1000 samples of the first and the last image rasterised by the CPU restatement give the
+    # same count map pixel for pixel (and with it mean / entropy / pred, exact functions of the count) and the same areas
+    cs = res.contour_samples.cpu().numpy()
+    for i in (0, n - 1):
+        want = port.convert_to_mask(cs[i])                                           # (T, 256, 256) uint8
+        assert np.array_equal(want.sum(0, dtype=np.int64), count[i].cpu().numpy())
+        assert np.array_equal(want.reshape(T, -1).sum(1, dtype=np.int64), res.area[i].cpu().numpy())
     # a sub-sample re-rasterised by the debug path gives the same areas (sample order / indexing)
     from contouring_uncertainty_b200.engine import rasterize_contours
 
