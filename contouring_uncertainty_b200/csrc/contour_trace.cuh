@@ -13,14 +13,36 @@ constexpr int SP_NMAX = CUB200_SIMPSON_MAX_POINTS;   // contour points kept per 
 // to-edge of the segment that STARTS at edge f (to_of_from) / from-edge of the segment that ENDS at
 // edge t (from_of_to), per square case (bit 0 ul, 1 ur, 2 ll, 3 lr; 'low' vertex connectivity).
 // Edges: 0 top, 1 bottom, 2 left, 3 right; 9 = no such segment.
-static __constant__ unsigned char c_to_of_from[16][4] = {
+// The tables live in registers as 2-bit fields (a per-thread index into __constant__ memory is replayed once per distinct
+// address of the warp, and every thread of a warp walks its own mask).
+constexpr unsigned char k_to_of_from[16][4] = {
     {9, 9, 9, 9}, {2, 9, 9, 9}, {9, 9, 9, 0}, {9, 9, 9, 2}, {9, 9, 1, 9}, {1, 9, 9, 9}, {9, 9, 1, 0}, {9, 9, 9, 1},
     {9, 3, 9, 9}, {2, 3, 9, 9}, {9, 0, 9, 9}, {9, 2, 9, 9}, {9, 9, 3, 9}, {3, 9, 9, 9}, {9, 9, 0, 9}, {9, 9, 9, 9}};
-static __constant__ unsigned char c_from_of_to[16][4] = {
+constexpr unsigned char k_from_of_to[16][4] = {
     {9, 9, 9, 9}, {9, 9, 0, 9}, {3, 9, 9, 9}, {9, 9, 3, 9}, {9, 2, 9, 9}, {9, 0, 9, 9}, {3, 2, 9, 9}, {9, 3, 9, 9},
     {9, 9, 9, 1}, {9, 9, 0, 1}, {1, 9, 9, 9}, {9, 9, 1, 9}, {9, 9, 9, 2}, {9, 9, 9, 0}, {2, 9, 9, 9}, {9, 9, 9, 9}};
 // from-edge of the FIRST segment a cell generates (cases 6 and 9 generate two)
-static __constant__ unsigned char c_first_from[16] = {9, 0, 3, 3, 2, 0, 3, 3, 1, 0, 1, 1, 2, 0, 2, 9};
+constexpr unsigned char k_first_from[16] = {9, 0, 3, 3, 2, 0, 3, 3, 1, 0, 1, 1, 2, 0, 2, 9};
+constexpr uint64_t pack_edge_table(const unsigned char (&t)[16][4], int half) {      // cases 8 half .. 8 half + 7; "none" -> 0
+    uint64_t v = 0;
+    for (int c = 0; c < 8; ++c)
+        for (int e = 0; e < 4; ++e) v |= (uint64_t)(t[8 * half + c][e] > 3 ? 0 : t[8 * half + c][e]) << (2 * (4 * c + e));
+    return v;
+}
+constexpr uint32_t pack_first_from() {
+    uint32_t v = 0;
+    for (int c = 0; c < 16; ++c) v |= (uint32_t)(k_first_from[c] > 3 ? 0 : k_first_from[c]) << (2 * c);
+    return v;
+}
+constexpr uint64_t TO_OF_FROM_LO = pack_edge_table(k_to_of_from, 0), TO_OF_FROM_HI = pack_edge_table(k_to_of_from, 1);
+constexpr uint64_t FROM_OF_TO_LO = pack_edge_table(k_from_of_to, 0), FROM_OF_TO_HI = pack_edge_table(k_from_of_to, 1);
+constexpr uint32_t FIRST_FROM = pack_first_from();
+__device__ __forceinline__ int to_of_from(int cs, int e) {
+    return (int)(((cs & 8) ? TO_OF_FROM_HI : TO_OF_FROM_LO) >> (2 * (4 * (cs & 7) + e))) & 3;
+}
+__device__ __forceinline__ int from_of_to(int cs, int e) {
+    return (int)(((cs & 8) ? FROM_OF_TO_HI : FROM_OF_TO_LO) >> (2 * (4 * (cs & 7) + e))) & 3;
+}
 
 // A mask as the Simpson code sees it: the 256 x 256 bit-packed mask itself, or (anisotropic voxel spacing) its
 // nearest-neighbour stretch to H x W -- resize_image_to_isotropic (vital/vital/utils/image/transform.py:52-66) through
@@ -34,8 +56,14 @@ struct MaskView {
         if (ri) { r = ri[r]; c = ci[c]; }
         return (m[r * 8 + (c >> 5)] >> (c & 31)) & 1u;
     }
-    __device__ __forceinline__ int cell(int r0, int c0) const {
-        return bit(r0, c0) | (bit(r0, c0 + 1) << 1) | (bit(r0 + 1, c0) << 2) | (bit(r0 + 1, c0 + 1) << 3);
+    __device__ __forceinline__ int cell(int r0, int c0) const {   // bit 0 ul, 1 ur, 2 ll, 3 lr of the cell at (r0, c0)
+        if (ri) return bit(r0, c0) | (bit(r0, c0 + 1) << 1) | (bit(r0 + 1, c0) << 2) | (bit(r0 + 1, c0 + 1) << 3);
+        // plain view: one word per row; the right-hand column sits in the next word only for c0 % 32 == 31 (c0 <= 254)
+        const int w = c0 >> 5, b = c0 & 31;
+        const uint32_t* p = m + r0 * 8 + w;
+        uint32_t x0 = p[0] >> b, x1 = p[8] >> b;
+        if (b == 31) { x0 |= p[1] << 1; x1 |= p[9] << 1; }
+        return (int)((x0 & 3u) | ((x1 & 3u) << 2));
     }
 };
 // a cell's second segment (saddle cases): the one starting at L (case 6) / B (case 9)
@@ -103,14 +131,13 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
     if (fr < 0) { npts[g] = 0; return; }                          // find_contours() == [] -> IndexError
     // pass A: walk backwards from the first segment to the chain start, or around the loop
     const int cs0 = mv.cell(fr, fc);
-    const int f0 = c_first_from[cs0];
-    int r0 = fr, c0 = fc, fe = f0;                                // current segment = (cell, from-edge)
+    const int f0 = (int)(FIRST_FROM >> (2 * cs0)) & 3;
+    int r0 = fr, c0 = fc, fe = f0, cs = cs0;                      // current segment = (cell, from-edge); cs = the cell's case
     int sr = fr, sc = fc, sf = f0;                                // start segment of pass B
     bool closed = false;
     int last_key = -1, lr = 0, lc = 0, lt = 0;                    // raster-last segment of the loop
     for (int it = 0; it < 4 * SP_NMAX; ++it) {
-        const int cs = mv.cell(r0, c0);
-        const int te = c_to_of_from[cs][fe];
+        const int te = to_of_from(cs, fe);
         const int key = ((r0 * (CM + 1) + c0) << 1) | seg_rank(cs, fe);
         if (key > last_key) { last_key = key; lr = r0; lc = c0; lt = te; }
         // predecessor: the cell across the from-edge, whose segment ends on the shared edge
@@ -118,8 +145,8 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
         if (fe == 0) { pr = r0 - 1; pe = 1; } else if (fe == 1) { pr = r0 + 1; pe = 0; }
         else if (fe == 2) { pc = c0 - 1; pe = 3; } else { pc = c0 + 1; pe = 2; }
         if (pr < 0 || pr > RM || pc < 0 || pc > CM) { sr = r0; sc = c0; sf = fe; break; }     // open chain start
-        const int pf = c_from_of_to[mv.cell(pr, pc)][pe];
-        r0 = pr; c0 = pc; fe = pf;
+        cs = mv.cell(pr, pc);
+        r0 = pr; c0 = pc; fe = from_of_to(cs, pe);
         if (r0 == fr && c0 == fc && fe == f0) { closed = true; break; }
     }
     if (closed) {
@@ -135,8 +162,7 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
     out[n++] = edge_point(r0, c0, fe);
     bool overflow = false;
     for (;;) {
-        const int cs = mv.cell(r0, c0);
-        const int te = c_to_of_from[cs][fe];
+        const int te = to_of_from(mv.cell(r0, c0), fe);
         if (n >= SP_NMAX) { overflow = true; break; }
         out[n++] = edge_point(r0, c0, te);
         int nr = r0, nc = c0, ne;

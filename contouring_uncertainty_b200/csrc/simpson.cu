@@ -21,6 +21,7 @@
 namespace cub200 {
 
 constexpr int SP_WARPS = 4;
+constexpr int CHORD_COARSE = 16;   // stride of the coarse pass of the chord search (8: 20 % more work, 32: 30 % more; tests/test_chord_search_cpu.py)
 
 // ---------------------------------------------------------------- S2: base chord, apex, discs; one warp per mask
 struct Chord {
@@ -33,6 +34,34 @@ __device__ __forceinline__ bool chord_better(const Chord& a, const Chord& b) {  
     return a.j < b.j;
 }
 
+
+// Exact pruning of the chord search.  Consecutive contour points are at most 2 half-pixel units apart (a marching-squares
+// segment joins two edge midpoints of one cell), so |P_i - P_j| <= 2 (i - j): with `wbest` the squared length of a valid
+// chord already held, pairs less than slim + 1 points apart, 4 slim^2 < wbest, are too short to be selected.
+__device__ __forceinline__ int chord_slim(int wbest) {          // largest s with 4 s^2 < wbest
+    if (wbest <= 4) return 0;
+    int s = (int)(0.5 * sqrt((double)wbest));
+    while (4 * s * s >= wbest) --s;
+    while (4 * (s + 1) * (s + 1) < wbest) ++s;
+    return s;
+}
+// Can point k be ruled out as the later end i (DIR = -1: partners j < k) or the earlier end j (DIR = +1: partners i > k) of
+// the answer?  Take a witness w = P[k + DIR s] - P[k], 1 <= s <= slim.  Partners up to the witness are too close (above).
+// For the others the witness is an intermediate point of the chord, whose direction a is admissible (|a_row| <= a_col):
+// |cross(a, w)| >= a_col (|w_row| - |w_col|) and |a|^2 <= 2 a_col^2, so (|w_row| - |w_col|)^2 > 512 puts the witness more
+// than 8 px (16 units) from the chord's line whatever the partner: 23^2 = 529.  No partner at all beyond slim: ruled out too.
+__device__ __forceinline__ bool chord_steep(uint32_t a, uint32_t b) {
+    const int dr = (int)(a & 0xffff) - (int)(b & 0xffff), dc = (int)(a >> 16) - (int)(b >> 16);
+    return abs(dr) - abs(dc) >= 23;
+}
+template <int DIR>
+__device__ __forceinline__ bool chord_dead(const uint32_t* P, int k, int n, int slim) {
+    if (slim <= 0) return false;
+    if ((DIR < 0 ? k : n - 1 - k) <= slim) return true;
+    const uint32_t p = P[k];
+    return chord_steep(P[k + DIR * slim], p) || chord_steep(P[k + DIR * ((3 * slim) >> 2)], p) || chord_steep(P[k + DIR * (slim >> 1)], p);
+}
+
 __global__ void __launch_bounds__(SP_WARPS * 32)
 simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __restrict__ pts_g, const int32_t* __restrict__ npts,
                          int64_t n_masks, const uint16_t* __restrict__ row_index, const uint16_t* __restrict__ col_index, int vh,
@@ -40,6 +69,7 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     __shared__ uint32_t s_pts[SP_WARPS][SP_NMAX];
     __shared__ uint32_t s_bmax[SP_WARPS][SP_NMAX / 32];
     __shared__ uint32_t s_brow[SP_WARPS][SP_NMAX / 32];
+    __shared__ uint32_t s_live[SP_WARPS][2 * (SP_NMAX / 32)];
     extern __shared__ uint16_t s_idx[];
     if (row_index) {
         for (int i = threadIdx.x; i < vh; i += blockDim.x) s_idx[i] = row_index[i];
@@ -61,86 +91,143 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     for (int k = lane; k < n; k += 32) P[k] = pts_g[g * SP_NMAX + k];
     __syncwarp();
     // ---- longest admissible chord (heart_us.py:127-146).  The reference keeps the first (i, j) in loop order among the
-    //      longest valid chords, so pairs may be visited in any order as long as ties are broken by (i, j): a coarse
-    //      pass over every 4th point first finds a long valid chord, and the full pass then skips, 32 candidates at a
-    //      time, the blocks of j whose columns cannot give a chord that long (|d_row| <= d_col  =>  len^2 <= 2 d_col^2).
-    uint32_t* bmax = s_bmax[wid];                        // max column (half-pixel units) of each block of 32 points
-    uint32_t* brow = s_brow[wid];                        // its row range: min | max << 16
-    for (int jb = lane; jb < (n + 31) / 32; jb += 32) {
-        int m = 0, r0 = 0xffff, r1 = 0;
-        for (int k = 32 * jb; k < min(32 * jb + 32, n); ++k) {
-            m = max(m, (int)(P[k] >> 16));
-            r0 = min(r0, (int)(P[k] & 0xffff));
-            r1 = max(r1, (int)(P[k] & 0xffff));
-        }
-        bmax[jb] = (uint32_t)m;
-        brow[jb] = (uint32_t)r0 | ((uint32_t)r1 << 16);
-    }
-    __syncwarp();
-    Chord best{0, 0x7fffffff, 0x7fffffff};
-    auto try_pair = [&](int i, int ir, int ic, int j, int wbest) {
-        const int ar = (int)(P[j] & 0xffff) - ir, ac = (int)(P[j] >> 16) - ic;         // contour[j] - contour[i]
-        // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
-        if (!(ac > 0 && abs(ar) <= ac)) return;
-        const Chord cand{ar * ar + ac * ac, i, j};
-        if (cand.len2 < wbest || !chord_better(cand, best)) return;                    // cannot be selected
-        const int64_t lim = 256ll * cand.len2;           // (8 px)^2 * len2 in half-pixel units: cross^2 <= 256 len2
-        bool ok = true;
-        {   // most far-away chords fail at the middle of the span: test it first
-            const int k = (i + j) >> 1;
-            if (k > j) {
+    //      longest valid chords, so pairs may be visited in any order as long as ties are broken by (i, j).  Three steps:
+    //      (1) a coarse pass over every 16th point finds a long valid chord; (2) with its length as a bound most points are
+    //      ruled out as an end of the answer by ONE intermediate point each (`chord_dead`, exact); (3) the full pass runs over
+    //      the surviving i only and skips, 32 candidates at a time, the blocks of surviving j whose columns / rows cannot
+    //      give a chord that long (|d_row| <= d_col  =>  len^2 <= 2 d_col^2).
+    Chord best{0, 0x7fffffff, 0x7fffffff};               // warp-uniform
+    // One candidate j per lane for the same i (on = the lane has one), j increasing with the lane.  Each lane applies the tests
+    // that need no loop (admissible angle, can still be selected, the middle of the span -- where most far-away chords
+    // fail); the survivors are then validated longest first (first j among equals) by the WHOLE warp, 32 intermediate points
+    // at a time: as soon as one is valid no other candidate of this call can be selected.
+    auto try_pairs = [&](int i, int ir, int ic, int j, bool on) {
+        uint32_t key = 0u;                               // len2 << 5 | (31 - lane); len2 < 2^24 (coordinates < 2^11)
+        if (on) {
+            const int ar = (int)(P[j] & 0xffff) - ir, ac = (int)(P[j] >> 16) - ic;     // contour[j] - contour[i]
+            // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
+            const Chord cand{ar * ar + ac * ac, i, j};
+            if (ac > 0 && abs(ar) <= ac && chord_better(cand, best)) {
+                const int k = (i + j) >> 1;
                 const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);
                 const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
-                ok = cr * cr <= lim;
+                if (k == j || cr * cr <= 256ll * cand.len2) key = ((uint32_t)cand.len2 << 5) | (uint32_t)(31 - lane);
             }
         }
-        for (int k = j + 1; ok && k < i; ++k) {
-            const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);      // contour[i] - contour[k]
-            const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
-            ok = cr * cr <= lim;
+        for (;;) {
+            const uint32_t top = __reduce_max_sync(FULL, key);
+            if (top == 0u) return;
+            const int wl = 31 - (int)(top & 31u), wlen2 = (int)(top >> 5);
+            const int wj = __shfl_sync(FULL, j, wl);
+            const int ar = (int)(P[wj] & 0xffff) - ir, ac = (int)(P[wj] >> 16) - ic;
+            const int64_t lim = 256ll * wlen2;           // (8 px)^2 * len2 in half-pixel units: cross^2 <= 256 len2
+            bool ok = true;
+            for (int k0 = wj + 1; ok && k0 < i; k0 += 32) {
+                const int k = k0 + lane;
+                bool good = true;
+                if (k < i) {
+                    const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);   // contour[i] - contour[k]
+                    const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
+                    good = cr * cr <= lim;
+                }
+                ok = __all_sync(FULL, good);
+            }
+            if (ok) { best = Chord{wlen2, i, wj}; return; }
+            if (lane == wl) key = 0u;
         }
-        if (ok) best = cand;
     };
-    // coarse pass: i and j on every 4th point (validity is always checked on ALL intermediate points), i DESCENDING: a
+    // (1) coarse pass: i and j on every 16th point (validity is always checked on ALL intermediate points), i DESCENDING: a
     // straight stretch of the contour then meets its far end first, i.e. its longest chord, and the bound it sets prunes
-    // the O(L^2) shorter chords of the same stretch that an ascending scan would have validated one after the other
-    for (int i = (n - 1) & ~3; i >= 4; i -= 4) {
-        const int ir = P[i] & 0xffff, ic = P[i] >> 16;
-        const int wbest = __reduce_max_sync(FULL, best.len2);
-        for (int j = 4 * lane; j < i; j += 128) try_pair(i, ir, ic, j, wbest);
-    }
-    // full pass
-    int dmin_for = -1, dmin = 1;
-    for (int i = 2; i < n; ++i) {
-        const int ir = P[i] & 0xffff, ic = P[i] >> 16;
-        // a chord shorter than the best one any lane holds can never be selected (equal ones still can: ties go to the
-        // first (i, j) in loop order)
-        const int wbest = __reduce_max_sync(FULL, best.len2);
-        if (wbest != dmin_for) {                                                        // d_col needed for len^2 >= wbest
-            dmin = max(1, (int)ceil(sqrt(0.5 * (double)wbest) - 1e-9));
-            dmin_for = wbest;
-        }
-        const int nblk = (i + 31) >> 5;
-        for (int jb0 = 0; jb0 < nblk; jb0 += 32) {
-            const int jb = jb0 + lane, jc = jb < nblk ? jb : 0;
-            // a block can hold a candidate only if its columns reach d_col >= dmin AND some row is within that d_col of
-            // row i (|d_row| <= d_col)
-            const int dcmax = (int)bmax[jc] - ic;
-            const int rlo = (int)(brow[jc] & 0xffff), rhi = (int)(brow[jc] >> 16);
-            const int rdist = max(0, max(rlo - ir, ir - rhi));
-            unsigned live = __ballot_sync(FULL, jb < nblk && dcmax >= dmin && rdist <= dcmax);
-            while (live) {
-                const int b = __ffs(live) - 1;
-                live &= live - 1;
-                const int j = 32 * (jb0 + b) + lane;
-                if (j < i) try_pair(i, ir, ic, j, wbest);
+    // the O(L^2) shorter chords of the same stretch that an ascending scan would have validated one after the other.  As
+    // soon as a chord is held, the i that `chord_dead` rules out are skipped here as well.
+    {
+        int slim = 0, slim_for = 0;
+        for (int i = (n - 1) & ~(CHORD_COARSE - 1); i >= CHORD_COARSE; i -= CHORD_COARSE) {
+            if (best.len2 != slim_for) { slim = chord_slim(best.len2); slim_for = best.len2; }
+            if (chord_dead<-1>(P, i, n, slim)) continue;                                // warp-uniform
+            const int ir = P[i] & 0xffff, ic = P[i] >> 16;
+            for (int j0 = 0; j0 < i; j0 += 32 * CHORD_COARSE) {
+                const int j = j0 + CHORD_COARSE * lane;
+                try_pairs(i, ir, ic, j < i ? j : 0, j < i);
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Chord t{__shfl_xor_sync(FULL, best.len2, o), __shfl_xor_sync(FULL, best.i, o), __shfl_xor_sync(FULL, best.j, o)};
-        if (chord_better(t, best)) best = t;
+    // (2) the points that cannot be the i / the j of the answer, and the column / row ranges of the others per block of 32
+    uint32_t* bmax = s_bmax[wid];                        // max column (half-pixel units) of the block's surviving j
+    uint32_t* brow = s_brow[wid];                        // their row range: min | max << 16
+    uint32_t* live_i = s_live[wid];                      // bit k of word t: point 32 t + k may be the i of the answer
+    uint32_t* live_j = s_live[wid] + SP_NMAX / 32;
+    const int nwords = (n + 31) >> 5;
+    {
+        const int slim = chord_slim(best.len2);
+        for (int t = 0; t < nwords; ++t) {
+            const int k = 32 * t + lane;
+            const bool inb = k < n;
+            const uint32_t p = inb ? P[k] : 0u;
+            const bool li = inb && k >= 2 && !chord_dead<-1>(P, k, n, slim);
+            const bool lj = inb && !chord_dead<+1>(P, k, n, slim);
+            const uint32_t wi = __ballot_sync(FULL, li), wj = __ballot_sync(FULL, lj);
+            const uint32_t cm = __reduce_max_sync(FULL, lj ? (p >> 16) : 0u);
+            const uint32_t r0 = __reduce_min_sync(FULL, lj ? (p & 0xffffu) : 0xffffu);
+            const uint32_t r1 = __reduce_max_sync(FULL, lj ? (p & 0xffffu) : 0u);
+            if (lane == 0) { live_i[t] = wi; live_j[t] = wj; bmax[t] = cm; brow[t] = r0 | (r1 << 16); }
+        }
+    }
+    __syncwarp();
+    // ... and the i none of whose blocks passes the block test of the full pass under the bound held now (the bound only
+    // grows): lane = point, 32 i at a time, instead of one warp-wide iteration of the full pass each
+    {
+        const int dmin0 = max(1, (int)ceil(sqrt(0.5 * (double)best.len2) - 1e-9));
+        for (int t = 0; t < nwords; ++t) {
+            const uint32_t m = live_i[t];
+            if (m == 0u) continue;                                                      // warp-uniform
+            const int i = 32 * t + lane;
+            bool keep = false;
+            if ((m >> lane) & 1u) {
+                const int ir = P[i] & 0xffff, ic = P[i] >> 16;
+                const int nblk = (i + 31) >> 5;
+                for (int b = 0; b < nblk && !keep; ++b) {
+                    const int dcmax = (int)bmax[b] - ic;
+                    const int rlo = (int)(brow[b] & 0xffff), rhi = (int)(brow[b] >> 16);
+                    keep = dcmax >= dmin0 && max(0, max(rlo - ir, ir - rhi)) <= dcmax;
+                }
+            }
+            const uint32_t m2 = __ballot_sync(FULL, keep);
+            if (lane == 0) live_i[t] = m2;
+        }
+    }
+    __syncwarp();
+    // (3) full pass over the surviving i
+    int dmin_for = -1, dmin = 1;
+    for (int t = 0; t < nwords; ++t) {
+        uint32_t todo = live_i[t];
+        while (todo) {
+            const int i = 32 * t + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ir = P[i] & 0xffff, ic = P[i] >> 16;
+            // a chord shorter than the best one held can never be selected (equal ones still can: ties go to the first
+            // (i, j) in loop order)
+            if (best.len2 != dmin_for) {                                                // d_col needed for len^2 >= best.len2
+                dmin = max(1, (int)ceil(sqrt(0.5 * (double)best.len2) - 1e-9));
+                dmin_for = best.len2;
+            }
+            const int nblk = (i + 31) >> 5;
+            for (int jb0 = 0; jb0 < nblk; jb0 += 32) {
+                const int jb = jb0 + lane, jc = jb < nblk ? jb : 0;
+                // a block can hold a candidate only if its columns reach d_col >= dmin AND some row is within that d_col
+                // of row i (|d_row| <= d_col); a block without a surviving j has column 0 and fails the first test
+                const int dcmax = (int)bmax[jc] - ic;
+                const int rlo = (int)(brow[jc] & 0xffff), rhi = (int)(brow[jc] >> 16);
+                const int rdist = max(0, max(rlo - ir, ir - rhi));
+                unsigned live = __ballot_sync(FULL, jb < nblk && dcmax >= dmin && rdist <= dcmax);
+                while (live) {
+                    const int b = __ffs(live) - 1;
+                    live &= live - 1;
+                    const int j = 32 * (jb0 + b) + lane;
+                    try_pairs(i, ir, ic, j < i ? j : 0, j < i && ((live_j[jb0 + b] >> lane) & 1u));
+                }
+            }
+        }
     }
     if (best.len2 <= 0) {                               // best_j never assigned -> UnboundLocalError
         if (lane < 20) dout[lane] = qnan;
@@ -181,26 +268,46 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     }
     __syncwarp();
     const MaskView mv{P, row_index ? s_idx : nullptr, row_index ? s_idx + vh : nullptr, vh, vw};
-    // 20 discs x 2 directions (heart_us.py:158-164)
-    double d_pos = 0.0, d_neg = 0.0, d_neg2 = 0.0;
-    for (int ray = lane; ray < 40; ray += 32) {
-        const int k = ray % 20;
-        const double sgn = ray < 20 ? 1.0 : -1.0;
+    // 20 discs x 2 directions (heart_us.py:158-164): 40 rays, each marched from 8 px in steps of 0.5 px until it leaves the
+    // mask (or the frame; NaN too: the reference raises there).  The distances are 8 + m / 2, exact however they are formed.
+    auto inside = [&](double pr, double pc, double vr, double vc, double dist) -> bool {
+        const double y = rint(__dadd_rn(pr, __dmul_rn(dist, vr))), x = rint(__dadd_rn(pc, __dmul_rn(dist, vc)));
+        if (!(y >= 0.0 && y < (double)vh && x >= 0.0 && x < (double)vw)) return false;
+        return mv.bit((int)y, (int)x);
+    };
+    double d_first = 0.0, d_neg2 = 0.0;
+    {   // rays 0..31, one per lane: lane k < 20 = disc k along +normal, lane 20 + k = disc k < 12 along -normal
+        const int k = lane % 20;
+        const double sgn = lane < 20 ? 1.0 : -1.0;
         const double frac = __dmul_rn((double)k, 0.05);                         // np.linspace(0, 1, 20, endpoint=False)
         const double pr = __dadd_rn(mid_r, __dmul_rn(dir_r, frac)), pc = __dadd_rn(mid_c, __dmul_rn(dir_c, frac));
         const double vr = sgn * nr, vc = sgn * nc;
         double dist = 8.0;
-        for (;;) {
-            const double y = rint(__dadd_rn(pr, __dmul_rn(dist, vr))), x = rint(__dadd_rn(pc, __dmul_rn(dist, vc)));
-            if (!(y >= 0.0 && y < (double)vh && x >= 0.0 && x < (double)vw)) break;   // out of bounds (NaN too: the reference raises there)
-            if (!mv.bit((int)y, (int)x)) break;
-            dist += 0.5;
-        }
-        if (ray < 20) d_pos = dist; else if (ray < 32) d_neg = dist; else d_neg2 = dist;
+        while (inside(pr, pc, vr, vc, dist)) dist += 0.5;
+        d_first = dist;
     }
-    // lane k < 20 holds d_pos of disc k; d_neg of disc k sits in lane 20 + k (k < 12) or lane k - 12 (second round)
-    const double neg_a = __shfl_sync(FULL, d_neg, (lane + 20) & 31);
-    const double neg_b = __shfl_sync(FULL, d_neg2, (lane + 20) & 31);            // lane k - 12 == (k + 20) & 31 for k >= 12
+    {   // rays 32..39 = discs 12..19 along -normal: four lanes per ray test four consecutive distances per iteration
+        const int q = lane >> 2, ph = lane & 3;
+        const double frac = __dmul_rn((double)(12 + q), 0.05);
+        const double pr = __dadd_rn(mid_r, __dmul_rn(dir_r, frac)), pc = __dadd_rn(mid_c, __dmul_rn(dir_c, frac));
+        const double vr = -nr, vc = -nc;
+        double dist = 8.0 + 0.5 * (double)ph;
+        bool found = false;
+        for (;;) {
+            const bool out = found || !inside(pr, pc, vr, vc, dist);
+            const unsigned grp = (__ballot_sync(FULL, out) >> (4 * q)) & 0xfu;
+            if (!found && grp) {                                                 // the first distance of this ray that is out
+                found = true;
+                d_neg2 = (dist - 0.5 * (double)ph) + 0.5 * (double)(__ffs(grp) - 1);
+            }
+            if (__all_sync(FULL, found)) break;
+            dist += 2.0;
+        }
+    }
+    // lane k < 20 holds d_pos of disc k; d_neg of disc k sits in lane 20 + k (k < 12) or in lanes 4 (k - 12) .. + 3
+    const double neg_a = __shfl_sync(FULL, d_first, (lane + 20) & 31);
+    const double neg_b = __shfl_sync(FULL, d_neg2, (4 * (lane - 12)) & 31);
+    const double d_pos = d_first;
     if (lane < 20) dout[lane] = __dmul_rn(__dadd_rn(d_pos, lane < 12 ? neg_a : neg_b), spacing);
     if (lane == 0) step_out[g] = __dmul_rn(0.5 * sqrt((double)a_len2), spacing) / 20.0;
 }
