@@ -66,6 +66,24 @@ struct MaskView {
         return (int)((x0 & 3u) | ((x1 & 3u) << 2));
     }
 };
+// The tracer's view of a plain mask: the walk moves one cell at a time, so the two row words under the current cell stay in
+// registers and a vertical step loads ONE word, a horizontal step inside a word none (every thread of a warp reads its own
+// mask: each load instruction is 32 separate sectors, which is what bounds the kernel).
+struct CellCache {
+    const uint32_t* m;
+    int rr, ww;            // cached: words ww of rows rr (wa) and rr + 1 (wb)
+    uint32_t wa, wb;
+    __device__ __forceinline__ int cell(int r0, int c0) {          // as MaskView::cell; r0 <= 254, c0 <= 254
+        const int w = c0 >> 5, b = c0 & 31;
+        if (w == ww && r0 == rr + 1) { wa = wb; wb = m[r0 * 8 + 8 + w]; }
+        else if (w == ww && r0 == rr - 1) { wb = wa; wa = m[r0 * 8 + w]; }
+        else if (w != ww || r0 != rr) { wa = m[r0 * 8 + w]; wb = m[r0 * 8 + 8 + w]; }
+        rr = r0; ww = w;
+        uint32_t x0 = wa >> b, x1 = wb >> b;
+        if (b == 31) { x0 |= m[r0 * 8 + w + 1] << 1; x1 |= m[r0 * 8 + 8 + w + 1] << 1; }
+        return (int)((x0 & 3u) | ((x1 & 3u) << 2));
+    }
+};
 // a cell's second segment (saddle cases): the one starting at L (case 6) / B (case 9)
 __device__ __forceinline__ int seg_rank(int cs, int from_edge) {
     return (cs == 6 && from_edge == 2) || (cs == 9 && from_edge == 1);
@@ -130,7 +148,9 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
     }
     if (fr < 0) { npts[g] = 0; return; }                          // find_contours() == [] -> IndexError
     // pass A: walk backwards from the first segment to the chain start, or around the loop
-    const int cs0 = mv.cell(fr, fc);
+    CellCache cc{m, -4, -4, 0u, 0u};
+    auto cell_at = [&](int r, int c) { return row_index ? mv.cell(r, c) : cc.cell(r, c); };
+    const int cs0 = cell_at(fr, fc);
     const int f0 = (int)(FIRST_FROM >> (2 * cs0)) & 3;
     int r0 = fr, c0 = fc, fe = f0, cs = cs0;                      // current segment = (cell, from-edge); cs = the cell's case
     int sr = fr, sc = fc, sf = f0;                                // start segment of pass B
@@ -145,7 +165,7 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
         if (fe == 0) { pr = r0 - 1; pe = 1; } else if (fe == 1) { pr = r0 + 1; pe = 0; }
         else if (fe == 2) { pc = c0 - 1; pe = 3; } else { pc = c0 + 1; pe = 2; }
         if (pr < 0 || pr > RM || pc < 0 || pc > CM) { sr = r0; sc = c0; sf = fe; break; }     // open chain start
-        cs = mv.cell(pr, pc);
+        cs = cell_at(pr, pc);
         r0 = pr; c0 = pc; fe = from_of_to(cs, pe);
         if (r0 == fr && c0 == fc && fe == f0) { closed = true; break; }
     }
@@ -156,21 +176,34 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
         else if (lt == 2) { nc = lc - 1; ne = 3; } else { nc = lc + 1; ne = 2; }
         sr = nr; sc = nc; sf = ne;
     }
-    // pass B: forward, recording points
+    // pass B: forward, recording points -- four at a time (one 16-byte store instead of four scattered 4-byte ones)
     int n = 0;
+    uint32_t q0 = 0u, q1 = 0u, q2 = 0u, q3 = 0u;
+    auto push = [&](uint32_t pt) {
+        const int slot = n & 3;
+        if (slot == 0) q0 = pt; else if (slot == 1) q1 = pt; else if (slot == 2) q2 = pt; else q3 = pt;
+        ++n;
+        if ((n & 3) == 0) reinterpret_cast<uint4*>(out)[(n >> 2) - 1] = make_uint4(q0, q1, q2, q3);
+    };
     r0 = sr; c0 = sc; fe = sf;
-    out[n++] = edge_point(r0, c0, fe);
+    push(edge_point(r0, c0, fe));
     bool overflow = false;
     for (;;) {
-        const int te = to_of_from(mv.cell(r0, c0), fe);
+        const int te = to_of_from(cell_at(r0, c0), fe);
         if (n >= SP_NMAX) { overflow = true; break; }
-        out[n++] = edge_point(r0, c0, te);
+        push(edge_point(r0, c0, te));
         int nr = r0, nc = c0, ne;
         if (te == 0) { nr = r0 - 1; ne = 1; } else if (te == 1) { nr = r0 + 1; ne = 0; }
         else if (te == 2) { nc = c0 - 1; ne = 3; } else { nc = c0 + 1; ne = 2; }
         if (nr < 0 || nr > RM || nc < 0 || nc > CM) break;         // open chain end
         r0 = nr; c0 = nc; fe = ne;
         if (closed && r0 == sr && c0 == sc && fe == sf) break;
+    }
+    if (n & 3) {                                                   // the last, incomplete group
+        const int base = n & ~3;
+        out[base] = q0;
+        if ((n & 3) > 1) out[base + 1] = q1;
+        if ((n & 3) > 2) out[base + 2] = q2;
     }
     npts[g] = overflow ? -1 : n;
 }

@@ -80,6 +80,9 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
     const int64_t g = blockIdx.x * (int64_t)SP_WARPS + wid;
     if (g >= n_masks) return;
     const int n = npts[g];
+    // the rays at the end read the mask itself: ask for its 64 lines now
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(masks + g * CUB200_MASK_WORDS + lane * 64));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(masks + g * CUB200_MASK_WORDS + lane * 64 + 32));
     double* dout = diam_out + g * 20;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     if (n < 3) {                                       // no contour / no chord: the reference raises
@@ -108,10 +111,15 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
             // |degrees(arctan2(d_row, d_col))| <= 45  <=>  d_col > 0 and |d_row| <= d_col  (zero vector: NaN distances)
             const Chord cand{ar * ar + ac * ac, i, j};
             if (ac > 0 && abs(ar) <= ac && chord_better(cand, best)) {
-                const int k = (i + j) >> 1;
-                const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);
-                const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
-                if (k == j || cr * cr <= 256ll * cand.len2) key = ((uint32_t)cand.len2 << 5) | (uint32_t)(31 - lane);
+                const int64_t lim = 256ll * cand.len2;
+                auto near = [&](int k) {                 // is intermediate point k within 8 px of the chord's line?
+                    const int br = ir - (int)(P[k] & 0xffff), bc = ic - (int)(P[k] >> 16);
+                    const int64_t cr = (int64_t)ar * bc - (int64_t)ac * br;
+                    return cr * cr <= lim;
+                };
+                const int q = (i - j) >> 2;              // the middle, then the quarter points (q >= 1: strictly inside)
+                if (near((i + j) >> 1) && (q == 0 || (near(j + q) && near(i - q))))
+                    key = ((uint32_t)cand.len2 << 5) | (uint32_t)(31 - lane);
             }
         }
         for (;;) {
@@ -150,6 +158,16 @@ simpson_diameters_kernel(const uint32_t* __restrict__ masks, const uint32_t* __r
                 const int j = j0 + CHORD_COARSE * lane;
                 try_pairs(i, ir, ic, j < i ? j : 0, j < i);
             }
+        }
+    }
+    // ... refined around the chord it found: every i within a coarse step of its i against the 32 j around its j, so that
+    // the bound the next steps prune with is (nearly always) the final one
+    if (best.len2 > 0) {
+        const int ci = best.i, cj = best.j;
+        for (int i = min(n - 1, ci + CHORD_COARSE - 1); i >= max(2, ci - (CHORD_COARSE - 1)); --i) {
+            const int j = cj - 16 + lane;
+            const bool on = j >= 0 && j < i;
+            try_pairs(i, P[i] & 0xffff, P[i] >> 16, on ? j : 0, on);
         }
     }
     // (2) the points that cannot be the i / the j of the answer, and the column / row ranges of the others per block of 32
