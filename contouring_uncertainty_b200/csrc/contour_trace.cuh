@@ -115,11 +115,16 @@ contour_trace_kernel(const uint32_t* __restrict__ masks, int64_t n_masks, const 
     int fr = -1, fc = -1;
     if (!row_index) {
         uint32_t a[8], b[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) a[w] = m[w];
+        const uint4* m4 = reinterpret_cast<const uint4*>(m);      // two 16-byte loads per row (one sector per thread)
+        {
+            const uint4 u = m4[0], v = m4[1];
+            a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w; a[4] = v.x; a[5] = v.y; a[6] = v.z; a[7] = v.w;
+        }
         for (int r0 = 0; r0 < 255 && fr < 0; ++r0) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) b[w] = m[(r0 + 1) * 8 + w];
+            {
+                const uint4 u = m4[2 * r0 + 2], v = m4[2 * r0 + 3];
+                b[0] = u.x; b[1] = u.y; b[2] = u.z; b[3] = u.w; b[4] = v.x; b[5] = v.y; b[6] = v.z; b[7] = v.w;
+            }
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const uint32_t a1 = (a[w] >> 1) | ((w < 7 ? a[w < 7 ? w + 1 : 7] : 0u) << 31);

@@ -430,6 +430,7 @@ extern "C" int cub200_mask_lv_length_myo(const uint32_t* lv_masks, const uint32_
     using namespace cub200;
     if (n_masks == 0) return 0;
     if (!lv_masks || !myo_masks || !length_out || !corners_out || !workspace || n_masks < 0 || n_masks > 0x7fffffff) return CUB200_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(lv_masks) | reinterpret_cast<uintptr_t>(workspace)) & 15u) return CUB200_EINVAL;   // the tracer's 16-byte accesses
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* pts = reinterpret_cast<uint32_t*>(workspace);
     int32_t* npts = reinterpret_cast<int32_t*>(pts + n_masks * SP_NMAX);
@@ -451,6 +452,7 @@ extern "C" int cub200_mask_lv_length(const uint32_t* masks, int64_t n_masks, dou
     if (!masks || !length_out || !workspace || n_masks < 0 || n_masks > 0x7fffffff || !(smoothing_factor >= 0.0) ||
         smoothing_factor > 5e-3)
         return CUB200_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(masks) | reinterpret_cast<uintptr_t>(workspace)) & 15u) return CUB200_EINVAL;   // the tracer's 16-byte accesses
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* pts = reinterpret_cast<uint32_t*>(workspace);
     int32_t* npts = reinterpret_cast<int32_t*>(pts + n_masks * SP_NMAX);

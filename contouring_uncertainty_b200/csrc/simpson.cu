@@ -390,6 +390,7 @@ extern "C" int64_t cub200_simpson_workspace_bytes(int64_t n_masks) {
 static int simpson_launch(const uint32_t* masks, int64_t n_masks, const uint16_t* row_index, const uint16_t* col_index, int vh, int vw,
                           double spacing, double* diam_out, double* step_out, int32_t* npts_out, void* workspace, cudaStream_t st) {
     using namespace cub200;
+    if ((reinterpret_cast<uintptr_t>(masks) | reinterpret_cast<uintptr_t>(workspace)) & 15u) return CUB200_EINVAL;   // 16-byte loads / stores
     uint32_t* pts = reinterpret_cast<uint32_t*>(workspace);
     int32_t* npts = reinterpret_cast<int32_t*>(pts + n_masks * SP_NMAX);
     const size_t idx_smem = row_index ? sizeof(uint16_t) * (size_t)(vh + vw) : 0;

@@ -370,12 +370,12 @@ int cub200_seq_skew_sample(const float* mu, const float* cov, const float* alpha
  * admissible base chord, the apex and the 20 disc diameters.
  *   replaces  _compute_diameters (+ helpers)      vital/vital/metrics/evaluate/clinical/heart_us.py:74-167
  *             skimage.measure.find_contours        (third party, restated; oracle/port.py::find_contours)
- *   masks (n_masks, 2048) uint32 bit-packed (cub200_rasterize_contours / cub200_sample_raster_aggregate)
+ *   masks (n_masks, 2048) uint32 bit-packed (cub200_rasterize_contours / cub200_sample_raster_aggregate), 16-byte aligned
  *   spacing: isotropic pixel size in mm (anisotropic spacing = PIL nearest-neighbour stretch first: not done here)
  *   diam_out (n_masks, 20) fp64 mm; step_out (n_masks) fp64 = mid-line length * spacing / 20; both NaN when the
  *   reference would raise (empty mask, no admissible chord, contour longer than CUB200_SIMPSON_MAX_POINTS)
  *   npts_out optional (n_masks) int32 contour length (0 none, -1 too long)
- *   workspace: cub200_simpson_workspace_bytes(n_masks) bytes of device memory
+ *   workspace: cub200_simpson_workspace_bytes(n_masks) bytes of device memory, 16-byte aligned
  */
 int64_t cub200_simpson_workspace_bytes(int64_t n_masks);
 int cub200_simpson_diameters(const uint32_t* masks, int64_t n_masks, double spacing, double* diam_out, double* step_out,
@@ -513,7 +513,7 @@ int cub200_seg_entropy(const float* probs, const uint32_t* masks, int64_t n_img,
  *   length_out (n_masks) f64: sum of the segment lengths of the base-less contour; NaN where the reference raises
  *   (no contour, fewer than two base corners, more than CUB200_SIMPSON_MAX_POINTS contour points).
  *   Optional: corners_out (n_masks, 2, 2) f64 = (left, right) base corners as (row, col); npts_out (n_masks) i32 = points
- *   of the base-less contour.  workspace: cub200_simpson_workspace_bytes(n_masks).
+ *   of the base-less contour.  workspace: cub200_simpson_workspace_bytes(n_masks).  masks and workspace 16-byte aligned.
  * GLS of frame k vs frame 0 = (L_k - L_0) / L_0 * 100.
  */
 #define CUB200_GLS_TABLE_STRIDE 48

@@ -44,18 +44,20 @@ BIND = {
     "skew_pdf_grid_kernel": "issue slots (fp64 special functions per grid cell), 2.2 GB written per 512 images",
     "skew_sample_kernel": "issue slots (ALU + XU), tables fed from L2 (hit rate > 93 %)",
     "seq_condition_kernel": "latency / HBM: per-sample 84-dim conditioning",
-    "contour_trace_kernel": "memory latency: one thread walks one mask's boundary (dependent loads)",
-    "simpson_diameters_kernel": "issue slots: exact integer chord search, one warp per mask",
+    "contour_trace_kernel": "DRAM / L2 sectors: one thread walks one mask's boundary, 32 separate sectors per load instruction, the mask read 2.7 times (scan + two walks, evicted in between)",
+    "simpson_diameters_kernel": "issue slots: exact integer chord search with exact pruning, one warp per mask",
+    "psm_sample_direct_kernel": "latency: the factor recursion on one column per (pair, sample) law, fp64",
     "simpson_volumes_kernel": "latency (small)",
 }
 PHASES = {
     2: {"dsnt": "dsnt_moments_kernel<1>", "factor": "psm_factor_kernel<4>", "sample": "sample_contours_kernel<34>", "raster": "raster_kernel<0>", "finalize": "finalize_maps_kernel"},
     3: {"dsnt": "dsnt_moments_kernel<1>", "pdf_tables": "skew_pdf_grid_kernel", "skew_sampler": "skew_sample_kernel", "raster": "raster_kernel<0>", "finalize": "finalize_maps_kernel"},
-    # the sequence sampler's dominant kernel is the per-sample factor of the second instant (one warp per sample: <1>)
-    4: {"sequence_sampler": "psm_factor_kernel<1>", "raster_masks": "raster_kernel<0>", "simpson_diameters": "simpson_diameters_kernel", "volumes": "simpson_volumes_kernel"},
+    # the sequence sampler's dominant kernel: the second instant's single sample per law (psm_sample_direct_kernel); config 5's
+    # capture (r02h) predates it and still lists the per-sample factor it replaced
+    4: {"sequence_sampler": "psm_sample_direct_kernel", "raster_masks": "raster_kernel<0>", "simpson_diameters": "simpson_diameters_kernel", "volumes": "simpson_volumes_kernel"},
     5: {"dsnt": "dsnt_moments_kernel<1>", "sequence_sampler": "psm_factor_kernel<1>", "raster": "raster_kernel<0>", "finalize_fac": "finalize_maps_kernel"},
 }
-SRC = {2: "r02g_ncu_full_summary_config2_step.csv", 3: "r02h_ncu_full_summary_config3.csv", 4: "r02h_ncu_full_summary_config4.csv", 5: "r02h_ncu_full_summary_config5.csv"}
+SRC = {2: "r02g_ncu_full_summary_config2_step.csv", 3: "r02h_ncu_full_summary_config3.csv", 4: "r02m_ncu_full_summary_config4.csv", 5: "r02h_ncu_full_summary_config5.csv"}
 
 
 def main():
