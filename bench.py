@@ -330,15 +330,38 @@ class LogitsPSM(PathConfig):
         """The step (+ the metric buffering of the exchange) as ONE CUDA-graph launch per step: one engine.GraphedStep per
         input batch of the pool, all advancing the same device-side step counter."""
         ring = exch.ring if exch is not None else None
-        first = self.E.GraphedStep(self.eng, self.ws, self.pool[0], seed=1000, metric_ring=ring)
-        self.gs = [first] + [self.E.GraphedStep(self.eng, self.ws, lg, seed=1000, metric_ring=ring, step=first.step) for lg in self.pool[1:]]
+        if not self.pipelined:
+            first = self.E.GraphedStep(self.eng, self.ws, self.pool[0], seed=1000, metric_ring=ring)
+            self.gs = [first] + [self.E.GraphedStep(self.eng, self.ws, lg, seed=1000, metric_ring=ring, step=first.step) for lg in self.pool[1:]]
+            return
+        # software-pipelined: the graph of batch b also runs the DSNT pass of batch b + 1 (side branch, into the other pair of
+        # moment buffers) beside the factor / sampler / rasteriser / finalize of batch b -- every replay does one whole step's
+        # work, the HBM-bound kernel of one batch under the issue-bound ones of the other (POOL is even: the pairs alternate)
+        torch = self.torch
+        self.moments = [(self.ws.mu, self.ws.cov), (torch.empty_like(self.ws.mu), torch.empty_like(self.ws.cov))]
+        for b in (0, 1):
+            self.eng.dsnt_into(self.ws, self.pool[b], *self.moments[b])
+        self.gs, step = [], None
+        for b in range(self.POOL):
+            g = self.E.GraphedStep(self.eng, self.ws, self.pool[b], seed=1000, metric_ring=ring, step=step,
+                                   prefetch=(self.pool[(b + 1) % self.POOL], self.moments[b % 2], self.moments[(b + 1) % 2]))
+            step = g.step
+            self.gs.append(g)
+        self.primed_for = None
+
+    pipelined = False
+    primed_for = None          # the batch whose moments the pipelined graphs will find in place at the next replay
 
     def step(self, i):
         b = (i + self.rank) % self.POOL
-        if self.gs is not None:
-            self.gs[b].replay()
-        else:
+        if self.gs is None:
             self.eng.run_into(self.ws, self.pool[b], seed=1000 + i)
+            return
+        if self.pipelined:
+            if self.primed_for != b:                     # first step of a run of consecutive steps: nobody prefetched batch b
+                self.eng.dsnt_into(self.ws, self.pool[b], *self.moments[b % 2])
+            self.primed_for = (b + 1) % self.POOL
+        self.gs[b].replay()
 
     def metric_values(self):
         return self.ws.area, self.E.metric_sums(self.ws.area, out=self.sums)
@@ -346,6 +369,7 @@ class LogitsPSM(PathConfig):
     def step_evented(self, i, tm):
         """The launches of engine.run_into, one by one, with an event between the phases (same buffers, no allocation)."""
         E, ws, eng = self.E, self.ws, self.eng
+        self.primed_for = None                                        # this leg overwrites ws.mu / ws.cov
         logits = self.pool[(i + self.rank) % self.POOL]
         L, n, T = E.nat.lib(), self.n, self.T
         st = self.torch.cuda.current_stream(self.dev).cuda_stream
@@ -688,6 +712,7 @@ def run_ours(args):
     exch = PAR.MetricExchange(vals0.shape[0], vals0.shape[1], every, dev) if (world > 1 or args.force_exchange) else None
     graphed = cfg_id in (1, 2) and not args.no_graph      # sub-millisecond steps: one graph launch instead of 8-12 launches
     if graphed:
+        cfg.pipelined = args.pipeline
         cfg.enable_graph(exch)
 
     def step(i):
@@ -843,7 +868,7 @@ def run_ours(args):
                          else "per-step working set (sampled contours / masks written and re-read, %.0f MB) larger than L2" % (units * 168 * 2 / 1e6) if units * 168 * 2 > 130e6
                          else "working set smaller than L2 (latency case): no flush",
                    "inputs": (f"{cfg.POOL} distinct batches cycled per rank (same pool on every rank, phase-shifted by rank)" if cfg_id in (1, 2) else "one batch per rank"),
-                   "rng": "in-kernel Philox4x32-10", "launch": "CUDA graph replay (one launch per step)" if graphed else "eager (one launch per kernel)", "exchange": f"one all_gather per {every} steps ({n_collectives} in the timed run)" if world > 1 else "none (1 GPU)"},
+                   "rng": "in-kernel Philox4x32-10", "launch": ("CUDA graph replay (one launch per step); the DSNT pass of batch i + 1 on a side branch beside the sampler / rasteriser of batch i" if getattr(cfg, "pipelined", False) else "CUDA graph replay (one launch per step)") if graphed else "eager (one launch per kernel)", "exchange": f"one all_gather per {every} steps ({n_collectives} in the timed run)" if world > 1 else "none (1 GPU)"},
         "contour_pixels_per_s": value * HW * HW,
         "kernel_ms": km,
         "roofline": roof(dominant),
@@ -872,6 +897,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange-every", type=int, default=0, help="steps per all_gather of the metric distributions (0 = one per run)")
     ap.add_argument("--no-graph", action="store_true", help="configs 1 / 2: launch the step's kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--pipeline", action="store_true", help="configs 1 / 2: the graph of batch i also runs the DSNT pass of batch i + 1 on a side branch (engine.GraphedStep(prefetch=...)): +1.1 % on one B200")
     ap.add_argument("--force-exchange", action="store_true", help="diagnostic: run the per-step metric push / block shipping on one GPU too")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (profiling runs)")

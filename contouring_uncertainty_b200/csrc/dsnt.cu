@@ -23,7 +23,17 @@
 
 namespace cub200 {
 
-constexpr int DSNT_THREADS = 256;
+#ifndef CUB200_DSNT_RESIDENT
+#define CUB200_DSNT_RESIDENT 3   // CTAs per SM of the persistent launch (= what __launch_bounds__ below allows)
+#endif
+#ifndef CUB200_DSNT_WARPS
+#define CUB200_DSNT_WARPS 8      // warps per CTA
+#endif
+#ifndef CUB200_DSNT_MINBLOCKS
+#define CUB200_DSNT_MINBLOCKS 3
+#endif
+constexpr int DSNT_NW = CUB200_DSNT_WARPS;
+constexpr int DSNT_THREADS = 32 * DSNT_NW;
 constexpr int DSNT_W = 256;
 constexpr int ROWS_PER_TILE = 4;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -41,13 +51,13 @@ struct DsntSlot {
 };
 
 template <bool IS_LOGIT>
-__global__ void __launch_bounds__(DSNT_THREADS, 3)
+__global__ void __launch_bounds__(DSNT_THREADS, CUB200_DSNT_MINBLOCKS)
 dsnt_moments_kernel(const float* __restrict__ heat, int64_t n_maps, int use_covar,
                     float* __restrict__ norm_out, float* __restrict__ pix_mu, float* __restrict__ pix_sigma,
                     int64_t rows_per_cta, DsntSlot* __restrict__ slots) {
-    __shared__ float s_m[8];
-    __shared__ int s_rc[8], s_cc[8];
-    __shared__ double s_red[8][6];
+    __shared__ float s_m[DSNT_NW];
+    __shared__ int s_rc[DSNT_NW], s_cc[DSNT_NW];
+    __shared__ double s_red[DSNT_NW][6];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total_rows = n_maps * DSNT_W;
@@ -68,7 +78,7 @@ dsnt_moments_kernel(const float* __restrict__ heat, int64_t n_maps, int use_cova
         int cc = 0;                            // column of the running max (warp-uniform)
 
         // the 8 warps take the tiles of the part round robin: at any time the CTA streams 32 consecutive rows
-        for (int r_tile = lo + warp * ROWS_PER_TILE; r_tile < hi; r_tile += 8 * ROWS_PER_TILE) {
+        for (int r_tile = lo + warp * ROWS_PER_TILE; r_tile < hi; r_tile += DSNT_NW * ROWS_PER_TILE) {
             float4 v[ROWS_PER_TILE][2];
 #pragma unroll
             for (int q = 0; q < ROWS_PER_TILE; ++q) {
@@ -140,7 +150,7 @@ dsnt_moments_kernel(const float* __restrict__ heat, int64_t n_maps, int use_cova
         float mstar = s_m[0];
         int best = 0;
 #pragma unroll
-        for (int w = 1; w < 8; ++w)
+        for (int w = 1; w < DSNT_NW; ++w)
             if (s_m[w] > mstar) { mstar = s_m[w]; best = w; }
         const int rcb = s_rc[best];
         const int ccb = s_cc[best];
@@ -171,7 +181,7 @@ dsnt_moments_kernel(const float* __restrict__ heat, int64_t n_maps, int use_cova
         if (threadIdx.x != 0) continue;
 
         double a[6] = {0, 0, 0, 0, 0, 0};
-        for (int w = 0; w < 8; ++w)
+        for (int w = 0; w < DSNT_NW; ++w)
             for (int q = 0; q < 6; ++q) a[q] += s_red[w][q];
         int rcs = rcb, ccs = ccb;                              // centre of the moments (of the heatmap's after a merge)
         if (hi - lo != DSNT_W) {
@@ -269,7 +279,7 @@ extern "C" int cub200_dsnt_moments(const float* heat, int64_t n_maps, int h, int
     if (workspace) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int64_t total_rows = n_maps * DSNT_W, resident = 3LL * sms;
+        const int64_t total_rows = n_maps * DSNT_W, resident = (int64_t)CUB200_DSNT_RESIDENT * sms;
         // measured (tools/bench_dsnt.py): equal row ranges win when the one-CTA-per-heatmap grid would be 1..6 waves (the
         // headline: 1344 heatmaps, 66.0 -> 63.6 us) or a small fraction of one (21 heatmaps: 16.4 -> 14.4 us); with many
         // waves the dynamic CTA scheduler already balances, and staggers the per-heatmap epilogues better (512 images: 404 us

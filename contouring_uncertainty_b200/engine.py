@@ -1225,27 +1225,51 @@ class UncertaintyEngine:
         ``after_raster``: callable invoked once the sampler / rasteriser launches are queued (contours and areas final), before
         finalize_maps: the place to fork work that only needs the per-sample outputs.  Returns ``ws``.
         """
+        self.dsnt_into(ws, logits, ws.mu, ws.cov, stream=stream)
+        return self.run_tail_into(ws, ws.mu, ws.cov, seed=seed, stream=stream, sample_offset=sample_offset, step_dev=step_dev,
+                                  after_raster=after_raster)
+
+    def dsnt_into(self, ws: Workspace, logits: torch.Tensor, mu: torch.Tensor, cov: torch.Tensor,
+                  stream: Optional[torch.cuda.Stream] = None):
+        """First launch of ``run_into``: the DSNT moments of ``logits`` into ``mu`` (n_img,21,2) / ``cov`` (n_img,21,2,2) fp32
+        (``ws.mu`` / ``ws.cov`` or buffers of the same shape: a pipelined caller keeps two pairs)."""
         if logits.dtype != torch.float32 or not logits.is_cuda or not logits.is_contiguous() or \
                 tuple(logits.shape) != (ws.n_img, K, HW, HW):
             raise ValueError(f"logits must be ({ws.n_img},{K},{HW},{HW}) fp32 CUDA contiguous")
+        self._check_moments(ws, mu, cov)
+        st = (stream or torch.cuda.current_stream(ws.device)).cuda_stream
+        with torch.cuda.device(ws.device):
+            nat.check(nat.lib().cub200_dsnt_moments(logits.data_ptr(), ws.n_img * K, HW, HW, 1, int(self.covar), None, mu.data_ptr(),
+                                                    cov.data_ptr(), ws.dsnt_ws.data_ptr(), st), "cub200_dsnt_moments")
+
+    @staticmethod
+    def _check_moments(ws: Workspace, mu: torch.Tensor, cov: torch.Tensor):
+        for t, ref, name in ((mu, ws.mu, "mu"), (cov, ws.cov, "cov")):
+            if t.dtype != ref.dtype or t.device != ref.device or t.shape != ref.shape or not t.is_contiguous():
+                raise ValueError(f"{name} must be {tuple(ref.shape)} {ref.dtype} contiguous on {ref.device}")
+
+    def run_tail_into(self, ws: Workspace, mu: torch.Tensor, cov: torch.Tensor, seed: int = 0,
+                      stream: Optional[torch.cuda.Stream] = None, sample_offset: int = 0,
+                      step_dev: Optional[torch.Tensor] = None, after_raster=None):
+        """``run_into`` after its DSNT launch: sampler factor, sampling + rasterisation + aggregation, maps, from the moments
+        in ``mu`` / ``cov``."""
+        self._check_moments(ws, mu, cov)
         L = nat.lib()
         st = (stream or torch.cuda.current_stream(ws.device)).cuda_stream
         n, T = ws.n_img, ws.t_a
         with torch.cuda.device(ws.device):
-            nat.check(L.cub200_dsnt_moments(logits.data_ptr(), n * K, HW, HW, 1, int(self.covar), None, ws.mu.data_ptr(),
-                                            ws.cov.data_ptr(), ws.dsnt_ws.data_ptr(), st), "cub200_dsnt_moments")
             if self.sampler == "psm":
                 m = self.model
-                nat.check(L.cub200_psm_factor(m.pack.data_ptr(), ws.mu.data_ptr(), ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st),
+                nat.check(L.cub200_psm_factor(m.pack.data_ptr(), mu.data_ptr(), cov.data_ptr(), n, ws.a_t.data_ptr(), st),
                           "cub200_psm_factor")
             else:
-                nat.check(L.cub200_naive_factor(ws.cov.data_ptr(), n, ws.a_t.data_ptr(), st), "cub200_naive_factor")
+                nat.check(L.cub200_naive_factor(cov.data_ptr(), n, ws.a_t.data_ptr(), st), "cub200_naive_factor")
             if stream is None:
                 ws.diff.zero_()
             else:
                 with torch.cuda.stream(stream):
                     ws.diff.zero_()
-            nat.check(L.cub200_sample_raster_aggregate(ws.mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
+            nat.check(L.cub200_sample_raster_aggregate(mu.data_ptr(), ws.a_t.data_ptr(), ws.zdim, None,
                                                        int(seed) & (2**64 - 1), int(sample_offset) & (2**64 - 1), n, T, 1,
                                                        ws.contours.data_ptr(),
                                                        ws.area.data_ptr(), ws.diff.data_ptr(), 1, None, ws.raster_ws.data_ptr(),
@@ -1283,10 +1307,23 @@ class GraphedStep:
     """
 
     def __init__(self, engine: "UncertaintyEngine", ws: Workspace, logits: torch.Tensor, seed: int = 0,
-                 metric_ring: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None):
+                 metric_ring: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None, prefetch=None):
         """``step``: an existing device counter to share (several GraphedSteps over different input buffers that advance one
-        sequence of steps); by default the object owns a fresh one.  Capturing leaves the counter at 0."""
+        sequence of steps); by default the object owns a fresh one.  Capturing leaves the counter at 0.
+
+        ``prefetch`` = (next_logits, (mu, cov), (mu_next, cov_next)): SOFTWARE-PIPELINED step for a stream of batches.  The
+        moments of THIS step's batch are expected in (mu, cov) already -- left there by the previous step's replay, or by
+        ``engine.dsnt_into`` for the first one -- and the graph runs the DSNT pass of ``next_logits`` into (mu_next, cov_next)
+        on a side branch beside this batch's factor / sampler / rasteriser / finalize: the HBM-bound kernel streams while the
+        issue-bound ones compute (tools/overlap_probe.py).  ``logits`` is then only the record of which batch this step is."""
         self.engine, self.ws, self.logits, self.seed, self.ring = engine, ws, logits, int(seed), metric_ring
+        self.prefetch = prefetch
+        if prefetch is not None:
+            nxt, (mu_c, cov_c), (mu_n, cov_n) = prefetch
+            engine._check_moments(ws, mu_c, cov_c)
+            engine._check_moments(ws, mu_n, cov_n)
+            if mu_c.data_ptr() == mu_n.data_ptr() or cov_c.data_ptr() == cov_n.data_ptr():
+                raise ValueError("prefetch: the next batch's moments need their own buffers")
         dev = ws.device
         if metric_ring is not None:
             metric_ring = nat.require_cuda(metric_ring, torch.int32, "metric_ring")
@@ -1295,8 +1332,9 @@ class GraphedStep:
         self.step = torch.zeros((1,), dtype=torch.int64, device=dev) if step is None else step
         if self.step.dtype != torch.int64 or self.step.numel() != 1 or self.step.device != dev:
             raise ValueError("step must be one int64 on the workspace's device")
-        self.stream = torch.cuda.Stream(dev)
+        self.stream = torch.cuda.Stream(dev, priority=-1 if prefetch is not None else 0)
         self.side = torch.cuda.Stream(dev)
+        self.ahead = torch.cuda.Stream(dev) if prefetch is not None else None
         self.graph = torch.cuda.CUDAGraph()
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self.stream):
@@ -1325,7 +1363,15 @@ class GraphedStep:
                 nat.check(L.cub200_metric_pack(self.ws.area.data_ptr(), self.ws.area.numel(), self.ring.data_ptr(),
                                                self.ring.shape[0], self.step.data_ptr(), self.side.cuda_stream), "cub200_metric_pack")
 
-        self.engine.run_into(self.ws, self.logits, seed=self.seed, stream=self.stream, step_dev=self.step, after_raster=fork_pack)
+        if self.prefetch is None:
+            self.engine.run_into(self.ws, self.logits, seed=self.seed, stream=self.stream, step_dev=self.step, after_raster=fork_pack)
+        else:
+            nxt, (mu_c, cov_c), (mu_n, cov_n) = self.prefetch
+            self.ahead.wait_stream(self.stream)                                       # fork: the next batch's DSNT pass
+            self.engine.dsnt_into(self.ws, nxt, mu_n, cov_n, stream=self.ahead)
+            self.engine.run_tail_into(self.ws, mu_c, cov_c, seed=self.seed, stream=self.stream, step_dev=self.step,
+                                      after_raster=fork_pack)
+            self.stream.wait_stream(self.ahead)                                       # join
         if self.ring is not None:
             self.stream.wait_stream(self.side)
         with torch.cuda.device(self.ws.device):

@@ -472,3 +472,37 @@ def test_graphed_step_replays_match_eager_steps_and_fill_the_metric_ring():
     gs.replay()
     torch.cuda.synchronize()
     assert torch.equal(ring[1][:n * T], ws_g.area.reshape(-1))
+
+
+def test_pipelined_graphed_steps_match_eager_steps():
+    """engine.GraphedStep(prefetch=...): a cycle of batches where the graph of batch b also runs the DSNT pass of batch b + 1 on a
+    side branch (two alternating pairs of moment buffers).  Replay i must leave exactly what the eager step i leaves: same
+    kernels on the same inputs, only their order in time differs."""
+    import synth
+    from contouring_uncertainty_b200 import engine as E
+
+    dev = torch.device("cuda:0")
+    n, T, P = 3, 40, 4
+    eng = E.UncertaintyEngine(device=dev)
+    pool = [torch.from_numpy(synth.heatmap_logits(n, seed=20 + b)).to(dev) for b in range(P)]
+    ws_g, ws_e = eng.workspace(n, T), eng.workspace(n, T)
+    moments = [(ws_g.mu, ws_g.cov), (torch.empty_like(ws_g.mu), torch.empty_like(ws_g.cov))]
+    for b in (0, 1):
+        eng.dsnt_into(ws_g, pool[b], *moments[b])
+    gs, step = [], None
+    for b in range(P):
+        g = E.GraphedStep(eng, ws_g, pool[b], seed=5, step=step, prefetch=(pool[(b + 1) % P], moments[b % 2], moments[(b + 1) % 2]))
+        step = g.step
+        gs.append(g)
+    with pytest.raises(ValueError):
+        E.GraphedStep(eng, ws_g, pool[0], seed=5, prefetch=(pool[1], moments[0], moments[0]))
+    eng.dsnt_into(ws_g, pool[0], *moments[0])             # nobody prefetched the first batch
+    for i in range(7):
+        b = i % P
+        gs[b].replay()
+        eng.run_into(ws_e, pool[b], seed=5, sample_offset=i * n * T)
+        torch.cuda.synchronize()
+        assert torch.equal(moments[b % 2][0], ws_e.mu) and torch.equal(moments[b % 2][1], ws_e.cov)
+        assert torch.equal(ws_g.contours, ws_e.contours) and torch.equal(ws_g.area, ws_e.area)
+        assert torch.equal(ws_g.count, ws_e.count) and torch.equal(ws_g.entropy, ws_e.entropy)
+    assert int(step.item()) == 7
