@@ -897,7 +897,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--exchange-every", type=int, default=0, help="steps per all_gather of the metric distributions (0 = one per run)")
     ap.add_argument("--no-graph", action="store_true", help="configs 1 / 2: launch the step's kernels one by one instead of replaying a CUDA graph")
-    ap.add_argument("--no-pipeline", action="store_true", help="configs 1 / 2: every graph runs its own batch's DSNT pass first instead of finding it prefetched by the previous step's graph (engine.GraphedStep(prefetch=...): 1.1 % on one B200, 2.8 % with the exchange buffer at 2 GPUs)")
+    ap.add_argument("--no-pipeline", action="store_true", help="configs 1 / 2: every graph runs its own batch's DSNT pass first instead of finding it prefetched by the previous step's graph (engine.GraphedStep(prefetch=...): 1.1 %% on one B200, 2.8 %% with the exchange buffer at 2 GPUs)")
     ap.add_argument("--force-exchange", action="store_true", help="diagnostic: run the per-step metric push / block shipping on one GPU too")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi (profiling runs)")
