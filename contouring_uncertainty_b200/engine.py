@@ -1230,9 +1230,12 @@ class UncertaintyEngine:
                                   after_raster=after_raster)
 
     def dsnt_into(self, ws: Workspace, logits: torch.Tensor, mu: torch.Tensor, cov: torch.Tensor,
-                  stream: Optional[torch.cuda.Stream] = None):
+                  stream: Optional[torch.cuda.Stream] = None, persistent: bool = True):
         """First launch of ``run_into``: the DSNT moments of ``logits`` into ``mu`` (n_img,21,2) / ``cov`` (n_img,21,2,2) fp32
-        (``ws.mu`` / ``ws.cov`` or buffers of the same shape: a pipelined caller keeps two pairs)."""
+        (``ws.mu`` / ``ws.cov`` or buffers of the same shape: a pipelined caller keeps two pairs).  ``persistent=False``: one CTA
+        per heatmap instead of one wave of equal row ranges (``cub200_dsnt_moments`` without a workspace) -- for a launch that
+        shares the GPU with other kernels.  A heatmap that the persistent launch splits between two CTAs is summed in another
+        order there: the two agree to fp32 rounding of the moments (~1e-7 relative), not bit for bit."""
         if logits.dtype != torch.float32 or not logits.is_cuda or not logits.is_contiguous() or \
                 tuple(logits.shape) != (ws.n_img, K, HW, HW):
             raise ValueError(f"logits must be ({ws.n_img},{K},{HW},{HW}) fp32 CUDA contiguous")
@@ -1240,7 +1243,7 @@ class UncertaintyEngine:
         st = (stream or torch.cuda.current_stream(ws.device)).cuda_stream
         with torch.cuda.device(ws.device):
             nat.check(nat.lib().cub200_dsnt_moments(logits.data_ptr(), ws.n_img * K, HW, HW, 1, int(self.covar), None, mu.data_ptr(),
-                                                    cov.data_ptr(), ws.dsnt_ws.data_ptr(), st), "cub200_dsnt_moments")
+                                                    cov.data_ptr(), ws.dsnt_ws.data_ptr() if persistent else None, st), "cub200_dsnt_moments")
 
     @staticmethod
     def _check_moments(ws: Workspace, mu: torch.Tensor, cov: torch.Tensor):
@@ -1368,7 +1371,9 @@ class GraphedStep:
         else:
             nxt, (mu_c, cov_c), (mu_n, cov_n) = self.prefetch
             self.ahead.wait_stream(self.stream)                                       # fork: the next batch's DSNT pass
-            self.engine.dsnt_into(self.ws, nxt, mu_n, cov_n, stream=self.ahead)
+            # one CTA per heatmap, not the persistent equal-range launch: that one assumes it owns every SM, and beside the
+            # tail's kernels a third of its CTAs would start late (0.4325 vs 0.4230 ms per step)
+            self.engine.dsnt_into(self.ws, nxt, mu_n, cov_n, stream=self.ahead, persistent=False)
             self.engine.run_tail_into(self.ws, mu_c, cov_c, seed=self.seed, stream=self.stream, step_dev=self.step,
                                       after_raster=fork_pack)
             self.stream.wait_stream(self.ahead)                                       # join

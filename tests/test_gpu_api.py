@@ -500,9 +500,15 @@ def test_pipelined_graphed_steps_match_eager_steps():
     for i in range(7):
         b = i % P
         gs[b].replay()
-        eng.run_into(ws_e, pool[b], seed=5, sample_offset=i * n * T)
+        # the eager step, with the prefetch branch's launch shape of the DSNT pass (one CTA per heatmap) for batches the graphs
+        # prefetched; the persistent launch agrees with it to fp32 rounding (checked below)
+        eng.dsnt_into(ws_e, pool[b], ws_e.mu, ws_e.cov, persistent=(i == 0))
+        eng.run_tail_into(ws_e, ws_e.mu, ws_e.cov, seed=5, sample_offset=i * n * T)
         torch.cuda.synchronize()
         assert torch.equal(moments[b % 2][0], ws_e.mu) and torch.equal(moments[b % 2][1], ws_e.cov)
+        mu_p, cov_p = torch.empty_like(ws_e.mu), torch.empty_like(ws_e.cov)
+        eng.dsnt_into(ws_e, pool[b], mu_p, cov_p)
+        assert float((mu_p - ws_e.mu).abs().max()) <= 1e-4 and float(((cov_p - ws_e.cov).abs() / (cov_p.abs() + 1e-2)).max()) <= 5e-5      # px, relative
         assert torch.equal(ws_g.contours, ws_e.contours) and torch.equal(ws_g.area, ws_e.area)
         assert torch.equal(ws_g.count, ws_e.count) and torch.equal(ws_g.entropy, ws_e.entropy)
     assert int(step.item()) == 7
