@@ -81,26 +81,43 @@ def kernel_search(P, coarse=COARSE, work=None):
     if n < 3:
         return best
 
-    def try_pair(i, j, wbest):
+    def near(i, j, k, l2):
+        a, b = P[j] - P[i], P[i] - P[k]
+        cr = int(a[0]) * int(b[1]) - int(a[1]) * int(b[0])
+        return cr * cr <= 256 * l2
+
+    def try_pairs(i, js):
+        """One warp-wide call: the candidates js (increasing) of the same i; per-candidate filter (angle, selectable, middle and
+        quarter points of the span), then validation longest first, first j among equals; the first valid one ends the call."""
         nonlocal best
-        a = P[j] - P[i]
-        if not (a[1] > 0 and abs(a[0]) <= a[1]):
-            return
-        c = (int(a @ a), int(i), int(j))
-        if c[0] < wbest or not _better(c, best):
-            return
-        work["validations"] += 1
-        if _valid(P, i, j, c[0]):
-            best = c
+        cands = []
+        for j in js:
+            a = P[j] - P[i]
+            if not (a[1] > 0 and abs(a[0]) <= a[1]):
+                continue
+            c = (int(a @ a), int(i), int(j))
+            if not _better(c, best):
+                continue
+            q = (i - j) >> 2
+            if near(i, j, (i + j) >> 1, c[0]) and (q == 0 or (near(i, j, j + q, c[0]) and near(i, j, i - q, c[0]))):
+                cands.append(c)
+        for c in sorted(cands, key=lambda c: (-c[0], c[2])):
+            work["validations"] += 1
+            if _valid(P, c[1], c[2], c[0]):
+                best = c
+                return
 
     for i in range((n - 1) // coarse * coarse, coarse - 1, -coarse):
-        w = best[0]
         work["coarse_i"] += 1
-        if chord_dead(P, i, n, chord_slim(w), -1):
+        if chord_dead(P, i, n, chord_slim(best[0]), -1):
             continue
-        work["coarse_iters"] += (len(range(0, i, coarse)) + 31) // 32
-        for j in range(0, i, coarse):
-            try_pair(i, j, w)
+        for j0 in range(0, i, 32 * coarse):
+            work["coarse_iters"] += 1
+            try_pairs(i, [j for j in range(j0, min(i, j0 + 32 * coarse), coarse)])
+    if best[0] > 0:                                        # refinement around the coarse chord
+        ci, cj = best[1], best[2]
+        for i in range(min(n - 1, ci + coarse - 1), max(2, ci - (coarse - 1)) - 1, -1):
+            try_pairs(i, [j for j in range(cj - 16, cj + 16) if 0 <= j < i])
     slim = chord_slim(best[0])
     dmin0 = max(1, int(np.ceil(np.sqrt(0.5 * best[0]) - 1e-9)))
     live_i = np.array([k >= 2 and not chord_dead(P, k, n, slim, -1) for k in range(n)])
@@ -121,15 +138,11 @@ def kernel_search(P, coarse=COARSE, work=None):
         if not any(block_ok(b, ir, ic, dmin0) for b in range((i + 31) >> 5)):
             continue
         work["full_i"] += 1
-        w = best[0]
-        dmin = max(1, int(np.ceil(np.sqrt(0.5 * w) - 1e-9)))
-        for b in range((i + 31) >> 5):
-            if not block_ok(b, ir, ic, dmin):
-                continue
+        dmin = max(1, int(np.ceil(np.sqrt(0.5 * best[0]) - 1e-9)))
+        blocks = [b for b in range((i + 31) >> 5) if block_ok(b, ir, ic, dmin)]     # one ballot per 32 blocks, then block by block
+        for b in blocks:
             work["live_blocks"] += 1
-            for j in range(32 * b, min(32 * b + 32, i)):
-                if live_j[j]:
-                    try_pair(i, j, w)
+            try_pairs(i, [j for j in range(32 * b, min(32 * b + 32, i)) if live_j[j]])
     return best
 
 
