@@ -105,10 +105,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm on the host cores: the VERBATIM reference (oracle/_ref, a git-ignored copy made by oracle/make_ref.py and run under
-# the import stubs of tests/golden/_refstub.py) for configs 1 and 2 when the copy is present, else -- and for configs 3-5 --
+# the import stubs of tests/golden/_refstub.py) for configs 1, 2, 3 and 5 when the copy is present, else -- and for config 4 --
 # the oracle port (numpy / scipy restatement of the reference).  `cpu_baseline.kind` says which.
 # ------------------------------------------------------------------------------------------------
-REF_CONFIGS = (1, 2)
+REF_CONFIGS = (1, 2, 3, 5)        # config 4's Simpson needs skimage.measure.find_contours (absent here): the port's restatement
 
 
 def _ref_kind(cfg):
@@ -153,6 +153,23 @@ def _cpu_worker(args):
         np.random.seed(seed); __import__("torch").manual_seed(seed)
         dt, _ = ref_runner.image_unit(logits, n_samples, "naive" if cfg == 1 else "psm", DEFAULT_PSM)
         return dt, n_samples
+    if cfg == 3 and getattr(_cpu_worker, "kind", "port") == "reference":
+        from oracle import ref_runner
+        from contouring_uncertainty_b200.engine import DEFAULT_PSM
+        logits = synth.heatmap_logits(1, seed=seed).astype(np.float32)
+        al = synth.skew_alphas(1, seed=seed + 1)
+        np.random.seed(seed); __import__("torch").manual_seed(seed)
+        dt, _ = ref_runner.skew_image_unit(logits, al[0], n_samples, DEFAULT_PSM)
+        return dt, n_samples
+    if cfg == 5 and getattr(_cpu_worker, "kind", "port") == "reference":
+        from oracle import ref_runner
+        from contouring_uncertainty_b200.engine import DEFAULT_PSM, DEFAULT_SEQ_PSM
+        mus, covs = synth.point_distributions(2, seed=seed)
+        ctr = mus[:1].mean(1, keepdims=True)
+        mus[1] = (ctr + (mus[:1] - ctr) * 0.8)[0]             # ES = ED shrunk about its centroid
+        np.random.seed(seed); __import__("torch").manual_seed(seed); __import__("random").seed(seed)
+        dt, _ = ref_runner.pair_unit(mus, covs, n_samples, DEFAULT_PSM, DEFAULT_SEQ_PSM)
+        return dt, 2 * n_samples
     if cfg in (1, 2):
         logits = synth.heatmap_logits(1, seed=seed)
         t0 = time.perf_counter()                              # the synthetic input is not part of the path
